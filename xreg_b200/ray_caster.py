@@ -1,0 +1,373 @@
+"""RayCasterLineIntCUDA: host-side mirror of xreg::RayCaster +
+RayCastLineIntParamInterface (lib/ray_cast/xregRayCastInterface.h:43-434,575-591)
+over the C ABI.  Same method names, argument meaning and error behaviour as the
+reference interface; every method forwards to libxreg_cuda.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+from .geometry import CameraModel, Volume, f32, to12
+
+
+class Context:
+    """One CUDA device + stream (replaces the OpenCL context/queue pair chosen by
+    --ocl-id, lib/common/xregProgOptUtils.cpp:1712-1725)."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        if stream is None:
+            check(self._lib.xrc_ctx_create(int(device), C.byref(h)))
+        else:
+            check(self._lib.xrc_ctx_create_on_stream(int(device), C.c_void_p(stream), C.byref(h)))
+        self.handle = h
+        self.device = int(device)
+
+    def synchronize(self) -> None:
+        check(self._lib.xrc_ctx_synchronize(self.handle))
+
+    @property
+    def stream(self) -> int:
+        s = C.c_void_p()
+        check(self._lib.xrc_ctx_stream(self.handle, C.byref(s)))
+        return int(s.value or 0)
+
+    def close(self) -> None:
+        if self.handle:
+            self._lib.xrc_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class RayCasterLineIntCUDA:
+    # RayCaster::InterpMethod / ProjPixelStoreMethod / RayCastLineIntKernel
+    kRAY_CAST_INTERP_LINEAR, kRAY_CAST_INTERP_NN, kRAY_CAST_INTERP_SINC, kRAY_CAST_INTERP_BSPLINE = 0, 1, 2, 3
+    kRAY_CAST_PIXEL_REPLACE, kRAY_CAST_PIXEL_ACCUM = 0, 1
+    kRAY_CAST_LINE_INT_SUM_KERNEL, kRAY_CAST_LINE_INT_MAX_KERNEL = 0, 1
+
+    def __init__(self, ctx: Context, layout: str = "default"):
+        self._lib = _lib.load()
+        self.ctx = ctx
+        h = C.c_void_p()
+        check(self._lib.xrc_rc_create(ctx.handle, C.byref(h)))
+        self.handle = h
+        check(self._lib.xrc_rc_set_layout(self.handle, _lib.LAYOUT_NAMES[layout]))
+        self._vols: List[Volume] = []
+        self._cams: List[CameraModel] = []
+        self._num_projs = 0
+        self._max_num_projs = 0
+        self._xforms: List[np.ndarray] = []          # xforms_cam_to_itk_phys_
+        self._cam_model_for_proj: List[int] = []     # cam_model_for_proj_
+        self._ray_step_size = 1.0                     # xregRayCastInterface.h:390
+        self._interp_method = self.kRAY_CAST_INTERP_LINEAR
+        self._proj_store_meth = self.kRAY_CAST_PIXEL_REPLACE
+        self._kernel_id = self.kRAY_CAST_LINE_INT_SUM_KERNEL
+        self._default_bg = 0.0
+        self._use_bg_projs = False
+        self._bg_projs: List[np.ndarray] = []
+        self._poses_dirty = True
+        self._params_dirty = True
+        self._resources_allocated = False
+
+    # ---- volumes / cameras -------------------------------------------------
+    def set_volume(self, vol: Volume) -> None:
+        self.set_volumes([vol])
+
+    def set_volumes(self, vols: Sequence[Volume]) -> None:
+        self._vols = list(vols)
+        self.vols_changed()
+
+    def num_vols(self) -> int:
+        return len(self._vols)
+
+    def vols_changed(self) -> None:
+        n = len(self._vols)
+        ptrs = (C.POINTER(C.c_float) * n)(*[v.data.ctypes.data_as(C.POINTER(C.c_float)) for v in self._vols])
+        dims = ((C.c_uint64 * 3) * n)(*[(C.c_uint64 * 3)(*v.dims) for v in self._vols])
+        xf = ((C.c_float * 12) * n)(*[(C.c_float * 12)(*[float(t) for t in v.idx_to_phys()]) for v in self._vols])
+        check(self._lib.xrc_rc_set_volumes(self.handle, n, ptrs, dims, xf))
+
+    def set_camera_model(self, cam: CameraModel) -> None:
+        self.set_camera_models([cam])
+
+    def set_camera_models(self, cams: Sequence[CameraModel]) -> None:
+        self._cams = list(cams)
+        self.camera_models_changed()
+
+    def camera_models_changed(self) -> None:
+        arr = (_lib.XrcCam * len(self._cams))(*[c.to_xrc() for c in self._cams])
+        check(self._lib.xrc_rc_set_cameras(self.handle, len(self._cams), arr))
+
+    def num_camera_models(self) -> int:
+        return len(self._cams)
+
+    def camera_models(self) -> List[CameraModel]:
+        return self._cams
+
+    def camera_model(self, cam_idx: int = 0) -> CameraModel:
+        return self._cams[cam_idx]
+
+    # ---- projections / poses -----------------------------------------------
+    def set_num_projs(self, num_projs: int) -> None:
+        """xregRayCastInterface.cpp:131-139; capacity is fixed at allocate_resources()."""
+        if self._resources_allocated:
+            check(self._lib.xrc_rc_set_num_projs(self.handle, int(num_projs)))
+        self._num_projs = int(num_projs)
+        self._cam_model_for_proj = (self._cam_model_for_proj + [0] * num_projs)[:num_projs]
+        ident = np.eye(4, dtype=f32)
+        self._xforms = (self._xforms + [ident.copy() for _ in range(num_projs)])[:num_projs]
+        self._poses_dirty = True
+
+    def num_projs(self) -> int:
+        return self._num_projs
+
+    def max_num_projs(self) -> int:
+        return self._max_num_projs
+
+    def set_proj_cam_model(self, proj_idx: int, cam_idx: int) -> None:
+        self._cam_model_for_proj[proj_idx] = int(cam_idx)
+        self._poses_dirty = True
+
+    def camera_model_proj_associations(self) -> List[int]:
+        return self._cam_model_for_proj
+
+    def set_camera_model_proj_associations(self, assoc: Sequence[int]) -> None:
+        if len(assoc) != self._num_projs:
+            raise _lib.XregError("set_camera_model_proj_associations: size must equal num_projs")
+        self._cam_model_for_proj = [int(a) for a in assoc]
+        self._poses_dirty = True
+
+    def set_xforms_cam_to_itk_phys(self, xforms: Sequence[np.ndarray]) -> None:
+        if len(xforms) != self._num_projs:
+            raise _lib.XregError("set_xforms_cam_to_itk_phys: size must equal num_projs")
+        self._xforms = [np.asarray(x, dtype=f32).reshape(4, 4).copy() for x in xforms]
+        self._poses_dirty = True
+
+    def xforms_cam_to_itk_phys(self) -> List[np.ndarray]:
+        return self._xforms
+
+    def xform_cam_to_itk_phys(self, proj_idx: int) -> np.ndarray:
+        """Mutable reference like the C++ accessor; marks the pose list dirty."""
+        self._poses_dirty = True
+        return self._xforms[proj_idx]
+
+    def distribute_xforms_among_cam_models(self, xforms: Sequence[np.ndarray]) -> None:
+        """xregRayCastInterface.cpp:97-114: camera-major replication."""
+        n_passed, n_cams = len(xforms), self.num_camera_models()
+        if n_passed * n_cams != self._num_projs:
+            raise _lib.XregError("distribute_xforms_among_cam_models: n_xforms * n_cams must equal num_projs")
+        g = 0
+        for cam_idx in range(n_cams):
+            for p in range(n_passed):
+                self._xforms[g] = np.asarray(xforms[p], dtype=f32).reshape(4, 4).copy()
+                self._cam_model_for_proj[g] = cam_idx
+                g += 1
+        self._poses_dirty = True
+
+    def distribute_xform_among_cam_models(self, xform: np.ndarray) -> None:
+        self.distribute_xforms_among_cam_models([xform])
+
+    def post_multiply_all_xforms(self, post_xform: np.ndarray) -> None:
+        self._xforms = [(x @ np.asarray(post_xform, dtype=f32)).astype(f32) for x in self._xforms]
+        self._poses_dirty = True
+
+    def pre_multiply_all_xforms(self, pre_xform: np.ndarray) -> None:
+        self._xforms = [(np.asarray(pre_xform, dtype=f32) @ x).astype(f32) for x in self._xforms]
+        self._poses_dirty = True
+
+    # ---- parameters --------------------------------------------------------
+    def set_ray_step_size(self, step_size: float) -> None:
+        self._ray_step_size = float(step_size)
+        self._params_dirty = True
+
+    def ray_step_size(self) -> float:
+        return self._ray_step_size
+
+    def set_interp_method(self, m: int) -> None:
+        self._interp_method = int(m)
+        self._params_dirty = True
+
+    def interp_method(self) -> int:
+        return self._interp_method
+
+    def use_linear_interp(self) -> None:
+        self.set_interp_method(self.kRAY_CAST_INTERP_LINEAR)
+
+    def use_nn_interp(self) -> None:
+        self.set_interp_method(self.kRAY_CAST_INTERP_NN)
+
+    def use_sinc_interp(self) -> None:
+        self.set_interp_method(self.kRAY_CAST_INTERP_SINC)
+
+    def use_bspline_interp(self) -> None:
+        self.set_interp_method(self.kRAY_CAST_INTERP_BSPLINE)
+
+    def set_proj_store_method(self, m: int) -> None:
+        self._proj_store_meth = int(m)
+        self._params_dirty = True
+
+    def proj_store_method(self) -> int:
+        return self._proj_store_meth
+
+    def use_proj_store_replace_method(self) -> None:
+        self.set_proj_store_method(self.kRAY_CAST_PIXEL_REPLACE)
+
+    def use_proj_store_accum_method(self) -> None:
+        self.set_proj_store_method(self.kRAY_CAST_PIXEL_ACCUM)
+
+    def kernel_id(self) -> int:
+        return self._kernel_id
+
+    def set_kernel_id(self, k: int) -> None:
+        self._kernel_id = int(k)
+        self._params_dirty = True
+
+    def default_bg_pixel_val(self) -> float:
+        return self._default_bg
+
+    def set_default_bg_pixel_val(self, v: float) -> None:
+        self._default_bg = float(v)
+        self._params_dirty = True
+
+    def set_use_bg_projs(self, use: bool) -> None:
+        self._use_bg_projs = bool(use)
+        self._push_bg()
+
+    def use_bg_projs(self) -> bool:
+        return self._use_bg_projs
+
+    def set_bg_proj(self, proj: np.ndarray, use_bg_projs: bool = True) -> None:
+        self.set_bg_projs([proj], use_bg_projs)
+
+    def set_bg_projs(self, projs: Sequence[np.ndarray], use_bg_projs: bool = True) -> None:
+        self._bg_projs = [np.ascontiguousarray(p, dtype=f32) for p in projs]
+        self._use_bg_projs = bool(use_bg_projs)
+        self._push_bg(upload=True)
+
+    def _push_bg(self, upload: bool = False) -> None:
+        if self._use_bg_projs:
+            if len(self._bg_projs) != self.num_camera_models():
+                raise _lib.XregError("background projections: need one per camera model (xregRayCastBaseCPU.cpp:135)")
+            if upload:
+                arr = (C.POINTER(C.c_float) * len(self._bg_projs))(
+                    *[b.ctypes.data_as(C.POINTER(C.c_float)) for b in self._bg_projs])
+                check(self._lib.xrc_rc_set_bg_projs(self.handle, arr, 1))
+            else:
+                check(self._lib.xrc_rc_set_bg_projs(self.handle, None, 1))
+        else:
+            check(self._lib.xrc_rc_set_bg_projs(self.handle, None, 0))
+
+    def set_layout_order(self, order: int) -> None:
+        check(self._lib.xrc_rc_set_cta_order(self.handle, int(order)))
+
+    # ---- resources / compute -----------------------------------------------
+    def allocate_resources(self) -> None:
+        """RayCaster::allocate_resources (xregRayCastInterface.cpp:262-270): capacity = num_projs now."""
+        if self._num_projs <= 0:
+            raise _lib.XregError("allocate_resources: set_num_projs first")
+        check(self._lib.xrc_rc_allocate(self.handle, self._num_projs))
+        self._max_num_projs = self._num_projs
+        self._resources_allocated = True
+        self._poses_dirty = True
+        self._params_dirty = True
+
+    def max_num_projs_possible(self) -> int:
+        n = C.c_uint64()
+        check(self._lib.xrc_rc_max_projs_possible(self.handle, C.byref(n)))
+        return int(n.value)
+
+    def use_other_proj_buf(self, other: "RayCasterLineIntCUDA") -> None:
+        check(self._lib.xrc_rc_use_other_proj_buf(self.handle, other.handle))
+
+    def _flush(self) -> None:
+        if self._params_dirty:
+            check(self._lib.xrc_rc_set_params(self.handle, self._ray_step_size, self._interp_method, self._kernel_id,
+                                              self._proj_store_meth, self._default_bg))
+            self._params_dirty = False
+        if self._poses_dirty and self._num_projs:
+            poses = to12(np.stack(self._xforms[: self._num_projs]))
+            idx = np.asarray(self._cam_model_for_proj[: self._num_projs], dtype=np.uint32)
+            check(self._lib.xrc_rc_set_poses(self.handle, self._num_projs, poses.ctypes.data_as(C.POINTER(C.c_float)),
+                                             idx.ctypes.data_as(C.POINTER(C.c_uint32))))
+            self._poses_dirty = False
+
+    def set_poses_array(self, poses12: np.ndarray, cam_idx: Optional[np.ndarray] = None) -> None:
+        """Fast path used by the registration loop: (n, 12) float32 array straight to the ABI."""
+        poses12 = np.ascontiguousarray(poses12, dtype=f32).reshape(-1, 12)
+        n = poses12.shape[0]
+        if n != self._num_projs:
+            raise _lib.XregError("set_poses_array: pose count must equal num_projs")
+        ip = None
+        if cam_idx is not None:
+            cam_idx = np.ascontiguousarray(cam_idx, dtype=np.uint32)
+            ip = cam_idx.ctypes.data_as(C.POINTER(C.c_uint32))
+        check(self._lib.xrc_rc_set_poses(self.handle, n, poses12.ctypes.data_as(C.POINTER(C.c_float)), ip))
+        self._xforms = [np.vstack([p.reshape(3, 4), np.array([[0, 0, 0, 1]], dtype=f32)]) for p in poses12]
+        self._cam_model_for_proj = [0] * n if cam_idx is None else [int(c) for c in cam_idx]
+        self._poses_dirty = False
+
+    def compute(self, vol_idx: int = 0) -> None:
+        if not self._resources_allocated:
+            raise _lib.XregError("compute: resources not allocated (xregRayCastLineIntCPU.cpp:296)")
+        self._flush()
+        check(self._lib.xrc_rc_compute(self.handle, int(vol_idx)))
+
+    def proj(self, proj_idx: int) -> np.ndarray:
+        """Copy of projection proj_idx (the reference returns a view of the host buffer)."""
+        cam = self._cams[self._cam_model_for_proj[proj_idx] if proj_idx < len(self._cam_model_for_proj) else 0]
+        out = np.empty((cam.num_det_rows, cam.num_det_cols), dtype=f32)
+        check(self._lib.xrc_rc_read_projs(self.handle, int(proj_idx), 1, out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
+
+    proj_ocv = proj
+
+    def raw_host_pixel_buf(self) -> np.ndarray:
+        """All current projections, image-major then row-major (xregRayCastBaseCPU.h:149-154)."""
+        cam = self._cams[0]
+        out = np.empty((self._num_projs, cam.num_det_rows, cam.num_det_cols), dtype=f32)
+        if self._num_projs:
+            check(self._lib.xrc_rc_read_projs(self.handle, 0, self._num_projs, out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
+
+    def use_external_host_pixel_buf(self, buf) -> None:
+        raise _lib.UnsupportedOperationException(
+            "use_external_host_pixel_buf: projections live in device memory; use raw_host_pixel_buf()/proj()")
+
+    def device_buf(self) -> int:
+        p = C.c_void_p()
+        check(self._lib.xrc_rc_device_buf(self.handle, C.byref(p)))
+        return int(p.value)
+
+    def ray_info(self, vol_idx: int = 0):
+        """(clip mask, samples per ray, total samples S) for the current poses."""
+        self._flush()
+        cam = self._cams[0]
+        shape = (self._num_projs, cam.num_det_rows, cam.num_det_cols)
+        mask = np.zeros(shape, np.uint8)
+        steps = np.zeros(shape, np.uint32)
+        S = C.c_uint64()
+        check(self._lib.xrc_rc_ray_info(self.handle, int(vol_idx), mask.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                        steps.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(S)))
+        return mask, steps, int(S.value)
+
+    def close(self) -> None:
+        if self.handle:
+            self._lib.xrc_rc_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,352 @@
+"""ImgSimMetric2D*CUDA: host-side mirrors of xreg::ImgSimMetric2D and its NCC /
+Grad-NCC / Patch-NCC / Patch-Grad-NCC implementations
+(lib/regi/sim_metrics_2d/xregImgSimMetric2D.h:42-156 and the *CPU / *OCL classes)
+over the C ABI.  The patch-grid / weight logic of ImgSimMetric2DPatchCommon stays
+on the host exactly like in the reference and is handed down as arrays.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+from .geometry import f32
+from .ray_caster import Context, RayCasterLineIntCUDA
+
+
+class ImgSimMetric2D:
+    """Common part of the interface (xregImgSimMetric2D.h:42-156)."""
+
+    KIND = _lib.SM_NCC
+
+    def __init__(self, ctx: Context):
+        self._lib = _lib.load()
+        self.ctx = ctx
+        h = C.c_void_p()
+        check(self._lib.xrc_sm_create(ctx.handle, self.KIND, C.byref(h)))
+        self.handle = h
+        self._fixed: Optional[np.ndarray] = None
+        self._mask: Optional[np.ndarray] = None
+        self._num_mov_imgs = 0
+        self._sim_vals = np.zeros(0, dtype=f32)
+        self._allocated = False
+        self._rc: Optional[RayCasterLineIntCUDA] = None
+        self._host_buf: Optional[np.ndarray] = None
+
+    # -- set-up ---------------------------------------------------------------
+    def set_fixed_image(self, fixed_img: np.ndarray) -> None:
+        self._fixed = np.ascontiguousarray(fixed_img, dtype=f32)
+        r, c = self._fixed.shape
+        check(self._lib.xrc_sm_set_fixed(self.handle, self._fixed.ctypes.data_as(C.POINTER(C.c_float)), r, c))
+
+    def fixed_image(self) -> Optional[np.ndarray]:
+        return self._fixed
+
+    def set_num_moving_images(self, n: int) -> None:
+        self._num_mov_imgs = int(n)
+        if self._allocated:
+            check(self._lib.xrc_sm_set_num_imgs(self.handle, int(n)))
+            self._sim_vals = np.zeros(int(n), dtype=f32)
+
+    def num_moving_images(self) -> int:
+        return self._num_mov_imgs
+
+    def set_mov_imgs_buf_from_ray_caster(self, ray_caster: RayCasterLineIntCUDA, proj_offset: int = 0) -> None:
+        check(self._lib.xrc_sm_bind_ray_caster(self.handle, ray_caster.handle, int(proj_offset)))
+        self._rc = ray_caster
+        self._host_buf = None
+
+    def set_mov_imgs_host_buf(self, mov_imgs_buf: np.ndarray, proj_offset: int = 0) -> None:
+        if mov_imgs_buf.dtype != f32 or not mov_imgs_buf.flags.c_contiguous:
+            raise _lib.XregError("set_mov_imgs_host_buf: need a C-contiguous float32 buffer")
+        self._host_buf = mov_imgs_buf  # caller-owned, must outlive the metric (as in the reference)
+        check(self._lib.xrc_sm_bind_host(self.handle, mov_imgs_buf.ctypes.data_as(C.POINTER(C.c_float)), int(proj_offset)))
+        self._rc = None
+
+    def set_mov_imgs_device_buf(self, dev_ptr: int, proj_offset: int = 0) -> None:
+        check(self._lib.xrc_sm_bind_device(self.handle, C.c_void_p(dev_ptr), int(proj_offset)))
+        self._rc = None
+        self._host_buf = None
+
+    def set_mask(self, mask: Optional[np.ndarray]) -> None:
+        if mask is None:
+            self._mask = None
+            check(self._lib.xrc_sm_set_mask(self.handle, None))
+        else:
+            self._mask = np.ascontiguousarray(mask, dtype=np.uint8)
+            if self._fixed is None or self._mask.shape != self._fixed.shape:
+                raise _lib.XregError("set_mask: mask must match the fixed image")
+            check(self._lib.xrc_sm_set_mask(self.handle, self._mask.ctypes.data_as(C.POINTER(C.c_uint8))))
+        self._mask_changed()
+
+    def mask(self) -> Optional[np.ndarray]:
+        return self._mask
+
+    def _mask_changed(self) -> None:
+        pass
+
+    def _pre_allocate(self) -> None:
+        pass
+
+    def allocate_resources(self) -> None:
+        if self._num_mov_imgs <= 0:
+            raise _lib.XregError("allocate_resources: set_num_moving_images first")
+        self._pre_allocate()
+        check(self._lib.xrc_sm_allocate(self.handle, self._num_mov_imgs))
+        self._sim_vals = np.zeros(self._num_mov_imgs, dtype=f32)
+        self._allocated = True
+
+    # -- compute --------------------------------------------------------------
+    def compute(self) -> None:
+        """Blocking like the reference: similarity values are valid on return."""
+        if not self._allocated:
+            raise _lib.XregError("compute: resources not allocated")
+        check(self._lib.xrc_sm_compute(self.handle))
+        if self._num_mov_imgs:
+            check(self._lib.xrc_sm_read_sims(self.handle, self._sim_vals.ctypes.data_as(C.POINTER(C.c_float)),
+                                             self._num_mov_imgs))
+
+    def compute_async(self) -> None:
+        check(self._lib.xrc_sm_compute(self.handle))
+
+    def sim_val(self, mov_img_idx: int) -> float:
+        return float(self._sim_vals[mov_img_idx])
+
+    def sim_vals(self) -> np.ndarray:
+        return self._sim_vals
+
+    def device_sims(self) -> int:
+        p = C.c_void_p()
+        check(self._lib.xrc_sm_device_sims(self.handle, C.byref(p)))
+        return int(p.value)
+
+    def close(self) -> None:
+        if self.handle:
+            self._lib.xrc_sm_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ImgSimMetric2DGradImgParamInterface:
+    """xregImgSimMetric2DGradImgParamInterface.h:31-39 ("radius" is the kernel width)."""
+
+    _smooth_img_kernel_rad = 5
+
+    def smooth_img_before_sobel_kernel_radius(self) -> int:
+        return self._smooth_img_kernel_rad
+
+    def set_smooth_img_before_sobel_kernel_radius(self, r: int) -> None:
+        self._smooth_img_kernel_rad = int(r)
+        check(self._lib.xrc_sm_set_grad_params(self.handle, int(r)))
+
+    def read_grads(self, img: int):
+        r, c = self._fixed.shape
+        gx = np.empty((r, c), dtype=f32)
+        gy = np.empty((r, c), dtype=f32)
+        check(self._lib.xrc_sm_read_grads(self.handle, int(img), gx.ctypes.data_as(C.POINTER(C.c_float)),
+                                          gy.ctypes.data_as(C.POINTER(C.c_float))))
+        return gx, gy
+
+
+class ImgSimMetric2DPatchCommon:
+    """Patch grid / weights / options (xregImgSimMetric2DPatchCommon.{h,cpp})."""
+
+    def _init_patch_common(self) -> None:
+        self._patch_radius = 5
+        self._patch_stride = 1
+        self._compute_mean_of_patch_sims = False
+        self._weight_patch_sims_in_combine = True
+        self._use_mask_for_weighting = True
+        self._use_mask_for_patch_stats = False
+        self._normalize_weights_as_prob = True
+        self._wgt_img: Optional[np.ndarray] = None
+        self._weights: Optional[np.ndarray] = None
+
+    def patch_radius(self) -> int:
+        return self._patch_radius
+
+    def set_patch_radius(self, r: int) -> None:
+        self._patch_radius = int(r)
+
+    def patch_stride(self) -> int:
+        return self._patch_stride
+
+    def set_patch_stride(self, s: int) -> None:
+        self._patch_stride = int(s)
+
+    def set_compute_mean_of_patch_sims(self, b: bool) -> None:
+        self._compute_mean_of_patch_sims = bool(b)
+
+    def compute_mean_of_patch_sims(self) -> bool:
+        return self._compute_mean_of_patch_sims
+
+    def set_weight_patch_sims_in_combine(self, b: bool) -> None:
+        self._weight_patch_sims_in_combine = bool(b)
+
+    def weight_patch_sims_in_combine(self) -> bool:
+        return self._weight_patch_sims_in_combine
+
+    def set_use_mask_for_patch_weighting(self, b: bool) -> None:
+        self._use_mask_for_weighting = bool(b)
+
+    def use_mask_for_patch_weighting(self) -> bool:
+        return self._use_mask_for_weighting
+
+    def set_use_mask_for_patch_stats(self, b: bool) -> None:
+        self._use_mask_for_patch_stats = bool(b)
+
+    def use_mask_for_patch_stats(self) -> bool:
+        return self._use_mask_for_patch_stats
+
+    def set_normalize_weights_as_prob(self, b: bool) -> None:
+        self._normalize_weights_as_prob = bool(b)
+
+    def normalize_weights_as_prob(self) -> bool:
+        return self._normalize_weights_as_prob
+
+    def set_choose_rand_patches(self, b: bool) -> None:
+        if b:
+            raise _lib.UnsupportedOperationException("random patch subsets are not supported by the CUDA metrics")
+
+    def set_wgt_img(self, wgt_img: Optional[np.ndarray]) -> None:
+        self._wgt_img = None if wgt_img is None else np.ascontiguousarray(wgt_img, dtype=f32)
+        if self._allocated:
+            self._push_patch_params()
+
+    def num_patches(self) -> int:
+        r, s = self._patch_radius, self._patch_stride
+        rows, cols = self._fixed.shape
+        return ((rows - 1 - 2 * r) // s + 1) * ((cols - 1 - 2 * r) // s + 1)
+
+    def compute_weights(self) -> Optional[np.ndarray]:
+        """ImgSimMetric2DPatchCommon::compute_weights (xregImgSimMetric2DPatchCommon.cpp:309-410).
+        Returns None when every weight stays 1."""
+        mask = self._mask
+        use_mask_wgts = self._use_mask_for_weighting and mask is not None
+        if self._wgt_img is None and not use_mask_wgts:
+            return None
+        r, s = self._patch_radius, self._patch_stride
+        rows, cols = self._fixed.shape
+        cr = np.arange(r, rows - r, s)
+        cc = np.arange(r, cols - r, s)
+        if self._wgt_img is not None:
+            w = self._wgt_img[np.ix_(cr, cc)].astype(f32)
+            if use_mask_wgts:
+                w = np.where(mask[np.ix_(cr, cc)] != 0, w, f32(0)).astype(f32)
+        else:
+            d = 2 * r + 1
+            ii = np.zeros((rows + 1, cols + 1), dtype=np.int64)
+            ii[1:, 1:] = np.cumsum(np.cumsum((mask != 0).astype(np.int64), axis=0), axis=1)
+            r0, c0 = cr - r, cc - r
+            cnt = (ii[np.ix_(r0 + d, c0 + d)] - ii[np.ix_(r0, c0 + d)] - ii[np.ix_(r0 + d, c0)] + ii[np.ix_(r0, c0)])
+            w = (cnt.astype(f32) / f32(d * d)).astype(f32)
+        w = np.ascontiguousarray(w.reshape(-1), dtype=f32)
+        if self._normalize_weights_as_prob:
+            ws = np.cumsum(w, dtype=f32)[-1]  # sequential f32 sum, as the reference's loop
+            w = (w / ws).astype(f32)
+        return w
+
+    def _push_patch_params(self) -> None:
+        self._weights = self.compute_weights()
+        wp, n = None, 0
+        if self._weights is not None:
+            wp, n = self._weights.ctypes.data_as(C.POINTER(C.c_float)), self._weights.size
+        check(self._lib.xrc_sm_set_patch_params(self.handle, self._patch_radius, self._patch_stride,
+                                                int(self._compute_mean_of_patch_sims),
+                                                int(self._weight_patch_sims_in_combine),
+                                                int(self._use_mask_for_patch_stats), wp, n))
+
+
+class ImgSimMetric2DNCCCUDA(ImgSimMetric2D):
+    """Replaces ImgSimMetric2DNCCOCL / mirrors ImgSimMetric2DNCCCPU (xregImgSimMetric2DNCCCPU.cpp).
+    Unlike the CPU class the moving-image buffer is left untouched (the CPU class
+    overwrites it with zero-mean images, xregImgSimMetric2DNCCCPU.h:36)."""
+
+    KIND = _lib.SM_NCC
+
+
+class ImgSimMetric2DGradNCCCUDA(ImgSimMetric2D, ImgSimMetric2DGradImgParamInterface):
+    """ImgSimMetric2DGradNCCCPU (xregImgSimMetric2DGradNCCCPU.cpp:29-65)."""
+
+    KIND = _lib.SM_GRAD_NCC
+
+
+class ImgSimMetric2DPatchNCCCUDA(ImgSimMetric2D, ImgSimMetric2DPatchCommon):
+    """ImgSimMetric2DPatchNCCCPU (xregImgSimMetric2DPatchNCCCPU.cpp)."""
+
+    KIND = _lib.SM_PATCH_NCC
+
+    def __init__(self, ctx: Context):
+        ImgSimMetric2D.__init__(self, ctx)
+        self._init_patch_common()
+
+    def _pre_allocate(self) -> None:
+        self._push_patch_params()
+
+    def _mask_changed(self) -> None:
+        if self._allocated:
+            self._push_patch_params()
+
+
+class ImgSimMetric2DPatchGradNCCCUDA(ImgSimMetric2D, ImgSimMetric2DPatchCommon, ImgSimMetric2DGradImgParamInterface):
+    """ImgSimMetric2DPatchGradNCCCPU (xregImgSimMetric2DPatchGradNCCCPU.cpp:34-253)."""
+
+    KIND = _lib.SM_PATCH_GRAD_NCC
+
+    def __init__(self, ctx: Context):
+        ImgSimMetric2D.__init__(self, ctx)
+        self._init_patch_common()
+
+    def _pre_allocate(self) -> None:
+        self._push_patch_params()
+
+    def _mask_changed(self) -> None:
+        if self._allocated:
+            self._push_patch_params()
+
+
+class ImgSimMetric2DCombineMean:
+    """ImgSimMetric2DCombineMean (xregImgSimMetric2DCombine.cpp:67-86): host mean over views."""
+
+    def __init__(self):
+        self._sims: List[ImgSimMetric2D] = []
+        self._sim_vals = np.zeros(0, dtype=f32)
+
+    def set_sim_metrics(self, sims: Sequence[ImgSimMetric2D]) -> None:
+        self._sims = list(sims)
+
+    def compute(self) -> None:
+        n = self._sims[0].num_moving_images()
+        acc = np.zeros(n, dtype=f32)
+        for s in self._sims:
+            acc = (acc + s.sim_vals()[:n]).astype(f32)
+        self._sim_vals = (acc / f32(len(self._sims))).astype(f32)
+
+    def sim_vals(self) -> np.ndarray:
+        return self._sim_vals
+
+    def sim_val(self, i: int) -> float:
+        return float(self._sim_vals[i])
+
+
+def eval_batch(rc: RayCasterLineIntCUDA, sims: Sequence[ImgSimMetric2D], n_per_view: int, vol_idx: int = 0) -> np.ndarray:
+    """One obj_fn evaluation (xregIntensity2D3DRegi.cpp:571-696): DRRs for all views,
+    every view's metric, one gather.  Returns (n_views, n_per_view) float32."""
+    lib = _lib.load()
+    rc._flush()
+    n_views = len(sims)
+    arr = (C.c_void_p * n_views)(*[s.handle for s in sims])
+    out = np.zeros((n_views, n_per_view), dtype=f32)
+    check(lib.xrc_eval_batch(rc.handle, int(vol_idx), arr, n_views, int(n_per_view),
+                             out.ctypes.data_as(C.POINTER(C.c_float))))
+    for v, s in enumerate(sims):
+        s._sim_vals[:n_per_view] = out[v]
+    return out
