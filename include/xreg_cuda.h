@@ -134,6 +134,12 @@ int xrc_rc_set_poses(xrc_rc* rc, uint32_t n, const float* cam_to_phys, const uin
 /* RayCaster::distribute_xforms_among_cam_models (xregRayCastInterface.cpp:97-114):
  * n_poses * n_cams must equal num_projs; camera-major replication. */
 int xrc_rc_distribute_poses(xrc_rc* rc, uint32_t n_poses, const float* cam_to_phys);
+/* Poses that already live on the device (e.g. written by a GPU-resident optimiser, or
+ * a torch tensor): the ray caster reads dev_cam_to_phys (n x 12 floats) and dev_cam_idx
+ * (n x uint32, NULL = camera 0 for all) in place at every compute() until the next
+ * xrc_rc_set_poses / xrc_rc_distribute_poses call.  No copy, no synchronisation. */
+int xrc_rc_set_poses_device(xrc_rc* rc, uint32_t n, const float* dev_cam_to_phys,
+                            const uint32_t* dev_cam_idx);
 
 /* set_ray_step_size / set_interp_method / RayCastLineIntParamInterface::set_kernel_id /
  * set_proj_store_method / set_default_bg_pixel_val (xregRayCastInterface.h:140-350,581-591) */

@@ -1,0 +1,236 @@
+"""GPU parity of ImgSimMetric2D{NCC,GradNCC,PatchNCC,PatchGradNCC}CUDA against the CPU oracle:
+similarity values within 1e-5 absolute, gradient images bit-exact."""
+import numpy as np
+import pytest
+
+import xreg_b200
+from xreg_b200 import synth
+from xreg_b200.geometry import to12
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+SIM_TOL = 1.0e-5  # BASELINE.json north_star: similarity values within 1e-5 absolute
+
+
+def _img(rows, cols, seed, smooth=True):
+    rng = np.random.default_rng(seed)
+    a = rng.standard_normal((rows, cols))
+    if smooth:
+        k = np.ones(5) / 5
+        a = np.apply_along_axis(lambda v: np.convolve(v, k, mode="same"), 0, a)
+        a = np.apply_along_axis(lambda v: np.convolve(v, k, mode="same"), 1, a)
+    return (a * 3 + 5).astype(f32)
+
+
+def _movs(fixed, n, seed):
+    out = [(_img(*fixed.shape, seed + i) * (0.2 + 0.1 * i) + (1.0 - 0.1 * i) * fixed).astype(f32) for i in range(n)]
+    out[-1] = np.full_like(fixed, 2.5)  # constant image: sigma clamp path
+    return np.ascontiguousarray(np.stack(out))
+
+
+def _run(sm, fixed, mov, mask=None):
+    sm.set_num_moving_images(mov.shape[0])
+    sm.set_fixed_image(fixed)
+    sm.set_mov_imgs_host_buf(mov)
+    if mask is not None:
+        sm.set_mask(mask)
+    sm.allocate_resources()
+    sm.compute()
+    return sm.sim_vals().copy()
+
+
+SHAPES = [(61, 73), (32, 32), (100, 37), (7, 9)]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("masked", [False, True])
+def test_ncc(ctx, xo, shape, masked):
+    fixed = _img(*shape, seed=1)
+    mov = _movs(fixed, 5, seed=10)
+    mask = (np.random.default_rng(2).random(shape) > 0.3).astype(np.uint8) if masked else None
+    got = _run(xreg_b200.ImgSimMetric2DNCCCUDA(ctx), fixed, mov, mask)
+    ref = xo.ncc(fixed, mov, mask=mask)
+    assert np.max(np.abs(got - ref)) <= SIM_TOL
+    assert abs(got[-1] - 0.5) < 1e-6
+
+
+@pytest.mark.parametrize("shape", SHAPES + [(64, 96), (3, 40)])
+@pytest.mark.parametrize("width", [0, 3, 5, 7, 9])
+def test_gradient_images_bit_exact(ctx, xo, shape, width):
+    fixed = _img(*shape, seed=3, smooth=False)
+    mov = _movs(fixed, 3, seed=20)
+    sm = xreg_b200.ImgSimMetric2DGradNCCCUDA(ctx)
+    sm.set_smooth_img_before_sobel_kernel_radius(width)
+    _run(sm, fixed, mov)
+    for i in range(3):
+        gx, gy = sm.read_grads(i)
+        rx, ry = xo.grad_imgs(mov[i], width)
+        np.testing.assert_array_equal(gx, rx)
+        np.testing.assert_array_equal(gy, ry)
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("masked", [False, True])
+def test_grad_ncc(ctx, xo, shape, masked):
+    fixed = _img(*shape, seed=4)
+    mov = _movs(fixed, 4, seed=30)
+    mask = (np.random.default_rng(5).random(shape) > 0.25).astype(np.uint8) if masked else None
+    sm = xreg_b200.ImgSimMetric2DGradNCCCUDA(ctx)
+    got = _run(sm, fixed, mov, mask)
+    ref = xo.grad_ncc(fixed, mov, mask=mask, gauss_width=5)
+    assert np.max(np.abs(got - ref)) <= SIM_TOL
+    sm0 = xreg_b200.ImgSimMetric2DGradNCCCUDA(ctx)
+    sm0.set_smooth_img_before_sobel_kernel_radius(0)
+    got0 = _run(sm0, fixed, mov, mask)
+    assert np.max(np.abs(got0 - xo.grad_ncc(fixed, mov, mask=mask, gauss_width=0))) <= SIM_TOL
+
+
+@pytest.mark.parametrize("shape,radius,stride", [((61, 73), 5, 1), ((40, 300), 10, 1), ((33, 35), 3, 2),
+                                                 ((11, 11), 5, 1), ((64, 64), 13, 3), ((50, 520), 21, 1)])
+def test_patch_ncc(ctx, xo, shape, radius, stride):
+    fixed = _img(*shape, seed=6)
+    mov = _movs(fixed, 3, seed=40)
+    sm = xreg_b200.ImgSimMetric2DPatchNCCCUDA(ctx)
+    sm.set_patch_radius(radius)
+    sm.set_patch_stride(stride)
+    got = _run(sm, fixed, mov)
+    ref = xo.patch_ncc(fixed, mov, xo.patch_opts(radius=radius, stride=stride))
+    assert np.max(np.abs(got - ref)) <= SIM_TOL
+    assert abs(got[-1] - 1.0) < 1e-6
+    assert sm.num_patches() == xo.num_patches(shape[0], shape[1], radius, stride)
+
+
+@pytest.mark.parametrize("mode", ["mean", "unweighted", "mask", "mask_stats", "wgt_img"])
+def test_patch_ncc_options(ctx, xo, mode):
+    shape = (45, 52)
+    fixed = _img(*shape, seed=7)
+    mov = _movs(fixed, 3, seed=50)
+    mask = np.zeros(shape, np.uint8)
+    mask[5:40, 8:45] = 1
+    mask[20:24, 20:30] = 0
+    sm = xreg_b200.ImgSimMetric2DPatchNCCCUDA(ctx)
+    sm.set_patch_radius(4)
+    o = xo.patch_opts(radius=4)
+    use_mask, wgt_img = None, None
+    if mode == "mean":
+        sm.set_compute_mean_of_patch_sims(True)
+        o.compute_mean_of_patch_sims = 1
+    elif mode == "unweighted":
+        sm.set_weight_patch_sims_in_combine(False)
+        o.weight_patch_sims = 0
+    elif mode == "mask":
+        use_mask = mask
+    elif mode == "mask_stats":
+        use_mask = mask
+        sm.set_use_mask_for_patch_stats(True)
+        o.use_mask_for_patch_stats = 1
+    elif mode == "wgt_img":
+        wgt_img = np.random.default_rng(8).random(shape).astype(f32)
+        sm.set_wgt_img(wgt_img)
+    got = _run(sm, fixed, mov, use_mask)
+    w = xo.patch_weights(shape[0], shape[1], o, mask=use_mask, wgt_img=wgt_img) if (use_mask is not None or wgt_img is not None) else None
+    ref = xo.patch_ncc(fixed, mov, o, mask=use_mask, weights=w)
+    tol = SIM_TOL if mode != "unweighted" else SIM_TOL * ref.max()
+    assert np.max(np.abs(got - ref)) <= tol
+
+
+@pytest.mark.parametrize("shape,radius", [((61, 73), 5), ((96, 96), 10), ((48, 300), 13)])
+@pytest.mark.parametrize("masked", [False, True])
+def test_patch_grad_ncc(ctx, xo, shape, radius, masked):
+    fixed = _img(*shape, seed=9)
+    mov = _movs(fixed, 3, seed=60)
+    mask = synth.circular_mask(*shape) if masked else None
+    sm = xreg_b200.ImgSimMetric2DPatchGradNCCCUDA(ctx)
+    sm.set_patch_radius(radius)
+    got = _run(sm, fixed, mov, mask)
+    o = xo.patch_opts(radius=radius)
+    w = xo.patch_weights(shape[0], shape[1], o, mask=mask) if masked else None
+    ref = xo.patch_grad_ncc(fixed, mov, o, mask=mask, weights=w, gauss_width=5)
+    assert np.max(np.abs(got - ref)) <= SIM_TOL
+
+
+def test_patch_grad_ncc_on_drrs_with_flat_regions(ctx, xo, small_scene):
+    """DRRs have exactly-zero background: the sigma clamp / zero-variance patches must agree."""
+    vol, cam, nominal = small_scene
+    poses = synth.pose_population(vol, nominal, 4)
+    rc = xreg_b200.RayCasterLineIntCUDA(ctx)
+    rc.set_volume(vol)
+    rc.set_camera_model(cam)
+    rc.set_num_projs(4)
+    rc.allocate_resources()
+    rc.set_xforms_cam_to_itk_phys(list(poses))
+    rc.compute()
+    drrs = rc.raw_host_pixel_buf()
+    fixed = synth.add_noise(drrs[0])
+    for cls, fn in ((xreg_b200.ImgSimMetric2DPatchGradNCCCUDA, lambda: xo.patch_grad_ncc(fixed, drrs, xo.patch_opts(radius=5))),
+                    (xreg_b200.ImgSimMetric2DGradNCCCUDA, lambda: xo.grad_ncc(fixed, drrs)),
+                    (xreg_b200.ImgSimMetric2DNCCCUDA, lambda: xo.ncc(fixed, drrs)),
+                    (xreg_b200.ImgSimMetric2DPatchNCCCUDA, lambda: xo.patch_ncc(fixed, drrs, xo.patch_opts(radius=5)))):
+        sm = cls(ctx)
+        sm.set_num_moving_images(4)
+        sm.set_fixed_image(fixed)
+        sm.set_mov_imgs_buf_from_ray_caster(rc)
+        sm.allocate_resources()
+        sm.compute()
+        assert np.max(np.abs(sm.sim_vals() - fn())) <= SIM_TOL, cls.__name__
+        assert int(np.argmin(sm.sim_vals())) == 0
+
+
+def test_rebinding_offsets_num_images_and_mask_update(ctx, xo):
+    fixed = _img(40, 44, seed=11)
+    mov = _movs(fixed, 6, seed=70)
+    sm = xreg_b200.ImgSimMetric2DGradNCCCUDA(ctx)
+    sm.set_num_moving_images(6)
+    sm.set_fixed_image(fixed)
+    sm.set_mov_imgs_host_buf(mov)
+    sm.allocate_resources()
+    sm.compute()
+    full = sm.sim_vals().copy()
+    # fewer images at an offset (xregImgSimMetric2DCPU.cpp:59-65)
+    sm.set_num_moving_images(2)
+    sm.set_mov_imgs_host_buf(mov, 3)
+    sm.compute()
+    np.testing.assert_array_equal(sm.sim_vals(), full[3:5])
+    with pytest.raises(xreg_b200.XregError):
+        sm.set_num_moving_images(7)
+    # mask set after allocation is picked up lazily (process_updated_mask)
+    mask = synth.circular_mask(40, 44)
+    sm.set_mask(mask)
+    sm.set_num_moving_images(6)
+    sm.set_mov_imgs_host_buf(mov, 0)
+    sm.compute()
+    assert np.max(np.abs(sm.sim_vals() - xo.grad_ncc(fixed, mov, mask=mask))) <= SIM_TOL
+    sm.set_mask(None)
+    sm.compute()
+    np.testing.assert_array_equal(sm.sim_vals(), full)
+
+
+def test_metric_errors(ctx):
+    sm = xreg_b200.ImgSimMetric2DPatchGradNCCCUDA(ctx)
+    with pytest.raises(xreg_b200.XregError):
+        sm.compute()
+    sm.set_num_moving_images(1)
+    sm.set_fixed_image(_img(8, 8, 0))
+    with pytest.raises(xreg_b200.XregError):
+        sm.allocate_resources()  # nothing bound
+    sm.set_mov_imgs_host_buf(_movs(_img(8, 8, 0), 1, 1))
+    sm.set_patch_radius(5)
+    with pytest.raises(xreg_b200.XregError):
+        sm.allocate_resources()  # patch diameter 11 > 8 (xregImgSimMetric2DPatchCommon.cpp:272-273)
+    with pytest.raises(xreg_b200.XregError):
+        sm.set_smooth_img_before_sobel_kernel_radius(4)  # width must be odd
+    with pytest.raises(xreg_b200.UnsupportedOperationException):
+        sm.set_choose_rand_patches(True)
+
+
+def test_combine_mean(ctx, xo):
+    fixed = _img(30, 30, seed=12)
+    mov = _movs(fixed, 4, seed=80)
+    a = xreg_b200.ImgSimMetric2DNCCCUDA(ctx)
+    b = xreg_b200.ImgSimMetric2DGradNCCCUDA(ctx)
+    _run(a, fixed, mov)
+    _run(b, fixed, mov)
+    comb = xreg_b200.ImgSimMetric2DCombineMean()
+    comb.set_sim_metrics([a, b])
+    comb.compute()
+    np.testing.assert_allclose(comb.sim_vals(), xo.combine_mean(np.stack([a.sim_vals(), b.sim_vals()])), rtol=1e-6)

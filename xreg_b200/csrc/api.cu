@@ -116,6 +116,9 @@ struct xrc_rc
   uint32_t* h_cam_idx = nullptr;
   float* d_poses = nullptr;
   uint32_t* d_cam_idx = nullptr;
+  uint32_t* d_zero_idx = nullptr;      // all-zero camera indices
+  const float* ext_poses = nullptr;    // caller-owned device poses (xrc_rc_set_poses_device)
+  const uint32_t* ext_cam_idx = nullptr;
   cudaEvent_t staged = nullptr;
   bool staged_pending = false;
   float step_size = 1.0f;
@@ -294,6 +297,7 @@ int xrc_rc_destroy(xrc_rc* rc)
   dfree(rc->d_buf_own);
   dfree(rc->d_poses);
   dfree(rc->d_cam_idx);
+  dfree(rc->d_zero_idx);
   dfree(rc->d_bg);
   if (rc->h_poses)
     cudaFreeHost(rc->h_poses);
@@ -403,6 +407,9 @@ int xrc_rc_allocate(xrc_rc* rc, uint32_t max_projs)
   dfree(rc->d_buf_own);
   dfree(rc->d_poses);
   dfree(rc->d_cam_idx);
+  dfree(rc->d_zero_idx);
+  rc->ext_poses = nullptr;
+  rc->ext_cam_idx = nullptr;
   if (rc->h_poses)
     cudaFreeHost(rc->h_poses);
   if (rc->h_cam_idx)
@@ -426,6 +433,8 @@ int xrc_rc_allocate(xrc_rc* rc, uint32_t max_projs)
   XRC_CUDA(cudaMalloc(&rc->d_poses, sizeof(float) * 12 * max_projs));
   XRC_CUDA(cudaMalloc(&rc->d_cam_idx, sizeof(uint32_t) * max_projs));
   XRC_CUDA(cudaMemsetAsync(rc->d_cam_idx, 0, sizeof(uint32_t) * max_projs, rc->ctx->stream));
+  XRC_CUDA(cudaMalloc(&rc->d_zero_idx, sizeof(uint32_t) * max_projs));
+  XRC_CUDA(cudaMemsetAsync(rc->d_zero_idx, 0, sizeof(uint32_t) * max_projs, rc->ctx->stream));
   XRC_CUDA(cudaHostAlloc(&rc->h_poses, sizeof(float) * 12 * max_projs, cudaHostAllocDefault));
   XRC_CUDA(cudaHostAlloc(&rc->h_cam_idx, sizeof(uint32_t) * max_projs, cudaHostAllocDefault));
   if (!rc->staged)
@@ -479,6 +488,8 @@ int xrc_rc_max_projs_possible(const xrc_rc* rc, uint64_t* n)
 static int rc_upload_poses(xrc_rc* rc, uint32_t n)
 {
   cudaStream_t st = rc->ctx->stream;
+  rc->ext_poses = nullptr;
+  rc->ext_cam_idx = nullptr;
   XRC_CUDA(cudaMemcpyAsync(rc->d_poses, rc->h_poses, sizeof(float) * 12 * n, cudaMemcpyHostToDevice, st));
   XRC_CUDA(cudaMemcpyAsync(rc->d_cam_idx, rc->h_cam_idx, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
   XRC_CUDA(cudaEventRecord(rc->staged, st));
@@ -536,6 +547,16 @@ int xrc_rc_distribute_poses(xrc_rc* rc, uint32_t n_poses, const float* cam_to_ph
   return rc_upload_poses(rc, g);
 }
 
+int xrc_rc_set_poses_device(xrc_rc* rc, uint32_t n, const float* dev_cam_to_phys, const uint32_t* dev_cam_idx)
+{
+  XRC_CHECK_ARG(rc && dev_cam_to_phys, "xrc_rc_set_poses_device: null argument");
+  XRC_CHECK_ARG(rc->allocated, "xrc_rc_set_poses_device: allocate first");
+  XRC_CHECK_ARG(n == rc->num_projs, "xrc_rc_set_poses_device: pose count must equal num_projs");
+  rc->ext_poses = dev_cam_to_phys;
+  rc->ext_cam_idx = dev_cam_idx ? dev_cam_idx : rc->d_zero_idx;
+  return XRC_OK;
+}
+
 int xrc_rc_set_params(xrc_rc* rc, float step_size, int interp, int kernel_id, int store_method, float default_bg)
 {
   XRC_CHECK_ARG(rc, "null ray caster");
@@ -591,8 +612,8 @@ static void rc_fill_args(xrc_rc* rc, uint32_t vol_idx, DrrArgs* a)
   a->nz = (int)v.dims[2];
   memcpy(a->phys_to_idx, v.phys_to_idx, sizeof(float) * 12);
   a->cams = rc->d_cams;
-  a->poses = rc->d_poses;
-  a->cam_idx = rc->d_cam_idx;
+  a->poses = rc->ext_poses ? rc->ext_poses : rc->d_poses;
+  a->cam_idx = rc->ext_poses ? rc->ext_cam_idx : rc->d_cam_idx;
   a->n_projs = rc->num_projs;
   a->rows = rc->rows;
   a->cols = rc->cols;

@@ -179,7 +179,7 @@ __device__ __forceinline__ Ray setup_ray(const xrc_cam& cam, const ProjConst& pc
 // trilinear sample for the different HBM layouts.  All produce
 //   vx00 + ... lerps in f32 with the ITK weight / neighbour rules (clamping the
 // coordinate to [0, n-1] reproduces ITK's start-index clamp, "distance <= 0" and
-// "neighbour beyond end index" branches exactly; see oracle/xreg_oracle.c).
+// "neighbour beyond end index" branches exactly; DESIGN.md has the argument).
 // floor() uses the round-down add trick (full-rate FADD.RM instead of F2I/I2F).
 // ----------------------------------------------------------------------------
 struct Cell

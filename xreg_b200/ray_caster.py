@@ -317,6 +317,12 @@ class RayCasterLineIntCUDA:
         self._cam_model_for_proj = [0] * n if cam_idx is None else [int(c) for c in cam_idx]
         self._poses_dirty = False
 
+    def set_poses_device(self, dev_poses_ptr: int, n: int, dev_cam_idx_ptr: int = 0) -> None:
+        """Poses already resident on the device (n x 12 float32, optional n x uint32 camera ids)."""
+        check(self._lib.xrc_rc_set_poses_device(self.handle, int(n), C.c_void_p(dev_poses_ptr),
+                                                C.c_void_p(dev_cam_idx_ptr) if dev_cam_idx_ptr else None))
+        self._poses_dirty = False
+
     def compute(self, vol_idx: int = 0) -> None:
         if not self._resources_allocated:
             raise _lib.XregError("compute: resources not allocated (xregRayCastLineIntCPU.cpp:296)")
@@ -349,14 +355,18 @@ class RayCasterLineIntCUDA:
         check(self._lib.xrc_rc_device_buf(self.handle, C.byref(p)))
         return int(p.value)
 
-    def ray_info(self, vol_idx: int = 0):
-        """(clip mask, samples per ray, total samples S) for the current poses."""
+    def ray_info(self, vol_idx: int = 0, counts_only: bool = False):
+        """(clip mask, samples per ray, total samples S) for the current poses
+        (mask / per-ray arrays are None with counts_only)."""
         self._flush()
+        S = C.c_uint64()
+        if counts_only:
+            check(self._lib.xrc_rc_ray_info(self.handle, int(vol_idx), None, None, C.byref(S)))
+            return None, None, int(S.value)
         cam = self._cams[0]
         shape = (self._num_projs, cam.num_det_rows, cam.num_det_cols)
         mask = np.zeros(shape, np.uint8)
         steps = np.zeros(shape, np.uint32)
-        S = C.c_uint64()
         check(self._lib.xrc_rc_ray_info(self.handle, int(vol_idx), mask.ctypes.data_as(C.POINTER(C.c_uint8)),
                                         steps.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(S)))
         return mask, steps, int(S.value)

@@ -1,0 +1,138 @@
+"""The batch objective of intensity-based 2D/3D registration and its multi-GPU sharding.
+
+Intensity2D3DObjFn is what Intensity2D3DRegi::obj_fn does per optimiser iteration
+(lib/regi/interfaces_2d_3d/xregIntensity2D3DRegi.cpp:571-696) for one moving volume:
+distribute the population over the views (camera-major), ray cast, evaluate every
+view's metric, average over views.  ShardedObjFn splits the population over the
+ranks of a torch.distributed job (one process per GPU, volume replicated, no
+data-path collective) and gathers only the per-pose scalars.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from .geometry import CameraModel, Volume, f32, to12
+from .ray_caster import Context, RayCasterLineIntCUDA
+from .sim_metrics import (ImgSimMetric2D, ImgSimMetric2DGradNCCCUDA, ImgSimMetric2DNCCCUDA,
+                          ImgSimMetric2DPatchGradNCCCUDA, ImgSimMetric2DPatchNCCCUDA, eval_batch)
+
+METRICS = {
+    "ncc": ImgSimMetric2DNCCCUDA,
+    "grad-ncc": ImgSimMetric2DGradNCCCUDA,
+    "patch-ncc": ImgSimMetric2DPatchNCCCUDA,
+    "patch-grad-ncc": ImgSimMetric2DPatchGradNCCCUDA,
+}
+
+
+def shard_bounds(n: int, world_size: int) -> List[Tuple[int, int]]:
+    """Contiguous, balanced [begin, end) pose ranges per rank; the first n % world ranks
+    take one extra pose (100 poses on 8 ranks -> 13,13,13,13,12,12,12,12)."""
+    base, extra = divmod(int(n), int(world_size))
+    out, b = [], 0
+    for r in range(world_size):
+        e = b + base + (1 if r < extra else 0)
+        out.append((b, e))
+        b = e
+    return out
+
+
+class Intensity2D3DObjFn:
+    """Single-GPU objective: poses (n, 4, 4) or (n, 12) cam->volume-physical -> (n,) similarity."""
+
+    def __init__(self, ctx: Context, vol: Volume, cams: Sequence[CameraModel], fixed_imgs: Sequence[np.ndarray],
+                 metric: str = "patch-grad-ncc", max_pop: int = 100, patch_radius: Optional[int] = None,
+                 patch_stride: int = 1, gauss_width: int = 5, masks: Optional[Sequence[Optional[np.ndarray]]] = None,
+                 step_size: float = 1.0, layout: str = "default"):
+        if len(cams) != len(fixed_imgs):
+            raise _lib.XregError("need one fixed image per camera model / view")
+        self.ctx = ctx
+        self.n_views = len(cams)
+        self.max_pop = int(max_pop)
+        self.rc = RayCasterLineIntCUDA(ctx, layout=layout)
+        self.rc.set_volume(vol)
+        self.rc.set_camera_models(list(cams))
+        self.rc.set_ray_step_size(step_size)
+        # xregIntensity2D3DRegi.cpp:63-94: view-major buffer, metric v reads [v*pop, (v+1)*pop)
+        self.rc.set_num_projs(self.max_pop * self.n_views)
+        self.rc.allocate_resources()
+        self.sims: List[ImgSimMetric2D] = []
+        for v in range(self.n_views):
+            sm = METRICS[metric](ctx)
+            sm.set_num_moving_images(self.max_pop)
+            sm.set_fixed_image(fixed_imgs[v])
+            sm.set_mov_imgs_buf_from_ray_caster(self.rc, self.max_pop * v)
+            if masks is not None and masks[v] is not None:
+                sm.set_mask(masks[v])
+            if hasattr(sm, "set_patch_radius") and patch_radius is not None:
+                sm.set_patch_radius(patch_radius)
+                sm.set_patch_stride(patch_stride)
+            if hasattr(sm, "set_smooth_img_before_sobel_kernel_radius"):
+                sm.set_smooth_img_before_sobel_kernel_radius(gauss_width)
+            sm.allocate_resources()
+            self.sims.append(sm)
+        self._cur_pop = self.max_pop
+
+    def _set_pop(self, n: int) -> None:
+        if n > self.max_pop:
+            raise _lib.XregError("population larger than the allocated capacity")
+        if n != self._cur_pop:
+            self.rc.set_num_projs(n * self.n_views)
+            for v, sm in enumerate(self.sims):
+                sm.set_num_moving_images(n)
+                sm.set_mov_imgs_buf_from_ray_caster(self.rc, n * v)
+            self._cur_pop = n
+
+    def __call__(self, poses: np.ndarray) -> np.ndarray:
+        p12 = to12(poses) if np.asarray(poses).ndim == 3 else np.ascontiguousarray(poses, dtype=f32).reshape(-1, 12)
+        n = p12.shape[0]
+        if n == 0:
+            return np.zeros(0, dtype=f32)
+        self._set_pop(n)
+        # distribute_xforms_among_cam_models: camera-major replication
+        allp = np.ascontiguousarray(np.tile(p12, (self.n_views, 1)))
+        cam_idx = np.repeat(np.arange(self.n_views, dtype=np.uint32), n)
+        self.rc.set_poses_array(allp, cam_idx)
+        per_view = eval_batch(self.rc, self.sims, n)
+        # ImgSimMetric2DCombineMean (xregImgSimMetric2DCombine.cpp:67-86)
+        acc = np.zeros(n, dtype=f32)
+        for v in range(self.n_views):
+            acc = (acc + per_view[v]).astype(f32)
+        return (acc / f32(self.n_views)).astype(f32)
+
+
+class ShardedObjFn:
+    """Pose-sharded objective over a torch.distributed process group.
+
+    local_fn evaluates this rank's slice; only the similarity scalars are gathered
+    (all_gather of <= ceil(n/world) floats per rank: NCCL over NVLink on GPUs, gloo in
+    the CPU tests).  Every rank returns the full (n,) vector in population order."""
+
+    def __init__(self, local_fn: Callable[[np.ndarray], np.ndarray], rank: int = 0, world_size: int = 1,
+                 device: str = "cpu", group=None):
+        self.local_fn = local_fn
+        self.rank, self.world_size = int(rank), int(world_size)
+        self.device = device
+        self.group = group
+
+    def __call__(self, poses: np.ndarray) -> np.ndarray:
+        poses = np.asarray(poses)
+        n = poses.shape[0]
+        bounds = shard_bounds(n, self.world_size)
+        b, e = bounds[self.rank]
+        local = np.asarray(self.local_fn(poses[b:e]), dtype=f32)
+        if self.world_size == 1:
+            return local
+        import torch
+        import torch.distributed as dist
+
+        width = max(hi - lo for lo, hi in bounds)
+        send = torch.zeros(width, dtype=torch.float32, device=self.device)
+        if e > b:
+            send[: e - b] = torch.from_numpy(local).to(self.device)
+        parts = [torch.empty(width, dtype=torch.float32, device=self.device) for _ in range(self.world_size)]
+        dist.all_gather(parts, send, group=self.group)
+        recv = torch.stack(parts).cpu().numpy()
+        return np.concatenate([recv[r, : hi - lo] for r, (lo, hi) in enumerate(bounds)]).astype(f32)
