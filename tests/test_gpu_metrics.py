@@ -17,8 +17,10 @@ def _img(rows, cols, seed, smooth=True):
     a = rng.standard_normal((rows, cols))
     if smooth:
         k = np.ones(5) / 5
-        a = np.apply_along_axis(lambda v: np.convolve(v, k, mode="same"), 0, a)
-        a = np.apply_along_axis(lambda v: np.convolve(v, k, mode="same"), 1, a)
+        if rows >= 5:
+            a = np.apply_along_axis(lambda v: np.convolve(v, k, mode="same"), 0, a)
+        if cols >= 5:
+            a = np.apply_along_axis(lambda v: np.convolve(v, k, mode="same"), 1, a)
     return (a * 3 + 5).astype(f32)
 
 
