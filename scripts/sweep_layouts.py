@@ -25,9 +25,13 @@ def main():
     dev = torch.device("cuda", 0)
     stream = torch.cuda.Stream(device=dev)
     results = []
+    only = os.environ.get("SWEEP_ONLY")  # e.g. "quad,lateral,fine,0" (for ncu captures)
+    layouts = os.environ.get("SWEEP_LAYOUTS", "quad,linear,oct,tex_quad").split(",")
+    if only:
+        layouts = [only.split(",")[0]]
     with torch.cuda.stream(stream):
         ctx = xreg_b200.Context(0, stream=stream.cuda_stream)
-        for layout in ["quad", "linear", "oct", "tex", "tex_quad"]:
+        for layout in layouts:
             rc = xreg_b200.RayCasterLineIntCUDA(ctx, layout=layout)
             rc.set_volume(vol)
             rc.set_camera_model(cam)
@@ -40,6 +44,8 @@ def main():
                         continue
                     pops = [synth.pose_population(vol, nominal, pop_n, seed=100 + k, sigma=sig) for k in range(6)]
                     for order in (0, 1):
+                        if only and (vname, sname, str(order)) != tuple(only.split(",")[1:4]):
+                            continue
                         rc.set_layout_order(order)
                         S = 0
                         for k in range(2):
