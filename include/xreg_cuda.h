@@ -73,7 +73,7 @@ enum { XRC_KERNEL_SUM = 0, XRC_KERNEL_MAX = 1 };
 enum { XRC_SM_NCC = 0, XRC_SM_GRAD_NCC = 1, XRC_SM_PATCH_NCC = 2, XRC_SM_PATCH_GRAD_NCC = 3 };
 /* Volume layouts in HBM (DESIGN.md "Data layout").  Results are identical for all. */
 enum { XRC_LAYOUT_DEFAULT = -1, XRC_LAYOUT_LINEAR = 0, XRC_LAYOUT_QUAD = 1, XRC_LAYOUT_TEX_QUAD = 2,
-       XRC_LAYOUT_OCT = 3, XRC_LAYOUT_TEX = 4 };
+       XRC_LAYOUT_OCT = 3, XRC_LAYOUT_TEX = 4, XRC_LAYOUT_PAX = 5 };
 
 const char* xrc_last_error(void);
 int xrc_version(void);

@@ -26,7 +26,7 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     results = []
     only = os.environ.get("SWEEP_ONLY")  # e.g. "quad,lateral,fine,0" (for ncu captures)
-    layouts = os.environ.get("SWEEP_LAYOUTS", "quad,linear,oct,tex_quad").split(",")
+    layouts = os.environ.get("SWEEP_LAYOUTS", "pax").split(",")
     if only:
         layouts = [only.split(",")[0]]
     with torch.cuda.stream(stream):
@@ -43,7 +43,7 @@ def main():
                     if sname == "coarse" and vname != "ap":
                         continue
                     pops = [synth.pose_population(vol, nominal, pop_n, seed=100 + k, sigma=sig) for k in range(6)]
-                    for order in (0, 1):
+                    for order in ((0, 8, 24, 32) if layout == 'pax' else (0,)):
                         if only and (vname, sname, str(order)) != tuple(only.split(",")[1:4]):
                             continue
                         rc.set_layout_order(order)

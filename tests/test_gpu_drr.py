@@ -11,7 +11,8 @@ pytestmark = pytest.mark.gpu
 f32 = np.float32
 
 DRR_REL_TOL = 1.0e-4  # BASELINE.json north_star: per-pixel DRR relative error <= 1e-4
-LAYOUTS = ["linear", "quad", "oct", "tex", "tex_quad"]
+LAYOUTS = ["linear", "quad", "oct", "tex", "tex_quad"]  # one lerp order: bitwise equal
+ALL_LAYOUTS = LAYOUTS + ["pax"]
 
 
 def _make_rc(ctx, vol, cams, n, layout="default"):
@@ -33,7 +34,7 @@ def _check_drr(got, ref, mask):
     return float(np.abs(got - ref).max())
 
 
-@pytest.mark.parametrize("layout", LAYOUTS)
+@pytest.mark.parametrize("layout", ALL_LAYOUTS)
 def test_drr_parity_all_layouts(ctx, xo, small_scene, layout):
     vol, cam, nominal = small_scene
     poses = synth.pose_population(vol, nominal, 5, sigma=(10, 10, 10, 6, 6, 6))
@@ -61,6 +62,44 @@ def test_layouts_agree_bitwise(ctx, small_scene):
         outs.append(rc.raw_host_pixel_buf())
     for o in outs[1:]:
         np.testing.assert_array_equal(o, outs[0])
+    # the principal-axis stacks lerp in a different order (b, c, a): same samples, last-ulp differences only
+    rc = _make_rc(ctx, vol, [cam], 3, "pax")
+    rc.set_xforms_cam_to_itk_phys(list(poses))
+    rc.compute()
+    pax = rc.raw_host_pixel_buf()
+    assert np.array_equal(pax == 0, outs[0] == 0)
+    sel = outs[0] != 0
+    assert np.max(np.abs(pax[sel] - outs[0][sel]) / np.abs(outs[0][sel])) < 2e-6
+
+
+@pytest.mark.parametrize("view_deg,axis", [(0.0, "y"), (90.0, "x"), (35.0, "y/x"), (55.0, "x/y")])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])  # bit0: scalar FP32 instead of f32x2; bit1: force the clamped loop
+def test_pax_every_stack_and_variant(ctx, xo, view_deg, axis, variant):
+    """Every principal-axis stack (rays along y, x and oblique; a tilted C-arm for z), packed and
+    scalar arithmetic, fast and clamped marching loops: all must match the oracle."""
+    vol = synth.make_volume(40, 56, 48, spacing=(1.1, 0.9, 1.0))
+    cam = CameraModel().setup(400.0, 48, 40, 2.2, 2.2)
+    for tilt in (None, "z"):
+        nominal = synth.nominal_pose(vol, src_to_iso=260.0, view_rot_deg=view_deg)
+        if tilt == "z":  # rotate the C-arm about x so that rays run along the volume's z axis
+            rot = np.array([[1, 0, 0, 0], [0, 0, -1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=f32)
+            c = np.asarray(vol.origin) + 0.5 * (np.asarray(vol.dims) - 1.0) * np.asarray(vol.spacing)
+            tr, tri = np.eye(4, dtype=f32), np.eye(4, dtype=f32)
+            tr[:3, 3], tri[:3, 3] = c, -c
+            nominal = (tr @ rot @ tri @ nominal).astype(f32)
+        poses = synth.pose_population(vol, nominal, 3, sigma=(4, 4, 4, 3, 3, 3))
+        ref, mask, steps, S = xo.drr(vol.data, vol.idx_to_phys(), [xo.cam_struct(cam)], to12(poses), want_info=True)
+        assert mask.sum() > 0.3 * mask.size
+        rc = _make_rc(ctx, vol, [cam], 3, "pax")
+        rc.set_layout_order(variant << 1)
+        rc.set_xforms_cam_to_itk_phys(list(poses))
+        rc.compute()
+        got = rc.raw_host_pixel_buf()
+        gmask, gsteps, gS = rc.ray_info()
+        np.testing.assert_array_equal(gmask, mask)
+        np.testing.assert_array_equal(gsteps, steps)
+        _check_drr(got, ref, mask)
+        rc.close()
 
 
 @pytest.mark.parametrize("frame_type", [0, 1, 2])

@@ -168,12 +168,12 @@ struct xrc_sm
   float* d_sims = nullptr;
   float* h_sims = nullptr;              // pinned
   // patch fixed stats (stride-1 grid)
-  float* d_pmean[2] = {nullptr, nullptr};
+  double* d_pmean[2] = {nullptr, nullptr};
   float* d_pden[2] = {nullptr, nullptr};
-  float* d_psmask[2] = {nullptr, nullptr};
+  double* d_psmask[2] = {nullptr, nullptr};
   float* d_pnmask = nullptr;
   float* d_weights = nullptr;
-  float divisor = 1.0f;
+  double divisor = 1.0;
   uint32_t n_strips = 0;
 };
 
@@ -312,7 +312,7 @@ int xrc_rc_destroy(xrc_rc* rc)
 int xrc_rc_set_layout(xrc_rc* rc, int layout)
 {
   XRC_CHECK_ARG(rc, "null ray caster");
-  XRC_CHECK_ARG(layout >= XRC_LAYOUT_DEFAULT && layout <= XRC_LAYOUT_TEX, "unknown layout");
+  XRC_CHECK_ARG(layout >= XRC_LAYOUT_DEFAULT && layout <= XRC_LAYOUT_PAX, "unknown layout");
   XRC_CHECK_ARG(rc->vols.empty(), "xrc_rc_set_layout must be called before xrc_rc_set_volumes");
   rc->layout = layout;
   return XRC_OK;
@@ -327,7 +327,6 @@ static int rc_set_volumes_impl(xrc_rc* rc, uint32_t n, const float* const* ptrs,
   cudaStream_t st = rc->ctx->stream;
   XRC_CUDA(cudaStreamSynchronize(st));
   rc_free_vols(rc);
-  const int layout = (rc->layout == XRC_LAYOUT_DEFAULT) ? XRC_LAYOUT_QUAD : rc->layout;
   rc->vols.resize(n);
   for (uint32_t i = 0; i < n; ++i)
   {
@@ -339,6 +338,14 @@ static int rc_set_volumes_impl(xrc_rc* rc, uint32_t n, const float* const* ptrs,
       v.dims[k] = dims[i][k];
     }
     XRC_CHECK_ARG(v.dims[0] * v.dims[1] < (1ull << 31), "xrc_rc_set_volumes: slice too large");
+    // default: principal-axis stacks; volumes whose padded record count exceeds 32 bits use one XY-quad stack
+    int layout = rc->layout;
+    if (layout == XRC_LAYOUT_DEFAULT)
+    {
+      const uint64_t dmax = std::max(v.dims[0], std::max(v.dims[1], v.dims[2]));
+      layout = ((v.dims[0] + 2) * (v.dims[1] + 2) * (v.dims[2] + 2) + dmax * dmax < (1ull << 32)) ? XRC_LAYOUT_PAX
+                                                                                                   : XRC_LAYOUT_QUAD;
+    }
     memcpy(v.idx_to_phys, idx_to_phys[i], sizeof(float) * 12);
     affine_inverse_f32(v.idx_to_phys, v.phys_to_idx);
     const size_t nvox = (size_t)v.dims[0] * v.dims[1] * v.dims[2];
@@ -622,7 +629,14 @@ static void rc_fill_args(xrc_rc* rc, uint32_t vol_idx, DrrArgs* a)
   a->init_mode = rc->use_bg ? 1 : ((rc->store_method == XRC_STORE_REPLACE) ? 0 : 2);
   a->default_bg = rc->default_bg;
   a->bg = rc->d_bg;
-  a->order = rc->order;
+  a->order = rc->order & 1;
+  a->variant = rc->order >> 1;
+  for (int k = 0; k < 3; ++k)
+  {
+    a->pax[k] = v.pax[k];
+    a->pax_sb[k] = v.pax_sb[k];
+    a->pax_sc[k] = v.pax_sc[k];
+  }
 }
 
 int xrc_rc_compute(xrc_rc* rc, uint32_t vol_idx)
@@ -719,8 +733,8 @@ int xrc_rc_ray_info(xrc_rc* rc, uint32_t vol_idx, uint8_t* host_mask, uint32_t* 
 // internal tuning hook (not part of the documented ABI surface): CTA ordering
 int xrc_rc_set_cta_order(xrc_rc* rc, int order)
 {
-  XRC_CHECK_ARG(rc && (order == 0 || order == 1), "bad argument");
-  rc->order = order;
+  XRC_CHECK_ARG(rc && order >= 0 && order < 256, "bad argument");
+  rc->order = order;  // bit 0: CTA order; bits 1..: kernel variant (measurement only)
   return XRC_OK;
 }
 
@@ -1013,21 +1027,20 @@ static int sm_prepare_fixed(xrc_sm* sm)
     }
     if (sm->compute_mean)
     {
-      sm->divisor = (float)np;
+      sm->divisor = (double)np;
     }
     else if (sm->weight_sims)
     {
-      float tw = 0.0f;
+      // tot_wgt (:277-284), summed in f64 like the kernel's sum of w_k s_k so that the ratio carries no
+      // f32 accumulation error (the reference's two sequential f32 sums have correlated rounding errors)
+      double tw = 0.0;
       for (uint64_t k = 0; k < np; ++k)
-      {
-        const volatile float t = tw + (sm->has_weights ? sm->h_weights[k] : 1.0f);
-        tw = t;
-      }
+        tw += sm->has_weights ? (double)sm->h_weights[k] : 1.0;
       sm->divisor = tw;
     }
     else
     {
-      sm->divisor = 1.0f;
+      sm->divisor = 1.0;
     }
   }
   XRC_CUDA(cudaStreamSynchronize(st));
@@ -1096,9 +1109,9 @@ int xrc_sm_allocate(xrc_sm* sm, uint32_t max_imgs)
     const size_t grid1 = (size_t)(sm->rows - 2 * r) * (sm->cols - 2 * r);
     for (int d = 0; d < n_dirs; ++d)
     {
-      XRC_CUDA(cudaMalloc(&sm->d_pmean[d], grid1 * sizeof(float)));
+      XRC_CUDA(cudaMalloc(&sm->d_pmean[d], grid1 * sizeof(double)));
       XRC_CUDA(cudaMalloc(&sm->d_pden[d], grid1 * sizeof(float)));
-      XRC_CUDA(cudaMalloc(&sm->d_psmask[d], grid1 * sizeof(float)));
+      XRC_CUDA(cudaMalloc(&sm->d_psmask[d], grid1 * sizeof(double)));
     }
     XRC_CUDA(cudaMalloc(&sm->d_pnmask, grid1 * sizeof(float)));
     const uint32_t W = patch_strip_width(r);

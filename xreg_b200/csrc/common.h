@@ -63,6 +63,11 @@ struct DeviceVolume
   cudaArray_t array = nullptr;      // TEX / TEX_QUAD
   cudaTextureObject_t tex = 0;
   size_t bytes = 0;
+  // XRC_LAYOUT_PAX: one padded XY-quad record stack per principal ray axis k
+  // (slow axis c = k, fast a = (k+1)%3, mid b = (k+2)%3); see drr.cu
+  void* pax[3] = {nullptr, nullptr, nullptr};
+  uint32_t pax_sb[3] = {0, 0, 0};   // record strides of the mid / slow axis
+  uint32_t pax_sc[3] = {0, 0, 0};
 };
 
 // Arguments of the DRR kernels (passed by value).
@@ -85,6 +90,9 @@ struct DrrArgs
   const float* bg;            // n_cams x rows x cols
   unsigned long long* sample_counter;  // optional
   int order;                  // 0: projection fastest over CTAs, 1: tile fastest
+  const void* pax[3];         // XRC_LAYOUT_PAX stacks
+  uint32_t pax_sb[3], pax_sc[3];
+  int variant;                // tuning: bit0 = scalar (non-packed) FP32 math in the PAX kernel
   uint8_t* ray_mask;          // ray-info kernel only
   uint32_t* ray_steps;        // ray-info kernel only
 };

@@ -461,6 +461,362 @@ __global__ void __launch_bounds__(kThreads) drr_kernel(const DrrArgs a)
   }
 }
 
+
+// ----------------------------------------------------------------------------
+// XRC_LAYOUT_PAX: principal-axis stacks (the default layout)
+//
+// Three padded XY-quad record stacks, one per principal ray axis k.  In stack k
+// the slow axis c is volume axis k, the fast axis a = (k+1)%3 and the mid axis
+// b = (k+2)%3; record (ia, ib, ic), ia in [-1, na-1], ib in [-1, nb-1],
+// ic in [-1, nc], is float4 {v(ia,ib,ic), v(ia+1,ib,ic), v(ia,ib+1,ic),
+// v(ia+1,ib+1,ic)} with indices clamped to the volume (replicated border).
+// A CTA picks the stack of the axis its central ray is most parallel to, so
+// that whatever the view direction
+//   * the 8x4-pixel warp footprint lies in the (a, b) plane: the 8 lanes of a
+//     quarter-warp read 4-5 consecutive 16-byte records (1-2 L1 wavefronts per
+//     quarter instead of 8 when rays run along the record axis), and
+//   * consecutive samples walk along c, so plane c+1 of one step is plane c of
+//     the next (L1 reuse).
+// The replicated one-record border makes coordinate clamping unnecessary: a
+// sample that f32 drift carries to x in (-1, 0) or (n-1, n) blends two copies
+// of the edge voxel, which is exactly ITK's "clamp base index / drop neighbour
+// beyond the end" result (xregRayCastLineIntCPU.cpp:273).  Rays for
+// which drift < 1/2 voxel cannot be proven take the clamped loop.
+// Inner loop (packed): FADD2 / FFMA2 (sm_100 f32x2) for the x,y position,
+// floor and the b- and c-lerps; 32-bit record index with the 1.5*2^23 magic
+// constants folded into one precomputed offset.
+// ----------------------------------------------------------------------------
+constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23: float_as_int(x + kMagic) - 0x4B400000 == floor(x), x in (-2^22, 2^22)
+
+__device__ __forceinline__ float2 mk2(float a, float b) { return make_float2(a, b); }
+
+struct PaxStack
+{
+  const float4* __restrict__ base;
+  uint32_t Sb, Sc, K;
+  float ha, hb, hc;
+};
+
+// record index + interpolation weights of one sample
+template <bool PACK, bool CLAMP>
+__device__ __forceinline__ void pax_cell(const PaxStack& st, float xa, float xb, float xc, uint32_t& rec, float& wa,
+                                         float& wb, float& wc)
+{
+  if (CLAMP)
+  {
+    xa = fminf(fmaxf(xa, 0.0f), st.ha);
+    xb = fminf(fmaxf(xb, 0.0f), st.hb);
+    xc = fminf(fmaxf(xc, 0.0f), st.hc);
+  }
+  if (PACK)
+  {
+    const float2 ab = mk2(xa, xb);
+    const float2 t = __fadd2_rd(ab, mk2(kMagic, kMagic));
+    const float tc = __fadd_rd(xc, kMagic);
+    rec = __float_as_uint(tc) * st.Sc + __float_as_uint(t.y) * st.Sb + __float_as_uint(t.x) + st.K;
+    const float2 nb = __fadd2_rn(mk2(kMagic, kMagic), mk2(-t.x, -t.y));  // -(floor) exactly
+    const float2 w = __fadd2_rn(ab, nb);                                  // x - floor(x), exact
+    wa = w.x;
+    wb = w.y;
+    wc = xc - (tc - kMagic);
+  }
+  else
+  {
+    const float ta = __fadd_rd(xa, kMagic), tb = __fadd_rd(xb, kMagic), tc = __fadd_rd(xc, kMagic);
+    rec = __float_as_uint(tc) * st.Sc + __float_as_uint(tb) * st.Sb + __float_as_uint(ta) + st.K;
+    wa = xa - (ta - kMagic);
+    wb = xb - (tb - kMagic);
+    wc = xc - (tc - kMagic);
+  }
+}
+
+// q0 = plane c, q1 = plane c+1, each {v(a,b), v(a+1,b), v(a,b+1), v(a+1,b+1)}
+template <bool PACK>
+__device__ __forceinline__ float pax_lerp(const float4& q0, const float4& q1, float wa, float wb, float wc)
+{
+  if (PACK)
+  {
+    // lerp along b and c on (a, a+1) pairs, then along a
+    const float2 l0 = mk2(q0.x, q0.y), h0 = mk2(q0.z, q0.w), l1 = mk2(q1.x, q1.y), h1 = mk2(q1.z, q1.w);
+    const float2 wb2 = mk2(wb, wb), wc2 = mk2(wc, wc);
+    const float2 r0 = __ffma2_rn(wb2, __fadd2_rn(h0, mk2(-l0.x, -l0.y)), l0);
+    const float2 r1 = __ffma2_rn(wb2, __fadd2_rn(h1, mk2(-l1.x, -l1.y)), l1);
+    const float2 rr = __ffma2_rn(wc2, __fadd2_rn(r1, mk2(-r0.x, -r0.y)), r0);
+    return fmaf(wa, rr.y - rr.x, rr.x);
+  }
+  return trilerp(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, wa, wb, wc);
+}
+
+template <bool PACK>
+__device__ __forceinline__ void pax_advance(float& pa, float& pb, float& pc, float sa, float sb, float sc)
+{
+  if (PACK)
+  {
+    const float2 p = __fadd2_rn(mk2(pa, pb), mk2(sa, sb));
+    pa = p.x;
+    pb = p.y;
+  }
+  else
+  {
+    pa = __fadd_rn(pa, sa);
+    pb = __fadd_rn(pb, sb);
+  }
+  pc = __fadd_rn(pc, sc);
+}
+
+// Software-pipelined marching loop.  Samples are processed in groups of BATCH; the
+// 2*BATCH loads of group g+1 are issued BEFORE the lerps of group g and consumed one
+// iteration later (values carried across the loop back-edge, so the assembler cannot
+// sink the loads next to their uses).  The kernel is bound by the L1 data pipe
+// (97 % busy in ncu, profiles/); the extra loads in flight per thread keep that pipe
+// fed through L1 misses.  Positions and the sum advance in sample order, exactly like
+// the sequential reference loop (xregRayCastLineIntCPU.cpp:270-277).
+template <int KERNEL_ID, bool PACK, bool CLAMP, int BATCH>
+__device__ __forceinline__ float pax_march(const PaxStack& st, float pa, float pb, float pc, float sa, float sb,
+                                           float sc, uint32_t n)
+{
+  float sum = (KERNEL_ID == XRC_KERNEL_MAX) ? -3.402823466e+38f : 0.0f;
+  const uint32_t ng = n / BATCH;
+  if (ng > 0)
+  {
+    float wa[BATCH], wb[BATCH], wc[BATCH];
+    float4 q0[BATCH], q1[BATCH];
+#pragma unroll
+    for (int j = 0; j < BATCH; ++j)
+    {
+      uint32_t rec;
+      pax_cell<PACK, CLAMP>(st, pa, pb, pc, rec, wa[j], wb[j], wc[j]);
+      q0[j] = __ldg(st.base + rec);
+      q1[j] = __ldg(st.base + (rec + st.Sc));
+      pax_advance<PACK>(pa, pb, pc, sa, sb, sc);
+    }
+#pragma unroll 2
+    for (uint32_t g = 1; g < ng; ++g)
+    {
+      float nwa[BATCH], nwb[BATCH], nwc[BATCH];
+      float4 n0[BATCH], n1[BATCH];
+#pragma unroll
+      for (int j = 0; j < BATCH; ++j)
+      {
+        uint32_t rec;
+        pax_cell<PACK, CLAMP>(st, pa, pb, pc, rec, nwa[j], nwb[j], nwc[j]);
+        n0[j] = __ldg(st.base + rec);
+        n1[j] = __ldg(st.base + (rec + st.Sc));
+        pax_advance<PACK>(pa, pb, pc, sa, sb, sc);
+      }
+#pragma unroll
+      for (int j = 0; j < BATCH; ++j)
+      {
+        const float v = pax_lerp<PACK>(q0[j], q1[j], wa[j], wb[j], wc[j]);
+        sum = (KERNEL_ID == XRC_KERNEL_MAX) ? fmaxf(sum, v) : __fadd_rn(sum, v);
+        q0[j] = n0[j];
+        q1[j] = n1[j];
+        wa[j] = nwa[j];
+        wb[j] = nwb[j];
+        wc[j] = nwc[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < BATCH; ++j)
+    {
+      const float v = pax_lerp<PACK>(q0[j], q1[j], wa[j], wb[j], wc[j]);
+      sum = (KERNEL_ID == XRC_KERNEL_MAX) ? fmaxf(sum, v) : __fadd_rn(sum, v);
+    }
+  }
+  for (uint32_t s = ng * BATCH; s < n; ++s)
+  {
+    uint32_t rec;
+    float wa, wb, wc;
+    pax_cell<PACK, CLAMP>(st, pa, pb, pc, rec, wa, wb, wc);
+    const float4 q0 = __ldg(st.base + rec);
+    const float4 q1 = __ldg(st.base + (rec + st.Sc));
+    const float v = pax_lerp<PACK>(q0, q1, wa, wb, wc);
+    sum = (KERNEL_ID == XRC_KERNEL_MAX) ? fmaxf(sum, v) : __fadd_rn(sum, v);
+    pax_advance<PACK>(pa, pb, pc, sa, sb, sc);
+  }
+  return sum;
+}
+
+__device__ __forceinline__ float sel3(int k, float v0, float v1, float v2) { return (k == 0) ? v0 : ((k == 1) ? v1 : v2); }
+
+template <int KERNEL_ID, bool PACK, int BATCH>
+__global__ void __launch_bounds__(kThreads) drr_pax_kernel(const DrrArgs a)
+{
+  __shared__ ProjConst pc;
+  __shared__ xrc_cam cam_s;
+  __shared__ unsigned long long cta_samples;
+  __shared__ int axis_s, swap_s;
+
+  uint32_t proj, tile;
+  cta_coords(a, proj, tile);
+
+  const uint32_t ci = a.cam_idx[proj];
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.cams + ci);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&cam_s);
+    if (threadIdx.x < sizeof(xrc_cam) / 4)
+      dst[threadIdx.x] = src[threadIdx.x];
+    if (threadIdx.x == 0)
+      cta_samples = 0ull;
+  }
+  __syncthreads();
+  compute_proj_const(a, cam_s, a.poses + 12 * (size_t)proj, &pc);
+
+  if (threadIdx.x == 0)
+  {
+    // Principal axis of this tile's central ray and the detector direction that maps onto
+    // the stack's fast axis (index space).  Any choice gives the same samples; it only
+    // decides the memory access pattern, so plain (contracted) arithmetic is fine here.
+    const uint32_t tx = tile % a.tiles_x, ty = tile / a.tiles_x;
+    const uint32_t cr = min(ty * kTileH + kTileH / 2, a.rows - 1), cc = min(tx * kTileW + kTileW / 2, a.cols - 1);
+    const float det_z = ((cam_s.frame_type == 1) ? -1.0f : 1.0f) * cam_s.focal_len;
+    const float* Ki = cam_s.intrins_inv;
+    const float* E = cam_s.extrins_inv;
+    const float* X = pc.X;
+    // camera-frame images of (col, row, 1), d/dcol and d/drow
+    float cv[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+    {
+      cv[0][r] = det_z * (Ki[3 * r] * (float)cc + Ki[3 * r + 1] * (float)cr + Ki[3 * r + 2]);
+      cv[1][r] = det_z * Ki[3 * r];
+      cv[2][r] = det_z * Ki[3 * r + 1];
+    }
+    if (cam_s.frame_type == 2)
+      cv[0][2] -= cam_s.focal_len;
+    float iv[3][3];  // index-space: centre detector point, d/dcol, d/drow
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+    {
+      float w[3];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+        w[r] = E[4 * r] * cv[q][0] + E[4 * r + 1] * cv[q][1] + E[4 * r + 2] * cv[q][2] + ((q == 0) ? E[4 * r + 3] : 0.0f);
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+        iv[q][r] = X[4 * r] * w[0] + X[4 * r + 1] * w[1] + X[4 * r + 2] * w[2] + ((q == 0) ? X[4 * r + 3] : 0.0f);
+    }
+    const float dx = fabsf(iv[0][0] - pc.p[0]), dy = fabsf(iv[0][1] - pc.p[1]), dz = fabsf(iv[0][2] - pc.p[2]);
+    const int k = (dz >= dx && dz >= dy) ? 2 : ((dy >= dx) ? 1 : 0);
+    const int ka = (k == 2) ? 0 : k + 1;
+    axis_s = k;
+    // quarter-warps (8 consecutive lanes) run along the detector direction that moves fastest along
+    // axis a, so that their 8 records are consecutive in memory (1-2 L1 wavefronts per quarter)
+    swap_s = (fabsf(sel3(ka, iv[2][0], iv[2][1], iv[2][2])) > fabsf(sel3(ka, iv[1][0], iv[1][1], iv[1][2]))) ? 1 : 0;
+    if (a.variant & 16)
+      swap_s = 0;
+  }
+  __syncthreads();
+
+  uint32_t row, col;
+  {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t tx = tile % a.tiles_x, ty = tile / a.tiles_x;
+    if (swap_s)
+    {
+      // warp = 4 (cols) x 8 (rows); 4 x 2 warps per 16 x 16 tile
+      col = tx * kTileW + (warp >> 1) * 4 + (lane >> 3);
+      row = ty * kTileH + (warp & 1) * 8 + (lane & 7);
+    }
+    else
+    {
+      col = tx * kTileW + (warp & 1) * 8 + (lane & 7);
+      row = ty * kTileH + (warp >> 1) * 4 + (lane >> 3);
+    }
+  }
+  const bool in_img = (row < a.rows) && (col < a.cols);
+
+  Ray ray;
+  ray.hit = false;
+  ray.nsamples = 0;
+  if (in_img)
+    ray = setup_ray(cam_s, pc, a.step_size, a.nx, a.ny, a.nz, row, col);
+
+  float sum = (KERNEL_ID == XRC_KERNEL_MAX) ? -3.402823466e+38f : 0.0f;
+  if (ray.hit)
+  {
+    const int k = axis_s, ka = (k == 2) ? 0 : k + 1, kb = (ka == 2) ? 0 : ka + 1;
+    PaxStack st;
+    st.base = (const float4*)((k == 0) ? a.pax[0] : ((k == 1) ? a.pax[1] : a.pax[2]));
+    st.Sb = (k == 0) ? a.pax_sb[0] : ((k == 1) ? a.pax_sb[1] : a.pax_sb[2]);
+    st.Sc = (k == 0) ? a.pax_sc[0] : ((k == 1) ? a.pax_sc[1] : a.pax_sc[2]);
+    // rec = (ic+1)*Sc + (ib+1)*Sb + (ia+1) with i* = float_as_int(t*) - 0x4B400000
+    st.K = (st.Sc + st.Sb + 1u) - 0x4B400000u * (st.Sc + st.Sb + 1u);
+    const float hx = (float)(a.nx - 1), hy = (float)(a.ny - 1), hz = (float)(a.nz - 1);
+    st.ha = sel3(ka, hx, hy, hz);
+    st.hb = sel3(kb, hx, hy, hz);
+    st.hc = sel3(k, hx, hy, hz);
+    const float a0 = sel3(ka, ray.x, ray.y, ray.z), b0 = sel3(kb, ray.x, ray.y, ray.z), c0 = sel3(k, ray.x, ray.y, ray.z);
+    const float sa = sel3(ka, ray.sx, ray.sy, ray.sz), sb = sel3(kb, ray.sx, ray.sy, ray.sz), sc = sel3(k, ray.sx, ray.sy, ray.sz);
+    const uint32_t n = ray.nsamples;
+    // drift bound: every add rounds by <= ulp(h)/2 <= h * 2^-24  ->  n * h < 2^23 keeps the
+    // accumulated error below 1/2 voxel; the end points themselves lie within [-1/2, h + 1/2]
+    const float fn = (float)n;
+    const float ea = fmaf(fn, sa, a0), eb = fmaf(fn, sb, b0), ec = fmaf(fn, sc, c0);
+    const float hmax = fmaxf(st.ha, fmaxf(st.hb, st.hc)) + 1.0f;
+    const bool safe = !(a.variant & 2) && (fn * hmax < 8388608.0f) && (fminf(a0, ea) > -0.5f) &&
+                      (fmaxf(a0, ea) < st.ha + 0.5f) && (fminf(b0, eb) > -0.5f) && (fmaxf(b0, eb) < st.hb + 0.5f) &&
+                      (fminf(c0, ec) > -0.5f) && (fmaxf(c0, ec) < st.hc + 0.5f);
+    if (safe)
+      sum = pax_march<KERNEL_ID, PACK, false, BATCH>(st, a0, b0, c0, sa, sb, sc, n);
+    else
+      sum = pax_march<KERNEL_ID, PACK, true, 1>(st, a0, b0, c0, sa, sb, sc, n);
+    sum = fmul(sum, a.step_size);  // xregRayCastLineIntCPU.cpp:279
+  }
+
+  if (in_img)
+  {
+    const size_t npix = (size_t)a.rows * a.cols;
+    const size_t o = (size_t)proj * npix + (size_t)row * a.cols + col;
+    float base_v;
+    if (a.init_mode == 0)
+      base_v = a.default_bg;
+    else if (a.init_mode == 1)
+      base_v = __ldg(a.bg + (size_t)ci * npix + (size_t)row * a.cols + col);
+    else
+      base_v = a.out[o];
+    const float aa = fadd(0.0f, fmul(sum, 1.0f));  // :282
+    a.out[o] = (KERNEL_ID == XRC_KERNEL_MAX) ? fmaxf(base_v, aa) : fadd(base_v, aa);  // :285
+  }
+
+  if (a.sample_counter)
+  {
+    unsigned long long n = ray.nsamples;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+      n += __shfl_xor_sync(0xffffffffu, n, o);
+    if ((threadIdx.x & 31) == 0)
+      atomicAdd(&cta_samples, n);
+    __syncthreads();
+    if (threadIdx.x == 0)
+      atomicAdd(a.sample_counter, cta_samples);
+  }
+}
+
+template <int KERNEL_ID>
+static int launch_pax_k(const DrrArgs& a, cudaStream_t st)
+{
+  const uint32_t nblocks = a.n_projs * a.tiles_x * a.tiles_y;
+  const bool scalar = (a.variant & 1) != 0;
+  const int batch = (a.variant >> 2) & 3;  // 0: default
+  if (scalar)
+    drr_pax_kernel<KERNEL_ID, false, 1><<<nblocks, kThreads, 0, st>>>(a);
+  else if (batch == 1)
+    drr_pax_kernel<KERNEL_ID, true, 1><<<nblocks, kThreads, 0, st>>>(a);
+  else if (batch == 3)
+    drr_pax_kernel<KERNEL_ID, true, 4><<<nblocks, kThreads, 0, st>>>(a);
+  else
+    drr_pax_kernel<KERNEL_ID, true, 2><<<nblocks, kThreads, 0, st>>>(a);
+  count_launch();
+  XRC_CUDA(cudaGetLastError());
+  return XRC_OK;
+}
+
+static int launch_pax(const DrrArgs& a, int kernel_id, cudaStream_t st)
+{
+  return (kernel_id == XRC_KERNEL_SUM) ? launch_pax_k<XRC_KERNEL_SUM>(a, st) : launch_pax_k<XRC_KERNEL_MAX>(a, st);
+}
+
 // same ray set-up, emits the clip mask and sample counts (parity instrumentation)
 __global__ void __launch_bounds__(kThreads) ray_info_kernel(const DrrArgs a)
 {
@@ -519,6 +875,7 @@ int launch_drr(const DrrArgs& a_in, int layout, int kernel_id, cudaStream_t st)
     case XRC_LAYOUT_OCT: return launch_layout<XRC_LAYOUT_OCT>(a, kernel_id, st);
     case XRC_LAYOUT_TEX: return launch_layout<XRC_LAYOUT_TEX>(a, kernel_id, st);
     case XRC_LAYOUT_TEX_QUAD: return launch_layout<XRC_LAYOUT_TEX_QUAD>(a, kernel_id, st);
+    case XRC_LAYOUT_PAX: return launch_pax(a, kernel_id, st);
     default: XRC_FAIL(XRC_ERR_INVALID, "unknown volume layout");
   }
 }
@@ -582,8 +939,37 @@ __global__ void repack_oct_kernel(const float* __restrict__ src, float4* __restr
   }
 }
 
+
+// stack k of XRC_LAYOUT_PAX: A x B x C records, A = n[a]+1, B = n[b]+1, C = n[c]+2
+__global__ void repack_pax_kernel(const float* __restrict__ src, float4* __restrict__ dst, int nx, int ny, int nz, int k)
+{
+  const int n[3] = {nx, ny, nz};
+  const int ka = (k + 1) % 3, kb = (k + 2) % 3;
+  const int A = n[ka] + 1, B = n[kb] + 1, C = n[k] + 2;
+  const size_t total = (size_t)A * B * C;
+  const size_t st[3] = {1, (size_t)nx, (size_t)nx * ny};
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+  {
+    const int ia = (int)(i % A) - 1;
+    const int ib = (int)((i / A) % B) - 1;
+    const int ic = (int)(i / ((size_t)A * B)) - 1;
+    const int a0 = min(max(ia, 0), n[ka] - 1), a1 = min(max(ia + 1, 0), n[ka] - 1);
+    const int b0 = min(max(ib, 0), n[kb] - 1), b1 = min(max(ib + 1, 0), n[kb] - 1);
+    const int c0 = min(max(ic, 0), n[k] - 1);
+    const float* p = src + (size_t)c0 * st[k];
+    dst[i] = make_float4(p[a0 * st[ka] + b0 * st[kb]], p[a1 * st[ka] + b0 * st[kb]], p[a0 * st[ka] + b1 * st[kb]],
+                         p[a1 * st[ka] + b1 * st[kb]]);
+  }
+}
+
 void free_volume(DeviceVolume* v)
 {
+  for (int k = 0; k < 3; ++k)
+  {
+    if (v->pax[k])
+      cudaFree(v->pax[k]);
+    v->pax[k] = nullptr;
+  }
   if (v->tex)
     cudaDestroyTextureObject(v->tex);
   if (v->array)
@@ -665,6 +1051,24 @@ int repack_volume(const float* d_linear, DeviceVolume* v, int layout, cudaStream
       cudaStreamSynchronize(st);
       cudaFree(tmp);
       XRC_TRY(s);
+      break;
+    }
+    case XRC_LAYOUT_PAX:
+    {
+      const int n[3] = {nx, ny, nz};
+      v->bytes = 0;
+      for (int k = 0; k < 3; ++k)
+      {
+        const size_t A = (size_t)n[(k + 1) % 3] + 1, B = (size_t)n[(k + 2) % 3] + 1, C = (size_t)n[k] + 2;
+        if (A * B * C >= (1ull << 32))
+          XRC_FAIL(XRC_ERR_UNSUPPORTED, "volume too large for the PAX layout (record index must fit 32 bits)");
+        XRC_CUDA(cudaMalloc(&v->pax[k], sizeof(float4) * A * B * C));
+        v->pax_sb[k] = (uint32_t)A;
+        v->pax_sc[k] = (uint32_t)(A * B);
+        v->bytes += sizeof(float4) * A * B * C;
+        repack_pax_kernel<<<grid, block, 0, st>>>(d_linear, (float4*)v->pax[k], nx, ny, nz, k);
+        count_launch();
+      }
       break;
     }
     default: XRC_FAIL(XRC_ERR_INVALID, "unknown volume layout");

@@ -375,7 +375,8 @@ __device__ __forceinline__ void patch_quantities(double mv, double fv, double M,
 }
 
 // mean / clamped std-dev from box sums (detail::ComputePatchMeanStdDev, :558-619)
-__device__ __forceinline__ void stats_from_sums(double S, double SS, double cnt, float& mean, float& sd)
+__device__ __forceinline__ void stats_from_sums(double S, double SS, double cnt, float& mean, float& sd,
+                                                double* mean_d = nullptr)
 {
   double mu = S, var = 0.0;
   if (cnt > 1.0)
@@ -386,6 +387,8 @@ __device__ __forceinline__ void stats_from_sums(double S, double SS, double cnt,
       var = 0.0;
   }
   mean = (float)mu;
+  if (mean_d)
+    *mean_d = mu;
   sd = fmaxf(1.0e-6f, (float)sqrt(var));
 }
 
@@ -469,27 +472,28 @@ __global__ void __launch_bounds__(kPatchThreads) patch_kernel(const PatchArgs a)
         if (FIXED)
         {
           float mean, sd;
+          double mean_d;
           if (MODE == 0)
           {
-            stats_from_sums(S[0], S[1], n_full, mean, sd);
-            a.o_mean[dir][pa] = mean;
+            stats_from_sums(S[0], S[1], n_full, mean, sd, &mean_d);
+            a.o_mean[dir][pa] = mean_d;
             a.o_den[dir][pa] = sd * (float)n_full;
           }
           else if (MODE == 1)
           {
-            stats_from_sums(S[0], S[1], n_full, mean, sd);
-            a.o_mean[dir][pa] = mean;
+            stats_from_sums(S[0], S[1], n_full, mean, sd, &mean_d);
+            a.o_mean[dir][pa] = mean_d;
             a.o_den[dir][pa] = sd * (float)n_full;
-            a.o_smask[dir][pa] = (float)S[2];
+            a.o_smask[dir][pa] = S[2];
             if (dir == 0)
               a.o_nmask[pa] = (float)S[3];
           }
           else
           {
-            stats_from_sums(S[0], S[1], S[2], mean, sd);
-            a.o_mean[dir][pa] = mean;
+            stats_from_sums(S[0], S[1], S[2], mean, sd, &mean_d);
+            a.o_mean[dir][pa] = mean_d;
             a.o_den[dir][pa] = sd * (float)S[2];
-            a.o_smask[dir][pa] = (float)S[0];
+            a.o_smask[dir][pa] = S[0];
             if (dir == 0)
               a.o_nmask[pa] = (float)S[2];
           }
@@ -501,33 +505,33 @@ __global__ void __launch_bounds__(kPatchThreads) patch_kernel(const PatchArgs a)
           if (!a.weight_patch_sims || (fabsf(w) > 1.0e-6f))
           {
             float mu_m, sd_m;
-            double num;
-            const double mu_f = (double)__ldg(a.f_mean[dir] + pa);
+            double num, mu_md;
+            const double mu_f = __ldg(a.f_mean[dir] + pa);
             const float den_f = __ldg(a.f_den[dir] + pa);
             if (MODE == 0)
             {
-              stats_from_sums(S[0], S[1], n_full, mu_m, sd_m);
+              stats_from_sums(S[0], S[1], n_full, mu_m, sd_m, &mu_md);
               // sum (m - mu_m)(f - mu_f) = Smf - mu_f Sm   (sum (f - mu_f) = 0)
               num = S[2] - mu_f * S[0];
             }
             else
             {
               const double nM = (double)__ldg(a.n_mask + pa);
-              const double SfM = (double)__ldg(a.f_smask[dir] + pa);
+              const double SfM = __ldg(a.f_smask[dir] + pa);
               double SmM, SmfM;
               if (MODE == 1)
               {
-                stats_from_sums(S[0], S[1], n_full, mu_m, sd_m);
+                stats_from_sums(S[0], S[1], n_full, mu_m, sd_m, &mu_md);
                 SmM = S[2];
                 SmfM = S[3];
               }
               else
               {
-                stats_from_sums(S[0], S[1], nM, mu_m, sd_m);
+                stats_from_sums(S[0], S[1], nM, mu_m, sd_m, &mu_md);
                 SmM = S[0];
                 SmfM = S[2];
               }
-              num = SmfM - mu_f * SmM - (double)mu_m * SfM + (double)mu_m * mu_f * nM;
+              num = SmfM - mu_f * SmM - mu_md * SfM + mu_md * mu_f * nM;
             }
             const float accv = (den_f != 0.0f) ? ((float)num / (sd_m * den_f)) : 0.0f;
             const float s = 1.0f - accv;
@@ -583,7 +587,7 @@ __global__ void patch_finalize_kernel(const PatchFinalizeArgs a)
     const double* p = a.partials + ((size_t)img * a.n_dirs + d) * a.n_strips;
     for (uint32_t k = 0; k < a.n_strips; ++k)
       s += p[k];
-    sd[d] = (float)s / a.divisor;
+    sd[d] = (float)(s / a.divisor);
   }
   a.sims[img] = (a.n_dirs == 1) ? sd[0] : (float)(0.5 * ((double)sd[0] + (double)sd[1]));
 }

@@ -59,17 +59,17 @@ struct PatchArgs
   uint32_t n_strips;
   int mask_mode;           // 0 none, 1 mask in correlation only, 2 mask in stats too
   // fixed per-patch statistics on the stride-1 grid (rows-2r) x (cols-2r), per direction
-  const float* f_mean[2];
+  const double* f_mean[2];  // f64: keeps sum(m - mu_m)(f - mu_f) = Smf - mu_f Sm free of f32 rounding of mu_f
   const float* f_den[2];   // sigma_f * n
-  const float* f_smask[2]; // sum over mask of f (mask modes)
+  const double* f_smask[2]; // sum over mask of f (mask modes)
   const float* n_mask;     // mask count per patch (mask modes)
   const float* weights;    // per strided patch or null
   int weight_patch_sims;
   double* partials;        // n_imgs x n_dirs x n_strips
   // fixed-stats mode outputs (when mov[0] == nullptr)
-  float* o_mean[2];
+  double* o_mean[2];
   float* o_den[2];
-  float* o_smask[2];
+  double* o_smask[2];
   float* o_nmask;
 };
 
@@ -77,7 +77,7 @@ struct PatchFinalizeArgs
 {
   const double* partials;
   uint32_t n_imgs, n_dirs, n_strips;
-  float divisor;   // num_patches (mean), total weight, or 1
+  double divisor;  // num_patches (mean), total weight, or 1
   float* sims;
 };
 
