@@ -733,7 +733,7 @@ int xrc_rc_ray_info(xrc_rc* rc, uint32_t vol_idx, uint8_t* host_mask, uint32_t* 
 // internal tuning hook (not part of the documented ABI surface): CTA ordering
 int xrc_rc_set_cta_order(xrc_rc* rc, int order)
 {
-  XRC_CHECK_ARG(rc && order >= 0 && order < 256, "bad argument");
+  XRC_CHECK_ARG(rc && order >= 0 && order < 1024, "bad argument");
   rc->order = order;  // bit 0: CTA order; bits 1..: kernel variant (measurement only)
   return XRC_OK;
 }

@@ -639,8 +639,8 @@ __device__ __forceinline__ float pax_march(const PaxStack& st, float pa, float p
 
 __device__ __forceinline__ float sel3(int k, float v0, float v1, float v2) { return (k == 0) ? v0 : ((k == 1) ? v1 : v2); }
 
-template <int KERNEL_ID, bool PACK, int BATCH>
-__global__ void __launch_bounds__(kThreads) drr_pax_kernel(const DrrArgs a)
+template <int KERNEL_ID, bool PACK, int BATCH, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) drr_pax_kernel(const DrrArgs a)
 {
   __shared__ ProjConst pc;
   __shared__ xrc_cam cam_s;
@@ -797,16 +797,29 @@ template <int KERNEL_ID>
 static int launch_pax_k(const DrrArgs& a, cudaStream_t st)
 {
   const uint32_t nblocks = a.n_projs * a.tiles_x * a.tiles_y;
+  // variant (measurement only): bit0 scalar FP32, bit1 force clamped loop, bits 2-3 batch id, bit4 no lane swap,
+  // bits 5-7 min CTAs per SM (register budget)
   const bool scalar = (a.variant & 1) != 0;
-  const int batch = (a.variant >> 2) & 3;  // 0: default
+  const int batch = (a.variant >> 2) & 3;
+  const int minb = (a.variant >> 5) & 7;
+#define XRC_PAX_LAUNCH(B, M) drr_pax_kernel<KERNEL_ID, true, B, M><<<nblocks, kThreads, 0, st>>>(a)
   if (scalar)
-    drr_pax_kernel<KERNEL_ID, false, 1><<<nblocks, kThreads, 0, st>>>(a);
-  else if (batch == 1)
-    drr_pax_kernel<KERNEL_ID, true, 1><<<nblocks, kThreads, 0, st>>>(a);
+    drr_pax_kernel<KERNEL_ID, false, 1, 5><<<nblocks, kThreads, 0, st>>>(a);
+  else if (KERNEL_ID != XRC_KERNEL_SUM)
+    XRC_PAX_LAUNCH(1, 5);
+  else if (batch == 2)
+  {
+    if (minb == 3) XRC_PAX_LAUNCH(2, 3);
+    else XRC_PAX_LAUNCH(2, 4);
+  }
   else if (batch == 3)
-    drr_pax_kernel<KERNEL_ID, true, 4><<<nblocks, kThreads, 0, st>>>(a);
-  else
-    drr_pax_kernel<KERNEL_ID, true, 2><<<nblocks, kThreads, 0, st>>>(a);
+    XRC_PAX_LAUNCH(4, 3);
+  else  // default: one sample group in flight ahead, 5 CTAs (40 warps) per SM -- best or tied in every sweep case
+  {
+    if (minb == 4) XRC_PAX_LAUNCH(1, 4);
+    else XRC_PAX_LAUNCH(1, 5);
+  }
+#undef XRC_PAX_LAUNCH
   count_launch();
   XRC_CUDA(cudaGetLastError());
   return XRC_OK;
