@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(1024) gather(const T* __restrict__ base, const
   const long long t0 = clock64();
   for (int i = 0; i < ITERS; i += UNROLL)
   {
-    const uint32_t shift = (uint32_t)(i & 7) * 128u;
+    const uint32_t shift = (uint32_t)((i >> 3) & 7) * 128u;
     T v[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u)

@@ -1114,8 +1114,8 @@ int xrc_sm_allocate(xrc_sm* sm, uint32_t max_imgs)
       XRC_CUDA(cudaMalloc(&sm->d_psmask[d], grid1 * sizeof(double)));
     }
     XRC_CUDA(cudaMalloc(&sm->d_pnmask, grid1 * sizeof(float)));
-    const uint32_t W = patch_strip_width(r);
-    sm->n_strips = (sm->cols - 2 * r + W - 1) / W;
+    const PatchPlan pl = patch_plan(sm->rows, sm->cols, r);
+    sm->n_strips = pl.n_strips * pl.n_bands;  // partial sums per image and direction
     parts_per_img = (size_t)n_dirs * sm->n_strips;
     const uint64_t np = (uint64_t)((sm->rows - 1 - 2 * r) / sm->stride + 1) * ((sm->cols - 1 - 2 * r) / sm->stride + 1);
     XRC_CUDA(cudaMalloc(&sm->d_weights, np * sizeof(float)));
@@ -1278,7 +1278,7 @@ int xrc_sm_compute(xrc_sm* sm)
   f.partials = sm->d_partials;
   f.n_imgs = sm->n_imgs;
   f.n_dirs = n_dirs;
-  f.n_strips = sm->n_strips;
+  f.n_parts = sm->n_strips;
   f.divisor = sm->divisor;
   f.sims = sm->d_sims;
   return launch_patch_finalize(f, st);

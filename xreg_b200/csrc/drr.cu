@@ -848,6 +848,7 @@ __global__ void __launch_bounds__(kThreads) ray_info_kernel(const DrrArgs a)
   compute_proj_const(a, cam_s, a.poses + 12 * (size_t)proj, &pc);
   uint32_t row, col;
   thread_pixel(a, tile, row, col);
+  unsigned long long n = 0ull;
   if ((row < a.rows) && (col < a.cols))
   {
     const Ray ray = setup_ray(cam_s, pc, a.step_size, a.nx, a.ny, a.nz, row, col);
@@ -856,8 +857,15 @@ __global__ void __launch_bounds__(kThreads) ray_info_kernel(const DrrArgs a)
       a.ray_mask[o] = ray.hit ? 1 : 0;
     if (a.ray_steps)
       a.ray_steps[o] = ray.nsamples;
-    if (a.sample_counter && ray.nsamples)
-      atomicAdd(a.sample_counter, (unsigned long long)ray.nsamples);
+    n = ray.nsamples;
+  }
+  if (a.sample_counter)
+  {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+      n += __shfl_xor_sync(0xffffffffu, n, o);
+    if ((threadIdx.x & 31) == 0 && n)
+      atomicAdd(a.sample_counter, n);
   }
 }
 

@@ -22,12 +22,31 @@ __device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b)
 
 __device__ __forceinline__ int reflect101(int i, int n)
 {
+  if ((unsigned)i < (unsigned)n)  // interior: the common case
+    return i;
   if (n == 1)
     return 0;
   while (i < 0 || i >= n)
     i = (i < 0) ? -i : (2 * (n - 1) - i);
   return i;
 }
+
+// (row, col) of flat index i in a window `w` columns wide, advanced by the CTA size without div / mod
+struct WinIdx
+{
+  int r, c, dr, dc, w;
+  __device__ WinIdx(int i, int stride, int w_) : r(i / w_), c(i % w_), dr(stride / w_), dc(stride % w_), w(w_) {}
+  __device__ __forceinline__ void next()
+  {
+    r += dr;
+    c += dc;
+    if (c >= w)
+    {
+      c -= w;
+      ++r;
+    }
+  }
+};
 
 __device__ __forceinline__ double warp_sum(double v)
 {
@@ -98,9 +117,10 @@ __global__ void __launch_bounds__(256) grad_kernel(const GradArgs a)
   {
     const int hr0 = max(r0 - 1 - h, 0), hr1 = min(r0 + T + h, rows - 1);
     const int hh = hr1 - hr0 + 1;
-    for (int i = threadIdx.x; i < hh * bw; i += blockDim.x)
+    WinIdx wa(threadIdx.x, blockDim.x, bw);
+    for (int i = threadIdx.x; i < hh * bw; i += blockDim.x, wa.next())
     {
-      const int r = hr0 + i / bw, c = bc0 + i % bw;
+      const int r = hr0 + wa.r, c = bc0 + wa.c;
       const float* __restrict__ row = src + (size_t)r * cols;
       float s = fmul(cf[h], __ldg(row + c));
       for (int j = 1; j <= h; ++j)
@@ -108,9 +128,10 @@ __global__ void __launch_bounds__(256) grad_kernel(const GradArgs a)
       Hs[i] = s;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < bh * bw; i += blockDim.x)
+    WinIdx wb(threadIdx.x, blockDim.x, bw);
+    for (int i = threadIdx.x; i < bh * bw; i += blockDim.x, wb.next())
     {
-      const int r = br0 + i / bw, cc = i % bw;
+      const int r = br0 + wb.r, cc = wb.c;
       float s = fmul(cf[h], Hs[(r - hr0) * bw + cc]);
       for (int j = 1; j <= h; ++j)
         s = fadd(s, fmul(cf[h + j], fadd(Hs[(reflect101(r - j, rows) - hr0) * bw + cc],
@@ -120,8 +141,9 @@ __global__ void __launch_bounds__(256) grad_kernel(const GradArgs a)
   }
   else
   {
-    for (int i = threadIdx.x; i < bh * bw; i += blockDim.x)
-      Bs[i] = __ldg(src + (size_t)(br0 + i / bw) * cols + bc0 + i % bw);
+    WinIdx wc(threadIdx.x, blockDim.x, bw);
+    for (int i = threadIdx.x; i < bh * bw; i += blockDim.x, wc.next())
+      Bs[i] = __ldg(src + (size_t)(br0 + wc.r) * cols + bc0 + wc.c);
   }
   __syncthreads();
 
@@ -392,154 +414,259 @@ __device__ __forceinline__ void stats_from_sums(double S, double SS, double cnt,
   sd = fmaxf(1.0e-6f, (float)sqrt(var));
 }
 
-template <int MODE, bool FIXED>
+// Box sums by running sums in BOTH directions (O(1) per pixel and quantity):
+//   * vertical: thread t owns C adjacent input columns of its strip and keeps, per
+//     quantity, the running sum V of the last d rows (add the row entering the window,
+//     subtract the row leaving it), f64;
+//   * horizontal: per output row, an exclusive prefix sum P of V across the strip
+//     (C-element local prefix, warp shuffle scan, warp totals through shared memory)
+//     is published in shared memory and the d-column window sum is P[j + d] - P[j]:
+//     one shared-memory read per output and quantity instead of d.
+// One CTA = (row band, column strip, image, direction); a band first accumulates the
+// d-1 rows above its first window (loads only), so bands give the grid enough CTAs
+// without repeating the horizontal work.  Loads of the next row are issued before the
+// scan of the current one.
+template <int MODE, bool FIXED, int C>
 __global__ void __launch_bounds__(kPatchThreads) patch_kernel(const PatchArgs a)
 {
   constexpr int NQ = PatchQ<MODE, FIXED>::N;
-  __shared__ double sh[2][NQ][kPatchThreads];
+  constexpr int NT = kPatchThreads;
+  constexpr int NW = NT / 32;
+  // exclusive prefix at local column j = C * t + i is stored at Pex[buf][q][i][t]; local columns run to C * NT (incl.)
+  __shared__ double Pex[2][NQ][C][NT + 1];
+  __shared__ double wtot[2][NQ][NW];
   __shared__ double red[8];
 
   const int rows = (int)a.rows, cols = (int)a.cols;
   const int r = (int)a.radius, d = 2 * r + 1;
-  const int W = kPatchThreads - 2 * r;
-  const int strip = blockIdx.x, img = blockIdx.y, dir = blockIdx.z;
-  const int t = threadIdx.x;
-  const int c = strip * W + t;  // input column == top-left column of "my" patch
-  const bool col_ok = c < cols;
-  const int ncc_all = cols - 2 * r;  // stride-1 centre columns
+  const int W_out = C * NT - 2 * r;
+  const int strip = blockIdx.x % a.n_strips, band = blockIdx.x / a.n_strips;
+  const int img = blockIdx.y, dir = blockIdx.z;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int c0 = strip * W_out;            // first input column == first stride-1 centre column of the strip
+  const int ncc_all = cols - 2 * r;        // stride-1 centre columns
+  const int nrr_all = rows - 2 * r;        // stride-1 centre rows
   const int st = (int)a.stride;
-  const int ncc_s = (ncc_all - 1) / st + 1;  // strided centre columns
-  const bool centre_ok = (t < W) && (c < ncc_all) && (c % st == 0);
+  const int ncc_s = (ncc_all - 1) / st + 1;
   const size_t npix = (size_t)rows * cols;
+  const int i_begin = band * kPatchBandRows, i_end = min(i_begin + kPatchBandRows, nrr_all);
 
   const float* __restrict__ m = FIXED ? nullptr : (a.mov[dir] + (size_t)img * npix);
   const float* __restrict__ f = a.fix[dir];
   const uint8_t* __restrict__ mask = a.mask;
   const double n_full = (double)d * (double)d;
+  const double inv_n = 1.0 / n_full, inv_nm1 = 1.0 / (n_full - 1.0);
 
-  double V[NQ];
+  bool col_ok[C];
 #pragma unroll
-  for (int k = 0; k < NQ; ++k)
-    V[k] = 0.0;
-  double total = 0.0;
+  for (int i = 0; i < C; ++i)
+    col_ok[i] = (c0 + C * t + i) < cols;
 
-  for (int y = 0; y < rows; ++y)
+  struct RowVals
   {
-    if (col_ok)
+    float mv[C], fv[C], Mv[C];
+  };
+  auto load_row = [&](int y, RowVals& v) {
+#pragma unroll
+    for (int i = 0; i < C; ++i)
     {
-      double q[NQ];
-      const size_t o = (size_t)y * cols + c;
-      const double fv = (double)__ldg(f + o);
-      const double mv = FIXED ? 0.0 : (double)__ldg(m + o);
-      const double M = (MODE != 0) ? (mask[o] ? 1.0 : 0.0) : 1.0;
-      patch_quantities<MODE, FIXED>(mv, fv, M, q);
-#pragma unroll
-      for (int k = 0; k < NQ; ++k)
-        V[k] += q[k];
-      if (y >= d)
+      v.mv[i] = 0.f;
+      v.fv[i] = 0.f;
+      v.Mv[i] = 0.f;
+      if (col_ok[i] && y < rows)
       {
-        const size_t o2 = (size_t)(y - d) * cols + c;
-        const double fv2 = (double)__ldg(f + o2);
-        const double mv2 = FIXED ? 0.0 : (double)__ldg(m + o2);
-        const double M2 = (MODE != 0) ? (mask[o2] ? 1.0 : 0.0) : 1.0;
-        patch_quantities<MODE, FIXED>(mv2, fv2, M2, q);
-#pragma unroll
-        for (int k = 0; k < NQ; ++k)
-          V[k] -= q[k];
+        const size_t o = (size_t)y * cols + c0 + C * t + i;
+        v.fv[i] = __ldg(f + o);
+        if (!FIXED)
+          v.mv[i] = __ldg(m + o);
+        v.Mv[i] = (MODE != 0) ? (mask[o] ? 1.f : 0.f) : 1.f;
       }
     }
-    if (y >= d - 1)
+  };
+
+  double V[C][NQ];
+#pragma unroll
+  for (int i = 0; i < C; ++i)
+#pragma unroll
+    for (int k = 0; k < NQ; ++k)
+      V[i][k] = 0.0;
+  auto accumulate = [&](const RowVals& v, double sign) {
+#pragma unroll
+    for (int i = 0; i < C; ++i)
     {
-      const int i = y - (d - 1);  // top row of the window == stride-1 centre row index
-      const int buf = y & 1;
+      double q[NQ];
+      patch_quantities<MODE, FIXED>((double)v.mv[i], (double)v.fv[i], (double)v.Mv[i], q);
 #pragma unroll
       for (int k = 0; k < NQ; ++k)
-        sh[buf][k][t] = V[k];
-      __syncthreads();
-      if (centre_ok && (i % st == 0))
-      {
-        double S[NQ];
+        V[i][k] += sign * q[k];
+    }
+  };
+
+  // rows above the first window of the band
+  for (int y = i_begin; y < i_begin + d - 1; ++y)
+  {
+    RowVals v;
+    load_row(y, v);
+    accumulate(v, 1.0);
+  }
+
+  double total = 0.0;
+  RowVals v_new, v_old;
+  load_row(i_begin + d - 1, v_new);
+  load_row(i_begin, v_old);
+  for (int i = i_begin; i < i_end; ++i)
+  {
+    const int buf = i & 1;
+    accumulate(v_new, 1.0);  // window rows i .. i + d - 1 complete
+    // local inclusive prefix over my C columns, then exclusive scan of the block totals
+    double L[C][NQ];
 #pragma unroll
-        for (int k = 0; k < NQ; ++k)
-          S[k] = 0.0;
-        for (int u = 0; u < d; ++u)
+    for (int k = 0; k < NQ; ++k)
+    {
+      L[0][k] = V[0][k];
+#pragma unroll
+      for (int c = 1; c < C; ++c)
+        L[c][k] = L[c - 1][k] + V[c][k];
+    }
+    double incl[NQ];
+#pragma unroll
+    for (int k = 0; k < NQ; ++k)
+    {
+      double x = L[C - 1][k];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1)
+      {
+        const double y2 = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o)
+          x += y2;
+      }
+      incl[k] = x;
+      if (lane == 31)
+        wtot[buf][k][warp] = x;
+    }
+    // subtract the row that leaves the window and prefetch the next rows while the scan settles
+    accumulate(v_old, -1.0);
+    RowVals n_new, n_old;
+    if (i + 1 < i_end)
+    {
+      load_row(i + d, n_new);
+      load_row(i + 1, n_old);
+    }
+    __syncthreads();
+    double ex[NQ];  // exclusive prefix of my first column
+#pragma unroll
+    for (int k = 0; k < NQ; ++k)
+    {
+      double off = 0.0;
+      for (int w = 0; w < warp; ++w)
+        off += wtot[buf][k][w];
+      ex[k] = off + (incl[k] - L[C - 1][k]);
+      Pex[buf][k][0][t] = ex[k];
+#pragma unroll
+      for (int c = 1; c < C; ++c)
+        Pex[buf][k][c][t] = ex[k] + L[c - 1][k];
+      if (t == NT - 1)
+        Pex[buf][k][0][NT] = ex[k] + L[C - 1][k];  // local column C * NT
+    }
+    __syncthreads();
+    if (i % st == 0 || FIXED)
+    {
+#pragma unroll
+      for (int cc = 0; cc < C; ++cc)
+      {
+        const int j = C * t + cc;  // local column == patch's left column
+        const int c = c0 + j;
+        if (j < W_out && c < ncc_all && (FIXED || c % st == 0))
         {
+          double S[NQ];
 #pragma unroll
           for (int k = 0; k < NQ; ++k)
-            S[k] += sh[buf][k][t + u];
-        }
-        const size_t pa = (size_t)i * ncc_all + c;  // index on the stride-1 grid
-        if (FIXED)
-        {
-          float mean, sd;
-          double mean_d;
-          if (MODE == 0)
           {
-            stats_from_sums(S[0], S[1], n_full, mean, sd, &mean_d);
-            a.o_mean[dir][pa] = mean_d;
-            a.o_den[dir][pa] = sd * (float)n_full;
+            const int je = j + d;
+            const double lo = (cc == 0) ? ex[k] : (ex[k] + L[cc - 1][k]);
+            S[k] = Pex[buf][k][je % C][je / C] - lo;
           }
-          else if (MODE == 1)
+          const size_t pa = (size_t)i * ncc_all + c;  // index on the stride-1 grid
+          if (FIXED)
           {
-            stats_from_sums(S[0], S[1], n_full, mean, sd, &mean_d);
-            a.o_mean[dir][pa] = mean_d;
-            a.o_den[dir][pa] = sd * (float)n_full;
-            a.o_smask[dir][pa] = S[2];
-            if (dir == 0)
-              a.o_nmask[pa] = (float)S[3];
-          }
-          else
-          {
-            stats_from_sums(S[0], S[1], S[2], mean, sd, &mean_d);
-            a.o_mean[dir][pa] = mean_d;
-            a.o_den[dir][pa] = sd * (float)S[2];
-            a.o_smask[dir][pa] = S[0];
-            if (dir == 0)
-              a.o_nmask[pa] = (float)S[2];
-          }
-        }
-        else
-        {
-          const size_t pk = (size_t)(i / st) * ncc_s + (c / st);  // strided patch index
-          const float w = a.weights ? __ldg(a.weights + pk) : 1.0f;
-          if (!a.weight_patch_sims || (fabsf(w) > 1.0e-6f))
-          {
-            float mu_m, sd_m;
-            double num, mu_md;
-            const double mu_f = __ldg(a.f_mean[dir] + pa);
-            const float den_f = __ldg(a.f_den[dir] + pa);
+            float mean, sd;
+            double mean_d;
             if (MODE == 0)
             {
-              stats_from_sums(S[0], S[1], n_full, mu_m, sd_m, &mu_md);
-              // sum (m - mu_m)(f - mu_f) = Smf - mu_f Sm   (sum (f - mu_f) = 0)
-              num = S[2] - mu_f * S[0];
+              stats_from_sums(S[0], S[1], n_full, mean, sd, &mean_d);
+              a.o_mean[dir][pa] = mean_d;
+              a.o_den[dir][pa] = sd * (float)n_full;
+            }
+            else if (MODE == 1)
+            {
+              stats_from_sums(S[0], S[1], n_full, mean, sd, &mean_d);
+              a.o_mean[dir][pa] = mean_d;
+              a.o_den[dir][pa] = sd * (float)n_full;
+              a.o_smask[dir][pa] = S[2];
+              if (dir == 0)
+                a.o_nmask[pa] = (float)S[3];
             }
             else
             {
-              const double nM = (double)__ldg(a.n_mask + pa);
-              const double SfM = __ldg(a.f_smask[dir] + pa);
-              double SmM, SmfM;
-              if (MODE == 1)
+              stats_from_sums(S[0], S[1], S[2], mean, sd, &mean_d);
+              a.o_mean[dir][pa] = mean_d;
+              a.o_den[dir][pa] = sd * (float)S[2];
+              a.o_smask[dir][pa] = S[0];
+              if (dir == 0)
+                a.o_nmask[pa] = (float)S[2];
+            }
+          }
+          else
+          {
+            const size_t pk = (size_t)(i / st) * ncc_s + (c / st);  // strided patch index
+            const float w = a.weights ? __ldg(a.weights + pk) : 1.0f;
+            if (!a.weight_patch_sims || (fabsf(w) > 1.0e-6f))
+            {
+              float sd_m;
+              double num;
+              const double mu_f = __ldg(a.f_mean[dir] + pa);
+              const float den_f = __ldg(a.f_den[dir] + pa);
+              if (MODE == 0)
               {
-                stats_from_sums(S[0], S[1], n_full, mu_m, sd_m, &mu_md);
-                SmM = S[2];
-                SmfM = S[3];
+                // mean / unbiased variance from raw moments; reciprocals of the constant counts
+                const double mu = S[0] * inv_n;
+                double var = (S[1] - S[0] * mu) * inv_nm1;
+                if (!(var > 0.0))
+                  var = 0.0;
+                sd_m = fmaxf(1.0e-6f, sqrtf((float)var));
+                // sum (m - mu_m)(f - mu_f) = Smf - mu_f Sm   (sum (f - mu_f) = 0)
+                num = S[2] - mu_f * S[0];
               }
               else
               {
-                stats_from_sums(S[0], S[1], nM, mu_m, sd_m, &mu_md);
-                SmM = S[0];
-                SmfM = S[2];
+                const double nM = (double)__ldg(a.n_mask + pa);
+                const double SfM = __ldg(a.f_smask[dir] + pa);
+                double SmM, SmfM, mu_md;
+                float mu_m;
+                if (MODE == 1)
+                {
+                  stats_from_sums(S[0], S[1], n_full, mu_m, sd_m, &mu_md);
+                  SmM = S[2];
+                  SmfM = S[3];
+                }
+                else
+                {
+                  stats_from_sums(S[0], S[1], nM, mu_m, sd_m, &mu_md);
+                  SmM = S[0];
+                  SmfM = S[2];
+                }
+                num = SmfM - mu_f * SmM - mu_md * SfM + mu_md * mu_f * nM;
               }
-              num = SmfM - mu_f * SmM - mu_md * SfM + mu_md * mu_f * nM;
+              const float accv = (den_f != 0.0f) ? ((float)num / (sd_m * den_f)) : 0.0f;
+              const float sv = 1.0f - accv;
+              total += (double)((a.weight_patch_sims ? w : 1.0f) * sv);
             }
-            const float accv = (den_f != 0.0f) ? ((float)num / (sd_m * den_f)) : 0.0f;
-            const float s = 1.0f - accv;
-            total += (double)((a.weight_patch_sims ? w : 1.0f) * s);
           }
         }
       }
     }
+    v_new = n_new;
+    v_old = n_old;
   }
   if (!FIXED)
   {
@@ -547,27 +674,37 @@ __global__ void __launch_bounds__(kPatchThreads) patch_kernel(const PatchArgs a)
     __syncthreads();
     block_sum<1>(v, red);
     if (t == 0)
-      a.partials[((size_t)img * a.n_dirs + dir) * a.n_strips + strip] = v[0];
+      a.partials[((size_t)img * a.n_dirs + dir) * a.n_parts + blockIdx.x] = v[0];
   }
 }
 
-template <bool FIXED>
-static int launch_patch_impl(const PatchArgs& a, cudaStream_t st)
+template <bool FIXED, int C>
+static int launch_patch_c(const PatchArgs& a, cudaStream_t st)
 {
   const uint32_t n_imgs = FIXED ? 1 : a.n_imgs;
-  if (!n_imgs)
-    return XRC_OK;
-  const dim3 grid(a.n_strips, n_imgs, a.n_dirs);
+  const dim3 grid(a.n_parts, n_imgs, a.n_dirs);
   switch (a.mask_mode)
   {
-    case 0: patch_kernel<0, FIXED><<<grid, kPatchThreads, 0, st>>>(a); break;
-    case 1: patch_kernel<1, FIXED><<<grid, kPatchThreads, 0, st>>>(a); break;
-    case 2: patch_kernel<2, FIXED><<<grid, kPatchThreads, 0, st>>>(a); break;
+    case 0: patch_kernel<0, FIXED, C><<<grid, kPatchThreads, 0, st>>>(a); break;
+    case 1: patch_kernel<1, FIXED, C><<<grid, kPatchThreads, 0, st>>>(a); break;
+    case 2: patch_kernel<2, FIXED, C><<<grid, kPatchThreads, 0, st>>>(a); break;
     default: XRC_FAIL(XRC_ERR_INVALID, "bad patch mask mode");
   }
   count_launch();
   XRC_CUDA(cudaGetLastError());
   return XRC_OK;
+}
+
+template <bool FIXED>
+static int launch_patch_impl(const PatchArgs& a_in, cudaStream_t st)
+{
+  PatchArgs a = a_in;
+  if (!(FIXED ? 1u : a.n_imgs))
+    return XRC_OK;
+  const PatchPlan pl = patch_plan(a.rows, a.cols, a.radius);
+  a.n_strips = pl.n_strips;
+  a.n_parts = pl.n_strips * pl.n_bands;
+  return (pl.cols_per_thread == 2) ? launch_patch_c<FIXED, 2>(a, st) : launch_patch_c<FIXED, 1>(a, st);
 }
 
 int launch_patch(const PatchArgs& a, cudaStream_t st) { return launch_patch_impl<false>(a, st); }
@@ -584,8 +721,8 @@ __global__ void patch_finalize_kernel(const PatchFinalizeArgs a)
   for (uint32_t d = 0; d < a.n_dirs; ++d)
   {
     double s = 0.0;
-    const double* p = a.partials + ((size_t)img * a.n_dirs + d) * a.n_strips;
-    for (uint32_t k = 0; k < a.n_strips; ++k)
+    const double* p = a.partials + ((size_t)img * a.n_dirs + d) * a.n_parts;
+    for (uint32_t k = 0; k < a.n_parts; ++k)
       s += p[k];
     sd[d] = (float)(s / a.divisor);
   }

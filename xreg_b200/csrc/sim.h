@@ -8,7 +8,8 @@ namespace xrc
 
 constexpr int kGradTile = 32;       // output tile edge of the gradient kernel
 constexpr int kMaxGaussWidth = 31;  // widest supported smoothing kernel
-constexpr int kPatchThreads = 256;  // strip width (input columns) of the patch kernel
+constexpr int kPatchThreads = 256;  // threads per CTA of the patch kernel (each owns 1 or 2 input columns)
+constexpr int kPatchBandRows = 64;  // patch rows per CTA
 constexpr int kMomChunk = 4096;     // pixels per CTA of the plain moments kernel
 
 struct GradArgs
@@ -56,7 +57,7 @@ struct PatchArgs
   const uint8_t* mask;     // rows x cols or null
   uint32_t n_imgs, n_dirs, rows, cols;
   uint32_t radius, stride;
-  uint32_t n_strips;
+  uint32_t n_strips, n_parts;  // filled by the launcher from patch_plan(); n_parts = n_strips * n_bands
   int mask_mode;           // 0 none, 1 mask in correlation only, 2 mask in stats too
   // fixed per-patch statistics on the stride-1 grid (rows-2r) x (cols-2r), per direction
   const double* f_mean[2];  // f64: keeps sum(m - mu_m)(f - mu_f) = Smf - mu_f Sm free of f32 rounding of mu_f
@@ -65,7 +66,7 @@ struct PatchArgs
   const float* n_mask;     // mask count per patch (mask modes)
   const float* weights;    // per strided patch or null
   int weight_patch_sims;
-  double* partials;        // n_imgs x n_dirs x n_strips
+  double* partials;        // n_imgs x n_dirs x n_parts
   // fixed-stats mode outputs (when mov[0] == nullptr)
   double* o_mean[2];
   float* o_den[2];
@@ -76,7 +77,7 @@ struct PatchArgs
 struct PatchFinalizeArgs
 {
   const double* partials;
-  uint32_t n_imgs, n_dirs, n_strips;
+  uint32_t n_imgs, n_dirs, n_parts;
   double divisor;  // num_patches (mean), total weight, or 1
   float* sims;
 };
@@ -88,6 +89,19 @@ int launch_patch(const PatchArgs& a, cudaStream_t st);
 int launch_patch_fixed_stats(const PatchArgs& a, cudaStream_t st);
 int launch_patch_finalize(const PatchFinalizeArgs& a, cudaStream_t st);
 
-inline uint32_t patch_strip_width(uint32_t radius) { return kPatchThreads - 2 * radius; }
+// decomposition of the patch grid into CTAs (column strips x row bands)
+struct PatchPlan
+{
+  uint32_t cols_per_thread, n_strips, n_bands;
+};
+inline PatchPlan patch_plan(uint32_t rows, uint32_t cols, uint32_t radius)
+{
+  PatchPlan p;
+  p.cols_per_thread = (cols > (uint32_t)kPatchThreads) ? 2u : 1u;
+  const uint32_t w_out = p.cols_per_thread * kPatchThreads - 2 * radius;
+  p.n_strips = (cols - 2 * radius + w_out - 1) / w_out;
+  p.n_bands = (rows - 2 * radius + kPatchBandRows - 1) / kPatchBandRows;
+  return p;
+}
 
 }  // namespace xrc
