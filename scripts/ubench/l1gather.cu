@@ -9,6 +9,10 @@
 constexpr int ITERS = 2048;
 constexpr int UNROLL = 8;
 
+__device__ __forceinline__ float total(float v) { return v; }
+__device__ __forceinline__ float total(float2 v) { return v.x + v.y; }
+__device__ __forceinline__ float total(float4 v) { return (v.x + v.y) + (v.z + v.w); }
+
 template <typename T>
 __global__ void __launch_bounds__(1024) gather(const T* __restrict__ base, const uint32_t* __restrict__ offs, int nsets,
                                                float* out, long long* clk)
@@ -31,7 +35,7 @@ __global__ void __launch_bounds__(1024) gather(const T* __restrict__ base, const
       v[u] = __ldg(base + ((o[u] + shift) & 2047u));
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u)
-      acc += *reinterpret_cast<float*>(&v[u]);
+      acc += total(v[u]);
   }
   const long long t1 = clock64();
   out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
