@@ -75,6 +75,27 @@ def make_camera(det_size: int, full_size: int = 1536, sdd: float = 1020.0, pixel
     return downsample_camera_model(cam, det_size / float(full_size))
 
 
+def multi_view_cameras(det_size: int, angles_deg: Sequence[float], src_to_iso: float = 650.0) -> list:
+    """Cameras of a multi-view acquisition: the C-arm of make_camera()
+    rotated by each angle about the axis through the isocentre that is parallel to the volume's
+    long axis in the nominal pose (the camera frame's y axis).  View 0 (angle 0) has identity
+    extrinsics; all share the world frame of view 0, as in the reference's multi-view apps."""
+    base = make_camera(det_size)
+    iso = np.array([0.0, 0.0, -src_to_iso])
+    cams = []
+    for ang in angles_deg:
+        E = np.eye(4)
+        if ang != 0.0:
+            C, Ci = np.eye(4), np.eye(4)
+            C[:3, 3], Ci[:3, 3] = iso, -iso
+            E = C @ rot_about_axis(1, ang) @ Ci
+        cam = CameraModel(coord_frame_type=base.coord_frame_type)
+        cam.setup_intrins_extrins(base.intrins, E.astype(f32), base.num_det_rows, base.num_det_cols,
+                                  base.det_row_spacing, base.det_col_spacing)
+        cams.append(cam)
+    return cams
+
+
 def rot_about_axis(axis: int, deg: float) -> np.ndarray:
     a = np.deg2rad(deg)
     c, s = np.cos(a), np.sin(a)
