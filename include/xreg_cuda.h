@@ -71,7 +71,9 @@ enum { XRC_STORE_REPLACE = 0, XRC_STORE_ACCUM = 1 };
 enum { XRC_KERNEL_SUM = 0, XRC_KERNEL_MAX = 1 };
 /* Metric kinds: ImgSimMetric2D{NCC,GradNCC,PatchNCC,PatchGradNCC}CPU/OCL */
 enum { XRC_SM_NCC = 0, XRC_SM_GRAD_NCC = 1, XRC_SM_PATCH_NCC = 2, XRC_SM_PATCH_GRAD_NCC = 3 };
-/* Volume layouts in HBM (DESIGN.md "Data layout").  Results are identical for all. */
+/* Volume layouts in HBM (DESIGN.md "Data layout").  All fetch exact f32 voxels and take the same samples;
+ * LINEAR..TEX lerp x, y, z and agree bit for bit, PAX (the default: one padded XY-quad stack per principal
+ * ray axis) lerps mid axis, slow axis, fast axis and differs from them in the last ulp only. */
 enum { XRC_LAYOUT_DEFAULT = -1, XRC_LAYOUT_LINEAR = 0, XRC_LAYOUT_QUAD = 1, XRC_LAYOUT_TEX_QUAD = 2,
        XRC_LAYOUT_OCT = 3, XRC_LAYOUT_TEX = 4, XRC_LAYOUT_PAX = 5 };
 
