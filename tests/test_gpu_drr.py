@@ -73,7 +73,7 @@ def test_layouts_agree_bitwise(ctx, small_scene):
 
 
 @pytest.mark.parametrize("view_deg,axis", [(0.0, "y"), (90.0, "x"), (35.0, "y/x"), (55.0, "x/y")])
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])  # bit0: scalar FP32 instead of f32x2; bit1: force the clamped loop
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])  # bit0: packed f32x2 instead of scalar FP32; bit1: force the clamped loop
 def test_pax_every_stack_and_variant(ctx, xo, view_deg, axis, variant):
     """Every principal-axis stack (rays along y, x and oblique; a tilted C-arm for z), packed and
     scalar arithmetic, fast and clamped marching loops: all must match the oracle."""

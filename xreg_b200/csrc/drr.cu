@@ -497,6 +497,25 @@ struct PaxStack
   float ha, hb, hc;
 };
 
+// &base[rec] without touching the FMA pipe: the compiler's choice for base + rec * 16 is IMAD.WIDE, which
+// competes with the lerps for the pipe that bounds the loop once the loads hit L1; LEA + LEA.HI.X run on the ALU pipe.
+__device__ __forceinline__ float4 pax_load(const float4* __restrict__ base, uint32_t rec)
+{
+  unsigned long long addr;
+  asm("{\n\t"
+      ".reg .u32 blo, bhi, alo, ahi;\n\t"
+      "mov.b64 {blo, bhi}, %1;\n\t"
+      "shf.l.wrap.b32 ahi, %2, 0, 4;\n\t"
+      "shl.b32 alo, %2, 4;\n\t"
+      "add.cc.u32 alo, alo, blo;\n\t"
+      "addc.u32 ahi, ahi, bhi;\n\t"
+      "mov.b64 %0, {alo, ahi};\n\t"
+      "}"
+      : "=l"(addr)
+      : "l"(base), "r"(rec));
+  return __ldg(reinterpret_cast<const float4*>(addr));
+}
+
 // record index + interpolation weights of one sample
 template <bool PACK, bool CLAMP>
 __device__ __forceinline__ void pax_cell(const PaxStack& st, float xa, float xb, float xc, uint32_t& rec, float& wa,
@@ -530,21 +549,17 @@ __device__ __forceinline__ void pax_cell(const PaxStack& st, float xa, float xb,
   }
 }
 
-// q0 = plane c, q1 = plane c+1, each {v(a,b), v(a+1,b), v(a,b+1), v(a+1,b+1)}
+// q0 = plane c, q1 = plane c+1, each in difference form {v00, dA, dB, dAB}:
+//   dA = v10 - v00, dB = v01 - v00, dAB = v11 - v10 - v01 + v00   (computed in f64, rounded once, at repack time)
+// so that the bilinear value of a plane is v00 + wa dA + wb (dB + wa dAB): 3 FMAs instead of 3 lerps (6 ops);
+// with the c-lerp a sample costs 8 FP32 operations instead of 14.  Each coefficient carries <= 1/2 ulp of its
+// own magnitude, the value <= ~1.5 ulp(max |v|): the same order as the rounding of the f32 lerp chain itself.
 template <bool PACK>
 __device__ __forceinline__ float pax_lerp(const float4& q0, const float4& q1, float wa, float wb, float wc)
 {
-  if (PACK)
-  {
-    // lerp along b and c on (a, a+1) pairs, then along a
-    const float2 l0 = mk2(q0.x, q0.y), h0 = mk2(q0.z, q0.w), l1 = mk2(q1.x, q1.y), h1 = mk2(q1.z, q1.w);
-    const float2 wb2 = mk2(wb, wb), wc2 = mk2(wc, wc);
-    const float2 r0 = __ffma2_rn(wb2, __fadd2_rn(h0, mk2(-l0.x, -l0.y)), l0);
-    const float2 r1 = __ffma2_rn(wb2, __fadd2_rn(h1, mk2(-l1.x, -l1.y)), l1);
-    const float2 rr = __ffma2_rn(wc2, __fadd2_rn(r1, mk2(-r0.x, -r0.y)), r0);
-    return fmaf(wa, rr.y - rr.x, rr.x);
-  }
-  return trilerp(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, wa, wb, wc);
+  const float p0 = fmaf(wa, fmaf(wb, q0.w, q0.y), fmaf(wb, q0.z, q0.x));
+  const float p1 = fmaf(wa, fmaf(wb, q1.w, q1.y), fmaf(wb, q1.z, q1.x));
+  return fmaf(wc, p1 - p0, p0);
 }
 
 template <bool PACK>
@@ -586,8 +601,8 @@ __device__ __forceinline__ float pax_march(const PaxStack& st, float pa, float p
     {
       uint32_t rec;
       pax_cell<PACK, CLAMP>(st, pa, pb, pc, rec, wa[j], wb[j], wc[j]);
-      q0[j] = __ldg(st.base + rec);
-      q1[j] = __ldg(st.base + (rec + st.Sc));
+      q0[j] = pax_load(st.base, rec);
+      q1[j] = pax_load(st.base, rec + st.Sc);
       pax_advance<PACK>(pa, pb, pc, sa, sb, sc);
     }
 #pragma unroll 2
@@ -600,8 +615,8 @@ __device__ __forceinline__ float pax_march(const PaxStack& st, float pa, float p
       {
         uint32_t rec;
         pax_cell<PACK, CLAMP>(st, pa, pb, pc, rec, nwa[j], nwb[j], nwc[j]);
-        n0[j] = __ldg(st.base + rec);
-        n1[j] = __ldg(st.base + (rec + st.Sc));
+        n0[j] = pax_load(st.base, rec);
+        n1[j] = pax_load(st.base, rec + st.Sc);
         pax_advance<PACK>(pa, pb, pc, sa, sb, sc);
       }
 #pragma unroll
@@ -628,8 +643,8 @@ __device__ __forceinline__ float pax_march(const PaxStack& st, float pa, float p
     uint32_t rec;
     float wa, wb, wc;
     pax_cell<PACK, CLAMP>(st, pa, pb, pc, rec, wa, wb, wc);
-    const float4 q0 = __ldg(st.base + rec);
-    const float4 q1 = __ldg(st.base + (rec + st.Sc));
+    const float4 q0 = pax_load(st.base, rec);
+    const float4 q1 = pax_load(st.base, rec + st.Sc);
     const float v = pax_lerp<PACK>(q0, q1, wa, wb, wc);
     sum = (KERNEL_ID == XRC_KERNEL_MAX) ? fmaxf(sum, v) : __fadd_rn(sum, v);
     pax_advance<PACK>(pa, pb, pc, sa, sb, sc);
@@ -797,16 +812,18 @@ template <int KERNEL_ID>
 static int launch_pax_k(const DrrArgs& a, cudaStream_t st)
 {
   const uint32_t nblocks = a.n_projs * a.tiles_x * a.tiles_y;
-  // variant (measurement only): bit0 scalar FP32, bit1 force clamped loop, bits 2-3 batch id, bit4 no lane swap,
+  // variant (measurement only): bit0 packed f32x2 position / floor arithmetic, bit1 force clamped loop, bits 2-3 batch id, bit4 no lane swap,
   // bits 5-7 min CTAs per SM (register budget)
-  const bool scalar = (a.variant & 1) != 0;
+  const bool packed = (a.variant & 1) != 0;
   const int batch = (a.variant >> 2) & 3;
   const int minb = (a.variant >> 5) & 7;
 #define XRC_PAX_LAUNCH(B, M) drr_pax_kernel<KERNEL_ID, true, B, M><<<nblocks, kThreads, 0, st>>>(a)
-  if (scalar)
+  if (KERNEL_ID != XRC_KERNEL_SUM)
     drr_pax_kernel<KERNEL_ID, false, 1, 5><<<nblocks, kThreads, 0, st>>>(a);
-  else if (KERNEL_ID != XRC_KERNEL_SUM)
-    XRC_PAX_LAUNCH(1, 5);
+  else if (!packed)
+    // default: scalar FP32 (FFMA / FADD issue to both FMA pipes; the packed f32x2 forms save issue slots the
+    // loop does not need and measured 1 % slower), one sample group in flight ahead, 5 CTAs (40 warps) per SM
+    drr_pax_kernel<KERNEL_ID, false, 1, 5><<<nblocks, kThreads, 0, st>>>(a);
   else if (batch == 2)
   {
     if (minb == 3) XRC_PAX_LAUNCH(2, 3);
@@ -814,7 +831,7 @@ static int launch_pax_k(const DrrArgs& a, cudaStream_t st)
   }
   else if (batch == 3)
     XRC_PAX_LAUNCH(4, 3);
-  else  // default: one sample group in flight ahead, 5 CTAs (40 warps) per SM -- best or tied in every sweep case
+  else
   {
     if (minb == 4) XRC_PAX_LAUNCH(1, 4);
     else XRC_PAX_LAUNCH(1, 5);
@@ -978,8 +995,9 @@ __global__ void repack_pax_kernel(const float* __restrict__ src, float4* __restr
     const int b0 = min(max(ib, 0), n[kb] - 1), b1 = min(max(ib + 1, 0), n[kb] - 1);
     const int c0 = min(max(ic, 0), n[k] - 1);
     const float* p = src + (size_t)c0 * st[k];
-    dst[i] = make_float4(p[a0 * st[ka] + b0 * st[kb]], p[a1 * st[ka] + b0 * st[kb]], p[a0 * st[ka] + b1 * st[kb]],
-                         p[a1 * st[ka] + b1 * st[kb]]);
+    const double v00 = p[a0 * st[ka] + b0 * st[kb]], v10 = p[a1 * st[ka] + b0 * st[kb]];
+    const double v01 = p[a0 * st[ka] + b1 * st[kb]], v11 = p[a1 * st[ka] + b1 * st[kb]];
+    dst[i] = make_float4((float)v00, (float)(v10 - v00), (float)(v01 - v00), (float)((v11 - v10) - (v01 - v00)));
   }
 }
 
