@@ -1088,8 +1088,9 @@ int xrc_sm_allocate(xrc_sm* sm, uint32_t max_imgs)
   {
     XRC_CUDA(cudaMalloc(&sm->d_f0[0], npix * sizeof(float)));
     XRC_CUDA(cudaMalloc(&sm->d_f0[1], npix * sizeof(float)));
-    const size_t tiles = (size_t)((sm->rows + kGradTile - 1) / kGradTile) * ((sm->cols + kGradTile - 1) / kGradTile);
-    parts_per_img = tiles * 6;
+    // the smoothing width may still change after allocation: size for the largest decomposition
+    const size_t parts = std::max(grad_num_parts(sm->rows, sm->cols, 7), grad_num_parts(sm->rows, sm->cols, 9));
+    parts_per_img = parts * 6;
   }
   else
   {
@@ -1219,7 +1220,7 @@ int xrc_sm_compute(xrc_sm* sm)
     memset(&f, 0, sizeof(f));
     f.partials = sm->d_partials;
     f.n_imgs = sm->n_imgs;
-    f.n_parts = ((sm->rows + kGradTile - 1) / kGradTile) * ((sm->cols + kGradTile - 1) / kGradTile);
+    f.n_parts = grad_num_parts(sm->rows, sm->cols, (int)sm->gauss_width);
     f.n_dirs = 2;
     f.n_eff = sm->n_eff;
     for (int d = 0; d < 2; ++d)

@@ -197,11 +197,156 @@ __global__ void __launch_bounds__(256) grad_kernel(const GradArgs a)
   }
 }
 
+// Fast path for the Gaussian widths the reference uses (0 / 3 / 5 / 7): one WARP streams a strip of
+// 32 - 2 (HW + 1) output columns down a band of rows.  Lane = column (halo lanes load the reflect-101
+// neighbours, so every lane simply filters the extended signal); the horizontal taps come from warp
+// shuffles, the vertical taps from a register ring of row-filtered values, the Sobel operands from a
+// 3-row ring of (right - left) and (left + right + 2 centre).  No shared memory, no barriers, ~60
+// instructions per pixel instead of ~400 for the tiled kernel above.  Operation order is the oracle's.
+template <int HW, bool MOMENTS>
+__global__ void __launch_bounds__(256) grad_fast_kernel(const GradArgs a)
+{
+  constexpr int HALO = HW + 1;
+  constexpr int OW = 32 - 2 * HALO;
+  const int rows = (int)a.rows, cols = (int)a.cols;
+  const int lane = threadIdx.x & 31;
+  const int n_cstrips = (cols + OW - 1) / OW;
+  const int n_bands = (rows + kGradBandRows - 1) / kGradBandRows;
+  const int unit = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (unit >= n_cstrips * n_bands)
+    return;
+  const int cstrip = unit % n_cstrips, band = unit / n_cstrips;
+  const int img = blockIdx.y;
+  const size_t npix = (size_t)rows * cols;
+  const float* __restrict__ src = a.src + (size_t)img * npix;
+  const int c = cstrip * OW + lane - HALO;
+  const int cl = reflect101(c, cols);
+  const int r0 = band * kGradBandRows, r1 = min(r0 + kGradBandRows, rows);
+  const bool lane_out = (lane >= HALO) && (lane < 32 - HALO) && (c < cols);
+
+  float cf[HW + 1];
+#pragma unroll
+  for (int j = 0; j <= HW; ++j)
+    cf[j] = a.coeffs[HW + j];
+
+  float Hr[2 * HW + 1];
+  float D[3], S[3];
+#pragma unroll
+  for (int k = 0; k < 2 * HW + 1; ++k)
+    Hr[k] = 0.f;
+  D[0] = D[1] = D[2] = S[0] = S[1] = S[2] = 0.f;
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+
+  float x_next = __ldg(src + (size_t)reflect101(r0 - HALO, rows) * cols + cl);
+  for (int rr = r0 - HALO; rr < r1 + HALO; ++rr)
+  {
+    const float x = x_next;
+    if (rr + 1 < r1 + HALO)
+      x_next = __ldg(src + (size_t)reflect101(rr + 1, rows) * cols + cl);
+    // row filter (cv::GaussianBlur, separable, fixed kernel; xregImgSimMetric2DGradImgCPU.cpp:93-96)
+    float hval = x;
+    if (HW > 0)
+    {
+      hval = fmul(cf[0], x);
+#pragma unroll
+      for (int j = 1; j <= HW; ++j)
+      {
+        const float xl = __shfl_sync(0xffffffffu, x, lane - j), xr = __shfl_sync(0xffffffffu, x, lane + j);
+        hval = fadd(hval, fmul(cf[j], fadd(xl, xr)));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 2 * HW; ++k)
+      Hr[k] = Hr[k + 1];
+    Hr[2 * HW] = hval;
+    if (rr < r0 - HALO + 2 * HW)
+      continue;  // ring not full yet
+    // column filter -> blurred row rb = rr - HW
+    float b = Hr[HW];
+    if (HW > 0)
+    {
+      b = fmul(cf[0], Hr[HW]);
+#pragma unroll
+      for (int j = 1; j <= HW; ++j)
+        b = fadd(b, fmul(cf[j], fadd(Hr[HW - j], Hr[HW + j])));
+    }
+    const float bl = __shfl_sync(0xffffffffu, b, lane - 1), br = __shfl_sync(0xffffffffu, b, lane + 1);
+    D[0] = D[1];
+    D[1] = D[2];
+    D[2] = fsub(br, bl);
+    S[0] = S[1];
+    S[1] = S[2];
+    S[2] = fadd(fadd(bl, br), fmul(2.0f, b));
+    const int ro = rr - HW - 1;  // output row once blurred rows ro - 1, ro, ro + 1 are in the rings
+    if (ro < r0 || !lane_out)
+      continue;
+    // cv::Sobel 3x3 (verified against cv2): gx = (dm + dp) + 2 d0, gy = sp - sm
+    const float gx = fadd(fadd(D[0], D[2]), fmul(2.0f, D[1]));
+    const float gy = fsub(S[2], S[0]);
+    const size_t o = (size_t)ro * cols + c;
+    if (a.gx)
+    {
+      a.gx[(size_t)img * npix + o] = gx;
+      a.gy[(size_t)img * npix + o] = gy;
+    }
+    if (MOMENTS)
+    {
+      if (!a.mask || a.mask[o])
+      {
+        const double dx = gx, dy = gy;
+        acc[0] += dx;
+        acc[1] += dx * dx;
+        acc[2] += dx * (double)__ldg(a.f0x + o);
+        acc[3] += dy;
+        acc[4] += dy * dy;
+        acc[5] += dy * (double)__ldg(a.f0y + o);
+      }
+    }
+  }
+  if (MOMENTS)
+  {
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+      acc[k] = warp_sum(acc[k]);
+    if (lane == 0)
+    {
+      double* p = a.partials + ((size_t)img * (n_cstrips * n_bands) + unit) * 6;
+#pragma unroll
+      for (int k = 0; k < 6; ++k)
+        p[k] = acc[k];
+    }
+  }
+}
+
+template <int HW>
+static void launch_grad_fast(const GradArgs& a, cudaStream_t st)
+{
+  const uint32_t units = grad_num_parts(a.rows, a.cols, a.gauss_width);
+  const dim3 grid((units + 7) / 8, a.n_imgs);
+  if (a.partials)
+    grad_fast_kernel<HW, true><<<grid, 256, 0, st>>>(a);
+  else
+    grad_fast_kernel<HW, false><<<grid, 256, 0, st>>>(a);
+}
+
 int launch_grad(const GradArgs& a_in, cudaStream_t st)
 {
   GradArgs a = a_in;
   if (!a.n_imgs)
     return XRC_OK;
+  if (grad_fast_path(a.gauss_width))
+  {
+    switch (a.gauss_width / 2)
+    {
+      case 0: launch_grad_fast<0>(a, st); break;
+      case 1: launch_grad_fast<1>(a, st); break;
+      case 2: launch_grad_fast<2>(a, st); break;
+      default: launch_grad_fast<3>(a, st); break;
+    }
+    count_launch();
+    XRC_CUDA(cudaGetLastError());
+    return XRC_OK;
+  }
   a.tiles_x = (a.cols + T - 1) / T;
   a.tiles_y = (a.rows + T - 1) / T;
   const dim3 grid(a.tiles_x * a.tiles_y, a.n_imgs);

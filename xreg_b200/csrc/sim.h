@@ -8,6 +8,7 @@ namespace xrc
 
 constexpr int kGradTile = 32;       // output tile edge of the gradient kernel
 constexpr int kMaxGaussWidth = 31;  // widest supported smoothing kernel
+constexpr int kGradBandRows = 64;   // output rows per warp of the fast gradient kernel
 constexpr int kPatchThreads = 256;  // threads per CTA of the patch kernel (each owns 1 or 2 input columns)
 constexpr int kPatchBandRows = 64;  // patch rows per CTA
 constexpr int kMomChunk = 4096;     // pixels per CTA of the plain moments kernel
@@ -88,6 +89,19 @@ int launch_ncc_finalize(const NccFinalizeArgs& a, cudaStream_t st);
 int launch_patch(const PatchArgs& a, cudaStream_t st);
 int launch_patch_fixed_stats(const PatchArgs& a, cudaStream_t st);
 int launch_patch_finalize(const PatchFinalizeArgs& a, cudaStream_t st);
+
+// Gaussian widths served by the warp-streaming gradient kernel (the reference's apps use 5; 0 = no smoothing)
+inline bool grad_fast_path(int gauss_width) { return gauss_width <= 1 || gauss_width == 3 || gauss_width == 5 || gauss_width == 7; }
+// per-image partial-sum slots the gradient kernel writes (Grad-NCC moments)
+inline uint32_t grad_num_parts(uint32_t rows, uint32_t cols, int gauss_width)
+{
+  if (grad_fast_path(gauss_width))
+  {
+    const uint32_t ow = 32 - 2 * ((gauss_width > 1 ? gauss_width / 2 : 0) + 1);
+    return ((cols + ow - 1) / ow) * ((rows + kGradBandRows - 1) / kGradBandRows);
+  }
+  return ((rows + kGradTile - 1) / kGradTile) * ((cols + kGradTile - 1) / kGradTile);
+}
 
 // decomposition of the patch grid into CTAs (column strips x row bands)
 struct PatchPlan
