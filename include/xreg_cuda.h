@@ -228,6 +228,28 @@ int xrc_eval_batch(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t n_
 /* same without the final read-back / synchronise (results via xrc_sm_device_sims) */
 int xrc_eval_batch_async(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t n_views);
 
+
+/* ---- the whole objective in one call (caller-side glue): what
+ * Intensity2D3DRegi::obj_fn(frame_xforms, ...) does for one moving volume
+ * (xregIntensity2D3DRegi.cpp:571-696): size the ray caster / metrics for the population
+ * (set_num_projs, set_num_moving_images, view-major offsets, :63-94), replicate the n_poses
+ * poses over the views camera-major (RayCaster::distribute_xforms_among_cam_models,
+ * xregRayCastInterface.cpp:97-114), ray cast, evaluate every view's metric, gather, and average
+ * over views (ImgSimMetric2DCombineMean, xregImgSimMetric2DCombine.cpp:67-86).
+ * cam_to_phys: n_poses x 12 host floats.  sims_out: n_poses.  per_view_out: optional
+ * n_views x n_poses.  n_views must equal the number of camera models.  One synchronisation. */
+int xrc_obj_fn(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t n_views, uint32_t n_poses,
+               const float* cam_to_phys, float* sims_out, float* per_view_out);
+/* Same from optimiser variables: pose_p = pre * ExpSE3(params_p) * post with
+ * SE3OptVarsLieAlg (lib/regi/xregSE3OptVars.cpp:128-137; params = [w_x w_y w_z v_x v_y v_z]) and the
+ * intermediate-frame composition of apply_inter_transforms_for_obj_fn (xregIntensity2D3DRegi.cpp:1049-1071).
+ * pre12 / post12: row-major 3x4, NULL = identity.  All f32, evaluated on the host. */
+int xrc_obj_fn_se3(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t n_views, uint32_t n_poses,
+                   const float* params, const float* pre12, const float* post12, float* sims_out,
+                   float* per_view_out);
+/* ExpSE3(Pt6) (lib/transforms/xregRigidUtils.cpp:40-85) in f32; host only, needs no device. */
+void xrc_exp_se3(const float params[6], float out12[12]);
+
 #ifdef __cplusplus
 }
 #endif

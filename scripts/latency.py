@@ -16,10 +16,14 @@ from xreg_b200 import regi, synth  # noqa: E402
 
 
 def main():
+    only = os.environ.get("LAT_ONLY")  # "det,metric,pop,reps" -> a single case (for ncu launch lists)
     vol = synth.make_volume(512, 512, 400, spacing=(0.8, 0.8, 1.0))
     nominal = synth.nominal_pose(vol)
     ctx = xreg_b200.Context(0)
-    for det, metric in ((192, "grad-ncc"), (384, "grad-ncc"), (768, "grad-ncc"), (192, "patch-grad-ncc"), (384, "patch-grad-ncc")):
+    cases = ((192, "grad-ncc"), (384, "grad-ncc"), (768, "grad-ncc"), (192, "patch-grad-ncc"), (384, "patch-grad-ncc"))
+    if only:
+        cases = ((int(only.split(",")[0]), only.split(",")[1]),)
+    for det, metric in cases:
         cam = synth.make_camera(det)
         pops = synth.pose_population(vol, nominal, 100, seed=3)
         rc0 = xreg_b200.RayCasterLineIntCUDA(ctx)
@@ -33,8 +37,10 @@ def main():
         rc0.close()
         fn = regi.Intensity2D3DObjFn(ctx, vol, [cam], [fixed], metric=metric, max_pop=100,
                                      patch_radius=synth.patch_radius_for(det))
-        for pop_n in (1, 100):
+        for pop_n in ((1, 100) if not only else (int(only.split(",")[2]),)):
             reps = 200 if pop_n == 1 else 20
+            if only:
+                reps = int(only.split(",")[3])
             for k in range(5):
                 fn(pops[k:k + pop_n])
             t0 = time.perf_counter()

@@ -37,6 +37,35 @@ def test_eval_batch_equals_separate_calls_multi_view(ctx, xo, small_scene):
         np.testing.assert_array_equal(three, got[[4, 1, 3]])
 
 
+def test_objective_from_se3_parameters(ctx, small_scene):
+    """xrc_obj_fn_se3: pose = pre * ExpSE3(x) * post composed inside the library equals the same poses
+    composed on the host and passed to xrc_obj_fn."""
+    from xreg_b200.geometry import exp_se3
+
+    vol, cam, nominal = small_scene
+    c = np.asarray(vol.origin) + 0.5 * (np.asarray(vol.dims) - 1.0) * np.asarray(vol.spacing)
+    pre, post = np.eye(4, dtype=f32), np.eye(4, dtype=f32)
+    pre[:3, 3] = c
+    post[:3, 3] = -c
+    post = (post @ nominal).astype(f32)   # pre * delta * post = C delta C^-1 nominal
+    rng = np.random.default_rng(3)
+    x = np.concatenate([rng.normal(0, 0.05, (7, 3)), rng.normal(0, 4.0, (7, 3))], axis=1).astype(f32)
+    x[0] = 0
+    fixed = np.ones((cam.num_det_rows, cam.num_det_cols), f32)
+    fn = regi.Intensity2D3DObjFn(ctx, vol, [cam], [fixed], metric="ncc", max_pop=7)
+    rc0 = fn.rc
+    poses = np.stack([(pre @ exp_se3(xi) @ post).astype(f32) for xi in x])
+    a = fn(poses)
+    fixed = synth.add_noise(rc0.proj(0))
+    fn2 = regi.Intensity2D3DObjFn(ctx, vol, [cam], [fixed], metric="grad-ncc", max_pop=7)
+    a = fn2(poses)
+    b = fn2.eval_se3(x, pre, post)
+    assert np.max(np.abs(a - b)) <= 1e-5
+    assert int(np.argmin(b)) == 0
+    one = fn2.eval_se3(x[3:4], pre, post)
+    assert abs(one[0] - b[3]) <= 1e-7
+
+
 def test_launch_counter_counts_our_kernels(ctx, small_scene):
     vol, cam, nominal = small_scene
     fn = regi.Intensity2D3DObjFn(ctx, vol, [cam], [np.ones((cam.num_det_rows, cam.num_det_cols), f32)], metric="patch-grad-ncc",

@@ -102,3 +102,26 @@ def test_patch_weights_match_oracle(xo, radius, stride):
     np.testing.assert_allclose(m.compute_weights(), xo.patch_weights(23, 29, o, mask=mask, wgt_img=wi), rtol=2e-6)
     m._wgt_img, m._mask = None, None
     assert m.compute_weights() is None
+
+
+def test_library_exp_se3_matches_host_model():
+    """xrc_exp_se3 (ExpSE3, lib/transforms/xregRigidUtils.cpp:40-85) is host-only code of the product library:
+    compare with the numpy restatement, including the small-angle branch."""
+    import ctypes as C
+
+    from xreg_b200 import _lib
+    from xreg_b200.geometry import exp_se3
+
+    lib = _lib.load()
+    rng = np.random.default_rng(11)
+    FP = C.POINTER(C.c_float)
+    cases = [np.zeros(6), np.array([0, 0, 0, 1.5, -2.0, 3.0]), np.array([1e-20, 0, 0, 1, 2, 3])]
+    cases += [np.concatenate([rng.normal(0, 0.4, 3), rng.normal(0, 30, 3)]) for _ in range(20)]
+    for x in cases:
+        x32 = np.ascontiguousarray(x, dtype=np.float32)
+        out = np.zeros(12, dtype=np.float32)
+        lib.xrc_exp_se3(x32.ctypes.data_as(FP), out.ctypes.data_as(FP))
+        ref = exp_se3(x32)[:3, :].reshape(12)
+        assert np.max(np.abs(out - ref)) <= 2e-5 * max(1.0, float(np.abs(ref).max())), (x, out, ref)
+        R = out.reshape(3, 4)[:, :3].astype(np.float64)
+        assert np.max(np.abs(R @ R.T - np.eye(3))) < 1e-5

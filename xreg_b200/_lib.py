@@ -109,8 +109,11 @@ SIGNATURES = {
     "xrc_sm_read_grads": [_VP, _U32, _FP, _FP],
     "xrc_eval_batch": [_VP, _U32, C.POINTER(_VP), _U32, _U32, _FP],
     "xrc_eval_batch_async": [_VP, _U32, C.POINTER(_VP), _U32],
+    "xrc_obj_fn": [_VP, _U32, C.POINTER(_VP), _U32, _U32, _FP, _FP, _FP],
+    "xrc_obj_fn_se3": [_VP, _U32, C.POINTER(_VP), _U32, _U32, _FP, _FP, _FP, _FP, _FP],
+    "xrc_exp_se3": [_FP, _FP],
 }
-_RESTYPES = {"xrc_last_error": C.c_char_p, "xrc_launch_count": C.c_uint64}
+_RESTYPES = {"xrc_last_error": C.c_char_p, "xrc_launch_count": C.c_uint64, "xrc_exp_se3": None}
 
 _lib = None
 

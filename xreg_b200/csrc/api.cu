@@ -1089,7 +1089,7 @@ int xrc_sm_allocate(xrc_sm* sm, uint32_t max_imgs)
     XRC_CUDA(cudaMalloc(&sm->d_f0[0], npix * sizeof(float)));
     XRC_CUDA(cudaMalloc(&sm->d_f0[1], npix * sizeof(float)));
     // the smoothing width may still change after allocation: size for the largest decomposition
-    const size_t parts = std::max(grad_num_parts(sm->rows, sm->cols, 7), grad_num_parts(sm->rows, sm->cols, 9));
+    const size_t parts = std::max(grad_num_parts(sm->rows, sm->cols, 7, kGradBandRowsMin), grad_num_parts(sm->rows, sm->cols, 9));
     parts_per_img = parts * 6;
   }
   else
@@ -1115,8 +1115,7 @@ int xrc_sm_allocate(xrc_sm* sm, uint32_t max_imgs)
       XRC_CUDA(cudaMalloc(&sm->d_psmask[d], grid1 * sizeof(double)));
     }
     XRC_CUDA(cudaMalloc(&sm->d_pnmask, grid1 * sizeof(float)));
-    const PatchPlan pl = patch_plan(sm->rows, sm->cols, r);
-    sm->n_strips = pl.n_strips * pl.n_bands;  // partial sums per image and direction
+    sm->n_strips = patch_max_parts(sm->rows, sm->cols, r);  // capacity: partial sums per image and direction
     parts_per_img = (size_t)n_dirs * sm->n_strips;
     const uint64_t np = (uint64_t)((sm->rows - 1 - 2 * r) / sm->stride + 1) * ((sm->cols - 1 - 2 * r) / sm->stride + 1);
     XRC_CUDA(cudaMalloc(&sm->d_weights, np * sizeof(float)));
@@ -1220,7 +1219,8 @@ int xrc_sm_compute(xrc_sm* sm)
     memset(&f, 0, sizeof(f));
     f.partials = sm->d_partials;
     f.n_imgs = sm->n_imgs;
-    f.n_parts = grad_num_parts(sm->rows, sm->cols, (int)sm->gauss_width);
+    f.n_parts = grad_num_parts(sm->rows, sm->cols, (int)sm->gauss_width,
+                               grad_band_rows(sm->rows, sm->cols, (int)sm->gauss_width, sm->n_imgs));
     f.n_dirs = 2;
     f.n_eff = sm->n_eff;
     for (int d = 0; d < 2; ++d)
@@ -1279,7 +1279,10 @@ int xrc_sm_compute(xrc_sm* sm)
   f.partials = sm->d_partials;
   f.n_imgs = sm->n_imgs;
   f.n_dirs = n_dirs;
-  f.n_parts = sm->n_strips;
+  {
+    const PatchPlan pl = patch_plan(sm->rows, sm->cols, sm->radius, sm->n_imgs * n_dirs);
+    f.n_parts = pl.n_strips * pl.n_bands;
+  }
   f.divisor = sm->divisor;
   f.sims = sm->d_sims;
   return launch_patch_finalize(f, st);
@@ -1366,6 +1369,117 @@ int xrc_eval_batch(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t n_
   for (uint32_t v = 0; v < n_views; ++v)
     memcpy(sims_out + (size_t)v * n_per_view, sms[v]->h_sims, n_per_view * sizeof(float));
   return XRC_OK;
+}
+
+// ---------------------------------------------------------------- whole objective
+// ExpSO3 / ExpSE3 (lib/transforms/xregRigidUtils.cpp:40-85, xregRotUtils): Rodrigues' formula in f32
+void xrc_exp_se3(const float x[6], float out[12])
+{
+  const float wx = x[0], wy = x[1], wz = x[2];
+  const float W[9] = {0.f, -wz, wy, wz, 0.f, -wx, -wy, wx, 0.f};
+  float W2[9];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c)
+      W2[3 * r + c] = (W[3 * r] * W[c] + W[3 * r + 1] * W[3 + c]) + W[3 * r + 2] * W[6 + c];
+  const float theta = sqrtf((wx * wx + wy * wy) + wz * wz);
+  float R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, A[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  if (theta > 1.0e-14f)
+  {
+    const float th2 = theta * theta;
+    const float s = sinf(theta), c1 = 1.0f - cosf(theta);
+    const float ra = s / theta, rb = c1 / th2;                     // R = I + sin/theta W + (1-cos)/theta^2 W^2
+    const float aa = c1 / th2, ab = (theta - s) / (theta * th2);  // A = I + (1-cos)/theta^2 W + (theta-sin)/theta^3 W^2
+    for (int i = 0; i < 9; ++i)
+    {
+      R[i] = (R[i] + ra * W[i]) + rb * W2[i];
+      A[i] = (A[i] + aa * W[i]) + ab * W2[i];
+    }
+  }
+  for (int r = 0; r < 3; ++r)
+  {
+    out[4 * r] = R[3 * r];
+    out[4 * r + 1] = R[3 * r + 1];
+    out[4 * r + 2] = R[3 * r + 2];
+    out[4 * r + 3] = (A[3 * r] * x[3] + A[3 * r + 1] * x[4]) + A[3 * r + 2] * x[5];
+  }
+}
+
+// c = a * b for row-major 3x4 affine transforms
+static void affine_mul(const float a[12], const float b[12], float c[12])
+{
+  float t[12];
+  for (int r = 0; r < 3; ++r)
+  {
+    for (int k = 0; k < 4; ++k)
+    {
+      float v = (a[4 * r] * b[k] + a[4 * r + 1] * b[4 + k]) + a[4 * r + 2] * b[8 + k];
+      if (k == 3)
+        v += a[4 * r + 3];
+      t[4 * r + k] = v;
+    }
+  }
+  memcpy(c, t, sizeof(t));
+}
+
+int xrc_obj_fn(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t n_views, uint32_t n_poses,
+               const float* cam_to_phys, float* sims_out, float* per_view_out)
+{
+  XRC_CHECK_ARG(rc && sms && cam_to_phys && sims_out, "xrc_obj_fn: null argument");
+  XRC_CHECK_ARG(rc->allocated, "xrc_obj_fn: ray caster resources not allocated");
+  XRC_CHECK_ARG(n_views == rc->cams.size(), "xrc_obj_fn: need one metric per camera model / view");
+  if (!n_poses)
+    return XRC_OK;
+  XRC_CHECK_ARG((uint64_t)n_poses * n_views <= rc->max_projs, "xrc_obj_fn: population exceeds the allocated projections");
+  // Intensity2D3DRegi::setup(): view v's metric reads projections [v * pop, (v + 1) * pop)
+  if (rc->num_projs != n_poses * n_views)
+    XRC_TRY(xrc_rc_set_num_projs(rc, n_poses * n_views));
+  for (uint32_t v = 0; v < n_views; ++v)
+  {
+    XRC_CHECK_ARG(sms[v] && sms[v]->rc == rc, "xrc_obj_fn: every metric must be bound to the ray caster");
+    if (sms[v]->n_imgs != n_poses)
+      XRC_TRY(xrc_sm_set_num_imgs(sms[v], n_poses));
+    if (sms[v]->proj_offset != v * n_poses)
+      XRC_TRY(xrc_sm_bind_ray_caster(sms[v], rc, v * n_poses));
+  }
+  rc->ext_poses = nullptr;  // host poses take over from a caller's device buffer
+  XRC_TRY(xrc_rc_distribute_poses(rc, n_poses, cam_to_phys));
+  std::vector<float> tmp;
+  float* pv = per_view_out;
+  if (!pv)
+  {
+    tmp.resize((size_t)n_views * n_poses);
+    pv = tmp.data();
+  }
+  XRC_TRY(xrc_eval_batch(rc, vol_idx, sms, n_views, n_poses, pv));
+  // ImgSimMetric2DCombineMean::compute: f32 running sum over views, then / n_views
+  for (uint32_t p = 0; p < n_poses; ++p)
+  {
+    float acc = 0.0f;
+    for (uint32_t v = 0; v < n_views; ++v)
+    {
+      const volatile float t = acc + pv[(size_t)v * n_poses + p];
+      acc = t;
+    }
+    sims_out[p] = acc / (float)n_views;
+  }
+  return XRC_OK;
+}
+
+int xrc_obj_fn_se3(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t n_views, uint32_t n_poses,
+                   const float* params, const float* pre12, const float* post12, float* sims_out, float* per_view_out)
+{
+  XRC_CHECK_ARG(params, "xrc_obj_fn_se3: null parameters");
+  std::vector<float> poses((size_t)n_poses * 12);
+  for (uint32_t p = 0; p < n_poses; ++p)
+  {
+    float* T = poses.data() + 12 * (size_t)p;
+    xrc_exp_se3(params + 6 * (size_t)p, T);
+    if (pre12)
+      affine_mul(pre12, T, T);
+    if (post12)
+      affine_mul(T, post12, T);
+  }
+  return xrc_obj_fn(rc, vol_idx, sms, n_views, n_poses, poses.data(), sims_out, per_view_out);
 }
 
 }  // extern "C"

@@ -820,9 +820,21 @@ static int launch_pax_k(const DrrArgs& a, cudaStream_t st)
 #define XRC_PAX_LAUNCH(B, M) drr_pax_kernel<KERNEL_ID, true, B, M><<<nblocks, kThreads, 0, st>>>(a)
   if (KERNEL_ID != XRC_KERNEL_SUM)
     drr_pax_kernel<KERNEL_ID, false, 1, 5><<<nblocks, kThreads, 0, st>>>(a);
+  else if (!packed && !batch)
+  {
+    // Default: scalar FP32 (FFMA / FADD issue to both FMA pipes; the packed f32x2 forms save issue slots the
+    // loop does not need and measured 1 % slower).  Throughput regime (a CMA-ES population: more CTAs than fit
+    // at once): one sample group in flight ahead, 5 CTAs / 40 warps per SM.  Latency regime (population 1,
+    // BOBYQA: the whole grid is resident in one wave and every ray is a serial chain of L2-latency loads): spend
+    // the idle registers on a deeper software pipeline.  All variants add the same values in the same order.
+    if (nblocks <= 148u * 2u)
+      drr_pax_kernel<KERNEL_ID, false, 4, 2><<<nblocks, kThreads, 0, st>>>(a);
+    else if (nblocks <= 148u * 4u)
+      drr_pax_kernel<KERNEL_ID, false, 2, 4><<<nblocks, kThreads, 0, st>>>(a);
+    else
+      drr_pax_kernel<KERNEL_ID, false, 1, 5><<<nblocks, kThreads, 0, st>>>(a);
+  }
   else if (!packed)
-    // default: scalar FP32 (FFMA / FADD issue to both FMA pipes; the packed f32x2 forms save issue slots the
-    // loop does not need and measured 1 % slower), one sample group in flight ahead, 5 CTAs (40 warps) per SM
     drr_pax_kernel<KERNEL_ID, false, 1, 5><<<nblocks, kThreads, 0, st>>>(a);
   else if (batch == 2)
   {

@@ -211,7 +211,8 @@ __global__ void __launch_bounds__(256) grad_fast_kernel(const GradArgs a)
   const int rows = (int)a.rows, cols = (int)a.cols;
   const int lane = threadIdx.x & 31;
   const int n_cstrips = (cols + OW - 1) / OW;
-  const int n_bands = (rows + kGradBandRows - 1) / kGradBandRows;
+  const int band_rows = (int)a.band_rows;
+  const int n_bands = (rows + band_rows - 1) / band_rows;
   const int unit = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (unit >= n_cstrips * n_bands)
     return;
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(256) grad_fast_kernel(const GradArgs a)
   const float* __restrict__ src = a.src + (size_t)img * npix;
   const int c = cstrip * OW + lane - HALO;
   const int cl = reflect101(c, cols);
-  const int r0 = band * kGradBandRows, r1 = min(r0 + kGradBandRows, rows);
+  const int r0 = band * band_rows, r1 = min(r0 + band_rows, rows);
   const bool lane_out = (lane >= HALO) && (lane < 32 - HALO) && (c < cols);
 
   float cf[HW + 1];
@@ -321,7 +322,7 @@ __global__ void __launch_bounds__(256) grad_fast_kernel(const GradArgs a)
 template <int HW>
 static void launch_grad_fast(const GradArgs& a, cudaStream_t st)
 {
-  const uint32_t units = grad_num_parts(a.rows, a.cols, a.gauss_width);
+  const uint32_t units = grad_num_parts(a.rows, a.cols, a.gauss_width, a.band_rows);
   const dim3 grid((units + 7) / 8, a.n_imgs);
   if (a.partials)
     grad_fast_kernel<HW, true><<<grid, 256, 0, st>>>(a);
@@ -336,6 +337,7 @@ int launch_grad(const GradArgs& a_in, cudaStream_t st)
     return XRC_OK;
   if (grad_fast_path(a.gauss_width))
   {
+    a.band_rows = grad_band_rows(a.rows, a.cols, a.gauss_width, a.n_imgs);
     switch (a.gauss_width / 2)
     {
       case 0: launch_grad_fast<0>(a, st); break;
@@ -594,7 +596,7 @@ __global__ void __launch_bounds__(kPatchThreads) patch_kernel(const PatchArgs a)
   const int st = (int)a.stride;
   const int ncc_s = (ncc_all - 1) / st + 1;
   const size_t npix = (size_t)rows * cols;
-  const int i_begin = band * kPatchBandRows, i_end = min(i_begin + kPatchBandRows, nrr_all);
+  const int i_begin = band * (int)a.band_rows, i_end = min(i_begin + (int)a.band_rows, nrr_all);
 
   const float* __restrict__ m = FIXED ? nullptr : (a.mov[dir] + (size_t)img * npix);
   const float* __restrict__ f = a.fix[dir];
@@ -846,9 +848,10 @@ static int launch_patch_impl(const PatchArgs& a_in, cudaStream_t st)
   PatchArgs a = a_in;
   if (!(FIXED ? 1u : a.n_imgs))
     return XRC_OK;
-  const PatchPlan pl = patch_plan(a.rows, a.cols, a.radius);
+  const PatchPlan pl = patch_plan(a.rows, a.cols, a.radius, (FIXED ? 1u : a.n_imgs) * a.n_dirs);
   a.n_strips = pl.n_strips;
   a.n_parts = pl.n_strips * pl.n_bands;
+  a.band_rows = pl.band_rows;
   return (pl.cols_per_thread == 2) ? launch_patch_c<FIXED, 2>(a, st) : launch_patch_c<FIXED, 1>(a, st);
 }
 

@@ -8,9 +8,11 @@ namespace xrc
 
 constexpr int kGradTile = 32;       // output tile edge of the gradient kernel
 constexpr int kMaxGaussWidth = 31;  // widest supported smoothing kernel
-constexpr int kGradBandRows = 64;   // output rows per warp of the fast gradient kernel
+constexpr int kGradBandRows = 64;   // output rows per warp of the fast gradient kernel (throughput regime)
+constexpr int kGradBandRowsMin = 8; // ... when only a few images are in flight (population 1)
 constexpr int kPatchThreads = 256;  // threads per CTA of the patch kernel (each owns 1 or 2 input columns)
-constexpr int kPatchBandRows = 64;  // patch rows per CTA
+constexpr int kPatchBandRows = 64;  // patch rows per CTA (throughput regime)
+constexpr int kPatchBandRowsMin = 8;  // ... with few images in flight (population 1)
 constexpr int kMomChunk = 4096;     // pixels per CTA of the plain moments kernel
 
 struct GradArgs
@@ -27,6 +29,7 @@ struct GradArgs
   const uint8_t* mask;
   double* partials;       // n_imgs x n_tiles x 6
   uint32_t tiles_x, tiles_y;
+  uint32_t band_rows;     // fast kernel: output rows per warp (filled by the launcher)
 };
 
 struct MomentArgs
@@ -59,6 +62,7 @@ struct PatchArgs
   uint32_t n_imgs, n_dirs, rows, cols;
   uint32_t radius, stride;
   uint32_t n_strips, n_parts;  // filled by the launcher from patch_plan(); n_parts = n_strips * n_bands
+  uint32_t band_rows;          // ditto
   int mask_mode;           // 0 none, 1 mask in correlation only, 2 mask in stats too
   // fixed per-patch statistics on the stride-1 grid (rows-2r) x (cols-2r), per direction
   const double* f_mean[2];  // f64: keeps sum(m - mu_m)(f - mu_f) = Smf - mu_f Sm free of f32 rounding of mu_f
@@ -92,13 +96,24 @@ int launch_patch_finalize(const PatchFinalizeArgs& a, cudaStream_t st);
 
 // Gaussian widths served by the warp-streaming gradient kernel (the reference's apps use 5; 0 = no smoothing)
 inline bool grad_fast_path(int gauss_width) { return gauss_width <= 1 || gauss_width == 3 || gauss_width == 5 || gauss_width == 7; }
+// rows per warp of the fast kernel: long bands amortise the halo rows, short bands give a small batch
+// enough warps to hide the per-row load latency (population 1: 61 us with 64-row bands at 384 x 384)
+inline uint32_t grad_band_rows(uint32_t rows, uint32_t cols, int gauss_width, uint32_t n_imgs)
+{
+  const uint32_t ow = 32 - 2 * ((gauss_width > 1 ? gauss_width / 2 : 0) + 1);
+  const uint64_t strips = (uint64_t)((cols + ow - 1) / ow) * n_imgs;
+  uint32_t band = kGradBandRows;
+  while (band > (uint32_t)kGradBandRowsMin && strips * ((rows + band - 1) / band) < 148u * 32u)
+    band /= 2;
+  return band;
+}
 // per-image partial-sum slots the gradient kernel writes (Grad-NCC moments)
-inline uint32_t grad_num_parts(uint32_t rows, uint32_t cols, int gauss_width)
+inline uint32_t grad_num_parts(uint32_t rows, uint32_t cols, int gauss_width, uint32_t band_rows = kGradBandRows)
 {
   if (grad_fast_path(gauss_width))
   {
     const uint32_t ow = 32 - 2 * ((gauss_width > 1 ? gauss_width / 2 : 0) + 1);
-    return ((cols + ow - 1) / ow) * ((rows + kGradBandRows - 1) / kGradBandRows);
+    return ((cols + ow - 1) / ow) * ((rows + band_rows - 1) / band_rows);
   }
   return ((rows + kGradTile - 1) / kGradTile) * ((cols + kGradTile - 1) / kGradTile);
 }
@@ -106,16 +121,29 @@ inline uint32_t grad_num_parts(uint32_t rows, uint32_t cols, int gauss_width)
 // decomposition of the patch grid into CTAs (column strips x row bands)
 struct PatchPlan
 {
-  uint32_t cols_per_thread, n_strips, n_bands;
+  uint32_t cols_per_thread, n_strips, n_bands, band_rows;
 };
-inline PatchPlan patch_plan(uint32_t rows, uint32_t cols, uint32_t radius)
+// n_units = images x directions in flight: small batches get short bands (more CTAs; each band re-reads the
+// d - 1 rows above it, loads only) so that the serial row loop is not the latency of a population-1 evaluation
+inline PatchPlan patch_plan(uint32_t rows, uint32_t cols, uint32_t radius, uint32_t n_units)
 {
   PatchPlan p;
   p.cols_per_thread = (cols > (uint32_t)kPatchThreads) ? 2u : 1u;
   const uint32_t w_out = p.cols_per_thread * kPatchThreads - 2 * radius;
   p.n_strips = (cols - 2 * radius + w_out - 1) / w_out;
-  p.n_bands = (rows - 2 * radius + kPatchBandRows - 1) / kPatchBandRows;
+  const uint32_t nrr = rows - 2 * radius;
+  p.band_rows = kPatchBandRows;
+  while (p.band_rows > (uint32_t)kPatchBandRowsMin &&
+         (uint64_t)p.n_strips * ((nrr + p.band_rows - 1) / p.band_rows) * n_units < 148u * 3u)
+    p.band_rows /= 2;
+  p.n_bands = (nrr + p.band_rows - 1) / p.band_rows;
   return p;
+}
+// upper bound of n_strips * n_bands over all batch sizes (sizes the partial-sum buffer)
+inline uint32_t patch_max_parts(uint32_t rows, uint32_t cols, uint32_t radius)
+{
+  const PatchPlan p = patch_plan(rows, cols, radius, 1u << 30);
+  return p.n_strips * ((rows - 2 * radius + kPatchBandRowsMin - 1) / kPatchBandRowsMin);
 }
 
 }  // namespace xrc

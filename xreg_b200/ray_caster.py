@@ -290,11 +290,14 @@ class RayCasterLineIntCUDA:
     def use_other_proj_buf(self, other: "RayCasterLineIntCUDA") -> None:
         check(self._lib.xrc_rc_use_other_proj_buf(self.handle, other.handle))
 
-    def _flush(self) -> None:
+    def _flush_params(self) -> None:
         if self._params_dirty:
             check(self._lib.xrc_rc_set_params(self.handle, self._ray_step_size, self._interp_method, self._kernel_id,
                                               self._proj_store_meth, self._default_bg))
             self._params_dirty = False
+
+    def _flush(self) -> None:
+        self._flush_params()
         if self._poses_dirty and self._num_projs:
             poses = to12(np.stack(self._xforms[: self._num_projs]))
             idx = np.asarray(self._cam_model_for_proj[: self._num_projs], dtype=np.uint32)

@@ -9,6 +9,7 @@ data-path collective) and gathers only the per-pose scalars.
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -74,6 +75,8 @@ class Intensity2D3DObjFn:
             sm.allocate_resources()
             self.sims.append(sm)
         self._cur_pop = self.max_pop
+        self._lib = _lib.load()
+        self._sm_arr = (C.c_void_p * self.n_views)(*[sm.handle for sm in self.sims])
 
     def _set_pop(self, n: int) -> None:
         if n > self.max_pop:
@@ -86,21 +89,41 @@ class Intensity2D3DObjFn:
             self._cur_pop = n
 
     def __call__(self, poses: np.ndarray) -> np.ndarray:
+        """One objective evaluation = one call into the library (xrc_obj_fn): distribute the poses over
+        the views camera-major, ray cast, every view's metric, one gather, mean over views."""
         p12 = to12(poses) if np.asarray(poses).ndim == 3 else np.ascontiguousarray(poses, dtype=f32).reshape(-1, 12)
         n = p12.shape[0]
         if n == 0:
             return np.zeros(0, dtype=f32)
         self._set_pop(n)
-        # distribute_xforms_among_cam_models: camera-major replication
-        allp = np.ascontiguousarray(np.tile(p12, (self.n_views, 1)))
-        cam_idx = np.repeat(np.arange(self.n_views, dtype=np.uint32), n)
-        self.rc.set_poses_array(allp, cam_idx)
-        per_view = eval_batch(self.rc, self.sims, n)
-        # ImgSimMetric2DCombineMean (xregImgSimMetric2DCombine.cpp:67-86)
-        acc = np.zeros(n, dtype=f32)
-        for v in range(self.n_views):
-            acc = (acc + per_view[v]).astype(f32)
-        return (acc / f32(self.n_views)).astype(f32)
+        self.rc._flush_params()
+        out = np.empty(n, dtype=f32)
+        per_view = np.empty((self.n_views, n), dtype=f32)
+        FP = C.POINTER(C.c_float)
+        _lib.check(self._lib.xrc_obj_fn(self.rc.handle, 0, self._sm_arr, self.n_views, n, p12.ctypes.data_as(FP),
+                                        out.ctypes.data_as(FP), per_view.ctypes.data_as(FP)))
+        self.rc._poses_dirty = False  # the library now holds the distributed poses
+        for v, sm in enumerate(self.sims):
+            sm._sim_vals[:n] = per_view[v]
+        return out
+
+    def eval_se3(self, params: np.ndarray, pre: Optional[np.ndarray] = None, post: Optional[np.ndarray] = None) -> np.ndarray:
+        """Objective from optimiser variables (SE3OptVarsLieAlg, xregSE3OptVars.cpp:128-137):
+        pose_p = pre * ExpSE3(params_p) * post (xregIntensity2D3DRegi.cpp:1049-1071), composed inside the library."""
+        x = np.ascontiguousarray(params, dtype=f32).reshape(-1, 6)
+        n = x.shape[0]
+        if n == 0:
+            return np.zeros(0, dtype=f32)
+        self._set_pop(n)
+        self.rc._flush_params()
+        out = np.empty(n, dtype=f32)
+        FP = C.POINTER(C.c_float)
+        pre12 = None if pre is None else to12(pre).ctypes.data_as(FP)
+        post12 = None if post is None else to12(post).ctypes.data_as(FP)
+        _lib.check(self._lib.xrc_obj_fn_se3(self.rc.handle, 0, self._sm_arr, self.n_views, n, x.ctypes.data_as(FP),
+                                            pre12, post12, out.ctypes.data_as(FP), None))
+        self.rc._poses_dirty = False
+        return out
 
 
 class ShardedObjFn:
