@@ -104,6 +104,13 @@ int xrc_rc_set_layout(xrc_rc* rc, int layout);
 /* Tuning knob: CTA launch order, 0 = projection fastest (default), 1 = detector tile fastest. */
 int xrc_rc_set_cta_order(xrc_rc* rc, int order);
 
+/* Empty-space trimming, default on.  Samples whose 8 corner voxels are all zero add +0 to the
+ * sequential f32 sum of xregRayCastLineIntCPU.cpp:270-279, so the sum kernel does not fetch the leading
+ * and trailing samples of a ray that a per-volume block map proves to be zero (air around the body,
+ * everything outside the bone mask).  Results are bit-identical with trimming on or off; 0 turns it off
+ * (measurement).  The max kernel never trims. */
+int xrc_rc_set_skip_empty(xrc_rc* rc, int enable);
+
 /* RayCaster::set_volumes (xregRayCastInterface.h:90) + vols_changed (:425).
  * host_ptrs[i]: x-fastest float volume of dims[i] = {nx, ny, nz}; copied to the
  * device (the caller's memory is not referenced afterwards).
@@ -171,6 +178,11 @@ int xrc_rc_use_other_proj_buf(xrc_rc* rc, xrc_rc* other);
  * SURVEY 8(d).  Synchronises. */
 int xrc_rc_ray_info(xrc_rc* rc, uint32_t vol_idx, uint8_t* host_mask, uint32_t* host_steps,
                     uint64_t* total_samples);
+
+/* Instrumentation: the number of trilinear samples compute() fetches for the current poses
+ * (<= total_samples of xrc_rc_ray_info; equal when trimming is off).  Projections are not touched.
+ * Synchronises. */
+int xrc_rc_fetched_samples(xrc_rc* rc, uint32_t vol_idx, uint64_t* fetched);
 
 /* ---- similarity metrics: replace ImgSimMetric2D*OCL
  * (lib/regi/sim_metrics_2d/xregImgSimMetric2D{NCC,GradImg,GradNCC,PatchNCC,PatchGradNCC}OCL.cpp)

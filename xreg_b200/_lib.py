@@ -92,6 +92,8 @@ SIGNATURES = {
     "xrc_rc_read_projs": [_VP, _U32, _U32, _FP],
     "xrc_rc_use_other_proj_buf": [_VP, _VP],
     "xrc_rc_ray_info": [_VP, _U32, _U8P, _U32P, C.POINTER(_U64)],
+    "xrc_rc_set_skip_empty": [_VP, C.c_int],
+    "xrc_rc_fetched_samples": [_VP, _U32, C.POINTER(_U64)],
     "xrc_sm_create": [_VP, C.c_int, C.POINTER(_VP)],
     "xrc_sm_destroy": [_VP],
     "xrc_sm_set_fixed": [_VP, _FP, _U32, _U32],

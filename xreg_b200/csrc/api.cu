@@ -129,6 +129,7 @@ struct xrc_rc
   bool use_bg = false;
   float* d_bg = nullptr;
   int order = 0;
+  bool skip_empty = true;  // empty-space trimming (exact; xrc_rc_set_skip_empty)
 };
 
 struct xrc_sm
@@ -357,7 +358,9 @@ static int rc_set_volumes_impl(xrc_rc* rc, uint32_t n, const float* const* ptrs,
       XRC_CUDA(cudaMemcpyAsync(staging, ptrs[i], nvox * sizeof(float), cudaMemcpyHostToDevice, st));
       d_src = staging;
     }
-    const int s = repack_volume(d_src, &v, layout, st);
+    int s = repack_volume(d_src, &v, layout, st);
+    if (s == XRC_OK && layout == XRC_LAYOUT_PAX)
+      s = build_occupancy(d_src, &v, st);
     cudaStreamSynchronize(st);
     if (staging)
       cudaFree(staging);
@@ -637,6 +640,9 @@ static void rc_fill_args(xrc_rc* rc, uint32_t vol_idx, DrrArgs* a)
     a->pax_sb[k] = v.pax_sb[k];
     a->pax_sc[k] = v.pax_sc[k];
   }
+  a->occ = rc->skip_empty ? v.occ : nullptr;
+  a->occ_wx = v.occ_wx;
+  a->occ_ny = v.occ_ny;
 }
 
 int xrc_rc_compute(xrc_rc* rc, uint32_t vol_idx)
@@ -727,6 +733,45 @@ int xrc_rc_ray_info(xrc_rc* rc, uint32_t vol_idx, uint8_t* host_mask, uint32_t* 
   cudaFree(d_mask);
   cudaFree(d_steps);
   cudaFree(d_cnt);
+  return status;
+}
+
+int xrc_rc_set_skip_empty(xrc_rc* rc, int enable)
+{
+  XRC_CHECK_ARG(rc, "null ray caster");
+  rc->skip_empty = enable != 0;
+  return XRC_OK;
+}
+
+int xrc_rc_fetched_samples(xrc_rc* rc, uint32_t vol_idx, uint64_t* fetched)
+{
+  XRC_CHECK_ARG(rc && fetched, "null argument");
+  XRC_CHECK_ARG(rc->allocated, "xrc_rc_fetched_samples: allocate first");
+  XRC_CHECK_ARG(vol_idx < rc->vols.size(), "xrc_rc_fetched_samples: volume index out of range");
+  XRC_CHECK_ARG(rc->vols[vol_idx].layout == XRC_LAYOUT_PAX, "xrc_rc_fetched_samples: only for the PAX layout");
+  XRC_TRY(use_device(rc->ctx));
+  cudaStream_t st = rc->ctx->stream;
+  unsigned long long* d_cnt = nullptr;
+  XRC_CUDA(cudaMalloc(&d_cnt, sizeof(unsigned long long)));
+  cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), st);
+  DrrArgs a;
+  rc_fill_args(rc, vol_idx, &a);
+  a.sample_counter = d_cnt;
+  a.count_only = 1;
+  int status = launch_drr(a, XRC_LAYOUT_PAX, rc->kernel_id, st);
+  unsigned long long cnt = 0;
+  if (status == XRC_OK)
+  {
+    cudaMemcpyAsync(&cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, st);
+    const cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess)
+    {
+      set_error(std::string("xrc_rc_fetched_samples: ") + cudaGetErrorString(e));
+      status = XRC_ERR_CUDA;
+    }
+  }
+  cudaFree(d_cnt);
+  *fetched = cnt;
   return status;
 }
 

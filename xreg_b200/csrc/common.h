@@ -68,6 +68,10 @@ struct DeviceVolume
   void* pax[3] = {nullptr, nullptr, nullptr};
   uint32_t pax_sb[3] = {0, 0, 0};   // record strides of the mid / slow axis
   uint32_t pax_sc[3] = {0, 0, 0};
+  // empty-space map (drr.cu, "empty-space trimming"): one bit per 8^3-voxel block, set when any voxel of the
+  // block or of its 26 neighbours is non-zero; x-fastest, 32 blocks per word
+  uint32_t* occ = nullptr;
+  uint32_t occ_wx = 0, occ_ny = 0, occ_nz = 0;   // words per block row, block rows, block slices
 };
 
 // Arguments of the DRR kernels (passed by value).
@@ -95,9 +99,13 @@ struct DrrArgs
   int variant;                // tuning: bit0 = scalar (non-packed) FP32 math in the PAX kernel
   uint8_t* ray_mask;          // ray-info kernel only
   uint32_t* ray_steps;        // ray-info kernel only
+  const uint32_t* occ;        // empty-space map of the volume (nullptr = march every sample)
+  uint32_t occ_wx, occ_ny;
+  int count_only;             // instrumentation: count the samples the kernel would fetch, do not march / store
 };
 
 int repack_volume(const float* d_linear, DeviceVolume* v, int layout, cudaStream_t st);
+int build_occupancy(const float* d_linear, DeviceVolume* v, cudaStream_t st);
 void free_volume(DeviceVolume* v);
 int launch_drr(const DrrArgs& a, int layout, int kernel_id, cudaStream_t st);
 int launch_ray_info(const DrrArgs& a, cudaStream_t st);

@@ -652,6 +652,66 @@ __device__ __forceinline__ float pax_march(const PaxStack& st, float pa, float p
   return sum;
 }
 
+
+// ----------------------------------------------------------------------------
+// Empty-space trimming (exact).  A sample whose 8 corner voxels are all zero adds
+// +0 to the sequential f32 sum, so not fetching it changes nothing, bit for bit.
+// The volume carries a map with one bit per 8^3-voxel block, set when the block or
+// any of its 26 neighbours holds a non-zero voxel (built once in set_volumes).
+// If the bit at a sample's position is clear, every voxel within 8 voxels of it
+// (per axis) is zero, hence so are all samples whose ideal position lies within
+// (8 - 2) voxels: 1 voxel for the interpolation neighbour, 1/2 voxel for the f32
+// drift of the position chain (bounded by the `safe` test), and slack.  A ray
+// therefore checks one bit per m = floor(6 / max|step_axis|) samples, walks in from
+// both ends while the bits are clear, and marches only [s0, s1).  The warp then
+// marches the union of its lanes' ranges so that its lanes stay on the same stack
+// planes (coalescing is what the kernel lives on).  Sample positions still come
+// from the same chain of f32 additions as in the reference loop
+// (xregRayCastLineIntCPU.cpp:270-277): the skipped samples only lose their fetch.
+// ----------------------------------------------------------------------------
+constexpr int kOccShift = 3;             // 8^3-voxel blocks
+constexpr float kOccReach = 6.0f;        // (1 << kOccShift) - 2
+
+__device__ __forceinline__ bool occ_clear(const DrrArgs& a, float x, float y, float z)
+{
+  const int ix = min(max(__float2int_rd(x), 0), a.nx - 1) >> kOccShift;
+  const int iy = min(max(__float2int_rd(y), 0), a.ny - 1) >> kOccShift;
+  const int iz = min(max(__float2int_rd(z), 0), a.nz - 1) >> kOccShift;
+  const uint32_t w = __ldg(a.occ + ((size_t)((uint32_t)iz * a.occ_ny + (uint32_t)iy) * a.occ_wx + ((uint32_t)ix >> 5)));
+  return ((w >> (ix & 31)) & 1u) == 0u;
+}
+
+// [s0, s1) = the samples of this ray that may be non-zero
+__device__ __forceinline__ void trim_ray(const DrrArgs& a, const Ray& ray, uint32_t& s0, uint32_t& s1)
+{
+  const uint32_t n = ray.nsamples;
+  s0 = 0;
+  s1 = n;
+  const float smax = fmaxf(fabsf(ray.sx), fmaxf(fabsf(ray.sy), fabsf(ray.sz)));
+  if (!(smax <= kOccReach))
+    return;
+  const uint32_t m = (uint32_t)fminf(kOccReach / fmaxf(smax, 1.0e-3f), 64.0f);  // >= 1
+  while (s0 < n)
+  {
+    const float f = (float)s0;
+    if (!occ_clear(a, fmaf(f, ray.sx, ray.x), fmaf(f, ray.sy, ray.y), fmaf(f, ray.sz, ray.z)))
+      break;
+    s0 += m;
+  }
+  if (s0 >= n)
+  {
+    s0 = s1 = n;  // nothing but air
+    return;
+  }
+  while (s1 > s0)
+  {
+    const float f = (float)(s1 - 1u);
+    if (!occ_clear(a, fmaf(f, ray.sx, ray.x), fmaf(f, ray.sy, ray.y), fmaf(f, ray.sz, ray.z)))
+      break;
+    s1 = (s1 - s0 > m) ? s1 - m : s0;
+  }
+}
+
 __device__ __forceinline__ float sel3(int k, float v0, float v1, float v2) { return (k == 0) ? v0 : ((k == 1) ? v1 : v2); }
 
 template <int KERNEL_ID, bool PACK, int BATCH, int MINB>
@@ -748,10 +808,12 @@ __global__ void __launch_bounds__(kThreads, MINB) drr_pax_kernel(const DrrArgs a
     ray = setup_ray(cam_s, pc, a.step_size, a.nx, a.ny, a.nz, row, col);
 
   float sum = (KERNEL_ID == XRC_KERNEL_MAX) ? -3.402823466e+38f : 0.0f;
+  PaxStack st;
+  float a0 = 0.f, b0 = 0.f, c0 = 0.f, sa = 0.f, sb = 0.f, sc = 0.f;
+  bool safe = false;
   if (ray.hit)
   {
     const int k = axis_s, ka = (k == 2) ? 0 : k + 1, kb = (ka == 2) ? 0 : ka + 1;
-    PaxStack st;
     st.base = (const float4*)((k == 0) ? a.pax[0] : ((k == 1) ? a.pax[1] : a.pax[2]));
     st.Sb = (k == 0) ? a.pax_sb[0] : ((k == 1) ? a.pax_sb[1] : a.pax_sb[2]);
     st.Sc = (k == 0) ? a.pax_sc[0] : ((k == 1) ? a.pax_sc[1] : a.pax_sc[2]);
@@ -761,25 +823,46 @@ __global__ void __launch_bounds__(kThreads, MINB) drr_pax_kernel(const DrrArgs a
     st.ha = sel3(ka, hx, hy, hz);
     st.hb = sel3(kb, hx, hy, hz);
     st.hc = sel3(k, hx, hy, hz);
-    const float a0 = sel3(ka, ray.x, ray.y, ray.z), b0 = sel3(kb, ray.x, ray.y, ray.z), c0 = sel3(k, ray.x, ray.y, ray.z);
-    const float sa = sel3(ka, ray.sx, ray.sy, ray.sz), sb = sel3(kb, ray.sx, ray.sy, ray.sz), sc = sel3(k, ray.sx, ray.sy, ray.sz);
-    const uint32_t n = ray.nsamples;
+    a0 = sel3(ka, ray.x, ray.y, ray.z), b0 = sel3(kb, ray.x, ray.y, ray.z), c0 = sel3(k, ray.x, ray.y, ray.z);
+    sa = sel3(ka, ray.sx, ray.sy, ray.sz), sb = sel3(kb, ray.sx, ray.sy, ray.sz), sc = sel3(k, ray.sx, ray.sy, ray.sz);
     // drift bound: every add rounds by <= ulp(h)/2 <= h * 2^-24  ->  n * h < 2^23 keeps the
     // accumulated error below 1/2 voxel; the end points themselves lie within [-1/2, h + 1/2]
-    const float fn = (float)n;
+    const float fn = (float)ray.nsamples;
     const float ea = fmaf(fn, sa, a0), eb = fmaf(fn, sb, b0), ec = fmaf(fn, sc, c0);
     const float hmax = fmaxf(st.ha, fmaxf(st.hb, st.hc)) + 1.0f;
-    const bool safe = !(a.variant & 2) && (fn * hmax < 8388608.0f) && (fminf(a0, ea) > -0.5f) &&
-                      (fmaxf(a0, ea) < st.ha + 0.5f) && (fminf(b0, eb) > -0.5f) && (fmaxf(b0, eb) < st.hb + 0.5f) &&
-                      (fminf(c0, ec) > -0.5f) && (fmaxf(c0, ec) < st.hc + 0.5f);
-    if (safe)
-      sum = pax_march<KERNEL_ID, PACK, false, BATCH>(st, a0, b0, c0, sa, sb, sc, n);
-    else
-      sum = pax_march<KERNEL_ID, PACK, true, 1>(st, a0, b0, c0, sa, sb, sc, n);
-    sum = fmul(sum, a.step_size);  // xregRayCastLineIntCPU.cpp:279
+    safe = !(a.variant & 2) && (fn * hmax < 8388608.0f) && (fminf(a0, ea) > -0.5f) &&
+           (fmaxf(a0, ea) < st.ha + 0.5f) && (fminf(b0, eb) > -0.5f) && (fmaxf(b0, eb) < st.hb + 0.5f) &&
+           (fminf(c0, ec) > -0.5f) && (fmaxf(c0, ec) < st.hc + 0.5f);
   }
 
-  if (in_img)
+  // empty-space trimming (sum kernel only: a zero sample is neutral for +, not for max)
+  uint32_t s0 = 0, s1 = ray.nsamples;
+  if (KERNEL_ID == XRC_KERNEL_SUM && a.occ)
+  {
+    if (ray.hit && safe)
+      trim_ray(a, ray, s0, s1);
+    const uint32_t lo = __reduce_min_sync(0xffffffffu, (ray.hit && s1 > s0) ? s0 : 0xffffffffu);
+    const uint32_t hi = __reduce_max_sync(0xffffffffu, (ray.hit && s1 > s0) ? s1 : 0u);
+    if (ray.hit && s1 > s0)
+    {
+      s0 = lo;
+      s1 = min(hi, ray.nsamples);
+    }
+  }
+
+  if (ray.hit && s1 > s0 && !a.count_only)
+  {
+    for (uint32_t i = 0; i < s0; ++i)
+      pax_advance<PACK>(a0, b0, c0, sa, sb, sc);
+    if (safe)
+      sum = pax_march<KERNEL_ID, PACK, false, BATCH>(st, a0, b0, c0, sa, sb, sc, s1 - s0);
+    else
+      sum = pax_march<KERNEL_ID, PACK, true, 1>(st, a0, b0, c0, sa, sb, sc, s1 - s0);
+  }
+  if (ray.hit)
+    sum = fmul(sum, a.step_size);  // xregRayCastLineIntCPU.cpp:279
+
+  if (in_img && !a.count_only)
   {
     const size_t npix = (size_t)a.rows * a.cols;
     const size_t o = (size_t)proj * npix + (size_t)row * a.cols + col;
@@ -796,7 +879,7 @@ __global__ void __launch_bounds__(kThreads, MINB) drr_pax_kernel(const DrrArgs a
 
   if (a.sample_counter)
   {
-    unsigned long long n = ray.nsamples;
+    unsigned long long n = ray.hit ? (unsigned long long)(s1 - s0) : 0ull;  // samples actually fetched
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
       n += __shfl_xor_sync(0xffffffffu, n, o);
@@ -1013,8 +1096,84 @@ __global__ void repack_pax_kernel(const float* __restrict__ src, float4* __restr
   }
 }
 
+
+// ---- empty-space map: bit (bx, by, bz) = any non-zero voxel in blocks [bx-1, bx+1] x [by-1, by+1] x [bz-1, bz+1]
+__global__ void occ_raw_kernel(const float* __restrict__ src, uint8_t* __restrict__ raw, int nx, int ny, int nz, int gx,
+                               int gy)
+{
+  // one CTA (8 x 8 x 8 threads) per block
+  const int bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z;
+  const int x = (bx << kOccShift) + (threadIdx.x & 7), y = (by << kOccShift) + ((threadIdx.x >> 3) & 7),
+            z = (bz << kOccShift) + (threadIdx.x >> 6);
+  int nonzero = 0;
+  if (x < nx && y < ny && z < nz)
+    nonzero = (__float_as_uint(src[((size_t)z * ny + y) * nx + x]) & 0x7fffffffu) != 0u;  // +0 and -0 are empty
+  nonzero = __syncthreads_or(nonzero);
+  if (threadIdx.x == 0)
+    raw[((size_t)bz * gy + by) * gx + bx] = (uint8_t)(nonzero != 0);
+}
+
+__global__ void occ_dilate_kernel(const uint8_t* __restrict__ raw, uint32_t* __restrict__ occ, int gx, int gy, int gz,
+                                  int wx)
+{
+  const size_t total = (size_t)wx * gy * gz;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+  {
+    const int w = (int)(i % wx), by = (int)((i / wx) % gy), bz = (int)(i / ((size_t)wx * gy));
+    uint32_t bits = 0;
+    for (int b = 0; b < 32; ++b)
+    {
+      const int bx = 32 * w + b;
+      if (bx >= gx)
+        break;
+      int any = 0;
+      for (int dz = -1; dz <= 1; ++dz)
+        for (int dy = -1; dy <= 1; ++dy)
+          for (int dx = -1; dx <= 1; ++dx)
+          {
+            const int qx = bx + dx, qy = by + dy, qz = bz + dz;
+            if (qx >= 0 && qx < gx && qy >= 0 && qy < gy && qz >= 0 && qz < gz)
+              any |= raw[((size_t)qz * gy + qy) * gx + qx];
+          }
+      bits |= (uint32_t)(any != 0) << b;
+    }
+    occ[i] = bits;
+  }
+}
+
+int build_occupancy(const float* d_linear, DeviceVolume* v, cudaStream_t st)
+{
+  const int nx = (int)v->dims[0], ny = (int)v->dims[1], nz = (int)v->dims[2];
+  const int E = 1 << kOccShift;
+  const int gx = (nx + E - 1) / E, gy = (ny + E - 1) / E, gz = (nz + E - 1) / E;
+  const int wx = (gx + 31) / 32;
+  if (gy > 65535 || gz > 65535)
+    return XRC_OK;  // no map: every sample is marched
+  uint8_t* raw = nullptr;
+  XRC_CUDA(cudaMalloc(&raw, (size_t)gx * gy * gz));
+  if (cudaMalloc(&v->occ, sizeof(uint32_t) * (size_t)wx * gy * gz) != cudaSuccess)
+  {
+    cudaFree(raw);
+    XRC_FAIL(XRC_ERR_NOMEM, "build_occupancy: out of device memory");
+  }
+  occ_raw_kernel<<<dim3(gx, gy, gz), 512, 0, st>>>(d_linear, raw, nx, ny, nz, gx, gy);
+  occ_dilate_kernel<<<148 * 2, 256, 0, st>>>(raw, v->occ, gx, gy, gz, wx);
+  count_launch(2);
+  const cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(raw);
+  XRC_CUDA(e);
+  XRC_CUDA(cudaGetLastError());
+  v->occ_wx = (uint32_t)wx;
+  v->occ_ny = (uint32_t)gy;
+  v->occ_nz = (uint32_t)gz;
+  return XRC_OK;
+}
+
 void free_volume(DeviceVolume* v)
 {
+  if (v->occ)
+    cudaFree(v->occ);
+  v->occ = nullptr;
   for (int k = 0; k < 3; ++k)
   {
     if (v->pax[k])

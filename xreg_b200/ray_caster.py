@@ -374,6 +374,17 @@ class RayCasterLineIntCUDA:
                                         steps.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(S)))
         return mask, steps, int(S.value)
 
+    def set_skip_empty(self, enable: bool) -> None:
+        """Empty-space trimming of the sum kernel (exact, default on); off only for measurement."""
+        check(self._lib.xrc_rc_set_skip_empty(self.handle, 1 if enable else 0))
+
+    def fetched_samples(self, vol_idx: int = 0) -> int:
+        """Trilinear samples compute() actually fetches for the current poses (<= S of ray_info)."""
+        self._flush()
+        n = C.c_uint64()
+        check(self._lib.xrc_rc_fetched_samples(self.handle, int(vol_idx), C.byref(n)))
+        return int(n.value)
+
     def close(self) -> None:
         if self.handle:
             self._lib.xrc_rc_destroy(self.handle)
