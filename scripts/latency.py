@@ -37,6 +37,8 @@ def main():
         rc0.close()
         fn = regi.Intensity2D3DObjFn(ctx, vol, [cam], [fixed], metric=metric, max_pop=100,
                                      patch_radius=synth.patch_radius_for(det))
+        if os.environ.get("LAT_VARIANT"):   # kernel variant bits (drr.cu launch_pax_k), measurement only
+            fn.rc.set_layout_order(int(os.environ["LAT_VARIANT"]) << 1)
         for pop_n in ((1, 100) if not only else (int(only.split(",")[2]),)):
             reps = 200 if pop_n == 1 else 20
             if only:

@@ -74,7 +74,7 @@ def test_c3_multires_grad_ncc_population_then_single(ctx, xo, c3_scene, ds):
     for k in range(n_oracle):
         _drr_check(fn.rc.proj(k), ref[k], mask[k])
     assert np.max(np.abs(sims[:n_oracle] - xo.grad_ncc(fixed, ref))) <= SIM_TOL
-    # population 1 (NLopt / BOBYQA regime): same values, bitwise, in any order
+    # population 1 (NLopt / BOBYQA regime; poses travel in the kernel parameters): same values, bitwise, in any order
     for k in (5, 0, 77):
         one = fn(pop[k:k + 1])
         assert one.shape == (1,) and one[0] == sims[k]

@@ -130,6 +130,9 @@ struct xrc_rc
   float* d_bg = nullptr;
   int order = 0;
   bool skip_empty = true;  // empty-space trimming (exact; xrc_rc_set_skip_empty)
+  // latency regime (xrc_obj_fn with <= kInlinePoses projections): the poses in h_poses / h_cam_idx travel in the
+  // kernel parameters; d_poses is refreshed lazily if another entry point needs it
+  bool inline_poses = false;
 };
 
 struct xrc_sm
@@ -467,11 +470,19 @@ int xrc_rc_allocate(xrc_rc* rc, uint32_t max_projs)
   return XRC_OK;
 }
 
+static int rc_upload_poses(xrc_rc* rc, uint32_t n);
+
 int xrc_rc_set_num_projs(xrc_rc* rc, uint32_t n)
 {
   XRC_CHECK_ARG(rc, "null ray caster");
   XRC_CHECK_ARG(rc->allocated, "xrc_rc_set_num_projs: allocate first (capacity is fixed by xrc_rc_allocate)");
   XRC_CHECK_ARG(n <= rc->max_projs, "xrc_rc_set_num_projs: exceeds allocated capacity");
+  if (rc->inline_poses && n != rc->num_projs)
+  {
+    // keep the device copy coherent with what the caller last set before the count changes
+    XRC_TRY(use_device(rc->ctx));
+    XRC_TRY(rc_upload_poses(rc, rc->num_projs));
+  }
   rc->num_projs = n;
   return XRC_OK;
 }
@@ -500,6 +511,7 @@ static int rc_upload_poses(xrc_rc* rc, uint32_t n)
   cudaStream_t st = rc->ctx->stream;
   rc->ext_poses = nullptr;
   rc->ext_cam_idx = nullptr;
+  rc->inline_poses = false;
   XRC_CUDA(cudaMemcpyAsync(rc->d_poses, rc->h_poses, sizeof(float) * 12 * n, cudaMemcpyHostToDevice, st));
   XRC_CUDA(cudaMemcpyAsync(rc->d_cam_idx, rc->h_cam_idx, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
   XRC_CUDA(cudaEventRecord(rc->staged, st));
@@ -564,6 +576,7 @@ int xrc_rc_set_poses_device(xrc_rc* rc, uint32_t n, const float* dev_cam_to_phys
   XRC_CHECK_ARG(n == rc->num_projs, "xrc_rc_set_poses_device: pose count must equal num_projs");
   rc->ext_poses = dev_cam_to_phys;
   rc->ext_cam_idx = dev_cam_idx ? dev_cam_idx : rc->d_zero_idx;
+  rc->inline_poses = false;
   return XRC_OK;
 }
 
@@ -639,6 +652,12 @@ static void rc_fill_args(xrc_rc* rc, uint32_t vol_idx, DrrArgs* a)
     a->pax[k] = v.pax[k];
     a->pax_sb[k] = v.pax_sb[k];
     a->pax_sc[k] = v.pax_sc[k];
+  }
+  if (rc->inline_poses && !rc->ext_poses && rc->num_projs <= kInlinePoses)
+  {
+    a->use_inline = 1;
+    memcpy(a->inl_poses, rc->h_poses, sizeof(float) * 12 * rc->num_projs);
+    memcpy(a->inl_cam, rc->h_cam_idx, sizeof(uint32_t) * rc->num_projs);
   }
   a->occ = rc->skip_empty ? v.occ : nullptr;
   a->occ_wx = v.occ_wx;
@@ -778,7 +797,7 @@ int xrc_rc_fetched_samples(xrc_rc* rc, uint32_t vol_idx, uint64_t* fetched)
 // internal tuning hook (not part of the documented ABI surface): CTA ordering
 int xrc_rc_set_cta_order(xrc_rc* rc, int order)
 {
-  XRC_CHECK_ARG(rc && order >= 0 && order < 1024, "bad argument");
+  XRC_CHECK_ARG(rc && order >= 0 && order < (1 << 16), "bad argument");
   rc->order = order;  // bit 0: CTA order; bits 1..: kernel variant (measurement only)
   return XRC_OK;
 }
@@ -1119,7 +1138,8 @@ int xrc_sm_allocate(xrc_sm* sm, uint32_t max_imgs)
   XRC_CUDA(cudaMalloc(&sm->d_fixed, npix * sizeof(float)));
   XRC_CUDA(cudaMalloc(&sm->d_sims, max_imgs * sizeof(float)));
   XRC_CUDA(cudaMemsetAsync(sm->d_sims, 0, max_imgs * sizeof(float), sm->ctx->stream));
-  XRC_CUDA(cudaHostAlloc(&sm->h_sims, max_imgs * sizeof(float), cudaHostAllocDefault));
+  XRC_CUDA(cudaHostAlloc(&sm->h_sims, max_imgs * sizeof(float), cudaHostAllocMapped | cudaHostAllocPortable));
+  memset(sm->h_sims, 0, max_imgs * sizeof(float));
   if (sm->host_src)
     XRC_CUDA(cudaMalloc(&sm->d_mov, npix * max_imgs * sizeof(float)));
 
@@ -1247,6 +1267,7 @@ int xrc_sm_compute(xrc_sm* sm)
     f.sf0[0] = sm->sf0[0];
     f.f_sd[0] = sm->f_sd[0];
     f.sims = sm->d_sims;
+    f.sims_host = sm->h_sims;
     return launch_ncc_finalize(f, st);
   }
   if (sm->kind == XRC_SM_GRAD_NCC)
@@ -1274,6 +1295,7 @@ int xrc_sm_compute(xrc_sm* sm)
       f.f_sd[d] = sm->f_sd[d];
     }
     f.sims = sm->d_sims;
+    f.sims_host = sm->h_sims;
     return launch_ncc_finalize(f, st);
   }
 
@@ -1330,6 +1352,7 @@ int xrc_sm_compute(xrc_sm* sm)
   }
   f.divisor = sm->divisor;
   f.sims = sm->d_sims;
+    f.sims_host = sm->h_sims;
   return launch_patch_finalize(f, st);
 }
 
@@ -1406,10 +1429,8 @@ int xrc_eval_batch(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t n_
   XRC_TRY(xrc_eval_batch_async(rc, vol_idx, sms, n_views));
   cudaStream_t st = rc->ctx->stream;
   for (uint32_t v = 0; v < n_views; ++v)
-  {
     XRC_CHECK_ARG(n_per_view <= sms[v]->max_imgs, "xrc_eval_batch: n_per_view exceeds metric capacity");
-    XRC_CUDA(cudaMemcpyAsync(sms[v]->h_sims, sms[v]->d_sims, n_per_view * sizeof(float), cudaMemcpyDeviceToHost, st));
-  }
+  // the finalize kernels also write the scalars to h_sims (host-mapped pinned memory): no D2H copy to wait for
   XRC_CUDA(cudaStreamSynchronize(st));
   for (uint32_t v = 0; v < n_views; ++v)
     memcpy(sims_out + (size_t)v * n_per_view, sms[v]->h_sims, n_per_view * sizeof(float));
@@ -1487,7 +1508,22 @@ int xrc_obj_fn(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t n_view
       XRC_TRY(xrc_sm_bind_ray_caster(sms[v], rc, v * n_poses));
   }
   rc->ext_poses = nullptr;  // host poses take over from a caller's device buffer
-  XRC_TRY(xrc_rc_distribute_poses(rc, n_poses, cam_to_phys));
+  if (n_poses * n_views <= kInlinePoses)
+  {
+    // latency regime: no H2D copy, the (camera-major, xregRayCastInterface.cpp:97-114) poses ride in the kernel parameters
+    XRC_TRY(use_device(rc->ctx));
+    XRC_TRY(rc_wait_staging(rc));
+    uint32_t g = 0;
+    for (uint32_t c = 0; c < n_views; ++c)
+      for (uint32_t p = 0; p < n_poses; ++p, ++g)
+      {
+        memcpy(rc->h_poses + 12 * (size_t)g, cam_to_phys + 12 * (size_t)p, sizeof(float) * 12);
+        rc->h_cam_idx[g] = c;
+      }
+    rc->inline_poses = true;
+  }
+  else
+    XRC_TRY(xrc_rc_distribute_poses(rc, n_poses, cam_to_phys));
   std::vector<float> tmp;
   float* pv = per_view_out;
   if (!pv)

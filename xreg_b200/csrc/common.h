@@ -74,6 +74,8 @@ struct DeviceVolume
   uint32_t occ_wx = 0, occ_ny = 0, occ_nz = 0;   // words per block row, block rows, block slices
 };
 
+constexpr uint32_t kInlinePoses = 8;
+
 // Arguments of the DRR kernels (passed by value).
 struct DrrArgs
 {
@@ -102,6 +104,10 @@ struct DrrArgs
   const uint32_t* occ;        // empty-space map of the volume (nullptr = march every sample)
   uint32_t occ_wx, occ_ny;
   int count_only;             // instrumentation: count the samples the kernel would fetch, do not march / store
+  // small populations (latency regime): poses travel in the kernel parameters instead of an H2D copy
+  int use_inline;
+  float inl_poses[kInlinePoses * 12];
+  uint32_t inl_cam[kInlinePoses];
 };
 
 int repack_volume(const float* d_linear, DeviceVolume* v, int layout, cudaStream_t st);

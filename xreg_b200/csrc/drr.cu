@@ -54,8 +54,12 @@ struct ProjConst
   float p[3];
 };
 
-__device__ __forceinline__ void compute_proj_const(const DrrArgs& a, const xrc_cam& cam,
-                                                   const float* __restrict__ pose, ProjConst* pc)
+__device__ __forceinline__ uint32_t proj_cam_index(const DrrArgs& a, uint32_t proj)
+{
+  return a.use_inline ? a.inl_cam[proj] : a.cam_idx[proj];
+}
+
+__device__ __forceinline__ void compute_proj_const(const DrrArgs& a, const xrc_cam& cam, uint32_t proj, ProjConst* pc)
 {
   // executed by threads 0..11 then 0..2 of the CTA (see callers)
   const int t = threadIdx.x;
@@ -63,7 +67,17 @@ __device__ __forceinline__ void compute_proj_const(const DrrArgs& a, const xrc_c
   {
     const int r = t >> 2, c = t & 3;
     const float* A = a.phys_to_idx;
-    float v = dot3(A[4 * r], A[4 * r + 1], A[4 * r + 2], pose[c], pose[4 + c], pose[8 + c]);
+    float p0, p1, p2;  // column c of the pose
+    if (a.use_inline)
+    {
+      p0 = a.inl_poses[12 * proj + c], p1 = a.inl_poses[12 * proj + 4 + c], p2 = a.inl_poses[12 * proj + 8 + c];
+    }
+    else
+    {
+      const float* __restrict__ pose = a.poses + 12 * (size_t)proj;
+      p0 = pose[c], p1 = pose[4 + c], p2 = pose[8 + c];
+    }
+    float v = dot3(A[4 * r], A[4 * r + 1], A[4 * r + 2], p0, p1, p2);
     if (c == 3)
       v = fadd(v, A[4 * r + 3]);
     pc->X[t] = v;
@@ -387,7 +401,7 @@ __global__ void __launch_bounds__(kThreads) drr_kernel(const DrrArgs a)
   uint32_t proj, tile;
   cta_coords(a, proj, tile);
 
-  const uint32_t ci = a.cam_idx[proj];
+  const uint32_t ci = proj_cam_index(a, proj);
   {
     // stage the camera (25 words) in shared memory
     const uint32_t* src = reinterpret_cast<const uint32_t*>(a.cams + ci);
@@ -398,7 +412,7 @@ __global__ void __launch_bounds__(kThreads) drr_kernel(const DrrArgs a)
       cta_samples = 0ull;
   }
   __syncthreads();
-  compute_proj_const(a, cam_s, a.poses + 12 * (size_t)proj, &pc);
+  compute_proj_const(a, cam_s, proj, &pc);
 
   uint32_t row, col;
   thread_pixel(a, tile, row, col);
@@ -714,40 +728,38 @@ __device__ __forceinline__ void trim_ray(const DrrArgs& a, const Ray& ray, uint3
 
 __device__ __forceinline__ float sel3(int k, float v0, float v1, float v2) { return (k == 0) ? v0 : ((k == 1) ? v1 : v2); }
 
-template <int KERNEL_ID, bool PACK, int BATCH, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) drr_pax_kernel(const DrrArgs a)
+// ---- pieces shared by the two PAX kernels ----------------------------------------------------------
+struct PaxCta
 {
-  __shared__ ProjConst pc;
-  __shared__ xrc_cam cam_s;
-  __shared__ unsigned long long cta_samples;
-  __shared__ int axis_s, swap_s;
+  ProjConst pc;
+  xrc_cam cam;
+  unsigned long long cta_samples;
+  int axis, swap;
+};
 
-  uint32_t proj, tile;
-  cta_coords(a, proj, tile);
-
-  const uint32_t ci = a.cam_idx[proj];
+// Camera + pose constants to shared memory, then the stack (principal axis of the ray through pixel
+// (cr, cc), the tile centre) and the warp orientation.  Any choice gives the same samples; it only
+// decides the memory access pattern, so plain (contracted) arithmetic is fine here.  Returns the camera index.
+__device__ __forceinline__ uint32_t pax_cta_prologue(const DrrArgs& a, PaxCta& sh, uint32_t proj, uint32_t cr, uint32_t cc)
+{
+  const uint32_t ci = proj_cam_index(a, proj);
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(a.cams + ci);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(&cam_s);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&sh.cam);
     if (threadIdx.x < sizeof(xrc_cam) / 4)
       dst[threadIdx.x] = src[threadIdx.x];
     if (threadIdx.x == 0)
-      cta_samples = 0ull;
+      sh.cta_samples = 0ull;
   }
   __syncthreads();
-  compute_proj_const(a, cam_s, a.poses + 12 * (size_t)proj, &pc);
+  compute_proj_const(a, sh.cam, proj, &sh.pc);
 
   if (threadIdx.x == 0)
   {
-    // Principal axis of this tile's central ray and the detector direction that maps onto
-    // the stack's fast axis (index space).  Any choice gives the same samples; it only
-    // decides the memory access pattern, so plain (contracted) arithmetic is fine here.
-    const uint32_t tx = tile % a.tiles_x, ty = tile / a.tiles_x;
-    const uint32_t cr = min(ty * kTileH + kTileH / 2, a.rows - 1), cc = min(tx * kTileW + kTileW / 2, a.cols - 1);
-    const float det_z = ((cam_s.frame_type == 1) ? -1.0f : 1.0f) * cam_s.focal_len;
-    const float* Ki = cam_s.intrins_inv;
-    const float* E = cam_s.extrins_inv;
-    const float* X = pc.X;
+    const float det_z = ((sh.cam.frame_type == 1) ? -1.0f : 1.0f) * sh.cam.focal_len;
+    const float* Ki = sh.cam.intrins_inv;
+    const float* E = sh.cam.extrins_inv;
+    const float* X = sh.pc.X;
     // camera-frame images of (col, row, 1), d/dcol and d/drow
     float cv[3][3];
 #pragma unroll
@@ -757,8 +769,8 @@ __global__ void __launch_bounds__(kThreads, MINB) drr_pax_kernel(const DrrArgs a
       cv[1][r] = det_z * Ki[3 * r];
       cv[2][r] = det_z * Ki[3 * r + 1];
     }
-    if (cam_s.frame_type == 2)
-      cv[0][2] -= cam_s.focal_len;
+    if (sh.cam.frame_type == 2)
+      cv[0][2] -= sh.cam.focal_len;
     float iv[3][3];  // index-space: centre detector point, d/dcol, d/drow
 #pragma unroll
     for (int q = 0; q < 3; ++q)
@@ -771,23 +783,136 @@ __global__ void __launch_bounds__(kThreads, MINB) drr_pax_kernel(const DrrArgs a
       for (int r = 0; r < 3; ++r)
         iv[q][r] = X[4 * r] * w[0] + X[4 * r + 1] * w[1] + X[4 * r + 2] * w[2] + ((q == 0) ? X[4 * r + 3] : 0.0f);
     }
-    const float dx = fabsf(iv[0][0] - pc.p[0]), dy = fabsf(iv[0][1] - pc.p[1]), dz = fabsf(iv[0][2] - pc.p[2]);
+    const float dx = fabsf(iv[0][0] - sh.pc.p[0]), dy = fabsf(iv[0][1] - sh.pc.p[1]), dz = fabsf(iv[0][2] - sh.pc.p[2]);
     const int k = (dz >= dx && dz >= dy) ? 2 : ((dy >= dx) ? 1 : 0);
     const int ka = (k == 2) ? 0 : k + 1;
-    axis_s = k;
+    sh.axis = k;
     // quarter-warps (8 consecutive lanes) run along the detector direction that moves fastest along
     // axis a, so that their 8 records are consecutive in memory (1-2 L1 wavefronts per quarter)
-    swap_s = (fabsf(sel3(ka, iv[2][0], iv[2][1], iv[2][2])) > fabsf(sel3(ka, iv[1][0], iv[1][1], iv[1][2]))) ? 1 : 0;
+    sh.swap = (fabsf(sel3(ka, iv[2][0], iv[2][1], iv[2][2])) > fabsf(sel3(ka, iv[1][0], iv[1][1], iv[1][2]))) ? 1 : 0;
     if (a.variant & 16)
-      swap_s = 0;
+      sh.swap = 0;
   }
   __syncthreads();
+  return ci;
+}
+
+// Per-lane marching state of one ray in the chosen stack's (a, b, c) axes.
+struct PaxLane
+{
+  PaxStack st;
+  float a0, b0, c0, sa, sb, sc;
+  bool hit, safe;
+  uint32_t n;       // num_steps + 1
+  uint32_t s0, s1;  // samples to fetch: [s0, s1) (empty-space trimming; the whole warp shares s0)
+};
+
+template <int KERNEL_ID>
+__device__ __forceinline__ PaxLane pax_lane_setup(const DrrArgs& a, const PaxCta& sh, uint32_t row, uint32_t col, bool in_img)
+{
+  PaxLane L;
+  Ray ray;
+  ray.hit = false;
+  ray.nsamples = 0;
+  ray.x = ray.y = ray.z = ray.sx = ray.sy = ray.sz = 0.f;
+  if (in_img)
+    ray = setup_ray(sh.cam, sh.pc, a.step_size, a.nx, a.ny, a.nz, row, col);
+  L.hit = ray.hit;
+  L.n = ray.nsamples;
+  L.safe = false;
+  L.st.base = nullptr;
+  L.st.Sb = L.st.Sc = L.st.K = 0u;
+  L.st.ha = L.st.hb = L.st.hc = 0.f;
+  L.a0 = L.b0 = L.c0 = L.sa = L.sb = L.sc = 0.f;
+  if (ray.hit)
+  {
+    const int k = sh.axis, ka = (k == 2) ? 0 : k + 1, kb = (ka == 2) ? 0 : ka + 1;
+    PaxStack& st = L.st;
+    st.base = (const float4*)((k == 0) ? a.pax[0] : ((k == 1) ? a.pax[1] : a.pax[2]));
+    st.Sb = (k == 0) ? a.pax_sb[0] : ((k == 1) ? a.pax_sb[1] : a.pax_sb[2]);
+    st.Sc = (k == 0) ? a.pax_sc[0] : ((k == 1) ? a.pax_sc[1] : a.pax_sc[2]);
+    // rec = (ic+1)*Sc + (ib+1)*Sb + (ia+1) with i* = float_as_int(t*) - 0x4B400000
+    st.K = (st.Sc + st.Sb + 1u) - 0x4B400000u * (st.Sc + st.Sb + 1u);
+    const float hx = (float)(a.nx - 1), hy = (float)(a.ny - 1), hz = (float)(a.nz - 1);
+    st.ha = sel3(ka, hx, hy, hz);
+    st.hb = sel3(kb, hx, hy, hz);
+    st.hc = sel3(k, hx, hy, hz);
+    L.a0 = sel3(ka, ray.x, ray.y, ray.z), L.b0 = sel3(kb, ray.x, ray.y, ray.z), L.c0 = sel3(k, ray.x, ray.y, ray.z);
+    L.sa = sel3(ka, ray.sx, ray.sy, ray.sz), L.sb = sel3(kb, ray.sx, ray.sy, ray.sz), L.sc = sel3(k, ray.sx, ray.sy, ray.sz);
+    // drift bound: every add rounds by <= ulp(h)/2 <= h * 2^-24  ->  n * h < 2^23 keeps the
+    // accumulated error below 1/2 voxel; the end points themselves lie within [-1/2, h + 1/2]
+    const float fn = (float)ray.nsamples;
+    const float ea = fmaf(fn, L.sa, L.a0), eb = fmaf(fn, L.sb, L.b0), ec = fmaf(fn, L.sc, L.c0);
+    const float hmax = fmaxf(st.ha, fmaxf(st.hb, st.hc)) + 1.0f;
+    L.safe = !(a.variant & 2) && (fn * hmax < 8388608.0f) && (fminf(L.a0, ea) > -0.5f) &&
+             (fmaxf(L.a0, ea) < st.ha + 0.5f) && (fminf(L.b0, eb) > -0.5f) && (fmaxf(L.b0, eb) < st.hb + 0.5f) &&
+             (fminf(L.c0, ec) > -0.5f) && (fmaxf(L.c0, ec) < st.hc + 0.5f);
+  }
+
+  // empty-space trimming (sum kernel only: a zero sample is neutral for +, not for max)
+  L.s0 = 0;
+  L.s1 = ray.nsamples;
+  if (KERNEL_ID == XRC_KERNEL_SUM && a.occ)
+  {
+    if (ray.hit && L.safe)
+      trim_ray(a, ray, L.s0, L.s1);
+    const uint32_t lo = __reduce_min_sync(0xffffffffu, (ray.hit && L.s1 > L.s0) ? L.s0 : 0xffffffffu);
+    const uint32_t hi = __reduce_max_sync(0xffffffffu, (ray.hit && L.s1 > L.s0) ? L.s1 : 0u);
+    if (ray.hit && L.s1 > L.s0)
+    {
+      L.s0 = lo;
+      L.s1 = min(hi, ray.nsamples);
+    }
+  }
+  return L;
+}
+
+// RayCasterCPU::pre_compute + the store of ComputeLineInts (xregRayCastBaseCPU.cpp:128-158, xregRayCastLineIntCPU.cpp:279-285)
+template <int KERNEL_ID>
+__device__ __forceinline__ void pax_store(const DrrArgs& a, uint32_t proj, uint32_t ci, uint32_t row, uint32_t col, float sum)
+{
+  const size_t npix = (size_t)a.rows * a.cols;
+  const size_t o = (size_t)proj * npix + (size_t)row * a.cols + col;
+  float base_v;
+  if (a.init_mode == 0)
+    base_v = a.default_bg;
+  else if (a.init_mode == 1)
+    base_v = __ldg(a.bg + (size_t)ci * npix + (size_t)row * a.cols + col);
+  else
+    base_v = a.out[o];
+  const float aa = fadd(0.0f, fmul(sum, 1.0f));  // :282
+  a.out[o] = (KERNEL_ID == XRC_KERNEL_MAX) ? fmaxf(base_v, aa) : fadd(base_v, aa);  // :285
+}
+
+// instrumentation: add this thread's fetched-sample count to the global counter (all threads of the CTA call it)
+__device__ __forceinline__ void pax_count(const DrrArgs& a, PaxCta& sh, unsigned long long n)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    n += __shfl_xor_sync(0xffffffffu, n, o);
+  if ((threadIdx.x & 31) == 0)
+    atomicAdd(&sh.cta_samples, n);
+  __syncthreads();
+  if (threadIdx.x == 0)
+    atomicAdd(a.sample_counter, sh.cta_samples);
+}
+
+// ---- one thread per pixel, CTA = 16 x 16 pixels of one projection ---------------------------------------
+template <int KERNEL_ID, bool PACK, int BATCH, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) drr_pax_kernel(const DrrArgs a)
+{
+  __shared__ PaxCta sh;
+
+  uint32_t proj, tile;
+  cta_coords(a, proj, tile);
+  const uint32_t tx = tile % a.tiles_x, ty = tile / a.tiles_x;
+  const uint32_t ci = pax_cta_prologue(a, sh, proj, min(ty * kTileH + kTileH / 2, a.rows - 1),
+                                       min(tx * kTileW + kTileW / 2, a.cols - 1));
 
   uint32_t row, col;
   {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t tx = tile % a.tiles_x, ty = tile / a.tiles_x;
-    if (swap_s)
+    if (sh.swap)
     {
       // warp = 4 (cols) x 8 (rows); 4 x 2 warps per 16 x 16 tile
       col = tx * kTileW + (warp >> 1) * 4 + (lane >> 3);
@@ -800,95 +925,25 @@ __global__ void __launch_bounds__(kThreads, MINB) drr_pax_kernel(const DrrArgs a
     }
   }
   const bool in_img = (row < a.rows) && (col < a.cols);
-
-  Ray ray;
-  ray.hit = false;
-  ray.nsamples = 0;
-  if (in_img)
-    ray = setup_ray(cam_s, pc, a.step_size, a.nx, a.ny, a.nz, row, col);
+  PaxLane L = pax_lane_setup<KERNEL_ID>(a, sh, row, col, in_img);
 
   float sum = (KERNEL_ID == XRC_KERNEL_MAX) ? -3.402823466e+38f : 0.0f;
-  PaxStack st;
-  float a0 = 0.f, b0 = 0.f, c0 = 0.f, sa = 0.f, sb = 0.f, sc = 0.f;
-  bool safe = false;
-  if (ray.hit)
+  if (L.hit && L.s1 > L.s0 && !a.count_only)
   {
-    const int k = axis_s, ka = (k == 2) ? 0 : k + 1, kb = (ka == 2) ? 0 : ka + 1;
-    st.base = (const float4*)((k == 0) ? a.pax[0] : ((k == 1) ? a.pax[1] : a.pax[2]));
-    st.Sb = (k == 0) ? a.pax_sb[0] : ((k == 1) ? a.pax_sb[1] : a.pax_sb[2]);
-    st.Sc = (k == 0) ? a.pax_sc[0] : ((k == 1) ? a.pax_sc[1] : a.pax_sc[2]);
-    // rec = (ic+1)*Sc + (ib+1)*Sb + (ia+1) with i* = float_as_int(t*) - 0x4B400000
-    st.K = (st.Sc + st.Sb + 1u) - 0x4B400000u * (st.Sc + st.Sb + 1u);
-    const float hx = (float)(a.nx - 1), hy = (float)(a.ny - 1), hz = (float)(a.nz - 1);
-    st.ha = sel3(ka, hx, hy, hz);
-    st.hb = sel3(kb, hx, hy, hz);
-    st.hc = sel3(k, hx, hy, hz);
-    a0 = sel3(ka, ray.x, ray.y, ray.z), b0 = sel3(kb, ray.x, ray.y, ray.z), c0 = sel3(k, ray.x, ray.y, ray.z);
-    sa = sel3(ka, ray.sx, ray.sy, ray.sz), sb = sel3(kb, ray.sx, ray.sy, ray.sz), sc = sel3(k, ray.sx, ray.sy, ray.sz);
-    // drift bound: every add rounds by <= ulp(h)/2 <= h * 2^-24  ->  n * h < 2^23 keeps the
-    // accumulated error below 1/2 voxel; the end points themselves lie within [-1/2, h + 1/2]
-    const float fn = (float)ray.nsamples;
-    const float ea = fmaf(fn, sa, a0), eb = fmaf(fn, sb, b0), ec = fmaf(fn, sc, c0);
-    const float hmax = fmaxf(st.ha, fmaxf(st.hb, st.hc)) + 1.0f;
-    safe = !(a.variant & 2) && (fn * hmax < 8388608.0f) && (fminf(a0, ea) > -0.5f) &&
-           (fmaxf(a0, ea) < st.ha + 0.5f) && (fminf(b0, eb) > -0.5f) && (fmaxf(b0, eb) < st.hb + 0.5f) &&
-           (fminf(c0, ec) > -0.5f) && (fmaxf(c0, ec) < st.hc + 0.5f);
-  }
-
-  // empty-space trimming (sum kernel only: a zero sample is neutral for +, not for max)
-  uint32_t s0 = 0, s1 = ray.nsamples;
-  if (KERNEL_ID == XRC_KERNEL_SUM && a.occ)
-  {
-    if (ray.hit && safe)
-      trim_ray(a, ray, s0, s1);
-    const uint32_t lo = __reduce_min_sync(0xffffffffu, (ray.hit && s1 > s0) ? s0 : 0xffffffffu);
-    const uint32_t hi = __reduce_max_sync(0xffffffffu, (ray.hit && s1 > s0) ? s1 : 0u);
-    if (ray.hit && s1 > s0)
-    {
-      s0 = lo;
-      s1 = min(hi, ray.nsamples);
-    }
-  }
-
-  if (ray.hit && s1 > s0 && !a.count_only)
-  {
-    for (uint32_t i = 0; i < s0; ++i)
-      pax_advance<PACK>(a0, b0, c0, sa, sb, sc);
-    if (safe)
-      sum = pax_march<KERNEL_ID, PACK, false, BATCH>(st, a0, b0, c0, sa, sb, sc, s1 - s0);
+    for (uint32_t i = 0; i < L.s0; ++i)
+      pax_advance<PACK>(L.a0, L.b0, L.c0, L.sa, L.sb, L.sc);
+    if (L.safe)
+      sum = pax_march<KERNEL_ID, PACK, false, BATCH>(L.st, L.a0, L.b0, L.c0, L.sa, L.sb, L.sc, L.s1 - L.s0);
     else
-      sum = pax_march<KERNEL_ID, PACK, true, 1>(st, a0, b0, c0, sa, sb, sc, s1 - s0);
+      sum = pax_march<KERNEL_ID, PACK, true, 1>(L.st, L.a0, L.b0, L.c0, L.sa, L.sb, L.sc, L.s1 - L.s0);
   }
-  if (ray.hit)
+  if (L.hit)
     sum = fmul(sum, a.step_size);  // xregRayCastLineIntCPU.cpp:279
 
   if (in_img && !a.count_only)
-  {
-    const size_t npix = (size_t)a.rows * a.cols;
-    const size_t o = (size_t)proj * npix + (size_t)row * a.cols + col;
-    float base_v;
-    if (a.init_mode == 0)
-      base_v = a.default_bg;
-    else if (a.init_mode == 1)
-      base_v = __ldg(a.bg + (size_t)ci * npix + (size_t)row * a.cols + col);
-    else
-      base_v = a.out[o];
-    const float aa = fadd(0.0f, fmul(sum, 1.0f));  // :282
-    a.out[o] = (KERNEL_ID == XRC_KERNEL_MAX) ? fmaxf(base_v, aa) : fadd(base_v, aa);  // :285
-  }
-
+    pax_store<KERNEL_ID>(a, proj, ci, row, col, sum);
   if (a.sample_counter)
-  {
-    unsigned long long n = ray.hit ? (unsigned long long)(s1 - s0) : 0ull;  // samples actually fetched
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-      n += __shfl_xor_sync(0xffffffffu, n, o);
-    if ((threadIdx.x & 31) == 0)
-      atomicAdd(&cta_samples, n);
-    __syncthreads();
-    if (threadIdx.x == 0)
-      atomicAdd(a.sample_counter, cta_samples);
-  }
+    pax_count(a, sh, L.hit ? (unsigned long long)(L.s1 - L.s0) : 0ull);  // samples actually fetched
 }
 
 template <int KERNEL_ID>
@@ -907,9 +962,8 @@ static int launch_pax_k(const DrrArgs& a, cudaStream_t st)
   {
     // Default: scalar FP32 (FFMA / FADD issue to both FMA pipes; the packed f32x2 forms save issue slots the
     // loop does not need and measured 1 % slower).  Throughput regime (a CMA-ES population: more CTAs than fit
-    // at once): one sample group in flight ahead, 5 CTAs / 40 warps per SM.  Latency regime (population 1,
-    // BOBYQA: the whole grid is resident in one wave and every ray is a serial chain of L2-latency loads): spend
-    // the idle registers on a deeper software pipeline.  All variants add the same values in the same order.
+    // at once): one sample group in flight ahead, 5 CTAs / 40 warps per SM.  Few CTAs (one wave): spend the
+    // idle registers on a deeper software pipeline.  All variants add the same values in the same order.
     if (nblocks <= 148u * 2u)
       drr_pax_kernel<KERNEL_ID, false, 4, 2><<<nblocks, kThreads, 0, st>>>(a);
     else if (nblocks <= 148u * 4u)
@@ -949,7 +1003,7 @@ __global__ void __launch_bounds__(kThreads) ray_info_kernel(const DrrArgs a)
   __shared__ xrc_cam cam_s;
   uint32_t proj, tile;
   cta_coords(a, proj, tile);
-  const uint32_t ci = a.cam_idx[proj];
+  const uint32_t ci = proj_cam_index(a, proj);
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(a.cams + ci);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&cam_s);
@@ -957,7 +1011,7 @@ __global__ void __launch_bounds__(kThreads) ray_info_kernel(const DrrArgs a)
       dst[threadIdx.x] = src[threadIdx.x];
   }
   __syncthreads();
-  compute_proj_const(a, cam_s, a.poses + 12 * (size_t)proj, &pc);
+  compute_proj_const(a, cam_s, proj, &pc);
   uint32_t row, col;
   thread_pixel(a, tile, row, col);
   unsigned long long n = 0ull;

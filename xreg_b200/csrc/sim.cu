@@ -403,24 +403,49 @@ int launch_moments(const MomentArgs& a, cudaStream_t st)
   return XRC_OK;
 }
 
-// one warp per image: fixed-order reduction of the partials, then
+// one CTA per image: fixed-order reduction of the partials (thread t sums partials t, t + 256, ...; warp
+// shuffles; the 8 warp totals in order), then
 // ncc = (Smf - mu_m * Sf0) / (N sigma_f sigma_m), sim = 0.5 (1 - ncc)  (:182,205)
-__global__ void ncc_finalize_kernel(const NccFinalizeArgs a)
+constexpr int kFinalizeThreads = 256;
+
+__global__ void __launch_bounds__(kFinalizeThreads) ncc_finalize_kernel(const NccFinalizeArgs a)
 {
-  const int img = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (img >= (int)a.n_imgs)
-    return;
+  __shared__ double wsum[kFinalizeThreads / 32][6];
+  const int img = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nv = 3 * (int)a.n_dirs;
   double s[6] = {0, 0, 0, 0, 0, 0};
   const double* p = a.partials + (size_t)img * a.n_parts * nv;
-  for (uint32_t k = lane; k < a.n_parts; k += 32)
-    for (int q = 0; q < nv; ++q)
-      s[q] += p[(size_t)k * nv + q];
-  for (int q = 0; q < nv; ++q)
+  for (uint32_t k = threadIdx.x; k < a.n_parts; k += kFinalizeThreads)
+  {
+    double v[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q)
+      v[q] = (q < nv) ? p[(size_t)k * nv + q] : 0.0;
+#pragma unroll
+    for (int q = 0; q < 6; ++q)
+      s[q] += v[q];
+  }
+#pragma unroll
+  for (int q = 0; q < 6; ++q)
     s[q] = warp_sum(s[q]);
   if (lane == 0)
   {
+#pragma unroll
+    for (int q = 0; q < 6; ++q)
+      wsum[warp][q] = s[q];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+#pragma unroll
+    for (int q = 0; q < 6; ++q)
+    {
+      double t = wsum[0][q];
+      for (int w = 1; w < kFinalizeThreads / 32; ++w)
+        t += wsum[w][q];
+      s[q] = t;
+    }
     float sim_dir[2] = {0.f, 0.f};
     for (uint32_t d = 0; d < a.n_dirs; ++d)
     {
@@ -434,7 +459,10 @@ __global__ void ncc_finalize_kernel(const NccFinalizeArgs a)
       const float ncc = num / (((float)a.n_eff * a.f_sd[d]) * sd);
       sim_dir[d] = (1.0f - ncc) * 0.5f;
     }
-    a.sims[img] = (a.n_dirs == 1) ? sim_dir[0] : (float)(0.5 * ((double)sim_dir[0] + (double)sim_dir[1]));
+    const float sim = (a.n_dirs == 1) ? sim_dir[0] : (float)(0.5 * ((double)sim_dir[0] + (double)sim_dir[1]));
+    a.sims[img] = sim;
+    if (a.sims_host)
+      a.sims_host[img] = sim;
   }
 }
 
@@ -442,8 +470,7 @@ int launch_ncc_finalize(const NccFinalizeArgs& a, cudaStream_t st)
 {
   if (!a.n_imgs)
     return XRC_OK;
-  const int wpb = 4;
-  ncc_finalize_kernel<<<(a.n_imgs + wpb - 1) / wpb, wpb * 32, 0, st>>>(a);
+  ncc_finalize_kernel<<<a.n_imgs, kFinalizeThreads, 0, st>>>(a);
   count_launch();
   XRC_CUDA(cudaGetLastError());
   return XRC_OK;
@@ -860,28 +887,34 @@ int launch_patch_fixed_stats(const PatchArgs& a, cudaStream_t st) { return launc
 
 // image score = sum_k w_k s_k / divisor per direction (:262-287), then
 // 0.5 (x + y) for the gradient variant (xregImgSimMetric2DPatchGradNCCCPU.cpp:222)
-__global__ void patch_finalize_kernel(const PatchFinalizeArgs a)
+// one warp per image: lane l sums partials l, l + 32, ... in order, then a shuffle tree (fixed order)
+__global__ void __launch_bounds__(32) patch_finalize_kernel(const PatchFinalizeArgs a)
 {
-  const uint32_t img = blockIdx.x * blockDim.x + threadIdx.x;
-  if (img >= a.n_imgs)
-    return;
+  const uint32_t img = blockIdx.x;
   float sd[2] = {0.f, 0.f};
   for (uint32_t d = 0; d < a.n_dirs; ++d)
   {
     double s = 0.0;
     const double* p = a.partials + ((size_t)img * a.n_dirs + d) * a.n_parts;
-    for (uint32_t k = 0; k < a.n_parts; ++k)
+    for (uint32_t k = threadIdx.x; k < a.n_parts; k += 32)
       s += p[k];
+    s = warp_sum(s);
     sd[d] = (float)(s / a.divisor);
   }
-  a.sims[img] = (a.n_dirs == 1) ? sd[0] : (float)(0.5 * ((double)sd[0] + (double)sd[1]));
+  if (threadIdx.x == 0)
+  {
+    const float sim = (a.n_dirs == 1) ? sd[0] : (float)(0.5 * ((double)sd[0] + (double)sd[1]));
+    a.sims[img] = sim;
+    if (a.sims_host)
+      a.sims_host[img] = sim;
+  }
 }
 
 int launch_patch_finalize(const PatchFinalizeArgs& a, cudaStream_t st)
 {
   if (!a.n_imgs)
     return XRC_OK;
-  patch_finalize_kernel<<<(a.n_imgs + 127) / 128, 128, 0, st>>>(a);
+  patch_finalize_kernel<<<a.n_imgs, 32, 0, st>>>(a);
   count_launch();
   XRC_CUDA(cudaGetLastError());
   return XRC_OK;

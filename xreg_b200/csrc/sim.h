@@ -52,6 +52,7 @@ struct NccFinalizeArgs
   double sf0[2];           // sum of zero-mean fixed (over mask)
   float f_sd[2];
   float* sims;
+  float* sims_host;        // optional host-mapped copy (pinned): saves the D2H memcpy of the scalars
 };
 
 struct PatchArgs
@@ -85,6 +86,7 @@ struct PatchFinalizeArgs
   uint32_t n_imgs, n_dirs, n_parts;
   double divisor;  // num_patches (mean), total weight, or 1
   float* sims;
+  float* sims_host;  // optional host-mapped copy (pinned)
 };
 
 int launch_grad(const GradArgs& a, cudaStream_t st);
