@@ -15,7 +15,7 @@ __device__ __forceinline__ float total(float4 v) { return (v.x + v.y) + (v.z + v
 
 template <typename T>
 __global__ void __launch_bounds__(1024) gather(const T* __restrict__ base, const uint32_t* __restrict__ offs, int nsets,
-                                               float* out, long long* clk)
+                                               float* out, long long* clk, uint32_t lane_mask)
 {
   // offs: [nsets][32] element offsets for the lanes of a warp; every thread keeps UNROLL of them in
   // registers and re-issues the same patterns shifted by a multiple of 128 elements (alignment-preserving)
@@ -30,9 +30,14 @@ __global__ void __launch_bounds__(1024) gather(const T* __restrict__ base, const
   {
     const uint32_t shift = (uint32_t)((i >> 3) & 7) * 128u;
     T v[UNROLL];
+    const bool on = (lane_mask >> lane) & 1u;  // predicated-off lanes issue no access
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u)
-      v[u] = __ldg(base + ((o[u] + shift) & 2047u));
+    {
+      v[u] = T();
+      if (on)
+        v[u] = __ldg(base + ((o[u] + shift) & 2047u));
+    }
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u)
       acc += total(v[u]);
@@ -44,7 +49,7 @@ __global__ void __launch_bounds__(1024) gather(const T* __restrict__ base, const
 }
 
 template <typename T>
-void run(const char* name, const std::vector<uint32_t>& h_offs, int nsets, size_t n_elems)
+void run(const char* name, const std::vector<uint32_t>& h_offs, int nsets, size_t n_elems, uint32_t lane_mask = 0xffffffffu)
 {
   T* base;
   uint32_t* offs;
@@ -57,7 +62,7 @@ void run(const char* name, const std::vector<uint32_t>& h_offs, int nsets, size_
   cudaMalloc(&out, 148 * 1024 * 4);
   cudaMalloc(&clk, 148 * 8);
   for (int rep = 0; rep < 2; ++rep)
-    gather<T><<<148, 1024>>>(base, offs, nsets, out, clk);
+    gather<T><<<148, 1024>>>(base, offs, nsets, out, clk, lane_mask);
   cudaDeviceSynchronize();
   long long h[148];
   cudaMemcpy(h, clk, sizeof(h), cudaMemcpyDeviceToHost);
@@ -99,6 +104,11 @@ int main()
       for (int l = 0; l < 8; ++l) o[s * 32 + q * 8 + l] = b + (uint32_t)(frac + 0.49f * l);
     }
   run<float4>("LDG.128 DRR-like, no line crossing", o, nsets, n_elems);
+  // predication: does a quarter-warp without active lanes cost a data-stage pass?
+  run<float4>("  same, quarters 0-1 active (16 lanes)", o, nsets, n_elems, 0x0000ffffu);
+  run<float4>("  same, quarter 0 active (8 lanes)", o, nsets, n_elems, 0x000000ffu);
+  run<float4>("  same, even lanes active (16 lanes)", o, nsets, n_elems, 0x55555555u);
+  run<float4>("  same, 1 lane per quarter active", o, nsets, n_elems, 0x01010101u);
   // P3: all 32 lanes the same record
   for (int s = 0; s < nsets; ++s) { const uint32_t b = rnd() % n_elems; for (int l = 0; l < 32; ++l) o[s * 32 + l] = b; }
   run<float4>("LDG.128 broadcast (1 record)", o, nsets, n_elems);
