@@ -252,6 +252,23 @@ int xrc_eval_batch_async(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint3
  * n_views x n_poses.  n_views must equal the number of camera models.  One synchronisation. */
 int xrc_obj_fn(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t n_views, uint32_t n_poses,
                const float* cam_to_phys, float* sims_out, float* per_view_out);
+/* The objective for several moving objects (Intensity2D3DRegi::obj_fn's loop over volumes,
+ * xregIntensity2D3DRegi.cpp:594-629): object j (volume vol_idx[j], poses cam_to_phys[j * n_poses .. (j + 1) * n_poses))
+ * is ray cast into the same n_views x n_poses projections -- the first object with the REPLACE store method (on top of
+ * the per-camera background projections when use_bg_projs != 0, the reference's has_a_static_vol_ case), the others
+ * with ACCUM -- then every view's metric, gather, mean over views.  The ray caster's own store method / background
+ * settings are untouched on return. */
+int xrc_obj_fn_objects(xrc_rc* rc, uint32_t n_objs, const uint32_t* vol_idx, xrc_sm* const* sms, uint32_t n_views,
+                       uint32_t n_poses, const float* cam_to_phys, int use_bg_projs, float* sims_out, float* per_view_out);
+/* The same objective spread over several GPUs from ONE host thread (the reference's optimiser loops are single
+ * threaded, SURVEY 8(b) "Threading"): device d owns rcs[d] and the n_views metrics
+ * sms[d * n_views .. d * n_views + n_views), each configured exactly like the single-device objects (same volume,
+ * cameras, fixed images, parameters; one xrc_ctx per device).  The population is cut into contiguous balanced chunks
+ * (the first n_poses % n_dev devices take one pose more), every device's work is enqueued before any is waited for,
+ * and only the n_views x n_poses scalars come back.  Results equal xrc_obj_fn's bit for bit (a pose's value does not
+ * depend on its batch).  Each rcs[d] must be allocated for ceil(n_poses / n_dev) * n_views projections. */
+int xrc_obj_fn_multi(uint32_t n_dev, xrc_rc* const* rcs, xrc_sm* const* sms, uint32_t vol_idx, uint32_t n_views,
+                     uint32_t n_poses, const float* cam_to_phys, float* sims_out, float* per_view_out);
 /* Same from optimiser variables: pose_p = pre * ExpSE3(params_p) * post with
  * SE3OptVarsLieAlg (lib/regi/xregSE3OptVars.cpp:128-137; params = [w_x w_y w_z v_x v_y v_z]) and the
  * intermediate-frame composition of apply_inter_transforms_for_obj_fn (xregIntensity2D3DRegi.cpp:1049-1071).

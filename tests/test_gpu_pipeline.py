@@ -66,6 +66,76 @@ def test_objective_from_se3_parameters(ctx, small_scene):
     assert abs(one[0] - b[3]) <= 1e-7
 
 
+def _device_lists():
+    import torch
+
+    lists = [[0, 0], [0, 0, 0]]          # several contexts / streams on one GPU: always available
+    if torch.cuda.device_count() >= 2:
+        lists.append(list(range(min(torch.cuda.device_count(), 8))))
+    return lists
+
+
+@pytest.mark.parametrize("metric", ["patch-grad-ncc", "grad-ncc"])
+def test_multi_device_objective_equals_single_device(ctx, xo, small_scene, metric):
+    """xrc_obj_fn_multi: the population split over several device replicas from one host thread gives the
+    single-device values bit for bit, for even / uneven chunks, fewer poses than devices, and two views."""
+    vol, cam, nominal = small_scene
+    cam2 = CameraModel().setup(380.0, cam.num_det_rows, cam.num_det_cols, 1.7, 1.4)
+    cams = [cam, cam2]
+    pop = synth.pose_population(vol, nominal, 11)
+    xcams = [xo.cam_struct(c) for c in cams]
+    fixed = [synth.add_noise(xo.drr(vol.data, vol.idx_to_phys(), [xc], to12(pop[:1]))[0], seed=s) for s, xc in enumerate(xcams)]
+    single = regi.Intensity2D3DObjFn(ctx, vol, cams, fixed, metric=metric, max_pop=11, patch_radius=6)
+    ref = single(pop)
+    ref_pv = np.stack([sm.sim_vals()[:11] for sm in single.sims])
+    for devices in _device_lists():
+        multi = regi.MultiDeviceObjFn(devices, vol, cams, fixed, max_pop=11, metric=metric, patch_radius=6)
+        got = multi(pop)
+        np.testing.assert_array_equal(got, ref)
+        np.testing.assert_array_equal(multi.per_view, ref_pv)
+        np.testing.assert_array_equal(multi(pop[3:10]), ref[3:10])       # 7 poses: uneven chunks
+        np.testing.assert_array_equal(multi(pop[5:6]), ref[5:6])         # 1 pose: the other devices idle
+        np.testing.assert_array_equal(multi(pop[::-1]), ref[::-1])
+        with pytest.raises(xreg_b200.XregError):
+            multi(np.concatenate([pop, pop]))                            # over capacity
+        multi.close()
+
+
+@pytest.mark.parametrize("n_poses", [1, 5])
+def test_multi_object_objective_matches_oracle(ctx, xo, small_scene, n_poses):
+    """xrc_obj_fn_objects: two moving volumes with their own pose populations accumulated into the same projections
+    (first REPLACE, then ACCUM; xregIntensity2D3DRegi.cpp:594-629), with and without a static background projection."""
+    vol, cam, nominal = small_scene
+    rng = np.random.default_rng(11)
+    d2 = np.zeros((30, 36, 40), f32)
+    d2[6:22, 8:30, 10:34] = rng.uniform(0.02, 0.06, (16, 22, 24)).astype(f32)
+    vol2 = xreg_b200.Volume(d2, spacing=(1.2, 0.9, 1.1), origin=(-20.0, -12.0, -10.0), direction=np.eye(3))
+    xcam = [xo.cam_struct(cam)]
+    pop_a = synth.pose_population(vol, nominal, n_poses, seed=1)
+    pop_b = synth.pose_population(vol, nominal, n_poses, seed=2, sigma=(8, 8, 8, 6, 6, 6))
+    fixed = synth.add_noise(xo.drr(vol.data, vol.idx_to_phys(), xcam, to12(pop_a[:1]))[0])
+    bg = np.abs(rng.normal(0.5, 0.1, fixed.shape)).astype(f32)
+    fn = regi.Intensity2D3DObjFn(ctx, [vol, vol2], [cam], [fixed], metric="grad-ncc", max_pop=5)
+    fn.rc.set_bg_projs([bg], use_bg_projs=True)   # uploads the image
+    fn.rc.set_use_bg_projs(False)                 # ... but plain calls do not use it
+    for use_bg in (False, True):
+        got = fn.eval_objects([pop_a, pop_b], use_bg_projs=use_bg)
+        buf = np.repeat(bg[None], n_poses, axis=0).copy() if use_bg else np.zeros((n_poses,) + fixed.shape, f32)
+        xo.drr(vol.data, vol.idx_to_phys(), xcam, to12(pop_a), buf=buf)
+        xo.drr(vol2.data, vol2.idx_to_phys(), xcam, to12(pop_b), buf=buf)
+        drr = fn.rc.raw_host_pixel_buf()[:n_poses]
+        sel = buf > 1e-3 * buf.max()
+        assert np.max(np.abs(drr[sel] - buf[sel]) / buf[sel]) <= 1e-4
+        assert np.max(np.abs(got - xo.grad_ncc(fixed, buf))) <= 1e-5
+    # the ray caster's own settings are untouched: a plain call still replaces and ignores the background
+    plain = fn(pop_a)
+    ref = xo.drr(vol.data, vol.idx_to_phys(), xcam, to12(pop_a))
+    assert np.max(np.abs(plain - xo.grad_ncc(fixed, ref))) <= 1e-5
+    # swapped order / explicit volume indices: object list [vol2, vol] gives the same projections up to rounding
+    swapped = fn.eval_objects([pop_b, pop_a], vol_inds=[1, 0])
+    assert np.max(np.abs(swapped - fn.eval_objects([pop_a, pop_b]))) <= 1e-5
+
+
 def test_launch_counter_counts_our_kernels(ctx, small_scene):
     vol, cam, nominal = small_scene
     fn = regi.Intensity2D3DObjFn(ctx, vol, [cam], [np.ones((cam.num_det_rows, cam.num_det_cols), f32)], metric="patch-grad-ncc",

@@ -112,6 +112,8 @@ SIGNATURES = {
     "xrc_eval_batch": [_VP, _U32, C.POINTER(_VP), _U32, _U32, _FP],
     "xrc_eval_batch_async": [_VP, _U32, C.POINTER(_VP), _U32],
     "xrc_obj_fn": [_VP, _U32, C.POINTER(_VP), _U32, _U32, _FP, _FP, _FP],
+    "xrc_obj_fn_objects": [_VP, _U32, _U32P, C.POINTER(_VP), _U32, _U32, _FP, C.c_int, _FP, _FP],
+    "xrc_obj_fn_multi": [_U32, C.POINTER(_VP), C.POINTER(_VP), _U32, _U32, _U32, _FP, _FP, _FP],
     "xrc_obj_fn_se3": [_VP, _U32, C.POINTER(_VP), _U32, _U32, _FP, _FP, _FP, _FP, _FP],
     "xrc_exp_se3": [_FP, _FP],
 }

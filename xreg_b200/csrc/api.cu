@@ -1487,14 +1487,16 @@ static void affine_mul(const float a[12], const float b[12], float c[12])
   memcpy(c, t, sizeof(t));
 }
 
-int xrc_obj_fn(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t n_views, uint32_t n_poses,
-               const float* cam_to_phys, float* sims_out, float* per_view_out)
+// first half of the objective: size the objects for the population, hand over the poses, enqueue the ray cast and every
+// view's metric on the ray caster's stream.  No synchronisation.
+static int obj_fn_set_poses(xrc_rc* rc, uint32_t n_views, uint32_t n_poses, const float* cam_to_phys);
+
+static int obj_fn_enqueue(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t n_views, uint32_t n_poses,
+                          const float* cam_to_phys, uint32_t n_objs = 1, const uint32_t* obj_vols = nullptr, int use_bg = -1)
 {
-  XRC_CHECK_ARG(rc && sms && cam_to_phys && sims_out, "xrc_obj_fn: null argument");
+  XRC_CHECK_ARG(rc && sms && cam_to_phys, "xrc_obj_fn: null argument");
   XRC_CHECK_ARG(rc->allocated, "xrc_obj_fn: ray caster resources not allocated");
   XRC_CHECK_ARG(n_views == rc->cams.size(), "xrc_obj_fn: need one metric per camera model / view");
-  if (!n_poses)
-    return XRC_OK;
   XRC_CHECK_ARG((uint64_t)n_poses * n_views <= rc->max_projs, "xrc_obj_fn: population exceeds the allocated projections");
   // Intensity2D3DRegi::setup(): view v's metric reads projections [v * pop, (v + 1) * pop)
   if (rc->num_projs != n_poses * n_views)
@@ -1502,15 +1504,45 @@ int xrc_obj_fn(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t n_view
   for (uint32_t v = 0; v < n_views; ++v)
   {
     XRC_CHECK_ARG(sms[v] && sms[v]->rc == rc, "xrc_obj_fn: every metric must be bound to the ray caster");
+    XRC_CHECK_ARG(n_poses <= sms[v]->max_imgs, "xrc_obj_fn: population exceeds the metric's capacity");
     if (sms[v]->n_imgs != n_poses)
       XRC_TRY(xrc_sm_set_num_imgs(sms[v], n_poses));
     if (sms[v]->proj_offset != v * n_poses)
       XRC_TRY(xrc_sm_bind_ray_caster(sms[v], rc, v * n_poses));
   }
   rc->ext_poses = nullptr;  // host poses take over from a caller's device buffer
+  if (n_objs <= 1 && !obj_vols && use_bg < 0)
+  {
+    XRC_TRY(obj_fn_set_poses(rc, n_views, n_poses, cam_to_phys));
+    return xrc_eval_batch_async(rc, vol_idx, sms, n_views);
+  }
+  // several moving objects (xregIntensity2D3DRegi.cpp:594-629): the first is stored with REPLACE (on the background
+  // projections when there is a static volume), the others are accumulated; the caller's settings are restored
+  const int saved_store = rc->store_method;
+  const bool saved_bg = rc->use_bg;
+  int status = XRC_OK;
+  for (uint32_t j = 0; j < n_objs && status == XRC_OK; ++j)
+  {
+    rc->store_method = (j == 0) ? XRC_STORE_REPLACE : XRC_STORE_ACCUM;
+    rc->use_bg = (j == 0) ? ((use_bg < 0) ? saved_bg : (use_bg != 0)) : false;
+    status = obj_fn_set_poses(rc, n_views, n_poses, cam_to_phys + 12 * (size_t)j * n_poses);
+    if (status == XRC_OK)
+      status = xrc_rc_compute(rc, obj_vols ? obj_vols[j] : vol_idx);
+  }
+  rc->store_method = saved_store;
+  rc->use_bg = saved_bg;
+  XRC_TRY(status);
+  for (uint32_t v = 0; v < n_views; ++v)
+    XRC_TRY(xrc_sm_compute(sms[v]));
+  return XRC_OK;
+}
+
+// hand one object's population to the ray caster, replicated over the views camera-major (xregRayCastInterface.cpp:97-114)
+static int obj_fn_set_poses(xrc_rc* rc, uint32_t n_views, uint32_t n_poses, const float* cam_to_phys)
+{
   if (n_poses * n_views <= kInlinePoses)
   {
-    // latency regime: no H2D copy, the (camera-major, xregRayCastInterface.cpp:97-114) poses ride in the kernel parameters
+    // latency regime: no H2D copy, the poses ride in the kernel parameters
     XRC_TRY(use_device(rc->ctx));
     XRC_TRY(rc_wait_staging(rc));
     uint32_t g = 0;
@@ -1521,18 +1553,25 @@ int xrc_obj_fn(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t n_view
         rc->h_cam_idx[g] = c;
       }
     rc->inline_poses = true;
+    return XRC_OK;
   }
-  else
-    XRC_TRY(xrc_rc_distribute_poses(rc, n_poses, cam_to_phys));
-  std::vector<float> tmp;
-  float* pv = per_view_out;
-  if (!pv)
-  {
-    tmp.resize((size_t)n_views * n_poses);
-    pv = tmp.data();
-  }
-  XRC_TRY(xrc_eval_batch(rc, vol_idx, sms, n_views, n_poses, pv));
-  // ImgSimMetric2DCombineMean::compute: f32 running sum over views, then / n_views
+  return xrc_rc_distribute_poses(rc, n_poses, cam_to_phys);
+}
+
+// second half: wait for the stream, collect the per-view scalars: per_view[v * stride + p], p < n_poses
+static int obj_fn_finish(xrc_rc* rc, xrc_sm* const* sms, uint32_t n_views, uint32_t n_poses, float* per_view, size_t stride)
+{
+  XRC_TRY(use_device(rc->ctx));
+  // the finalize kernels also write the scalars to h_sims (host-mapped pinned memory): no D2H copy to wait for
+  XRC_CUDA(cudaStreamSynchronize(rc->ctx->stream));
+  for (uint32_t v = 0; v < n_views; ++v)
+    memcpy(per_view + (size_t)v * stride, sms[v]->h_sims, n_poses * sizeof(float));
+  return XRC_OK;
+}
+
+// ImgSimMetric2DCombineMean::compute: f32 running sum over views, then / n_views
+static void combine_mean(const float* pv, uint32_t n_views, uint32_t n_poses, float* sims_out)
+{
   for (uint32_t p = 0; p < n_poses; ++p)
   {
     float acc = 0.0f;
@@ -1543,6 +1582,87 @@ int xrc_obj_fn(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t n_view
     }
     sims_out[p] = acc / (float)n_views;
   }
+}
+
+int xrc_obj_fn(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t n_views, uint32_t n_poses,
+               const float* cam_to_phys, float* sims_out, float* per_view_out)
+{
+  XRC_CHECK_ARG(sims_out, "xrc_obj_fn: null output");
+  if (!n_poses)
+    return XRC_OK;
+  XRC_TRY(obj_fn_enqueue(rc, vol_idx, sms, n_views, n_poses, cam_to_phys));
+  std::vector<float> tmp;
+  float* pv = per_view_out;
+  if (!pv)
+  {
+    tmp.resize((size_t)n_views * n_poses);
+    pv = tmp.data();
+  }
+  XRC_TRY(obj_fn_finish(rc, sms, n_views, n_poses, pv, n_poses));
+  combine_mean(pv, n_views, n_poses, sims_out);
+  return XRC_OK;
+}
+
+int xrc_obj_fn_objects(xrc_rc* rc, uint32_t n_objs, const uint32_t* vol_idx, xrc_sm* const* sms, uint32_t n_views,
+                       uint32_t n_poses, const float* cam_to_phys, int use_bg_projs, float* sims_out, float* per_view_out)
+{
+  XRC_CHECK_ARG(rc && vol_idx && sims_out && n_objs > 0, "xrc_obj_fn_objects: bad argument");
+  for (uint32_t j = 0; j < n_objs; ++j)
+    XRC_CHECK_ARG(vol_idx[j] < rc->vols.size(), "xrc_obj_fn_objects: volume index out of range");
+  XRC_CHECK_ARG(!use_bg_projs || rc->d_bg, "xrc_obj_fn_objects: no background projections set (xrc_rc_set_bg_projs)");
+  if (!n_poses)
+    return XRC_OK;
+  XRC_TRY(obj_fn_enqueue(rc, 0, sms, n_views, n_poses, cam_to_phys, n_objs, vol_idx, use_bg_projs ? 1 : 0));
+  std::vector<float> tmp;
+  float* pv = per_view_out;
+  if (!pv)
+  {
+    tmp.resize((size_t)n_views * n_poses);
+    pv = tmp.data();
+  }
+  XRC_TRY(obj_fn_finish(rc, sms, n_views, n_poses, pv, n_poses));
+  combine_mean(pv, n_views, n_poses, sims_out);
+  return XRC_OK;
+}
+
+int xrc_obj_fn_multi(uint32_t n_dev, xrc_rc* const* rcs, xrc_sm* const* sms, uint32_t vol_idx, uint32_t n_views,
+                     uint32_t n_poses, const float* cam_to_phys, float* sims_out, float* per_view_out)
+{
+  XRC_CHECK_ARG(n_dev > 0 && rcs && sms && cam_to_phys && sims_out, "xrc_obj_fn_multi: bad argument");
+  if (!n_poses)
+    return XRC_OK;
+  std::vector<float> tmp;
+  float* pv = per_view_out;
+  if (!pv)
+  {
+    tmp.resize((size_t)n_views * n_poses);
+    pv = tmp.data();
+  }
+  // contiguous balanced chunks: the first n_poses % n_dev devices take one pose more (100 poses on 8 devices: 13 13 13 13 12 12 12 12)
+  const uint32_t base = n_poses / n_dev, extra = n_poses % n_dev;
+  std::vector<uint32_t> begin(n_dev + 1, 0);
+  for (uint32_t d = 0; d < n_dev; ++d)
+    begin[d + 1] = begin[d] + base + (d < extra ? 1u : 0u);
+  // enqueue everything first (asynchronous launches: the devices run concurrently), then collect
+  int status = XRC_OK;
+  uint32_t enqueued = 0;
+  for (uint32_t d = 0; d < n_dev && status == XRC_OK; ++d, ++enqueued)
+  {
+    const uint32_t n = begin[d + 1] - begin[d];
+    if (n)
+      status = obj_fn_enqueue(rcs[d], vol_idx, sms + (size_t)d * n_views, n_views, n, cam_to_phys + 12 * (size_t)begin[d]);
+  }
+  for (uint32_t d = 0; d < enqueued; ++d)
+  {
+    const uint32_t n = begin[d + 1] - begin[d];
+    if (!n || !rcs[d])
+      continue;
+    const int s2 = obj_fn_finish(rcs[d], sms + (size_t)d * n_views, n_views, n, pv + begin[d], n_poses);
+    if (status == XRC_OK)
+      status = s2;
+  }
+  XRC_TRY(status);
+  combine_mean(pv, n_views, n_poses, sims_out);
   return XRC_OK;
 }
 

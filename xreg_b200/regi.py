@@ -53,7 +53,8 @@ class Intensity2D3DObjFn:
         self.n_views = len(cams)
         self.max_pop = int(max_pop)
         self.rc = RayCasterLineIntCUDA(ctx, layout=layout)
-        self.rc.set_volume(vol)
+        # one moving volume, or several (multi-object registration: eval_objects)
+        self.rc.set_volumes(list(vol) if isinstance(vol, (list, tuple)) else [vol])
         self.rc.set_camera_models(list(cams))
         self.rc.set_ray_step_size(step_size)
         # xregIntensity2D3DRegi.cpp:63-94: view-major buffer, metric v reads [v*pop, (v+1)*pop)
@@ -107,6 +108,40 @@ class Intensity2D3DObjFn:
             sm._sim_vals[:n] = per_view[v]
         return out
 
+    def close(self) -> None:
+        """Destroy the metrics and the ray caster (before their Context is closed)."""
+        for sm in self.sims:
+            sm.close()
+        self.sims = []
+        self.rc.close()
+
+    def eval_objects(self, poses_per_object: Sequence[np.ndarray], vol_inds: Optional[Sequence[int]] = None,
+                     use_bg_projs: bool = False) -> np.ndarray:
+        """Multi-object objective (Intensity2D3DRegi::obj_fn's loop over volumes, xregIntensity2D3DRegi.cpp:594-629):
+        object j's population poses_per_object[j] (n, 4, 4) is ray cast through volume vol_inds[j] (default j) into the
+        same projections -- first object REPLACE (on the background projections if use_bg_projs), the others ACCUM --
+        then the metrics.  One library call (xrc_obj_fn_objects)."""
+        n_objs = len(poses_per_object)
+        p12 = np.ascontiguousarray(np.stack([to12(p) if np.asarray(p).ndim == 3 else np.asarray(p, f32).reshape(-1, 12)
+                                             for p in poses_per_object]), dtype=f32)
+        n = p12.shape[1]
+        if n == 0:
+            return np.zeros(0, dtype=f32)
+        self._set_pop(n)
+        self.rc._flush_params()
+        vi = np.ascontiguousarray(np.arange(n_objs) if vol_inds is None else vol_inds, dtype=np.uint32)
+        out = np.empty(n, dtype=f32)
+        per_view = np.empty((self.n_views, n), dtype=f32)
+        FP = C.POINTER(C.c_float)
+        _lib.check(self._lib.xrc_obj_fn_objects(self.rc.handle, n_objs, vi.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                self._sm_arr, self.n_views, n, p12.ctypes.data_as(FP),
+                                                1 if use_bg_projs else 0, out.ctypes.data_as(FP),
+                                                per_view.ctypes.data_as(FP)))
+        self.rc._poses_dirty = False
+        for v, sm in enumerate(self.sims):
+            sm._sim_vals[:n] = per_view[v]
+        return out
+
     def eval_se3(self, params: np.ndarray, pre: Optional[np.ndarray] = None, post: Optional[np.ndarray] = None) -> np.ndarray:
         """Objective from optimiser variables (SE3OptVarsLieAlg, xregSE3OptVars.cpp:128-137):
         pose_p = pre * ExpSE3(params_p) * post (xregIntensity2D3DRegi.cpp:1049-1071), composed inside the library."""
@@ -124,6 +159,63 @@ class Intensity2D3DObjFn:
                                             pre12, post12, out.ctypes.data_as(FP), None))
         self.rc._poses_dirty = False
         return out
+
+
+class MultiDeviceObjFn:
+    """The objective spread over several GPUs of one box from ONE host thread (xrc_obj_fn_multi): one
+    Intensity2D3DObjFn replica per device (volume, cameras and fixed images replicated), the population cut
+    into contiguous balanced chunks, all devices enqueued before any is waited for, only the scalars gathered.
+    This is what a single-threaded C++ caller (the reference's optimiser loop) uses; multi-process jobs use
+    ShardedObjFn.  `devices` may name the same device more than once (two contexts / streams on one GPU)."""
+
+    def __init__(self, devices: Sequence[int], vol: Volume, cams: Sequence[CameraModel], fixed_imgs: Sequence[np.ndarray],
+                 max_pop: int = 100, **kw):
+        self.devices = [int(d) for d in devices]
+        n_dev = len(self.devices)
+        if n_dev == 0:
+            raise _lib.XregError("need at least one device")
+        self.n_views = len(cams)
+        self.max_pop = int(max_pop)
+        per_dev = (self.max_pop + n_dev - 1) // n_dev
+        self.ctxs = [Context(d) for d in self.devices]
+        self.replicas = [Intensity2D3DObjFn(c, vol, cams, fixed_imgs, max_pop=per_dev, **kw) for c in self.ctxs]
+        self._lib = _lib.load()
+        self._rc_arr = (C.c_void_p * n_dev)(*[r.rc.handle for r in self.replicas])
+        self._sm_arr = (C.c_void_p * (n_dev * self.n_views))(*[sm.handle for r in self.replicas for sm in r.sims])
+
+    def __call__(self, poses: np.ndarray) -> np.ndarray:
+        p12 = to12(poses) if np.asarray(poses).ndim == 3 else np.ascontiguousarray(poses, dtype=f32).reshape(-1, 12)
+        n = p12.shape[0]
+        if n > self.max_pop:
+            raise _lib.XregError("population larger than the allocated capacity")
+        out = np.empty(n, dtype=f32)
+        if n == 0:
+            return out
+        for r in self.replicas:
+            r.rc._flush_params()
+        self.per_view = np.empty((self.n_views, n), dtype=f32)
+        FP = C.POINTER(C.c_float)
+        _lib.check(self._lib.xrc_obj_fn_multi(len(self.replicas), self._rc_arr, self._sm_arr, 0, self.n_views, n,
+                                              p12.ctypes.data_as(FP), out.ctypes.data_as(FP),
+                                              self.per_view.ctypes.data_as(FP)))
+        for r in self.replicas:
+            r.rc._poses_dirty = False
+            r._cur_pop = -1  # the library re-sized the replica; re-bind on the next direct call
+        return out
+
+    def close(self) -> None:
+        for r in self.replicas:   # objects first, then the contexts they live on
+            r.close()
+        self.replicas = []
+        for c in self.ctxs:
+            c.close()
+        self.ctxs = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class ShardedObjFn:
