@@ -69,8 +69,10 @@ enum { XRC_INTERP_LINEAR = 0, XRC_INTERP_NN = 1, XRC_INTERP_SINC = 2, XRC_INTERP
 enum { XRC_STORE_REPLACE = 0, XRC_STORE_ACCUM = 1 };
 /* RayCastLineIntKernel (xregRayCastInterface.h:575-579) */
 enum { XRC_KERNEL_SUM = 0, XRC_KERNEL_MAX = 1 };
-/* Metric kinds: ImgSimMetric2D{NCC,GradNCC,PatchNCC,PatchGradNCC}CPU/OCL */
-enum { XRC_SM_NCC = 0, XRC_SM_GRAD_NCC = 1, XRC_SM_PATCH_NCC = 2, XRC_SM_PATCH_GRAD_NCC = 3 };
+/* Metric kinds: ImgSimMetric2D{NCC,GradNCC,PatchNCC,PatchGradNCC}CPU/OCL, and
+ * ImgSimMetric2DSSDCPU/OCL: sum over ALL pixels of (fixed - moving)^2 / num_pixels with both images zeroed outside
+ * the mask (xregImgSimMetric2DSSDCPU.cpp:62-88) */
+enum { XRC_SM_NCC = 0, XRC_SM_GRAD_NCC = 1, XRC_SM_PATCH_NCC = 2, XRC_SM_PATCH_GRAD_NCC = 3, XRC_SM_SSD = 4 };
 /* Volume layouts in HBM (DESIGN.md "Data layout").  All fetch exact f32 voxels and take the same samples;
  * LINEAR..TEX lerp x, y, z and agree bit for bit, PAX (the default: one padded XY-quad stack per principal
  * ray axis) lerps mid axis, slow axis, fast axis and differs from them in the last ulp only. */

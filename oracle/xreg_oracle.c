@@ -453,11 +453,11 @@ int xo_drr(const float* vol, const uint64_t dims[3], const float idx_to_phys[12]
 /* Eigen 3.3 linear vectorised reduction (SSE Packet4f, two packet
  * accumulators, then predux (a0+a2)+(a1+a3), scalar tail), as used by
  * .mean() / .sum() / .dot() at xregImgSimMetric2DNCCCPU.cpp:58-61,72,182.
- * kind 0: sum a[i]; 1: sum (a[i]-c)^2; 2: sum a[i]*b[i].  Buffers are taken
- * as aligned (alignedStart = 0). */
+ * kind 0: sum a[i]; 1: sum (a[i]-c)^2; 2: sum a[i]*b[i]; 3: sum (a[i]-b[i])^2
+ * (xregImgSimMetric2DSSDCPU.cpp:81).  Buffers are taken as aligned (alignedStart = 0). */
 static float eigen_redux(const float* a, const float* b, float c, size_t n, int kind)
 {
-#define ELEM(i) ((kind == 0) ? a[i] : (kind == 1) ? ((a[i] - c) * (a[i] - c)) : (a[i] * b[i]))
+#define ELEM(i) ((kind == 0) ? a[i] : (kind == 1) ? ((a[i] - c) * (a[i] - c)) : (kind == 2) ? (a[i] * b[i]) : ((a[i] - b[i]) * (a[i] - b[i])))
   const size_t ps = 4;
   const size_t aligned2 = (n / (2 * ps)) * (2 * ps);
   const size_t aligned = (n / ps) * ps;
@@ -533,6 +533,33 @@ static void img_mean_std_mask(const float* a, const uint8_t* mask, size_t n, siz
   s = sqrtf(s / (float)(len - 1));
   *mean = mu;
   *sd = (s < 1.0e-6f) ? 1.0e-6f : s;
+}
+
+/* ImgSimMetric2DSSDCPU::compute / process_mask (xregImgSimMetric2DSSDCPU.cpp:62-110): fixed and moving
+ * images zeroed outside the mask (the moving buffer IS modified), sum of squared differences / num pixels */
+void xo_ssd(const float* fixed, const uint8_t* mask, uint32_t rows, uint32_t cols,
+            float* mov, uint32_t n_imgs, float* sims, int n_threads)
+{
+  const size_t n = (size_t)rows * cols;
+  float* f = (float*)malloc(sizeof(float) * n);
+  memcpy(f, fixed, sizeof(float) * n);
+  if (mask)
+    for (size_t i = 0; i < n; ++i)
+      if (!mask[i])
+        f[i] = 0.0f;
+  const int nt = resolve_threads(n_threads);
+  (void)nt;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nt)
+  for (int64_t k = 0; k < (int64_t)n_imgs; ++k)
+  {
+    float* m = mov + (size_t)k * n;
+    if (mask)
+      for (size_t i = 0; i < n; ++i)
+        if (!mask[i])
+          m[i] = 0.0f;
+    sims[k] = eigen_redux(f, m, 0.0f, n, 3) / (float)n; /* :81 */
+  }
+  free(f);
 }
 
 void xo_ncc(const float* fixed, const uint8_t* mask, uint32_t rows, uint32_t cols,

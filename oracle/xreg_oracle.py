@@ -198,6 +198,18 @@ def ncc(fixed, mov, mask=None, n_threads=0, inplace=False):
     return sims
 
 
+def ssd(fixed, mov, mask=None, n_threads=0):
+    """ImgSimMetric2DSSDCPU: sum((fixed - mov)^2) / num_pixels, images zeroed outside the mask."""
+    fixed = _f32(fixed)
+    rows, cols = fixed.shape
+    mov = _f32(mov).reshape(-1, rows, cols).copy()
+    sims = np.zeros(mov.shape[0], np.float32)
+    m = np.ascontiguousarray(mask, dtype=np.uint8) if mask is not None else None
+    lib().xo_ssd(_fp(fixed), _u8p(m) if m is not None else None, C.c_uint32(rows), C.c_uint32(cols), _fp(mov),
+                 C.c_uint32(mov.shape[0]), _fp(sims), C.c_int(n_threads))
+    return sims
+
+
 def gauss_kernel(width):
     cf = np.zeros(width, np.float32)
     if lib().xo_gauss_kernel(C.c_int(width), _fp(cf)) != 0:

@@ -42,6 +42,25 @@ def test_ncc_matches_float64_model_and_overwrites_moving(xo):
     assert abs(buf[0].mean()) < 1e-5  # zero-mean in place (xregImgSimMetric2DNCCCPU.h:36)
 
 
+def test_ssd_known_answers_and_float64_model(xo):
+    """ImgSimMetric2DSSDCPU (xregImgSimMetric2DSSDCPU.cpp:62-110): sum((f - m)^2) / num_pixels over the whole image,
+    both images zero outside the mask."""
+    f = _img(seed=5)
+    n = f.size
+    assert xo.ssd(f, f[None])[0] == 0.0
+    assert abs(xo.ssd(f, (f + f32(2.0))[None])[0] - 4.0) < 1e-5            # constant offset c -> c^2
+    m = np.stack([_img(seed=6), 0.5 * f])
+    s = xo.ssd(f, m)
+    for k in range(2):
+        ref = np.sum((f.astype(np.float64) - m[k].astype(np.float64)) ** 2) / n
+        assert abs(s[k] - ref) <= 1e-5 * ref
+    mask = (np.random.default_rng(7).random(f.shape) > 0.4).astype(np.uint8)
+    sm = xo.ssd(f, m, mask=mask)
+    for k in range(2):
+        d = (f.astype(np.float64) - m[k].astype(np.float64)) * mask
+        assert abs(sm[k] - np.sum(d ** 2) / n) <= 1e-5 * sm[k]              # the divisor stays the full pixel count
+
+
 def test_gauss_kernel_tables(xo):
     cv2 = pytest.importorskip("cv2")
     for k in (1, 3, 5, 7):

@@ -8,6 +8,6 @@ from .geometry import (CameraModel, Volume, downsample_camera_model, exp_se3, se
 from .ray_caster import Context, RayCasterLineIntCUDA
 from .sim_metrics import (ImgSimMetric2D, ImgSimMetric2DCombineMean, ImgSimMetric2DGradNCCCUDA,
                           ImgSimMetric2DNCCCUDA, ImgSimMetric2DPatchGradNCCCUDA, ImgSimMetric2DPatchNCCCUDA,
-                          eval_batch)
+                          ImgSimMetric2DSSDCUDA, eval_batch)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -21,7 +21,7 @@ XRC_ERR_NOMEM = 4
 INTERP_LINEAR, INTERP_NN, INTERP_SINC, INTERP_BSPLINE = 0, 1, 2, 3
 STORE_REPLACE, STORE_ACCUM = 0, 1
 KERNEL_SUM, KERNEL_MAX = 0, 1
-SM_NCC, SM_GRAD_NCC, SM_PATCH_NCC, SM_PATCH_GRAD_NCC = 0, 1, 2, 3
+SM_NCC, SM_GRAD_NCC, SM_PATCH_NCC, SM_PATCH_GRAD_NCC, SM_SSD = 0, 1, 2, 3, 4
 LAYOUT_DEFAULT, LAYOUT_LINEAR, LAYOUT_QUAD, LAYOUT_TEX_QUAD, LAYOUT_OCT, LAYOUT_TEX = -1, 0, 1, 2, 3, 4
 LAYOUT_NAMES = {"default": -1, "linear": 0, "quad": 1, "tex_quad": 2, "oct": 3, "tex": 4, "pax": 5}
 

@@ -806,7 +806,7 @@ int xrc_rc_set_cta_order(xrc_rc* rc, int order)
 int xrc_sm_create(xrc_ctx* ctx, int kind, xrc_sm** out)
 {
   XRC_CHECK_ARG(ctx && out, "xrc_sm_create: null argument");
-  XRC_CHECK_ARG(kind >= XRC_SM_NCC && kind <= XRC_SM_PATCH_GRAD_NCC, "xrc_sm_create: unknown metric kind");
+  XRC_CHECK_ARG(kind >= XRC_SM_NCC && kind <= XRC_SM_SSD, "xrc_sm_create: unknown metric kind");
   xrc_sm* sm = new xrc_sm;
   sm->ctx = ctx;
   sm->kind = kind;
@@ -1046,7 +1046,24 @@ static int sm_prepare_fixed(xrc_sm* sm)
     }
   }
 
-  if (sm->kind == XRC_SM_NCC || sm->kind == XRC_SM_GRAD_NCC)
+  if (sm->kind == XRC_SM_SSD)
+  {
+    // ImgSimMetric2DSSDCPU::process_mask (xregImgSimMetric2DSSDCPU.cpp:91-110): fixed image zeroed outside the mask;
+    // the divisor is the full pixel count
+    std::vector<float> f0(sm->h_fixed);
+    double sff = 0.0;
+    for (size_t i = 0; i < npix; ++i)
+    {
+      if (mask && !(*mask)[i])
+        f0[i] = 0.0f;
+      sff += (double)f0[i] * f0[i];
+    }
+    sm->sf0[0] = sff;
+    sm->n_eff = (double)npix;
+    XRC_CUDA(cudaMemcpyAsync(sm->d_f0[0], f0.data(), npix * sizeof(float), cudaMemcpyHostToDevice, st));
+    XRC_CUDA(cudaStreamSynchronize(st));  // f0 is a local
+  }
+  else if (sm->kind == XRC_SM_NCC || sm->kind == XRC_SM_GRAD_NCC)
   {
     for (int d = 0; d < n_dirs; ++d)
     {
@@ -1144,7 +1161,7 @@ int xrc_sm_allocate(xrc_sm* sm, uint32_t max_imgs)
     XRC_CUDA(cudaMalloc(&sm->d_mov, npix * max_imgs * sizeof(float)));
 
   size_t parts_per_img = 0;
-  if (sm->kind == XRC_SM_NCC)
+  if (sm->kind == XRC_SM_NCC || sm->kind == XRC_SM_SSD)
   {
     XRC_CUDA(cudaMalloc(&sm->d_f0[0], npix * sizeof(float)));
     parts_per_img = ((npix + kMomChunk - 1) / kMomChunk) * 3;
@@ -1245,7 +1262,7 @@ int xrc_sm_compute(xrc_sm* sm)
   XRC_TRY(sm_source(sm, &src));
   const uint8_t* mask = sm->has_mask ? sm->d_mask : nullptr;
 
-  if (sm->kind == XRC_SM_NCC)
+  if (sm->kind == XRC_SM_NCC || sm->kind == XRC_SM_SSD)
   {
     MomentArgs m;
     memset(&m, 0, sizeof(m));
@@ -1263,6 +1280,7 @@ int xrc_sm_compute(xrc_sm* sm)
     f.n_imgs = sm->n_imgs;
     f.n_parts = m.n_chunks;
     f.n_dirs = 1;
+    f.ssd = (sm->kind == XRC_SM_SSD) ? 1 : 0;
     f.n_eff = sm->n_eff;
     f.sf0[0] = sm->sf0[0];
     f.f_sd[0] = sm->f_sd[0];

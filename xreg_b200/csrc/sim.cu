@@ -447,7 +447,12 @@ __global__ void __launch_bounds__(kFinalizeThreads) ncc_finalize_kernel(const Nc
       s[q] = t;
     }
     float sim_dir[2] = {0.f, 0.f};
-    for (uint32_t d = 0; d < a.n_dirs; ++d)
+    if (a.ssd)
+    {
+      // sum (f - m)^2 / N from the raw moments (f64: the cancellation costs ~1e-12 relative)
+      sim_dir[0] = (float)(((s[1] - 2.0 * s[2]) + a.sf0[0]) / a.n_eff);
+    }
+    for (uint32_t d = 0; d < (a.ssd ? 0u : a.n_dirs); ++d)
     {
       const double Sm = s[3 * d], Smm = s[3 * d + 1], Smf = s[3 * d + 2];
       const double mu = Sm / a.n_eff;

@@ -53,6 +53,7 @@ struct NccFinalizeArgs
   float f_sd[2];
   float* sims;
   float* sims_host;        // optional host-mapped copy (pinned): saves the D2H memcpy of the scalars
+  int ssd;                 // 1: sim = (Smm - 2 Smf + sf0[0]) / n_eff with f0 = the (masked) fixed image, sf0[0] = sum f^2
 };
 
 struct PatchArgs

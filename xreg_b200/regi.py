@@ -18,9 +18,10 @@ from . import _lib
 from .geometry import CameraModel, Volume, f32, to12
 from .ray_caster import Context, RayCasterLineIntCUDA
 from .sim_metrics import (ImgSimMetric2D, ImgSimMetric2DGradNCCCUDA, ImgSimMetric2DNCCCUDA,
-                          ImgSimMetric2DPatchGradNCCCUDA, ImgSimMetric2DPatchNCCCUDA, eval_batch)
+                          ImgSimMetric2DPatchGradNCCCUDA, ImgSimMetric2DPatchNCCCUDA, ImgSimMetric2DSSDCUDA, eval_batch)
 
 METRICS = {
+    "ssd": ImgSimMetric2DSSDCUDA,
     "ncc": ImgSimMetric2DNCCCUDA,
     "grad-ncc": ImgSimMetric2DGradNCCCUDA,
     "patch-ncc": ImgSimMetric2DPatchNCCCUDA,

@@ -273,6 +273,14 @@ class ImgSimMetric2DNCCCUDA(ImgSimMetric2D):
     KIND = _lib.SM_NCC
 
 
+class ImgSimMetric2DSSDCUDA(ImgSimMetric2D):
+    """Replaces ImgSimMetric2DSSDOCL / mirrors ImgSimMetric2DSSDCPU (xregImgSimMetric2DSSDCPU.cpp:62-110):
+    sum((fixed - moving)^2) / num_pixels, both images taken as zero outside the mask.  The moving-image
+    buffer is left untouched (the CPU class zeroes its masked pixels in place)."""
+
+    KIND = _lib.SM_SSD
+
+
 class ImgSimMetric2DGradNCCCUDA(ImgSimMetric2D, ImgSimMetric2DGradImgParamInterface):
     """ImgSimMetric2DGradNCCCPU (xregImgSimMetric2DGradNCCCPU.cpp:29-65)."""
 
