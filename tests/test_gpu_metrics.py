@@ -56,6 +56,21 @@ def test_ncc(ctx, xo, shape, masked):
     assert abs(got[-1] - 0.5) < 1e-6
 
 
+@pytest.mark.parametrize("shape", SHAPES + [(480, 480)])
+@pytest.mark.parametrize("masked", [False, True])
+def test_ssd(ctx, xo, shape, masked):
+    """ImgSimMetric2DSSDCUDA vs ImgSimMetric2DSSDCPU's restatement: SSD is not normalised, so the tolerance is
+    relative (1e-5, the rounding noise of the reference's own f32 sum)."""
+    fixed = _img(*shape, seed=21)
+    mov = _movs(fixed, 4, seed=22)
+    mov[1] = fixed                                   # identical image: exactly 0
+    mask = (np.random.default_rng(23).random(shape) > 0.35).astype(np.uint8) if masked else None
+    got = _run(xreg_b200.ImgSimMetric2DSSDCUDA(ctx), fixed, mov, mask)
+    ref = xo.ssd(fixed, mov, mask)
+    assert got[1] == 0.0 and ref[1] == 0.0
+    assert np.max(np.abs(got - ref) / np.maximum(ref, 1e-12)) <= 1e-5
+
+
 @pytest.mark.parametrize("shape", SHAPES + [(64, 96), (3, 40)])
 @pytest.mark.parametrize("width", [0, 3, 5, 7, 9])
 def test_gradient_images_bit_exact(ctx, xo, shape, width):
