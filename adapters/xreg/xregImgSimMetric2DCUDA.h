@@ -60,6 +60,13 @@ public:
   explicit ImgSimMetric2DNCCCUDA(xrc_ctx* ctx) : ImgSimMetric2DCUDA(ctx, XRC_SM_NCC) { }
 };
 
+/// Replaces ImgSimMetric2DSSDOCL (SSDSimMetricFromProgOpts, xregImgSimMetric2DProgOpts.cpp)
+class ImgSimMetric2DSSDCUDA : public ImgSimMetric2DCUDA
+{
+public:
+  explicit ImgSimMetric2DSSDCUDA(xrc_ctx* ctx) : ImgSimMetric2DCUDA(ctx, XRC_SM_SSD) { }
+};
+
 class ImgSimMetric2DGradNCCCUDA : public ImgSimMetric2DCUDA, public ImgSimMetric2DGradImgParamInterface
 {
 public:
