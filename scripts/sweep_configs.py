@@ -3,7 +3,7 @@
 C1 (256^3 CT, 256^2 detector, NCC), C4 (three views, 512^3 CT, 768^2 detectors, patch gradient-NCC,
 population 100) and C5 (768^3 CT, 1536^2 detector, 0.5-voxel step, pose batch 1..2048), through the public
 host API (host poses in, host scalars out).  GPU only; one JSON line per case.
-SWEEP_CASES=c1,c4,c5 selects a subset; SWEEP_C5_MAX caps the C5 batch (default 2048)."""
+SWEEP_CASES=c1,c2bone,c4,c5 selects a subset; SWEEP_C5_MAX caps the C5 batch (default 2048)."""
 import json
 import os
 import sys
@@ -54,7 +54,7 @@ def report(case, fn, pops, dt, n_views=1, **extra):
 
 
 def main():
-    cases = os.environ.get("SWEEP_CASES", "c1,c4,c5").split(",")
+    cases = os.environ.get("SWEEP_CASES", "c1,c2bone,c4,c5").split(",")
     ctx = xreg_b200.Context(0)
 
     if "c1" in cases:
@@ -68,6 +68,25 @@ def main():
             dt = timed(fn, pops, 200 if pop_n == 1 else 20)
             report("C1 256^3 CT, 256^2 detector, NCC", fn, pops, dt)
             del fn
+
+    if "c2bone" in cases:
+        # what the reference's registration apps really ray cast: the CT with everything outside the bone
+        # segmentation zeroed (here: the phantom's 12 "bones" only).  Shows what empty-space trimming buys.
+        base = synth.make_volume(512, 512, 400, spacing=(0.8, 0.8, 1.0))
+        vol = xreg_b200.Volume(np.where(base.data >= 0.045, base.data, 0.0).astype(np.float32), base.spacing,
+                               base.origin, base.direction)
+        cam = synth.make_camera(480)
+        nominal = synth.nominal_pose(vol)
+        fixed = render_fixed(ctx, vol, cam, nominal)
+        fn = regi.Intensity2D3DObjFn(ctx, vol, [cam], [fixed], metric="patch-grad-ncc", max_pop=100,
+                                     patch_radius=synth.patch_radius_for(480))
+        pops = [synth.pose_population(vol, nominal, 100, seed=30 + k) for k in range(3)]
+        for skip in (True, False):
+            fn.rc.set_skip_empty(skip)
+            dt = timed(fn, pops, 10)
+            report("C2 geometry, bone-masked volume (non-bone voxels zero), patch gradient-NCC, trimming %s"
+                   % ("on" if skip else "off"), fn, pops, dt)
+        del fn
 
     if "c4" in cases:
         vol = synth.make_volume(512, 512, 512)

@@ -43,7 +43,7 @@ def main():
                     if sname == "coarse" and vname != "ap":
                         continue
                     pops = [synth.pose_population(vol, nominal, pop_n, seed=100 + k, sigma=sig) for k in range(6)]
-                    for order in (0,):
+                    for order in [int(o) for o in os.environ.get("SWEEP_ORDERS", "0").split(",")]:
                         if only and (vname, sname, str(order)) != tuple(only.split(",")[1:4]):
                             continue
                         rc.set_layout_order(order)
