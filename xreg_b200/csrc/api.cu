@@ -662,6 +662,11 @@ static void rc_fill_args(xrc_rc* rc, uint32_t vol_idx, DrrArgs* a)
   a->occ = rc->skip_empty ? v.occ : nullptr;
   a->occ_wx = v.occ_wx;
   a->occ_ny = v.occ_ny;
+  for (int k = 0; k < 3; ++k)
+  {
+    a->occ_lo[k] = v.occ_lo[k];
+    a->occ_hi[k] = v.occ_hi[k];
+  }
 }
 
 int xrc_rc_compute(xrc_rc* rc, uint32_t vol_idx)

@@ -72,6 +72,7 @@ struct DeviceVolume
   // block or of its 26 neighbours is non-zero; x-fastest, 32 blocks per word
   uint32_t* occ = nullptr;
   uint32_t occ_wx = 0, occ_ny = 0, occ_nz = 0;   // words per block row, block rows, block slices
+  float occ_lo[3] = {0, 0, 0}, occ_hi[3] = {0, 0, 0};  // box of sample positions that can touch a non-zero voxel
 };
 
 constexpr uint32_t kInlinePoses = 8;
@@ -103,6 +104,7 @@ struct DrrArgs
   uint32_t* ray_steps;        // ray-info kernel only
   const uint32_t* occ;        // empty-space map of the volume (nullptr = march every sample)
   uint32_t occ_wx, occ_ny;
+  float occ_lo[3], occ_hi[3];
   int count_only;             // instrumentation: count the samples the kernel would fetch, do not march / store
   // small populations (latency regime): poses travel in the kernel parameters instead of an H2D copy
   int use_inline;

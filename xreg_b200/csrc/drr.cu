@@ -14,6 +14,8 @@
 //    per-sample fetch is 2 x 128-bit loads (XY-quad records) instead of 8
 //    scattered 32-bit loads; other layouts are kept for measurement.
 //  * no tensor cores: the path is a gather + lerp, not a contraction.
+#include <algorithm>
+
 #include "common.h"
 
 namespace xrc
@@ -686,13 +688,25 @@ __device__ __forceinline__ float pax_march(const PaxStack& st, float pa, float p
 constexpr int kOccShift = 3;             // 8^3-voxel blocks
 constexpr float kOccReach = 6.0f;        // (1 << kOccShift) - 2
 
-__device__ __forceinline__ bool occ_clear(const DrrArgs& a, float x, float y, float z)
+// Map bit of the block holding (x, y, z) and, when it is clear, the number m >= 1 of consecutive samples starting at
+// this one (walking with velocity (vx, vy, vz) voxels per sample) that the bit vouches for: block b guarantees zeros
+// for voxel indices [8b - 8, 8b + 15] per axis, i.e. for samples whose ideal position stays inside [8b - 6.5, 8b + 14.5)
+// (1 voxel for the interpolation neighbour, 1/2 for the drift of the f32 position chain).  iv* = 1 / max(|v*|, 1e-6).
+__device__ __forceinline__ bool occ_clear(const DrrArgs& a, float x, float y, float z, float vx, float vy, float vz,
+                                          float ivx, float ivy, float ivz, uint32_t& m)
 {
-  const int ix = min(max(__float2int_rd(x), 0), a.nx - 1) >> kOccShift;
-  const int iy = min(max(__float2int_rd(y), 0), a.ny - 1) >> kOccShift;
-  const int iz = min(max(__float2int_rd(z), 0), a.nz - 1) >> kOccShift;
-  const uint32_t w = __ldg(a.occ + ((size_t)((uint32_t)iz * a.occ_ny + (uint32_t)iy) * a.occ_wx + ((uint32_t)ix >> 5)));
-  return ((w >> (ix & 31)) & 1u) == 0u;
+  const int bx = min(max(__float2int_rd(x), 0), a.nx - 1) >> kOccShift;
+  const int by = min(max(__float2int_rd(y), 0), a.ny - 1) >> kOccShift;
+  const int bz = min(max(__float2int_rd(z), 0), a.nz - 1) >> kOccShift;
+  const uint32_t w = __ldg(a.occ + ((size_t)((uint32_t)bz * a.occ_ny + (uint32_t)by) * a.occ_wx + ((uint32_t)bx >> 5)));
+  const float ox = (float)(bx << kOccShift), oy = (float)(by << kOccShift), oz = (float)(bz << kOccShift);
+  // distance to the end of the vouched interval in the walking direction, 0.1 voxel of slack
+  const float dx = (vx > 0.f) ? (ox + 14.4f) - x : x - (ox - 6.4f);
+  const float dy = (vy > 0.f) ? (oy + 14.4f) - y : y - (oy - 6.4f);
+  const float dz = (vz > 0.f) ? (oz + 14.4f) - z : z - (oz - 6.4f);
+  const float k = fminf(fminf(dx * ivx, dy * ivy), fminf(dz * ivz, 63.0f));
+  m = 1u + (uint32_t)fmaxf(k, 0.0f);
+  return ((w >> (bx & 31)) & 1u) == 0u;
 }
 
 // [s0, s1) = the samples of this ray that may be non-zero
@@ -701,18 +715,52 @@ __device__ __forceinline__ void trim_ray(const DrrArgs& a, const Ray& ray, uint3
   const uint32_t n = ray.nsamples;
   s0 = 0;
   s1 = n;
-  const float smax = fmaxf(fabsf(ray.sx), fmaxf(fabsf(ray.sy), fabsf(ray.sz)));
-  if (!(smax <= kOccReach))
+  const float ax = fabsf(ray.sx), ay = fabsf(ray.sy), az = fabsf(ray.sz);
+  if (!(fmaxf(ax, fmaxf(ay, az)) <= kOccReach))
     return;
-  const uint32_t m = (uint32_t)fminf(kOccReach / fmaxf(smax, 1.0e-3f), 64.0f);  // >= 1
-  while (s0 < n)
+  // 1. clip against the bounding box of the non-zero voxels (grown by 2 voxels: interpolation neighbour + drift):
+  //    samples whose ideal position is outside cannot touch a non-zero voxel
+  {
+    float tmin = 0.0f, tmax = (float)n;
+    const float p[3] = {ray.x, ray.y, ray.z}, v[3] = {ray.sx, ray.sy, ray.sz};
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+    {
+      if (fabsf(v[k]) > 1.0e-6f)
+      {
+        const float inv = __frcp_rn(v[k]);
+        const float t1 = (a.occ_lo[k] - p[k]) * inv, t2 = (a.occ_hi[k] - p[k]) * inv;
+        tmin = fmaxf(tmin, fminf(t1, t2));
+        tmax = fminf(tmax, fmaxf(t1, t2));
+      }
+      else if (p[k] < a.occ_lo[k] || p[k] > a.occ_hi[k])
+        tmax = -1.0f;
+    }
+    if (!(tmin <= tmax))
+    {
+      s0 = s1 = n;  // the ray misses everything that is not zero
+      return;
+    }
+    s0 = (uint32_t)fmaxf(floorf(tmin) - 1.0f, 0.0f);
+    s1 = min(n, (uint32_t)(ceilf(tmax) + 2.0f));
+    if (s0 >= s1)
+    {
+      s0 = s1 = n;
+      return;
+    }
+  }
+  // 2. walk in from both ends while the map bits are clear
+  const float ivx = __frcp_rn(fmaxf(ax, 1.0e-6f)), ivy = __frcp_rn(fmaxf(ay, 1.0e-6f)), ivz = __frcp_rn(fmaxf(az, 1.0e-6f));
+  while (s0 < s1)
   {
     const float f = (float)s0;
-    if (!occ_clear(a, fmaf(f, ray.sx, ray.x), fmaf(f, ray.sy, ray.y), fmaf(f, ray.sz, ray.z)))
+    uint32_t m;
+    if (!occ_clear(a, fmaf(f, ray.sx, ray.x), fmaf(f, ray.sy, ray.y), fmaf(f, ray.sz, ray.z), ray.sx, ray.sy, ray.sz, ivx,
+                   ivy, ivz, m))
       break;
     s0 += m;
   }
-  if (s0 >= n)
+  if (s0 >= s1)
   {
     s0 = s1 = n;  // nothing but air
     return;
@@ -720,7 +768,9 @@ __device__ __forceinline__ void trim_ray(const DrrArgs& a, const Ray& ray, uint3
   while (s1 > s0)
   {
     const float f = (float)(s1 - 1u);
-    if (!occ_clear(a, fmaf(f, ray.sx, ray.x), fmaf(f, ray.sy, ray.y), fmaf(f, ray.sz, ray.z)))
+    uint32_t m;
+    if (!occ_clear(a, fmaf(f, ray.sx, ray.x), fmaf(f, ray.sy, ray.y), fmaf(f, ray.sz, ray.z), -ray.sx, -ray.sy, -ray.sz,
+                   ivx, ivy, ivz, m))
       break;
     s1 = (s1 - s0 > m) ? s1 - m : s0;
   }
@@ -1167,6 +1217,25 @@ __global__ void occ_raw_kernel(const float* __restrict__ src, uint8_t* __restric
     raw[((size_t)bz * gy + by) * gx + bx] = (uint8_t)(nonzero != 0);
 }
 
+// bounding box (in blocks) of the raw flags: bb = {min x, y, z, max x, y, z}, initialised to {INT_MAX.., -1..}
+__global__ void occ_bbox_kernel(const uint8_t* __restrict__ raw, int* __restrict__ bb, int gx, int gy, int gz)
+{
+  const size_t total = (size_t)gx * gy * gz;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+  {
+    if (raw[i])
+    {
+      const int x = (int)(i % gx), y = (int)((i / gx) % gy), z = (int)(i / ((size_t)gx * gy));
+      atomicMin(bb + 0, x);
+      atomicMin(bb + 1, y);
+      atomicMin(bb + 2, z);
+      atomicMax(bb + 3, x);
+      atomicMax(bb + 4, y);
+      atomicMax(bb + 5, z);
+    }
+  }
+}
+
 __global__ void occ_dilate_kernel(const uint8_t* __restrict__ raw, uint32_t* __restrict__ occ, int gx, int gy, int gz,
                                   int wx)
 {
@@ -1210,13 +1279,39 @@ int build_occupancy(const float* d_linear, DeviceVolume* v, cudaStream_t st)
     cudaFree(raw);
     XRC_FAIL(XRC_ERR_NOMEM, "build_occupancy: out of device memory");
   }
+  int* d_bb = nullptr;
+  if (cudaMalloc(&d_bb, 6 * sizeof(int)) != cudaSuccess)
+  {
+    cudaFree(raw);
+    XRC_FAIL(XRC_ERR_NOMEM, "build_occupancy: out of device memory");
+  }
+  int h_bb[6] = {0x7fffffff, 0x7fffffff, 0x7fffffff, -1, -1, -1};
+  cudaMemcpyAsync(d_bb, h_bb, sizeof(h_bb), cudaMemcpyHostToDevice, st);
   occ_raw_kernel<<<dim3(gx, gy, gz), 512, 0, st>>>(d_linear, raw, nx, ny, nz, gx, gy);
   occ_dilate_kernel<<<148 * 2, 256, 0, st>>>(raw, v->occ, gx, gy, gz, wx);
-  count_launch(2);
+  occ_bbox_kernel<<<148 * 2, 256, 0, st>>>(raw, d_bb, gx, gy, gz);
+  count_launch(3);
+  cudaMemcpyAsync(h_bb, d_bb, sizeof(h_bb), cudaMemcpyDeviceToHost, st);
   const cudaError_t e = cudaStreamSynchronize(st);
   cudaFree(raw);
+  cudaFree(d_bb);
   XRC_CUDA(e);
   XRC_CUDA(cudaGetLastError());
+  // ideal sample positions that can touch a non-zero voxel: voxel range of the flagged blocks, grown by 2
+  const int dims[3] = {nx, ny, nz};
+  for (int k = 0; k < 3; ++k)
+  {
+    if (h_bb[3 + k] < 0)
+    {
+      v->occ_lo[k] = 1.0f;  // all-zero volume: an empty box
+      v->occ_hi[k] = 0.0f;
+    }
+    else
+    {
+      v->occ_lo[k] = (float)(h_bb[k] * E) - 2.0f;
+      v->occ_hi[k] = (float)std::min(h_bb[3 + k] * E + E - 1, dims[k] - 1) + 2.0f;
+    }
+  }
   v->occ_wx = (uint32_t)wx;
   v->occ_ny = (uint32_t)gy;
   v->occ_nz = (uint32_t)gz;
