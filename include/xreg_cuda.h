@@ -121,6 +121,12 @@ int xrc_rc_set_skip_empty(xrc_rc* rc, int enable);
  * already cast to float. */
 int xrc_rc_set_volumes(xrc_rc* rc, uint32_t n, const float* const* host_ptrs,
                        const uint64_t (*dims)[3], const float (*idx_to_phys)[12]);
+/* the volumes are in Hounsfield units; convert them to linear attenuation on the device
+ * while loading (HUToLinAtt, lib/image/xregHUToLinAtt.cpp:45-69: max(hu * (mu_water - mu_air) / 1000 + mu_water -
+ * mu_lower, 0) in double, mu_lower = the value of hu_lower, reference default -1000) -- what the registration
+ * apps do on the host before set_volumes.  Bit-identical to converting on the host first. */
+int xrc_rc_set_volumes_hu(xrc_rc* rc, uint32_t n, const float* const* host_ptrs, const uint64_t (*dims)[3],
+                          const float (*idx_to_phys)[12], float hu_lower);
 /* same, but the source volume already lives on this context's device */
 int xrc_rc_set_volumes_device(xrc_rc* rc, uint32_t n, const float* const* dev_ptrs,
                               const uint64_t (*dims)[3], const float (*idx_to_phys)[12]);

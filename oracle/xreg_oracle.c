@@ -446,6 +446,19 @@ int xo_drr(const float* vol, const uint64_t dims[3], const float idx_to_phys[12]
   return 0;
 }
 
+/* HUToLinAttFilter::GenerateData (lib/image/xregHUToLinAtt.cpp:45-69; constants xregHUToLinAtt.h:73-76) */
+void xo_hu_to_lin_att(const float* hu, float* att, uint64_t n, float hu_lower)
+{
+  const double mu_water = 0.02683 * 1.0, mu_air = 0.02485 * 0.0001;
+  const double hu_scale = (mu_water - mu_air) * 1.0e-3;
+  const double mu_lower = ((double)hu_lower * hu_scale) + mu_water;
+  for (uint64_t i = 0; i < n; ++i)
+  {
+    const double a = (hu[i] * hu_scale) + mu_water - mu_lower;
+    att[i] = (float)((a > 0.0) ? a : 0.0);
+  }
+}
+
 /* ------------------------------------------------------------------------ */
 /* NCC                                                                      */
 /* ------------------------------------------------------------------------ */

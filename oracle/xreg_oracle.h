@@ -93,6 +93,7 @@ double xo_interp_linear(const float* vol, const uint64_t dims[3], const float x[
 /* ImgSimMetric2DNCCCPU (xregImgSimMetric2DNCCCPU.cpp:52-236).  mov is
  * overwritten with the zero-mean images exactly like the reference.
  * mask may be NULL. */
+void xo_hu_to_lin_att(const float* hu, float* att, uint64_t n, float hu_lower);
 void xo_ssd(const float* fixed, const uint8_t* mask, uint32_t rows, uint32_t cols,
             float* mov, uint32_t n_imgs, float* sims, int n_threads);
 void xo_ncc(const float* fixed, const uint8_t* mask, uint32_t rows, uint32_t cols,

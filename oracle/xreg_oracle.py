@@ -198,6 +198,14 @@ def ncc(fixed, mov, mask=None, n_threads=0, inplace=False):
     return sims
 
 
+def hu_to_lin_att(hu, hu_lower=-1000.0):
+    """HUToLinAtt (lib/image/xregHUToLinAtt.cpp:45-69)."""
+    hu = _f32(hu)
+    out = np.zeros_like(hu)
+    lib().xo_hu_to_lin_att(_fp(hu), _fp(out), C.c_uint64(hu.size), C.c_float(hu_lower))
+    return out
+
+
 def ssd(fixed, mov, mask=None, n_threads=0):
     """ImgSimMetric2DSSDCPU: sum((fixed - mov)^2) / num_pixels, images zeroed outside the mask."""
     fixed = _f32(fixed)

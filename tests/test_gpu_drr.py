@@ -310,3 +310,31 @@ def test_multiple_volumes_accumulate(ctx, xo, small_scene):
     buf = xo.drr(vol.data, vol.idx_to_phys(), cams, to12(poses))
     xo.drr(vol2.data, vol2.idx_to_phys(), cams, to12(poses), buf=buf)
     np.testing.assert_allclose(rc.raw_host_pixel_buf(), buf, rtol=DRR_REL_TOL, atol=1e-7)
+
+
+def test_hu_volume_converted_on_device_is_bit_identical(ctx, xo, small_scene):
+    """xrc_rc_set_volumes_hu == HUToLinAtt on the host followed by set_volumes, bit for bit (f64 arithmetic in the
+    reference's order on both sides)."""
+    vol, cam, nominal = small_scene
+    rng = np.random.default_rng(8)
+    hu = (vol.data * f32(40000.0) - f32(1000.0) + rng.normal(0, 30, vol.data.shape).astype(f32)).astype(f32)  # -1000 .. ~1500 HU
+    poses = synth.pose_population(vol, nominal, 3)
+    outs = []
+    for hu_lower in (-1000.0, -300.0):
+        vol_hu = Volume(hu, vol.spacing, vol.origin, vol.direction)
+        vol_att = Volume(xo.hu_to_lin_att(hu, hu_lower), vol.spacing, vol.origin, vol.direction)
+        rc_a = xreg_b200.RayCasterLineIntCUDA(ctx)
+        rc_a.set_volumes_hu([vol_hu], hu_lower)
+        rc_b = _make_rc(ctx, vol_att, [cam], 3)
+        rc_a.set_camera_model(cam)
+        rc_a.set_num_projs(3)
+        rc_a.allocate_resources()
+        for rc in (rc_a, rc_b):
+            rc.set_xforms_cam_to_itk_phys(list(poses))
+            rc.compute()
+        a, b = rc_a.raw_host_pixel_buf(), rc_b.raw_host_pixel_buf()
+        assert a.tobytes() == b.tobytes() and a.max() > 0
+        outs.append(a.copy())
+        rc_a.close()
+        rc_b.close()
+    assert outs[1].sum() < outs[0].sum()   # the higher threshold removes attenuation

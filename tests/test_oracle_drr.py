@@ -215,3 +215,19 @@ def test_multi_camera_uses_per_projection_camera(xo, small_scene):
     with pytest.raises(ValueError):
         bad = CameraModel().setup(380.0, cam.num_det_rows + 1, cam.num_det_cols, 1.7, 1.4)
         xo.drr(vol.data, vol.idx_to_phys(), [xo.cam_struct(cam), xo.cam_struct(bad)], poses, cam_idx=idx)
+
+
+def test_hu_to_lin_att_known_answers(xo):
+    """HUToLinAtt (lib/image/xregHUToLinAtt.cpp:45-69): air (-1000 HU) -> 0, water (0 HU) -> mu_water - mu_air,
+    linear in between, clamped at 0 below hu_lower."""
+    hu = np.array([-2000.0, -1000.0, -500.0, 0.0, 1000.0, 3000.0], np.float32)
+    att = xo.hu_to_lin_att(hu)
+    mu_w, mu_a = 0.02683, 0.02485e-4
+    assert att[0] == 0.0 and att[1] == 0.0
+    assert abs(att[3] - (mu_w - mu_a)) < 1e-9
+    assert abs(att[2] - 0.5 * (mu_w - mu_a)) < 1e-9
+    assert abs(att[4] - 2.0 * (mu_w - mu_a)) < 1e-8
+    ref = np.maximum((hu.astype(np.float64) + 1000.0) * (mu_w - mu_a) * 1e-3, 0.0)
+    assert np.max(np.abs(att - ref) / np.maximum(ref, 1e-3)) < 1e-7   # f32 rounding of the result
+    att2 = xo.hu_to_lin_att(hu, hu_lower=-500.0)     # a higher threshold removes more soft tissue
+    assert att2[2] == 0.0 and abs(att2[3] - 0.5 * (mu_w - mu_a)) < 1e-9

@@ -76,6 +76,7 @@ SIGNATURES = {
     "xrc_rc_set_layout": [_VP, C.c_int],
     "xrc_rc_set_cta_order": [_VP, C.c_int],
     "xrc_rc_set_volumes": [_VP, _U32, C.POINTER(_FP), C.POINTER(_U64 * 3), C.POINTER(C.c_float * 12)],
+    "xrc_rc_set_volumes_hu": [_VP, _U32, C.POINTER(_FP), C.POINTER(_U64 * 3), C.POINTER(C.c_float * 12), C.c_float],
     "xrc_rc_set_volumes_device": [_VP, _U32, C.POINTER(_VP), C.POINTER(_U64 * 3), C.POINTER(C.c_float * 12)],
     "xrc_rc_set_cameras": [_VP, _U32, C.POINTER(XrcCam)],
     "xrc_rc_allocate": [_VP, _U32],

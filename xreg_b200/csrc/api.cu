@@ -323,7 +323,7 @@ int xrc_rc_set_layout(xrc_rc* rc, int layout)
 }
 
 static int rc_set_volumes_impl(xrc_rc* rc, uint32_t n, const float* const* ptrs, const uint64_t (*dims)[3],
-                               const float (*idx_to_phys)[12], bool on_device)
+                               const float (*idx_to_phys)[12], bool on_device, const float* hu_lower = nullptr)
 {
   XRC_CHECK_ARG(rc && ptrs && dims && idx_to_phys, "xrc_rc_set_volumes: null argument");
   XRC_CHECK_ARG(n > 0, "xrc_rc_set_volumes: need at least one volume");
@@ -361,6 +361,18 @@ static int rc_set_volumes_impl(xrc_rc* rc, uint32_t n, const float* const* ptrs,
       XRC_CUDA(cudaMemcpyAsync(staging, ptrs[i], nvox * sizeof(float), cudaMemcpyHostToDevice, st));
       d_src = staging;
     }
+    if (hu_lower)
+    {
+      // HU -> linear attenuation on the device before repacking (HUToLinAttFilter, lib/image/xregHUToLinAtt.cpp:45-69);
+      // a device-resident source must not be modified: convert a copy
+      if (!staging)
+      {
+        XRC_CUDA(cudaMalloc(&staging, nvox * sizeof(float)));
+        XRC_CUDA(cudaMemcpyAsync(staging, ptrs[i], nvox * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        d_src = staging;
+      }
+      launch_hu_to_lin_att(staging, nvox, *hu_lower, st);
+    }
     int s = repack_volume(d_src, &v, layout, st);
     if (s == XRC_OK && layout == XRC_LAYOUT_PAX)
       s = build_occupancy(d_src, &v, st);
@@ -376,6 +388,12 @@ int xrc_rc_set_volumes(xrc_rc* rc, uint32_t n, const float* const* host_ptrs, co
                        const float (*idx_to_phys)[12])
 {
   return rc_set_volumes_impl(rc, n, host_ptrs, dims, idx_to_phys, false);
+}
+
+int xrc_rc_set_volumes_hu(xrc_rc* rc, uint32_t n, const float* const* host_ptrs, const uint64_t (*dims)[3],
+                          const float (*idx_to_phys)[12], float hu_lower)
+{
+  return rc_set_volumes_impl(rc, n, host_ptrs, dims, idx_to_phys, false, &hu_lower);
 }
 
 int xrc_rc_set_volumes_device(xrc_rc* rc, uint32_t n, const float* const* dev_ptrs, const uint64_t (*dims)[3],

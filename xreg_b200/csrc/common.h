@@ -114,6 +114,7 @@ struct DrrArgs
 
 int repack_volume(const float* d_linear, DeviceVolume* v, int layout, cudaStream_t st);
 int build_occupancy(const float* d_linear, DeviceVolume* v, cudaStream_t st);
+void launch_hu_to_lin_att(float* d_vol, size_t n, float hu_lower, cudaStream_t st);
 void free_volume(DeviceVolume* v);
 int launch_drr(const DrrArgs& a, int layout, int kernel_id, cudaStream_t st);
 int launch_ray_info(const DrrArgs& a, cudaStream_t st);

@@ -1201,6 +1201,26 @@ __global__ void repack_pax_kernel(const float* __restrict__ src, float4* __restr
 }
 
 
+// HUToLinAttFilter::GenerateData (lib/image/xregHUToLinAtt.cpp:45-69), in place: f64 arithmetic in the reference's
+// operation order (no contraction), rounded to f32 once; mu_water = 0.02683, mu_air = 0.02485e-4 (xregHUToLinAtt.h:73-74)
+__global__ void hu_to_lin_att_kernel(float* __restrict__ v, size_t n, double hu_lower)
+{
+  const double mu_water = 0.02683 * 1.0, mu_air = 0.02485 * 0.0001;
+  const double hu_scale = __dmul_rn(__dsub_rn(mu_water, mu_air), 1.0e-3);
+  const double mu_lower = __dadd_rn(__dmul_rn(hu_lower, hu_scale), mu_water);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+  {
+    const double a = __dsub_rn(__dadd_rn(__dmul_rn((double)v[i], hu_scale), mu_water), mu_lower);
+    v[i] = (float)fmax(a, 0.0);
+  }
+}
+
+void launch_hu_to_lin_att(float* d_vol, size_t n, float hu_lower, cudaStream_t st)
+{
+  hu_to_lin_att_kernel<<<148 * 8, 256, 0, st>>>(d_vol, n, (double)hu_lower);
+  count_launch();
+}
+
 // ---- empty-space map: bit (bx, by, bz) = any non-zero voxel in blocks [bx-1, bx+1] x [by-1, by+1] x [bz-1, bz+1]
 __global__ void occ_raw_kernel(const float* __restrict__ src, uint8_t* __restrict__ raw, int nx, int ny, int nz, int gx,
                                int gy)

@@ -88,6 +88,16 @@ class RayCasterLineIntCUDA:
         self._vols = list(vols)
         self.vols_changed()
 
+    def set_volumes_hu(self, vols: Sequence[Volume], hu_lower: float = -1000.0) -> None:
+        """Volumes in Hounsfield units: converted to linear attenuation on the device while loading
+        (HUToLinAtt, lib/image/xregHUToLinAtt.cpp:45-69), bit-identical to converting on the host first."""
+        self._vols = list(vols)
+        n = len(self._vols)
+        ptrs = (C.POINTER(C.c_float) * n)(*[v.data.ctypes.data_as(C.POINTER(C.c_float)) for v in self._vols])
+        dims = ((C.c_uint64 * 3) * n)(*[(C.c_uint64 * 3)(*v.dims) for v in self._vols])
+        xf = ((C.c_float * 12) * n)(*[(C.c_float * 12)(*[float(t) for t in v.idx_to_phys()]) for v in self._vols])
+        check(self._lib.xrc_rc_set_volumes_hu(self.handle, n, ptrs, dims, xf, float(hu_lower)))
+
     def num_vols(self) -> int:
         return len(self._vols)
 
