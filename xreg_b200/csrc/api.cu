@@ -1533,7 +1533,8 @@ static void affine_mul(const float a[12], const float b[12], float c[12])
 static int obj_fn_set_poses(xrc_rc* rc, uint32_t n_views, uint32_t n_poses, const float* cam_to_phys);
 
 static int obj_fn_enqueue(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t n_views, uint32_t n_poses,
-                          const float* cam_to_phys, uint32_t n_objs = 1, const uint32_t* obj_vols = nullptr, int use_bg = -1)
+                          const float* cam_to_phys, uint32_t n_objs = 1, const uint32_t* obj_vols = nullptr, int use_bg = -1,
+                          bool drr_only = false)
 {
   XRC_CHECK_ARG(rc && sms && cam_to_phys, "xrc_obj_fn: null argument");
   XRC_CHECK_ARG(rc->allocated, "xrc_obj_fn: ray caster resources not allocated");
@@ -1555,6 +1556,8 @@ static int obj_fn_enqueue(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint
   if (n_objs <= 1 && !obj_vols && use_bg < 0)
   {
     XRC_TRY(obj_fn_set_poses(rc, n_views, n_poses, cam_to_phys));
+    if (drr_only)
+      return xrc_rc_compute(rc, vol_idx);
     return xrc_eval_batch_async(rc, vol_idx, sms, n_views);
   }
   // several moving objects (xregIntensity2D3DRegi.cpp:594-629): the first is stored with REPLACE (on the background
@@ -1684,14 +1687,23 @@ int xrc_obj_fn_multi(uint32_t n_dev, xrc_rc* const* rcs, xrc_sm* const* sms, uin
   std::vector<uint32_t> begin(n_dev + 1, 0);
   for (uint32_t d = 0; d < n_dev; ++d)
     begin[d + 1] = begin[d] + base + (d < extra ? 1u : 0u);
-  // enqueue everything first (asynchronous launches: the devices run concurrently), then collect
+  // enqueue everything first (asynchronous launches: the devices run concurrently), then collect.  The ray casts of
+  // all devices go out before any metric kernel, so that the last device starts after n_dev launches, not 4 n_dev.
   int status = XRC_OK;
   uint32_t enqueued = 0;
   for (uint32_t d = 0; d < n_dev && status == XRC_OK; ++d, ++enqueued)
   {
     const uint32_t n = begin[d + 1] - begin[d];
     if (n)
-      status = obj_fn_enqueue(rcs[d], vol_idx, sms + (size_t)d * n_views, n_views, n, cam_to_phys + 12 * (size_t)begin[d]);
+      status = obj_fn_enqueue(rcs[d], vol_idx, sms + (size_t)d * n_views, n_views, n, cam_to_phys + 12 * (size_t)begin[d],
+                              1, nullptr, -1, true);
+  }
+  for (uint32_t d = 0; d < n_dev && status == XRC_OK; ++d)
+  {
+    if (begin[d + 1] == begin[d])
+      continue;
+    for (uint32_t v = 0; v < n_views && status == XRC_OK; ++v)
+      status = xrc_sm_compute(sms[(size_t)d * n_views + v]);
   }
   for (uint32_t d = 0; d < enqueued; ++d)
   {
