@@ -129,9 +129,18 @@ def load():
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
-        raise ImportError(
-            "%s not found: build it with `make -C xreg_b200/csrc` (or __graft_entry__.build()). "
-            "xreg_b200 has no CPU or PyTorch fallback." % LIB_PATH)
+        # a fresh checkout (built artefacts are not in git): compile the product once, or fail loudly
+        csrc = os.path.join(os.path.dirname(LIB_PATH), "csrc")
+        try:
+            import subprocess
+
+            subprocess.run(["make", "-C", csrc], check=True, capture_output=True)
+        except Exception as e:  # no nvcc, compile error, ...
+            raise ImportError(
+                "%s not found and `make -C xreg_b200/csrc` failed (%s). xreg_b200 has no CPU or PyTorch fallback."
+                % (LIB_PATH, e))
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("%s not found after the build. xreg_b200 has no CPU or PyTorch fallback." % LIB_PATH)
     lib = C.CDLL(LIB_PATH)
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
