@@ -115,6 +115,33 @@ int main()
   // P4: each quarter broadcast of one record (4 records per request)
   for (int s = 0; s < nsets; ++s) for (int q = 0; q < 4; ++q) { const uint32_t b = rnd() % n_elems; for (int l = 0; l < 8; ++l) o[s * 32 + q * 8 + l] = b; }
   run<float4>("LDG.128 one record per quarter", o, nsets, n_elems);
+  // P6: DRR-like, but a fraction of the quarters is split between two row/plane segments (lanes 0..k-1 on one run of
+  // records, lanes k..7 on another, far away): what a quarter-warp costs when its rays straddle a b-row or c-plane boundary
+  for (int pct : {25, 50, 100})
+  {
+    for (int s = 0; s < nsets; ++s)
+      for (int q = 0; q < 4; ++q)
+      {
+        const uint32_t b0 = rnd() % (n_elems - 16), b1 = rnd() % (n_elems - 16);
+        const float frac = (rnd() % 1000) / 1000.0f;
+        const bool split = (int)(rnd() % 100) < pct;
+        const int k = 1 + (int)(rnd() % 7);
+        for (int l = 0; l < 8; ++l) o[s * 32 + q * 8 + l] = ((split && l >= k) ? b1 : b0) + (uint32_t)(frac + 0.49f * l);
+      }
+    char name[96];
+    snprintf(name, sizeof(name), "LDG.128 DRR-like, %d %% of the quarters on 2 segments", pct);
+    run<float4>(name, o, nsets, n_elems);
+  }
+  // P7: every quarter on 4 segments (2 rows x 2 planes)
+  for (int s = 0; s < nsets; ++s)
+    for (int q = 0; q < 4; ++q)
+    {
+      uint32_t b[4];
+      for (int j = 0; j < 4; ++j) b[j] = rnd() % (n_elems - 16);
+      const float frac = (rnd() % 1000) / 1000.0f;
+      for (int l = 0; l < 8; ++l) o[s * 32 + q * 8 + l] = b[l >> 1] + (uint32_t)(frac + 0.49f * l);
+    }
+  run<float4>("LDG.128 DRR-like, every quarter on 4 segments", o, nsets, n_elems);
   // P5: fully scattered
   for (int s = 0; s < nsets; ++s) for (int l = 0; l < 32; ++l) o[s * 32 + l] = rnd() % n_elems;
   run<float4>("LDG.128 scattered (32 lines)", o, nsets, n_elems);
