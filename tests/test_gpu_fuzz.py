@@ -111,3 +111,69 @@ def test_random_scene_matches_oracle(ctx, xo, seed):
         assert (np.abs(got[sel] - ref[sel]) / np.abs(ref[sel])).max() <= 1.0e-4
     # numerically tiny pixels: absolute agreement at the rounding level of the largest ones
     assert np.abs(got - ref).max() <= 1.0e-4 * max(scale, 1e-30) + 1e-12
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_metric_case_matches_oracle(ctx, xo, seed):
+    """Randomised parity of the five metrics: image sizes from a few pixels to non-square hundreds, 1..6 moving
+    images (one constant, one equal to the fixed image), masks of random density, Gaussian widths 0..9, patch
+    radii up to the image size limit, strides 1..3."""
+    rng = np.random.default_rng(5000 + seed)
+    kind = ["ncc", "grad-ncc", "patch-ncc", "patch-grad-ncc", "ssd"][seed % 5]
+    rows, cols = int(rng.integers(7, 90)), int(rng.integers(7, 140))
+    n = int(rng.integers(1, 7))
+    base = rng.standard_normal((rows, cols))
+    for ax in (0, 1):   # mild smoothing so that gradients are not pure noise
+        base = (base + np.roll(base, 1, ax) + np.roll(base, -1, ax)) / 3.0
+    fixed = (base * 4 + 6).astype(f32)
+    mov = np.stack([(rng.uniform(0.2, 1.0) * fixed + rng.uniform(0.0, 1.0) * rng.standard_normal((rows, cols)) * 2).astype(f32)
+                    for _ in range(n)])
+    if n >= 2:
+        mov[-1] = 3.25          # constant image: sigma clamp
+    if n >= 3:
+        mov[-2] = fixed
+    mask = None
+    if rng.random() < 0.5:
+        mask = (rng.random((rows, cols)) < rng.uniform(0.3, 0.95)).astype(np.uint8)
+        mask[rows // 2, cols // 2] = 1
+    width = int(rng.choice([0, 3, 5, 7, 9]))
+    rmax = max(1, min(rows, cols) // 2 - 1)
+    # radius >= 2: with 3x3 patches of a heavily smoothed gradient image the reference's f32 two-pass patch
+    # statistics carry ~1e-5 of rounding noise themselves (seen: 1.3e-5 at radius 1, Gaussian width 9)
+    radius = int(rng.integers(2, max(min(rmax, 14), 2) + 1))
+    stride = int(rng.integers(1, 4))
+    cls = {"ncc": xreg_b200.ImgSimMetric2DNCCCUDA, "grad-ncc": xreg_b200.ImgSimMetric2DGradNCCCUDA,
+           "patch-ncc": xreg_b200.ImgSimMetric2DPatchNCCCUDA, "patch-grad-ncc": xreg_b200.ImgSimMetric2DPatchGradNCCCUDA,
+           "ssd": xreg_b200.ImgSimMetric2DSSDCUDA}[kind]
+    sm = cls(ctx)
+    if "grad" in kind:
+        sm.set_smooth_img_before_sobel_kernel_radius(width)
+    opts = xo.patch_opts(radius=radius, stride=stride)
+    if "patch" in kind:
+        sm.set_patch_radius(radius)
+        sm.set_patch_stride(stride)
+    sm.set_num_moving_images(n)
+    sm.set_fixed_image(fixed)
+    sm.set_mov_imgs_host_buf(np.ascontiguousarray(mov))
+    if mask is not None:
+        sm.set_mask(mask)
+    sm.allocate_resources()
+    sm.compute()
+    got = sm.sim_vals()[:n].copy()
+    w = xo.patch_weights(rows, cols, opts, mask=mask) if (mask is not None and "patch" in kind) else None
+    if kind == "ncc":
+        ref = xo.ncc(fixed, mov, mask=mask)
+    elif kind == "grad-ncc":
+        ref = xo.grad_ncc(fixed, mov, mask=mask, gauss_width=width)
+    elif kind == "patch-ncc":
+        ref = xo.patch_ncc(fixed, mov, opts, mask=mask, weights=w)
+    elif kind == "patch-grad-ncc":
+        ref = xo.patch_grad_ncc(fixed, mov, opts, mask=mask, weights=w, gauss_width=width)
+    else:
+        ref = xo.ssd(fixed, mov, mask)
+    sm.close()
+    assert np.all(np.isfinite(got))
+    if kind == "ssd":
+        assert np.all(np.abs(got - ref) <= 1e-5 * ref + 1e-9 * max(float(ref.max()), 1e-30))
+    else:
+        assert np.max(np.abs(got - ref)) <= 1.0e-5, (kind, rows, cols, radius, stride, width, mask is not None)
