@@ -89,3 +89,43 @@ def test_product_does_not_import_the_oracle():
     # the shared library does not link the oracle either
     out = subprocess.run(["ldd", os.path.join(pkg, "libxreg_cuda.so")], capture_output=True, text=True).stdout
     assert "oracle" not in out
+
+
+def _build_c_client(tmp_path):
+    """tests/c_abi/abi_smoke.c: a plain-C99 client of include/xreg_cuda.h linked against libxreg_cuda.so."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "abi_smoke")
+    libdir = os.path.join(root, "xreg_b200")
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
+           os.path.join(root, "tests", "c_abi", "abi_smoke.c"), "-o", exe, "-L", libdir, "-lxreg_cuda", "-lm",
+           "-Wl,-rpath," + libdir]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_header_is_valid_c99_and_c_client_links(tmp_path):
+    """The boundary is a C ABI: the header must compile as strict C99 and a C program must link and run the
+    entry points that need no device (version, exp map, error convention)."""
+    import subprocess
+
+    from xreg_b200 import _lib
+
+    _lib.load()  # builds the library on a fresh checkout
+    exe = _build_c_client(tmp_path)
+    r = subprocess.run([exe, "--no-gpu"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ok" in r.stdout
+
+
+@pytest.mark.gpu
+def test_c_client_end_to_end_on_gpu(tmp_path):
+    """The same C program, whole path: analytic line integral of a constant volume, NCC through xrc_obj_fn."""
+    import subprocess
+
+    exe = _build_c_client(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "abi_smoke: ok" in r.stdout
