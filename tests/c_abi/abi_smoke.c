@@ -87,9 +87,21 @@ int main(int argc, char** argv)
   OK(xrc_rc_compute(rc, 0));
   float* drr = (float*)malloc(sizeof(float) * 2 * 33 * 33);
   OK(xrc_rc_read_projs(rc, 0, 2, drr));
-  /* central ray: along z through 23 mm of material minus the 2 x 1e-3 nudge -> 23 samples of 0.02 at step 1 */
+  /* central ray: along z, 23 voxels of material; the 1e-3 nudge is in units of the 500 mm source-detector segment, so
+   * 0.5 mm goes at either end: 22 steps, 23 samples of 0.02 at step 1 (constant volume, axis-aligned ray) */
   const float centre = drr[16 * 33 + 16];
   CHECK(fabsf(centre - 23.0f * 0.02f) < 1e-5f);
+  /* a denser 8 x 8 column through the middle (re-setting the volume re-packs it): the central ray now sums 0.05's,
+   * and the projection is no longer constant, which the similarity test below needs */
+  for (int z = 0; z < N; ++z)
+    for (int y = 8; y < 16; ++y)
+      for (int x = 8; x < 16; ++x)
+        vol[(z * N + y) * N + x] = 0.05f;
+  OK(xrc_rc_set_volumes(rc, 1, vols, dims, i2p));
+  OK(xrc_rc_compute(rc, 0));
+  OK(xrc_rc_read_projs(rc, 0, 2, drr));
+  CHECK(fabsf(drr[16 * 33 + 16] - 23.0f * 0.05f) < 1e-5f);
+  CHECK(fabsf(drr[0] - 23.0f * 0.02f) < 1e-5f);
   uint64_t total = 0, fetched = 0;
   OK(xrc_rc_ray_info(rc, 0, NULL, NULL, &total));
   OK(xrc_rc_fetched_samples(rc, 0, &fetched));
