@@ -11,7 +11,6 @@ constexpr int kMaxGaussWidth = 31;  // widest supported smoothing kernel
 constexpr int kGradBandRows = 64;   // output rows per warp of the fast gradient kernel (throughput regime)
 constexpr int kGradBandRowsMin = 8; // ... when only a few images are in flight (population 1)
 constexpr int kPatchThreads = 256;  // threads per CTA of the patch kernel (each owns 1 or 2 input columns)
-constexpr int kPatchBandRows = 64;  // patch rows per CTA (throughput regime)
 constexpr int kPatchBandRowsMin = 8;  // ... with few images in flight (population 1)
 constexpr int kMomChunk = 4096;     // pixels per CTA of the plain moments kernel
 
@@ -135,11 +134,30 @@ inline PatchPlan patch_plan(uint32_t rows, uint32_t cols, uint32_t radius, uint3
   const uint32_t w_out = p.cols_per_thread * kPatchThreads - 2 * radius;
   p.n_strips = (cols - 2 * radius + w_out - 1) / w_out;
   const uint32_t nrr = rows - 2 * radius;
-  p.band_rows = kPatchBandRows;
-  while (p.band_rows > (uint32_t)kPatchBandRowsMin &&
-         (uint64_t)p.n_strips * ((nrr + p.band_rows - 1) / p.band_rows) * n_units < 148u * 3u)
-    p.band_rows /= 2;
-  p.n_bands = (nrr + p.band_rows - 1) / p.band_rows;
+  // Every band costs its rows plus the 2 r rows above them (loads only: counted half), and the grid runs in waves
+  // of 148 SMs x 3 resident CTAs.  Pick the number of bands that minimises waves x rows per band; bands shorter
+  // than kPatchBandRowsMin are not worth their pre-roll.
+  const uint64_t slots = 148u * 3u;
+  uint64_t best_cost = ~0ull;
+  uint32_t best_bands = 1;
+  const uint32_t max_bands = (nrr + kPatchBandRowsMin - 1) / kPatchBandRowsMin;
+  for (uint32_t nb = 1; nb <= max_bands; ++nb)
+  {
+    const uint32_t br = (nrr + nb - 1) / nb;
+    const uint32_t bands = (nrr + br - 1) / br;
+    const uint64_t ctas = (uint64_t)p.n_strips * bands * n_units;
+    const uint64_t waves = (ctas + slots - 1) / slots;
+    const uint64_t cost = waves * (2ull * br + 2ull * radius);
+    if (cost < best_cost)
+    {
+      best_cost = cost;
+      best_bands = bands;
+      p.band_rows = br;
+    }
+    if (ctas >= 8 * slots)
+      break;  // many waves already: finer bands only add pre-roll
+  }
+  p.n_bands = best_bands;
   return p;
 }
 // upper bound of n_strips * n_bands over all batch sizes (sizes the partial-sum buffer)
