@@ -216,6 +216,22 @@ int xrc_sm_set_patch_params(xrc_sm* sm, uint32_t radius, uint32_t stride,
                             int use_mask_for_patch_stats, const float* weights,
                             uint64_t n_weights);
 
+/* How the patch metrics combine the per-patch values into the image score.  The reference adds them with a
+ * sequential f32 loop and divides by an f32 total weight accumulated the same way
+ * (xregImgSimMetric2DPatchNCCCPU.cpp:262-287); that sum's rounding error is part of its result (up to ~3e-5 of the
+ * value with mask-coverage weights, ~5e-6 rms at 200 000 unweighted patches).
+ *   XRC_COMBINE_REFERENCE (default): the same sequential f32 sum, reproduced bit for bit by a parallel kernel
+ *       (sim.cu: patch_seqsum_kernel); agrees with the CPU class to ~1e-7.
+ *   XRC_COMBINE_REFERENCE_SERIAL: the literal one-thread loop (verification of the parallel emulation; slow).
+ *   XRC_COMBINE_F64: f64 sums and divisor: closest to exact arithmetic, not to the reference; no per-patch buffer.
+ * Patch kinds only; ignored by the others.  May be changed between computes. */
+enum { XRC_COMBINE_REFERENCE = 0, XRC_COMBINE_REFERENCE_SERIAL = 1, XRC_COMBINE_F64 = 2 };
+int xrc_sm_set_combine_mode(xrc_sm* sm, int mode);
+/* Instrumentation: the kernel behind XRC_COMBINE_REFERENCE on caller data.  host_vals: n_seq sequences of n floats;
+ * host_out[s] = (((0 + v[s][0]) + v[s][1]) + ...) with one f32 rounding per addition.  serial != 0 runs the literal
+ * loop instead of the parallel emulation.  Synchronises. */
+int xrc_seqsum_f32(xrc_ctx* ctx, const float* host_vals, uint32_t n_seq, uint64_t n, int serial, float* host_out);
+
 /* set_mov_imgs_buf_from_ray_caster (:119): zero-copy device hand-off. Re-callable
  * with a new offset; a different ray caster than the first is an error
  * (xregImgSimMetric2DCPU.cpp:45-70). */

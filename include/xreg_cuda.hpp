@@ -1193,6 +1193,10 @@ class ImgSimMetric2DPatchNCCCUDA : public ImgSimMetric2D, public ImgSimMetric2DP
 public:
   explicit ImgSimMetric2DPatchNCCCUDA(Context& ctx) : ImgSimMetric2D(ctx, XRC_SM_PATCH_NCC) {}
 
+  /// XRC_COMBINE_REFERENCE (default: the reference's sequential f32 sum of the per-patch values, bit for bit),
+  /// XRC_COMBINE_REFERENCE_SERIAL (literal loop, verification) or XRC_COMBINE_F64 (double; closest to exact)
+  void set_combine_mode(const int mode) { detail::Check(xrc_sm_set_combine_mode(sm_, mode)); }
+
 protected:
   ImgSimMetric2DPatchNCCCUDA(Context& ctx, const int kind) : ImgSimMetric2D(ctx, kind) {}
 

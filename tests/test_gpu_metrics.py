@@ -251,3 +251,126 @@ def test_combine_mean(ctx, xo):
     comb.set_sim_metrics([a, b])
     comb.compute()
     np.testing.assert_allclose(comb.sim_vals(), xo.combine_mean(np.stack([a.sim_vals(), b.sim_vals()])), rtol=1e-6)
+
+
+# ---- reference-order combine of the per-patch values (XRC_COMBINE_*) -------------------------------------------
+
+def _seqsum(ctx, seqs, serial=False):
+    import ctypes as C
+
+    from xreg_b200 import _lib
+
+    lib = _lib.load()
+    v = np.ascontiguousarray(seqs, dtype=f32)
+    out = np.zeros(v.shape[0], dtype=f32)
+    FP = C.POINTER(C.c_float)
+    _lib.check(lib.xrc_seqsum_f32(ctx.handle, v.ctypes.data_as(FP), v.shape[0], v.shape[1], 1 if serial else 0,
+                                  out.ctypes.data_as(FP)))
+    return out
+
+
+def _seq_literal(seqs):
+    """the reference's loop: `Scalar sum = 0; for (s : vals) sum += s;` (np.cumsum on float32 is sequential)"""
+    v = np.ascontiguousarray(seqs, dtype=f32)
+    if v.shape[1] == 0:
+        return np.zeros(v.shape[0], dtype=f32)
+    with np.errstate(all="ignore"):
+        return np.cumsum(v, axis=1, dtype=f32)[:, -1]
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, dtype=f32).view(np.uint32)
+
+
+@pytest.mark.parametrize("n", [0, 1, 5, 127, 128, 129, 1023, 4099, 206116])
+def test_seqsum_emulation_is_bit_exact(ctx, n):
+    """patch_seqsum_kernel == the literal sequential f32 loop, bit for bit, on the sequences the metric produces
+    (per-patch values in [0, 2], near-constant weighted values) and on adversarial ones (ties at every step, a sum
+    walking down across a binade, mixed signs, tiny and huge magnitudes, NaN)."""
+    rng = np.random.default_rng(n + 1)
+    seqs = [
+        rng.random(n),                                         # per-patch similarities, weights 1
+        rng.random(n) * 3.0e-4,                                # normalised weights times similarities
+        np.full(n, 1.0 / 3800.0),                              # full-coverage weights (total-weight sum)
+        rng.standard_normal(n),                                # mixed signs: the sum keeps crossing zero
+        -rng.random(n),                                        # negative running sum
+        rng.random(n) * 1.0e-20,
+        np.concatenate([[1.0e30], rng.random(max(n - 1, 0)) * 1.0e29])[:n],   # leaves the fast range
+        np.concatenate([[1.0], np.full(max(n - 1, 0), 2.0 ** -24)])[:n],      # every addend is a tie
+        np.concatenate([[8388608.0], np.full(max(n - 1, 0), -0.75)])[:n],     # walks down out of its binade
+        (rng.random(n) * 2 - 0.3) * 1.0e-38,                   # denormal range
+        np.where(rng.random(n) < 0.5, 0.0, rng.random(n)),     # skipped patches contribute +0
+    ]
+    v = np.stack([np.asarray(s, dtype=f32) for s in seqs])
+    want = _seq_literal(v)
+    np.testing.assert_array_equal(_bits(_seqsum(ctx, v, serial=True)), _bits(want))
+    np.testing.assert_array_equal(_bits(_seqsum(ctx, v)), _bits(want))
+    if n > 200:
+        w = v[:1].copy()
+        w[0, n // 2] = np.nan
+        assert np.isnan(_seqsum(ctx, w)[0])
+
+
+def _drr_scene_images(ctx, xo, small_scene, n=4):
+    vol, cam, nominal = small_scene
+    poses = synth.pose_population(vol, nominal, n)
+    drrs = xo.drr(vol.data, vol.idx_to_phys(), [xo.cam_struct(cam)], to12(poses))
+    return synth.add_noise(drrs[0]), np.ascontiguousarray(drrs)
+
+
+@pytest.mark.parametrize("kind", ["patch-ncc", "patch-grad-ncc"])
+@pytest.mark.parametrize("frac", [None, 0.45, 0.9])
+def test_patch_combine_follows_the_reference_sum(ctx, xo, small_scene, kind, frac):
+    """With mask-coverage weights the reference's sequential f32 sums carry a systematic error of a few 1e-5
+    (oracle vs an exact float64 model, checked below); the default combine mode reproduces that sum, so the CUDA
+    value agrees with the CPU class to ~1e-6; the literal-loop mode is bitwise identical to it; the f64 mode
+    agrees with the exact model instead."""
+    from tests.helpers import patch_ncc_model_f64
+
+    fixed, drrs = _drr_scene_images(ctx, xo, small_scene)
+    rows, cols = fixed.shape
+    mask = synth.circular_mask(rows, cols, frac) if frac else None
+    grad = kind == "patch-grad-ncc"
+    cls = xreg_b200.ImgSimMetric2DPatchGradNCCCUDA if grad else xreg_b200.ImgSimMetric2DPatchNCCCUDA
+    o = xo.patch_opts(radius=5)
+    w = xo.patch_weights(rows, cols, o, mask=mask) if mask is not None else None
+    ref = (xo.patch_grad_ncc(fixed, drrs, o, mask=mask, weights=w) if grad else xo.patch_ncc(fixed, drrs, o, mask=mask, weights=w))
+
+    got = {}
+    for mode in ("reference", "reference-serial", "f64"):
+        sm = cls(ctx)
+        sm.set_patch_radius(5)
+        sm.set_combine_mode(mode)
+        got[mode] = _run(sm, fixed, drrs, mask)
+    np.testing.assert_array_equal(_bits(got["reference"]), _bits(got["reference-serial"]))
+    assert np.max(np.abs(got["reference"] - ref)) <= 2.0e-6
+
+    # exact float64 model of the same formula on the oracle's gradient images
+    def exact(k):
+        if not grad:
+            return patch_ncc_model_f64(fixed, drrs[k], 5, mask=mask, weights=w)
+        fgx, fgy = xo.grad_imgs(fixed, 5)
+        gx, gy = xo.grad_imgs(drrs[k], 5)
+        return 0.5 * (patch_ncc_model_f64(fgx, gx, 5, mask=mask, weights=w) + patch_ncc_model_f64(fgy, gy, 5, mask=mask, weights=w))
+
+    ex = np.array([exact(k) for k in range(2)])
+    assert np.max(np.abs(got["f64"][:2] - ex)) <= 2.0e-6
+    if frac == 0.9:
+        # the point of the default mode: here the reference itself is > 1e-5 away from exact arithmetic
+        assert np.max(np.abs(ref[:2] - ex)) > 1.0e-5
+
+
+def test_combine_mode_switch_after_allocation(ctx, xo):
+    fixed = _img(61, 73, seed=3)
+    mov = _movs(fixed, 3, seed=90)
+    sm = xreg_b200.ImgSimMetric2DPatchNCCCUDA(ctx)
+    sm.set_patch_radius(4)
+    sm.set_combine_mode("f64")
+    a = _run(sm, fixed, mov)
+    sm.set_combine_mode("reference")   # per-patch buffer is allocated on demand
+    sm.compute()
+    b = sm.sim_vals().copy()
+    ref = xo.patch_ncc(fixed, mov, xo.patch_opts(radius=4))
+    assert np.max(np.abs(b - ref)) <= 2.0e-6 and np.max(np.abs(a - ref)) <= SIM_TOL
+    with pytest.raises(KeyError):
+        sm.set_combine_mode("bogus")

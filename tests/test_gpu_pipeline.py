@@ -142,7 +142,7 @@ def test_launch_counter_counts_our_kernels(ctx, small_scene):
                                  max_pop=2, patch_radius=5)
     before = xreg_b200.launch_count()
     fn(synth.pose_population(vol, nominal, 2))
-    assert xreg_b200.launch_count() - before == 4  # drr + grad + patch + finalize
+    assert xreg_b200.launch_count() - before == 5  # drr + grad + patch + sequential patch sum + finalize
 
 
 @pytest.fixture(scope="module")

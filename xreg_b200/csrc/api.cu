@@ -179,6 +179,13 @@ struct xrc_sm
   float* d_weights = nullptr;
   double divisor = 1.0;
   uint32_t n_strips = 0;
+  // reference-order combine of the per-patch values (XRC_COMBINE_*)
+  int combine_mode = XRC_COMBINE_REFERENCE;
+  float* d_vals = nullptr;      // max_imgs x n_dirs x n_patches
+  float* d_seq = nullptr;       // max_imgs x n_dirs
+  uint64_t n_patches = 0;
+  float divisor_f = 1.0f;
+  int divide_f = 0;
 };
 
 static int use_device(const xrc_ctx* ctx)
@@ -857,6 +864,8 @@ static void sm_free_resources(xrc_sm* sm)
   dfree(sm->d_partials);
   dfree(sm->d_sims);
   dfree(sm->d_weights);
+  dfree(sm->d_vals);
+  dfree(sm->d_seq);
   if (sm->h_sims)
     cudaFreeHost(sm->h_sims);
   sm->h_sims = nullptr;
@@ -912,6 +921,52 @@ int xrc_sm_set_grad_params(xrc_sm* sm, uint32_t gauss_width)
     XRC_FAIL(XRC_ERR_UNSUPPORTED, "xrc_sm_set_grad_params: smoothing kernel wider than 31 is not supported");
   sm->gauss_width = gauss_width;
   sm->fixed_dirty = true;
+  return XRC_OK;
+}
+
+int xrc_seqsum_f32(xrc_ctx* ctx, const float* host_vals, uint32_t n_seq, uint64_t n, int serial, float* host_out)
+{
+  XRC_CHECK_ARG(ctx && host_vals && host_out && n_seq > 0, "xrc_seqsum_f32: bad argument");
+  XRC_TRY(use_device(ctx));
+  float* d_v = nullptr;
+  float* d_o = nullptr;
+  const size_t len = (size_t)n_seq * n;
+  XRC_CUDA(cudaMalloc(&d_v, std::max<size_t>(len, 1) * sizeof(float)));
+  if (cudaMalloc(&d_o, n_seq * sizeof(float)) != cudaSuccess)
+  {
+    cudaFree(d_v);
+    XRC_FAIL(XRC_ERR_NOMEM, "xrc_seqsum_f32: out of device memory");
+  }
+  int status = XRC_OK;
+  if (cudaMemcpyAsync(d_v, host_vals, len * sizeof(float), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+    status = XRC_ERR_CUDA;
+  if (status == XRC_OK)
+  {
+    SeqSumArgs q;
+    q.vals = d_v;
+    q.n = n;
+    q.n_seq = n_seq;
+    q.out = d_o;
+    q.serial = serial;
+    status = launch_seqsum(q, ctx->stream);
+  }
+  if (status == XRC_OK && (cudaMemcpyAsync(host_out, d_o, n_seq * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                           cudaStreamSynchronize(ctx->stream) != cudaSuccess))
+  {
+    set_error("xrc_seqsum_f32: device failure");
+    status = XRC_ERR_CUDA;
+  }
+  cudaFree(d_v);
+  cudaFree(d_o);
+  return status;
+}
+
+int xrc_sm_set_combine_mode(xrc_sm* sm, int mode)
+{
+  XRC_CHECK_ARG(sm, "null metric");
+  XRC_CHECK_ARG(mode == XRC_COMBINE_REFERENCE || mode == XRC_COMBINE_REFERENCE_SERIAL || mode == XRC_COMBINE_F64,
+                "xrc_sm_set_combine_mode: unknown mode");
+  sm->combine_mode = mode;
   return XRC_OK;
 }
 
@@ -1129,6 +1184,19 @@ static int sm_prepare_fixed(xrc_sm* sm)
       XRC_CHECK_ARG(sm->h_weights.size() == np, "patch weights: expected one weight per patch of the grid");
       XRC_CUDA(cudaMemcpyAsync(sm->d_weights, sm->h_weights.data(), np * sizeof(float), cudaMemcpyHostToDevice, st));
     }
+    // the reference's own divisor: f32, tot_wgt accumulated sequentially over ALL patches (:268-284)
+    sm->divide_f = (sm->compute_mean || sm->weight_sims) ? 1 : 0;
+    if (sm->compute_mean)
+    {
+      sm->divisor_f = (float)np;
+    }
+    else if (sm->weight_sims)
+    {
+      volatile float tw = 0.0f;  // volatile: one rounding per addition, in order
+      for (uint64_t k = 0; k < np; ++k)
+        tw = tw + (sm->has_weights ? sm->h_weights[k] : 1.0f);
+      sm->divisor_f = tw;
+    }
     if (sm->compute_mean)
     {
       sm->divisor = (double)np;
@@ -1224,6 +1292,12 @@ int xrc_sm_allocate(xrc_sm* sm, uint32_t max_imgs)
     parts_per_img = (size_t)n_dirs * sm->n_strips;
     const uint64_t np = (uint64_t)((sm->rows - 1 - 2 * r) / sm->stride + 1) * ((sm->cols - 1 - 2 * r) / sm->stride + 1);
     XRC_CUDA(cudaMalloc(&sm->d_weights, np * sizeof(float)));
+    sm->n_patches = np;
+    if (sm->combine_mode != XRC_COMBINE_F64)
+    {
+      XRC_CUDA(cudaMalloc(&sm->d_vals, (size_t)max_imgs * n_dirs * np * sizeof(float)));
+      XRC_CUDA(cudaMalloc(&sm->d_seq, (size_t)max_imgs * n_dirs * sizeof(float)));
+    }
   }
   sm->partials_len = parts_per_img * max_imgs;
   XRC_CUDA(cudaMalloc(&sm->d_partials, sm->partials_len * sizeof(double)));
@@ -1381,9 +1455,31 @@ int xrc_sm_compute(xrc_sm* sm)
   p.weights = sm->has_weights ? sm->d_weights : nullptr;
   p.weight_patch_sims = sm->weight_sims;
   p.partials = sm->d_partials;
+  const bool ref_order = sm->combine_mode != XRC_COMBINE_F64;
+  if (ref_order && !sm->d_vals)
+  {
+    // the mode was switched on after allocation
+    XRC_CUDA(cudaMalloc(&sm->d_vals, (size_t)sm->max_imgs * n_dirs * sm->n_patches * sizeof(float)));
+    XRC_CUDA(cudaMalloc(&sm->d_seq, (size_t)sm->max_imgs * n_dirs * sizeof(float)));
+  }
+  p.vals = ref_order ? sm->d_vals : nullptr;
+  p.n_patches = sm->n_patches;
   XRC_TRY(launch_patch(p, st));
   PatchFinalizeArgs f;
   memset(&f, 0, sizeof(f));
+  if (ref_order)
+  {
+    SeqSumArgs q;
+    q.vals = sm->d_vals;
+    q.n = sm->n_patches;
+    q.n_seq = sm->n_imgs * n_dirs;
+    q.out = sm->d_seq;
+    q.serial = (sm->combine_mode == XRC_COMBINE_REFERENCE_SERIAL) ? 1 : 0;
+    XRC_TRY(launch_seqsum(q, st));
+    f.seq_sums = sm->d_seq;
+    f.divisor_f = sm->divisor_f;
+    f.divide = sm->divide_f;
+  }
   f.partials = sm->d_partials;
   f.n_imgs = sm->n_imgs;
   f.n_dirs = n_dirs;

@@ -750,9 +750,13 @@ __global__ void __launch_bounds__(kPatchThreads) patch_kernel(const PatchArgs a)
     __syncthreads();
     if (i % st == 0 || FIXED)
     {
+      float vout[C];       // per-patch values of this thread's columns (reference-order combine)
+      bool vhave[C];
 #pragma unroll
       for (int cc = 0; cc < C; ++cc)
       {
+        vhave[cc] = false;
+        vout[cc] = 0.0f;
         const int j = C * t + cc;  // local column == patch's left column
         const int c = c0 + j;
         if (j < W_out && c < ncc_all && (FIXED || c % st == 0))
@@ -799,6 +803,7 @@ __global__ void __launch_bounds__(kPatchThreads) patch_kernel(const PatchArgs a)
           {
             const size_t pk = (size_t)(i / st) * ncc_s + (c / st);  // strided patch index
             const float w = a.weights ? __ldg(a.weights + pk) : 1.0f;
+            float val = 0.0f;  // cur_mov_img_patch_ncc_vals_[k] stays 0 for a skipped patch (:247-250)
             if (!a.weight_patch_sims || (fabsf(w) > 1.0e-6f))
             {
               float sd_m;
@@ -838,9 +843,30 @@ __global__ void __launch_bounds__(kPatchThreads) patch_kernel(const PatchArgs a)
               }
               const float accv = (den_f != 0.0f) ? ((float)num / (sd_m * den_f)) : 0.0f;
               const float sv = 1.0f - accv;
-              total += (double)((a.weight_patch_sims ? w : 1.0f) * sv);
+              val = (a.weight_patch_sims ? w : 1.0f) * sv;
+              total += (double)val;
             }
+            vout[cc] = val;
+            vhave[cc] = true;
           }
+        }
+      }
+      if (!FIXED && a.vals)
+      {
+        // [img][dir][strided patch, row-major]: the reference's patch order (xregImgSimMetric2DPatchCommon.cpp:275-290)
+        const size_t row0 = ((size_t)img * a.n_dirs + dir) * a.n_patches + (size_t)(i / st) * ncc_s;
+        const int cfirst = c0 + C * t;
+        // stride 1: the C columns of a thread are adjacent patches -> one 8-byte store when aligned
+        if (C == 2 && st == 1 && vhave[0] && vhave[C - 1] && (((row0 + cfirst) & 1) == 0))
+        {
+          *reinterpret_cast<float2*>(a.vals + row0 + cfirst) = make_float2(vout[0], vout[C - 1]);
+        }
+        else
+        {
+#pragma unroll
+          for (int cc = 0; cc < C; ++cc)
+            if (vhave[cc])
+              a.vals[row0 + (size_t)((cfirst + cc) / st)] = vout[cc];
         }
       }
     }
@@ -897,6 +923,23 @@ __global__ void __launch_bounds__(32) patch_finalize_kernel(const PatchFinalizeA
 {
   const uint32_t img = blockIdx.x;
   float sd[2] = {0.f, 0.f};
+  if (a.seq_sums)
+  {
+    // reference order: f32 sum / f32 divisor (:268-287), then 0.5 * (x + y)
+    if (threadIdx.x == 0)
+    {
+      for (uint32_t d = 0; d < a.n_dirs; ++d)
+      {
+        const float s = a.seq_sums[(size_t)img * a.n_dirs + d];
+        sd[d] = a.divide ? __fdiv_rn(s, a.divisor_f) : s;
+      }
+      const float sim = (a.n_dirs == 1) ? sd[0] : (float)(0.5 * (double)__fadd_rn(sd[0], sd[1]));
+      a.sims[img] = sim;
+      if (a.sims_host)
+        a.sims_host[img] = sim;
+    }
+    return;
+  }
   for (uint32_t d = 0; d < a.n_dirs; ++d)
   {
     double s = 0.0;
@@ -913,6 +956,249 @@ __global__ void __launch_bounds__(32) patch_finalize_kernel(const PatchFinalizeA
     if (a.sims_host)
       a.sims_host[img] = sim;
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The reference combines the per-patch values with `Scalar patch_sims_sum = 0; for (s : vals) patch_sims_sum += s;`
+// (xregImgSimMetric2DPatchNCCCPU.cpp:262-266): a sequential f32 sum whose rounding errors do not average out
+// (206 116 addends at C2; with mask-coverage weights they are near-constant and the error is systematic, ~3e-5 of the
+// similarity value).  To agree with the reference to ~1e-7 instead of ~1e-5 the same sum is evaluated here, exactly,
+// but not serially:
+//   while the running sum S stays inside one binade [2^e, 2^(e+1)) its ulp u = 2^(e-23) is constant and
+//   RN(S + x) = S + u * rint(x / u) unless x / u lies exactly half-way between two integers (a tie, whose
+//   resolution depends on the parity of S / u).  So a chunk of addends can be rounded to the grid independently,
+//   added as integers (associative: warp scan), and accepted if (a) no addend is a tie, (b) every prefix
+//   S/u + sum q stays in [2^23 + 1, 2^24 - 1] (strictly inside the binade, so that the grid really is u).
+//   A chunk that fails is summed serially (one warp, 128 dependent adds) and the chunks after it are judged again
+//   against the new S.
+// One CTA (8 warps) per sequence; a round is 4096 elements = 32 chunks, one per quarter-warp (16 consecutive
+// addends per lane); lane w of warp 0 judges chunk w.  Bitwise equal to the
+// literal loop (patch_seqsum_serial_kernel; tests/test_gpu_metrics.py::test_seqsum_emulation_is_bit_exact).
+constexpr int kSeqChunk = 128;   // addends per chunk: the unit that is accepted or falls back to the literal loop
+constexpr int kSeqChunks = 32;   // chunks in flight per round (lane w of warp 0 judges chunk w)
+constexpr int kSeqPerLane = 16;  // consecutive addends per lane: a chunk is a quarter-warp (8 lanes)
+constexpr int kSeqWarps = kSeqChunks * kSeqChunk / (32 * kSeqPerLane);  // 8
+
+// lane l of warp w holds elements [i, i + 16), i = round + 512 w + 16 l; the tail is padded with +0 (neutral: the
+// running sum is never -0, a sum started at +0 cannot reach it)
+__device__ __forceinline__ void seq_load(const float* __restrict__ v, uint64_t n, uint64_t i, float (&x)[kSeqPerLane])
+{
+  if (i + kSeqPerLane <= n && ((reinterpret_cast<uintptr_t>(v + i) & 15u) == 0))
+  {
+#pragma unroll
+    for (int k = 0; k < kSeqPerLane / 4; ++k)
+    {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(v + i) + k);
+      x[4 * k] = q.x; x[4 * k + 1] = q.y; x[4 * k + 2] = q.z; x[4 * k + 3] = q.w;
+    }
+  }
+  else
+  {
+#pragma unroll
+    for (int j = 0; j < kSeqPerLane; ++j)
+      x[j] = (i + j < n) ? __ldg(v + i + j) : 0.0f;
+  }
+}
+
+// the literal loop over one chunk (quarter-warp `qtr`): every lane of the warp runs the same chain, the addends
+// come by shuffle
+__device__ __forceinline__ float seq_chunk_serial(float S, const float (&x)[kSeqPerLane], int qtr)
+{
+#pragma unroll 1
+  for (int l = 8 * qtr; l < 8 * qtr + 8; ++l)
+  {
+#pragma unroll
+    for (int j = 0; j < kSeqPerLane; ++j)
+      S = __fadd_rn(S, __shfl_sync(0xffffffffu, x[j], l));
+  }
+  return S;
+}
+
+__global__ void __launch_bounds__(kSeqWarps * 32) patch_seqsum_kernel(const SeqSumArgs a)
+{
+  static_assert(kSeqChunks == 32 && kSeqPerLane * 8 == kSeqChunk, "lane w of warp 0 judges chunk w; a chunk is 8 lanes");
+  // per-chunk records, double buffered by iteration parity: one barrier per iteration is enough (a warp can only
+  // overwrite set k % 2 in iteration k after passing barrier k - 1, which every warp reaches after its reads of
+  // iteration k - 2)
+  __shared__ int sh_sum[2][kSeqChunks], sh_min[2][kSeqChunks], sh_max[2][kSeqChunks], sh_bad[2][kSeqChunks];
+  __shared__ float sh_S_serial[2];
+  const float* __restrict__ v = a.vals + (size_t)blockIdx.x * a.n;
+  const uint64_t n = a.n;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int qtr = lane >> 3, chunk = 4 * warp + qtr;  // this lane's chunk within the round
+  constexpr uint64_t kRound = (uint64_t)kSeqChunks * kSeqChunk;
+  const uint64_t mine = (uint64_t)threadIdx.x * kSeqPerLane;  // offset of this lane's elements inside a round
+  float S = 0.0f;
+  int it = 0;  // iteration parity
+  // rounds are fixed 4096-element windows, the same lanes always own the same part of the window: the loads do not
+  // depend on the sum and are issued two rounds ahead into three register buffers used in rotation (the loop is
+  // unrolled by hand: a register move from a buffer whose load is in flight would wait for it)
+  auto run_round = [&](const uint64_t base, const float (&x)[kSeqPerLane]) {
+    int first = 0;  // chunks [0, first) of this round are already in S
+    while (first < kSeqChunks && base + (uint64_t)first * kSeqChunk < n)
+    {
+      it ^= 1;
+      const float aS = fabsf(S);
+      // fast path needs a normal, finite S with room for the scaling below: 2^-100 <= |S| < 2^100
+      const bool fast = (aS >= 7.888609e-31f) && (aS < 1.2676506e30f);
+      const int e = (__float_as_int(aS) >> 23) - 127;                     // |S| in [2^e, 2^(e+1))
+      int ok = first;
+      if (fast)
+      {
+        if (4 * warp + 3 >= first)
+        {
+          const float scale = __int_as_float((127 + 23 - e) << 23);       // 1 / u = 2^(23 - e), exact
+          const float sgn = (S < 0.0f) ? -1.0f : 1.0f;                    // RN is symmetric: work with |S|, sgn * x
+          // 16 independent roundings first (instruction-level parallelism: only two warps share a scheduler), then
+          // the integer prefix chain
+          int q[kSeqPerLane];
+          unsigned badbits = 0;
+#pragma unroll
+          for (int j = 0; j < kSeqPerLane; ++j)
+          {
+            const float t = __fmul_rn(sgn * x[j], scale);                 // exact (power of two) or flushed towards 0 when tiny
+            // rint and float -> int by the 1.5 * 2^23 trick (exact for |t| < 2^22): FRND / F2I run on the
+            // quarter-rate conversion pipe
+            const float tm = __fadd_rn(t, 12582912.0f);
+            const float r = __fadd_rn(tm, -12582912.0f);
+            // |t| <= 2^18 keeps every integer below inside int32 with room to spare (a larger addend cannot stay in
+            // the binade for long anyway); NaN fails the comparison too
+            const bool b = !(fabsf(t) <= 262144.0f) || (fabsf(__fsub_rn(t, r)) == 0.5f);
+            badbits |= b ? (1u << j) : 0u;
+            q[j] = __float_as_int(tm) - 0x4B400000;
+          }
+          const bool bad = badbits != 0u;
+          int p = 0, mn = 0x7fffffff, mx = -0x7fffffff - 1;
+#pragma unroll
+          for (int j = 0; j < kSeqPerLane; ++j)
+          {
+            p += q[j];
+            mn = min(mn, p);
+            mx = max(mx, p);
+          }
+          if (bad)
+          {
+            // keep the integers below finite; the chunk is rejected anyway
+            p = 0;
+            mn = 0;
+            mx = 0;
+          }
+          // prefix over the 8 lanes of the chunk
+          int incl = p;
+#pragma unroll
+          for (int o = 1; o < 8; o <<= 1)
+          {
+            const int y = __shfl_up_sync(0xffffffffu, incl, o, 8);
+            if ((lane & 7) >= o)
+              incl += y;
+          }
+          const int pre = incl - p;
+          mn += pre;
+          mx += pre;
+#pragma unroll
+          for (int o = 1; o < 8; o <<= 1)
+          {
+            mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o, 8));
+            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o, 8));
+          }
+          const int tot = __shfl_sync(0xffffffffu, incl, 7, 8);
+          const unsigned any_bad = (__ballot_sync(0xffffffffu, bad) >> (8 * qtr)) & 0xffu;
+          if ((lane & 7) == 0)
+          {
+            sh_sum[it][chunk] = tot;   // |tot| <= 128 * 2^18 = 2^25
+            sh_min[it][chunk] = mn;
+            sh_max[it][chunk] = mx;
+            sh_bad[it][chunk] = any_bad != 0u;
+          }
+        }
+        __syncthreads();
+        // every warp judges all chunks (lane w: chunk w): accepted if every chunk of [first, w) is and its own
+        // prefixes stay inside the binade.  32 sums of at most 2^25 fit int32.
+        const int A = (__float_as_int(aS) & 0x7fffff) | 0x800000;  // |S| / u, in [2^23, 2^24)
+        const bool pending = lane >= first;
+        const bool exists = base + (uint64_t)lane * kSeqChunk < n;
+        const int my_sum = pending ? sh_sum[it][lane] : 0;
+        const int my_min = sh_min[it][lane], my_max = sh_max[it][lane], my_bad = sh_bad[it][lane];
+        int incl = my_sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+          const int y = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o)
+            incl += y;
+        }
+        // beyond the first rejected chunk the prefixes are meaningless (and may have wrapped); they are not used
+        const int A_in = A + incl - my_sum;
+        const bool valid = !pending || (exists && !my_bad && ((long long)A_in + my_min >= (1ll << 23) + 1) &&
+                                        ((long long)A_in + my_max <= (1ll << 24) - 1));
+        const unsigned fails = __ballot_sync(0xffffffffu, !valid);
+        ok = fails ? (__ffs(fails) - 1) : 32;  // >= first: the lanes below first vote valid
+        const int add = __shfl_sync(0xffffffffu, incl, ok > 0 ? ok - 1 : 0);
+        const int A_out = A + (ok > 0 ? add : 0);
+        const float u = __int_as_float((127 + e - 23) << 23);
+        const float mag = __fmul_rn((float)A_out, u);  // A_out < 2^24: exact
+        S = (S < 0.0f) ? -mag : mag;
+      }
+      if (ok < kSeqChunks && base + (uint64_t)ok * kSeqChunk < n)
+      {
+        // the first chunk that did not pass: the literal loop, by the warp that holds it; then the rest of the round
+        // is judged again against the new sum
+        if (warp == (ok >> 2))
+        {
+          const float Sn = seq_chunk_serial(S, x, ok & 3);
+          if (lane == 0)
+            sh_S_serial[it] = Sn;
+        }
+        __syncthreads();
+        S = sh_S_serial[it];
+        first = ok + 1;
+      }
+      else
+      {
+        first = kSeqChunks;
+      }
+    }
+  };
+  float xa[kSeqPerLane], xb[kSeqPerLane], xc[kSeqPerLane];
+  seq_load(v, n, mine, xa);
+  seq_load(v, n, kRound + mine, xb);
+  for (uint64_t base = 0; base < n; base += 3 * kRound)
+  {
+    seq_load(v, n, base + 2 * kRound + mine, xc);
+    run_round(base, xa);
+    if (base + kRound >= n)
+      break;
+    seq_load(v, n, base + 3 * kRound + mine, xa);
+    run_round(base + kRound, xb);
+    if (base + 2 * kRound >= n)
+      break;
+    seq_load(v, n, base + 4 * kRound + mine, xb);
+    run_round(base + 2 * kRound, xc);
+  }
+  if (threadIdx.x == 0)
+    a.out[blockIdx.x] = S;
+}
+
+__global__ void patch_seqsum_serial_kernel(const SeqSumArgs a)
+{
+  const float* __restrict__ v = a.vals + (size_t)blockIdx.x * a.n;
+  float S = 0.0f;
+  for (uint64_t k = 0; k < a.n; ++k)
+    S = __fadd_rn(S, v[k]);
+  a.out[blockIdx.x] = S;
+}
+
+int launch_seqsum(const SeqSumArgs& a, cudaStream_t st)
+{
+  if (!a.n_seq)
+    return XRC_OK;
+  if (a.serial)
+    patch_seqsum_serial_kernel<<<a.n_seq, 1, 0, st>>>(a);
+  else
+    patch_seqsum_kernel<<<a.n_seq, kSeqWarps * 32, 0, st>>>(a);
+  count_launch();
+  XRC_CUDA(cudaGetLastError());
+  return XRC_OK;
 }
 
 int launch_patch_finalize(const PatchFinalizeArgs& a, cudaStream_t st)

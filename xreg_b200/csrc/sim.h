@@ -73,6 +73,10 @@ struct PatchArgs
   const float* weights;    // per strided patch or null
   int weight_patch_sims;
   double* partials;        // n_imgs x n_dirs x n_parts
+  // reference-order combine: per-patch values w_k * s_k (0 for skipped patches) in the reference's patch order,
+  // [img][dir][strided patch], or null (f64 combine through `partials` only)
+  float* vals;
+  uint64_t n_patches;      // strided patch count (stride of `vals` per image and direction)
   // fixed-stats mode outputs (when mov[0] == nullptr)
   double* o_mean[2];
   float* o_den[2];
@@ -85,9 +89,26 @@ struct PatchFinalizeArgs
   const double* partials;
   uint32_t n_imgs, n_dirs, n_parts;
   double divisor;  // num_patches (mean), total weight, or 1
+  // reference-order combine: seq_sums[img * n_dirs + dir] = the f32 sequential sum of the per-patch values
+  // (patch_seqsum), divided in f32 by divisor_f when divide != 0 (xregImgSimMetric2DPatchNCCCPU.cpp:262-287)
+  const float* seq_sums;
+  float divisor_f;
+  int divide;
   float* sims;
   float* sims_host;  // optional host-mapped copy (pinned)
 };
+
+// out[s] = (((0 + v[s][0]) + v[s][1]) + ...) in f32, round to nearest even at every step: the reference's
+// `patch_sims_sum += s` loop.  serial != 0: one thread runs the literal loop (verification of the parallel emulation).
+struct SeqSumArgs
+{
+  const float* vals;   // n_seq x n
+  uint64_t n;
+  uint32_t n_seq;
+  float* out;          // n_seq
+  int serial;
+};
+int launch_seqsum(const SeqSumArgs& a, cudaStream_t st);
 
 int launch_grad(const GradArgs& a, cudaStream_t st);
 int launch_moments(const MomentArgs& a, cudaStream_t st);

@@ -216,6 +216,15 @@ class ImgSimMetric2DPatchCommon:
         if b:
             raise _lib.UnsupportedOperationException("random patch subsets are not supported by the CUDA metrics")
 
+    COMBINE_MODES = {"reference": 0, "reference-serial": 1, "f64": 2}
+
+    def set_combine_mode(self, mode: str) -> None:
+        """How the per-patch values become the image score (include/xreg_cuda.h, XRC_COMBINE_*): "reference"
+        (default) reproduces the reference's sequential f32 sum and f32 total weight bit for bit
+        (xregImgSimMetric2DPatchNCCCPU.cpp:262-287), "reference-serial" is the literal one-thread loop, "f64" sums in
+        double (closest to exact arithmetic; differs from the CPU class by its f32 accumulation error)."""
+        check(self._lib.xrc_sm_set_combine_mode(self.handle, self.COMBINE_MODES[mode]))
+
     def set_wgt_img(self, wgt_img: Optional[np.ndarray]) -> None:
         self._wgt_img = None if wgt_img is None else np.ascontiguousarray(wgt_img, dtype=f32)
         if self._allocated:
