@@ -15,6 +15,7 @@
 #include "xregImgSimMetric2D.h"
 #include "xregImgSimMetric2DGradImgParamInterface.h"
 #include "xregImgSimMetric2DPatchCommon.h"
+#include "xregRayCastSyncBuf.h"
 
 #include "xreg_cuda.h"
 
