@@ -352,6 +352,14 @@ def main():
             "fetched_GBps": (32.0 * F_timed + 4.0 * npix * pop_n * K) / (ms_drr * 1e-3) / 1e9,
             "l1tex_peak": l1tex_peak,
             "l1tex_frac": (32.0 * F_timed + 4.0 * npix * pop_n * K) / (ms_drr * 1e-3) / 1e9 / l1tex_peak,
+            # SURVEY 8(d) HBM floor: compulsory bytes of one launch = the volume the beams cross (<= the whole f32
+            # volume; the PAX stack of the principal axis stores it as 16-byte XY-quad records, 4x) + the projections
+            # written + poses + fixed image; measured DRAM traffic / floor = re-read factor
+            "hbm_floor_bytes_f32_volume": float(vol.data.nbytes + 4 * npix * pop_n + 48 * pop_n + 4 * npix),
+            "hbm_floor_bytes_pax_stack": float(4 * vol.data.nbytes + 4 * npix * pop_n + 48 * pop_n + 4 * npix),
+            "reread_factor_vs_f32_volume": (traffic / float(vol.data.nbytes + 4 * npix * pop_n)) if traffic else None,
+            "reread_factor_vs_pax_stack": (traffic / float(4 * vol.data.nbytes + 4 * npix * pop_n)) if traffic else None,
+            "hbm_floor_frac_of_kernel_time": (4 * vol.data.nbytes + 4 * npix * pop_n) / (ms_drr / K * 1e-3) / 1e9 / peak,
             "kernel_ms_no_trim": ms_drr_dense / K,
             "achieved_no_trim": alg_bytes / (ms_drr_dense * 1e-3) / 1e9,
             "l1tex_frac_no_trim": alg_bytes / (ms_drr_dense * 1e-3) / 1e9 / l1tex_peak,
