@@ -1177,12 +1177,14 @@ __global__ void repack_oct_kernel(const float* __restrict__ src, float4* __restr
 }
 
 
-// stack k of XRC_LAYOUT_PAX: A x B x C records, A = n[a]+1, B = n[b]+1, C = n[c]+2
-__global__ void repack_pax_kernel(const float* __restrict__ src, float4* __restrict__ dst, int nx, int ny, int nz, int k)
+// stack k of XRC_LAYOUT_PAX: A x B x C records, A >= n[a]+1, B >= n[b]+1 (row / plane pitch, see pax_pitch), C = n[c]+2;
+// records beyond n[a] / n[b] are never addressed (they hold replicated edge values like the border)
+__global__ void repack_pax_kernel(const float* __restrict__ src, float4* __restrict__ dst, int nx, int ny, int nz, int k,
+                                  int A, int B)
 {
   const int n[3] = {nx, ny, nz};
   const int ka = (k + 1) % 3, kb = (k + 2) % 3;
-  const int A = n[ka] + 1, B = n[kb] + 1, C = n[k] + 2;
+  const int C = n[k] + 2;
   const size_t total = (size_t)A * B * C;
   const size_t st[3] = {1, (size_t)nx, (size_t)nx * ny};
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
@@ -1198,6 +1200,21 @@ __global__ void repack_pax_kernel(const float* __restrict__ src, float4* __restr
     const double v01 = p[a0 * st[ka] + b1 * st[kb]], v11 = p[a1 * st[ka] + b1 * st[kb]];
     dst[i] = make_float4((float)v00, (float)(v10 - v00), (float)(v01 - v00), (float)((v11 - v10) - (v01 - v00)));
   }
+}
+
+
+// Row pitch A (records) and plane pitch A * B of a PAX stack.  Measurement knob: XRC_PAX_PITCH="ra,rb" rounds the
+// row pitch up to ra (mod 8 records = mod one 128-byte line) and B so that the plane pitch is rb (mod 8).
+static void pax_pitch(size_t& A, size_t& B)
+{
+  const char* e = getenv("XRC_PAX_PITCH");
+  int ra = -1, rb = -1;
+  if (!e || sscanf(e, "%d,%d", &ra, &rb) != 2 || ra < 0 || ra > 7 || rb < 0 || rb > 7)
+    return;
+  while ((A & 7) != (size_t)ra)
+    ++A;
+  for (int i = 0; i < 8 && ((A * B) & 7) != (size_t)rb; ++i)
+    ++B;
 }
 
 
@@ -1438,14 +1455,16 @@ int repack_volume(const float* d_linear, DeviceVolume* v, int layout, cudaStream
       v->bytes = 0;
       for (int k = 0; k < 3; ++k)
       {
-        const size_t A = (size_t)n[(k + 1) % 3] + 1, B = (size_t)n[(k + 2) % 3] + 1, C = (size_t)n[k] + 2;
+        size_t A = (size_t)n[(k + 1) % 3] + 1, B = (size_t)n[(k + 2) % 3] + 1;
+        const size_t C = (size_t)n[k] + 2;
+        pax_pitch(A, B);
         if (A * B * C >= (1ull << 32))
           XRC_FAIL(XRC_ERR_UNSUPPORTED, "volume too large for the PAX layout (record index must fit 32 bits)");
         XRC_CUDA(cudaMalloc(&v->pax[k], sizeof(float4) * A * B * C));
         v->pax_sb[k] = (uint32_t)A;
         v->pax_sc[k] = (uint32_t)(A * B);
         v->bytes += sizeof(float4) * A * B * C;
-        repack_pax_kernel<<<grid, block, 0, st>>>(d_linear, (float4*)v->pax[k], nx, ny, nz, k);
+        repack_pax_kernel<<<grid, block, 0, st>>>(d_linear, (float4*)v->pax[k], nx, ny, nz, k, (int)A, (int)B);
         count_launch();
       }
       break;
