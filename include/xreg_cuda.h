@@ -287,10 +287,14 @@ int xrc_obj_fn_objects(xrc_rc* rc, uint32_t n_objs, const uint32_t* vol_idx, xrc
 /* The same objective spread over several GPUs from ONE host thread (the reference's optimiser loops are single
  * threaded, SURVEY 8(b) "Threading"): device d owns rcs[d] and the n_views metrics
  * sms[d * n_views .. d * n_views + n_views), each configured exactly like the single-device objects (same volume,
- * cameras, fixed images, parameters; one xrc_ctx per device).  The population is cut into contiguous balanced chunks
- * (the first n_poses % n_dev devices take one pose more), every device's work is enqueued before any is waited for,
- * and only the n_views x n_poses scalars come back.  Results equal xrc_obj_fn's bit for bit (a pose's value does not
- * depend on its batch).  Each rcs[d] must be allocated for ceil(n_poses / n_dev) * n_views projections. */
+ * cameras, fixed images, parameters; one xrc_ctx per device).  The camera-major list of n_views x n_poses projections
+ * (unit u = v * n_poses + p, the reference's global projection index) is cut into contiguous balanced chunks that may
+ * straddle views (the first n_units % n_dev devices take one unit more): with one view this splits the
+ * population (100 poses on 8 devices: 13 13 13 13 12 12 12 12), with several views and few poses it puts the views
+ * on different devices (three views, one pose: one view each).  Every device's work is enqueued before any is waited
+ * for, and only the n_views x n_poses scalars come back.  Results equal xrc_obj_fn's bit for bit (a pose's value does
+ * not depend on its batch).  Each rcs[d] must be allocated for ceil(n_views * n_poses / n_dev) projections and each
+ * metric for min(n_poses, that many) images. */
 int xrc_obj_fn_multi(uint32_t n_dev, xrc_rc* const* rcs, xrc_sm* const* sms, uint32_t vol_idx, uint32_t n_views,
                      uint32_t n_poses, const float* cam_to_phys, float* sims_out, float* per_view_out);
 /* Same from optimiser variables: pose_p = pre * ExpSE3(params_p) * post with

@@ -101,6 +101,36 @@ def test_multi_device_objective_equals_single_device(ctx, xo, small_scene, metri
         multi.close()
 
 
+def test_multi_device_objective_shards_views(ctx, xo, small_scene):
+    """the camera-major (view, pose) list is cut into contiguous chunks that may straddle views,
+    so a small multi-view population (BOBYQA: one pose, three views) still spreads over the devices.  Values are the
+    single-device ones bit for bit, whatever the split."""
+    vol, cam, nominal = small_scene
+    cams = [cam, CameraModel().setup(380.0, cam.num_det_rows, cam.num_det_cols, 1.7, 1.4),
+            CameraModel().setup(420.0, cam.num_det_rows, cam.num_det_cols, 1.5, 1.6)]
+    pop = synth.pose_population(vol, nominal, 7)
+    xcams = [xo.cam_struct(c) for c in cams]
+    fixed = [synth.add_noise(xo.drr(vol.data, vol.idx_to_phys(), [xc], to12(pop[:1]))[0], seed=s) for s, xc in enumerate(xcams)]
+    single = regi.Intensity2D3DObjFn(ctx, vol, cams, fixed, metric="grad-ncc", max_pop=7)
+    ref = single(pop)
+    ref_pv = np.stack([sm.sim_vals()[:7] for sm in single.sims])
+    lists = _device_lists() + [[0] * 4, [0] * 5]
+    for devices in lists:
+        multi = regi.MultiDeviceObjFn(devices, vol, cams, fixed, max_pop=7, metric="grad-ncc")
+        for sel in (slice(0, 7), slice(2, 3), slice(1, 3), slice(0, 5), slice(6, 7)):
+            got = multi(pop[sel])
+            np.testing.assert_array_equal(got, ref[sel])
+            np.testing.assert_array_equal(multi.per_view, ref_pv[:, sel])
+        # the replicas stay usable on their own after the library re-sized them
+        np.testing.assert_array_equal(multi.replicas[0](pop[:1]), ref[:1])
+        np.testing.assert_array_equal(multi(pop[3:6]), ref[3:6])
+        multi.close()
+    # oracle: the three-view mean of one pose
+    d = [xo.drr(vol.data, vol.idx_to_phys(), [xc], to12(pop[2:3]))[0] for xc in xcams]
+    want = xo.combine_mean(np.stack([xo.grad_ncc(fixed[v], d[v][None], gauss_width=5) for v in range(3)]))
+    assert abs(float(want[0]) - float(ref[2])) <= 1e-5
+
+
 @pytest.mark.parametrize("n_poses", [1, 5])
 def test_multi_object_objective_matches_oracle(ctx, xo, small_scene, n_poses):
     """xrc_obj_fn_objects: two moving volumes with their own pose populations accumulated into the same projections

@@ -1765,12 +1765,75 @@ int xrc_obj_fn_objects(xrc_rc* rc, uint32_t n_objs, const uint32_t* vol_idx, xrc
   return XRC_OK;
 }
 
+// Device d's share of the camera-major (view, pose) unit list, u = v * n_poses + p (the reference's global projection
+// index, xregRayCastInterface.cpp:97-114): of units [u0, u1), view v contributes the poses [p0, p1).
+static void unit_range(uint32_t u0, uint32_t u1, uint32_t v, uint32_t n_poses, uint32_t& p0, uint32_t& p1)
+{
+  const uint64_t lo = (uint64_t)v * n_poses, hi = lo + n_poses;
+  const uint64_t a = std::max<uint64_t>(u0, lo), b = std::min<uint64_t>(u1, hi);
+  p0 = p1 = 0;
+  if (b > a)
+  {
+    p0 = (uint32_t)(a - lo);
+    p1 = (uint32_t)(b - lo);
+  }
+}
+
+// units [u0, u1) on one device: size the ray caster for them, bind each view's metric to its run of projections, hand
+// over the poses (camera-major within the chunk) and enqueue the ray cast.  No synchronisation.
+static int obj_fn_enqueue_units(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t n_views, uint32_t n_poses,
+                                const float* cam_to_phys, uint32_t u0, uint32_t u1)
+{
+  XRC_CHECK_ARG(rc && sms && cam_to_phys, "xrc_obj_fn_multi: null argument");
+  XRC_CHECK_ARG(rc->allocated, "xrc_obj_fn_multi: ray caster resources not allocated");
+  XRC_CHECK_ARG(n_views == rc->cams.size(), "xrc_obj_fn_multi: need one metric per camera model / view");
+  const uint32_t n = u1 - u0;
+  XRC_CHECK_ARG(n <= rc->max_projs, "xrc_obj_fn_multi: a device's share exceeds its allocated projections");
+  if (rc->num_projs != n)
+    XRC_TRY(xrc_rc_set_num_projs(rc, n));
+  uint32_t off = 0;
+  for (uint32_t v = 0; v < n_views; ++v)
+  {
+    uint32_t p0, p1;
+    unit_range(u0, u1, v, n_poses, p0, p1);
+    if (p1 == p0)
+      continue;
+    XRC_CHECK_ARG(sms[v] && sms[v]->rc == rc, "xrc_obj_fn_multi: every metric must be bound to its device's ray caster");
+    XRC_CHECK_ARG(p1 - p0 <= sms[v]->max_imgs, "xrc_obj_fn_multi: a device's share exceeds a metric's capacity");
+    if (sms[v]->n_imgs != p1 - p0)
+      XRC_TRY(xrc_sm_set_num_imgs(sms[v], p1 - p0));
+    if (sms[v]->proj_offset != off)
+      XRC_TRY(xrc_sm_bind_ray_caster(sms[v], rc, off));
+    off += p1 - p0;
+  }
+  rc->ext_poses = nullptr;
+  XRC_TRY(use_device(rc->ctx));
+  XRC_TRY(rc_wait_staging(rc));
+  uint32_t g = 0;
+  for (uint32_t v = 0; v < n_views; ++v)
+  {
+    uint32_t p0, p1;
+    unit_range(u0, u1, v, n_poses, p0, p1);
+    for (uint32_t p = p0; p < p1; ++p, ++g)
+    {
+      memcpy(rc->h_poses + 12 * (size_t)g, cam_to_phys + 12 * (size_t)p, sizeof(float) * 12);
+      rc->h_cam_idx[g] = v;
+    }
+  }
+  if (n <= kInlinePoses)
+    rc->inline_poses = true;  // latency regime: the poses ride in the kernel parameters
+  else
+    XRC_TRY(rc_upload_poses(rc, n));
+  return xrc_rc_compute(rc, vol_idx);
+}
+
 int xrc_obj_fn_multi(uint32_t n_dev, xrc_rc* const* rcs, xrc_sm* const* sms, uint32_t vol_idx, uint32_t n_views,
                      uint32_t n_poses, const float* cam_to_phys, float* sims_out, float* per_view_out)
 {
-  XRC_CHECK_ARG(n_dev > 0 && rcs && sms && cam_to_phys && sims_out, "xrc_obj_fn_multi: bad argument");
+  XRC_CHECK_ARG(n_dev > 0 && rcs && sms && cam_to_phys && sims_out && n_views > 0, "xrc_obj_fn_multi: bad argument");
   if (!n_poses)
     return XRC_OK;
+  XRC_CHECK_ARG((uint64_t)n_views * n_poses < (1ull << 32), "xrc_obj_fn_multi: too many projections");
   std::vector<float> tmp;
   float* pv = per_view_out;
   if (!pv)
@@ -1778,8 +1841,11 @@ int xrc_obj_fn_multi(uint32_t n_dev, xrc_rc* const* rcs, xrc_sm* const* sms, uin
     tmp.resize((size_t)n_views * n_poses);
     pv = tmp.data();
   }
-  // contiguous balanced chunks: the first n_poses % n_dev devices take one pose more (100 poses on 8 devices: 13 13 13 13 12 12 12 12)
-  const uint32_t base = n_poses / n_dev, extra = n_poses % n_dev;
+  // the n_views x n_poses projection list (camera-major) is cut into contiguous balanced chunks, which may
+  // straddle views; the first n_units % n_dev devices take one unit more.  One view: 100 poses on 8 devices -> 13 13 13 13
+  // 12 12 12 12.  Three views, one pose (the BOBYQA regime of a multi-view registration): one view per device.
+  const uint32_t n_units = n_views * n_poses;
+  const uint32_t base = n_units / n_dev, extra = n_units % n_dev;
   std::vector<uint32_t> begin(n_dev + 1, 0);
   for (uint32_t d = 0; d < n_dev; ++d)
     begin[d + 1] = begin[d] + base + (d < extra ? 1u : 0u);
@@ -1788,25 +1854,39 @@ int xrc_obj_fn_multi(uint32_t n_dev, xrc_rc* const* rcs, xrc_sm* const* sms, uin
   int status = XRC_OK;
   uint32_t enqueued = 0;
   for (uint32_t d = 0; d < n_dev && status == XRC_OK; ++d, ++enqueued)
-  {
-    const uint32_t n = begin[d + 1] - begin[d];
-    if (n)
-      status = obj_fn_enqueue(rcs[d], vol_idx, sms + (size_t)d * n_views, n_views, n, cam_to_phys + 12 * (size_t)begin[d],
-                              1, nullptr, -1, true);
-  }
+    if (begin[d + 1] > begin[d])
+      status = obj_fn_enqueue_units(rcs[d], vol_idx, sms + (size_t)d * n_views, n_views, n_poses, cam_to_phys, begin[d],
+                                    begin[d + 1]);
   for (uint32_t d = 0; d < n_dev && status == XRC_OK; ++d)
-  {
-    if (begin[d + 1] == begin[d])
-      continue;
     for (uint32_t v = 0; v < n_views && status == XRC_OK; ++v)
-      status = xrc_sm_compute(sms[(size_t)d * n_views + v]);
-  }
+    {
+      uint32_t p0, p1;
+      unit_range(begin[d], begin[d + 1], v, n_poses, p0, p1);
+      if (p1 > p0)
+        status = xrc_sm_compute(sms[(size_t)d * n_views + v]);
+    }
   for (uint32_t d = 0; d < enqueued; ++d)
   {
-    const uint32_t n = begin[d + 1] - begin[d];
-    if (!n || !rcs[d])
+    if (begin[d + 1] == begin[d] || !rcs[d])
       continue;
-    const int s2 = obj_fn_finish(rcs[d], sms + (size_t)d * n_views, n_views, n, pv + begin[d], n_poses);
+    // the finalize kernels also write the scalars to h_sims (host-mapped pinned memory): no D2H copy to wait for
+    int s2 = use_device(rcs[d]->ctx);
+    if (s2 == XRC_OK)
+    {
+      const cudaError_t e = cudaStreamSynchronize(rcs[d]->ctx->stream);
+      if (e != cudaSuccess)
+      {
+        set_error(std::string("xrc_obj_fn_multi: ") + cudaGetErrorString(e));
+        s2 = XRC_ERR_CUDA;
+      }
+    }
+    for (uint32_t v = 0; v < n_views && s2 == XRC_OK && status == XRC_OK; ++v)
+    {
+      uint32_t p0, p1;
+      unit_range(begin[d], begin[d + 1], v, n_poses, p0, p1);
+      if (p1 > p0)
+        memcpy(pv + (size_t)v * n_poses + p0, sms[(size_t)d * n_views + v]->h_sims, (p1 - p0) * sizeof(float));
+    }
     if (status == XRC_OK)
       status = s2;
   }

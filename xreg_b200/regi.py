@@ -164,8 +164,10 @@ class Intensity2D3DObjFn:
 
 class MultiDeviceObjFn:
     """The objective spread over several GPUs of one box from ONE host thread (xrc_obj_fn_multi): one
-    Intensity2D3DObjFn replica per device (volume, cameras and fixed images replicated), the population cut
-    into contiguous balanced chunks, all devices enqueued before any is waited for, only the scalars gathered.
+    Intensity2D3DObjFn replica per device (volume, cameras and fixed images replicated), the camera-major
+    (view, pose) projection list cut into contiguous balanced chunks that may straddle views (a
+    single-view population is split over the devices, the views of a small multi-view population land on
+    different devices), all devices enqueued before any is waited for, only the scalars gathered.
     This is what a single-threaded C++ caller (the reference's optimiser loop) uses; multi-process jobs use
     ShardedObjFn.  `devices` may name the same device more than once (two contexts / streams on one GPU)."""
 
@@ -177,7 +179,8 @@ class MultiDeviceObjFn:
             raise _lib.XregError("need at least one device")
         self.n_views = len(cams)
         self.max_pop = int(max_pop)
-        per_dev = (self.max_pop + n_dev - 1) // n_dev
+        # a device's chunk of ceil(views * pop / n_dev) projections may lie in a single view
+        per_dev = min(self.max_pop, (self.max_pop * self.n_views + n_dev - 1) // n_dev)
         self.ctxs = [Context(d) for d in self.devices]
         self.replicas = [Intensity2D3DObjFn(c, vol, cams, fixed_imgs, max_pop=per_dev, **kw) for c in self.ctxs]
         self._lib = _lib.load()
