@@ -3,6 +3,8 @@ axis, anisotropic spacing, oblique direction cosines, random cameras (all three 
 poses from "looking at the volume" to "camera inside it" and "missing it", step sizes, both line-integral
 kernels, REPLACE / ACCUM, sparse and dense contents.  Every case: clip masks and per-ray sample counts
 bit-exact, DRR relative error <= 1e-4 (on pixels that are not numerically tiny), trimming on/off bitwise equal."""
+import os
+
 import numpy as np
 import pytest
 
@@ -11,6 +13,8 @@ from xreg_b200.geometry import CameraModel, Volume, to12
 
 pytestmark = pytest.mark.gpu
 f32 = np.float32
+# XREG_FUZZ_SCALE=k multiplies the number of random cases (long runs recorded under profiles/)
+_SCALE = max(1, int(os.environ.get("XREG_FUZZ_SCALE", "1")))
 
 
 def _scene(seed):
@@ -64,7 +68,7 @@ def _scene(seed):
     return vol, cam, np.stack(poses), step, kernel_id, kind
 
 
-@pytest.mark.parametrize("seed", range(48))
+@pytest.mark.parametrize("seed", range(48 * _SCALE))
 def test_random_scene_matches_oracle(ctx, xo, seed):
     vol, cam, poses, step, kernel_id, kind = _scene(seed)
     n = poses.shape[0]
@@ -113,7 +117,7 @@ def test_random_scene_matches_oracle(ctx, xo, seed):
     assert np.abs(got - ref).max() <= 1.0e-4 * max(scale, 1e-30) + 1e-12
 
 
-@pytest.mark.parametrize("seed", range(40))
+@pytest.mark.parametrize("seed", range(40 * _SCALE))
 def test_random_metric_case_matches_oracle(ctx, xo, seed):
     """Randomised parity of the five metrics: image sizes from a few pixels to non-square hundreds, 1..6 moving
     images (one constant, one equal to the fixed image), masks of random density, Gaussian widths 0..9, patch
