@@ -297,6 +297,10 @@ int xrc_obj_fn_objects(xrc_rc* rc, uint32_t n_objs, const uint32_t* vol_idx, xrc
  * metric for min(n_poses, that many) images. */
 int xrc_obj_fn_multi(uint32_t n_dev, xrc_rc* const* rcs, xrc_sm* const* sms, uint32_t vol_idx, uint32_t n_views,
                      uint32_t n_poses, const float* cam_to_phys, float* sims_out, float* per_view_out);
+/* The partition xrc_obj_fn_multi uses (host only, needs no device): of view `view`, device `dev` evaluates the poses
+ * [*first_pose, *first_pose + *count).  For sizing the per-device objects and for callers that shard by themselves. */
+int xrc_obj_fn_multi_share(uint32_t n_dev, uint32_t n_views, uint32_t n_poses, uint32_t dev, uint32_t view,
+                           uint32_t* first_pose, uint32_t* count);
 /* Same from optimiser variables: pose_p = pre * ExpSE3(params_p) * post with
  * SE3OptVarsLieAlg (lib/regi/xregSE3OptVars.cpp:128-137; params = [w_x w_y w_z v_x v_y v_z]) and the
  * intermediate-frame composition of apply_inter_transforms_for_obj_fn (xregIntensity2D3DRegi.cpp:1049-1071).

@@ -125,3 +125,33 @@ def test_library_exp_se3_matches_host_model():
         assert np.max(np.abs(out - ref)) <= 2e-5 * max(1.0, float(np.abs(ref).max())), (x, out, ref)
         R = out.reshape(3, 4)[:, :3].astype(np.float64)
         assert np.max(np.abs(R @ R.T - np.eye(3))) < 1e-5
+
+
+def test_multi_device_partition_covers_every_projection_once():
+    """xrc_obj_fn_multi_share (host-only code of the product library): the camera-major (view, pose) list is cut into
+    contiguous chunks whose sizes differ by at most one; every projection is owned by exactly one device; with one
+    view the chunks are shard_bounds()' (100 poses on 8 devices -> 13 13 13 13 12 12 12 12)."""
+    from xreg_b200 import regi
+
+    for n_dev, n_views, n_poses in [(8, 1, 100), (3, 3, 1), (4, 3, 1), (2, 3, 1), (8, 3, 100), (5, 2, 7), (3, 4, 0), (7, 1, 3)]:
+        owner = -np.ones((n_views, n_poses), dtype=np.int64)
+        sizes = []
+        for d in range(n_dev):
+            tot = 0
+            for v in range(n_views):
+                b, e = regi.multi_device_share(n_dev, n_views, n_poses, d, v)
+                assert 0 <= b <= e <= n_poses
+                assert np.all(owner[v, b:e] == -1)
+                owner[v, b:e] = d
+                tot += e - b
+            sizes.append(tot)
+        assert np.all(owner >= 0)
+        assert max(sizes) - min(sizes) <= 1 and sum(sizes) == n_views * n_poses
+        flat = owner.reshape(-1)                     # camera-major order: owners are non-decreasing -> contiguous chunks
+        assert np.all(np.diff(flat) >= 0)
+        if n_views == 1:
+            mine = [regi.multi_device_share(n_dev, 1, n_poses, d, 0) for d in range(n_dev)]
+            assert [r for r in mine if r[1] > r[0]] == [r for r in regi.shard_bounds(n_poses, n_dev) if r[1] > r[0]]
+    assert [regi.multi_device_share(3, 3, 1, d, d) for d in range(3)] == [(0, 1)] * 3      # C4, population 1: a view each
+    with pytest.raises(Exception):
+        regi.multi_device_share(2, 1, 5, 2, 0)

@@ -1827,6 +1827,27 @@ static int obj_fn_enqueue_units(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms
   return xrc_rc_compute(rc, vol_idx);
 }
 
+// chunk d of n_units units cut into n_dev contiguous balanced chunks: the first n_units % n_dev chunks take one more
+static void unit_chunk(uint32_t n_units, uint32_t n_dev, uint32_t d, uint32_t& u0, uint32_t& u1)
+{
+  const uint32_t base = n_units / n_dev, extra = n_units % n_dev;
+  u0 = d * base + std::min(d, extra);
+  u1 = u0 + base + (d < extra ? 1u : 0u);
+}
+
+int xrc_obj_fn_multi_share(uint32_t n_dev, uint32_t n_views, uint32_t n_poses, uint32_t dev, uint32_t view,
+                           uint32_t* first_pose, uint32_t* count)
+{
+  XRC_CHECK_ARG(n_dev > 0 && dev < n_dev && view < n_views && first_pose && count, "xrc_obj_fn_multi_share: bad argument");
+  XRC_CHECK_ARG((uint64_t)n_views * n_poses < (1ull << 32), "xrc_obj_fn_multi_share: too many projections");
+  uint32_t u0, u1, p0, p1;
+  unit_chunk(n_views * n_poses, n_dev, dev, u0, u1);
+  unit_range(u0, u1, view, n_poses, p0, p1);
+  *first_pose = p0;
+  *count = p1 - p0;
+  return XRC_OK;
+}
+
 int xrc_obj_fn_multi(uint32_t n_dev, xrc_rc* const* rcs, xrc_sm* const* sms, uint32_t vol_idx, uint32_t n_views,
                      uint32_t n_poses, const float* cam_to_phys, float* sims_out, float* per_view_out)
 {
@@ -1844,11 +1865,9 @@ int xrc_obj_fn_multi(uint32_t n_dev, xrc_rc* const* rcs, xrc_sm* const* sms, uin
   // the n_views x n_poses projection list (camera-major) is cut into contiguous balanced chunks, which may
   // straddle views; the first n_units % n_dev devices take one unit more.  One view: 100 poses on 8 devices -> 13 13 13 13
   // 12 12 12 12.  Three views, one pose (the BOBYQA regime of a multi-view registration): one view per device.
-  const uint32_t n_units = n_views * n_poses;
-  const uint32_t base = n_units / n_dev, extra = n_units % n_dev;
   std::vector<uint32_t> begin(n_dev + 1, 0);
   for (uint32_t d = 0; d < n_dev; ++d)
-    begin[d + 1] = begin[d] + base + (d < extra ? 1u : 0u);
+    unit_chunk(n_views * n_poses, n_dev, d, begin[d], begin[d + 1]);
   // enqueue everything first (asynchronous launches: the devices run concurrently), then collect.  The ray casts of
   // all devices go out before any metric kernel, so that the last device starts after n_dev launches, not 4 n_dev.
   int status = XRC_OK;

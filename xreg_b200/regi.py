@@ -162,6 +162,14 @@ class Intensity2D3DObjFn:
         return out
 
 
+def multi_device_share(n_dev: int, n_views: int, n_poses: int, dev: int, view: int) -> Tuple[int, int]:
+    """[begin, end) of the poses of `view` that device `dev` evaluates in xrc_obj_fn_multi (the library's own
+    partition of the camera-major (view, pose) list; host only)."""
+    a, n = C.c_uint32(0), C.c_uint32(0)
+    _lib.check(_lib.load().xrc_obj_fn_multi_share(n_dev, n_views, n_poses, dev, view, C.byref(a), C.byref(n)))
+    return int(a.value), int(a.value + n.value)
+
+
 class MultiDeviceObjFn:
     """The objective spread over several GPUs of one box from ONE host thread (xrc_obj_fn_multi): one
     Intensity2D3DObjFn replica per device (volume, cameras and fixed images replicated), the camera-major
