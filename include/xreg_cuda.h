@@ -297,6 +297,14 @@ int xrc_obj_fn_objects(xrc_rc* rc, uint32_t n_objs, const uint32_t* vol_idx, xrc
  * metric for min(n_poses, that many) images. */
 int xrc_obj_fn_multi(uint32_t n_dev, xrc_rc* const* rcs, xrc_sm* const* sms, uint32_t vol_idx, uint32_t n_views,
                      uint32_t n_poses, const float* cam_to_phys, float* sims_out, float* per_view_out);
+/* One device's part of a sharded objective, for callers that shard across PROCESSES (one rank per GPU: SURVEY 8(e)):
+ * evaluates only the units [first_unit, first_unit + n_units) of the camera-major list u = view * n_poses + pose
+ * (Intensity2D3DRegi::setup's projection order, xregIntensity2D3DRegi.cpp:63-94) and writes their per-view similarity
+ * values to unit_sims_out[0 .. n_units).  cam_to_phys holds all n_poses poses.  The ranks exchange these scalars
+ * (all-gather) and average over views themselves (ImgSimMetric2DCombineMean).  Values equal xrc_obj_fn's per-view
+ * values bit for bit.  rc must be allocated for n_units projections, each metric for the poses of its view in range. */
+int xrc_obj_fn_units(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t n_views, uint32_t n_poses,
+                     const float* cam_to_phys, uint32_t first_unit, uint32_t n_units, float* unit_sims_out);
 /* The partition xrc_obj_fn_multi uses (host only, needs no device): of view `view`, device `dev` evaluates the poses
  * [*first_pose, *first_pose + *count).  For sizing the per-device objects and for callers that shard by themselves. */
 int xrc_obj_fn_multi_share(uint32_t n_dev, uint32_t n_views, uint32_t n_poses, uint32_t dev, uint32_t view,

@@ -131,6 +131,30 @@ def test_multi_device_objective_shards_views(ctx, xo, small_scene):
     assert abs(float(want[0]) - float(ref[2])) <= 1e-5
 
 
+def test_objective_units_equal_the_full_objective(ctx, xo, small_scene):
+    """xrc_obj_fn_units (one rank's part of a (view, pose)-sharded objective): any contiguous range of the camera-major
+    unit list reproduces the full call's per-view values bit for bit; ShardedViewObjFn on one rank = the full objective."""
+    vol, cam, nominal = small_scene
+    cams = [cam, CameraModel().setup(380.0, cam.num_det_rows, cam.num_det_cols, 1.7, 1.4),
+            CameraModel().setup(420.0, cam.num_det_rows, cam.num_det_cols, 1.5, 1.6)]
+    pop = synth.pose_population(vol, nominal, 5)
+    xcams = [xo.cam_struct(c) for c in cams]
+    fixed = [synth.add_noise(xo.drr(vol.data, vol.idx_to_phys(), [xc], to12(pop[:1]))[0], seed=s) for s, xc in enumerate(xcams)]
+    fn = regi.Intensity2D3DObjFn(ctx, vol, cams, fixed, metric="patch-grad-ncc", max_pop=5, patch_radius=6)
+    ref = fn(pop)
+    flat = np.stack([sm.sim_vals()[:5] for sm in fn.sims]).reshape(-1)
+    for first, count in [(0, 15), (0, 1), (4, 3), (5, 5), (7, 8), (14, 1), (3, 0)]:
+        np.testing.assert_array_equal(fn.eval_units(pop, first, count), flat[first:first + count])
+    np.testing.assert_array_equal(fn(pop), ref)                      # the object still works as a whole afterwards
+    one = fn.eval_units(pop[2:3], 1, 2)                              # one pose: views 1 and 2
+    np.testing.assert_array_equal(one, flat.reshape(3, 5)[1:, 2])
+    sharded = regi.ShardedViewObjFn(fn.eval_units, 3)
+    np.testing.assert_array_equal(sharded(pop), ref)
+    with pytest.raises(xreg_b200.XregError):
+        fn.eval_units(pop, 10, 6)                                    # beyond the 15 units
+    fn.close()
+
+
 @pytest.mark.parametrize("n_poses", [1, 5])
 def test_multi_object_objective_matches_oracle(ctx, xo, small_scene, n_poses):
     """xrc_obj_fn_objects: two moving volumes with their own pose populations accumulated into the same projections

@@ -76,3 +76,66 @@ def test_sharded_objective_world_size_2(n_poses):
     for rank, full, ref in res:
         assert len(full) == n_poses
         np.testing.assert_array_equal(np.array(full, np.float32), np.array(ref, np.float32))
+
+
+def _view_worker(rank, world, port, n_poses, q):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import xreg_oracle as xo
+    from xreg_b200 import synth
+    from xreg_b200.geometry import CameraModel, to12
+    from xreg_b200.regi import ShardedViewObjFn, combine_mean
+
+    vol = synth.make_volume(24, 24, 20, spacing=(1.5, 1.5, 1.8))
+    cams = [xo.cam_struct(CameraModel().setup(f, 20, 24, 4.0, 4.0)) for f in (300.0, 280.0, 320.0)]
+    nominal = synth.nominal_pose(vol, src_to_iso=180.0)
+    poses = synth.pose_population(vol, nominal, n_poses)
+    fixed = [xo.drr(vol.data, vol.idx_to_phys(), [c], to12(poses[:1]), n_threads=1)[0] for c in cams]
+    calls = []
+
+    def view_vals(v, p):
+        return xo.grad_ncc(fixed[v], xo.drr(vol.data, vol.idx_to_phys(), [cams[v]], to12(p), n_threads=1), n_threads=1)
+
+    def local_units(p, first, count):   # the oracle standing in for Intensity2D3DObjFn.eval_units on this rank
+        calls.append((first, count))
+        n = len(p)
+        out = []
+        for v in range(3):
+            lo, hi = max(first, v * n), min(first + count, (v + 1) * n)
+            if hi > lo:
+                out.append(view_vals(v, p[lo - v * n:hi - v * n]))
+        return np.concatenate(out)
+
+    fn = ShardedViewObjFn(local_units, 3, rank, world)
+    full = fn(poses)
+    ref_pv = np.stack([view_vals(v, poses) for v in range(3)])
+    q.put((rank, full.tolist(), combine_mean(ref_pv).tolist(), fn.per_view.tolist(), ref_pv.tolist(), calls))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_poses", [1, 4])
+def test_view_sharded_objective_world_size_2(n_poses):
+    """Config C4's sharding: the camera-major (view, pose) list split over the ranks, chunks straddling views
+    (3 views x 1 pose on 2 ranks -> 2 + 1 projections), scalars all-gathered, view mean on every rank."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_view_worker, args=(r, 2, port, n_poses, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    units = 3 * n_poses
+    for rank, full, ref, pv, ref_pv, calls in res:
+        assert len(full) == n_poses
+        np.testing.assert_array_equal(np.array(full, np.float32), np.array(ref, np.float32))
+        np.testing.assert_array_equal(np.array(pv, np.float32), np.array(ref_pv, np.float32))
+        first = 0 if rank == 0 else (units + 1) // 2
+        count = (units + 1) // 2 if rank == 0 else units // 2
+        assert calls == [(first, count)]

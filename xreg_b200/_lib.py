@@ -118,6 +118,7 @@ SIGNATURES = {
     "xrc_obj_fn_objects": [_VP, _U32, _U32P, C.POINTER(_VP), _U32, _U32, _FP, C.c_int, _FP, _FP],
     "xrc_obj_fn_multi": [_U32, C.POINTER(_VP), C.POINTER(_VP), _U32, _U32, _U32, _FP, _FP, _FP],
     "xrc_obj_fn_se3": [_VP, _U32, C.POINTER(_VP), _U32, _U32, _FP, _FP, _FP, _FP, _FP],
+    "xrc_obj_fn_units": [_VP, _U32, C.POINTER(_VP), _U32, _U32, _FP, _U32, _U32, _FP],
     "xrc_obj_fn_multi_share": [_U32, _U32, _U32, _U32, _U32, _U32P, _U32P],
     "xrc_exp_se3": [_FP, _FP],
 }

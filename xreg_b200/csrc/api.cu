@@ -1848,6 +1848,43 @@ int xrc_obj_fn_multi_share(uint32_t n_dev, uint32_t n_views, uint32_t n_poses, u
   return XRC_OK;
 }
 
+// wait for a device's chunk and scatter its scalars: unit u = v * n_poses + p goes to dst[u - dst_first_unit]
+static int obj_fn_finish_units(xrc_rc* rc, xrc_sm* const* sms, uint32_t n_views, uint32_t n_poses, uint32_t u0, uint32_t u1,
+                               float* dst, uint32_t dst_first_unit)
+{
+  XRC_TRY(use_device(rc->ctx));
+  // the finalize kernels also write the scalars to h_sims (host-mapped pinned memory): no D2H copy to wait for
+  XRC_CUDA(cudaStreamSynchronize(rc->ctx->stream));
+  for (uint32_t v = 0; v < n_views; ++v)
+  {
+    uint32_t p0, p1;
+    unit_range(u0, u1, v, n_poses, p0, p1);
+    if (p1 > p0)
+      memcpy(dst + ((size_t)v * n_poses + p0 - dst_first_unit), sms[v]->h_sims, (p1 - p0) * sizeof(float));
+  }
+  return XRC_OK;
+}
+
+int xrc_obj_fn_units(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t n_views, uint32_t n_poses,
+                     const float* cam_to_phys, uint32_t first_unit, uint32_t n_units, float* unit_sims_out)
+{
+  XRC_CHECK_ARG(rc && sms && cam_to_phys && unit_sims_out && n_views > 0, "xrc_obj_fn_units: bad argument");
+  XRC_CHECK_ARG((uint64_t)n_views * n_poses < (1ull << 32) && (uint64_t)first_unit + n_units <= (uint64_t)n_views * n_poses,
+                "xrc_obj_fn_units: unit range outside the n_views x n_poses projection list");
+  if (!n_units)
+    return XRC_OK;
+  const uint32_t u0 = first_unit, u1 = first_unit + n_units;
+  XRC_TRY(obj_fn_enqueue_units(rc, vol_idx, sms, n_views, n_poses, cam_to_phys, u0, u1));
+  for (uint32_t v = 0; v < n_views; ++v)
+  {
+    uint32_t p0, p1;
+    unit_range(u0, u1, v, n_poses, p0, p1);
+    if (p1 > p0)
+      XRC_TRY(xrc_sm_compute(sms[v]));
+  }
+  return obj_fn_finish_units(rc, sms, n_views, n_poses, u0, u1, unit_sims_out, u0);
+}
+
 int xrc_obj_fn_multi(uint32_t n_dev, xrc_rc* const* rcs, xrc_sm* const* sms, uint32_t vol_idx, uint32_t n_views,
                      uint32_t n_poses, const float* cam_to_phys, float* sims_out, float* per_view_out)
 {
@@ -1888,24 +1925,7 @@ int xrc_obj_fn_multi(uint32_t n_dev, xrc_rc* const* rcs, xrc_sm* const* sms, uin
   {
     if (begin[d + 1] == begin[d] || !rcs[d])
       continue;
-    // the finalize kernels also write the scalars to h_sims (host-mapped pinned memory): no D2H copy to wait for
-    int s2 = use_device(rcs[d]->ctx);
-    if (s2 == XRC_OK)
-    {
-      const cudaError_t e = cudaStreamSynchronize(rcs[d]->ctx->stream);
-      if (e != cudaSuccess)
-      {
-        set_error(std::string("xrc_obj_fn_multi: ") + cudaGetErrorString(e));
-        s2 = XRC_ERR_CUDA;
-      }
-    }
-    for (uint32_t v = 0; v < n_views && s2 == XRC_OK && status == XRC_OK; ++v)
-    {
-      uint32_t p0, p1;
-      unit_range(begin[d], begin[d + 1], v, n_poses, p0, p1);
-      if (p1 > p0)
-        memcpy(pv + (size_t)v * n_poses + p0, sms[(size_t)d * n_views + v]->h_sims, (p1 - p0) * sizeof(float));
-    }
+    const int s2 = obj_fn_finish_units(rcs[d], sms + (size_t)d * n_views, n_views, n_poses, begin[d], begin[d + 1], pv, 0);
     if (status == XRC_OK)
       status = s2;
   }

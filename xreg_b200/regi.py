@@ -109,6 +109,24 @@ class Intensity2D3DObjFn:
             sm._sim_vals[:n] = per_view[v]
         return out
 
+    def eval_units(self, poses: np.ndarray, first_unit: int, n_units: int) -> np.ndarray:
+        """This device's part of a sharded objective (xrc_obj_fn_units): the per-view similarity values of the units
+        [first_unit, first_unit + n_units) of the camera-major list u = view * n + pose, for all n poses given."""
+        p12 = to12(poses) if np.asarray(poses).ndim == 3 else np.ascontiguousarray(poses, dtype=f32).reshape(-1, 12)
+        n = p12.shape[0]
+        out = np.empty(int(n_units), dtype=f32)
+        if n_units == 0:
+            return out
+        if n > self.max_pop:
+            raise _lib.XregError("population larger than the allocated capacity")
+        self.rc._flush_params()
+        FP = C.POINTER(C.c_float)
+        _lib.check(self._lib.xrc_obj_fn_units(self.rc.handle, 0, self._sm_arr, self.n_views, n, p12.ctypes.data_as(FP),
+                                              int(first_unit), int(n_units), out.ctypes.data_as(FP)))
+        self.rc._poses_dirty = False
+        self._cur_pop = -1   # the library re-sized / re-bound the objects
+        return out
+
     def close(self) -> None:
         """Destroy the metrics and the ray caster (before their Context is closed)."""
         for sm in self.sims:
@@ -228,6 +246,64 @@ class MultiDeviceObjFn:
             self.close()
         except Exception:
             pass
+
+
+def unit_chunks(n_units: int, world_size: int) -> List[Tuple[int, int]]:
+    """[begin, end) of every rank's chunk of the camera-major (view, pose) unit list: shard_bounds() over units
+    (the partition of xrc_obj_fn_multi / xrc_obj_fn_multi_share)."""
+    return shard_bounds(n_units, world_size)
+
+
+def combine_mean(per_view: np.ndarray) -> np.ndarray:
+    """ImgSimMetric2DCombineMean::compute (xregImgSimMetric2DCombine.cpp:67-86): sequential f32 sum over views / n_views."""
+    pv = np.asarray(per_view, dtype=f32)
+    acc = np.zeros(pv.shape[1], dtype=f32)
+    for v in range(pv.shape[0]):
+        acc = (acc + pv[v]).astype(f32)
+    return (acc / f32(pv.shape[0])).astype(f32)
+
+
+class ShardedViewObjFn:
+    """(view, pose)-sharded objective over a torch.distributed process group (config C4: "views sharded across GPUs").
+
+    The camera-major list of n_views x n projections is cut into world_size contiguous balanced chunks that may
+    straddle views; local_units_fn(poses, first_unit, n_units) evaluates this rank's chunk (on a GPU rank:
+    Intensity2D3DObjFn.eval_units) and returns its per-view values; the ranks all-gather the scalars and every rank
+    averages over views.  A population of one pose and three views keeps three ranks busy instead of one."""
+
+    def __init__(self, local_units_fn: Callable[[np.ndarray, int, int], np.ndarray], n_views: int, rank: int = 0,
+                 world_size: int = 1, device: str = "cpu", group=None):
+        self.local_units_fn = local_units_fn
+        self.n_views = int(n_views)
+        self.rank, self.world_size = int(rank), int(world_size)
+        self.device = device
+        self.group = group
+        self.per_view: Optional[np.ndarray] = None
+
+    def __call__(self, poses: np.ndarray) -> np.ndarray:
+        poses = np.asarray(poses)
+        n = poses.shape[0]
+        if n == 0:
+            return np.zeros(0, dtype=f32)
+        bounds = unit_chunks(self.n_views * n, self.world_size)
+        b, e = bounds[self.rank]
+        local = np.asarray(self.local_units_fn(poses, b, e - b), dtype=f32) if e > b else np.zeros(0, dtype=f32)
+        if self.world_size == 1:
+            flat = local
+        else:
+            import torch
+            import torch.distributed as dist
+
+            width = max(hi - lo for lo, hi in bounds)
+            send = torch.zeros(width, dtype=torch.float32, device=self.device)
+            if e > b:
+                send[: e - b] = torch.from_numpy(local).to(self.device)
+            parts = [torch.empty(width, dtype=torch.float32, device=self.device) for _ in range(self.world_size)]
+            dist.all_gather(parts, send, group=self.group)
+            recv = torch.stack(parts).cpu().numpy()
+            flat = np.concatenate([recv[r, : hi - lo] for r, (lo, hi) in enumerate(bounds)]).astype(f32)
+        self.per_view = flat.reshape(self.n_views, n)
+        return combine_mean(self.per_view)
 
 
 class ShardedObjFn:
