@@ -124,6 +124,8 @@ def cpu_oracle_leg(w, vol, cam, pops, fixed, budget_s, steps=1, warmup=0):
     from xreg_b200 import synth
     from xreg_b200.geometry import to12
 
+    # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank)
+    xo.set_num_threads(xo.host_cores())
     xcam = [xo.cam_struct(cam)]
     radius = synth.patch_radius_for(w["det"])
     opts = xo.patch_opts(radius=radius)
@@ -158,6 +160,7 @@ def run_reference(args, w):
     from xreg_b200 import synth
     from xreg_b200.geometry import to12
 
+    xo.set_num_threads(xo.host_cores())   # torchrun exports OMP_NUM_THREADS=1 to every rank
     fixed = synth.add_noise(xo.drr(vol.data, vol.idx_to_phys(), [xo.cam_struct(cam)], to12(held_out[None]))[0])
     pps, cores, n, ms = cpu_oracle_leg(w, vol, cam, pops, fixed, budget_s=150.0, steps=args.steps, warmup=args.warmup)
     sample = "%d of %d poses per step (full %dx%d detector, full volume), %d steps" % (n, w["pop"], w["det"], w["det"], args.steps)

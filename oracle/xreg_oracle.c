@@ -29,6 +29,17 @@ int xo_num_threads(void)
 #endif
 }
 
+/* Overrides OMP_NUM_THREADS (launchers such as torchrun export OMP_NUM_THREADS=1 to every rank). */
+void xo_set_num_threads(int n)
+{
+#ifdef _OPENMP
+  if (n > 0)
+    omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 static int resolve_threads(int n_threads)
 {
   const int mx = xo_num_threads();

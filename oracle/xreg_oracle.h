@@ -151,6 +151,8 @@ void xo_patch_grad_ncc(const float* fixed, const uint8_t* mask, uint32_t rows, u
 void xo_combine_mean(const float* view_sims, uint32_t n_views, uint32_t n_poses, float* out);
 
 int xo_num_threads(void);
+/* omp_set_num_threads: overrides an inherited OMP_NUM_THREADS (torchrun exports 1 to every rank) */
+void xo_set_num_threads(int n);
 
 #ifdef __cplusplus
 }

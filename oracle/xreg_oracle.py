@@ -93,6 +93,19 @@ def num_threads() -> int:
     return int(lib().xo_num_threads())
 
 
+def set_num_threads(n: int) -> None:
+    """Use n OpenMP threads from now on, whatever OMP_NUM_THREADS said at start-up."""
+    lib().xo_set_num_threads(C.c_int(int(n)))
+
+
+def host_cores() -> int:
+    """Cores this process may run on (affinity mask), the thread count of the timed CPU legs."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def affine_inverse(a12):
     a = _f32(a12).reshape(12)
     out = np.zeros(12, np.float32)
