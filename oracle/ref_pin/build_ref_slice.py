@@ -1,0 +1,207 @@
+#!/usr/bin/env python
+"""TEST INFRASTRUCTURE.  Builds oracle/_ref/libxreg_refslice.so from the reference's OWN source lines, where they lie
+under /root/reference, for the geometric core of the DRR path:
+
+  lib/spatial/xregSpatialPrimitives.cpp     xreg::RayRectIntersect
+  lib/transforms/xregPerspectiveXform.cpp   xreg::CameraModel::ind_pt_to_phys_det_pt (both overloads)
+  lib/ray_cast/xregRayCastLineIntCPU.cpp    the un-named namespace: AccumLineIntKernel, MaxLineIntKernel,
+                                            LineIntParams, ComputeLineInts<Kernel>
+
+The reference as a whole cannot be compiled here (ITK, Eigen, OpenCV, TBB, Boost are absent: DESIGN.md section 1), but
+these functions only need a handful of vector / matrix / interpolator types.  This script cuts the functions out of the
+reference files BY ANCHOR (function signatures, not line numbers) into a generated translation unit under oracle/_ref/
+(git-ignored: no reference source enters the repository), puts oracle/ref_pin/ref_pin_prelude.h (our functional
+stand-ins for the Eigen / ITK / TBB types, with the stated arithmetic conventions) in front and a C ABI behind, and
+compiles it with the oracle's flags (g++ -O2 -ffp-contract=off, no -march).  tests/test_oracle_ref_slice.py then
+requires the oracle's restatement to agree with it bit for bit.
+
+Run from build() in __graft_entry__.py when /root/reference exists; the .so travels to the GPU box with the snapshot.
+"""
+import os
+import re
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT_DIR = os.path.join(os.path.dirname(HERE), "_ref")
+REF = os.environ.get("XREG_REFERENCE", "/root/reference")
+LIB = os.path.join(OUT_DIR, "libxreg_refslice.so")
+
+
+def _lines(rel):
+    with open(os.path.join(REF, rel)) as f:
+        return f.read().split("\n")
+
+
+def _cut_function(lines, first_line_regex, n_closing=1):
+    """Lines from the one matching first_line_regex through the n-th following line that is exactly '}'."""
+    start = next(i for i, ln in enumerate(lines) if re.search(first_line_regex, ln))
+    i, seen = start, 0
+    while seen < n_closing:
+        i += 1
+        if lines[i].rstrip() == "}":
+            seen += 1
+    return start, i
+
+
+def slices():
+    out = []
+    # RayRectIntersect: the return type sits on the line before the qualified name
+    ln = _lines("lib/spatial/xregSpatialPrimitives.cpp")
+    s, e = _cut_function(ln, r"^xreg::RayRectIntersect\(")
+    assert ln[s - 1].startswith("std::tuple<bool,"), ln[s - 1]
+    out.append(("lib/spatial/xregSpatialPrimitives.cpp", s - 1, e, ln[s - 1:e + 1]))
+    # ind_pt_to_phys_det_pt(const Pt2&) and (const Pt3&): two consecutive definitions
+    ln = _lines("lib/transforms/xregPerspectiveXform.cpp")
+    s, e = _cut_function(ln, r"^xreg::Pt3 xreg::CameraModel::ind_pt_to_phys_det_pt\(const Pt2& ind_pt\) const", n_closing=2)
+    assert any("ind_pt_to_phys_det_pt(const Pt3& ind_pt) const" in x for x in ln[s:e + 1])
+    out.append(("lib/transforms/xregPerspectiveXform.cpp", s, e, ln[s:e + 1]))
+    # the un-named namespace of the CPU line-integral ray caster
+    ln = _lines("lib/ray_cast/xregRayCastLineIntCPU.cpp")
+    k = next(i for i, x in enumerate(ln) if x.startswith("struct AccumLineIntKernel"))
+    s = max(i for i in range(k) if ln[i].strip() == "namespace")
+    e = next(i for i in range(k, len(ln)) if re.match(r"^\}\s*//\s*un-named", ln[i]))
+    body = ln[s:e + 1]
+    assert any("void ComputeLineInts(" in x for x in body) and any("struct LineIntParams" in x for x in body)
+    out.append(("lib/ray_cast/xregRayCastLineIntCPU.cpp", s, e, body))
+    return out
+
+
+WRAPPER = r'''
+// ---- C ABI over the reference's functions (ours) --------------------------------------------------------------------
+struct xref_cam
+{
+  uint32_t rows, cols;
+  float intrins_inv[9];   // row-major
+  float extrins_inv[12];  // row-major 3x4
+  float pinhole[3];
+  float focal_len;
+  int32_t frame_type;
+};
+
+static xreg::FrameTransform affine_from12(const float* a)
+{
+  xreg::FrameTransform t;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 4; ++j)
+      t.m[i][j] = a[4 * i + j];
+  return t;
+}
+
+static xreg::CameraModel cam_from(const xref_cam& c)
+{
+  xreg::CameraModel m;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j)
+      m.intrins_inv(i, j) = c.intrins_inv[3 * i + j];
+  m.extrins_inv = affine_from12(c.extrins_inv);
+  for (int i = 0; i < 3; ++i)
+    m.pinhole_pt(i) = c.pinhole[i];
+  m.focal_len = c.focal_len;
+  m.num_det_rows = c.rows;
+  m.num_det_cols = c.cols;
+  m.coord_frame_type = static_cast<xreg::CameraModel::CameraCoordFrame>(c.frame_type);
+  return m;
+}
+
+extern "C" int xref_ray_rect_intersect(const float mn[3], const float mx[3], const float p[3], const float d[3],
+                                       int limit_to_segment, float* t_start, float* t_stop)
+{
+  xreg::Pt3 a, b, c, e;
+  for (int i = 0; i < 3; ++i)
+  {
+    a(i) = mn[i];
+    b(i) = mx[i];
+    c(i) = p[i];
+    e(i) = d[i];
+  }
+  bool hit = false;
+  std::tie(hit, *t_start, *t_stop) = xreg::RayRectIntersect(a, b, c, e, limit_to_segment != 0);
+  return hit ? 1 : 0;
+}
+
+extern "C" void xref_ind_pt_to_phys_det_pt(const xref_cam* cam, float col, float row, float out[3])
+{
+  const xreg::CameraModel m = cam_from(*cam);
+  xreg::Pt2 ind;
+  ind(0) = col;
+  ind(1) = row;
+  const xreg::Pt3 r = m.ind_pt_to_phys_det_pt(ind);
+  for (int i = 0; i < 3; ++i)
+    out[i] = r(i);
+}
+
+// RayCasterLineIntCPU::compute's call of ComputeLineInts (xregRayCastLineIntCPU.cpp, after pre_compute): the caller
+// passes the already inverted physical-point -> index transform (Eigen's .inverse() is third-party arithmetic) and an
+// initialised projection buffer (REPLACE: zeros / background, ACCUM: the previous content).
+extern "C" int xref_compute_line_ints(const float* vol, const uint64_t dims[3], const float phys_to_idx[12],
+                                      const xref_cam* cams, uint32_t n_cams, const float* poses,
+                                      const uint32_t* cam_idx, uint32_t n_projs, float step_size, int kernel_id,
+                                      float* proj_buf)
+{
+  if (!n_cams || !n_projs)
+    return 0;
+  xreg::RayCaster::Vol img;
+  img.data = vol;
+  for (int i = 0; i < 3; ++i)
+    img.size[i] = (std::size_t)dims[i];
+  xreg::RayCaster::CameraModelList cam_list;
+  for (uint32_t c = 0; c < n_cams; ++c)
+    cam_list.push_back(cam_from(cams[c]));
+  xreg::FrameTransformList xforms;
+  xreg::RayCaster::CamModelAssocList assoc;
+  for (uint32_t p = 0; p < n_projs; ++p)
+  {
+    xforms.push_back(affine_from12(poses + 12 * (std::size_t)p));
+    assoc.push_back(cam_idx ? cam_idx[p] : 0);
+  }
+  xreg::Pt3 bb_min, bb_max;  // ITKImageIndexBoundsAsEigen: [0, size - 1]
+  for (int i = 0; i < 3; ++i)
+  {
+    bb_min(i) = 0;
+    bb_max(i) = static_cast<float>(dims[i] - 1);
+  }
+  const LineIntParams params = {0, &img, bb_min, bb_max, affine_from12(phys_to_idx), n_projs, cam_list, xforms, assoc,
+                                step_size, xreg::RayCaster::kRAY_CAST_INTERP_LINEAR};
+  const xreg::RangeType full_range(0, (std::size_t)n_projs * cam_list[0].num_det_rows * cam_list[0].num_det_cols);
+  if (kernel_id == 0)
+    ComputeLineInts<AccumLineIntKernel>(params, proj_buf, full_range);
+  else
+    ComputeLineInts<MaxLineIntKernel>(params, proj_buf, full_range);
+  return 0;
+}
+'''
+
+
+def build(verbose=False):
+    if not os.path.isdir(REF):
+        return None
+    os.makedirs(OUT_DIR, exist_ok=True)
+    gen = os.path.join(OUT_DIR, "ref_slice_gen.cpp")
+    parts = ['// GENERATED by oracle/ref_pin/build_ref_slice.py -- not tracked; the slices below are the reference\'s own lines',
+             '#include "ref_pin_prelude.h"', ""]
+    for rel, s, e, body in slices():
+        parts.append("// ---- %s:%d-%d " % (rel, s + 1, e + 1) + "-" * 40)
+        parts.extend(body)
+        parts.append("")
+    parts.append(WRAPPER)
+    with open(gen, "w") as f:
+        f.write("\n".join(parts))
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [cxx, "-std=c++11", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I", HERE, gen, "-o", LIB]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if not os.environ.get("XREG_KEEP_REF_SLICE_SOURCE"):
+        os.remove(gen)   # the generated unit holds reference source lines: only the binary stays (and only untracked)
+    if r.returncode != 0:
+        raise RuntimeError("reference slice failed to compile:\n" + r.stderr[-4000:])
+    if verbose:
+        for rel, s, e, _ in slices():
+            print("%s:%d-%d" % (rel, s + 1, e + 1))
+        print(LIB)
+    return LIB
+
+
+if __name__ == "__main__":
+    if build(verbose=True) is None:
+        print("reference checkout not found at %s: nothing built" % REF)
+        sys.exit(0)

@@ -1,0 +1,66 @@
+"""TEST INFRASTRUCTURE.  ctypes binding of oracle/_ref/libxreg_refslice.so: the reference's own RayRectIntersect,
+CameraModel::ind_pt_to_phys_det_pt and ComputeLineInts<Kernel>, compiled from /root/reference by build_ref_slice.py
+over the stand-in types of ref_pin_prelude.h.  Used only by tests/test_oracle_ref_slice.py to pin the oracle."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build_ref_slice
+from ..xreg_oracle import XoCam, _f32, _fp
+
+_lib = None
+
+
+def available() -> bool:
+    return os.path.exists(build_ref_slice.LIB) or os.path.isdir(build_ref_slice.REF)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if os.path.isdir(build_ref_slice.REF):   # rebuild where the reference exists (cheap); elsewhere use the shipped .so
+            build_ref_slice.build()
+        _lib = C.CDLL(build_ref_slice.LIB)
+        _lib.xref_ray_rect_intersect.restype = C.c_int
+        _lib.xref_compute_line_ints.restype = C.c_int
+    return _lib
+
+
+def ray_rect_intersect(mn, mx, p, d, limit_to_segment=True):
+    t0, t1 = C.c_float(0), C.c_float(0)
+    a, b, c, e = (_f32(v).reshape(3) for v in (mn, mx, p, d))
+    hit = lib().xref_ray_rect_intersect(_fp(a), _fp(b), _fp(c), _fp(e), C.c_int(1 if limit_to_segment else 0),
+                                        C.byref(t0), C.byref(t1))
+    return bool(hit), np.float32(t0.value), np.float32(t1.value)
+
+
+def ind_pt_to_phys_det_pt(cam: XoCam, col: float, row: float) -> np.ndarray:
+    out = np.zeros(3, np.float32)
+    lib().xref_ind_pt_to_phys_det_pt(C.byref(cam), C.c_float(col), C.c_float(row), _fp(out))
+    return out
+
+
+def compute_line_ints(vol, phys_to_idx, cams, poses, cam_idx=None, step_size=1.0, kernel_id=0, buf=None):
+    """ComputeLineInts<Accum|Max kernel> over the whole projection range (serial).  vol (nz, ny, nx) f32; phys_to_idx the
+    already inverted 3x4 (row-major); cams list of XoCam; poses (n, 12).  buf: initialised projection buffer or None
+    (zeros: the REPLACE store without background)."""
+    vol = _f32(vol)
+    nz, ny, nx = vol.shape
+    dims = (C.c_uint64 * 3)(nx, ny, nz)
+    poses = _f32(poses).reshape(-1, 12)
+    n = poses.shape[0]
+    cam_arr = (XoCam * len(cams))(*cams)
+    rows, cols = cams[0].rows, cams[0].cols
+    ci = np.ascontiguousarray(np.zeros(n, np.uint32) if cam_idx is None else cam_idx, dtype=np.uint32)
+    if buf is None:
+        buf = np.zeros((n, rows, cols), np.float32)
+    a = _f32(phys_to_idx).reshape(12)
+    rc = lib().xref_compute_line_ints(_fp(vol), dims, _fp(a), cam_arr, C.c_uint32(len(cams)), _fp(poses),
+                                      ci.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_uint32(n), C.c_float(step_size),
+                                      C.c_int(kernel_id), _fp(buf))
+    if rc != 0:
+        raise ValueError("xref_compute_line_ints failed")
+    return buf

@@ -1,8 +1,10 @@
 /*
  * xreg_oracle.c -- CPU restatement of the xReg DRR + similarity-metric hot path.
  *
- * TEST INFRASTRUCTURE ONLY (see xreg_oracle.h).  PARITY UNPINNED by the
- * reference's own tests (it has none for this path); pinned by tests/ instead.
+ * TEST INFRASTRUCTURE ONLY (see xreg_oracle.h).  The reference has no tests for
+ * this path.  xo_drr is pinned to the reference's own source lines compiled over
+ * stand-in types (oracle/ref_pin/, tests/test_oracle_ref_slice.py: bit for bit);
+ * the metrics are PARITY UNPINNED by the reference and pinned by tests/ instead.
  *
  * Build: gcc -O2 -ffp-contract=off -fopenmp -fPIC -shared  (no -march, no -ffast-math)
  * OpenMP stands in for tbb::parallel_for at exactly the reference's parallel

@@ -7,11 +7,21 @@
  * legs may load it.  The shipped library (libxreg_cuda.so) never links or
  * calls anything in oracle/.
  *
- * PARITY UNPINNED: the reference ships no golden vectors, known-answer tests
- * or fixtures for this path, and its own sources
- * cannot be compiled here (ITK / Eigen / OpenCV / TBB are absent).  The
- * restatement is pinned instead by analytic known answers, an independent
- * numpy float64 model and OpenCV's Python binding (tests/test_oracle_*.py).
+ * PINNING.  The reference ships no golden vectors, known-answer tests or
+ * fixtures for this path, and as a whole it cannot
+ * be compiled here (ITK / Eigen / OpenCV / TBB are absent).
+ *   DRR (xo_drr): PINNED TO THE REFERENCE'S OWN SOURCE.  oracle/ref_pin/ compiles
+ *     RayRectIntersect, CameraModel::ind_pt_to_phys_det_pt and the line-integral
+ *     kernels + ComputeLineInts<Kernel> from /root/reference where they lie, over
+ *     functional stand-ins for the Eigen / ITK / TBB types (our restatement of the
+ *     un-vendored dependencies, conventions stated in ref_pin_prelude.h), into
+ *     oracle/_ref/libxreg_refslice.so; tests/test_oracle_ref_slice.py requires
+ *     xo_drr to equal that code bit for bit on every pixel of 48 random scenes
+ *     (both kernels, all frame types, REPLACE and ACCUM).
+ *   Metrics: PARITY UNPINNED by the reference (their CPU classes are member
+ *     functions over cv::Mat / Eigen::Map state); pinned instead by analytic known
+ *     answers, an independent numpy float64 model and OpenCV's Python binding for
+ *     the Gaussian / Sobel arithmetic (tests/test_oracle_metrics.py).
  *
  * Every function cites the reference file:line it follows (paths relative to
  * the reference checkout).  Arithmetic is single precision wherever the

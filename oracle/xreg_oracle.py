@@ -2,8 +2,9 @@
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
 cpu_baseline / --impl reference legs of bench.py.  Nothing under xreg_b200/
-imports this module.  PARITY UNPINNED by the reference's own tests (it has
-none for this path); see xreg_oracle.h.
+imports this module.  The DRR restatement is pinned to the reference's own source
+lines (oracle/ref_pin/, tests/test_oracle_ref_slice.py); the metrics are PARITY
+UNPINNED by the reference (it has no tests for this path); see xreg_oracle.h.
 """
 from __future__ import annotations
 

@@ -1,0 +1,99 @@
+"""Pins the oracle to the reference's OWN code for the geometric core of the DRR path.
+
+oracle/ref_pin/build_ref_slice.py compiles, from /root/reference where it lies, the reference's RayRectIntersect
+(lib/spatial/xregSpatialPrimitives.cpp:175-222), CameraModel::ind_pt_to_phys_det_pt
+(lib/transforms/xregPerspectiveXform.cpp:391-414) and the line-integral kernels + ComputeLineInts<Kernel>
+(lib/ray_cast/xregRayCastLineIntCPU.cpp:40-292) over functional stand-ins for the Eigen / ITK / TBB types
+(oracle/ref_pin/ref_pin_prelude.h: the un-vendored dependencies restated with the conventions DESIGN.md lists).
+The oracle's C restatement (oracle/xreg_oracle.c: xo_drr) must agree with that code BIT FOR BIT: every pixel of every
+projection, both kernels, all camera frame types, oblique volumes, tiny volumes, cameras inside / missing the volume,
+step sizes, REPLACE and ACCUM stores.  A transcription error in the restatement (operation order, a cast, a comparison,
+the nudge, the step count, the loop bounds) shows up here.
+
+Runs where the reference checkout exists (it rebuilds the slice) or where the built oracle/_ref/libxreg_refslice.so
+was shipped with the snapshot; skipped otherwise."""
+import numpy as np
+import pytest
+
+from oracle.ref_pin import ref_slice
+from xreg_b200 import synth
+from xreg_b200.geometry import CameraModel, to12
+
+from .test_gpu_fuzz import _scene
+
+pytestmark = pytest.mark.skipif(not ref_slice.available(), reason="neither the reference checkout nor a built oracle/_ref slice")
+f32 = np.float32
+
+
+def test_ray_rect_intersect_is_the_reference_code(xo):
+    """The slab test alone: random segments against random boxes, axis-parallel and grazing cases included, compared
+    through one-pixel DRR set-ups is indirect -- here the reference function is called directly and the oracle's
+    restatement is exercised through xo.drr's clip mask below; this test fixes the function's known answers."""
+    hit, t0, t1 = ref_slice.ray_rect_intersect([0, 0, 0], [9, 9, 9], [-5, 4, 4], [20, 0, 0])
+    assert hit and t0 == f32(0.25) and t1 == f32(0.7)
+    hit, _, _ = ref_slice.ray_rect_intersect([0, 0, 0], [9, 9, 9], [-5, 10, 4], [20, 0, 0])       # parallel, outside a slab
+    assert not hit
+    hit, t0, t1 = ref_slice.ray_rect_intersect([0, 0, 0], [9, 9, 9], [4, 4, 4], [1, 1, 1])        # starts inside
+    assert hit and t0 == 0 and t1 == 1
+    hit, _, _ = ref_slice.ray_rect_intersect([0, 0, 0], [9, 9, 9], [-5, 4, 4], [2, 0, 0])         # segment ends before the box
+    assert not hit
+    hit, t0, t1 = ref_slice.ray_rect_intersect([0, 0, 0], [9, 9, 9], [-5, 4, 4], [2, 0, 0], limit_to_segment=False)
+    assert hit and t0 == f32(2.5) and t1 == f32(7.0)
+
+
+@pytest.mark.parametrize("frame", [0, 1, 2])
+def test_detector_points_are_the_reference_code(xo, frame):
+    """ind_pt_to_phys_det_pt of the reference == the detector points the oracle's DRR uses: checked through a camera with
+    non-trivial extrinsics for every frame type (the oracle's camera set-up fills intrins_inv / extrins_inv / pinhole)."""
+    rng = np.random.default_rng(frame)
+    E = np.eye(4)
+    E[:3, :3] = np.linalg.qr(rng.standard_normal((3, 3)))[0]
+    E[:3, 3] = rng.uniform(-40, 40, 3)
+    K = np.array([[-1200.0, 0.3, 35.5], [0, -1180.0, 28.25], [0, 0, 1]])
+    cam = xo.cam_setup(K, E, 64, 72, 0.8, 0.9, frame_type=frame)
+    # the reference maps (col, row) -> camera-world point; linear in (col, row) up to f32 rounding: spot values + consistency
+    p00 = ref_slice.ind_pt_to_phys_det_pt(cam, 0, 0)
+    p10 = ref_slice.ind_pt_to_phys_det_pt(cam, 1, 0)
+    p01 = ref_slice.ind_pt_to_phys_det_pt(cam, 0, 1)
+    p = ref_slice.ind_pt_to_phys_det_pt(cam, 37, 21)
+    assert np.allclose(p, p00 + 37 * (p10 - p00) + 21 * (p01 - p00), rtol=0, atol=2e-3)
+    # a one-voxel-thick slab orthogonal to nothing in particular: the DRR comparison below is the bitwise statement
+
+
+def _both(xo, vol, cam, poses, step, kernel_id, cam_idx=None, buf=None):
+    xcams = cam if isinstance(cam, list) else [xo.cam_struct(cam)]
+    p12 = to12(poses)
+    a = xo.drr(vol.data, vol.idx_to_phys(), xcams, p12, cam_idx=cam_idx, step_size=step, kernel_id=kernel_id,
+               buf=None if buf is None else buf.copy(), n_threads=1)
+    b = ref_slice.compute_line_ints(vol.data, xo.affine_inverse(vol.idx_to_phys()), xcams, p12, cam_idx=cam_idx,
+                                    step_size=step, kernel_id=kernel_id, buf=None if buf is None else buf.copy())
+    return a, b
+
+
+@pytest.mark.parametrize("seed", range(48))
+def test_oracle_drr_equals_the_reference_code_on_random_scenes(xo, seed):
+    """The 48 scenes of the GPU fuzz test (tests/test_gpu_fuzz.py::_scene)."""
+    vol, cam, poses, step, kernel_id, kind = _scene(seed)
+    a, b = _both(xo, vol, cam, poses, step, kernel_id)
+    assert a.tobytes() == b.tobytes()
+    # ACCUM on top of a previous projection (the store `buf = K(buf, val)`)
+    prev = (np.abs(a) * f32(0.5) + f32(0.125)).astype(f32)
+    a2, b2 = _both(xo, vol, cam, poses, step, kernel_id, buf=prev)
+    assert a2.tobytes() == b2.tobytes()
+
+
+def test_oracle_drr_equals_the_reference_code_on_the_test_scene(xo, small_scene):
+    """The 64x64x48 anisotropic phantom of the GPU parity tests, two cameras, camera-major association."""
+    vol, cam, nominal = small_scene
+    cam2 = CameraModel().setup(380.0, cam.num_det_rows, cam.num_det_cols, 1.7, 1.4)
+    pop = synth.pose_population(vol, nominal, 3)
+    xcams = [xo.cam_struct(cam), xo.cam_struct(cam2)]
+    poses = np.concatenate([pop, pop])
+    cam_idx = np.array([0, 0, 0, 1, 1, 1], np.uint32)
+    for step in (1.0, 0.37):
+        a, b = _both(xo, vol, xcams, poses, step, 0, cam_idx=cam_idx)
+        assert a.max() > 0 and a.tobytes() == b.tobytes()
+    # the comparison is not vacuous: one ulp on the step size changes the bytes
+    c = ref_slice.compute_line_ints(vol.data, xo.affine_inverse(vol.idx_to_phys()), xcams, to12(poses), cam_idx=cam_idx,
+                                    step_size=float(np.nextafter(f32(0.37), f32(1.0))))
+    assert c.tobytes() != b.tobytes()
