@@ -173,31 +173,151 @@ extern "C" int xref_compute_line_ints(const float* vol, const uint64_t dims[3], 
 '''
 
 
+METRIC_WRAPPER = r'''
+// ---- C ABI over the reference's patch-NCC class (ours) --------------------------------------------------------------
+struct xref_patch_opts   // layout of oracle/xreg_oracle.h: xo_patch_opts
+{
+  uint32_t radius, stride;
+  int32_t compute_mean_of_patch_sims, weight_patch_sims, use_mask_for_weighting, use_mask_for_patch_stats,
+      normalize_weights_as_prob;
+};
+
+extern "C" void xref_patch_mean_std(const float* img, const uint8_t* mask, uint32_t rows, uint32_t cols, uint32_t r0,
+                                    uint32_t c0, uint32_t d, int use_mask_for_stats, float* mean, float* sd, uint64_t* n)
+{
+  cv::Mat im(rows, cols, cv::DataType<float>::type, const_cast<float*>(img));
+  cv::Mat mk(rows, cols, cv::DataType<unsigned char>::type, const_cast<uint8_t*>(mask));
+  cv::Rect roi;
+  roi.x = (int)c0;
+  roi.y = (int)r0;
+  roi.width = roi.height = (int)d;
+  const cv::Mat p = im(roi), m = mk(roi);
+  xreg::size_type cnt = 0;
+  std::tie(*mean, *sd, cnt) = xreg::detail::ComputePatchMeanStdDev(p, mask ? &m : nullptr, use_mask_for_stats != 0);
+  *n = cnt;
+}
+
+// set_fixed_image / set_mask / set_mov_imgs_host_buf / patch parameters, allocate_resources(), compute(), sim_vals()
+extern "C" int xref_patch_ncc(const float* fixed, const uint8_t* mask, uint32_t rows, uint32_t cols,
+                              const xref_patch_opts* o, const float* wgt_img, const float* mov, uint32_t n_imgs,
+                              float* sims_out, float* weights_out, float* patch_sims_out)
+{
+  using Sim = xreg::ImgSimMetric2DPatchNCCCPU;
+  Sim sm;
+  sm.fixed_img_.p = std::make_shared<Sim::Image>();
+  sm.fixed_img_.p->buf = const_cast<float*>(fixed);
+  sm.fixed_img_.p->sz.s[0] = cols;
+  sm.fixed_img_.p->sz.s[1] = rows;
+  if (mask)
+  {
+    sm.mask_.p = std::make_shared<Sim::ImageMask>();
+    sm.mask_.p->buf = const_cast<uint8_t*>(mask);
+    sm.mask_.p->sz.s[0] = cols;
+    sm.mask_.p->sz.s[1] = rows;
+  }
+  if (wgt_img)
+  {
+    Sim::WgtImgPtr w;
+    w.p = std::make_shared<Sim::WgtImg>();
+    w.p->buf = const_cast<float*>(wgt_img);
+    w.p->sz.s[0] = cols;
+    w.p->sz.s[1] = rows;
+    sm.set_wgt_img(w);
+  }
+  std::vector<float> mov_copy(mov, mov + (std::size_t)n_imgs * rows * cols);   // the metric may modify its buffer
+  sm.num_mov_imgs_ = n_imgs;
+  sm.mov_imgs_buf_ = mov_copy.data();
+  sm.patch_radius_ = o->radius;
+  sm.patch_stride_ = o->stride;
+  sm.compute_mean_of_patch_sims_ = o->compute_mean_of_patch_sims != 0;
+  sm.weight_patch_sims_in_combine_ = o->weight_patch_sims != 0;
+  sm.use_mask_for_weighting_ = o->use_mask_for_weighting != 0;
+  sm.use_mask_for_patch_stats_ = o->use_mask_for_patch_stats != 0;
+  sm.normalize_weights_as_prob_ = o->normalize_weights_as_prob != 0;
+  sm.save_all_per_patch_scores_ = patch_sims_out != nullptr;
+  sm.allocate_resources();
+  sm.compute();
+  for (uint32_t i = 0; i < n_imgs; ++i)
+    sims_out[i] = sm.sim_vals_[i];
+  const std::size_t np = sm.patch_infos_.size();
+  if (weights_out)
+    for (std::size_t k = 0; k < np; ++k)
+      weights_out[k] = sm.patch_infos_[k].weight;
+  if (patch_sims_out)
+    for (uint32_t i = 0; i < n_imgs; ++i)
+      for (std::size_t k = 0; k < np; ++k)
+        patch_sims_out[(std::size_t)i * np + k] = sm.sim_vals_for_each_patch_[k][i];
+  return (int)np;
+}
+'''
+
+
+def _with_prev(lines, regex, n_prev, n_closing=1):
+    s, e = _cut_function(lines, regex, n_closing)
+    return s - n_prev, e
+
+
+def metric_slices():
+    out = []
+    rel = "lib/regi/sim_metrics_2d/xregImgSimMetric2DPatchCommon.cpp"
+    ln = _lines(rel)
+    for regex, n_prev in ((r"^xreg::ImgSimMetric2DPatchCommon::PatchInfo::center_row_col\(\) const", 1),
+                          (r"^xreg::ImgSimMetric2DPatchCommon::PatchInfo::ocv_roi\(\) const", 1),
+                          (r"^xreg::size_type xreg::ImgSimMetric2DPatchCommon::num_patches\(\) const", 0),
+                          (r"^void xreg::ImgSimMetric2DPatchCommon::setup_patches\(", 0),
+                          (r"^bool xreg::ImgSimMetric2DPatchCommon::compute_weights\(", 0),
+                          (r"^xreg::ImgSimMetric2DPatchCommon::patch_indices_to_use\(\)", 1)):
+        s, e = _with_prev(ln, regex, n_prev)
+        out.append((rel, s, e, ln[s:e + 1]))
+    rel = "lib/regi/sim_metrics_2d/xregImgSimMetric2DPatchNCCCPU.cpp"
+    ln = _lines(rel)
+    for regex, n_prev in ((r"^void xreg::ImgSimMetric2DPatchNCCCPU::allocate_resources\(\)", 0),
+                          (r"^void xreg::ImgSimMetric2DPatchNCCCPU::compute\(\)", 0),
+                          (r"^void xreg::ImgSimMetric2DPatchNCCCPU::process_mask\(\)", 0),
+                          (r"^xreg::detail::ComputePatchMeanStdDev\(", 3)):
+        s, e = _with_prev(ln, regex, n_prev)
+        out.append((rel, s, e, ln[s:e + 1]))
+    assert out[-1][3][0].startswith("std::tuple<"), out[-1][3][0]
+    return out
+
+
+UNITS = (
+    # (library, prelude header, slice list function, C ABI wrapper)
+    ("libxreg_refslice.so", "ref_pin_prelude.h", slices, WRAPPER),
+    ("libxreg_refslice_metric.so", "ref_pin_metric_prelude.h", metric_slices, METRIC_WRAPPER),
+)
+METRIC_LIB = os.path.join(OUT_DIR, "libxreg_refslice_metric.so")
+
+
 def build(verbose=False):
+    """Compile every unit; returns the DRR library path, or None without a reference checkout."""
     if not os.path.isdir(REF):
         return None
     os.makedirs(OUT_DIR, exist_ok=True)
-    gen = os.path.join(OUT_DIR, "ref_slice_gen.cpp")
-    parts = ['// GENERATED by oracle/ref_pin/build_ref_slice.py -- not tracked; the slices below are the reference\'s own lines',
-             '#include "ref_pin_prelude.h"', ""]
-    for rel, s, e, body in slices():
-        parts.append("// ---- %s:%d-%d " % (rel, s + 1, e + 1) + "-" * 40)
-        parts.extend(body)
-        parts.append("")
-    parts.append(WRAPPER)
-    with open(gen, "w") as f:
-        f.write("\n".join(parts))
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    cmd = [cxx, "-std=c++11", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I", HERE, gen, "-o", LIB]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if not os.environ.get("XREG_KEEP_REF_SLICE_SOURCE"):
-        os.remove(gen)   # the generated unit holds reference source lines: only the binary stays (and only untracked)
-    if r.returncode != 0:
-        raise RuntimeError("reference slice failed to compile:\n" + r.stderr[-4000:])
-    if verbose:
-        for rel, s, e, _ in slices():
-            print("%s:%d-%d" % (rel, s + 1, e + 1))
-        print(LIB)
+    for lib_name, prelude, slice_fn, wrapper in UNITS:
+        gen = os.path.join(OUT_DIR, lib_name.replace(".so", "_gen.cpp"))
+        parts = ["// GENERATED by oracle/ref_pin/build_ref_slice.py -- not tracked; the slices below are the reference's own lines",
+                 '#include "%s"' % prelude, ""]
+        cut = slice_fn()
+        for rel, s, e, body in cut:
+            parts.append("// ---- %s:%d-%d " % (rel, s + 1, e + 1) + "-" * 40)
+            parts.extend(body)
+            parts.append("")
+        parts.append(wrapper)
+        with open(gen, "w") as f:
+            f.write("\n".join(parts))
+        cmd = [cxx, "-std=c++11", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I", HERE, gen, "-o",
+               os.path.join(OUT_DIR, lib_name)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if not os.environ.get("XREG_KEEP_REF_SLICE_SOURCE"):
+            os.remove(gen)   # the generated unit holds reference source lines: only the binary stays (and only untracked)
+        if r.returncode != 0:
+            raise RuntimeError("reference slice %s failed to compile:\n%s" % (lib_name, r.stderr[-6000:]))
+        if verbose:
+            for rel, s, e, _ in cut:
+                print("%s:%d-%d" % (rel, s + 1, e + 1))
+            print(os.path.join(OUT_DIR, lib_name))
     return LIB
 
 

@@ -64,3 +64,50 @@ def compute_line_ints(vol, phys_to_idx, cams, poses, cam_idx=None, step_size=1.0
     if rc != 0:
         raise ValueError("xref_compute_line_ints failed")
     return buf
+
+
+# ---- the reference's patch-NCC class (oracle/_ref/libxreg_refslice_metric.so) ----------------------------------------
+_mlib = None
+
+
+def metric_lib():
+    global _mlib
+    if _mlib is None:
+        lib()   # (re)builds both units where the reference exists
+        _mlib = C.CDLL(build_ref_slice.METRIC_LIB)
+        _mlib.xref_patch_ncc.restype = C.c_int
+    return _mlib
+
+
+def patch_mean_std(img, mask, r0, c0, d, use_mask_for_stats):
+    """detail::ComputePatchMeanStdDev on the d x d patch at (r0, c0): (mean, clamped std dev, pixels counted)."""
+    img = _f32(img)
+    rows, cols = img.shape
+    m = np.ascontiguousarray(mask, dtype=np.uint8) if mask is not None else None
+    mean, sd, n = C.c_float(0), C.c_float(0), C.c_uint64(0)
+    metric_lib().xref_patch_mean_std(_fp(img), m.ctypes.data_as(C.POINTER(C.c_uint8)) if m is not None else None,
+                                     C.c_uint32(rows), C.c_uint32(cols), C.c_uint32(r0), C.c_uint32(c0), C.c_uint32(d),
+                                     C.c_int(1 if use_mask_for_stats else 0), C.byref(mean), C.byref(sd), C.byref(n))
+    return np.float32(mean.value), np.float32(sd.value), int(n.value)
+
+
+def patch_ncc(fixed, mov, opts, mask=None, wgt_img=None, want_patch_sims=False):
+    """ImgSimMetric2DPatchNCCCPU: set_fixed_image / set_mask / set_wgt_img / patch parameters, allocate_resources(),
+    compute().  Returns (sims, patch weights[, per-patch values (n, num_patches)])."""
+    from ..xreg_oracle import num_patches
+
+    fixed = _f32(fixed)
+    rows, cols = fixed.shape
+    mov = _f32(mov).reshape(-1, rows, cols)
+    n = mov.shape[0]
+    np_ = num_patches(rows, cols, opts.radius, opts.stride)
+    sims = np.zeros(n, np.float32)
+    w = np.zeros(np_, np.float32)
+    ps = np.zeros((n, np_), np.float32) if want_patch_sims else None
+    m = np.ascontiguousarray(mask, dtype=np.uint8) if mask is not None else None
+    wi = _f32(wgt_img) if wgt_img is not None else None
+    got = metric_lib().xref_patch_ncc(_fp(fixed), m.ctypes.data_as(C.POINTER(C.c_uint8)) if m is not None else None,
+                                      C.c_uint32(rows), C.c_uint32(cols), C.byref(opts), _fp(wi) if wi is not None else None,
+                                      _fp(mov), C.c_uint32(n), _fp(sims), _fp(w), _fp(ps) if ps is not None else None)
+    assert got == np_, "patch grid size differs: reference %d, oracle %d" % (got, np_)
+    return (sims, w, ps) if want_patch_sims else (sims, w)

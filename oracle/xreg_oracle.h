@@ -18,10 +18,20 @@
  *     oracle/_ref/libxreg_refslice.so; tests/test_oracle_ref_slice.py requires
  *     xo_drr to equal that code bit for bit on every pixel of 48 random scenes
  *     (both kernels, all frame types, REPLACE and ACCUM).
- *   Metrics: PARITY UNPINNED by the reference (their CPU classes are member
- *     functions over cv::Mat / Eigen::Map state); pinned instead by analytic known
- *     answers, an independent numpy float64 model and OpenCV's Python binding for
- *     the Gaussian / Sobel arithmetic (tests/test_oracle_metrics.py).
+ *   Patch NCC (xo_patch_weights, xo_patch_ncc; the core of patch gradient-NCC,
+ *     which the reference composes from two patch-NCC objects on the gradient
+ *     images): PINNED TO THE REFERENCE'S OWN SOURCE the same way --
+ *     ImgSimMetric2DPatchCommon::{setup_patches, compute_weights,
+ *     patch_indices_to_use}, ImgSimMetric2DPatchNCCCPU::{allocate_resources,
+ *     compute, process_mask} and detail::ComputePatchMeanStdDev compiled over
+ *     cv::Mat / itk::Image stand-ins that carry no arithmetic
+ *     (oracle/_ref/libxreg_refslice_metric.so); patch grid, weights, per-patch
+ *     values and image scores agree bit for bit on 40 random cases x every option
+ *     combination (tests/test_oracle_ref_slice.py).
+ *   NCC, SSD, Gaussian / Sobel gradient images: PARITY UNPINNED by the reference
+ *     (their arithmetic is inside Eigen's vectorised reductions and OpenCV);
+ *     pinned instead by analytic known answers, an independent numpy float64
+ *     model and OpenCV's Python binding (tests/test_oracle_metrics.py).
  *
  * Every function cites the reference file:line it follows (paths relative to
  * the reference checkout).  Arithmetic is single precision wherever the

@@ -97,3 +97,70 @@ def test_oracle_drr_equals_the_reference_code_on_the_test_scene(xo, small_scene)
     c = ref_slice.compute_line_ints(vol.data, xo.affine_inverse(vol.idx_to_phys()), xcams, to12(poses), cam_idx=cam_idx,
                                     step_size=float(np.nextafter(f32(0.37), f32(1.0))))
     assert c.tobytes() != b.tobytes()
+
+
+# ---- the patch-NCC metric: the reference's own class code ----------------------------------------------------------------
+def _metric_case(seed):
+    rng = np.random.default_rng(9000 + seed)
+    rows, cols = int(rng.integers(7, 70)), int(rng.integers(7, 90))
+    n = int(rng.integers(1, 5))
+    base = rng.standard_normal((rows, cols))
+    for ax in (0, 1):
+        base = (base + np.roll(base, 1, ax) + np.roll(base, -1, ax)) / 3.0
+    fixed = (base * 4 + 6).astype(f32)
+    mov = np.stack([(rng.uniform(0.2, 1.0) * fixed + rng.uniform(0.0, 1.0) * rng.standard_normal((rows, cols)) * 2).astype(f32)
+                    for _ in range(n)])
+    if n >= 2:
+        mov[-1] = 3.25          # constant image: every patch takes the sigma clamp
+    if n >= 3:
+        mov[-2] = fixed
+    mask = None
+    if seed % 2 == 1:
+        mask = (rng.random((rows, cols)) < rng.uniform(0.3, 0.95)).astype(np.uint8)
+        mask[rows // 2, cols // 2] = 1
+    rmax = max(1, min(rows, cols) // 2 - 1)
+    radius = int(rng.integers(1, max(min(rmax, 12), 1) + 1))
+    stride = int(rng.integers(1, 4))
+    wgt_img = rng.uniform(0.0, 2.0, (rows, cols)).astype(f32) if seed % 5 == 3 else None
+    return fixed, mov, mask, radius, stride, wgt_img
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_oracle_patch_ncc_equals_the_reference_class_code(xo, seed):
+    """ImgSimMetric2DPatchNCCCPU::{allocate_resources, compute, process_mask}, ImgSimMetric2DPatchCommon::{setup_patches,
+    compute_weights, patch_indices_to_use} and detail::ComputePatchMeanStdDev, compiled from the reference's own lines
+    (xregImgSimMetric2DPatchNCCCPU.cpp:34-72,74-300,332-441,558-619; xregImgSimMetric2DPatchCommon.cpp:35-54,180-184,
+    256-493) over cv::Mat / itk::Image stand-ins that carry no arithmetic: patch grid, patch weights, per-patch values
+    and image scores of the oracle are the reference's, bit for bit, for every option combination the CUDA path accepts."""
+    fixed, mov, mask, radius, stride, wgt_img = _metric_case(seed)
+    rows, cols = fixed.shape
+    combos = [dict(), dict(compute_mean=True), dict(weight_sims=False), dict(normalize=False)]
+    if mask is not None:
+        combos += [dict(mask_stats=True), dict(mask_weighting=False), dict(mask_stats=True, mask_weighting=False, normalize=False)]
+    for kw in combos:
+        opts = xo.patch_opts(radius=radius, stride=stride, **kw)
+        w_or = xo.patch_weights(rows, cols, opts, mask=mask, wgt_img=wgt_img)
+        need_w = (mask is not None and opts.use_mask_for_weighting) or wgt_img is not None
+        s_or, p_or = xo.patch_ncc(fixed, mov, opts, mask=mask, weights=w_or if need_w else None, want_patch_sims=True, n_threads=1)
+        s_rf, w_rf, p_rf = ref_slice.patch_ncc(fixed, mov, opts, mask=mask, wgt_img=wgt_img, want_patch_sims=True)
+        assert w_or.tobytes() == w_rf.tobytes(), kw
+        assert s_or.tobytes() == s_rf.tobytes(), (kw, s_or, s_rf)
+        if opts.weight_patch_sims:
+            live = np.abs(w_rf) > 1.0e-6      # patches the reference skips keep whatever the vector held
+            assert np.array_equal(p_or[:, live], p_rf[:, live]), kw
+        else:
+            assert p_or.tobytes() == p_rf.tobytes(), kw
+
+
+def test_patch_mean_std_is_the_reference_code(xo):
+    rng = np.random.default_rng(4)
+    img = rng.standard_normal((20, 24)).astype(f32) * 3 + 1
+    mask = (rng.random((20, 24)) < 0.6).astype(np.uint8)
+    mean, sd, n = ref_slice.patch_mean_std(img, None, 3, 5, 7, False)
+    p = img[3:10, 5:12].astype(np.float64)
+    assert n == 49 and abs(mean - p.mean()) < 1e-5 and abs(sd - p.std(ddof=1)) < 1e-5
+    mean, sd, n = ref_slice.patch_mean_std(img, mask, 3, 5, 7, True)
+    sel = mask[3:10, 5:12] > 0
+    assert n == int(sel.sum()) and abs(mean - p[sel].mean()) < 1e-5 and abs(sd - p[sel].std(ddof=1)) < 1e-5
+    mean, sd, n = ref_slice.patch_mean_std(np.full((9, 9), 2.5, f32), None, 0, 0, 9, False)
+    assert mean == f32(2.5) and sd == f32(1.0e-6) and n == 81          # the clamp
