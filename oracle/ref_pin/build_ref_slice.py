@@ -281,11 +281,37 @@ def metric_slices():
     return out
 
 
+HU_WRAPPER = r'''
+// HUToLinAtt(hu_vol, hu_lower): SetInput, SetHULower, Update (= GenerateData), GetOutput
+extern "C" void xref_hu_to_lin_att(const float* hu, float* att, uint64_t n, float hu_lower)
+{
+  xreg::HUToLinAttFilter::Vol in;
+  in.in = hu;
+  in.n = (std::size_t)n;
+  xreg::HUToLinAttFilter f;
+  f.input = &in;
+  f.hu_lower_ = hu_lower;   // SetHULower(const double hul)
+  f.GenerateData();
+  for (uint64_t i = 0; i < n; ++i)
+    att[i] = f.output.out[i];
+}
+'''
+
+
+def hu_slices():
+    rel = "lib/image/xregHUToLinAtt.cpp"
+    ln = _lines(rel)
+    s, e = _cut_function(ln, r"^void xreg::HUToLinAttFilter::GenerateData\(\)")
+    return [(rel, s, e, ln[s:e + 1])]
+
+
 UNITS = (
     # (library, prelude header, slice list function, C ABI wrapper)
     ("libxreg_refslice.so", "ref_pin_prelude.h", slices, WRAPPER),
     ("libxreg_refslice_metric.so", "ref_pin_metric_prelude.h", metric_slices, METRIC_WRAPPER),
+    ("libxreg_refslice_hu.so", "ref_pin_hu_prelude.h", hu_slices, HU_WRAPPER),
 )
+HU_LIB = os.path.join(OUT_DIR, "libxreg_refslice_hu.so")
 METRIC_LIB = os.path.join(OUT_DIR, "libxreg_refslice_metric.so")
 
 

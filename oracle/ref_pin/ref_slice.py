@@ -111,3 +111,13 @@ def patch_ncc(fixed, mov, opts, mask=None, wgt_img=None, want_patch_sims=False):
                                       _fp(mov), C.c_uint32(n), _fp(sims), _fp(w), _fp(ps) if ps is not None else None)
     assert got == np_, "patch grid size differs: reference %d, oracle %d" % (got, np_)
     return (sims, w, ps) if want_patch_sims else (sims, w)
+
+
+def hu_to_lin_att(hu, hu_lower=-1000.0):
+    """HUToLinAtt(hu_vol, hu_lower) through the reference's HUToLinAttFilter::GenerateData."""
+    lib()
+    hl = C.CDLL(build_ref_slice.HU_LIB)
+    hu = _f32(hu)
+    out = np.zeros_like(hu)
+    hl.xref_hu_to_lin_att(_fp(hu), _fp(out), C.c_uint64(hu.size), C.c_float(hu_lower))
+    return out

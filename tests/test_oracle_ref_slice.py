@@ -164,3 +164,13 @@ def test_patch_mean_std_is_the_reference_code(xo):
     assert n == int(sel.sum()) and abs(mean - p[sel].mean()) < 1e-5 and abs(sd - p[sel].std(ddof=1)) < 1e-5
     mean, sd, n = ref_slice.patch_mean_std(np.full((9, 9), 2.5, f32), None, 0, 0, 9, False)
     assert mean == f32(2.5) and sd == f32(1.0e-6) and n == 81          # the clamp
+
+
+def test_oracle_hu_to_lin_att_equals_the_reference_filter_code(xo):
+    """HUToLinAttFilter::GenerateData (lib/image/xregHUToLinAtt.cpp:45-69) over flat-image / iterator stand-ins."""
+    rng = np.random.default_rng(11)
+    hu = np.concatenate([rng.uniform(-1200, 3000, 50000), [-1000.0, -999.99994, -1000.0001, 0.0, 1e-30, -3e4, 6e4]]).astype(f32)
+    for lower in (-1000.0, -800.0, 150.0):
+        a = xo.hu_to_lin_att(hu, lower)
+        b = ref_slice.hu_to_lin_att(hu, lower)
+        assert a.tobytes() == b.tobytes() and a.max() > 0 and (a == 0).any()
