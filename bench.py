@@ -333,7 +333,7 @@ def main():
         peak, peak_src = measured_peak_hbm()
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
+        if os.path.exists(tpath) and args.workload == "c2" and args.layout == "default":   # the capture is of the C2 launch
             try:
                 traffic = json.load(open(tpath)).get("drr_dram_bytes_per_launch")
             except Exception:
