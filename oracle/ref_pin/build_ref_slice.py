@@ -305,12 +305,58 @@ def hu_slices():
     return [(rel, s, e, ln[s:e + 1])]
 
 
+NCC_WRAPPER = r'''
+// set_fixed_image / set_mask / set_mov_imgs_host_buf, allocate_resources(), compute(), sim_vals()
+extern "C" void xref_ncc(const float* fixed, const uint8_t* mask, uint32_t rows, uint32_t cols, const float* mov,
+                         uint32_t n_imgs, float* sims_out)
+{
+  using Sim = xreg::ImgSimMetric2DNCCCPU;
+  Sim sm;
+  sm.fixed_img_.p = std::make_shared<Sim::Image>();
+  sm.fixed_img_.p->buf = const_cast<float*>(fixed);
+  sm.fixed_img_.p->sz.s[0] = cols;
+  sm.fixed_img_.p->sz.s[1] = rows;
+  if (mask)
+  {
+    sm.mask_.p = std::make_shared<Sim::ImageMask>();
+    sm.mask_.p->buf = const_cast<uint8_t*>(mask);
+    sm.mask_.p->sz.s[0] = cols;
+    sm.mask_.p->sz.s[1] = rows;
+  }
+  std::vector<float> mov_copy(mov, mov + (std::size_t)n_imgs * rows * cols);   // NCC zero-means its buffer in place
+  sm.num_mov_imgs_ = n_imgs;
+  sm.mov_imgs_buf_ = mov_copy.data();
+  sm.allocate_resources();
+  sm.compute();
+  for (uint32_t i = 0; i < n_imgs; ++i)
+    sims_out[i] = sm.sim_vals_[i];
+}
+'''
+
+
+def ncc_slices():
+    rel = "lib/regi/sim_metrics_2d/xregImgSimMetric2DNCCCPU.cpp"
+    ln = _lines(rel)
+    out = []
+    k = next(i for i, x in enumerate(ln) if "ComputeLenFromMask(" in x)
+    s = max(i for i in range(k) if ln[i].startswith("namespace"))
+    e = next(i for i in range(k, len(ln)) if re.match(r"^\}\s*//\s*un-named", ln[i]))
+    out.append((rel, s, e, ln[s:e + 1]))
+    for regex in (r"^void xreg::ImgSimMetric2DNCCCPU::allocate_resources\(\)", r"^void xreg::ImgSimMetric2DNCCCPU::compute\(\)",
+                  r"^void xreg::ImgSimMetric2DNCCCPU::process_mask\(\)"):
+        s, e = _cut_function(ln, regex)
+        out.append((rel, s, e, ln[s:e + 1]))
+    return out
+
+
 UNITS = (
     # (library, prelude header, slice list function, C ABI wrapper)
     ("libxreg_refslice.so", "ref_pin_prelude.h", slices, WRAPPER),
     ("libxreg_refslice_metric.so", "ref_pin_metric_prelude.h", metric_slices, METRIC_WRAPPER),
     ("libxreg_refslice_hu.so", "ref_pin_hu_prelude.h", hu_slices, HU_WRAPPER),
+    ("libxreg_refslice_ncc.so", "ref_pin_ncc_prelude.h", ncc_slices, NCC_WRAPPER),
 )
+NCC_LIB = os.path.join(OUT_DIR, "libxreg_refslice_ncc.so")
 HU_LIB = os.path.join(OUT_DIR, "libxreg_refslice_hu.so")
 METRIC_LIB = os.path.join(OUT_DIR, "libxreg_refslice_metric.so")
 

@@ -121,3 +121,17 @@ def hu_to_lin_att(hu, hu_lower=-1000.0):
     out = np.zeros_like(hu)
     hl.xref_hu_to_lin_att(_fp(hu), _fp(out), C.c_uint64(hu.size), C.c_float(hu_lower))
     return out
+
+
+def ncc(fixed, mov, mask=None):
+    """ImgSimMetric2DNCCCPU: set_fixed_image / set_mask, allocate_resources(), compute() -> sim_vals."""
+    lib()
+    nl = C.CDLL(build_ref_slice.NCC_LIB)
+    fixed = _f32(fixed)
+    rows, cols = fixed.shape
+    mov = _f32(mov).reshape(-1, rows, cols)
+    sims = np.zeros(mov.shape[0], np.float32)
+    m = np.ascontiguousarray(mask, dtype=np.uint8) if mask is not None else None
+    nl.xref_ncc(_fp(fixed), m.ctypes.data_as(C.POINTER(C.c_uint8)) if m is not None else None, C.c_uint32(rows),
+                C.c_uint32(cols), _fp(mov), C.c_uint32(mov.shape[0]), _fp(sims))
+    return sims

@@ -4,7 +4,8 @@
  * TEST INFRASTRUCTURE ONLY (see xreg_oracle.h).  The reference has no tests for
  * this path.  xo_drr is pinned to the reference's own source lines compiled over
  * stand-in types (oracle/ref_pin/, tests/test_oracle_ref_slice.py: bit for bit),
- * and so are xo_patch_weights / xo_patch_ncc; NCC, SSD and the gradient images are
+ * and so are xo_patch_weights / xo_patch_ncc, xo_ncc (unmasked: up to the Eigen
+ * reduction convention) and xo_hu_to_lin_att; SSD and the gradient images are
  * PARITY UNPINNED by the reference and pinned by tests/ instead.
  *
  * Build: gcc -O2 -ffp-contract=off -fopenmp -fPIC -shared  (no -march, no -ffast-math)

@@ -28,10 +28,17 @@
  *     (oracle/_ref/libxreg_refslice_metric.so); patch grid, weights, per-patch
  *     values and image scores agree bit for bit on 40 random cases x every option
  *     combination (tests/test_oracle_ref_slice.py).
- *   NCC, SSD, Gaussian / Sobel gradient images: PARITY UNPINNED by the reference
- *     (their arithmetic is inside Eigen's vectorised reductions and OpenCV);
- *     pinned instead by analytic known answers, an independent numpy float64
- *     model and OpenCV's Python binding (tests/test_oracle_metrics.py).
+ *   NCC (xo_ncc; gradient-NCC is two of them on the gradient images): the class
+ *     code is pinned the same way (libxreg_refslice_ncc.so).  Masked: plain scalar
+ *     loops in the reference -> bit for bit, no convention.  Unmasked: three Eigen
+ *     reductions, for which stand-in and oracle follow the same documented Eigen 3.3
+ *     SSE reduction shape -> pinned up to that convention.
+ *   HU -> linear attenuation (xo_hu_to_lin_att): pinned to
+ *     HUToLinAttFilter::GenerateData (libxreg_refslice_hu.so).
+ *   SSD, Gaussian / Sobel gradient images: PARITY UNPINNED by the reference
+ *     (an Eigen reduction; OpenCV filters); pinned instead by analytic known
+ *     answers, an independent numpy float64 model and OpenCV's Python binding
+ *     (tests/test_oracle_metrics.py).
  *
  * Every function cites the reference file:line it follows (paths relative to
  * the reference checkout).  Arithmetic is single precision wherever the

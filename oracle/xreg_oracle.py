@@ -2,10 +2,10 @@
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
 cpu_baseline / --impl reference legs of bench.py.  Nothing under xreg_b200/
-imports this module.  The DRR and patch-NCC restatements are pinned to the
-reference's own source lines (oracle/ref_pin/, tests/test_oracle_ref_slice.py);
-NCC, SSD and the gradient images are PARITY UNPINNED by the reference (it has no
-tests for this path); see xreg_oracle.h.
+imports this module.  The DRR, patch-NCC, NCC and HU-conversion restatements are
+pinned to the reference's own source lines (oracle/ref_pin/,
+tests/test_oracle_ref_slice.py); SSD and the gradient images are PARITY UNPINNED by
+the reference (it has no tests for this path); see xreg_oracle.h.
 """
 from __future__ import annotations
 

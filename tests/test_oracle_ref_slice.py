@@ -174,3 +174,29 @@ def test_oracle_hu_to_lin_att_equals_the_reference_filter_code(xo):
         a = xo.hu_to_lin_att(hu, lower)
         b = ref_slice.hu_to_lin_att(hu, lower)
         assert a.tobytes() == b.tobytes() and a.max() > 0 and (a == 0).any()
+
+
+@pytest.mark.parametrize("seed", range(30))
+def test_oracle_ncc_equals_the_reference_class_code(xo, seed):
+    """ImgSimMetric2DNCCCPU::{allocate_resources, compute, process_mask} and its helper templates
+    (xregImgSimMetric2DNCCCPU.cpp:29-132,134-236), compiled from the reference's own lines.  With a mask the reference
+    computes everything in plain scalar loops: pinned without any convention.  Without a mask it calls three Eigen
+    reductions (mean, sum of squares, dot), for which the stand-in follows the documented Eigen 3.3 SSE reduction shape --
+    the same convention the oracle states: that path is pinned up to it (image sizes cover every tail length)."""
+    rng = np.random.default_rng(7000 + seed)
+    rows, cols = int(rng.integers(1, 40)), int(rng.integers(2, 60))
+    n = int(rng.integers(1, 5))
+    fixed = (rng.standard_normal((rows, cols)) * 3 + 5).astype(f32)
+    mov = np.stack([(rng.uniform(-1.0, 1.0) * fixed + rng.standard_normal((rows, cols))).astype(f32) for _ in range(n)])
+    if n >= 2:
+        mov[-1] = 1.5                      # constant image: the sigma clamp
+    if n >= 3:
+        mov[-2] = fixed                    # identical image: similarity 0
+    a = xo.ncc(fixed, mov)
+    b = ref_slice.ncc(fixed, mov)
+    assert a.tobytes() == b.tobytes(), (a, b)
+    mask = (rng.random((rows, cols)) < rng.uniform(0.3, 0.95)).astype(np.uint8)
+    mask.flat[:2] = 1                      # at least two pixels (N - 1 in the denominator)
+    am = xo.ncc(fixed, mov, mask=mask)
+    bm = ref_slice.ncc(fixed, mov, mask=mask)
+    assert am.tobytes() == bm.tobytes(), (am, bm)
