@@ -64,6 +64,13 @@ def slices():
     body = ln[s:e + 1]
     assert any("void ComputeLineInts(" in x for x in body) and any("struct LineIntParams" in x for x in body)
     out.append(("lib/ray_cast/xregRayCastLineIntCPU.cpp", s, e, body))
+    # RayCaster::distribute_xforms_among_cam_models and RayCasterCPU::pre_compute
+    ln = _lines("lib/ray_cast/xregRayCastInterface.cpp")
+    s, e = _cut_function(ln, r"^void xreg::RayCaster::distribute_xforms_among_cam_models\(")
+    out.append(("lib/ray_cast/xregRayCastInterface.cpp", s, e, ln[s:e + 1]))
+    ln = _lines("lib/ray_cast/xregRayCastBaseCPU.cpp")
+    s, e = _cut_function(ln, r"^void xreg::RayCasterCPU::pre_compute\(\)")
+    out.append(("lib/ray_cast/xregRayCastBaseCPU.cpp", s, e, ln[s:e + 1]))
     return out
 
 
@@ -129,6 +136,59 @@ extern "C" void xref_ind_pt_to_phys_det_pt(const xref_cam* cam, float col, float
   const xreg::Pt3 r = m.ind_pt_to_phys_det_pt(ind);
   for (int i = 0; i < 3; ++i)
     out[i] = r(i);
+}
+
+// distribute_xforms_among_cam_models: n_poses poses -> n_cams * n_poses (pose, camera index) pairs
+extern "C" void xref_distribute_xforms(const float* poses, uint32_t n_poses, uint32_t n_cams, float* out_poses,
+                                       uint32_t* out_cam_idx)
+{
+  xreg::RayCaster rc;
+  rc.camera_models_.resize(n_cams);
+  rc.num_projs_ = (std::size_t)n_poses * n_cams;
+  rc.xforms_cam_to_itk_phys_.resize(rc.num_projs_);
+  rc.cam_model_for_proj_.assign(rc.num_projs_, ~(std::size_t)0);
+  xreg::FrameTransformList in;
+  for (uint32_t p = 0; p < n_poses; ++p)
+    in.push_back(affine_from12(poses + 12 * (std::size_t)p));
+  rc.distribute_xforms_among_cam_models(in);
+  for (std::size_t g = 0; g < rc.num_projs_; ++g)
+  {
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 4; ++j)
+        out_poses[12 * g + 4 * i + j] = rc.xforms_cam_to_itk_phys_[g].m[i][j];
+    out_cam_idx[g] = (uint32_t)rc.cam_model_for_proj_[g];
+  }
+}
+
+// RayCasterCPU::pre_compute on a caller-owned projection buffer
+extern "C" void xref_pre_compute(float* buf, uint32_t n_projs, uint32_t rows, uint32_t cols, const uint32_t* cam_idx,
+                                 float* const* bg_projs, uint32_t n_cams, int store_method, float default_bg)
+{
+  xreg::RayCasterCPU rc;
+  rc.camera_models_.resize(n_cams);
+  for (auto& c : rc.camera_models_)
+  {
+    c.num_det_rows = rows;
+    c.num_det_cols = cols;
+  }
+  rc.num_projs_ = n_projs;
+  rc.cam_model_for_proj_.assign(cam_idx, cam_idx + n_projs);
+  rc.buf_ = buf;
+  rc.proj_store_meth_ = static_cast<xreg::RayCaster::ProjPixelStoreMethod>(store_method);
+  rc.default_bg_pixel_val_ = default_bg;
+  std::vector<xreg::Proj2D> bgs(n_cams);
+  if (bg_projs)
+  {
+    rc.use_bg_projs_ = true;
+    for (uint32_t c = 0; c < n_cams; ++c)
+    {
+      bgs[c].buf = bg_projs[c];
+      xreg::Proj2D::Pointer p;
+      p.p = &bgs[c];
+      rc.bg_projs_for_each_cam_.push_back(p);
+    }
+  }
+  rc.pre_compute();
 }
 
 // RayCasterLineIntCPU::compute's call of ComputeLineInts (xregRayCastLineIntCPU.cpp, after pre_compute): the caller

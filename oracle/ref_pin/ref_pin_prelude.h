@@ -29,6 +29,7 @@
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
+#include <cstring>
 #include <limits>
 #include <memory>
 #include <random>
@@ -374,6 +375,21 @@ struct CameraModel
   Pt3 ind_pt_to_phys_det_pt(const Pt3& ind_pt) const;
 };
 
+/* a background projection: only GetBufferPointer() is used (through the smart pointer) */
+struct Proj2D
+{
+  float* buf = nullptr;
+  float* GetBufferPointer() { return buf; }
+  struct Pointer
+  {
+    Proj2D* p = nullptr;
+    Proj2D* operator->() const { return p; }
+  };
+};
+
+/* RayCaster / RayCasterCPU: type names, enums and the data members that distribute_xforms_among_cam_models
+ * (xregRayCastInterface.cpp) and RayCasterCPU::pre_compute (xregRayCastBaseCPU.cpp) touch; their definitions are the
+ * reference's lines */
 struct RayCaster
 {
   using PixelScalar2D = float;
@@ -381,6 +397,7 @@ struct RayCaster
   using Vol = itk::Image<float, 3>;
   using CameraModelList = std::vector<CameraModel>;
   using CamModelAssocList = std::vector<size_type>;
+  using ProjList = std::vector<Proj2D::Pointer>;
   enum InterpMethod
   {
     kRAY_CAST_INTERP_LINEAR = 0,
@@ -388,11 +405,35 @@ struct RayCaster
     kRAY_CAST_INTERP_SINC,
     kRAY_CAST_INTERP_BSPLINE
   };
+  enum ProjPixelStoreMethod
+  {
+    kRAY_CAST_PIXEL_REPLACE = 0,
+    kRAY_CAST_PIXEL_ACCUM
+  };
+  size_type num_camera_models() const { return camera_models_.size(); }
+  size_type num_projs() const { return num_projs_; }
+  void distribute_xforms_among_cam_models(const FrameTransformList& xforms_cam_to_itk_phys);
+
+  CameraModelList camera_models_;
+  FrameTransformList xforms_cam_to_itk_phys_;
+  CamModelAssocList cam_model_for_proj_;
+  size_type num_projs_ = 0;
+  ProjPixelStoreMethod proj_store_meth_ = kRAY_CAST_PIXEL_REPLACE;
+  bool use_bg_projs_ = false;
+  ProjList bg_projs_for_each_cam_;
+  PixelScalar2D default_bg_pixel_val_ = 0;
 };
 
-struct RayCasterLineIntCPU
+struct RayCasterCPU : RayCaster
 {
   constexpr static CoordScalar kVOL_BB_STEP_INC_TOL = 1.0e-3;
+  PixelScalar2D* buf_ = nullptr;
+  PixelScalar2D* pixel_buf_to_use() { return buf_; }
+  void pre_compute();
+};
+
+struct RayCasterLineIntCPU : RayCasterCPU
+{
 };
 
 struct RangeType

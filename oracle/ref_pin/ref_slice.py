@@ -135,3 +135,27 @@ def ncc(fixed, mov, mask=None):
     nl.xref_ncc(_fp(fixed), m.ctypes.data_as(C.POINTER(C.c_uint8)) if m is not None else None, C.c_uint32(rows),
                 C.c_uint32(cols), _fp(mov), C.c_uint32(mov.shape[0]), _fp(sims))
     return sims
+
+
+def distribute_xforms(poses, n_cams):
+    """RayCaster::distribute_xforms_among_cam_models: (n, 12) poses -> (n_cams * n, 12) poses + camera indices."""
+    poses = _f32(poses).reshape(-1, 12)
+    n = poses.shape[0]
+    out = np.zeros((n * n_cams, 12), np.float32)
+    idx = np.zeros(n * n_cams, np.uint32)
+    lib().xref_distribute_xforms(_fp(poses), C.c_uint32(n), C.c_uint32(n_cams), _fp(out),
+                                 idx.ctypes.data_as(C.POINTER(C.c_uint32)))
+    return out, idx
+
+
+def pre_compute(buf, cam_idx, n_cams, bg_projs=None, store_method=0, default_bg=0.0):
+    """RayCasterCPU::pre_compute on buf (n_projs, rows, cols), in place."""
+    n, rows, cols = buf.shape
+    ci = np.ascontiguousarray(cam_idx, dtype=np.uint32)
+    arr = None
+    if bg_projs is not None:
+        bgs = [_f32(b) for b in bg_projs]
+        arr = (C.POINTER(C.c_float) * len(bgs))(*[_fp(b) for b in bgs])
+    lib().xref_pre_compute(_fp(buf), C.c_uint32(n), C.c_uint32(rows), C.c_uint32(cols),
+                           ci.ctypes.data_as(C.POINTER(C.c_uint32)), arr, C.c_uint32(n_cams), C.c_int(store_method),
+                           C.c_float(default_bg))

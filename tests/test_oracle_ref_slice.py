@@ -200,3 +200,25 @@ def test_oracle_ncc_equals_the_reference_class_code(xo, seed):
     am = xo.ncc(fixed, mov, mask=mask)
     bm = ref_slice.ncc(fixed, mov, mask=mask)
     assert am.tobytes() == bm.tobytes(), (am, bm)
+
+
+def test_pose_distribution_and_pre_compute_are_the_reference_code(xo):
+    """RayCaster::distribute_xforms_among_cam_models (xregRayCastInterface.cpp:97-114) and RayCasterCPU::pre_compute
+    (xregRayCastBaseCPU.cpp:128-158): camera-major replication; REPLACE fills with the default value unless background
+    projections are in use, ACCUM keeps the content, background projections are copied per camera association."""
+    rng = np.random.default_rng(2)
+    poses = rng.standard_normal((5, 12)).astype(f32)
+    for n_cams in (1, 3):
+        a, ia = xo.distribute_xforms(poses, n_cams)
+        b, ib = ref_slice.distribute_xforms(poses, n_cams)
+        assert a.tobytes() == b.tobytes() and np.array_equal(ia, ib)
+    cam_idx = np.array([0, 0, 1, 1, 2, 0], np.uint32)
+    bgs = [rng.standard_normal((4, 6)).astype(f32) for _ in range(3)]
+    for store in (0, 1):
+        for bg in (None, bgs):
+            for default in (0.0, 2.5):
+                a = rng.standard_normal((6, 4, 6)).astype(f32)
+                b = a.copy()
+                xo.pre_compute(a, cam_idx, bg_projs=bg, store_method=store, default_bg=default)
+                ref_slice.pre_compute(b, cam_idx, 3, bg_projs=bg, store_method=store, default_bg=default)
+                assert a.tobytes() == b.tobytes(), (store, bg is not None, default)
