@@ -391,6 +391,29 @@ extern "C" void xref_ncc(const float* fixed, const uint8_t* mask, uint32_t rows,
   for (uint32_t i = 0; i < n_imgs; ++i)
     sims_out[i] = sm.sim_vals_[i];
 }
+
+// ImgSimMetric2DCombineMean / Addition over n_views metrics holding view_sims[v * n_poses + p]
+struct HeldSims : xreg::ImgSimMetric2DCPU
+{
+  void compute() override {}
+};
+extern "C" void xref_combine(const float* view_sims, uint32_t n_views, uint32_t n_poses, int mean, float* out)
+{
+  std::vector<HeldSims> held(n_views);
+  xreg::ImgSimMetric2DCombineMean cm;
+  xreg::ImgSimMetric2DCombineAddition ca;
+  xreg::ImgSimMetric2DCombine* c = mean ? static_cast<xreg::ImgSimMetric2DCombine*>(&cm) : &ca;
+  c->num_sim_metrics_ = n_views;
+  c->num_projs_per_sim_metric_ = n_poses;
+  for (uint32_t v = 0; v < n_views; ++v)
+  {
+    held[v].sim_vals_.assign(view_sims + (std::size_t)v * n_poses, view_sims + (std::size_t)(v + 1) * n_poses);
+    c->sim_objs_.push_back(&held[v]);
+  }
+  c->compute();
+  for (uint32_t p = 0; p < n_poses; ++p)
+    out[p] = c->sim_vals_[p];
+}
 '''
 
 
@@ -404,6 +427,11 @@ def ncc_slices():
     out.append((rel, s, e, ln[s:e + 1]))
     for regex in (r"^void xreg::ImgSimMetric2DNCCCPU::allocate_resources\(\)", r"^void xreg::ImgSimMetric2DNCCCPU::compute\(\)",
                   r"^void xreg::ImgSimMetric2DNCCCPU::process_mask\(\)"):
+        s, e = _cut_function(ln, regex)
+        out.append((rel, s, e, ln[s:e + 1]))
+    rel = "lib/regi/sim_metrics_2d/xregImgSimMetric2DCombine.cpp"
+    ln = _lines(rel)
+    for regex in (r"^void xreg::ImgSimMetric2DCombineAddition::compute\(\)", r"^void xreg::ImgSimMetric2DCombineMean::compute\(\)"):
         s, e = _cut_function(ln, regex)
         out.append((rel, s, e, ln[s:e + 1]))
     return out

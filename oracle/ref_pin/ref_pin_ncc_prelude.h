@@ -207,6 +207,31 @@ public:
   size_type mask_len_ = 0;
 };
 
+/* xregImgSimMetric2DCombine.h:36-100: the view combiners (members as in the reference; compute() bodies are its lines) */
+using ImgSimMetric2D = ImgSimMetric2DCPU;
+class ImgSimMetric2DCombine
+{
+public:
+  using Scalar = ImgSimMetric2D::Scalar;
+  using ScalarList = ImgSimMetric2D::ScalarList;
+  virtual ~ImgSimMetric2DCombine() {}
+  virtual void compute() = 0;
+  size_type num_sim_metrics_ = 0;
+  size_type num_projs_per_sim_metric_ = 0;
+  ScalarList sim_vals_;
+  std::vector<ImgSimMetric2D*> sim_objs_;
+};
+class ImgSimMetric2DCombineAddition : public ImgSimMetric2DCombine
+{
+public:
+  void compute();
+};
+class ImgSimMetric2DCombineMean : public ImgSimMetric2DCombine
+{
+public:
+  void compute();
+};
+
 }  // namespace xreg
 
 #endif

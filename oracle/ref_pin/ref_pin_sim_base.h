@@ -109,6 +109,8 @@ public:
   /* ImgSimMetric2DCPU::pre_compute (xregImgSimMetric2DCPU.cpp:90-98) with a host buffer: nothing to sync */
   void pre_compute() { process_updated_mask(); }
 
+  Scalar sim_val(const size_type i) const { return sim_vals_[i]; }
+
   ImagePtr fixed_img_;
   ImageMaskPtr mask_;
   bool mask_updated_ = true;

@@ -159,3 +159,13 @@ def pre_compute(buf, cam_idx, n_cams, bg_projs=None, store_method=0, default_bg=
     lib().xref_pre_compute(_fp(buf), C.c_uint32(n), C.c_uint32(rows), C.c_uint32(cols),
                            ci.ctypes.data_as(C.POINTER(C.c_uint32)), arr, C.c_uint32(n_cams), C.c_int(store_method),
                            C.c_float(default_bg))
+
+
+def combine(view_sims, mean=True):
+    """ImgSimMetric2DCombineMean (mean=True) / ImgSimMetric2DCombineAddition over per-view similarity values (views, poses)."""
+    lib()
+    nl = C.CDLL(build_ref_slice.NCC_LIB)
+    v = _f32(view_sims)
+    out = np.zeros(v.shape[1], np.float32)
+    nl.xref_combine(_fp(v), C.c_uint32(v.shape[0]), C.c_uint32(v.shape[1]), C.c_int(1 if mean else 0), _fp(out))
+    return out

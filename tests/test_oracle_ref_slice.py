@@ -222,3 +222,20 @@ def test_pose_distribution_and_pre_compute_are_the_reference_code(xo):
                 xo.pre_compute(a, cam_idx, bg_projs=bg, store_method=store, default_bg=default)
                 ref_slice.pre_compute(b, cam_idx, 3, bg_projs=bg, store_method=store, default_bg=default)
                 assert a.tobytes() == b.tobytes(), (store, bg is not None, default)
+
+
+def test_view_combination_is_the_reference_code(xo):
+    """ImgSimMetric2DCombineMean::compute (xregImgSimMetric2DCombine.cpp:79-98): the oracle's xo_combine_mean and the
+    product's host-side combine_mean (xreg_b200.regi) equal it bit for bit."""
+    from xreg_b200 import regi
+
+    rng = np.random.default_rng(8)
+    for views, poses in ((1, 7), (2, 5), (3, 100), (5, 1)):
+        v = rng.uniform(0, 1, (views, poses)).astype(f32)
+        ref = ref_slice.combine(v, mean=True)
+        assert xo.combine_mean(v).tobytes() == ref.tobytes()
+        assert regi.combine_mean(v).tobytes() == ref.tobytes()
+        acc = np.zeros(poses, f32)
+        for k in range(views):
+            acc = (acc + v[k]).astype(f32)
+        assert ref_slice.combine(v, mean=False).tobytes() == acc.tobytes()
