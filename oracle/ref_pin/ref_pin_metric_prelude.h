@@ -50,12 +50,32 @@ struct DataType<unsigned char>
 {
   enum { type = 0 };
 };
+struct Size
+{
+  int width = 0, height = 0;
+  Size() {}
+  Size(std::size_t w, std::size_t h) : width((int)w), height((int)h) {}
+};
 struct Mat
 {
   int rows = 0, cols = 0;
   int type_ = 0;
   unsigned char* data = nullptr;
   std::size_t step = 0;  // bytes per row
+  std::shared_ptr<std::vector<unsigned char>> own;   // storage of Mat::zeros
+  Size size() const { return Size(cols, rows); }
+  int type() const { return type_; }
+  static Mat zeros(Size s, int type)
+  {
+    Mat m;
+    m.rows = s.height;
+    m.cols = s.width;
+    m.type_ = type;
+    m.step = (std::size_t)s.width * elem(type);
+    m.own = std::make_shared<std::vector<unsigned char>>(m.step * (std::size_t)s.height, (unsigned char)0);
+    m.data = m.own->data();
+    return m;
+  }
   static std::size_t elem(int type) { return type == 5 ? 4u : 1u; }
   Mat() {}
   Mat(std::size_t r, std::size_t c, int type, void* p)
@@ -85,31 +105,7 @@ struct Mat
 };
 }  // namespace cv
 
-namespace Eigen
-{
-/* only Matrix<double,2,1> is used (distance between patch centres in the random-patch branch) */
-template <class T, int R, int C>
-struct Matrix
-{
-  T v[R * C];
-  T& operator[](int i) { return v[i]; }
-  const T& operator[](int i) const { return v[i]; }
-  Matrix operator-(const Matrix& o) const
-  {
-    Matrix r;
-    for (int i = 0; i < R * C; ++i)
-      r.v[i] = v[i] - o.v[i];
-    return r;
-  }
-  T norm() const
-  {
-    T s = 0;
-    for (int i = 0; i < R * C; ++i)
-      s += v[i] * v[i];
-    return std::sqrt(s);
-  }
-};
-}  // namespace Eigen
+#include "ref_pin_eigen_fixed.h"
 
 
 namespace xreg

@@ -15,6 +15,7 @@
 #define XREG_REF_PIN_NCC_PRELUDE_H
 
 #include "ref_pin_sim_base.h"
+#include "ref_pin_eigen_fixed.h"
 
 namespace Eigen
 {
@@ -135,8 +136,9 @@ struct MatrixBase
 template <class M>
 struct Map;
 
-template <class S, int R, int C>
-struct Matrix : MatrixBase<Matrix<S, R, C>>
+/* dynamic row vector: specialisation of the fixed-size template of ref_pin_eigen_fixed.h */
+template <class S>
+struct Matrix<S, 1, Dynamic> : MatrixBase<Matrix<S, 1, Dynamic>>
 {
   using Scalar = S;
   std::vector<S> v;
@@ -146,8 +148,8 @@ struct Matrix : MatrixBase<Matrix<S, R, C>>
   S* ptr_() { return v.data(); }
   Matrix& operator=(const Map<Matrix>& m);
 };
-template <class S, int R, int C>
-struct scalar_of<Matrix<S, R, C>>
+template <class S>
+struct scalar_of<Matrix<S, 1, Dynamic>>
 {
   using type = S;
 };
@@ -169,8 +171,8 @@ struct scalar_of<Map<M>>
   using type = typename scalar_of<M>::type;
 };
 
-template <class S, int R, int C>
-Matrix<S, R, C>& Matrix<S, R, C>::operator=(const Map<Matrix<S, R, C>>& m)
+template <class S>
+Matrix<S, 1, Dynamic>& Matrix<S, 1, Dynamic>::operator=(const Map<Matrix<S, 1, Dynamic>>& m)
 {
   v.assign(m.p, m.p + m.n);
   return *this;

@@ -110,6 +110,20 @@ public:
   void pre_compute() { process_updated_mask(); }
 
   Scalar sim_val(const size_type i) const { return sim_vals_[i]; }
+  /* ImgSimMetric2D / ImgSimMetric2DCPU setters (xregImgSimMetric2D.cpp, xregImgSimMetric2DCPU.cpp:72-88): assignments */
+  void set_num_moving_images(const size_type n) { num_mov_imgs_ = n; }
+  void set_mov_imgs_host_buf(Scalar* buf, const size_type proj_offset = 0)
+  {
+    mov_imgs_buf_ = buf;
+    (void)proj_offset;
+  }
+  void set_fixed_image(ImagePtr img) { fixed_img_ = img; }
+  void set_mask(ImageMaskPtr m)
+  {
+    mask_ = m;
+    mask_updated_ = true;
+  }
+  void set_save_aux_info(const bool b) { save_aux_info_ = b; }
 
   ImagePtr fixed_img_;
   ImageMaskPtr mask_;
