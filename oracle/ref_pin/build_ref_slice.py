@@ -437,13 +437,123 @@ def ncc_slices():
     return out
 
 
+GRAD_WRAPPER = r'''
+cv::gauss_fn cv::g_gauss = nullptr;
+cv::sobel_fn cv::g_sobel = nullptr;
+
+// which Gaussian / Sobel the classes call: the real OpenCV (through cv2) or the oracle's restatement
+extern "C" void xref_set_cv(cv::gauss_fn g, cv::sobel_fn s)
+{
+  cv::g_gauss = g;
+  cv::g_sobel = s;
+}
+
+struct xref_patch_opts   // layout of oracle/xreg_oracle.h: xo_patch_opts
+{
+  uint32_t radius, stride;
+  int32_t compute_mean_of_patch_sims, weight_patch_sims, use_mask_for_weighting, use_mask_for_patch_stats,
+      normalize_weights_as_prob;
+};
+
+template <class Sim>
+static void set_images(Sim& sm, const float* fixed, const uint8_t* mask, uint32_t rows, uint32_t cols, float* mov, uint32_t n)
+{
+  sm.fixed_img_.p = std::make_shared<typename Sim::Image>();
+  sm.fixed_img_.p->buf = const_cast<float*>(fixed);
+  sm.fixed_img_.p->sz.s[0] = cols;
+  sm.fixed_img_.p->sz.s[1] = rows;
+  if (mask)
+  {
+    sm.mask_.p = std::make_shared<typename Sim::ImageMask>();
+    sm.mask_.p->buf = const_cast<uint8_t*>(mask);
+    sm.mask_.p->sz.s[0] = cols;
+    sm.mask_.p->sz.s[1] = rows;
+  }
+  sm.num_mov_imgs_ = n;
+  sm.mov_imgs_buf_ = mov;
+}
+
+extern "C" void xref_grad_ncc(const float* fixed, const uint8_t* mask, uint32_t rows, uint32_t cols, int gauss_width,
+                              const float* mov, uint32_t n_imgs, float* sims_out)
+{
+  xreg::ImgSimMetric2DGradNCCCPU sm;
+  std::vector<float> mov_copy(mov, mov + (std::size_t)n_imgs * rows * cols);
+  set_images(sm, fixed, mask, rows, cols, mov_copy.data(), n_imgs);
+  sm.smooth_img_kernel_rad_ = (std::size_t)gauss_width;   // set_smooth_img_before_sobel_kernel_radius
+  sm.allocate_resources();
+  sm.compute();
+  for (uint32_t i = 0; i < n_imgs; ++i)
+    sims_out[i] = sm.sim_vals_[i];
+}
+
+extern "C" int xref_patch_grad_ncc(const float* fixed, const uint8_t* mask, uint32_t rows, uint32_t cols, int gauss_width,
+                                   const xref_patch_opts* o, const float* mov, uint32_t n_imgs, float* sims_out)
+{
+  xreg::ImgSimMetric2DPatchGradNCCCPU sm;
+  std::vector<float> mov_copy(mov, mov + (std::size_t)n_imgs * rows * cols);
+  set_images(sm, fixed, mask, rows, cols, mov_copy.data(), n_imgs);
+  sm.smooth_img_kernel_rad_ = (std::size_t)gauss_width;
+  sm.patch_radius_ = o->radius;
+  sm.patch_stride_ = o->stride;
+  sm.compute_mean_of_patch_sims_ = o->compute_mean_of_patch_sims != 0;
+  sm.weight_patch_sims_in_combine_ = o->weight_patch_sims != 0;
+  sm.use_mask_for_weighting_ = o->use_mask_for_weighting != 0;
+  sm.use_mask_for_patch_stats_ = o->use_mask_for_patch_stats != 0;
+  sm.normalize_weights_as_prob_ = o->normalize_weights_as_prob != 0;
+  sm.allocate_resources();
+  sm.compute();
+  for (uint32_t i = 0; i < n_imgs; ++i)
+    sims_out[i] = sm.sim_vals_[i];
+  return (int)sm.patch_infos_.size();
+}
+'''
+
+
+def grad_slices():
+    out = [x for x in ncc_slices() if "Combine" not in x[0]] + metric_slices()
+    d = "lib/regi/sim_metrics_2d/"
+    more = (
+        (d + "xregImgSimMetric2DPatchCommon.cpp", (r"^void xreg::ImgSimMetric2DPatchCommon::set_from_other\(",
+                                                   r"^void xreg::ImgSimMetric2DPatchCommon::set_weights_from_other\(",
+                                                   r"^void xreg::ImgSimMetric2DPatchCommon::set_patches_to_use\(")),
+        (d + "xregImgSimMetric2DPatchNCCCPU.cpp", (r"^void xreg::ImgSimMetric2DPatchNCCCPU::set_use_fixed_img_patch_variances_as_wgts\(",
+                                                   r"^void xreg::ImgSimMetric2DPatchNCCCPU::set_use_mov_img_patch_variances_as_wgts\(",
+                                                   r"^void xreg::ImgSimMetric2DPatchNCCCPU::set_other_mov_img_patch_vars\(")),
+        (d + "xregImgSimMetric2DGradImgCPU.cpp", (r"^void xreg::ImgSimMetric2DGradImgCPU::allocate_resources\(\)",
+                                                  r"^void xreg::ImgSimMetric2DGradImgCPU::compute_sobel_grads\(\)")),
+        (d + "xregImgSimMetric2DGradNCCCPU.cpp", (r"^void xreg::ImgSimMetric2DGradNCCCPU::allocate_resources\(\)",
+                                                  r"^void xreg::ImgSimMetric2DGradNCCCPU::compute\(\)",
+                                                  r"^void xreg::ImgSimMetric2DGradNCCCPU::process_mask\(\)")),
+        (d + "xregImgSimMetric2DPatchGradNCCCPU.cpp", (r"^void xreg::ImgSimMetric2DPatchGradNCCCPU::allocate_resources\(\)",
+                                                       r"^void xreg::ImgSimMetric2DPatchGradNCCCPU::compute\(\)",
+                                                       r"^void xreg::ImgSimMetric2DPatchGradNCCCPU::process_mask\(\)")),
+    )
+    for rel, regexes in more:
+        ln = _lines(rel)
+        for regex in regexes:
+            s, e = _cut_function(ln, regex)
+            out.append((rel, s, e, ln[s:e + 1]))
+    # two accessors whose return type sits on the line before the qualified name
+    ln = _lines(d + "xregImgSimMetric2DPatchNCCCPU.cpp")
+    s, e = _with_prev(ln, r"^xreg::ImgSimMetric2DPatchNCCCPU::aux_info\(\)|aux_info\(\)$", 0)
+    if not ln[s].startswith("std::shared_ptr"):
+        s -= 1
+    out.append((d + "xregImgSimMetric2DPatchNCCCPU.cpp", s, e, ln[s:e + 1]))
+    ln = _lines(d + "xregImgSimMetric2DPatchCommon.cpp")
+    s, e = _cut_function(ln, r"^xreg::ImgSimMetric2DPatchCommon::sim_vals_for_each_patch\(\) const")
+    out.append((d + "xregImgSimMetric2DPatchCommon.cpp", s - 1, e, ln[s - 1:e + 1]))
+    return out
+
+
 UNITS = (
     # (library, prelude header, slice list function, C ABI wrapper)
     ("libxreg_refslice.so", "ref_pin_prelude.h", slices, WRAPPER),
     ("libxreg_refslice_metric.so", "ref_pin_metric_prelude.h", metric_slices, METRIC_WRAPPER),
     ("libxreg_refslice_hu.so", "ref_pin_hu_prelude.h", hu_slices, HU_WRAPPER),
     ("libxreg_refslice_ncc.so", "ref_pin_ncc_prelude.h", ncc_slices, NCC_WRAPPER),
+    ("libxreg_refslice_grad.so", "ref_pin_grad_prelude.h", grad_slices, GRAD_WRAPPER),
 )
+GRAD_LIB = os.path.join(OUT_DIR, "libxreg_refslice_grad.so")
 NCC_LIB = os.path.join(OUT_DIR, "libxreg_refslice_ncc.so")
 HU_LIB = os.path.join(OUT_DIR, "libxreg_refslice_hu.so")
 METRIC_LIB = os.path.join(OUT_DIR, "libxreg_refslice_metric.so")

@@ -118,7 +118,7 @@ cv::Mat ShallowCopyItkToOpenCV(itk::Image2<T, 2>* img)
 }
 
 template <class T>
-typename itk::Image2<T, 2>::Pointer MakeITK2DVol(const size_type num_cols, const size_type num_rows, const T val)
+typename itk::Image2<T, 2>::Pointer MakeITK2DVol(const size_type num_cols, const size_type num_rows, const T val = T())
 {
   typename itk::Image2<T, 2>::Pointer p;
   p.p = std::make_shared<itk::Image2<T, 2>>();
@@ -169,6 +169,10 @@ public:
   using PatchIndexList = std::vector<size_type>;
 
   size_type num_patches() const;
+  void set_from_other(const ImgSimMetric2DPatchCommon& other);
+  void set_weights_from_other(const ImgSimMetric2DPatchCommon& other);
+  void set_patches_to_use(const PatchIndexList& patch_inds);
+  const ListOfSimScalarLists& sim_vals_for_each_patch() const;
   void set_wgt_img(WgtImgPtr wgt_img)
   {
     wgt_img_ = wgt_img;
@@ -219,6 +223,10 @@ public:
   };
 
   void process_mask() override;
+  std::shared_ptr<H5ReadWriteInterface> aux_info();
+  void set_use_fixed_img_patch_variances_as_wgts(const bool use_vars_as_wgts);
+  void set_use_mov_img_patch_variances_as_wgts(const bool use_vars_as_wgts);
+  void set_other_mov_img_patch_vars(const std::vector<ScalarList>* other_vars);
 
   size_type img_num_rows_ = 0;
   size_type img_num_cols_ = 0;

@@ -169,3 +169,62 @@ def combine(view_sims, mean=True):
     out = np.zeros(v.shape[1], np.float32)
     nl.xref_combine(_fp(v), C.c_uint32(v.shape[0]), C.c_uint32(v.shape[1]), C.c_int(1 if mean else 0), _fp(out))
     return out
+
+
+# ---- the gradient-metric classes (oracle/_ref/libxreg_refslice_grad.so); cv::GaussianBlur / cv::Sobel are call-outs --
+_GAUSS_T = C.CFUNCTYPE(None, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float))
+_SOBEL_T = C.CFUNCTYPE(None, C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float))
+_glib = None
+_cv_keep = None
+
+
+def grad_lib():
+    global _glib
+    if _glib is None:
+        lib()
+        _glib = C.CDLL(build_ref_slice.GRAD_LIB)
+        _glib.xref_patch_grad_ncc.restype = C.c_int
+    return _glib
+
+
+def set_filters(gauss, sobel):
+    """Install the Gaussian / Sobel the reference classes call: gauss(img (rows, cols) f32, ksize) -> img,
+    sobel(img, dx, dy) -> img (3x3, scale 1, default border)."""
+    global _cv_keep
+
+    def g(src, rows, cols, ksize, dst):
+        a = np.ctypeslib.as_array(src, shape=(rows, cols)).copy()
+        np.ctypeslib.as_array(dst, shape=(rows, cols))[:] = np.asarray(gauss(a, ksize), dtype=np.float32)
+
+    def s(src, rows, cols, dx, dy, dst):
+        a = np.ctypeslib.as_array(src, shape=(rows, cols)).copy()
+        np.ctypeslib.as_array(dst, shape=(rows, cols))[:] = np.asarray(sobel(a, dx, dy), dtype=np.float32)
+
+    _cv_keep = (_GAUSS_T(g), _SOBEL_T(s))
+    grad_lib().xref_set_cv(_cv_keep[0], _cv_keep[1])
+
+
+def grad_ncc(fixed, mov, mask=None, gauss_width=5):
+    """ImgSimMetric2DGradNCCCPU (set_filters first)."""
+    fixed = _f32(fixed)
+    rows, cols = fixed.shape
+    mov = _f32(mov).reshape(-1, rows, cols)
+    sims = np.zeros(mov.shape[0], np.float32)
+    m = np.ascontiguousarray(mask, dtype=np.uint8) if mask is not None else None
+    grad_lib().xref_grad_ncc(_fp(fixed), m.ctypes.data_as(C.POINTER(C.c_uint8)) if m is not None else None,
+                             C.c_uint32(rows), C.c_uint32(cols), C.c_int(gauss_width), _fp(mov),
+                             C.c_uint32(mov.shape[0]), _fp(sims))
+    return sims
+
+
+def patch_grad_ncc(fixed, mov, opts, mask=None, gauss_width=5):
+    """ImgSimMetric2DPatchGradNCCCPU (set_filters first)."""
+    fixed = _f32(fixed)
+    rows, cols = fixed.shape
+    mov = _f32(mov).reshape(-1, rows, cols)
+    sims = np.zeros(mov.shape[0], np.float32)
+    m = np.ascontiguousarray(mask, dtype=np.uint8) if mask is not None else None
+    grad_lib().xref_patch_grad_ncc(_fp(fixed), m.ctypes.data_as(C.POINTER(C.c_uint8)) if m is not None else None,
+                                   C.c_uint32(rows), C.c_uint32(cols), C.c_int(gauss_width), C.byref(opts), _fp(mov),
+                                   C.c_uint32(mov.shape[0]), _fp(sims))
+    return sims

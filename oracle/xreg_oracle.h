@@ -33,6 +33,11 @@
  *     loops in the reference -> bit for bit, no convention.  Unmasked: three Eigen
  *     reductions, for which stand-in and oracle follow the same documented Eigen 3.3
  *     SSE reduction shape -> pinned up to that convention.
+ *   Gradient-NCC and patch gradient-NCC (xo_grad_ncc, xo_patch_grad_ncc): the
+ *     reference's GradImgCPU / GradNCCCPU / PatchGradNCCCPU classes compile the same
+ *     way (libxreg_refslice_grad.so) with cv::GaussianBlur / cv::Sobel as call-outs:
+ *     bit for bit with the oracle's filters installed, <= 2e-6 with the real OpenCV
+ *     (cv2) installed.
  *   HU -> linear attenuation (xo_hu_to_lin_att): pinned to
  *     HUToLinAttFilter::GenerateData (libxreg_refslice_hu.so).
  *   SSD, Gaussian / Sobel gradient images: PARITY UNPINNED by the reference

@@ -239,3 +239,54 @@ def test_view_combination_is_the_reference_code(xo):
         for k in range(views):
             acc = (acc + v[k]).astype(f32)
         assert ref_slice.combine(v, mean=False).tobytes() == acc.tobytes()
+
+
+# ---- gradient-NCC and patch gradient-NCC (the headline metric): the reference's class code over chosen filters -------------
+def _oracle_filters(xo):
+    def sobel(img, dx, dy):
+        gx, gy = xo.sobel(img)
+        return gx if dx == 1 else gy
+
+    return (lambda img, k: xo.gauss_blur(img, k)), sobel
+
+
+def _cv2_filters():
+    import cv2
+
+    return (lambda img, k: cv2.GaussianBlur(img, (k, k), 0)), (lambda img, dx, dy: cv2.Sobel(img, -1, dx, dy))
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_oracle_gradient_metrics_equal_the_reference_class_code(xo, seed):
+    """ImgSimMetric2DGradImgCPU::{allocate_resources, compute_sobel_grads}, ImgSimMetric2DGradNCCCPU::{allocate_resources,
+    compute, process_mask} and ImgSimMetric2DPatchGradNCCCPU::{allocate_resources, compute, process_mask}
+    (xregImgSimMetric2DGradImgCPU.cpp:32-102, ...GradNCCCPU.cpp:29-81, ...PatchGradNCCCPU.cpp:34-253,313-409) compiled from
+    the reference's own lines on top of its NCC / patch-NCC classes; cv::GaussianBlur / cv::Sobel are call-outs.
+    (1) With the oracle's restatement of the two filters installed, the oracle's gradient-NCC and patch gradient-NCC equal
+        the reference classes bit for bit: everything except OpenCV's arithmetic is pinned.
+    (2) With the REAL OpenCV installed (cv2), the reference classes give what an xReg build gives up to OpenCV's version:
+        the oracle agrees to <= 2e-6 (its Gaussian is within 1 ulp of OpenCV's, its Sobel identical)."""
+    fixed, mov, mask, radius, stride, _ = _metric_case(100 + seed)
+    width = [0, 3, 5, 7][seed % 4]
+    ref_slice.set_filters(*_oracle_filters(xo))
+    a = xo.grad_ncc(fixed, mov, mask=mask, gauss_width=width, n_threads=1)
+    b = ref_slice.grad_ncc(fixed, mov, mask=mask, gauss_width=width)
+    assert a.tobytes() == b.tobytes(), (a, b)
+    for kw in (dict(), dict(compute_mean=True), dict(mask_stats=True) if mask is not None else dict(weight_sims=False)):
+        opts = xo.patch_opts(radius=radius, stride=stride, **kw)
+        w = xo.patch_weights(fixed.shape[0], fixed.shape[1], opts, mask=mask) if (mask is not None and opts.use_mask_for_weighting) else None
+        pa = xo.patch_grad_ncc(fixed, mov, opts, mask=mask, weights=w, gauss_width=width, n_threads=1)
+        pb = ref_slice.patch_grad_ncc(fixed, mov, opts, mask=mask, gauss_width=width)
+        assert pa.tobytes() == pb.tobytes(), (kw, pa, pb)
+    try:
+        ref_slice.set_filters(*_cv2_filters())
+    except ImportError:
+        return
+    c = ref_slice.grad_ncc(fixed, mov, mask=mask, gauss_width=width)
+    assert np.max(np.abs(a - c)) <= 2e-6, (a, c)
+    opts = xo.patch_opts(radius=radius, stride=stride)
+    w = xo.patch_weights(fixed.shape[0], fixed.shape[1], opts, mask=mask) if mask is not None else None
+    pa = xo.patch_grad_ncc(fixed, mov, opts, mask=mask, weights=w, gauss_width=width, n_threads=1)
+    pc = ref_slice.patch_grad_ncc(fixed, mov, opts, mask=mask, gauss_width=width)
+    finite = pa < 1e30
+    assert np.array_equal(finite, pc < 1e30) and np.max(np.abs(pa[finite] - pc[finite]), initial=0.0) <= 2e-6, (pa, pc)
