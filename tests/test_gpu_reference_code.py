@@ -1,0 +1,54 @@
+"""CUDA path against the REFERENCE'S OWN CODE, end to end: DRRs from the reference's ComputeLineInts<Kernel>
+(xregRayCastLineIntCPU.cpp:40-292) and similarity values from its ImgSimMetric2D{NCC,GradNCC,PatchNCC,PatchGradNCC}CPU
+classes, compiled from /root/reference over stand-in types into oracle/_ref/ (oracle/ref_pin/build_ref_slice.py), with the
+real OpenCV (cv2) behind cv::GaussianBlur / cv::Sobel.  This is the closest thing to "the reference run here" that this
+image allows; the tolerances are north_star's: clip masks exact, DRR <= 1e-4 relative, similarity <= 1e-5 absolute."""
+import numpy as np
+import pytest
+
+from oracle.ref_pin import ref_slice
+from xreg_b200 import regi, synth
+from xreg_b200.geometry import to12
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not ref_slice.available(), reason="neither the reference checkout nor a built oracle/_ref slice")]
+f32 = np.float32
+
+
+def _cv2_filters():
+    cv2 = pytest.importorskip("cv2")
+    return (lambda img, k: cv2.GaussianBlur(img, (k, k), 0)), (lambda img, dx, dy: cv2.Sobel(img, -1, dx, dy))
+
+
+@pytest.mark.parametrize("metric", ["patch-grad-ncc", "grad-ncc", "ncc", "patch-ncc"])
+def test_cuda_path_matches_the_reference_code(ctx, xo, small_scene, metric):
+    vol, cam, nominal = small_scene
+    pop = synth.pose_population(vol, nominal, 6)
+    xcam = [xo.cam_struct(cam)]
+    # reference code: DRRs
+    ref_drr = ref_slice.compute_line_ints(vol.data, xo.affine_inverse(vol.idx_to_phys()), xcam, to12(pop))
+    fixed = synth.add_noise(ref_drr[0])
+    mask = synth.circular_mask(cam.num_det_rows, cam.num_det_cols) if metric in ("patch-grad-ncc", "ncc") else None
+    # CUDA path
+    fn = regi.Intensity2D3DObjFn(ctx, vol, [cam], [fixed], metric=metric, max_pop=6, patch_radius=6,
+                                 masks=[mask] if mask is not None else None)
+    sims = fn(pop)
+    got = fn.rc.raw_host_pixel_buf().copy()
+    fn.close()
+    # DRR parity against the reference code
+    assert np.array_equal(got == 0, ref_drr == 0)          # rays that miss / cross only air: exactly zero in both
+    sel = ref_drr > 1e-3 * ref_drr.max()
+    assert (np.abs(got[sel] - ref_drr[sel]) / ref_drr[sel]).max() <= 1e-4
+    # metric parity against the reference classes, fed with the reference's DRRs, real OpenCV inside
+    ref_slice.set_filters(*_cv2_filters())
+    opts = xo.patch_opts(radius=6)
+    if metric == "patch-grad-ncc":
+        ref = ref_slice.patch_grad_ncc(fixed, ref_drr, opts, mask=mask, gauss_width=5)
+    elif metric == "grad-ncc":
+        ref = ref_slice.grad_ncc(fixed, ref_drr, mask=mask, gauss_width=5)
+    elif metric == "ncc":
+        ref = ref_slice.ncc(fixed, ref_drr, mask=mask)
+    else:
+        ref = ref_slice.patch_ncc(fixed, ref_drr, opts, mask=mask)[0]
+    assert np.max(np.abs(sims - ref)) <= 1e-5, (metric, sims, ref)
+    assert int(np.argmin(sims)) == 0 == int(np.argmin(ref))
