@@ -392,6 +392,32 @@ extern "C" void xref_ncc(const float* fixed, const uint8_t* mask, uint32_t rows,
     sims_out[i] = sm.sim_vals_[i];
 }
 
+extern "C" void xref_ssd(const float* fixed, const uint8_t* mask, uint32_t rows, uint32_t cols, const float* mov,
+                         uint32_t n_imgs, float* sims_out)
+{
+  using Sim = xreg::ImgSimMetric2DSSDCPU;
+  Sim sm;
+  std::vector<float> fixed_copy(fixed, fixed + (std::size_t)rows * cols);   // the mask is applied to the fixed image in place
+  sm.fixed_img_.p = std::make_shared<Sim::Image>();
+  sm.fixed_img_.p->buf = fixed_copy.data();
+  sm.fixed_img_.p->sz.s[0] = cols;
+  sm.fixed_img_.p->sz.s[1] = rows;
+  if (mask)
+  {
+    sm.mask_.p = std::make_shared<Sim::ImageMask>();
+    sm.mask_.p->buf = const_cast<uint8_t*>(mask);
+    sm.mask_.p->sz.s[0] = cols;
+    sm.mask_.p->sz.s[1] = rows;
+  }
+  std::vector<float> mov_copy(mov, mov + (std::size_t)n_imgs * rows * cols);
+  sm.num_mov_imgs_ = n_imgs;
+  sm.mov_imgs_buf_ = mov_copy.data();
+  sm.allocate_resources();
+  sm.compute();
+  for (uint32_t i = 0; i < n_imgs; ++i)
+    sims_out[i] = sm.sim_vals_[i];
+}
+
 // ImgSimMetric2DCombineMean / Addition over n_views metrics holding view_sims[v * n_poses + p]
 struct HeldSims : xreg::ImgSimMetric2DCPU
 {
@@ -427,6 +453,16 @@ def ncc_slices():
     out.append((rel, s, e, ln[s:e + 1]))
     for regex in (r"^void xreg::ImgSimMetric2DNCCCPU::allocate_resources\(\)", r"^void xreg::ImgSimMetric2DNCCCPU::compute\(\)",
                   r"^void xreg::ImgSimMetric2DNCCCPU::process_mask\(\)"):
+        s, e = _cut_function(ln, regex)
+        out.append((rel, s, e, ln[s:e + 1]))
+    rel = "lib/regi/sim_metrics_2d/xregImgSimMetric2DSSDCPU.cpp"
+    ln = _lines(rel)
+    k = next(i for i, x in enumerate(ln) if "void ApplyMaskToEigenMatInPlace(" in x)
+    s = max(i for i in range(k) if ln[i].startswith("namespace"))
+    e = next(i for i in range(k, len(ln)) if re.match(r"^\}\s*//\s*un-named", ln[i]))
+    out.append((rel, s, e, ln[s:e + 1]))
+    for regex in (r"^void xreg::ImgSimMetric2DSSDCPU::allocate_resources\(\)", r"^void xreg::ImgSimMetric2DSSDCPU::compute\(\)",
+                  r"^void xreg::ImgSimMetric2DSSDCPU::process_mask\(\)"):
         s, e = _cut_function(ln, regex)
         out.append((rel, s, e, ln[s:e + 1]))
     rel = "lib/regi/sim_metrics_2d/xregImgSimMetric2DCombine.cpp"
@@ -510,7 +546,7 @@ extern "C" int xref_patch_grad_ncc(const float* fixed, const uint8_t* mask, uint
 
 
 def grad_slices():
-    out = [x for x in ncc_slices() if "Combine" not in x[0]] + metric_slices()
+    out = [x for x in ncc_slices() if "Combine" not in x[0] and "SSDCPU" not in x[0]] + metric_slices()
     d = "lib/regi/sim_metrics_2d/"
     more = (
         (d + "xregImgSimMetric2DPatchCommon.cpp", (r"^void xreg::ImgSimMetric2DPatchCommon::set_from_other\(",

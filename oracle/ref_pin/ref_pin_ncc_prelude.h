@@ -113,6 +113,23 @@ struct ArrayView
   }
 };
 
+/* (a - b).array().square().sum(): the SSD reduction, same vectorised order */
+template <class S>
+struct VecSqDiffSum
+{
+  const S* a;
+  const S* b;
+  std::ptrdiff_t n;
+  const VecSqDiffSum& array() const { return *this; }
+  const VecSqDiffSum& square() const { return *this; }
+  S sum() const
+  {
+    const S* p = a;
+    const S* q = b;
+    return redux::run(n, [p, q](std::ptrdiff_t i) { return (p[i] - q[i]) * (p[i] - q[i]); });
+  }
+};
+
 template <class D>
 struct MatrixBase
 {
@@ -124,6 +141,16 @@ struct MatrixBase
   Scalar& operator()(std::ptrdiff_t i) { return derived().ptr_()[i]; }
   ConstArrayView<Scalar> array() const { return ConstArrayView<Scalar>{derived().ptr_(), size()}; }
   ArrayView<Scalar> array() { return ArrayView<Scalar>{derived().ptr_(), size()}; }
+  /* row vectors: 1 x n */
+  unsigned long rows() const { return 1; }
+  unsigned long cols() const { return (unsigned long)size(); }
+  Scalar operator()(unsigned long, unsigned long c) const { return derived().ptr_()[c]; }
+  Scalar& operator()(unsigned long, unsigned long c) { return derived().ptr_()[c]; }
+  template <class O>
+  VecSqDiffSum<Scalar> operator-(const MatrixBase<O>& o) const
+  {
+    return VecSqDiffSum<Scalar>{derived().ptr_(), o.derived().ptr_(), size()};
+  }
   template <class O>
   Scalar dot(const MatrixBase<O>& o) const
   {
@@ -207,6 +234,21 @@ public:
   Scalar fixed_img_stddev_ = 0;
   ImageMaskVec mask_vec_;
   size_type mask_len_ = 0;
+};
+
+/* xregImgSimMetric2DSSDCPU.h:36-75 */
+class ImgSimMetric2DSSDCPU : public ImgSimMetric2DCPU
+{
+public:
+  void allocate_resources() override;
+  void compute() override;
+  void process_mask() override;
+  using ImageVec = Eigen::Matrix<Scalar, 1, Eigen::Dynamic>;
+  using ImageMaskVec = Eigen::Matrix<MaskScalar, 1, Eigen::Dynamic>;
+  using MappedImageVec = Eigen::Map<ImageVec>;
+  using MappedImageMaskVec = Eigen::Map<ImageMaskVec>;
+  ImageVec fixed_img_vec_;
+  ImageMaskVec mask_vec_;
 };
 
 /* xregImgSimMetric2DCombine.h:36-100: the view combiners (members as in the reference; compute() bodies are its lines) */

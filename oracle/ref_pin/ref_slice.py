@@ -228,3 +228,17 @@ def patch_grad_ncc(fixed, mov, opts, mask=None, gauss_width=5):
                                    C.c_uint32(rows), C.c_uint32(cols), C.c_int(gauss_width), C.byref(opts), _fp(mov),
                                    C.c_uint32(mov.shape[0]), _fp(sims))
     return sims
+
+
+def ssd(fixed, mov, mask=None):
+    """ImgSimMetric2DSSDCPU: allocate_resources(), compute() -> sim_vals."""
+    lib()
+    nl = C.CDLL(build_ref_slice.NCC_LIB)
+    fixed = _f32(fixed)
+    rows, cols = fixed.shape
+    mov = _f32(mov).reshape(-1, rows, cols)
+    sims = np.zeros(mov.shape[0], np.float32)
+    m = np.ascontiguousarray(mask, dtype=np.uint8) if mask is not None else None
+    nl.xref_ssd(_fp(fixed), m.ctypes.data_as(C.POINTER(C.c_uint8)) if m is not None else None, C.c_uint32(rows),
+                C.c_uint32(cols), _fp(mov), C.c_uint32(mov.shape[0]), _fp(sims))
+    return sims

@@ -5,8 +5,9 @@
  * this path.  xo_drr is pinned to the reference's own source lines compiled over
  * stand-in types (oracle/ref_pin/, tests/test_oracle_ref_slice.py: bit for bit),
  * and so are xo_patch_weights / xo_patch_ncc, xo_ncc (unmasked: up to the Eigen
- * reduction convention) and xo_hu_to_lin_att; SSD and the gradient images are
- * PARITY UNPINNED by the reference and pinned by tests/ instead.
+ * reduction convention), xo_ssd, xo_grad_ncc / xo_patch_grad_ncc (OpenCV filters as
+ * call-outs) and xo_hu_to_lin_att; the Gaussian / Sobel filter arithmetic itself is
+ * PARITY UNPINNED by the reference and pinned by OpenCV's Python binding instead.
  *
  * Build: gcc -O2 -ffp-contract=off -fopenmp -fPIC -shared  (no -march, no -ffast-math)
  * OpenMP stands in for tbb::parallel_for at exactly the reference's parallel

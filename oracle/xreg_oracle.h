@@ -40,9 +40,11 @@
  *     (cv2) installed.
  *   HU -> linear attenuation (xo_hu_to_lin_att): pinned to
  *     HUToLinAttFilter::GenerateData (libxreg_refslice_hu.so).
- *   SSD, Gaussian / Sobel gradient images: PARITY UNPINNED by the reference
- *     (an Eigen reduction; OpenCV filters); pinned instead by analytic known
- *     answers, an independent numpy float64 model and OpenCV's Python binding
+ *   SSD (xo_ssd): class code pinned like unmasked NCC (one Eigen reduction under
+ *     the stated convention).
+ *   Gaussian / Sobel gradient images (xo_gauss_blur, xo_sobel): PARITY UNPINNED by
+ *     the reference (OpenCV's filters); pinned instead by OpenCV's Python binding
+ *     (Sobel bit-exact, Gaussian <= 1 ulp) and known answers
  *     (tests/test_oracle_metrics.py).
  *
  * Every function cites the reference file:line it follows (paths relative to

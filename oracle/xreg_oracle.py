@@ -2,10 +2,11 @@
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
 cpu_baseline / --impl reference legs of bench.py.  Nothing under xreg_b200/
-imports this module.  The DRR, patch-NCC, NCC and HU-conversion restatements are
-pinned to the reference's own source lines (oracle/ref_pin/,
-tests/test_oracle_ref_slice.py); SSD and the gradient images are PARITY UNPINNED by
-the reference (it has no tests for this path); see xreg_oracle.h.
+imports this module.  The DRR, NCC, SSD, patch-NCC, gradient-NCC, patch gradient-NCC
+and HU-conversion restatements are pinned to the reference's own source lines
+(oracle/ref_pin/, tests/test_oracle_ref_slice.py); the Gaussian / Sobel filter
+arithmetic (OpenCV) is PARITY UNPINNED by the reference (it has no tests for this
+path) and pinned by the cv2 binding; see xreg_oracle.h.
 """
 from __future__ import annotations
 

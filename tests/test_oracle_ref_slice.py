@@ -290,3 +290,20 @@ def test_oracle_gradient_metrics_equal_the_reference_class_code(xo, seed):
     pc = ref_slice.patch_grad_ncc(fixed, mov, opts, mask=mask, gauss_width=width)
     finite = pa < 1e30
     assert np.array_equal(finite, pc < 1e30) and np.max(np.abs(pa[finite] - pc[finite]), initial=0.0) <= 2e-6, (pa, pc)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_oracle_ssd_equals_the_reference_class_code(xo, seed):
+    """ImgSimMetric2DSSDCPU::{allocate_resources, compute, process_mask} + ApplyMaskToEigenMatInPlace
+    (xregImgSimMetric2DSSDCPU.cpp:29-109): masking, difference, division by the pixel count are the reference's lines; the one
+    Eigen reduction follows the stated convention (as for unmasked NCC)."""
+    rng = np.random.default_rng(3000 + seed)
+    rows, cols = int(rng.integers(1, 40)), int(rng.integers(1, 60))
+    n = int(rng.integers(1, 4))
+    fixed = (rng.standard_normal((rows, cols)) * 3 + 5).astype(f32)
+    mov = np.stack([(fixed + rng.standard_normal((rows, cols)) * rng.uniform(0, 2)).astype(f32) for _ in range(n)])
+    mov[0] = fixed
+    assert xo.ssd(fixed, mov).tobytes() == ref_slice.ssd(fixed, mov).tobytes()
+    mask = (rng.random((rows, cols)) < 0.7).astype(np.uint8)
+    a, b = xo.ssd(fixed, mov, mask), ref_slice.ssd(fixed, mov, mask)
+    assert a.tobytes() == b.tobytes() and a[0] == 0
