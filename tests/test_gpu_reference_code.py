@@ -52,3 +52,29 @@ def test_cuda_path_matches_the_reference_code(ctx, xo, small_scene, metric):
         ref = ref_slice.patch_ncc(fixed, ref_drr, opts, mask=mask)[0]
     assert np.max(np.abs(sims - ref)) <= 1e-5, (metric, sims, ref)
     assert int(np.argmin(sims)) == 0 == int(np.argmin(ref))
+
+
+def test_config_c1_full_size_against_the_reference_code(ctx, xo):
+    """BASELINE.json configs[0] verbatim -- "single line-integral DRR of synthetic 256^3 float CT at 256x256 detector via
+    RayCasterLineIntCPU + NCC" -- with the reference's own ComputeLineInts and NCC class code as the CPU side."""
+    vol = synth.make_volume(256, 256, 256)
+    cam = synth.make_camera(256)
+    nominal = synth.nominal_pose(vol)
+    pop = synth.pose_population(vol, nominal, 2)
+    xcam = [xo.cam_struct(cam)]
+    ref_drr = ref_slice.compute_line_ints(vol.data, xo.affine_inverse(vol.idx_to_phys()), xcam, to12(pop))
+    fixed = synth.add_noise(ref_drr[0])
+    fn = regi.Intensity2D3DObjFn(ctx, vol, [cam], [fixed], metric="ncc", max_pop=2)
+    sims = fn(pop)
+    got = fn.rc.raw_host_pixel_buf().copy()
+    gmask, gsteps, gS = fn.rc.ray_info()
+    fn.close()
+    assert ref_drr.max() > 1.0 and (ref_drr > 0).mean() > 0.3
+    assert np.array_equal(got == 0, ref_drr == 0)
+    sel = ref_drr > 1e-3 * ref_drr.max()
+    assert (np.abs(got[sel] - ref_drr[sel]) / ref_drr[sel]).max() <= 1e-4
+    ref = ref_slice.ncc(fixed, ref_drr)
+    assert np.max(np.abs(sims - ref)) <= 1e-5, (sims, ref)
+    # and the oracle is that code, bit for bit, at this size too
+    o = xo.drr(vol.data, vol.idx_to_phys(), xcam, to12(pop))
+    assert o.tobytes() == ref_drr.tobytes()
