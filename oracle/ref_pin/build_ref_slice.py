@@ -581,6 +581,37 @@ def grad_slices():
     return out
 
 
+SE3_WRAPPER = r'''
+// ExpSE3(Pt6): [w_x w_y w_z v_x v_y v_z] -> row-major 3x4
+extern "C" void xref_exp_se3(const float x[6], float out12[12])
+{
+  xreg::Pt6 p;
+  for (int i = 0; i < 6; ++i)
+    p(i) = x[i];
+  const xreg::Mat4x4 T = xreg::ExpSE3(p);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 4; ++j)
+      out12[4 * i + j] = T(i, j);
+}
+'''
+
+
+def se3_slices():
+    out = []
+    rel = "lib/transforms/xregRotUtils.cpp"
+    ln = _lines(rel)
+    for regex in (r"^xreg::Mat3x3 xreg::SkewMatrix\(const Pt3& v\)", r"^xreg::Pt3 xreg::WedgeSkew\(const Mat3x3& W\)",
+                  r"^xreg::Mat3x3 xreg::ExpSO3\(const Pt3& x\)", r"^xreg::Mat3x3 xreg::ExpSO3\(const Mat3x3& W\)"):
+        s, e = _cut_function(ln, regex)
+        out.append((rel, s, e, ln[s:e + 1]))
+    rel = "lib/transforms/xregRigidUtils.cpp"
+    ln = _lines(rel)
+    for regex in (r"^xreg::Mat4x4 xreg::ExpSE3\(const Mat4x4& M\)", r"^xreg::Mat4x4 xreg::ExpSE3\(const Pt6& x\)"):
+        s, e = _cut_function(ln, regex)
+        out.append((rel, s, e, ln[s:e + 1]))
+    return out
+
+
 UNITS = (
     # (library, prelude header, slice list function, C ABI wrapper)
     ("libxreg_refslice.so", "ref_pin_prelude.h", slices, WRAPPER),
@@ -588,7 +619,9 @@ UNITS = (
     ("libxreg_refslice_hu.so", "ref_pin_hu_prelude.h", hu_slices, HU_WRAPPER),
     ("libxreg_refslice_ncc.so", "ref_pin_ncc_prelude.h", ncc_slices, NCC_WRAPPER),
     ("libxreg_refslice_grad.so", "ref_pin_grad_prelude.h", grad_slices, GRAD_WRAPPER),
+    ("libxreg_refslice_se3.so", "ref_pin_se3_prelude.h", se3_slices, SE3_WRAPPER),
 )
+SE3_LIB = os.path.join(OUT_DIR, "libxreg_refslice_se3.so")
 GRAD_LIB = os.path.join(OUT_DIR, "libxreg_refslice_grad.so")
 NCC_LIB = os.path.join(OUT_DIR, "libxreg_refslice_ncc.so")
 HU_LIB = os.path.join(OUT_DIR, "libxreg_refslice_hu.so")

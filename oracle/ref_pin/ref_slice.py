@@ -242,3 +242,13 @@ def ssd(fixed, mov, mask=None):
     nl.xref_ssd(_fp(fixed), m.ctypes.data_as(C.POINTER(C.c_uint8)) if m is not None else None, C.c_uint32(rows),
                 C.c_uint32(cols), _fp(mov), C.c_uint32(mov.shape[0]), _fp(sims))
     return sims
+
+
+def exp_se3(x):
+    """ExpSE3(Pt6) of the reference (lib/transforms/xregRigidUtils.cpp:40-85 over xregRotUtils.cpp): row-major 3x4."""
+    lib()
+    sl = C.CDLL(build_ref_slice.SE3_LIB)
+    xx = _f32(x).reshape(6)
+    out = np.zeros(12, np.float32)
+    sl.xref_exp_se3(_fp(xx), _fp(out))
+    return out

@@ -307,3 +307,33 @@ def test_oracle_ssd_equals_the_reference_class_code(xo, seed):
     mask = (rng.random((rows, cols)) < 0.7).astype(np.uint8)
     a, b = xo.ssd(fixed, mov, mask), ref_slice.ssd(fixed, mov, mask)
     assert a.tobytes() == b.tobytes() and a[0] == 0
+
+
+def test_product_exp_se3_matches_the_reference_code():
+    """xrc_exp_se3 (host-only code of the product library; the pose composition of xrc_obj_fn_se3) against the reference's
+    own SkewMatrix / WedgeSkew / ExpSO3 / ExpSE3 lines (xregRotUtils.cpp:33-105, xregRigidUtils.cpp:40-85): same SE(3)
+    element to f32 rounding, from tiny to large rotations, and the Python host model too."""
+    import ctypes as C
+
+    from xreg_b200 import _lib
+    from xreg_b200.geometry import exp_se3
+
+    lib = _lib.load()
+    FP = C.POINTER(C.c_float)
+    rng = np.random.default_rng(5)
+    cases = [np.zeros(6), [0, 0, 0, 3, -4, 5], [1e-9, 0, 0, 1, 2, 3], [0.3, -0.2, 0.1, 10, -20, 30], [3.0, 0.5, -0.4, 1, 1, 1]]
+    cases += [np.concatenate([rng.normal(0, s, 3), rng.normal(0, 50, 3)]) for s in (1e-4, 0.05, 0.5, 1.5) for _ in range(10)]
+    worst = 0.0
+    for x in cases:
+        x32 = np.asarray(x, f32)
+        ref = ref_slice.exp_se3(x32).reshape(3, 4)
+        out = np.zeros(12, f32)
+        lib.xrc_exp_se3(x32.ctypes.data_as(FP), out.ctypes.data_as(FP))
+        got = out.reshape(3, 4)
+        scale = max(1.0, float(np.abs(ref[:, 3]).max()))
+        worst = max(worst, float(np.abs(got[:, :3] - ref[:, :3]).max()), float(np.abs(got[:, 3] - ref[:, 3]).max()) / scale)
+        model = exp_se3(x32.astype(np.float64))[:3]
+        assert np.abs(model[:, :3] - ref[:, :3]).max() <= 2e-6 and np.abs(model[:, 3] - ref[:, 3]).max() <= 2e-6 * scale
+        R = ref[:, :3].astype(np.float64)
+        assert np.abs(R @ R.T - np.eye(3)).max() <= 5e-6
+    assert worst <= 2e-6, worst
