@@ -612,6 +612,102 @@ def se3_slices():
     return out
 
 
+CAM_WRAPPER = r'''
+struct xref_cam_out
+{
+  uint32_t rows, cols;
+  float intrins_inv[9];
+  float extrins_inv[12];
+  float pinhole[3];
+  float focal_len;
+  int32_t frame_type;
+};
+
+static void export_cam(const xreg::CameraModel& m, xref_cam_out* o, float* intrins9, float* spacing2)
+{
+  o->rows = (uint32_t)m.num_det_rows;
+  o->cols = (uint32_t)m.num_det_cols;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j)
+    {
+      o->intrins_inv[3 * i + j] = m.intrins_inv(i, j);
+      if (intrins9)
+        intrins9[3 * i + j] = m.intrins(i, j);
+    }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 4; ++j)
+      o->extrins_inv[4 * i + j] = m.extrins_inv.matrix()(i, j);
+  for (int i = 0; i < 3; ++i)
+    o->pinhole[i] = m.pinhole_pt(i);
+  o->focal_len = m.focal_len;
+  o->frame_type = (int32_t)m.coord_frame_type;
+  if (spacing2)
+  {
+    spacing2[0] = m.det_row_spacing;
+    spacing2[1] = m.det_col_spacing;
+  }
+}
+
+extern "C" void xref_cam_setup_naive(xref_cam_out* o, float focal_len, uint32_t rows, uint32_t cols, float row_spacing,
+                                     float col_spacing, int32_t frame_type)
+{
+  xreg::CameraModel m;
+  m.coord_frame_type = static_cast<xreg::CameraModel::CameraCoordFrame>(frame_type);
+  m.setup(focal_len, rows, cols, row_spacing, col_spacing);
+  export_cam(m, o, nullptr, nullptr);
+}
+
+static xreg::CameraModel make_cam(const float intrins[9], const float extrins[16], uint32_t rows, uint32_t cols,
+                                  float row_spacing, float col_spacing, int32_t frame_type)
+{
+  xreg::CameraModel m;
+  m.coord_frame_type = static_cast<xreg::CameraModel::CameraCoordFrame>(frame_type);
+  xreg::Mat3x3 K;
+  xreg::Mat4x4 E;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j)
+      K(i, j) = intrins[3 * i + j];
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j)
+      E(i, j) = extrins[4 * i + j];
+  m.setup(K, E, rows, cols, row_spacing, col_spacing);
+  return m;
+}
+
+extern "C" void xref_cam_setup(xref_cam_out* o, const float intrins[9], const float extrins[16], uint32_t rows,
+                               uint32_t cols, float row_spacing, float col_spacing, int32_t frame_type)
+{
+  export_cam(make_cam(intrins, extrins, rows, cols, row_spacing, col_spacing, frame_type), o, nullptr, nullptr);
+}
+
+// DownsampleCameraModel of a camera made by setup(intrins, extrins): also returns the new intrinsics and spacings
+extern "C" void xref_cam_downsample(xref_cam_out* o, float intrins_out[9], float spacing_out[2], const float intrins[9],
+                                    const float extrins[16], uint32_t rows, uint32_t cols, float row_spacing,
+                                    float col_spacing, int32_t frame_type, float ds_factor, int force_even_dims)
+{
+  const xreg::CameraModel src = make_cam(intrins, extrins, rows, cols, row_spacing, col_spacing, frame_type);
+  export_cam(xreg::DownsampleCameraModel(src, ds_factor, force_even_dims != 0), o, intrins_out, spacing_out);
+}
+'''
+
+
+def cam_slices():
+    out = []
+    rel = "lib/transforms/xregRigidUtils.cpp"
+    ln = _lines(rel)
+    s, e = _cut_function(ln, r"^xreg::Mat4x4 xreg::SE3Inv\(const Mat4x4& T\)")
+    out.append((rel, s, e, ln[s:e + 1]))
+    rel = "lib/transforms/xregPerspectiveXform.cpp"
+    ln = _lines(rel)
+    for regex, n_closing in ((r"^xreg::CoordScalar xreg::FocalLenFromIntrins\(", 1), (r"^xreg::Mat3x3 xreg::MakeNaiveIntrins\(", 1),
+                             (r"^void xreg::CameraModel::setup\(const CoordScalar focal_len_arg", 1),
+                             (r"^void xreg::CameraModel::setup\(const Mat3x3& intrins_mat, const Mat4x4& extrins_mat", 1),
+                             (r"^xreg::CameraModel xreg::DownsampleCameraModel\(", 1)):
+        s, e = _cut_function(ln, regex, n_closing)
+        out.append((rel, s, e, ln[s:e + 1]))
+    return out
+
+
 UNITS = (
     # (library, prelude header, slice list function, C ABI wrapper)
     ("libxreg_refslice.so", "ref_pin_prelude.h", slices, WRAPPER),
@@ -620,7 +716,9 @@ UNITS = (
     ("libxreg_refslice_ncc.so", "ref_pin_ncc_prelude.h", ncc_slices, NCC_WRAPPER),
     ("libxreg_refslice_grad.so", "ref_pin_grad_prelude.h", grad_slices, GRAD_WRAPPER),
     ("libxreg_refslice_se3.so", "ref_pin_se3_prelude.h", se3_slices, SE3_WRAPPER),
+    ("libxreg_refslice_cam.so", "ref_pin_cam_prelude.h", cam_slices, CAM_WRAPPER),
 )
+CAM_LIB = os.path.join(OUT_DIR, "libxreg_refslice_cam.so")
 SE3_LIB = os.path.join(OUT_DIR, "libxreg_refslice_se3.so")
 GRAD_LIB = os.path.join(OUT_DIR, "libxreg_refslice_grad.so")
 NCC_LIB = os.path.join(OUT_DIR, "libxreg_refslice_ncc.so")

@@ -252,3 +252,37 @@ def exp_se3(x):
     out = np.zeros(12, np.float32)
     sl.xref_exp_se3(_fp(xx), _fp(out))
     return out
+
+
+# ---- camera set-up (oracle/_ref/libxreg_refslice_cam.so) ---------------------------------------------------------------
+def _cam_lib():
+    lib()
+    return C.CDLL(build_ref_slice.CAM_LIB)
+
+
+def cam_setup_naive(focal_len, rows, cols, row_spacing, col_spacing, frame_type=1) -> XoCam:
+    """CameraModel::setup(focal_len, nr, nc, rs, cs) of the reference (MakeNaiveIntrins inside)."""
+    s = XoCam()
+    _cam_lib().xref_cam_setup_naive(C.byref(s), C.c_float(focal_len), C.c_uint32(rows), C.c_uint32(cols),
+                                    C.c_float(row_spacing), C.c_float(col_spacing), C.c_int32(frame_type))
+    return s
+
+
+def cam_setup(intrins, extrins, rows, cols, row_spacing, col_spacing, frame_type=1) -> XoCam:
+    """CameraModel::setup(intrins, extrins, nr, nc, rs, cs) of the reference (FocalLenFromIntrins, SE3Inv inside)."""
+    s = XoCam()
+    k, e = _f32(intrins).reshape(9), _f32(extrins).reshape(16)
+    _cam_lib().xref_cam_setup(C.byref(s), _fp(k), _fp(e), C.c_uint32(rows), C.c_uint32(cols), C.c_float(row_spacing),
+                              C.c_float(col_spacing), C.c_int32(frame_type))
+    return s
+
+
+def cam_downsample(intrins, extrins, rows, cols, row_spacing, col_spacing, frame_type, ds_factor, force_even_dims=False):
+    """DownsampleCameraModel of the camera setup(intrins, extrins, ...) makes: (XoCam, intrins (3,3), (row, col) spacing)."""
+    s = XoCam()
+    k, e = _f32(intrins).reshape(9), _f32(extrins).reshape(16)
+    ko, sp = np.zeros(9, np.float32), np.zeros(2, np.float32)
+    _cam_lib().xref_cam_downsample(C.byref(s), _fp(ko), _fp(sp), _fp(k), _fp(e), C.c_uint32(rows), C.c_uint32(cols),
+                                   C.c_float(row_spacing), C.c_float(col_spacing), C.c_int32(frame_type),
+                                   C.c_float(ds_factor), C.c_int(1 if force_even_dims else 0))
+    return s, ko.reshape(3, 3), sp

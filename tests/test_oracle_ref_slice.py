@@ -337,3 +337,45 @@ def test_product_exp_se3_matches_the_reference_code():
         R = ref[:, :3].astype(np.float64)
         assert np.abs(R @ R.T - np.eye(3)).max() <= 5e-6
     assert worst <= 2e-6, worst
+
+
+def _cam_bytes(c):
+    return (int(c.rows), int(c.cols), bytes(c.intrins_inv), bytes(c.extrins_inv), bytes(c.pinhole), float(c.focal_len),
+            int(c.frame_type))
+
+
+def test_camera_setup_is_the_reference_code(xo):
+    """CameraModel::setup (naive; intrinsics + extrinsics), MakeNaiveIntrins, FocalLenFromIntrins, SE3Inv and
+    DownsampleCameraModel (xregPerspectiveXform.cpp:186-254,302-334,654-688; xregRigidUtils.cpp:29-38) compiled from the
+    reference's lines: the oracle's camera set-up and the product's host mirror (xreg_b200.geometry: what the tests and the
+    bench build their cameras with) produce the same cameras bit for bit, for all three frame types.  Eigen's 3x3 inverse
+    and `-1 * R^T * t` are conventions shared by stand-in and oracle; everything around them is the reference's."""
+    from xreg_b200.geometry import CameraModel as PyCam, downsample_camera_model
+
+    rng = np.random.default_rng(12)
+    for frame in (0, 1, 2):
+        for (f, nr, nc, rs, cs) in ((1020.0, 1536, 1536, 0.194, 0.194), (400.0, 80, 96, 1.6, 1.5), (655.5, 7, 1001, 0.31, 2.7)):
+            a = xo.cam_setup_naive(f, nr, nc, rs, cs, frame_type=frame)
+            b = ref_slice.cam_setup_naive(f, nr, nc, rs, cs, frame_type=frame)
+            assert _cam_bytes(a) == _cam_bytes(b)
+            py = PyCam(coord_frame_type=frame).setup(f, nr, nc, rs, cs)
+            assert _cam_bytes(xo.cam_struct(py)) == _cam_bytes(b)
+        for _ in range(6):
+            E = np.eye(4)
+            E[:3, :3] = np.linalg.qr(rng.standard_normal((3, 3)))[0]
+            E[:3, 3] = rng.uniform(-300, 300, 3)
+            K = np.array([[rng.uniform(-6000, -500), rng.uniform(-1, 1), rng.uniform(10, 800)],
+                          [0, rng.uniform(-6000, -500), rng.uniform(10, 800)], [0, 0, 1]])
+            nr, nc = int(rng.integers(8, 2000)), int(rng.integers(8, 2000))
+            rs, cs = float(rng.uniform(0.1, 2.0)), float(rng.uniform(0.1, 2.0))
+            a = xo.cam_setup(K, E, nr, nc, rs, cs, frame_type=frame)
+            b = ref_slice.cam_setup(K, E, nr, nc, rs, cs, frame_type=frame)
+            assert _cam_bytes(a) == _cam_bytes(b)
+            src = PyCam(coord_frame_type=frame).setup_intrins_extrins(K.astype(f32), E.astype(f32), nr, nc, rs, cs)
+            assert _cam_bytes(xo.cam_struct(src)) == _cam_bytes(b)
+            for ds, even in ((0.5, False), (0.125, True), (0.3125, False), (0.25, True)):
+                rb, kb, sp = ref_slice.cam_downsample(K, E, nr, nc, rs, cs, frame, ds, even)
+                d = downsample_camera_model(src, ds, even)
+                assert _cam_bytes(xo.cam_struct(d)) == _cam_bytes(rb), (frame, ds, even)
+                assert np.asarray(d.intrins, f32).tobytes() == kb.tobytes()
+                assert f32(d.det_row_spacing) == sp[0] and f32(d.det_col_spacing) == sp[1]

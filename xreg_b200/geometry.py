@@ -37,8 +37,15 @@ def se3_inv(T: np.ndarray) -> np.ndarray:
     T = np.asarray(T, dtype=f32)
     out = np.eye(4, dtype=f32)
     out[:3, :3] = T[:3, :3].T
-    out[:3, 3] = -(out[:3, :3] @ T[:3, 3])
+    # -1 * R^T * t with the products summed left to right in f32 (a BLAS matmul may fuse or reorder: 1 ulp off)
+    for r in range(3):
+        out[r, 3] = -_dot3(out[r, 0], out[r, 1], out[r, 2], T[0, 3], T[1, 3], T[2, 3])
     return out
+
+
+def _dot3(a0, a1, a2, b0, b1, b2) -> np.float32:
+    """(a0 b0 + a1 b1) + a2 b2 in f32, each operation rounded (Eigen's small fixed-size products, no FMA)."""
+    return f32(f32(f32(f32(a0) * f32(b0)) + f32(f32(a1) * f32(b1))) + f32(f32(a2) * f32(b2)))
 
 
 def skew(w: Sequence[float]) -> np.ndarray:
@@ -124,7 +131,9 @@ class CameraModel:
         if self.coord_frame_type in (kORIGIN_AT_FOCAL_PT_DET_POS_Z, kORIGIN_AT_FOCAL_PT_DET_NEG_Z):
             self.pinhole_pt = self.extrins_inv[:3, 3].copy()
         else:
-            self.pinhole_pt = (self.extrins_inv[:3, :3] @ np.array([0, 0, self.focal_len], dtype=f32) + self.extrins_inv[:3, 3]).astype(f32)
+            ei = self.extrins_inv
+            self.pinhole_pt = np.array([f32(_dot3(ei[r, 0], ei[r, 1], ei[r, 2], 0.0, 0.0, self.focal_len) + ei[r, 3])
+                                        for r in range(3)], dtype=f32)
         return self
 
     def to_xrc(self) -> _lib.XrcCam:
