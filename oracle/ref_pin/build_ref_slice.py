@@ -708,6 +708,48 @@ def cam_slices():
     return out
 
 
+ITK_WRAPPER = r'''
+// the two helpers RayCasterLineIntCPU::compute starts with, for an image given by its meta data
+extern "C" void xref_itk_volume_geometry(const uint64_t dims[3], const double origin[3], const double spacing[3],
+                                         const double direction[9], float aabb_min[3], float aabb_max[3],
+                                         float idx_to_phys12[12])
+{
+  itk::Image<float, 3> img;
+  for (int i = 0; i < 3; ++i)
+  {
+    img.size.s[i] = (std::size_t)dims[i];
+    img.origin.p[i] = origin[i];
+    img.spacing.p[i] = spacing[i];
+    for (int j = 0; j < 3; ++j)
+      img.direction.d[i][j] = direction[3 * i + j];
+  }
+  Eigen::Matrix<float, 3, 1> mn, mx;
+  std::tie(mn, mx) = xreg::ITKImageIndexBoundsAsEigen(&img);
+  const Eigen::Transform<float, 3, Eigen::Affine> t = xreg::ITKImagePhysicalPointTransformsAsEigen(&img);
+  for (int i = 0; i < 3; ++i)
+  {
+    aabb_min[i] = mn[i];
+    aabb_max[i] = mx[i];
+    for (int j = 0; j < 4; ++j)
+      idx_to_phys12[4 * i + j] = t.matrix()(i, j);
+  }
+}
+'''
+
+
+def itk_slices():
+    """Two function templates defined inside `namespace xreg { }` of a header: re-wrapped in that namespace."""
+    rel = "lib/itk/xregITKBasicImageUtils.h"
+    ln = _lines(rel)
+    out = []
+    for name in ("ITKImageIndexBoundsAsEigen", "ITKImagePhysicalPointTransformsAsEigen"):
+        k = next(i for i, x in enumerate(ln) if x.startswith(name + "("))
+        s = max(i for i in range(k) if ln[i].startswith("template <"))
+        e = next(i for i in range(k, len(ln)) if ln[i].rstrip() == "}")
+        out.append((rel, s, e, ["namespace xreg", "{"] + ln[s:e + 1] + ["}"]))
+    return out
+
+
 UNITS = (
     # (library, prelude header, slice list function, C ABI wrapper)
     ("libxreg_refslice.so", "ref_pin_prelude.h", slices, WRAPPER),
@@ -717,7 +759,9 @@ UNITS = (
     ("libxreg_refslice_grad.so", "ref_pin_grad_prelude.h", grad_slices, GRAD_WRAPPER),
     ("libxreg_refslice_se3.so", "ref_pin_se3_prelude.h", se3_slices, SE3_WRAPPER),
     ("libxreg_refslice_cam.so", "ref_pin_cam_prelude.h", cam_slices, CAM_WRAPPER),
+    ("libxreg_refslice_itk.so", "ref_pin_itk_prelude.h", itk_slices, ITK_WRAPPER),
 )
+ITK_LIB = os.path.join(OUT_DIR, "libxreg_refslice_itk.so")
 CAM_LIB = os.path.join(OUT_DIR, "libxreg_refslice_cam.so")
 SE3_LIB = os.path.join(OUT_DIR, "libxreg_refslice_se3.so")
 GRAD_LIB = os.path.join(OUT_DIR, "libxreg_refslice_grad.so")

@@ -286,3 +286,18 @@ def cam_downsample(intrins, extrins, rows, cols, row_spacing, col_spacing, frame
                                    C.c_float(row_spacing), C.c_float(col_spacing), C.c_int32(frame_type),
                                    C.c_float(ds_factor), C.c_int(1 if force_even_dims else 0))
     return s, ko.reshape(3, 3), sp
+
+
+def itk_volume_geometry(dims, origin, spacing, direction):
+    """ITKImageIndexBoundsAsEigen + ITKImagePhysicalPointTransformsAsEigen of the reference for an image with these meta
+    data (nx, ny, nz; doubles): (aabb_min (3,), aabb_max (3,), idx_to_phys (12,) row-major 3x4)."""
+    lib()
+    il = C.CDLL(build_ref_slice.ITK_LIB)
+    d = (C.c_uint64 * 3)(*[int(v) for v in dims])
+    o = np.ascontiguousarray(origin, dtype=np.float64).reshape(3)
+    sp = np.ascontiguousarray(spacing, dtype=np.float64).reshape(3)
+    dr = np.ascontiguousarray(direction, dtype=np.float64).reshape(9)
+    mn, mx, a = np.zeros(3, np.float32), np.zeros(3, np.float32), np.zeros(12, np.float32)
+    DP = C.POINTER(C.c_double)
+    il.xref_itk_volume_geometry(d, o.ctypes.data_as(DP), sp.ctypes.data_as(DP), dr.ctypes.data_as(DP), _fp(mn), _fp(mx), _fp(a))
+    return mn, mx, a
