@@ -106,6 +106,9 @@ int xrc_rc_set_layout(xrc_rc* rc, int layout);
 /* Tuning knob: CTA launch order, 0 = projection fastest (default), 1 = detector tile fastest. */
 int xrc_rc_set_cta_order(xrc_rc* rc, int order);
 
+/* Device memory the ray caster's volume representation occupies right now (all volumes; payload stacks, the f32 source
+ * kept for stacks built on demand, the empty-space maps).  Reported in bench.py's config. */
+int xrc_rc_volume_bytes(const xrc_rc* rc, uint64_t* bytes);
 /* Empty-space trimming, default on.  Samples whose 8 corner voxels are all zero add +0 to the
  * sequential f32 sum of xregRayCastLineIntCPU.cpp:270-279, so the sum kernel does not fetch the leading
  * and trailing samples of a ray that a per-volume block map proves to be zero (air around the body,
@@ -305,6 +308,12 @@ int xrc_obj_fn_multi(uint32_t n_dev, xrc_rc* const* rcs, xrc_sm* const* sms, uin
  * values bit for bit.  rc must be allocated for n_units projections, each metric for the poses of its view in range. */
 int xrc_obj_fn_units(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t n_views, uint32_t n_poses,
                      const float* cam_to_phys, uint32_t first_unit, uint32_t n_units, float* unit_sims_out);
+/* xrc_obj_fn_units without the final synchronise / read-back: hands over the poses and enqueues the ray cast and the
+ * metrics of the units in range on the context stream.  View v's values land in the first entries of its metric's
+ * device result vector (xrc_sm_device_sims) and host-mapped copy, for callers that gather on the device (NCCL
+ * all-gather straight from that vector) and synchronise once after their collective. */
+int xrc_obj_fn_units_enqueue(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t n_views, uint32_t n_poses,
+                             const float* cam_to_phys, uint32_t first_unit, uint32_t n_units);
 /* The partition xrc_obj_fn_multi uses (host only, needs no device): of view `view`, device `dev` evaluates the poses
  * [*first_pose, *first_pose + *count).  For sizing the per-device objects and for callers that shard by themselves. */
 int xrc_obj_fn_multi_share(uint32_t n_dev, uint32_t n_views, uint32_t n_poses, uint32_t dev, uint32_t view,

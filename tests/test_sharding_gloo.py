@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 import torch.multiprocessing as mp
 
+from xreg_b200 import regi
 from xreg_b200.regi import shard_bounds
 
 
@@ -21,6 +22,13 @@ def test_shard_bounds():
             assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
             sizes = [e - s for s, e in b]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_view_segments():
+    assert regi.view_segments(0, 300, 3, 100) == [(0, 0, 100), (1, 0, 100), (2, 0, 100)]
+    assert regi.view_segments(75, 113, 3, 100) == [(0, 75, 25), (1, 0, 13)]
+    assert regi.view_segments(13, 26, 1, 100) == [(0, 13, 13)]
+    assert regi.view_segments(5, 5, 2, 4) == []
 
 
 def _free_port():

@@ -93,6 +93,7 @@ SIGNATURES = {
     "xrc_rc_read_projs": [_VP, _U32, _U32, _FP],
     "xrc_rc_use_other_proj_buf": [_VP, _VP],
     "xrc_rc_ray_info": [_VP, _U32, _U8P, _U32P, C.POINTER(_U64)],
+    "xrc_rc_volume_bytes": [_VP, C.POINTER(_U64)],
     "xrc_rc_set_skip_empty": [_VP, C.c_int],
     "xrc_rc_fetched_samples": [_VP, _U32, C.POINTER(_U64)],
     "xrc_sm_create": [_VP, C.c_int, C.POINTER(_VP)],
@@ -119,6 +120,7 @@ SIGNATURES = {
     "xrc_obj_fn_multi": [_U32, C.POINTER(_VP), C.POINTER(_VP), _U32, _U32, _U32, _FP, _FP, _FP],
     "xrc_obj_fn_se3": [_VP, _U32, C.POINTER(_VP), _U32, _U32, _FP, _FP, _FP, _FP, _FP],
     "xrc_obj_fn_units": [_VP, _U32, C.POINTER(_VP), _U32, _U32, _FP, _U32, _U32, _FP],
+    "xrc_obj_fn_units_enqueue": [_VP, _U32, C.POINTER(_VP), _U32, _U32, _FP, _U32, _U32],
     "xrc_obj_fn_multi_share": [_U32, _U32, _U32, _U32, _U32, _U32P, _U32P],
     "xrc_exp_se3": [_FP, _FP],
 }

@@ -109,9 +109,9 @@ struct xrc_rc
   uint32_t rows = 0, cols = 0;
   uint32_t max_projs = 0, num_projs = 0;
   bool allocated = false;
-  float* d_buf = nullptr;     // projection buffer in use (own or shared)
-  float* d_buf_own = nullptr;
-  xrc_rc* other = nullptr;
+  float* d_buf_own = nullptr;   // own projection buffer; a borrower (use_other_proj_buf) has none
+  xrc_rc* other = nullptr;      // lender of the projection buffer, resolved at every use (rc_proj_buf)
+  uint32_t n_borrowers = 0;     // ray casters whose `other` is this one: it cannot be destroyed before them
   float* h_poses = nullptr;   // pinned staging: max_projs x 12 floats
   uint32_t* h_cam_idx = nullptr;
   float* d_poses = nullptr;
@@ -187,6 +187,23 @@ struct xrc_sm
   float divisor_f = 1.0f;
   int divide_f = 0;
 };
+
+// projection buffer in use: own, or the lender's as it is NOW (the lender may have been re-allocated since)
+static float* rc_proj_buf(const xrc_rc* rc)
+{
+  const xrc_rc* r = rc;
+  for (int hops = 0; r->other && hops < 8; ++hops)
+    r = r->other;
+  return r->d_buf_own;
+}
+
+static uint32_t rc_proj_capacity(const xrc_rc* rc)
+{
+  const xrc_rc* r = rc;
+  for (int hops = 0; r->other && hops < 8; ++hops)
+    r = r->other;
+  return r->allocated ? r->max_projs : 0u;
+}
 
 static int use_device(const xrc_ctx* ctx)
 {
@@ -301,6 +318,11 @@ int xrc_rc_destroy(xrc_rc* rc)
 {
   if (!rc)
     return XRC_OK;
+  if (rc->n_borrowers)
+    XRC_FAIL(XRC_ERR_INVALID, "xrc_rc_destroy: other ray casters still use this one's projection buffer "
+                              "(xrc_rc_use_other_proj_buf); destroy them first");
+  if (rc->other)
+    --rc->other->n_borrowers;
   cudaSetDevice(rc->ctx->device);
   cudaStreamSynchronize(rc->ctx->stream);
   rc_free_vols(rc);
@@ -334,21 +356,25 @@ static int rc_set_volumes_impl(xrc_rc* rc, uint32_t n, const float* const* ptrs,
 {
   XRC_CHECK_ARG(rc && ptrs && dims && idx_to_phys, "xrc_rc_set_volumes: null argument");
   XRC_CHECK_ARG(n > 0, "xrc_rc_set_volumes: need at least one volume");
+  // validate everything before touching the volumes in place: a failure leaves the previous ones usable
+  for (uint32_t i = 0; i < n; ++i)
+  {
+    XRC_CHECK_ARG(ptrs[i], "xrc_rc_set_volumes: null volume pointer");
+    for (int k = 0; k < 3; ++k)
+      XRC_CHECK_ARG(dims[i][k] >= 1 && dims[i][k] < (1u << 22), "xrc_rc_set_volumes: bad volume dimension");
+    XRC_CHECK_ARG(dims[i][0] * dims[i][1] < (1ull << 31), "xrc_rc_set_volumes: slice too large");
+  }
   XRC_TRY(use_device(rc->ctx));
   cudaStream_t st = rc->ctx->stream;
   XRC_CUDA(cudaStreamSynchronize(st));
-  rc_free_vols(rc);
-  rc->vols.resize(n);
-  for (uint32_t i = 0; i < n; ++i)
+  // the new volumes are built aside and swapped in only when all of them exist
+  std::vector<DeviceVolume> fresh(n);
+  int status = XRC_OK;
+  for (uint32_t i = 0; i < n && status == XRC_OK; ++i)
   {
-    DeviceVolume& v = rc->vols[i];
-    XRC_CHECK_ARG(ptrs[i], "xrc_rc_set_volumes: null volume pointer");
+    DeviceVolume& v = fresh[i];
     for (int k = 0; k < 3; ++k)
-    {
-      XRC_CHECK_ARG(dims[i][k] >= 1 && dims[i][k] < (1u << 22), "xrc_rc_set_volumes: bad volume dimension");
       v.dims[k] = dims[i][k];
-    }
-    XRC_CHECK_ARG(v.dims[0] * v.dims[1] < (1ull << 31), "xrc_rc_set_volumes: slice too large");
     // default: principal-axis stacks; volumes whose padded record count exceeds 32 bits use one XY-quad stack
     int layout = rc->layout;
     if (layout == XRC_LAYOUT_DEFAULT)
@@ -362,32 +388,50 @@ static int rc_set_volumes_impl(xrc_rc* rc, uint32_t n, const float* const* ptrs,
     const size_t nvox = (size_t)v.dims[0] * v.dims[1] * v.dims[2];
     const float* d_src = ptrs[i];
     float* staging = nullptr;
-    if (!on_device)
-    {
-      XRC_CUDA(cudaMalloc(&staging, nvox * sizeof(float)));
-      XRC_CUDA(cudaMemcpyAsync(staging, ptrs[i], nvox * sizeof(float), cudaMemcpyHostToDevice, st));
-      d_src = staging;
-    }
-    if (hu_lower)
-    {
-      // HU -> linear attenuation on the device before repacking (HUToLinAttFilter, lib/image/xregHUToLinAtt.cpp:45-69);
-      // a device-resident source must not be modified: convert a copy
-      if (!staging)
+    status = [&]() -> int {
+      if (!on_device)
       {
         XRC_CUDA(cudaMalloc(&staging, nvox * sizeof(float)));
-        XRC_CUDA(cudaMemcpyAsync(staging, ptrs[i], nvox * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        XRC_CUDA(cudaMemcpyAsync(staging, ptrs[i], nvox * sizeof(float), cudaMemcpyHostToDevice, st));
         d_src = staging;
       }
-      launch_hu_to_lin_att(staging, nvox, *hu_lower, st);
-    }
-    int s = repack_volume(d_src, &v, layout, st);
-    if (s == XRC_OK && layout == XRC_LAYOUT_PAX)
-      s = build_occupancy(d_src, &v, st);
+      if (hu_lower)
+      {
+        // HU -> linear attenuation on the device before repacking (HUToLinAttFilter, lib/image/xregHUToLinAtt.cpp:45-69);
+        // a device-resident source must not be modified: convert a copy
+        if (!staging)
+        {
+          XRC_CUDA(cudaMalloc(&staging, nvox * sizeof(float)));
+          XRC_CUDA(cudaMemcpyAsync(staging, ptrs[i], nvox * sizeof(float), cudaMemcpyDeviceToDevice, st));
+          d_src = staging;
+        }
+        launch_hu_to_lin_att(staging, nvox, *hu_lower, st);
+      }
+      int s = repack_volume(d_src, &v, layout, st);
+      if (s == XRC_ERR_NOMEM && rc->layout == XRC_LAYOUT_DEFAULT && layout == XRC_LAYOUT_PAX)
+      {
+        // not even the f32 copy the stacks are built from fits: one XY-quad stack instead (4x instead of up to 12x)
+        cudaGetLastError();
+        free_volume(&v);
+        layout = XRC_LAYOUT_QUAD;
+        s = repack_volume(d_src, &v, layout, st);
+      }
+      if (s == XRC_OK && layout == XRC_LAYOUT_PAX)
+        s = build_occupancy(d_src, &v, st);
+      return s;
+    }();
     cudaStreamSynchronize(st);
     if (staging)
-      cudaFree(staging);
-    XRC_TRY(s);
+      cudaFree(staging);   // on every exit path
   }
+  if (status != XRC_OK)
+  {
+    for (auto& v : fresh)
+      free_volume(&v);
+    return status;
+  }
+  rc_free_vols(rc);
+  rc->vols.swap(fresh);
   return XRC_OK;
 }
 
@@ -409,6 +453,8 @@ int xrc_rc_set_volumes_device(xrc_rc* rc, uint32_t n, const float* const* dev_pt
   return rc_set_volumes_impl(rc, n, dev_ptrs, dims, idx_to_phys, true);
 }
 
+static int rc_wait_staging(xrc_rc* rc);
+
 int xrc_rc_set_cameras(xrc_rc* rc, uint32_t n, const xrc_cam* cams)
 {
   XRC_CHECK_ARG(rc && cams && n > 0, "xrc_rc_set_cameras: bad argument");
@@ -425,6 +471,16 @@ int xrc_rc_set_cameras(xrc_rc* rc, uint32_t n, const xrc_cam* cams)
   XRC_TRY(use_device(rc->ctx));
   cudaStream_t st = rc->ctx->stream;
   XRC_CUDA(cudaStreamSynchronize(st));
+  if (n < rc->cams.size() && rc->allocated)
+  {
+    // stored per-projection camera indices may now be out of range: back to camera 0 until the caller sets them again
+    // (a caller's device index array, xrc_rc_set_poses_device, is clamped inside the kernels)
+    XRC_TRY(rc_wait_staging(rc));
+    for (uint32_t p = 0; p < rc->max_projs; ++p)
+      if (rc->h_cam_idx[p] >= n)
+        rc->h_cam_idx[p] = 0;
+    XRC_CUDA(cudaMemcpy(rc->d_cam_idx, rc->h_cam_idx, sizeof(uint32_t) * rc->max_projs, cudaMemcpyHostToDevice));
+  }
   rc->cams.assign(cams, cams + n);
   rc->rows = cams[0].rows;
   rc->cols = cams[0].cols;
@@ -459,14 +515,11 @@ int xrc_rc_allocate(xrc_rc* rc, uint32_t max_projs)
   {
     XRC_CUDA(cudaMalloc(&rc->d_buf_own, npix * max_projs * sizeof(float)));
     XRC_CUDA(cudaMemsetAsync(rc->d_buf_own, 0, npix * max_projs * sizeof(float), rc->ctx->stream));
-    rc->d_buf = rc->d_buf_own;
   }
   else
   {
-    XRC_CHECK_ARG(rc->other->allocated && rc->other->max_projs >= max_projs && rc->other->rows == rc->rows &&
-                      rc->other->cols == rc->cols,
+    XRC_CHECK_ARG(rc_proj_capacity(rc) >= max_projs && rc->other->rows == rc->rows && rc->other->cols == rc->cols,
                   "xrc_rc_allocate: shared projection buffer is too small");
-    rc->d_buf = rc->other->d_buf;
   }
   XRC_CUDA(cudaMalloc(&rc->d_poses, sizeof(float) * 12 * max_projs));
   XRC_CUDA(cudaMalloc(&rc->d_cam_idx, sizeof(uint32_t) * max_projs));
@@ -649,6 +702,74 @@ int xrc_rc_set_bg_projs(xrc_rc* rc, const float* const* host_imgs, int use_bg)
   return XRC_OK;
 }
 
+// XRC_LAYOUT_PAX stacks are built on demand.  The kernel decides per CTA which stack it wants (the principal axis of
+// the ray through its tile centre, pax_cta_prologue); a CTA whose stack is missing uses a built one (same samples,
+// worse access pattern) and reports the wish through host-mapped memory, which the next compute() honours.  So that
+// the common case never runs on the wrong stack, the host also predicts the wishes of the poses it can see from the
+// rays through the detector centre and corners (plain f32; a wrong guess only costs speed).
+static int rc_prepare_stacks(xrc_rc* rc, uint32_t vol_idx)
+{
+  DeviceVolume& v = rc->vols[vol_idx];
+  if (v.layout != XRC_LAYOUT_PAX || (v.pax[0] && v.pax[1] && v.pax[2]))
+    return XRC_OK;
+  bool need[3] = {false, false, false};
+  if (v.h_want)
+    for (int k = 0; k < 3; ++k)
+      if (*(volatile uint32_t*)(v.h_want + k))
+      {
+        need[k] = true;
+        v.h_want[k] = 0u;
+      }
+  if (!rc->ext_poses)
+  {
+    const float* A = v.phys_to_idx;
+    for (uint32_t p = 0; p < rc->num_projs; ++p)
+    {
+      const float* P = rc->h_poses + 12 * (size_t)p;
+      const xrc_cam& cam = rc->cams[std::min<size_t>(rc->h_cam_idx[p], rc->cams.size() - 1)];
+      float X[12];
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 4; ++c)
+          X[4 * r + c] = A[4 * r] * P[c] + A[4 * r + 1] * P[4 + c] + A[4 * r + 2] * P[8 + c] + ((c == 3) ? A[4 * r + 3] : 0.0f);
+      float src[3];
+      for (int r = 0; r < 3; ++r)
+        src[r] = X[4 * r] * cam.pinhole[0] + X[4 * r + 1] * cam.pinhole[1] + X[4 * r + 2] * cam.pinhole[2] + X[4 * r + 3];
+      const float det_z = ((cam.frame_type == 1) ? -1.0f : 1.0f) * cam.focal_len;
+      static const float gx[5] = {0.5f, 0.f, 1.f, 0.f, 1.f}, gy[5] = {0.5f, 0.f, 0.f, 1.f, 1.f};
+      for (int g = 0; g < 5; ++g)
+      {
+        const float col = (float)(cam.cols - 1) * gx[g], row = (float)(cam.rows - 1) * gy[g];
+        float cv[3], w[3], d[3];
+        for (int r = 0; r < 3; ++r)
+          cv[r] = det_z * (cam.intrins_inv[3 * r] * col + cam.intrins_inv[3 * r + 1] * row + cam.intrins_inv[3 * r + 2]);
+        if (cam.frame_type == 2)
+          cv[2] -= cam.focal_len;
+        for (int r = 0; r < 3; ++r)
+          w[r] = cam.extrins_inv[4 * r] * cv[0] + cam.extrins_inv[4 * r + 1] * cv[1] + cam.extrins_inv[4 * r + 2] * cv[2] +
+                 cam.extrins_inv[4 * r + 3];
+        for (int r = 0; r < 3; ++r)
+          d[r] = fabsf(X[4 * r] * w[0] + X[4 * r + 1] * w[1] + X[4 * r + 2] * w[2] + X[4 * r + 3] - src[r]);
+        need[(d[2] >= d[0] && d[2] >= d[1]) ? 2 : ((d[1] >= d[0]) ? 1 : 0)] = true;
+      }
+    }
+  }
+  for (int k = 0; k < 3; ++k)
+  {
+    if (!need[k] || v.pax[k])
+      continue;
+    const int s = build_pax_stack(&v, k, rc->ctx->stream);
+    if (s == XRC_ERR_NOMEM && (v.pax[0] || v.pax[1] || v.pax[2]))
+    {
+      cudaGetLastError();   // no room for another stack: the kernel keeps falling back to one that exists
+      continue;
+    }
+    XRC_TRY(s);
+  }
+  if (!(v.pax[0] || v.pax[1] || v.pax[2]))
+    XRC_TRY(build_pax_stack(&v, 2, rc->ctx->stream));   // poses only the device knows: start anywhere, the kernel reports
+  return XRC_OK;
+}
+
 static void rc_fill_args(xrc_rc* rc, uint32_t vol_idx, DrrArgs* a)
 {
   const DeviceVolume& v = rc->vols[vol_idx];
@@ -660,13 +781,14 @@ static void rc_fill_args(xrc_rc* rc, uint32_t vol_idx, DrrArgs* a)
   a->nz = (int)v.dims[2];
   memcpy(a->phys_to_idx, v.phys_to_idx, sizeof(float) * 12);
   a->cams = rc->d_cams;
+  a->n_cams = (uint32_t)rc->cams.size();
   a->poses = rc->ext_poses ? rc->ext_poses : rc->d_poses;
   a->cam_idx = rc->ext_poses ? rc->ext_cam_idx : rc->d_cam_idx;
   a->n_projs = rc->num_projs;
   a->rows = rc->rows;
   a->cols = rc->cols;
   a->step_size = rc->step_size;
-  a->out = rc->d_buf;
+  a->out = rc_proj_buf(rc);
   a->init_mode = rc->use_bg ? 1 : ((rc->store_method == XRC_STORE_REPLACE) ? 0 : 2);
   a->default_bg = rc->default_bg;
   a->bg = rc->d_bg;
@@ -678,6 +800,7 @@ static void rc_fill_args(xrc_rc* rc, uint32_t vol_idx, DrrArgs* a)
     a->pax_sb[k] = v.pax_sb[k];
     a->pax_sc[k] = v.pax_sc[k];
   }
+  a->pax_want = v.h_want;
   if (rc->inline_poses && !rc->ext_poses && rc->num_projs <= kInlinePoses)
   {
     a->use_inline = 1;
@@ -699,17 +822,30 @@ int xrc_rc_compute(xrc_rc* rc, uint32_t vol_idx)
   XRC_CHECK_ARG(rc, "null ray caster");
   XRC_CHECK_ARG(rc->allocated, "xrc_rc_compute: resources not allocated (xregRayCastLineIntCPU.cpp:296)");
   XRC_CHECK_ARG(vol_idx < rc->vols.size(), "xrc_rc_compute: volume index out of range");
+  XRC_CHECK_ARG(rc_proj_buf(rc) && rc->num_projs <= rc_proj_capacity(rc),
+                "xrc_rc_compute: the shared projection buffer (xrc_rc_use_other_proj_buf) is gone or too small");
   XRC_TRY(use_device(rc->ctx));
+  XRC_TRY(rc_prepare_stacks(rc, vol_idx));
   DrrArgs a;
   rc_fill_args(rc, vol_idx, &a);
   return launch_drr(a, rc->vols[vol_idx].layout, rc->kernel_id, rc->ctx->stream);
+}
+
+int xrc_rc_volume_bytes(const xrc_rc* rc, uint64_t* bytes)
+{
+  XRC_CHECK_ARG(rc && bytes, "null argument");
+  uint64_t b = 0;
+  for (const auto& v : rc->vols)
+    b += v.bytes + (v.occ ? sizeof(uint32_t) * (uint64_t)v.occ_wx * v.occ_ny * v.occ_nz : 0);
+  *bytes = b;
+  return XRC_OK;
 }
 
 int xrc_rc_device_buf(xrc_rc* rc, float** dev_ptr)
 {
   XRC_CHECK_ARG(rc && dev_ptr, "null argument");
   XRC_CHECK_ARG(rc->allocated, "xrc_rc_device_buf: allocate first");
-  *dev_ptr = rc->d_buf;
+  *dev_ptr = rc_proj_buf(rc);
   return XRC_OK;
 }
 
@@ -720,7 +856,7 @@ int xrc_rc_read_projs(xrc_rc* rc, uint32_t first, uint32_t count, float* host_ds
   XRC_CHECK_ARG((uint64_t)first + count <= rc->max_projs, "xrc_rc_read_projs: range exceeds capacity");
   XRC_TRY(use_device(rc->ctx));
   const size_t npix = (size_t)rc->rows * rc->cols;
-  XRC_CUDA(cudaMemcpyAsync(host_dst, rc->d_buf + first * npix, count * npix * sizeof(float), cudaMemcpyDeviceToHost,
+  XRC_CUDA(cudaMemcpyAsync(host_dst, rc_proj_buf(rc) + first * npix, count * npix * sizeof(float), cudaMemcpyDeviceToHost,
                            rc->ctx->stream));
   XRC_CUDA(cudaStreamSynchronize(rc->ctx->stream));
   return XRC_OK;
@@ -731,7 +867,12 @@ int xrc_rc_use_other_proj_buf(xrc_rc* rc, xrc_rc* other)
   XRC_CHECK_ARG(rc && other && rc != other, "xrc_rc_use_other_proj_buf: bad argument");
   XRC_CHECK_ARG(rc->ctx == other->ctx, "xrc_rc_use_other_proj_buf: ray casters live on different contexts");
   XRC_CHECK_ARG(!rc->allocated, "xrc_rc_use_other_proj_buf: must be called before allocation");
+  for (const xrc_rc* r = other; r; r = r->other)
+    XRC_CHECK_ARG(r != rc, "xrc_rc_use_other_proj_buf: circular buffer sharing");
+  if (rc->other)
+    --rc->other->n_borrowers;
   rc->other = other;
+  ++other->n_borrowers;
   return XRC_OK;
 }
 
@@ -803,6 +944,11 @@ int xrc_rc_fetched_samples(xrc_rc* rc, uint32_t vol_idx, uint64_t* fetched)
   unsigned long long* d_cnt = nullptr;
   XRC_CUDA(cudaMalloc(&d_cnt, sizeof(unsigned long long)));
   cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), st);
+  if (rc_prepare_stacks(rc, vol_idx) != XRC_OK)
+  {
+    cudaFree(d_cnt);
+    return XRC_ERR_CUDA;
+  }
   DrrArgs a;
   rc_fill_args(rc, vol_idx, &a);
   a.sample_counter = d_cnt;
@@ -1322,9 +1468,10 @@ static int sm_source(xrc_sm* sm, const float** src)
   cudaStream_t st = sm->ctx->stream;
   if (sm->rc)
   {
-    XRC_CHECK_ARG((uint64_t)sm->proj_offset + sm->n_imgs <= sm->rc->max_projs,
+    XRC_CHECK_ARG((uint64_t)sm->proj_offset + sm->n_imgs <= sm->rc->max_projs &&
+                      (uint64_t)sm->proj_offset + sm->n_imgs <= rc_proj_capacity(sm->rc),
                   "metric reads beyond the ray caster's projection buffer");
-    *src = sm->rc->d_buf + (size_t)sm->proj_offset * npix;
+    *src = rc_proj_buf(sm->rc) + (size_t)sm->proj_offset * npix;
   }
   else if (sm->host_src)
   {
@@ -1865,10 +2012,10 @@ static int obj_fn_finish_units(xrc_rc* rc, xrc_sm* const* sms, uint32_t n_views,
   return XRC_OK;
 }
 
-int xrc_obj_fn_units(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t n_views, uint32_t n_poses,
-                     const float* cam_to_phys, uint32_t first_unit, uint32_t n_units, float* unit_sims_out)
+int xrc_obj_fn_units_enqueue(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t n_views, uint32_t n_poses,
+                             const float* cam_to_phys, uint32_t first_unit, uint32_t n_units)
 {
-  XRC_CHECK_ARG(rc && sms && cam_to_phys && unit_sims_out && n_views > 0, "xrc_obj_fn_units: bad argument");
+  XRC_CHECK_ARG(rc && sms && cam_to_phys && n_views > 0, "xrc_obj_fn_units: bad argument");
   XRC_CHECK_ARG((uint64_t)n_views * n_poses < (1ull << 32) && (uint64_t)first_unit + n_units <= (uint64_t)n_views * n_poses,
                 "xrc_obj_fn_units: unit range outside the n_views x n_poses projection list");
   if (!n_units)
@@ -1882,7 +2029,17 @@ int xrc_obj_fn_units(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t 
     if (p1 > p0)
       XRC_TRY(xrc_sm_compute(sms[v]));
   }
-  return obj_fn_finish_units(rc, sms, n_views, n_poses, u0, u1, unit_sims_out, u0);
+  return XRC_OK;
+}
+
+int xrc_obj_fn_units(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t n_views, uint32_t n_poses,
+                     const float* cam_to_phys, uint32_t first_unit, uint32_t n_units, float* unit_sims_out)
+{
+  XRC_CHECK_ARG(unit_sims_out, "xrc_obj_fn_units: null output");
+  XRC_TRY(xrc_obj_fn_units_enqueue(rc, vol_idx, sms, n_views, n_poses, cam_to_phys, first_unit, n_units));
+  if (!n_units)
+    return XRC_OK;
+  return obj_fn_finish_units(rc, sms, n_views, n_poses, first_unit, first_unit + n_units, unit_sims_out, first_unit);
 }
 
 int xrc_obj_fn_multi(uint32_t n_dev, xrc_rc* const* rcs, xrc_sm* const* sms, uint32_t vol_idx, uint32_t n_views,

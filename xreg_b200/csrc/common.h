@@ -65,9 +65,15 @@ struct DeviceVolume
   size_t bytes = 0;
   // XRC_LAYOUT_PAX: one padded XY-quad record stack per principal ray axis k
   // (slow axis c = k, fast a = (k+1)%3, mid b = (k+2)%3); see drr.cu
+  // Stacks are built ON DEMAND (build_pax_stack): only the principal axes the current cameras x poses can select
+  // exist, from the f32 copy `src` kept until all three are built (a single-view registration lives on one stack:
+  // 4x + 1x the volume instead of 12x).  A CTA whose preferred stack is missing uses any built one (same samples).
   void* pax[3] = {nullptr, nullptr, nullptr};
   uint32_t pax_sb[3] = {0, 0, 0};   // record strides of the mid / slow axis
   uint32_t pax_sc[3] = {0, 0, 0};
+  float* src = nullptr;             // x-fastest f32 volume on the device (PAX only; freed once all stacks exist)
+  uint32_t* h_want = nullptr;       // 3 words of host-mapped pinned memory: a CTA that had to fall back from stack k
+                                    // stores 1 to word k; the next compute() builds that stack (drr.cu, api.cu)
   // empty-space map (drr.cu, "empty-space trimming"): one bit per 8^3-voxel block, set when any voxel of the
   // block or of its 26 neighbours is non-zero; x-fastest, 32 blocks per word
   uint32_t* occ = nullptr;
@@ -85,6 +91,7 @@ struct DrrArgs
   int nx, ny, nz;             // volume dims
   float phys_to_idx[12];
   const xrc_cam* cams;        // device
+  uint32_t n_cams;            // camera indices read from device memory are clamped to n_cams - 1
   const float* poses;         // device, n_projs x 12
   const uint32_t* cam_idx;    // device
   uint32_t n_projs;
@@ -97,7 +104,8 @@ struct DrrArgs
   const float* bg;            // n_cams x rows x cols
   unsigned long long* sample_counter;  // optional
   int order;                  // 0: projection fastest over CTAs, 1: tile fastest
-  const void* pax[3];         // XRC_LAYOUT_PAX stacks
+  const void* pax[3];         // XRC_LAYOUT_PAX stacks (nullptr: not built yet)
+  uint32_t* pax_want;         // host-mapped: word k := 1 when a CTA wanted the missing stack k
   uint32_t pax_sb[3], pax_sc[3];
   int variant;                // tuning: bit0 = scalar (non-packed) FP32 math in the PAX kernel
   uint8_t* ray_mask;          // ray-info kernel only
@@ -113,6 +121,7 @@ struct DrrArgs
 };
 
 int repack_volume(const float* d_linear, DeviceVolume* v, int layout, cudaStream_t st);
+int build_pax_stack(DeviceVolume* v, int k, cudaStream_t st);   // no-op when stack k exists
 int build_occupancy(const float* d_linear, DeviceVolume* v, cudaStream_t st);
 void launch_hu_to_lin_att(float* d_vol, size_t n, float hu_lower, cudaStream_t st);
 void free_volume(DeviceVolume* v);

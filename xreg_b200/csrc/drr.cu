@@ -58,7 +58,8 @@ struct ProjConst
 
 __device__ __forceinline__ uint32_t proj_cam_index(const DrrArgs& a, uint32_t proj)
 {
-  return a.use_inline ? a.inl_cam[proj] : a.cam_idx[proj];
+  // host-supplied indices are validated by the ABI; a caller's device array (xrc_rc_set_poses_device) is not, so clamp
+  return min(a.use_inline ? a.inl_cam[proj] : a.cam_idx[proj], a.n_cams - 1u);
 }
 
 __device__ __forceinline__ void compute_proj_const(const DrrArgs& a, const xrc_cam& cam, uint32_t proj, ProjConst* pc)
@@ -834,7 +835,15 @@ __device__ __forceinline__ uint32_t pax_cta_prologue(const DrrArgs& a, PaxCta& s
         iv[q][r] = X[4 * r] * w[0] + X[4 * r + 1] * w[1] + X[4 * r + 2] * w[2] + ((q == 0) ? X[4 * r + 3] : 0.0f);
     }
     const float dx = fabsf(iv[0][0] - sh.pc.p[0]), dy = fabsf(iv[0][1] - sh.pc.p[1]), dz = fabsf(iv[0][2] - sh.pc.p[2]);
-    const int k = (dz >= dx && dz >= dy) ? 2 : ((dy >= dx) ? 1 : 0);
+    int k = (dz >= dx && dz >= dy) ? 2 : ((dy >= dx) ? 1 : 0);
+    // stacks are built on demand from a host-side estimate of the axes needed: a missing one is replaced by any
+    // built one (the samples are the same, only the access pattern is worse)
+    if (!a.pax[k])
+    {
+      if (a.pax_want)
+        *(volatile uint32_t*)(a.pax_want + k) = 1u;   // host-mapped: the next compute() builds stack k
+      k = a.pax[(k + 1) % 3] ? (k + 1) % 3 : (k + 2) % 3;
+    }
     const int ka = (k == 2) ? 0 : k + 1;
     sh.axis = k;
     // quarter-warps (8 consecutive lanes) run along the detector direction that moves fastest along
@@ -1355,8 +1364,42 @@ int build_occupancy(const float* d_linear, DeviceVolume* v, cudaStream_t st)
   return XRC_OK;
 }
 
+int build_pax_stack(DeviceVolume* v, int k, cudaStream_t st)
+{
+  if (v->pax[k])
+    return XRC_OK;
+  if (!v->src)
+    XRC_FAIL(XRC_ERR_INVALID, "build_pax_stack: the f32 source of the volume is gone");
+  const int n[3] = {(int)v->dims[0], (int)v->dims[1], (int)v->dims[2]};
+  size_t A = (size_t)n[(k + 1) % 3] + 1, B = (size_t)n[(k + 2) % 3] + 1;
+  const size_t C = (size_t)n[k] + 2;
+  pax_pitch(A, B);
+  XRC_CUDA(cudaMalloc(&v->pax[k], sizeof(float4) * A * B * C));
+  v->pax_sb[k] = (uint32_t)A;
+  v->pax_sc[k] = (uint32_t)(A * B);
+  v->bytes += sizeof(float4) * A * B * C;
+  repack_pax_kernel<<<148 * 8, 256, 0, st>>>(v->src, (float4*)v->pax[k], n[0], n[1], n[2], k, (int)A, (int)B);
+  count_launch();
+  XRC_CUDA(cudaGetLastError());
+  if (v->pax[0] && v->pax[1] && v->pax[2])
+  {
+    // all three exist: the f32 copy has served its purpose
+    XRC_CUDA(cudaStreamSynchronize(st));
+    v->bytes -= sizeof(float) * (size_t)n[0] * n[1] * n[2];
+    cudaFree(v->src);
+    v->src = nullptr;
+  }
+  return XRC_OK;
+}
+
 void free_volume(DeviceVolume* v)
 {
+  if (v->src)
+    cudaFree(v->src);
+  v->src = nullptr;
+  if (v->h_want)
+    cudaFreeHost(v->h_want);
+  v->h_want = nullptr;
   if (v->occ)
     cudaFree(v->occ);
   v->occ = nullptr;
@@ -1451,8 +1494,8 @@ int repack_volume(const float* d_linear, DeviceVolume* v, int layout, cudaStream
     }
     case XRC_LAYOUT_PAX:
     {
+      // the stacks themselves are built on demand (build_pax_stack) from a device copy of the f32 volume
       const int n[3] = {nx, ny, nz};
-      v->bytes = 0;
       for (int k = 0; k < 3; ++k)
       {
         size_t A = (size_t)n[(k + 1) % 3] + 1, B = (size_t)n[(k + 2) % 3] + 1;
@@ -1460,13 +1503,13 @@ int repack_volume(const float* d_linear, DeviceVolume* v, int layout, cudaStream
         pax_pitch(A, B);
         if (A * B * C >= (1ull << 32))
           XRC_FAIL(XRC_ERR_UNSUPPORTED, "volume too large for the PAX layout (record index must fit 32 bits)");
-        XRC_CUDA(cudaMalloc(&v->pax[k], sizeof(float4) * A * B * C));
-        v->pax_sb[k] = (uint32_t)A;
-        v->pax_sc[k] = (uint32_t)(A * B);
-        v->bytes += sizeof(float4) * A * B * C;
-        repack_pax_kernel<<<grid, block, 0, st>>>(d_linear, (float4*)v->pax[k], nx, ny, nz, k, (int)A, (int)B);
-        count_launch();
       }
+      const size_t nb = sizeof(float) * (size_t)nx * ny * nz;
+      XRC_CUDA(cudaMalloc(&v->src, nb));
+      XRC_CUDA(cudaMemcpyAsync(v->src, d_linear, nb, cudaMemcpyDeviceToDevice, st));
+      v->bytes = nb;
+      XRC_CUDA(cudaHostAlloc(&v->h_want, 3 * sizeof(uint32_t), cudaHostAllocMapped | cudaHostAllocPortable));
+      v->h_want[0] = v->h_want[1] = v->h_want[2] = 0u;
       break;
     }
     default: XRC_FAIL(XRC_ERR_INVALID, "unknown volume layout");

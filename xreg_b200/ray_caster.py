@@ -384,6 +384,12 @@ class RayCasterLineIntCUDA:
                                         steps.ctypes.data_as(C.POINTER(C.c_uint32)), C.byref(S)))
         return mask, steps, int(S.value)
 
+    def volume_bytes(self) -> int:
+        """Device bytes of the volume representation right now (PAX stacks are built on demand)."""
+        n = C.c_uint64()
+        check(self._lib.xrc_rc_volume_bytes(self.handle, C.byref(n)))
+        return int(n.value)
+
     def set_skip_empty(self, enable: bool) -> None:
         """Empty-space trimming of the sum kernel (exact, default on); off only for measurement."""
         check(self._lib.xrc_rc_set_skip_empty(self.handle, 1 if enable else 0))

@@ -127,6 +127,20 @@ class Intensity2D3DObjFn:
         self._cur_pop = -1   # the library re-sized / re-bound the objects
         return out
 
+    def enqueue_units(self, poses: np.ndarray, first_unit: int, n_units: int) -> None:
+        """eval_units without the synchronise / read-back (xrc_obj_fn_units_enqueue): view v's values are left in the
+        first entries of self.sims[v]'s device result vector, for a gather on the device (ShardedDeviceObjFn)."""
+        p12 = to12(poses) if np.asarray(poses).ndim == 3 else np.ascontiguousarray(poses, dtype=f32).reshape(-1, 12)
+        n = p12.shape[0]
+        if n_units == 0:
+            return
+        self.rc._flush_params()   # the library checks the chunk against the allocated capacity
+        FP = C.POINTER(C.c_float)
+        _lib.check(self._lib.xrc_obj_fn_units_enqueue(self.rc.handle, 0, self._sm_arr, self.n_views, n,
+                                                      p12.ctypes.data_as(FP), int(first_unit), int(n_units)))
+        self.rc._poses_dirty = False
+        self._cur_pop = -1   # the library re-sized / re-bound the objects
+
     def close(self) -> None:
         """Destroy the metrics and the ray caster (before their Context is closed)."""
         for sm in self.sims:
@@ -339,3 +353,89 @@ class ShardedObjFn:
         dist.all_gather(parts, send, group=self.group)
         recv = torch.stack(parts).cpu().numpy()
         return np.concatenate([recv[r, : hi - lo] for r, (lo, hi) in enumerate(bounds)]).astype(f32)
+
+
+def view_segments(b: int, e: int, n_views: int, n: int) -> List[Tuple[int, int, int]]:
+    """The runs (view, first pose, count) that the units [b, e) of the camera-major list u = view * n + pose cover."""
+    out = []
+    for v in range(n_views):
+        lo, hi = max(b, v * n), min(e, (v + 1) * n)
+        if hi > lo:
+            out.append((v, lo - v * n, hi - lo))
+    return out
+
+
+class ShardedDeviceObjFn:
+    """The (view, pose)-sharded objective of a torch.distributed job with one rank per GPU, gathered ON the device:
+    the population of `n` poses x n_views views is the camera-major unit list of the reference, cut into
+    world_size contiguous balanced chunks (100 poses on 8 ranks: 13 13 13 13 12 12 12 12); every rank ray casts and
+    scores only its chunk (xrc_obj_fn_units_enqueue: poses H2D from the library's pinned staging, kernels, no host
+    synchronisation), the per-view scalars are all-gathered straight out of the metrics' device result vectors (NCCL
+    over NVLink, `width` floats per rank), copied to pinned host memory, and the stream is synchronised ONCE.  Every
+    rank returns the full (n,) vector; values are bitwise those of the single-GPU objective (a pose's value does not
+    depend on its batch).  The volume and fixed images are replicated; there is no other data-path collective."""
+
+    def __init__(self, fn: Intensity2D3DObjFn, rank: int, world_size: int, group=None):
+        import torch
+
+        self.fn, self.rank, self.world_size, self.group = fn, int(rank), int(world_size), group
+        self.n_views = fn.n_views
+        self.device = torch.device("cuda", fn.ctx.device)
+        self.stream = torch.cuda.ExternalStream(fn.ctx.stream, device=self.device)
+        cap = fn.max_pop * self.n_views
+        self._send = torch.zeros(cap, dtype=torch.float32, device=self.device)
+        self._recv = torch.zeros(cap * self.world_size, dtype=torch.float32, device=self.device)
+        self._host = torch.zeros(cap * self.world_size, dtype=torch.float32).pin_memory()
+        self._sims = [device_vector(sm.device_sims(), fn.max_pop, self.device) for sm in fn.sims]
+        self.per_view: Optional[np.ndarray] = None
+
+    def enqueue(self, poses: np.ndarray):
+        """Everything but the final synchronise: returns (bounds, width) for collect()."""
+        import torch
+        import torch.distributed as dist
+
+        n = np.asarray(poses).shape[0]
+        bounds = unit_chunks(self.n_views * n, self.world_size)
+        width = max(hi - lo for lo, hi in bounds)
+        b, e = bounds[self.rank]
+        with torch.cuda.stream(self.stream):
+            self.fn.enqueue_units(poses, b, e - b)
+            segs = view_segments(b, e, self.n_views, n)
+            if len(segs) == 1 and width <= self.fn.max_pop:
+                send = self._sims[segs[0][0]][:width]          # zero copy: the metric's own result vector
+            else:
+                send, off = self._send[:width], 0
+                for v, _, cnt in segs:
+                    send[off:off + cnt].copy_(self._sims[v][:cnt])
+                    off += cnt
+            recv = self._recv[: width * self.world_size]
+            if self.world_size > 1:
+                dist.all_gather_into_tensor(recv, send, group=self.group)
+            else:
+                recv.copy_(send)
+            self._host[: width * self.world_size].copy_(recv, non_blocking=True)
+        return bounds, width
+
+    def collect(self, bounds, width: int, n: int) -> np.ndarray:
+        self.stream.synchronize()
+        h = self._host.numpy()
+        flat = np.concatenate([h[r * width: r * width + (hi - lo)] for r, (lo, hi) in enumerate(bounds)]).astype(f32)
+        self.per_view = flat.reshape(self.n_views, n)
+        return combine_mean(self.per_view) if self.n_views > 1 else self.per_view[0].copy()
+
+    def __call__(self, poses: np.ndarray) -> np.ndarray:
+        n = np.asarray(poses).shape[0]
+        if n == 0:
+            return np.zeros(0, dtype=f32)
+        bounds, width = self.enqueue(poses)
+        return self.collect(bounds, width, n)
+
+
+def device_vector(ptr: int, n: int, device):
+    """Zero-copy torch view of n device floats at `ptr` (memory owned by the library)."""
+    import torch
+
+    class _Ptr:
+        __cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+    return torch.as_tensor(_Ptr(), device=device)
