@@ -181,9 +181,12 @@ void xreg::RayCasterLineIntCUDA::push_params_and_poses()
     CheckXRC(xrc_rc_set_bg_projs(rc_, bgs.data(), 1));
     this->bg_projs_updated_ = false;
   }
-  else if (!this->use_bg_projs_)
+  else
   {
-    CheckXRC(xrc_rc_set_bg_projs(rc_, nullptr, 0));
+    // set_use_bg_projs() only flips the flag in the reference, and Intensity2D3DRegi::obj_fn toggles it around every
+    // static-volume evaluation (true -> compute(vol 0) -> false -> compute(vol 1), xregIntensity2D3DRegi.cpp:594-629):
+    // push the flag on every compute; NULL images re-enable the background already resident on the device
+    CheckXRC(xrc_rc_set_bg_projs(rc_, nullptr, this->use_bg_projs_ ? 1 : 0));
   }
 
   const size_type n = this->num_projs_;

@@ -308,6 +308,8 @@ def main():
         # ---- this rank's chunk of every population, resident in HBM (camera-major within the chunk)
         def chunk_arrays(pop, a, b):
             p12 = to12(pop)
+            if b <= a:
+                return np.zeros((0, 12), np.float32), np.zeros(0, np.uint32)
             rows, cam = [], []
             for v, p0, cnt in regi.view_segments(a, b, n_views, pop_n):
                 rows.append(p12[p0:p0 + cnt])
@@ -328,25 +330,33 @@ def main():
 
         def resident(a, b):
             arr = [chunk_arrays(p, a, b) for p in pops]
-            poses_dev = torch.from_numpy(np.ascontiguousarray(np.stack([x[0] for x in arr]))).to(dev)
+            poses_host = np.ascontiguousarray(np.stack([x[0] for x in arr]))
+            poses_dev = torch.from_numpy(poses_host).to(dev)
             cam_dev = torch.from_numpy(np.ascontiguousarray(arr[0][1].astype(np.int32))).to(dev)
-            return poses_dev, cam_dev
+            return poses_dev, cam_dev, poses_host, arr[0][1]
+
+        def set_resident(r, k, n):
+            # device-resident poses; the host mirror only tells the library which volume stacks these poses need
+            fn.rc.set_poses_device(r[0][k].data_ptr(), n, r[1].data_ptr(), host_mirror=r[2][k], host_cam_idx=r[3])
 
         sims_dev = [regi.device_vector(sm.device_sims(), pop_n, dev) for sm in fn.sims]
         send_buf = torch.zeros(max(width, 1), dtype=torch.float32, device=dev)
         gathered = torch.zeros(world * max(width, 1), dtype=torch.float32, device=dev)
 
         def make_step(a, b, gather):
-            poses_dev, cam_dev = resident(a, b)
+            res = resident(a, b)
             sm_arr, n_active = setup_chunk(a, b)
             sg = regi.view_segments(a, b, n_views, pop_n)
             wd = max(hi - lo for lo, hi in regi.unit_chunks(n_units, world)) if gather else b - a
 
             def step(k):
-                fn.rc.set_poses_device(poses_dev[k].data_ptr(), b - a, cam_dev.data_ptr())
-                check(lib.xrc_eval_batch_async(fn.rc.handle, 0, sm_arr, n_active))
+                if b > a:   # a rank without units (fewer units than ranks) only takes part in the gather
+                    set_resident(res, k, b - a)
+                    check(lib.xrc_eval_batch_async(fn.rc.handle, 0, sm_arr, n_active))
                 if gather and world > 1:
-                    if len(sg) == 1:
+                    if len(sg) == 0:
+                        send = send_buf[:wd]
+                    elif len(sg) == 1:
                         send = sims_dev[sg[0][0]][:wd]      # zero copy: the metric's own result vector
                     else:
                         send, off = send_buf[:wd], 0
@@ -354,7 +364,7 @@ def main():
                             send[off:off + cnt].copy_(sims_dev[v][:cnt])
                             off += cnt
                     dist.all_gather_into_tensor(gathered[: wd * world], send)
-            return step, (poses_dev, cam_dev, sm_arr)
+            return step, res
 
         def barrier():
             if world > 1:
@@ -378,7 +388,11 @@ def main():
         step_resident, keep = make_step(u0, u1, gather=True)
         S, F = [], []
         for k in range(n_sets):
-            fn.rc.set_poses_device(keep[0][k].data_ptr(), n_local, keep[1].data_ptr())
+            if n_local == 0:
+                S.append(0)
+                F.append(0)
+                continue
+            set_resident(keep, k, n_local)
             S.append(fn.rc.ray_info(counts_only=True)[2])
             F.append(fn.rc.fetched_samples() if args.layout in ("default", "pax") else S[-1])
 
@@ -406,12 +420,12 @@ def main():
             assert e2e_last[0].shape == (pop_n,) and np.all(np.isfinite(e2e_last[0]))
 
             # dominant kernel alone: K launches of the DRR kernel on this rank's chunk, CUDA events on its stream
-            poses_dev, cam_dev = keep[0], keep[1]
             setup_chunk(u0, u1)
 
             def step_drr(k):
-                fn.rc.set_poses_device(poses_dev[k].data_ptr(), n_local, cam_dev.data_ptr())
-                fn.rc.compute()
+                if n_local:
+                    set_resident(keep, k, n_local)
+                    fn.rc.compute()
 
             for k in range(W):
                 step_drr(k)

@@ -160,6 +160,13 @@ int xrc_rc_distribute_poses(xrc_rc* rc, uint32_t n_poses, const float* cam_to_ph
  * xrc_rc_set_poses / xrc_rc_distribute_poses call.  No copy, no synchronisation. */
 int xrc_rc_set_poses_device(xrc_rc* rc, uint32_t n, const float* dev_cam_to_phys,
                             const uint32_t* dev_cam_idx);
+/* Same, with a host copy of the same values (n x 12 floats, optional n camera ids): the device arrays are what the
+ * kernels read; the mirror only lets the host see which principal-axis stacks of the volume these poses need, so that
+ * it builds just those (without a mirror, device poses make the ray caster build all three stacks: 12x instead of
+ * 4x + 1x the f32 volume for a single view).  A mirror that disagrees with the device arrays costs speed and
+ * last-bit reproducibility, never correctness. */
+int xrc_rc_set_poses_device_mirrored(xrc_rc* rc, uint32_t n, const float* dev_cam_to_phys, const uint32_t* dev_cam_idx,
+                                     const float* host_cam_to_phys, const uint32_t* host_cam_idx);
 
 /* set_ray_step_size / set_interp_method / RayCastLineIntParamInterface::set_kernel_id /
  * set_proj_store_method / set_default_bg_pixel_val (xregRayCastInterface.h:140-350,581-591) */

@@ -52,19 +52,26 @@ def test_sharded_device_objective_two_gpus_nccl():
 
 
 def test_pax_stacks_are_built_on_demand(ctx, xo):
-    """Only the principal-axis stacks the poses need exist (SURVEY 8(d) HBM budget): one stack + the f32 source for a
-    single view; a second view direction adds its stack; with all three the f32 source is dropped.  Projections are
-    bitwise the same whichever stacks exist (a CTA whose stack is missing uses another: same samples)."""
+    """Only the principal-axis stacks the poses can select exist (SURVEY 8(d) HBM budget): one stack + the f32 source
+    for a single view; a second view direction adds its stack; device-resident poses with a host mirror behave the
+    same, without a mirror all three stacks are built (and the f32 source is dropped).  Because every stack a CTA can
+    choose exists before the launch, projections are bitwise the same whichever OTHER stacks exist."""
+    import torch
+
     vol = synth.make_volume(72, 64, 56, spacing=(1.0, 1.1, 1.2))
     cam = CameraModel().setup(420.0, 64, 72, 1.9, 1.9)
     rec = lambda k: 16 * (vol.dims[(k + 1) % 3] + 1) * (vol.dims[(k + 2) % 3] + 1) * (vol.dims[k] + 2)
     f32b = 4 * vol.dims[0] * vol.dims[1] * vol.dims[2]
 
-    rc = xreg_b200.RayCasterLineIntCUDA(ctx)
-    rc.set_volume(vol)
-    rc.set_camera_model(cam)
-    rc.set_num_projs(3)
-    rc.allocate_resources()
+    def caster():
+        rc = xreg_b200.RayCasterLineIntCUDA(ctx)
+        rc.set_volume(vol)
+        rc.set_camera_model(cam)
+        rc.set_num_projs(3)
+        rc.allocate_resources()
+        return rc
+
+    rc = caster()
     b0 = rc.volume_bytes()
     assert f32b <= b0 < f32b + 4096                      # the source and the (tiny) empty-space map, no stack yet
     ap = synth.pose_population(vol, synth.nominal_pose(vol, src_to_iso=260.0), 3)
@@ -77,32 +84,39 @@ def test_pax_stacks_are_built_on_demand(ctx, xo):
     rc.compute()
     img_lat = rc.raw_host_pixel_buf().copy()
     assert rc.volume_bytes() - b0 == rec(1) + rec(0)     # lateral looks along x
-    # poses only the device knows: the kernel reports the stack it missed, the next compute() builds it
-    import torch
+    # an oblique population between the two needs both (the 45 degree rays choose per tile)
+    obl = synth.pose_population(vol, synth.nominal_pose(vol, src_to_iso=260.0, view_rot_deg=45.0), 3)
+    rc.set_xforms_cam_to_itk_phys(list(obl))
+    rc.compute()
+    img_obl = rc.raw_host_pixel_buf().copy()
+    assert rc.volume_bytes() - b0 == rec(1) + rec(0)
 
-    R = np.eye(4, dtype=np.float32)
-    R[:3, :3] = np.array([[1, 0, 0], [0, 0, -1], [0, 1, 0]], np.float32)        # look along z
-    c = np.asarray(vol.origin) + 0.5 * (np.asarray(vol.dims) - 1.0) * np.asarray(vol.spacing)
-    C, Ci = np.eye(4, dtype=np.float32), np.eye(4, dtype=np.float32)
-    C[:3, 3], Ci[:3, 3] = c, -c
-    axial = np.stack([(C @ R @ Ci @ p).astype(np.float32) for p in ap])
-    d_poses = torch.from_numpy(to12(axial)).cuda()
-    rc.set_poses_device(d_poses.data_ptr(), 3)
-    rc.compute()
-    first = rc.raw_host_pixel_buf().copy()               # ran on a fallback stack
-    rc.compute()
-    second = rc.raw_host_pixel_buf().copy()              # stack 2 now exists
-    assert rc.volume_bytes() == b0 - f32b + rec(0) + rec(1) + rec(2)
-    np.testing.assert_array_equal(first, second)
-    # oracle parity of the fallback result, and bitwise agreement with a ray caster that has every stack
+    # a fresh ray caster that sees the oblique population FIRST builds both stacks at once: same bits
+    rc2 = caster()
+    rc2.set_xforms_cam_to_itk_phys(list(obl))
+    rc2.compute()
+    np.testing.assert_array_equal(rc2.raw_host_pixel_buf(), img_obl)
+    assert rc2.volume_bytes() - b0 == rec(1) + rec(0)
+    # device-resident poses with a host mirror: only the stack they need; without: all three, f32 source dropped
+    rc3 = caster()
+    d_ap = torch.from_numpy(to12(ap)).cuda()
+    rc3.set_poses_device(d_ap.data_ptr(), 3, host_mirror=to12(ap))
+    rc3.compute()
+    np.testing.assert_array_equal(rc3.raw_host_pixel_buf(), img_ap)
+    assert rc3.volume_bytes() - b0 == rec(1)
+    rc3.set_poses_device(d_ap.data_ptr(), 3)
+    rc3.compute()
+    np.testing.assert_array_equal(rc3.raw_host_pixel_buf(), img_ap)
+    assert rc3.volume_bytes() == b0 - f32b + rec(0) + rec(1) + rec(2)
+    d_lat = torch.from_numpy(to12(lat)).cuda()
+    rc3.set_poses_device(d_lat.data_ptr(), 3)
+    rc3.compute()
+    np.testing.assert_array_equal(rc3.raw_host_pixel_buf(), img_lat)
+    # oracle parity of what the on-demand stacks produced
     xc = [xo.cam_struct(cam)]
-    ref = xo.drr(vol.data, vol.idx_to_phys(), xc, to12(axial))
-    sel = ref > 1e-3 * ref.max()
-    assert np.max(np.abs(first[sel] - ref[sel]) / ref[sel]) <= 1e-4
-    rc.set_xforms_cam_to_itk_phys(list(ap))
-    rc.compute()
-    np.testing.assert_array_equal(rc.raw_host_pixel_buf(), img_ap)
-    rc.set_xforms_cam_to_itk_phys(list(lat))
-    rc.compute()
-    np.testing.assert_array_equal(rc.raw_host_pixel_buf(), img_lat)
-    rc.close()
+    for imgs, poses in ((img_ap, ap), (img_lat, lat), (img_obl, obl)):
+        ref = xo.drr(vol.data, vol.idx_to_phys(), xc, to12(poses))
+        sel = ref > 1e-3 * ref.max()
+        assert np.max(np.abs(imgs[sel] - ref[sel]) / ref[sel]) <= 1e-4
+    for r in (rc, rc2, rc3):
+        r.close()

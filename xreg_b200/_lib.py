@@ -86,6 +86,7 @@ SIGNATURES = {
     "xrc_rc_set_poses": [_VP, _U32, _FP, _U32P],
     "xrc_rc_distribute_poses": [_VP, _U32, _FP],
     "xrc_rc_set_poses_device": [_VP, _U32, _VP, _VP],
+    "xrc_rc_set_poses_device_mirrored": [_VP, _U32, _VP, _VP, _FP, _U32P],
     "xrc_rc_set_params": [_VP, C.c_float, C.c_int, C.c_int, C.c_int, C.c_float],
     "xrc_rc_set_bg_projs": [_VP, C.POINTER(_FP), C.c_int],
     "xrc_rc_compute": [_VP, _U32],

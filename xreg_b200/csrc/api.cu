@@ -119,6 +119,7 @@ struct xrc_rc
   uint32_t* d_zero_idx = nullptr;      // all-zero camera indices
   const float* ext_poses = nullptr;    // caller-owned device poses (xrc_rc_set_poses_device)
   const uint32_t* ext_cam_idx = nullptr;
+  bool ext_mirrored = false;           // h_poses / h_cam_idx hold a host copy of ext_poses (xrc_rc_set_poses_device_mirrored)
   cudaEvent_t staged = nullptr;
   bool staged_pending = false;
   float step_size = 1.0f;
@@ -654,7 +655,29 @@ int xrc_rc_set_poses_device(xrc_rc* rc, uint32_t n, const float* dev_cam_to_phys
   XRC_CHECK_ARG(n == rc->num_projs, "xrc_rc_set_poses_device: pose count must equal num_projs");
   rc->ext_poses = dev_cam_to_phys;
   rc->ext_cam_idx = dev_cam_idx ? dev_cam_idx : rc->d_zero_idx;
+  rc->ext_mirrored = false;
   rc->inline_poses = false;
+  return XRC_OK;
+}
+
+int xrc_rc_set_poses_device_mirrored(xrc_rc* rc, uint32_t n, const float* dev_cam_to_phys, const uint32_t* dev_cam_idx,
+                                     const float* host_cam_to_phys, const uint32_t* host_cam_idx)
+{
+  XRC_CHECK_ARG(host_cam_to_phys, "xrc_rc_set_poses_device_mirrored: null host mirror");
+  XRC_CHECK_ARG((dev_cam_idx == nullptr) == (host_cam_idx == nullptr),
+                "xrc_rc_set_poses_device_mirrored: camera indices must be given on both sides or on neither");
+  XRC_TRY(xrc_rc_set_poses_device(rc, n, dev_cam_to_phys, dev_cam_idx));
+  if (host_cam_idx)
+    for (uint32_t i = 0; i < n; ++i)
+      XRC_CHECK_ARG(host_cam_idx[i] < rc->cams.size(), "xrc_rc_set_poses_device_mirrored: camera index out of range");
+  XRC_TRY(use_device(rc->ctx));
+  XRC_TRY(rc_wait_staging(rc));
+  memcpy(rc->h_poses, host_cam_to_phys, sizeof(float) * 12 * n);
+  if (host_cam_idx)
+    memcpy(rc->h_cam_idx, host_cam_idx, sizeof(uint32_t) * n);
+  else
+    memset(rc->h_cam_idx, 0, sizeof(uint32_t) * n);
+  rc->ext_mirrored = true;
   return XRC_OK;
 }
 
@@ -702,11 +725,16 @@ int xrc_rc_set_bg_projs(xrc_rc* rc, const float* const* host_imgs, int use_bg)
   return XRC_OK;
 }
 
-// XRC_LAYOUT_PAX stacks are built on demand.  The kernel decides per CTA which stack it wants (the principal axis of
-// the ray through its tile centre, pax_cta_prologue); a CTA whose stack is missing uses a built one (same samples,
-// worse access pattern) and reports the wish through host-mapped memory, which the next compute() honours.  So that
-// the common case never runs on the wrong stack, the host also predicts the wishes of the poses it can see from the
-// rays through the detector centre and corners (plain f32; a wrong guess only costs speed).
+// XRC_LAYOUT_PAX stacks are built on demand.  The kernel decides per CTA which stack it marches (the principal axis of
+// the ray through its tile centre, pax_cta_prologue), and the low bits of a sample depend on that choice (the plane of
+// the bilinear step differs between stacks), so for results to be a pure function of (volume, camera, pose) every
+// stack a CTA can choose must exist before the launch.  Host-visible poses: the index-space ray direction is affine in
+// (col, row), so axis i can never win anywhere on the detector if some axis k with constant sign s satisfies
+// s d_k >= (1 + eps) |d_i| at the four detector corners; every axis not excluded that way is built (a superset of the
+// kernel's choices; eps covers the different rounding of kernel and host).  Poses only the device knows
+// (xrc_rc_set_poses_device without a host mirror) get all three stacks.  The kernel still has a fallback for a missing
+// stack (any built one; it reports the wish through host-mapped memory and the next compute() honours it), which only
+// an out-of-memory condition or a wrong mirror can trigger.
 static int rc_prepare_stacks(xrc_rc* rc, uint32_t vol_idx)
 {
   DeviceVolume& v = rc->vols[vol_idx];
@@ -720,10 +748,13 @@ static int rc_prepare_stacks(xrc_rc* rc, uint32_t vol_idx)
         need[k] = true;
         v.h_want[k] = 0u;
       }
-  if (!rc->ext_poses)
+  if (rc->ext_poses && !rc->ext_mirrored)
+    need[0] = need[1] = need[2] = true;
+  else
   {
     const float* A = v.phys_to_idx;
-    for (uint32_t p = 0; p < rc->num_projs; ++p)
+    const float eps = 1.0e-3f;
+    for (uint32_t p = 0; p < rc->num_projs && !(need[0] && need[1] && need[2]); ++p)
     {
       const float* P = rc->h_poses + 12 * (size_t)p;
       const xrc_cam& cam = rc->cams[std::min<size_t>(rc->h_cam_idx[p], rc->cams.size() - 1)];
@@ -735,11 +766,11 @@ static int rc_prepare_stacks(xrc_rc* rc, uint32_t vol_idx)
       for (int r = 0; r < 3; ++r)
         src[r] = X[4 * r] * cam.pinhole[0] + X[4 * r + 1] * cam.pinhole[1] + X[4 * r + 2] * cam.pinhole[2] + X[4 * r + 3];
       const float det_z = ((cam.frame_type == 1) ? -1.0f : 1.0f) * cam.focal_len;
-      static const float gx[5] = {0.5f, 0.f, 1.f, 0.f, 1.f}, gy[5] = {0.5f, 0.f, 0.f, 1.f, 1.f};
-      for (int g = 0; g < 5; ++g)
+      float d[4][3];
+      for (int g = 0; g < 4; ++g)
       {
-        const float col = (float)(cam.cols - 1) * gx[g], row = (float)(cam.rows - 1) * gy[g];
-        float cv[3], w[3], d[3];
+        const float col = (g & 1) ? (float)(cam.cols - 1) : 0.0f, row = (g & 2) ? (float)(cam.rows - 1) : 0.0f;
+        float cv[3], w[3];
         for (int r = 0; r < 3; ++r)
           cv[r] = det_z * (cam.intrins_inv[3 * r] * col + cam.intrins_inv[3 * r + 1] * row + cam.intrins_inv[3 * r + 2]);
         if (cam.frame_type == 2)
@@ -748,8 +779,25 @@ static int rc_prepare_stacks(xrc_rc* rc, uint32_t vol_idx)
           w[r] = cam.extrins_inv[4 * r] * cv[0] + cam.extrins_inv[4 * r + 1] * cv[1] + cam.extrins_inv[4 * r + 2] * cv[2] +
                  cam.extrins_inv[4 * r + 3];
         for (int r = 0; r < 3; ++r)
-          d[r] = fabsf(X[4 * r] * w[0] + X[4 * r + 1] * w[1] + X[4 * r + 2] * w[2] + X[4 * r + 3] - src[r]);
-        need[(d[2] >= d[0] && d[2] >= d[1]) ? 2 : ((d[1] >= d[0]) ? 1 : 0)] = true;
+          d[g][r] = X[4 * r] * w[0] + X[4 * r + 1] * w[1] + X[4 * r + 2] * w[2] + X[4 * r + 3] - src[r];
+      }
+      for (int i = 0; i < 3; ++i)
+      {
+        bool dominated = false;
+        for (int k = 0; k < 3 && !dominated; ++k)
+        {
+          if (k == i)
+            continue;
+          for (int sgn = -1; sgn <= 1 && !dominated; sgn += 2)
+          {
+            bool all = true;
+            for (int g = 0; g < 4; ++g)
+              all = all && ((float)sgn * d[g][k] >= (1.0f + eps) * fabsf(d[g][i])) && ((float)sgn * d[g][k] > 0.0f);
+            dominated = all;
+          }
+        }
+        if (!dominated)
+          need[i] = true;
       }
     }
   }
@@ -766,7 +814,7 @@ static int rc_prepare_stacks(xrc_rc* rc, uint32_t vol_idx)
     XRC_TRY(s);
   }
   if (!(v.pax[0] || v.pax[1] || v.pax[2]))
-    XRC_TRY(build_pax_stack(&v, 2, rc->ctx->stream));   // poses only the device knows: start anywhere, the kernel reports
+    XRC_TRY(build_pax_stack(&v, 2, rc->ctx->stream));   // nothing to project yet: any stack will do
   return XRC_OK;
 }
 

@@ -330,10 +330,22 @@ class RayCasterLineIntCUDA:
         self._cam_model_for_proj = [0] * n if cam_idx is None else [int(c) for c in cam_idx]
         self._poses_dirty = False
 
-    def set_poses_device(self, dev_poses_ptr: int, n: int, dev_cam_idx_ptr: int = 0) -> None:
-        """Poses already resident on the device (n x 12 float32, optional n x uint32 camera ids)."""
-        check(self._lib.xrc_rc_set_poses_device(self.handle, int(n), C.c_void_p(dev_poses_ptr),
-                                                C.c_void_p(dev_cam_idx_ptr) if dev_cam_idx_ptr else None))
+    def set_poses_device(self, dev_poses_ptr: int, n: int, dev_cam_idx_ptr: int = 0,
+                         host_mirror: Optional[np.ndarray] = None, host_cam_idx: Optional[np.ndarray] = None) -> None:
+        """Poses already resident on the device (n x 12 float32, optional n x uint32 camera ids).  host_mirror: the same
+        values on the host, so that only the principal-axis stacks these poses need are built (without it: all three)."""
+        if host_mirror is None:
+            check(self._lib.xrc_rc_set_poses_device(self.handle, int(n), C.c_void_p(dev_poses_ptr),
+                                                    C.c_void_p(dev_cam_idx_ptr) if dev_cam_idx_ptr else None))
+        else:
+            hm = np.ascontiguousarray(host_mirror, dtype=f32).reshape(-1, 12)
+            hc = None
+            if dev_cam_idx_ptr:
+                hc_arr = np.ascontiguousarray(host_cam_idx, dtype=np.uint32)
+                hc = hc_arr.ctypes.data_as(C.POINTER(C.c_uint32))
+            check(self._lib.xrc_rc_set_poses_device_mirrored(
+                self.handle, int(n), C.c_void_p(dev_poses_ptr), C.c_void_p(dev_cam_idx_ptr) if dev_cam_idx_ptr else None,
+                hm.ctypes.data_as(C.POINTER(C.c_float)), hc))
         self._poses_dirty = False
 
     def compute(self, vol_idx: int = 0) -> None:
