@@ -59,12 +59,17 @@ def main():
             if rank == 0:
                 print(json.dumps({"world": world, "views": len(cams), "metric": metric, "poses": int(len(got)),
                                   "devices": [int(torch.cuda.current_device())], "bitwise_equal_to_single_gpu": same}), flush=True)
+        del sharded
         fn.close()
         single.close()
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    code = 0 if int(flag.item()) == 1 else 1
+    ctx.close()
+    torch.cuda.synchronize()
     dist.destroy_process_group()
-    sys.exit(0 if int(flag.item()) == 1 else 1)
+    sys.stdout.flush()
+    os._exit(code)   # skip interpreter teardown: pinned buffers would be released after the CUDA context is gone
 
 
 if __name__ == "__main__":

@@ -194,8 +194,10 @@ def test_launch_counter_counts_our_kernels(ctx, small_scene):
     vol, cam, nominal = small_scene
     fn = regi.Intensity2D3DObjFn(ctx, vol, [cam], [np.ones((cam.num_det_rows, cam.num_det_cols), f32)], metric="patch-grad-ncc",
                                  max_pop=2, patch_radius=5)
+    pop = synth.pose_population(vol, nominal, 2)
+    fn(pop)                                        # the first call also builds the volume stack these poses need
     before = xreg_b200.launch_count()
-    fn(synth.pose_population(vol, nominal, 2))
+    fn(pop)
     assert xreg_b200.launch_count() - before == 5  # drr + grad + patch + sequential patch sum + finalize
 
 
