@@ -30,10 +30,6 @@ void CheckXRC(const int status)
 template <class tPatchSim>
 void PushPatchParams(tPatchSim* self, xrc_sm* sm, const bool weights_are_trivial)
 {
-  if (self->choose_rand_patches())
-  {
-    throw ImgSimMetric2D::UnsupportedOperationException();
-  }
   std::vector<float> w;
   if (!weights_are_trivial)
   {
@@ -49,6 +45,33 @@ void PushPatchParams(tPatchSim* self, xrc_sm* sm, const bool weights_are_trivial
                                    self->weight_patch_sims_in_combine() ? 1 : 0,
                                    self->use_mask_for_patch_stats() ? 1 : 0,
                                    w.empty() ? nullptr : w.data(), w.size()));
+}
+
+/// The local patch list of this compute() call, exactly as ImgSimMetric2DPatchNCCCPU::compute chooses it
+/// (xregImgSimMetric2DPatchNCCCPU.cpp:97-101): a fresh patch_indices_to_use() draw unless set_patches_to_use() pinned
+/// the list; the whole grid in natural order needs no list.
+template <class tPatchSim>
+void PushPatchSubset(tPatchSim* self, xrc_sm* sm, const bool pinned, const std::vector<xreg::size_type>& pinned_inds,
+                     std::vector<xreg::size_type>* drawn)
+{
+  const std::vector<xreg::size_type>* inds = nullptr;
+  if (pinned)
+  {
+    inds = &pinned_inds;
+  }
+  else if (self->choose_rand_patches())
+  {
+    inds = drawn;
+  }
+  if (inds)
+  {
+    std::vector<uint64_t> tmp(inds->begin(), inds->end());
+    CheckXRC(xrc_sm_set_patch_subset(sm, tmp.data(), tmp.size()));
+  }
+  else
+  {
+    CheckXRC(xrc_sm_set_patch_subset(sm, nullptr, 0));
+  }
 }
 
 }  // namespace
@@ -124,6 +147,7 @@ void xreg::ImgSimMetric2DCUDA::compute()
     sync_host_buf_->sync();
   }
   this->process_updated_mask();
+  pre_compute_params();
   CheckXRC(xrc_sm_set_num_imgs(sm_, static_cast<uint32_t>(this->num_mov_imgs_)));
   CheckXRC(xrc_sm_compute(sm_));
   CheckXRC(xrc_sm_read_sims(sm_, this->sim_vals_.data(), static_cast<uint32_t>(this->num_mov_imgs_)));
@@ -158,6 +182,25 @@ void xreg::ImgSimMetric2DPatchNCCCUDA::push_params()
   this->compute_weights(this->mask_ ? &ocv_mask : nullptr);
   const bool trivial = !this->wgt_img_ && !(this->use_mask_for_weighting_ && this->mask_);
   PushPatchParams(this, sm_, trivial);
+}
+
+void xreg::ImgSimMetric2DPatchNCCCUDA::pre_compute_params()
+{
+  if (!this->do_not_update_patch_inds_to_use_)
+  {
+    this->patch_inds_to_use_ = this->patch_indices_to_use();
+  }
+  PushPatchSubset(this, sm_, this->do_not_update_patch_inds_to_use_, this->patch_inds_to_use_, &this->patch_inds_to_use_);
+}
+
+void xreg::ImgSimMetric2DPatchGradNCCCUDA::pre_compute_params()
+{
+  // one list for both gradient directions (xregImgSimMetric2DPatchGradNCCCPU.cpp:126-135)
+  if (!this->do_not_update_patch_inds_to_use_)
+  {
+    this->patch_inds_to_use_ = this->patch_indices_to_use();
+  }
+  PushPatchSubset(this, sm_, this->do_not_update_patch_inds_to_use_, this->patch_inds_to_use_, &this->patch_inds_to_use_);
 }
 
 void xreg::ImgSimMetric2DPatchGradNCCCUDA::allocate_resources()

@@ -47,6 +47,9 @@ protected:
   /// hook for the patch / gradient parameters, called before allocation and on mask updates
   virtual void push_params() { }
 
+  /// hook run at the start of every compute() (the patch metrics choose their patch list here)
+  virtual void pre_compute_params() { }
+
   xrc_ctx* ctx_ = nullptr;
   xrc_sm* sm_ = nullptr;
 
@@ -90,6 +93,8 @@ public:
 
 protected:
   void push_params() override;
+
+  void pre_compute_params() override;
 };
 
 class ImgSimMetric2DPatchGradNCCCUDA : public ImgSimMetric2DCUDA,
@@ -107,6 +112,8 @@ public:
 
 protected:
   void push_params() override;
+
+  void pre_compute_params() override;
 
 private:
   size_type smooth_img_kernel_rad_ = 5;

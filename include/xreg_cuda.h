@@ -242,6 +242,15 @@ int xrc_sm_set_combine_mode(xrc_sm* sm, int mode);
  * loop instead of the parallel emulation.  Synchronises. */
 int xrc_seqsum_f32(xrc_ctx* ctx, const float* host_vals, uint32_t n_seq, uint64_t n, int serial, float* host_out);
 
+/* ImgSimMetric2DPatchCommon::set_patches_to_use / reset_patches_to_use and the random patches of
+ * patch_indices_to_use (xregImgSimMetric2DPatchCommon.cpp:231-241, 413-493): the metric is evaluated over the
+ * LOCAL patch list patch_inds[0 .. n) of global indices into the (strided) patch grid, in list order, repeats allowed --
+ * per-patch values and weights are those of the whole grid, the sequential f32 sum, the mean's divisor (n) and the
+ * weighted divisor (sequential f32 sum of the listed weights) follow xregImgSimMetric2DPatchNCCCPU.cpp:97-101, 204,
+ * 262-285.  n == 0 restores the whole grid.  Patch kinds only; may be changed between computes (the adapter of a
+ * random-patch metric calls it with the reference's own draw before every compute).  The host picks the indices. */
+int xrc_sm_set_patch_subset(xrc_sm* sm, const uint64_t* patch_inds, uint64_t n);
+
 /* set_mov_imgs_buf_from_ray_caster (:119): zero-copy device hand-off. Re-callable
  * with a new offset; a different ray caster than the first is an error
  * (xregImgSimMetric2DCPU.cpp:45-70). */

@@ -260,7 +260,8 @@ extern "C" void xref_patch_mean_std(const float* img, const uint8_t* mask, uint3
 // set_fixed_image / set_mask / set_mov_imgs_host_buf / patch parameters, allocate_resources(), compute(), sim_vals()
 extern "C" int xref_patch_ncc(const float* fixed, const uint8_t* mask, uint32_t rows, uint32_t cols,
                               const xref_patch_opts* o, const float* wgt_img, const float* mov, uint32_t n_imgs,
-                              float* sims_out, float* weights_out, float* patch_sims_out)
+                              float* sims_out, float* weights_out, float* patch_sims_out,
+                              const uint64_t* subset = nullptr, uint64_t n_subset = 0)
 {
   using Sim = xreg::ImgSimMetric2DPatchNCCCPU;
   Sim sm;
@@ -295,6 +296,11 @@ extern "C" int xref_patch_ncc(const float* fixed, const uint8_t* mask, uint32_t 
   sm.use_mask_for_patch_stats_ = o->use_mask_for_patch_stats != 0;
   sm.normalize_weights_as_prob_ = o->normalize_weights_as_prob != 0;
   sm.save_all_per_patch_scores_ = patch_sims_out != nullptr;
+  if (n_subset)
+  {
+    Sim::PatchIndexList inds(subset, subset + n_subset);
+    sm.set_patches_to_use(inds);   // the reference's own lines (xregImgSimMetric2DPatchCommon.cpp:231-235)
+  }
   sm.allocate_resources();
   sm.compute();
   for (uint32_t i = 0; i < n_imgs; ++i)
@@ -305,8 +311,8 @@ extern "C" int xref_patch_ncc(const float* fixed, const uint8_t* mask, uint32_t 
       weights_out[k] = sm.patch_infos_[k].weight;
   if (patch_sims_out)
     for (uint32_t i = 0; i < n_imgs; ++i)
-      for (std::size_t k = 0; k < np; ++k)
-        patch_sims_out[(std::size_t)i * np + k] = sm.sim_vals_for_each_patch_[k][i];
+      for (std::size_t k = 0; k < sm.sim_vals_for_each_patch_.size(); ++k)
+        patch_sims_out[(std::size_t)i * sm.sim_vals_for_each_patch_.size() + k] = sm.sim_vals_for_each_patch_[k][i];
   return (int)np;
 }
 '''
@@ -326,6 +332,7 @@ def metric_slices():
                           (r"^xreg::size_type xreg::ImgSimMetric2DPatchCommon::num_patches\(\) const", 0),
                           (r"^void xreg::ImgSimMetric2DPatchCommon::setup_patches\(", 0),
                           (r"^bool xreg::ImgSimMetric2DPatchCommon::compute_weights\(", 0),
+                          (r"^void xreg::ImgSimMetric2DPatchCommon::set_patches_to_use\(", 0),
                           (r"^xreg::ImgSimMetric2DPatchCommon::patch_indices_to_use\(\)", 1)):
         s, e = _with_prev(ln, regex, n_prev)
         out.append((rel, s, e, ln[s:e + 1]))
@@ -550,8 +557,7 @@ def grad_slices():
     d = "lib/regi/sim_metrics_2d/"
     more = (
         (d + "xregImgSimMetric2DPatchCommon.cpp", (r"^void xreg::ImgSimMetric2DPatchCommon::set_from_other\(",
-                                                   r"^void xreg::ImgSimMetric2DPatchCommon::set_weights_from_other\(",
-                                                   r"^void xreg::ImgSimMetric2DPatchCommon::set_patches_to_use\(")),
+                                                   r"^void xreg::ImgSimMetric2DPatchCommon::set_weights_from_other\(")),
         (d + "xregImgSimMetric2DPatchNCCCPU.cpp", (r"^void xreg::ImgSimMetric2DPatchNCCCPU::set_use_fixed_img_patch_variances_as_wgts\(",
                                                    r"^void xreg::ImgSimMetric2DPatchNCCCPU::set_use_mov_img_patch_variances_as_wgts\(",
                                                    r"^void xreg::ImgSimMetric2DPatchNCCCPU::set_other_mov_img_patch_vars\(")),

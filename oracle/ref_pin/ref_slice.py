@@ -91,6 +91,23 @@ def patch_mean_std(img, mask, r0, c0, d, use_mask_for_stats):
     return np.float32(mean.value), np.float32(sd.value), int(n.value)
 
 
+def patch_ncc_subset(fixed, mov, opts, subset, mask=None, wgt_img=None):
+    """ImgSimMetric2DPatchNCCCPU with set_patches_to_use(subset) before allocate_resources() / compute()."""
+    fixed = _f32(fixed)
+    rows, cols = fixed.shape
+    mov = _f32(mov).reshape(-1, rows, cols)
+    n = mov.shape[0]
+    sims = np.zeros(n, np.float32)
+    m = np.ascontiguousarray(mask, dtype=np.uint8) if mask is not None else None
+    wi = _f32(wgt_img) if wgt_img is not None else None
+    sub = np.ascontiguousarray(subset, dtype=np.uint64)
+    fn = metric_lib().xref_patch_ncc
+    fn(_fp(fixed), m.ctypes.data_as(C.POINTER(C.c_uint8)) if m is not None else None, C.c_uint32(rows), C.c_uint32(cols),
+       C.byref(opts), _fp(wi) if wi is not None else None, _fp(mov), C.c_uint32(n), _fp(sims), None, None,
+       sub.ctypes.data_as(C.POINTER(C.c_uint64)), C.c_uint64(sub.size))
+    return sims
+
+
 def patch_ncc(fixed, mov, opts, mask=None, wgt_img=None, want_patch_sims=False):
     """ImgSimMetric2DPatchNCCCPU: set_fixed_image / set_mask / set_wgt_img / patch parameters, allocate_resources(),
     compute().  Returns (sims, patch weights[, per-patch values (n, num_patches)])."""
@@ -108,7 +125,8 @@ def patch_ncc(fixed, mov, opts, mask=None, wgt_img=None, want_patch_sims=False):
     wi = _f32(wgt_img) if wgt_img is not None else None
     got = metric_lib().xref_patch_ncc(_fp(fixed), m.ctypes.data_as(C.POINTER(C.c_uint8)) if m is not None else None,
                                       C.c_uint32(rows), C.c_uint32(cols), C.byref(opts), _fp(wi) if wi is not None else None,
-                                      _fp(mov), C.c_uint32(n), _fp(sims), _fp(w), _fp(ps) if ps is not None else None)
+                                      _fp(mov), C.c_uint32(n), _fp(sims), _fp(w), _fp(ps) if ps is not None else None,
+                                      None, C.c_uint64(0))
     assert got == np_, "patch grid size differs: reference %d, oracle %d" % (got, np_)
     return (sims, w, ps) if want_patch_sims else (sims, w)
 

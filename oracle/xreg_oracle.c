@@ -1000,6 +1000,76 @@ void xo_patch_ncc(const float* fixed, const uint8_t* mask, uint32_t rows, uint32
   free(f_den);
 }
 
+/* Patch subsets: ImgSimMetric2DPatchCommon::set_patches_to_use / the random patches of patch_indices_to_use
+ * (xregImgSimMetric2DPatchCommon.cpp:231-241, 413-493).  ImgSimMetric2DPatchNCCCPU::compute then loops over the LOCAL
+ * index list patch_inds_to_use_ (:97-101, :204): the value of local patch j is that of global patch subset[j]
+ * (weights are those of the whole grid), the sequential f32 sum runs in subset order (:262-266), the mean divides by
+ * the subset size (:268-271, num_patches() = patch_inds_to_use_.size()) and the weighted combine by the sequential f32
+ * sum of the subset's weights (:272-285).  Indices may repeat. */
+void xo_patch_ncc_subset(const float* fixed, const uint8_t* mask, uint32_t rows, uint32_t cols,
+                         const xo_patch_opts* o, const float* weights, const uint64_t* subset, uint64_t n_subset,
+                         const float* mov, uint32_t n_imgs, float* sims, int n_threads)
+{
+  const size_t np = (size_t)n_centres(rows, o->radius, o->stride) * n_centres(cols, o->radius, o->stride);
+  float* ps = (float*)malloc(sizeof(float) * np * (n_imgs ? n_imgs : 1));
+  float* all = (float*)malloc(sizeof(float) * (n_imgs ? n_imgs : 1));
+  xo_patch_ncc(fixed, mask, rows, cols, o, weights, mov, n_imgs, all, ps, n_threads);
+  for (uint32_t mi = 0; mi < n_imgs; ++mi)
+  {
+    float sum = 0.0f;
+    for (uint64_t j = 0; j < n_subset; ++j)
+    {
+      const size_t k = (size_t)subset[j];
+      const float w = weights ? weights[k] : 1.0f;
+      float v = 0.0f;
+      if (!o->weight_patch_sims || (fabsf(w) > 1.0e-6f))
+        v = (o->weight_patch_sims ? w : 1.0f) * ps[(size_t)mi * np + k];
+      sum += v;
+    }
+    if (o->compute_mean_of_patch_sims)
+    {
+      sum /= (float)n_subset;
+    }
+    else if (o->weight_patch_sims)
+    {
+      float tw = 0.0f;
+      for (uint64_t j = 0; j < n_subset; ++j)
+        tw += weights ? weights[subset[j]] : 1.0f;
+      sum /= tw;
+    }
+    sims[mi] = sum;
+  }
+  free(ps);
+  free(all);
+}
+
+/* xregImgSimMetric2DPatchGradNCCCPU.cpp:126-135: the same subset for both directions */
+void xo_patch_grad_ncc_subset(const float* fixed, const uint8_t* mask, uint32_t rows, uint32_t cols, int gauss_width,
+                              const xo_patch_opts* o, const float* weights, const uint64_t* subset, uint64_t n_subset,
+                              const float* mov, uint32_t n_imgs, float* sims, int n_threads)
+{
+  const size_t n = (size_t)rows * cols;
+  float* fgx = (float*)malloc(sizeof(float) * n);
+  float* fgy = (float*)malloc(sizeof(float) * n);
+  float* mgx = (float*)malloc(sizeof(float) * n * n_imgs);
+  float* mgy = (float*)malloc(sizeof(float) * n * n_imgs);
+  float* sx = (float*)malloc(sizeof(float) * n_imgs);
+  float* sy = (float*)malloc(sizeof(float) * n_imgs);
+  xo_grad_imgs(fixed, rows, cols, gauss_width, fgx, fgy);
+  for (uint32_t k = 0; k < n_imgs; ++k)
+    xo_grad_imgs(mov + (size_t)k * n, rows, cols, gauss_width, mgx + (size_t)k * n, mgy + (size_t)k * n);
+  xo_patch_ncc_subset(fgx, mask, rows, cols, o, weights, subset, n_subset, mgx, n_imgs, sx, n_threads);
+  xo_patch_ncc_subset(fgy, mask, rows, cols, o, weights, subset, n_subset, mgy, n_imgs, sy, n_threads);
+  for (uint32_t k = 0; k < n_imgs; ++k)
+    sims[k] = (float)(0.5 * (sx[k] + sy[k]));
+  free(fgx);
+  free(fgy);
+  free(mgx);
+  free(mgy);
+  free(sx);
+  free(sy);
+}
+
 /* lib/regi/sim_metrics_2d/xregImgSimMetric2DPatchGradNCCCPU.cpp:34-253 */
 void xo_patch_grad_ncc(const float* fixed, const uint8_t* mask, uint32_t rows, uint32_t cols,
                        int gauss_width, const xo_patch_opts* o, const float* weights,

@@ -180,6 +180,13 @@ void xo_patch_ncc(const float* fixed, const uint8_t* mask, uint32_t rows, uint32
 void xo_patch_grad_ncc(const float* fixed, const uint8_t* mask, uint32_t rows, uint32_t cols,
                        int gauss_width, const xo_patch_opts* o, const float* weights,
                        const float* mov, uint32_t n_imgs, float* sims, int n_threads);
+/* the same metrics over a patch subset (set_patches_to_use / random patches; local order = subset order) */
+void xo_patch_ncc_subset(const float* fixed, const uint8_t* mask, uint32_t rows, uint32_t cols,
+                         const xo_patch_opts* o, const float* weights, const uint64_t* subset, uint64_t n_subset,
+                         const float* mov, uint32_t n_imgs, float* sims, int n_threads);
+void xo_patch_grad_ncc_subset(const float* fixed, const uint8_t* mask, uint32_t rows, uint32_t cols, int gauss_width,
+                              const xo_patch_opts* o, const float* weights, const uint64_t* subset, uint64_t n_subset,
+                              const float* mov, uint32_t n_imgs, float* sims, int n_threads);
 
 /* ImgSimMetric2DCombineMean (xregImgSimMetric2DCombine.cpp:67-86) */
 void xo_combine_mean(const float* view_sims, uint32_t n_views, uint32_t n_poses, float* out);

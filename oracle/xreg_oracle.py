@@ -325,6 +325,29 @@ def patch_grad_ncc(fixed, mov, opts, mask=None, weights=None, gauss_width=5, n_t
     return sims
 
 
+def patch_ncc_subset(fixed, mov, opts, subset, mask=None, weights=None, gauss_width=None, n_threads=0):
+    """Patch NCC (gauss_width None) or patch gradient-NCC over the patch subset `subset` (global patch indices, local
+    order = list order, repeats allowed): set_patches_to_use / random patches of the reference."""
+    fixed = _f32(fixed)
+    rows, cols = fixed.shape
+    mov = _f32(mov).reshape(-1, rows, cols)
+    n = mov.shape[0]
+    sims = np.zeros(n, np.float32)
+    m = np.ascontiguousarray(mask, dtype=np.uint8) if mask is not None else None
+    w = _f32(weights) if weights is not None else None
+    sub = np.ascontiguousarray(subset, dtype=np.uint64)
+    sp = sub.ctypes.data_as(C.POINTER(C.c_uint64))
+    if gauss_width is None:
+        lib().xo_patch_ncc_subset(_fp(fixed), _u8p(m) if m is not None else None, C.c_uint32(rows), C.c_uint32(cols),
+                                  C.byref(opts), _fp(w) if w is not None else None, sp, C.c_uint64(sub.size), _fp(mov),
+                                  C.c_uint32(n), _fp(sims), C.c_int(n_threads))
+    else:
+        lib().xo_patch_grad_ncc_subset(_fp(fixed), _u8p(m) if m is not None else None, C.c_uint32(rows), C.c_uint32(cols),
+                                       C.c_int(gauss_width), C.byref(opts), _fp(w) if w is not None else None, sp,
+                                       C.c_uint64(sub.size), _fp(mov), C.c_uint32(n), _fp(sims), C.c_int(n_threads))
+    return sims
+
+
 def combine_mean(view_sims):
     v = _f32(view_sims)
     out = np.zeros(v.shape[1], np.float32)

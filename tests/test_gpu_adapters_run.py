@@ -195,3 +195,23 @@ def test_adapter_static_volume_background_survives_repeated_evaluations(ctx, xo,
         assert np.max(np.abs(sims[e] - ref)) <= 1e-5, "evaluation %d lost the static background" % e
     sel = buf > 1e-3 * buf.max()
     assert np.max(np.abs(projs[sel] - buf[sel]) / buf[sel]) <= 1e-4
+
+
+@pytest.mark.gpu
+def test_adapter_patch_subset_through_the_reference_mixin(ctx, xo, small_scene, tmp_path):
+    """set_patches_to_use through the reference's own ImgSimMetric2DPatchCommon (reached by dynamic_cast, as the apps do):
+    the adapter hands the local patch list to the library before every compute()."""
+    vol, cam, nominal = small_scene
+    cam = _via_intrins(cam)
+    rows, cols = cam.num_det_rows, cam.num_det_cols
+    pops = synth.pose_population(vol, nominal, 4, seed=8)[None, None]
+    xcam = [xo.cam_struct(cam)]
+    fixed = [synth.add_noise(xo.drr(vol.data, vol.idx_to_phys(), xcam, to12(pops[0, 0, :1]))[0])]
+    n_p = xo.num_patches(rows, cols, 6, 1)
+    sub = np.random.default_rng(3).integers(0, n_p, size=200)
+    sims, per_view, projs, _, _, _, n_patches = run_driver(tmp_path, vols=[vol], cams=[cam], fixed=fixed, masks=None, poses=pops,
+                                                          kind="patch-grad-ncc", patch_radius=6, subset=sub)
+    assert n_patches == 200          # ImgSimMetric2DPatchCommon::num_patches() of a pinned list
+    ref = xo.patch_ncc_subset(fixed[0], xo.drr(vol.data, vol.idx_to_phys(), xcam, to12(pops[0, 0])), xo.patch_opts(radius=6), sub,
+                              gauss_width=5)
+    assert np.max(np.abs(sims[0] - ref)) <= 1e-5

@@ -374,3 +374,69 @@ def test_combine_mode_switch_after_allocation(ctx, xo):
     assert np.max(np.abs(b - ref)) <= 2.0e-6 and np.max(np.abs(a - ref)) <= SIM_TOL
     with pytest.raises(KeyError):
         sm.set_combine_mode("bogus")
+
+
+@pytest.mark.parametrize("grad", [False, True])
+@pytest.mark.parametrize("mode", ["default", "mean", "unweighted", "mask"])
+def test_patch_subsets_follow_the_reference(ctx, xo, grad, mode):
+    """set_patches_to_use / reset_patches_to_use and random patches (xregImgSimMetric2DPatchCommon.cpp:231-241,
+    413-493): the metric over a local patch list -- unordered, with repeats, a single patch -- equals the oracle's
+    xo_patch_ncc_subset (itself bit-equal to the reference's class code with set_patches_to_use), the list can change
+    between computes without re-allocation, and resetting it restores the whole grid bit for bit."""
+    shape = (57, 66)
+    fixed = _img(*shape, seed=21)
+    mov = _movs(fixed, 4, seed=70)
+    mask = synth.circular_mask(*shape, 0.8) if mode == "mask" else None
+    cls = xreg_b200.ImgSimMetric2DPatchGradNCCCUDA if grad else xreg_b200.ImgSimMetric2DPatchNCCCUDA
+    sm = cls(ctx)
+    sm.set_patch_radius(5)
+    sm.set_patch_stride(2)
+    o = xo.patch_opts(radius=5, stride=2)
+    if mode == "mean":
+        sm.set_compute_mean_of_patch_sims(True)
+        o.compute_mean_of_patch_sims = 1
+    elif mode == "unweighted":
+        sm.set_weight_patch_sims_in_combine(False)
+        o.weight_patch_sims = 0
+    full = _run(sm, fixed, mov, mask)
+    n_p = sm.num_patches()
+    assert n_p == xo.num_patches(shape[0], shape[1], 5, 2)
+    w = xo.patch_weights(shape[0], shape[1], o, mask=mask) if mask is not None else None
+    gw = 5 if grad else None
+    rng = np.random.default_rng(5)
+    for sub in (rng.integers(0, n_p, size=n_p // 4), np.array([n_p - 1]), np.repeat(rng.integers(0, n_p, size=5), 3),
+                np.arange(n_p)[::-1]):
+        sm.set_patches_to_use(sub)
+        sm.compute()
+        got = sm.sim_vals().copy()
+        ref = xo.patch_ncc_subset(fixed, mov, o, sub, mask=mask, weights=w, gauss_width=gw)
+        tol = SIM_TOL if mode != "unweighted" else SIM_TOL * max(1.0, float(np.max(np.abs(ref))))
+        assert np.max(np.abs(got - ref)) <= tol, (mode, len(sub))
+    sm.reset_patches_to_use()
+    sm.compute()
+    np.testing.assert_array_equal(sm.sim_vals(), full)
+    # random patches: a fresh weighted draw per compute(), separated by the minimum distance
+    sm.seed_rand_patches(11)
+    sm.set_choose_rand_patches(True)
+    sm.set_num_rand_patches(30)
+    draws = []
+    for _ in range(2):
+        sm.compute()
+        inds = sm.patch_inds_to_use().copy()
+        assert inds.size == 30
+        ref = xo.patch_ncc_subset(fixed, mov, o, inds, mask=mask, weights=w, gauss_width=gw)
+        tol = SIM_TOL if mode != "unweighted" else SIM_TOL * max(1.0, float(np.max(np.abs(ref))))
+        assert np.max(np.abs(sm.sim_vals() - ref)) <= tol
+        ncc_ = (shape[1] - 1 - 10) // 2 + 1
+        c = np.stack([5 + (inds // ncc_) * 2, 5 + (inds % ncc_) * 2], axis=1).astype(np.float64)
+        d = np.linalg.norm(c[:, None] - c[None], axis=2) + np.eye(30) * 1e9
+        assert d.min() >= np.sqrt(2.0 * 25) - 1e-9
+        if mask is not None:
+            assert np.all(w[inds.astype(np.int64)] > 0)      # never a patch of weight zero
+        draws.append(inds)
+    assert not np.array_equal(draws[0], draws[1])
+    sm.set_choose_rand_patches(False)
+    sm.compute()
+    np.testing.assert_array_equal(sm.sim_vals(), full)
+    with pytest.raises(xreg_b200.XregError):
+        sm.set_patches_to_use([n_p])

@@ -152,6 +152,37 @@ def test_oracle_patch_ncc_equals_the_reference_class_code(xo, seed):
             assert p_or.tobytes() == p_rf.tobytes(), kw
 
 
+@pytest.mark.parametrize("seed", range(16))
+def test_oracle_patch_subset_equals_the_reference_class_code(xo, seed):
+    """SURVEY a12: ImgSimMetric2DPatchCommon::set_patches_to_use (xregImgSimMetric2DPatchCommon.cpp:231-235, cut from the
+    reference) followed by the reference's ImgSimMetric2DPatchNCCCPU::compute over patch_inds_to_use_: the oracle's
+    xo_patch_ncc_subset gives the same scores bit for bit -- unordered subsets, repeated indices (the random patches are
+    drawn with replacement), a single patch, the whole grid in reverse."""
+    fixed, mov, mask, radius, stride, wgt_img = _metric_case(seed)
+    rows, cols = fixed.shape
+    rng = np.random.default_rng(77 + seed)
+    n_p = xo.num_patches(rows, cols, radius, stride)
+    subsets = [rng.integers(0, n_p, size=max(1, n_p // 3)), np.array([int(rng.integers(0, n_p))]), np.arange(n_p)[::-1],
+               np.repeat(rng.integers(0, n_p, size=3), 2)]
+    combos = [dict(), dict(compute_mean=True), dict(weight_sims=False)]
+    if mask is not None:
+        combos += [dict(mask_stats=True)]
+    for kw in combos:
+        opts = xo.patch_opts(radius=radius, stride=stride, **kw)
+        w_or = xo.patch_weights(rows, cols, opts, mask=mask, wgt_img=wgt_img)
+        need_w = (mask is not None and opts.use_mask_for_weighting) or wgt_img is not None
+        for sub in subsets:
+            s_or = xo.patch_ncc_subset(fixed, mov, opts, sub, mask=mask, weights=w_or if need_w else None, n_threads=1)
+            s_rf = ref_slice.patch_ncc_subset(fixed, mov, opts, sub, mask=mask, wgt_img=wgt_img)
+            assert np.array_equal(s_or, s_rf, equal_nan=True), (kw, len(sub), s_or, s_rf)
+    # the full grid in natural order is the plain metric
+    opts = xo.patch_opts(radius=radius, stride=stride)
+    w_or = xo.patch_weights(rows, cols, opts, mask=mask, wgt_img=wgt_img)
+    need_w = (mask is not None and opts.use_mask_for_weighting) or wgt_img is not None
+    full = xo.patch_ncc_subset(fixed, mov, opts, np.arange(n_p), mask=mask, weights=w_or if need_w else None, n_threads=1)
+    assert np.array_equal(full, xo.patch_ncc(fixed, mov, opts, mask=mask, weights=w_or if need_w else None, n_threads=1), equal_nan=True)
+
+
 def test_patch_mean_std_is_the_reference_code(xo):
     rng = np.random.default_rng(4)
     img = rng.standard_normal((20, 24)).astype(f32) * 3 + 1

@@ -103,6 +103,7 @@ SIGNATURES = {
     "xrc_sm_set_mask": [_VP, _U8P],
     "xrc_sm_set_grad_params": [_VP, _U32],
     "xrc_sm_set_patch_params": [_VP, _U32, _U32, C.c_int, C.c_int, C.c_int, _FP, _U64],
+    "xrc_sm_set_patch_subset": [_VP, C.POINTER(_U64), _U64],
     "xrc_sm_set_combine_mode": [_VP, C.c_int],
     "xrc_seqsum_f32": [_VP, _FP, _U32, _U64, C.c_int, _FP],
     "xrc_sm_bind_ray_caster": [_VP, _VP, _U32],

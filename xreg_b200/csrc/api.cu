@@ -187,6 +187,14 @@ struct xrc_sm
   uint64_t n_patches = 0;
   float divisor_f = 1.0f;
   int divide_f = 0;
+  // patch subset (ImgSimMetric2DPatchCommon::set_patches_to_use / random patches): local list of global patch indices
+  std::vector<uint32_t> h_subset;
+  bool subset_dirty = false;
+  uint32_t* d_subset = nullptr;
+  size_t d_subset_cap = 0;
+  float* d_sub_vals = nullptr;   // max_imgs x n_dirs x |subset|
+  size_t d_sub_vals_cap = 0;
+  float sub_divisor_f = 1.0f;
 };
 
 // projection buffer in use: own, or the lender's as it is NOW (the lender may have been re-allocated since)
@@ -1027,6 +1035,8 @@ int xrc_rc_set_cta_order(xrc_rc* rc, int order)
 }
 
 // ---------------------------------------------------------------- metrics
+static bool sm_is_patch_kind(int kind) { return kind == XRC_SM_PATCH_NCC || kind == XRC_SM_PATCH_GRAD_NCC; }
+
 int xrc_sm_create(xrc_ctx* ctx, int kind, xrc_sm** out)
 {
   XRC_CHECK_ARG(ctx && out, "xrc_sm_create: null argument");
@@ -1060,6 +1070,10 @@ static void sm_free_resources(xrc_sm* sm)
   dfree(sm->d_weights);
   dfree(sm->d_vals);
   dfree(sm->d_seq);
+  dfree(sm->d_subset);
+  dfree(sm->d_sub_vals);
+  sm->d_subset_cap = sm->d_sub_vals_cap = 0;
+  sm->subset_dirty = !sm->h_subset.empty();
   if (sm->h_sims)
     cudaFreeHost(sm->h_sims);
   sm->h_sims = nullptr;
@@ -1190,6 +1204,25 @@ int xrc_sm_set_patch_params(xrc_sm* sm, uint32_t radius, uint32_t stride, int co
     sm->has_weights = false;
   }
   sm->fixed_dirty = true;
+  return XRC_OK;
+}
+
+int xrc_sm_set_patch_subset(xrc_sm* sm, const uint64_t* patch_inds, uint64_t n)
+{
+  XRC_CHECK_ARG(sm, "null metric");
+  XRC_CHECK_ARG(sm_is_patch_kind(sm->kind), "xrc_sm_set_patch_subset: not a patch metric");
+  XRC_CHECK_ARG(n == 0 || patch_inds, "xrc_sm_set_patch_subset: null index list");
+  XRC_CHECK_ARG(n < (1ull << 31), "xrc_sm_set_patch_subset: too many indices");
+  if (sm->allocated)
+    for (uint64_t j = 0; j < n; ++j)
+      XRC_CHECK_ARG(patch_inds[j] < sm->n_patches, "xrc_sm_set_patch_subset: patch index outside the patch grid");
+  sm->h_subset.resize((size_t)n);
+  for (uint64_t j = 0; j < n; ++j)
+  {
+    XRC_CHECK_ARG(patch_inds[j] < (1ull << 32), "xrc_sm_set_patch_subset: patch index outside the patch grid");
+    sm->h_subset[(size_t)j] = (uint32_t)patch_inds[j];
+  }
+  sm->subset_dirty = true;
   return XRC_OK;
 }
 
@@ -1650,7 +1683,47 @@ int xrc_sm_compute(xrc_sm* sm)
   p.weights = sm->has_weights ? sm->d_weights : nullptr;
   p.weight_patch_sims = sm->weight_sims;
   p.partials = sm->d_partials;
-  const bool ref_order = sm->combine_mode != XRC_COMBINE_F64;
+  // a patch subset is always combined in the reference's order (its f64 form would need the gathered values anyway)
+  const bool use_subset = !sm->h_subset.empty();
+  const bool ref_order = sm->combine_mode != XRC_COMBINE_F64 || use_subset;
+  if (use_subset)
+  {
+    const size_t ns = sm->h_subset.size();
+    if (sm->subset_dirty)
+    {
+      for (size_t j = 0; j < ns; ++j)
+        XRC_CHECK_ARG(sm->h_subset[j] < sm->n_patches, "patch subset: index outside the patch grid");
+      if (sm->d_subset_cap < ns)
+      {
+        XRC_CUDA(cudaStreamSynchronize(st));
+        dfree(sm->d_subset);
+        XRC_CUDA(cudaMalloc(&sm->d_subset, ns * sizeof(uint32_t)));
+        sm->d_subset_cap = ns;
+      }
+      const size_t need = (size_t)sm->max_imgs * n_dirs * ns;
+      if (sm->d_sub_vals_cap < need)
+      {
+        XRC_CUDA(cudaStreamSynchronize(st));
+        dfree(sm->d_sub_vals);
+        XRC_CUDA(cudaMalloc(&sm->d_sub_vals, need * sizeof(float)));
+        sm->d_sub_vals_cap = need;
+      }
+      // pageable source: the copy is staged before the call returns, h_subset may change afterwards
+      XRC_CUDA(cudaMemcpyAsync(sm->d_subset, sm->h_subset.data(), ns * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+      // divisor of the subset (xregImgSimMetric2DPatchNCCCPU.cpp:268-285): subset size, or the sequential f32 sum of
+      // the subset's weights in subset order
+      if (sm->compute_mean)
+        sm->sub_divisor_f = (float)ns;
+      else if (sm->weight_sims)
+      {
+        volatile float tw = 0.0f;
+        for (size_t j = 0; j < ns; ++j)
+          tw = tw + (sm->has_weights ? sm->h_weights[sm->h_subset[j]] : 1.0f);
+        sm->sub_divisor_f = tw;
+      }
+      sm->subset_dirty = false;
+    }
+  }
   if (ref_order && !sm->d_vals)
   {
     // the mode was switched on after allocation
@@ -1670,9 +1743,16 @@ int xrc_sm_compute(xrc_sm* sm)
     q.n_seq = sm->n_imgs * n_dirs;
     q.out = sm->d_seq;
     q.serial = (sm->combine_mode == XRC_COMBINE_REFERENCE_SERIAL) ? 1 : 0;
+    if (use_subset)
+    {
+      XRC_TRY(launch_patch_gather(sm->d_vals, sm->d_subset, sm->d_sub_vals, sm->n_patches, (uint32_t)sm->h_subset.size(),
+                                  q.n_seq, st));
+      q.vals = sm->d_sub_vals;
+      q.n = sm->h_subset.size();
+    }
     XRC_TRY(launch_seqsum(q, st));
     f.seq_sums = sm->d_seq;
-    f.divisor_f = sm->divisor_f;
+    f.divisor_f = use_subset ? sm->sub_divisor_f : sm->divisor_f;
     f.divide = sm->divide_f;
   }
   f.partials = sm->d_partials;

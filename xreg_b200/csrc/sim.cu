@@ -1201,6 +1201,29 @@ int launch_seqsum(const SeqSumArgs& a, cudaStream_t st)
   return XRC_OK;
 }
 
+// Patch subsets (set_patches_to_use / random patches): dst[seq][j] = vals[seq][subset[j]], the per-patch values of the
+// LOCAL patch list in its own order (xregImgSimMetric2DPatchNCCCPU.cpp:204), ready for patch_seqsum_kernel
+__global__ void patch_gather_kernel(const float* __restrict__ vals, const uint32_t* __restrict__ subset, float* __restrict__ dst,
+                                    uint64_t n_patches, uint32_t n_subset)
+{
+  const float* __restrict__ v = vals + (size_t)blockIdx.y * n_patches;
+  float* __restrict__ d = dst + (size_t)blockIdx.y * n_subset;
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_subset; j += gridDim.x * blockDim.x)
+    d[j] = v[subset[j]];
+}
+
+int launch_patch_gather(const float* vals, const uint32_t* subset, float* dst, uint64_t n_patches, uint32_t n_subset,
+                        uint32_t n_seq, cudaStream_t st)
+{
+  if (!n_seq || !n_subset)
+    return XRC_OK;
+  const uint32_t bx = std::min<uint32_t>((n_subset + 255u) / 256u, 64u);
+  patch_gather_kernel<<<dim3(bx, n_seq), 256, 0, st>>>(vals, subset, dst, n_patches, n_subset);
+  count_launch();
+  XRC_CUDA(cudaGetLastError());
+  return XRC_OK;
+}
+
 int launch_patch_finalize(const PatchFinalizeArgs& a, cudaStream_t st)
 {
   if (!a.n_imgs)

@@ -109,6 +109,9 @@ struct SeqSumArgs
   int serial;
 };
 int launch_seqsum(const SeqSumArgs& a, cudaStream_t st);
+// dst[seq][j] = vals[seq][subset[j]] for n_seq sequences of n_patches values (patch subsets)
+int launch_patch_gather(const float* vals, const uint32_t* subset, float* dst, uint64_t n_patches, uint32_t n_subset,
+                        uint32_t n_seq, cudaStream_t st);
 
 int launch_grad(const GradArgs& a, cudaStream_t st);
 int launch_moments(const MomentArgs& a, cudaStream_t st);

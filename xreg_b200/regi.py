@@ -99,6 +99,8 @@ class Intensity2D3DObjFn:
             return np.zeros(0, dtype=f32)
         self._set_pop(n)
         self.rc._flush_params()
+        for sm in self.sims:
+            sm._pre_compute()   # random patch subsets are drawn per evaluation
         out = np.empty(n, dtype=f32)
         per_view = np.empty((self.n_views, n), dtype=f32)
         FP = C.POINTER(C.c_float)

@@ -104,13 +104,18 @@ class ImgSimMetric2D:
         """Blocking like the reference: similarity values are valid on return."""
         if not self._allocated:
             raise _lib.XregError("compute: resources not allocated")
+        self._pre_compute()
         check(self._lib.xrc_sm_compute(self.handle))
         if self._num_mov_imgs:
             check(self._lib.xrc_sm_read_sims(self.handle, self._sim_vals.ctypes.data_as(C.POINTER(C.c_float)),
                                              self._num_mov_imgs))
 
     def compute_async(self) -> None:
+        self._pre_compute()
         check(self._lib.xrc_sm_compute(self.handle))
+
+    def _pre_compute(self) -> None:
+        """Hook run before every compute (the patch metrics draw their random patch subset here)."""
 
     def sim_val(self, mov_img_idx: int) -> float:
         return float(self._sim_vals[mov_img_idx])
@@ -169,6 +174,13 @@ class ImgSimMetric2DPatchCommon:
         self._normalize_weights_as_prob = True
         self._wgt_img: Optional[np.ndarray] = None
         self._weights: Optional[np.ndarray] = None
+        # patch subsets (xregImgSimMetric2DPatchCommon.h:100-123, .cpp:231-241, 413-493)
+        self._choose_rand_patches = False
+        self._num_rand_patches = 100
+        self._rand_patch_min_pixels_sep = -1.0
+        self._patch_inds_to_use: Optional[np.ndarray] = None
+        self._do_not_update_patch_inds_to_use = False
+        self._rng = np.random.default_rng()
 
     def patch_radius(self) -> int:
         return self._patch_radius
@@ -213,8 +225,83 @@ class ImgSimMetric2DPatchCommon:
         return self._normalize_weights_as_prob
 
     def set_choose_rand_patches(self, b: bool) -> None:
-        if b:
-            raise _lib.UnsupportedOperationException("random patch subsets are not supported by the CUDA metrics")
+        self._choose_rand_patches = bool(b)
+        if not b and not self._do_not_update_patch_inds_to_use:
+            self._push_subset(None)
+
+    def choose_rand_patches(self) -> bool:
+        return self._choose_rand_patches
+
+    def set_num_rand_patches(self, n: int) -> None:
+        self._num_rand_patches = int(n)
+
+    def num_rand_patches(self) -> int:
+        return self._num_rand_patches
+
+    def set_rand_patch_min_pixels_sep(self, sep: float) -> None:
+        self._rand_patch_min_pixels_sep = float(sep)
+
+    def rand_patch_min_pixels_sep(self) -> float:
+        return self._rand_patch_min_pixels_sep
+
+    def seed_rand_patches(self, seed: int) -> None:
+        """The reference seeds from std::random_device (SeedRNGEngWithRandDev); tests want reproducible draws."""
+        self._rng = np.random.default_rng(seed)
+
+    def set_patches_to_use(self, patch_inds) -> None:
+        """set_patches_to_use (xregImgSimMetric2DPatchCommon.cpp:231-235): the metric is evaluated over this local
+        list of global patch indices, in list order, until reset_patches_to_use()."""
+        self._patch_inds_to_use = np.ascontiguousarray(patch_inds, dtype=np.uint64).reshape(-1)
+        self._do_not_update_patch_inds_to_use = True
+        self._push_subset(self._patch_inds_to_use)
+
+    def reset_patches_to_use(self) -> None:
+        self._patch_inds_to_use = None
+        self._do_not_update_patch_inds_to_use = False
+        self._push_subset(None)
+
+    def patch_inds_to_use(self) -> Optional[np.ndarray]:
+        return self._patch_inds_to_use
+
+    def patch_indices_to_use(self) -> np.ndarray:
+        """patch_indices_to_use (xregImgSimMetric2DPatchCommon.cpp:413-493): every patch, or num_rand_patches indices
+        drawn (with replacement) from the discrete distribution of the patch weights, rejecting candidates closer
+        than the minimum separation to an accepted one."""
+        n_p = self.num_patches()
+        if not self._choose_rand_patches:
+            return np.arange(n_p, dtype=np.uint64)
+        if not self._num_rand_patches < n_p:
+            raise _lib.XregError("patch_indices_to_use: num_rand_patches must be smaller than the number of patches")
+        w = self.compute_weights()
+        p = None if w is None else (w.astype(np.float64) / float(np.sum(w, dtype=np.float64)))
+        sep = self._rand_patch_min_pixels_sep
+        min_sep = float(np.sqrt(2.0 * self._patch_radius * self._patch_radius)) if sep < 0 else sep
+        check_sep = min_sep > 1.0e-8
+        r, st = self._patch_radius, self._patch_stride
+        ncc = (self._fixed.shape[1] - 1 - 2 * r) // st + 1
+        inds, centres = [], []
+        while len(inds) < self._num_rand_patches:
+            k = int(self._rng.choice(n_p, p=p))
+            if check_sep:
+                c = np.array([r + (k // ncc) * st, r + (k % ncc) * st], dtype=np.float64)
+                if any(np.linalg.norm(e - c) < min_sep for e in centres):
+                    continue
+                centres.append(c)
+            inds.append(k)
+        return np.asarray(inds, dtype=np.uint64)
+
+    def _push_subset(self, inds: Optional[np.ndarray]) -> None:
+        if inds is None or len(inds) == 0:
+            check(self._lib.xrc_sm_set_patch_subset(self.handle, None, 0))
+        else:
+            a = np.ascontiguousarray(inds, dtype=np.uint64)
+            check(self._lib.xrc_sm_set_patch_subset(self.handle, a.ctypes.data_as(C.POINTER(C.c_uint64)), a.size))
+
+    def _pre_compute(self) -> None:
+        # ImgSimMetric2DPatchNCCCPU::compute, xregImgSimMetric2DPatchNCCCPU.cpp:97-100: a fresh draw per compute()
+        if self._choose_rand_patches and not self._do_not_update_patch_inds_to_use:
+            self._patch_inds_to_use = self.patch_indices_to_use()
+            self._push_subset(self._patch_inds_to_use)
 
     COMBINE_MODES = {"reference": 0, "reference-serial": 1, "f64": 2}
 
@@ -300,6 +387,7 @@ class ImgSimMetric2DPatchNCCCUDA(ImgSimMetric2D, ImgSimMetric2DPatchCommon):
     """ImgSimMetric2DPatchNCCCPU (xregImgSimMetric2DPatchNCCCPU.cpp)."""
 
     KIND = _lib.SM_PATCH_NCC
+    _pre_compute = ImgSimMetric2DPatchCommon._pre_compute   # (the first base's hook is a no-op)
 
     def __init__(self, ctx: Context):
         ImgSimMetric2D.__init__(self, ctx)
@@ -317,6 +405,7 @@ class ImgSimMetric2DPatchGradNCCCUDA(ImgSimMetric2D, ImgSimMetric2DPatchCommon, 
     """ImgSimMetric2DPatchGradNCCCPU (xregImgSimMetric2DPatchGradNCCCPU.cpp:34-253)."""
 
     KIND = _lib.SM_PATCH_GRAD_NCC
+    _pre_compute = ImgSimMetric2DPatchCommon._pre_compute
 
     def __init__(self, ctx: Context):
         ImgSimMetric2D.__init__(self, ctx)
