@@ -148,7 +148,8 @@ def test_adapters_behind_the_reference_base_classes(ctx, xo, small_scene, tmp_pa
         np.testing.assert_array_equal(projs, mirror_projs)
         np.testing.assert_array_equal(last, mirror_projs[-1])
         np.testing.assert_array_equal(first_ocv, mirror_projs[0])
-        assert spacing[0] == f32(cam.det_col_spacing) and spacing[1] == f32(cam.det_row_spacing)
+        # proj(last) is a view of the LAST camera's image with that camera's spacing (xregRayCastBaseCPU.cpp:90-118)
+        assert spacing[0] == f32(cams[-1].det_col_spacing) and spacing[1] == f32(cams[-1].det_row_spacing)
         if kind.startswith("patch"):
             assert n_patches == (rows - 12) * (cols - 12)
         fn.close()
