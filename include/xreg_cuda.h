@@ -109,6 +109,9 @@ int xrc_rc_set_cta_order(xrc_rc* rc, int order);
 /* Device memory the ray caster's volume representation occupies right now (all volumes; payload stacks, the f32 source
  * kept for stacks built on demand, the empty-space maps).  Reported in bench.py's config. */
 int xrc_rc_volume_bytes(const xrc_rc* rc, uint64_t* bytes);
+/* The layout volume vol_idx really uses (XRC_LAYOUT_*): with XRC_LAYOUT_DEFAULT the library chooses the principal-axis
+ * stacks and falls back to one XY-quad stack when the record index does not fit 32 bits or device memory runs out. */
+int xrc_rc_volume_layout(const xrc_rc* rc, uint32_t vol_idx, int* layout);
 /* Empty-space trimming, default on.  Samples whose 8 corner voxels are all zero add +0 to the
  * sequential f32 sum of xregRayCastLineIntCPU.cpp:270-279, so the sum kernel does not fetch the leading
  * and trailing samples of a ray that a per-volume block map proves to be zero (air around the body,
@@ -341,6 +344,30 @@ int xrc_obj_fn_multi_share(uint32_t n_dev, uint32_t n_views, uint32_t n_poses, u
 int xrc_obj_fn_se3(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t n_views, uint32_t n_poses,
                    const float* params, const float* pre12, const float* post12, float* sims_out,
                    float* per_view_out);
+/* The regulariser of Intensity2D3DRegi::obj_fn (xregIntensity2D3DRegi.cpp:653-688) for the penalty the reference's
+ * multi-object apps use, Regi2D3DPenaltyFnSE3Mag with FoldNormDist densities
+ * (lib/regi/penalty_fns_2d_3d/xregRegi2D3DPenaltyFnSE3Mag.cpp:32-117, lib/basic_math/xregFoldNormDist.cpp; e.g.
+ * apps/hip_surgery/pao/frag_multi_view_regi_2d_3d/...main.cpp:303-309): per pose, the rotation angle and translation
+ * magnitude of  inter^-1 * init * cur * inter  (ComputeRotAngTransMag, xregRigidUtils.cpp:247-251) against folded
+ * normal densities, reg = (log Z_rot - log p_rot) + (log Z_trans - log p_trans).  All f32, host only. */
+typedef struct xrc_se3_penalty
+{
+  float rot_mean, rot_std;       /* FoldNormDist(m, s) of the rotation angle, radians */
+  float trans_mean, trans_std;   /* FoldNormDist(m, s) of the translation magnitude, mm */
+  int32_t use_coeffs;            /* set_img_sim_penalty_coefs was called: sim * img_sim_coeff + reg * penalty_coeff */
+  float img_sim_coeff, penalty_coeff;
+  int32_t inter_wrt_vol;         /* intermediate_frames_wrt_vol[obj] */
+  float inter_frame[12];         /* intermediate_frames[obj], row-major 3x4 */
+  float init_cam_to_vol[12];     /* regi_xform_guesses[obj], row-major 3x4 */
+} xrc_se3_penalty;
+/* reg_vals_out[p] for the n poses cam_wrt_obj (n x 12, the transforms handed to the ray caster).  Needs no device. */
+int xrc_se3_mag_penalty(const xrc_se3_penalty* pen, uint32_t n, const float* cam_wrt_obj, float* reg_vals_out);
+/* xrc_obj_fn_se3 plus the regulariser, as one call: sims_out[p] = sim[p] (* img_sim_coeff) + reg[p] (* penalty_coeff).
+ * The host evaluates the regulariser while the device ray casts.  penalty_out (optional): the unscaled reg values.
+ * pen == NULL: plain xrc_obj_fn_se3. */
+int xrc_obj_fn_se3_pen(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t n_views, uint32_t n_poses,
+                       const float* params, const float* pre12, const float* post12, const xrc_se3_penalty* pen,
+                       float* sims_out, float* per_view_out, float* penalty_out);
 /* ExpSE3(Pt6) (lib/transforms/xregRigidUtils.cpp:40-85) in f32; host only, needs no device. */
 void xrc_exp_se3(const float params[6], float out12[12]);
 

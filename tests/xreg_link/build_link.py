@@ -91,5 +91,85 @@ def build(force: bool = False) -> str:
     return BIN
 
 
+# ---- the reference's SE(3) magnitude penalty (Regi2D3DPenaltyFnSE3Mag + FoldNormDist) as a shared library, to pin
+# xrc_se3_mag_penalty: whole files lib/basic_math/xregFoldNormDist.cpp, xregDistInterface.cpp,
+# lib/regi/penalty_fns_2d_3d/xregRegi2D3DPenaltyFn.cpp, xregRegi2D3DPenaltyFnSE3Mag.cpp; LogSO3ToPt
+# (xregRotUtils.cpp:107-126) and ComputeRotAngTransMag (xregRigidUtils.cpp:246-251) by anchor
+PEN_LIB = os.path.join(OUT_DIR, "libxreg_refpenalty.so")
+PEN_WHOLE = ["lib/basic_math/xregFoldNormDist.cpp", "lib/basic_math/xregDistInterface.cpp",
+             "lib/regi/penalty_fns_2d_3d/xregRegi2D3DPenaltyFn.cpp", "lib/regi/penalty_fns_2d_3d/xregRegi2D3DPenaltyFnSE3Mag.cpp",
+             "lib/common/xregExceptionUtils.cpp", "lib/common/xregAssert.cpp"]
+PEN_WRAPPER = r'''
+#include <memory>
+#include "xregRegi2D3DPenaltyFnSE3Mag.h"
+#include "xregFoldNormDist.h"
+#include "xregPerspectiveXform.h"
+
+static xreg::FrameTransform from12(const float* a)
+{
+  xreg::FrameTransform t;
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 4; ++c)
+      t.matrix()(r, c) = a[4 * r + c];
+  return t;
+}
+
+extern "C" int xref_se3_mag_penalty(float rot_m, float rot_s, float trans_m, float trans_s, int inter_wrt_vol,
+                                    const float* inter12, const float* init12, unsigned n, const float* cams12, float* out)
+{
+  xreg::Regi2D3DPenaltyFnSE3Mag pen;
+  pen.rot_pdfs_per_obj = {std::make_shared<xreg::FoldNormDist>(rot_m, rot_s)};
+  pen.trans_pdfs_per_obj = {std::make_shared<xreg::FoldNormDist>(trans_m, trans_s)};
+  xreg::Regi2D3DPenaltyFn::ListOfFrameTransformLists cams(1);
+  for (unsigned p = 0; p < n; ++p)
+    cams[0].push_back(from12(cams12 + 12 * p));
+  pen.compute(cams, n, xreg::Regi2D3DPenaltyFn::CamList(), xreg::Regi2D3DPenaltyFn::CamAssocList(), {inter_wrt_vol != 0},
+              {from12(inter12)}, {from12(init12)}, nullptr);
+  for (unsigned p = 0; p < n; ++p)
+    out[p] = pen.reg_vals()[p];
+  return 0;
+}
+'''
+
+
+def _pen_slice():
+    out = ['#include "xregRotUtils.h"', '#include "xregRigidUtils.h"', "#include <cmath>", "#include <tuple>", ""]
+    ln = _lines("lib/transforms/xregRotUtils.cpp")
+    s, e = _cut_function(ln, r"^xreg::Pt3 xreg::LogSO3ToPt\(const Mat3x3& R\)")
+    out += ln[s:e + 1] + [""]
+    ln = _lines("lib/transforms/xregRigidUtils.cpp")
+    s, e = _cut_function(ln, r"^xreg::ComputeRotAngTransMag\(const FrameTransform& xform\)")
+    out += ln[s - 1:e + 1] + [""]     # the return type sits on the line before
+    return "\n".join(out)
+
+
+def build_penalty(force: bool = False) -> str:
+    if not os.path.isdir(REF):
+        return PEN_LIB
+    if not force and os.path.exists(PEN_LIB) and os.path.getmtime(PEN_LIB) >= os.path.getmtime(__file__):
+        return PEN_LIB
+    os.makedirs(OUT_DIR, exist_ok=True)
+    tmp = tempfile.mkdtemp(prefix="xreg_pen_")
+    try:
+        inc = includes() + ["-I", os.path.join(REF, "lib", "regi", "penalty_fns_2d_3d")]
+        cxx = ["g++", "-std=c++11", "-O1", "-ffp-contract=off", "-fPIC", "-DXREG_NO_TBB", "-include", "cmath"] + inc
+        srcs = [os.path.join(REF, w) for w in PEN_WHOLE]
+        for name, text in (("pen_slice.cpp", _pen_slice()), ("pen_wrapper.cpp", PEN_WRAPPER)):
+            path = os.path.join(tmp, name)
+            with open(path, "w") as f:
+                f.write(text)
+            srcs.append(path)
+        objs = []
+        for i, src in enumerate(srcs):
+            obj = os.path.join(tmp, "p%d.o" % i)
+            subprocess.run(cxx + ["-c", src, "-o", obj], check=True)
+            objs.append(obj)
+        subprocess.run(["g++", "-shared", "-o", PEN_LIB] + objs, check=True)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return PEN_LIB
+
+
 if __name__ == "__main__":
+    print(build_penalty(force="--force" in sys.argv))
     print(build(force="--force" in sys.argv))

@@ -40,6 +40,16 @@ class XrcCam(C.Structure):
     ]
 
 
+class XrcSe3Penalty(C.Structure):
+    """xrc_se3_penalty (include/xreg_cuda.h)"""
+
+    _fields_ = [
+        ("rot_mean", C.c_float), ("rot_std", C.c_float), ("trans_mean", C.c_float), ("trans_std", C.c_float),
+        ("use_coeffs", C.c_int32), ("img_sim_coeff", C.c_float), ("penalty_coeff", C.c_float),
+        ("inter_wrt_vol", C.c_int32), ("inter_frame", C.c_float * 12), ("init_cam_to_vol", C.c_float * 12),
+    ]
+
+
 class XregError(RuntimeError):
     """StringMessageException / AssertFailedException analogue
     (lib/common/xregExceptionUtils.h:36-63, lib/common/xregAssert.h:30-41)."""
@@ -95,6 +105,7 @@ SIGNATURES = {
     "xrc_rc_use_other_proj_buf": [_VP, _VP],
     "xrc_rc_ray_info": [_VP, _U32, _U8P, _U32P, C.POINTER(_U64)],
     "xrc_rc_volume_bytes": [_VP, C.POINTER(_U64)],
+    "xrc_rc_volume_layout": [_VP, _U32, C.POINTER(C.c_int)],
     "xrc_rc_set_skip_empty": [_VP, C.c_int],
     "xrc_rc_fetched_samples": [_VP, _U32, C.POINTER(_U64)],
     "xrc_sm_create": [_VP, C.c_int, C.POINTER(_VP)],
@@ -125,6 +136,8 @@ SIGNATURES = {
     "xrc_obj_fn_units_enqueue": [_VP, _U32, C.POINTER(_VP), _U32, _U32, _FP, _U32, _U32],
     "xrc_obj_fn_multi_share": [_U32, _U32, _U32, _U32, _U32, _U32P, _U32P],
     "xrc_exp_se3": [_FP, _FP],
+    "xrc_se3_mag_penalty": [C.POINTER(XrcSe3Penalty), _U32, _FP, _FP],
+    "xrc_obj_fn_se3_pen": [_VP, _U32, C.POINTER(_VP), _U32, _U32, _FP, _FP, _FP, C.POINTER(XrcSe3Penalty), _FP, _FP, _FP],
 }
 _RESTYPES = {"xrc_last_error": C.c_char_p, "xrc_launch_count": C.c_uint64, "xrc_exp_se3": None}
 

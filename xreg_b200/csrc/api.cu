@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <limits>
 #include <memory>
 
 #include "common.h"
@@ -819,6 +820,22 @@ static int rc_prepare_stacks(xrc_rc* rc, uint32_t vol_idx)
       cudaGetLastError();   // no room for another stack: the kernel keeps falling back to one that exists
       continue;
     }
+    if (s == XRC_ERR_NOMEM && v.src && rc->layout == XRC_LAYOUT_DEFAULT)
+    {
+      // not even one padded stack fits: the unpadded XY-quad stack of the measurement layouts instead (same
+      // samples to 1 ulp of the lerp chain, slower for views along x; reported by xrc_rc_volume_layout)
+      cudaGetLastError();
+      float* lin = v.src;
+      v.src = nullptr;
+      if (v.occ)
+        cudaFree(v.occ);
+      v.occ = nullptr;
+      const int s2 = repack_volume(lin, &v, XRC_LAYOUT_QUAD, rc->ctx->stream);
+      cudaStreamSynchronize(rc->ctx->stream);
+      cudaFree(lin);
+      XRC_TRY(s2);
+      return XRC_OK;
+    }
     XRC_TRY(s);
   }
   if (!(v.pax[0] || v.pax[1] || v.pax[2]))
@@ -885,6 +902,14 @@ int xrc_rc_compute(xrc_rc* rc, uint32_t vol_idx)
   DrrArgs a;
   rc_fill_args(rc, vol_idx, &a);
   return launch_drr(a, rc->vols[vol_idx].layout, rc->kernel_id, rc->ctx->stream);
+}
+
+int xrc_rc_volume_layout(const xrc_rc* rc, uint32_t vol_idx, int* layout)
+{
+  XRC_CHECK_ARG(rc && layout, "null argument");
+  XRC_CHECK_ARG(vol_idx < rc->vols.size(), "xrc_rc_volume_layout: volume index out of range");
+  *layout = rc->vols[vol_idx].layout;
+  return XRC_OK;
 }
 
 int xrc_rc_volume_bytes(const xrc_rc* rc, uint64_t* bytes)
@@ -2219,20 +2244,142 @@ int xrc_obj_fn_multi(uint32_t n_dev, xrc_rc* const* rcs, xrc_sm* const* sms, uin
   return XRC_OK;
 }
 
-int xrc_obj_fn_se3(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t n_views, uint32_t n_poses,
-                   const float* params, const float* pre12, const float* post12, float* sims_out, float* per_view_out)
+// ---- SE(3) magnitude penalty (Regi2D3DPenaltyFnSE3Mag + FoldNormDist), host arithmetic in f32 in the reference's order
+namespace
 {
-  XRC_CHECK_ARG(params, "xrc_obj_fn_se3: null parameters");
-  std::vector<float> poses((size_t)n_poses * 12);
+// FoldNormDist (lib/basic_math/xregFoldNormDist.cpp:30-70)
+struct FoldNorm
+{
+  float m, s, two_s_sq, norm_const, log_norm_const;
+  FoldNorm(float m_arg, float s_arg)
+      : m(m_arg), s(s_arg), two_s_sq(2 * s_arg * s_arg), norm_const(std::sqrt(two_s_sq * 3.141592653589793f)),
+        log_norm_const(std::log(norm_const))
+  {
+  }
+  float exp_helper(float x) const
+  {
+    const float x_minus_m = x - m, x_plus_m = x + m;
+    return std::exp((x_minus_m * x_minus_m) / -two_s_sq) + std::exp((x_plus_m * x_plus_m) / -two_s_sq);
+  }
+  float log_density(float x) const
+  {
+    if (x >= 0)
+    {
+      const float un_norm_prob = exp_helper(x);
+      return (un_norm_prob > 1.0e-14f) ? (std::log(un_norm_prob) - log_norm_const) : std::numeric_limits<float>::lowest();
+    }
+    return -std::numeric_limits<float>::infinity();
+  }
+};
+
+// ComputeRotAngTransMag (lib/transforms/xregRigidUtils.cpp:247-251) with LogSO3ToPt (xregRotUtils.cpp:107-126)
+void rot_ang_trans_mag(const float T[12], float* rot, float* trans)
+{
+  const float theta = std::acos((T[0] + T[5] + T[10] - 1) / 2);
+  float x[3] = {0.f, 0.f, 0.f};
+  if (std::abs(theta) > 1.0e-14f)
+  {
+    x[0] = T[9] - T[6];
+    x[1] = T[2] - T[8];
+    x[2] = T[4] - T[1];
+    const float k = theta / (2 * std::sin(theta));
+    for (int i = 0; i < 3; ++i)
+      x[i] *= k;
+  }
+  *rot = std::sqrt((x[0] * x[0] + x[1] * x[1]) + x[2] * x[2]);
+  *trans = std::sqrt((T[3] * T[3] + T[7] * T[7]) + T[11] * T[11]);
+}
+}  // namespace
+
+int xrc_se3_mag_penalty(const xrc_se3_penalty* pen, uint32_t n, const float* cam_wrt_obj, float* reg_vals_out)
+{
+  XRC_CHECK_ARG(pen && reg_vals_out && (n == 0 || cam_wrt_obj), "xrc_se3_mag_penalty: null argument");
+  XRC_CHECK_ARG(pen->rot_std > 0.f && pen->trans_std > 0.f, "xrc_se3_mag_penalty: standard deviations must be positive");
+  const FoldNorm rot_pdf(pen->rot_mean, pen->rot_std), trans_pdf(pen->trans_mean, pen->trans_std);
+  // xregRegi2D3DPenaltyFnSE3Mag.cpp:70-77
+  float inter_inv[12], init_vol_to_cam[12], init_X_to_inter[12];
+  affine_inverse_f32(pen->inter_frame, inter_inv);
+  affine_inverse_f32(pen->init_cam_to_vol, init_vol_to_cam);
+  affine_mul(inter_inv, pen->inter_wrt_vol ? pen->init_cam_to_vol : init_vol_to_cam, init_X_to_inter);
+  for (uint32_t p = 0; p < n; ++p)
+  {
+    // :86-103
+    const float* cur = cam_wrt_obj + 12 * (size_t)p;
+    float tmp[12], cur_inter_to_X[12], M[12];
+    if (pen->inter_wrt_vol)
+    {
+      affine_inverse_f32(cur, tmp);
+      affine_mul(tmp, pen->inter_frame, cur_inter_to_X);
+    }
+    else
+      affine_mul(cur, pen->inter_frame, cur_inter_to_X);
+    affine_mul(init_X_to_inter, cur_inter_to_X, M);
+    float rot_err, trans_err;
+    rot_ang_trans_mag(M, &rot_err, &trans_err);
+    const float rot_lp = rot_pdf.log_density(rot_err), trans_lp = trans_pdf.log_density(trans_err);
+    reg_vals_out[p] = 0.0f + (rot_pdf.log_norm_const - rot_lp + trans_pdf.log_norm_const - trans_lp);
+  }
+  return XRC_OK;
+}
+
+static void compose_se3_poses(uint32_t n_poses, const float* params, const float* pre12, const float* post12, float* poses)
+{
   for (uint32_t p = 0; p < n_poses; ++p)
   {
-    float* T = poses.data() + 12 * (size_t)p;
+    float* T = poses + 12 * (size_t)p;
     xrc_exp_se3(params + 6 * (size_t)p, T);
     if (pre12)
       affine_mul(pre12, T, T);
     if (post12)
       affine_mul(T, post12, T);
   }
+}
+
+int xrc_obj_fn_se3_pen(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t n_views, uint32_t n_poses,
+                       const float* params, const float* pre12, const float* post12, const xrc_se3_penalty* pen,
+                       float* sims_out, float* per_view_out, float* penalty_out)
+{
+  XRC_CHECK_ARG(params && sims_out, "xrc_obj_fn_se3_pen: null argument");
+  if (!pen)
+    return xrc_obj_fn_se3(rc, vol_idx, sms, n_views, n_poses, params, pre12, post12, sims_out, per_view_out);
+  if (!n_poses)
+    return XRC_OK;
+  std::vector<float> poses((size_t)n_poses * 12), reg(n_poses), tmp;
+  compose_se3_poses(n_poses, params, pre12, post12, poses.data());
+  // the device works on the projections while the host evaluates the regulariser of the same poses
+  XRC_TRY(obj_fn_enqueue(rc, vol_idx, sms, n_views, n_poses, poses.data()));
+  const int ps = xrc_se3_mag_penalty(pen, n_poses, poses.data(), reg.data());
+  float* pv = per_view_out;
+  if (!pv)
+  {
+    tmp.resize((size_t)n_views * n_poses);
+    pv = tmp.data();
+  }
+  XRC_TRY(obj_fn_finish(rc, sms, n_views, n_poses, pv, n_poses));
+  XRC_TRY(ps);
+  combine_mean(pv, n_views, n_poses, sims_out);
+  // Intensity2D3DRegi::obj_fn, xregIntensity2D3DRegi.cpp:653-688
+  for (uint32_t p = 0; p < n_poses; ++p)
+  {
+    if (penalty_out)
+      penalty_out[p] = reg[p];
+    float sv = sims_out[p], rv = reg[p];
+    if (pen->use_coeffs)
+    {
+      sv *= pen->img_sim_coeff;
+      rv *= pen->penalty_coeff;
+    }
+    sims_out[p] = sv + rv;
+  }
+  return XRC_OK;
+}
+
+int xrc_obj_fn_se3(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t n_views, uint32_t n_poses,
+                   const float* params, const float* pre12, const float* post12, float* sims_out, float* per_view_out)
+{
+  XRC_CHECK_ARG(params, "xrc_obj_fn_se3: null parameters");
+  std::vector<float> poses((size_t)n_poses * 12);
+  compose_se3_poses(n_poses, params, pre12, post12, poses.data());
   return xrc_obj_fn(rc, vol_idx, sms, n_views, n_poses, poses.data(), sims_out, per_view_out);
 }
 

@@ -66,12 +66,13 @@ struct DeviceVolume
   // XRC_LAYOUT_PAX: one padded XY-quad record stack per principal ray axis k
   // (slow axis c = k, fast a = (k+1)%3, mid b = (k+2)%3); see drr.cu
   // Stacks are built ON DEMAND (build_pax_stack): only the principal axes the current cameras x poses can select
-  // exist, from the f32 copy `src` kept until all three are built (a single-view registration lives on one stack:
-  // 4x + 1x the volume instead of 12x).  A CTA whose preferred stack is missing uses any built one (same samples).
+  // exist -- the first from the f32 copy `src` (dropped right after), further ones from an existing stack, whose
+  // records keep the voxel values unchanged (a single-view registration lives on one stack: 4x the volume instead of
+  // 12x).  A CTA whose preferred stack is missing uses any built one (same samples).
   void* pax[3] = {nullptr, nullptr, nullptr};
   uint32_t pax_sb[3] = {0, 0, 0};   // record strides of the mid / slow axis
   uint32_t pax_sc[3] = {0, 0, 0};
-  float* src = nullptr;             // x-fastest f32 volume on the device (PAX only; freed once all stacks exist)
+  float* src = nullptr;             // x-fastest f32 volume on the device (PAX only; until the first stack is built)
   uint32_t* h_want = nullptr;       // 3 words of host-mapped pinned memory: a CTA that had to fall back from stack k
                                     // stores 1 to word k; the next compute() builds that stack (drr.cu, api.cu)
   // empty-space map (drr.cu, "empty-space trimming"): one bit per 8^3-voxel block, set when any voxel of the

@@ -1188,29 +1188,52 @@ __global__ void repack_oct_kernel(const float* __restrict__ src, float4* __restr
 
 // stack k of XRC_LAYOUT_PAX: A x B x C records, A >= n[a]+1, B >= n[b]+1 (row / plane pitch, see pax_pitch), C = n[c]+2;
 // records beyond n[a] / n[b] are never addressed (they hold replicated edge values like the border)
-__global__ void repack_pax_kernel(const float* __restrict__ src, float4* __restrict__ dst, int nx, int ny, int nz, int k,
-                                  int A, int B)
+
+// The f32 volume read back out of a built stack: record (ia, ib, ic) of stack j keeps v(ia, ib, ic) unchanged in .x, so
+// a further stack can be built from any existing one and the f32 copy need not stay resident.
+struct PaxSource
+{
+  const float* lin;      // x-fastest f32 volume, or null
+  const float4* stack;   // else: stack j
+  int j;
+  uint32_t sb, sc;
+};
+
+__device__ __forceinline__ float pax_source_voxel(const PaxSource& s, int x, int y, int z, int nx, int ny)
+{
+  if (s.lin)
+    return s.lin[((size_t)z * ny + y) * nx + x];
+  const int i[3] = {x, y, z};
+  const int ja = (s.j + 1) % 3, jb = (s.j + 2) % 3;
+  return s.stack[(size_t)(i[s.j] + 1) * s.sc + (size_t)(i[jb] + 1) * s.sb + (size_t)(i[ja] + 1)].x;
+}
+
+__global__ void repack_pax_from_kernel(const PaxSource src, float4* __restrict__ dst, int nx, int ny, int nz, int k, int A, int B)
 {
   const int n[3] = {nx, ny, nz};
   const int ka = (k + 1) % 3, kb = (k + 2) % 3;
   const int C = n[k] + 2;
   const size_t total = (size_t)A * B * C;
-  const size_t st[3] = {1, (size_t)nx, (size_t)nx * ny};
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
   {
     const int ia = (int)(i % A) - 1;
     const int ib = (int)((i / A) % B) - 1;
     const int ic = (int)(i / ((size_t)A * B)) - 1;
-    const int a0 = min(max(ia, 0), n[ka] - 1), a1 = min(max(ia + 1, 0), n[ka] - 1);
-    const int b0 = min(max(ib, 0), n[kb] - 1), b1 = min(max(ib + 1, 0), n[kb] - 1);
-    const int c0 = min(max(ic, 0), n[k] - 1);
-    const float* p = src + (size_t)c0 * st[k];
-    const double v00 = p[a0 * st[ka] + b0 * st[kb]], v10 = p[a1 * st[ka] + b0 * st[kb]];
-    const double v01 = p[a0 * st[ka] + b1 * st[kb]], v11 = p[a1 * st[ka] + b1 * st[kb]];
+    int p0[3], p1[3];
+    p0[ka] = min(max(ia, 0), n[ka] - 1), p1[ka] = min(max(ia + 1, 0), n[ka] - 1);
+    p0[kb] = min(max(ib, 0), n[kb] - 1), p1[kb] = min(max(ib + 1, 0), n[kb] - 1);
+    p0[k] = p1[k] = min(max(ic, 0), n[k] - 1);
+    int q[3] = {p0[0], p0[1], p0[2]};
+    const double v00 = pax_source_voxel(src, q[0], q[1], q[2], nx, ny);
+    q[ka] = p1[ka];
+    const double v10 = pax_source_voxel(src, q[0], q[1], q[2], nx, ny);
+    q[kb] = p1[kb];
+    const double v11 = pax_source_voxel(src, q[0], q[1], q[2], nx, ny);
+    q[ka] = p0[ka];
+    const double v01 = pax_source_voxel(src, q[0], q[1], q[2], nx, ny);
     dst[i] = make_float4((float)v00, (float)(v10 - v00), (float)(v01 - v00), (float)((v11 - v10) - (v01 - v00)));
   }
 }
-
 
 // Row pitch A (records) and plane pitch A * B of a PAX stack.  Measurement knob: XRC_PAX_PITCH="ra,rb" rounds the
 // row pitch up to ra (mod 8 records = mod one 128-byte line) and B so that the plane pitch is rb (mod 8).
@@ -1368,8 +1391,25 @@ int build_pax_stack(DeviceVolume* v, int k, cudaStream_t st)
 {
   if (v->pax[k])
     return XRC_OK;
+  PaxSource src;
+  src.lin = v->src;
+  src.stack = nullptr;
+  src.j = 0;
+  src.sb = src.sc = 0;
   if (!v->src)
-    XRC_FAIL(XRC_ERR_INVALID, "build_pax_stack: the f32 source of the volume is gone");
+  {
+    // no f32 copy any more: read the voxels back out of a stack that exists
+    for (int j = 0; j < 3 && !src.stack; ++j)
+      if (v->pax[j])
+      {
+        src.stack = (const float4*)v->pax[j];
+        src.j = j;
+        src.sb = v->pax_sb[j];
+        src.sc = v->pax_sc[j];
+      }
+    if (!src.stack)
+      XRC_FAIL(XRC_ERR_INVALID, "build_pax_stack: the volume has neither its f32 source nor a stack");
+  }
   const int n[3] = {(int)v->dims[0], (int)v->dims[1], (int)v->dims[2]};
   size_t A = (size_t)n[(k + 1) % 3] + 1, B = (size_t)n[(k + 2) % 3] + 1;
   const size_t C = (size_t)n[k] + 2;
@@ -1378,12 +1418,12 @@ int build_pax_stack(DeviceVolume* v, int k, cudaStream_t st)
   v->pax_sb[k] = (uint32_t)A;
   v->pax_sc[k] = (uint32_t)(A * B);
   v->bytes += sizeof(float4) * A * B * C;
-  repack_pax_kernel<<<148 * 8, 256, 0, st>>>(v->src, (float4*)v->pax[k], n[0], n[1], n[2], k, (int)A, (int)B);
+  repack_pax_from_kernel<<<148 * 8, 256, 0, st>>>(src, (float4*)v->pax[k], n[0], n[1], n[2], k, (int)A, (int)B);
   count_launch();
   XRC_CUDA(cudaGetLastError());
-  if (v->pax[0] && v->pax[1] && v->pax[2])
+  if (v->src)
   {
-    // all three exist: the f32 copy has served its purpose
+    // the first stack exists: further ones are built from it, the f32 copy has served its purpose
     XRC_CUDA(cudaStreamSynchronize(st));
     v->bytes -= sizeof(float) * (size_t)n[0] * n[1] * n[2];
     cudaFree(v->src);

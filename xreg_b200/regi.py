@@ -177,23 +177,63 @@ class Intensity2D3DObjFn:
             sm._sim_vals[:n] = per_view[v]
         return out
 
-    def eval_se3(self, params: np.ndarray, pre: Optional[np.ndarray] = None, post: Optional[np.ndarray] = None) -> np.ndarray:
+    def eval_se3(self, params: np.ndarray, pre: Optional[np.ndarray] = None, post: Optional[np.ndarray] = None,
+                 penalty: Optional["_lib.XrcSe3Penalty"] = None) -> np.ndarray:
         """Objective from optimiser variables (SE3OptVarsLieAlg, xregSE3OptVars.cpp:128-137):
-        pose_p = pre * ExpSE3(params_p) * post (xregIntensity2D3DRegi.cpp:1049-1071), composed inside the library."""
+        pose_p = pre * ExpSE3(params_p) * post (xregIntensity2D3DRegi.cpp:1049-1071), composed inside the library;
+        with `penalty` (se3_penalty()) the regulariser of xregIntensity2D3DRegi.cpp:653-688 is added in the same call
+        (self.last_penalty holds the unscaled values)."""
         x = np.ascontiguousarray(params, dtype=f32).reshape(-1, 6)
         n = x.shape[0]
         if n == 0:
             return np.zeros(0, dtype=f32)
         self._set_pop(n)
         self.rc._flush_params()
+        for sm in self.sims:
+            sm._pre_compute()
         out = np.empty(n, dtype=f32)
         FP = C.POINTER(C.c_float)
-        pre12 = None if pre is None else to12(pre).ctypes.data_as(FP)
-        post12 = None if post is None else to12(post).ctypes.data_as(FP)
-        _lib.check(self._lib.xrc_obj_fn_se3(self.rc.handle, 0, self._sm_arr, self.n_views, n, x.ctypes.data_as(FP),
-                                            pre12, post12, out.ctypes.data_as(FP), None))
+        pre_a = None if pre is None else to12(np.asarray(pre, f32)[None])
+        post_a = None if post is None else to12(np.asarray(post, f32)[None])
+        pre12 = None if pre_a is None else pre_a.ctypes.data_as(FP)
+        post12 = None if post_a is None else post_a.ctypes.data_as(FP)
+        if penalty is None:
+            _lib.check(self._lib.xrc_obj_fn_se3(self.rc.handle, 0, self._sm_arr, self.n_views, n, x.ctypes.data_as(FP),
+                                                pre12, post12, out.ctypes.data_as(FP), None))
+        else:
+            self.last_penalty = np.empty(n, dtype=f32)
+            _lib.check(self._lib.xrc_obj_fn_se3_pen(self.rc.handle, 0, self._sm_arr, self.n_views, n, x.ctypes.data_as(FP),
+                                                    pre12, post12, C.byref(penalty), out.ctypes.data_as(FP), None,
+                                                    self.last_penalty.ctypes.data_as(FP)))
         self.rc._poses_dirty = False
         return out
+
+
+def se3_penalty(rot_mean: float, rot_std: float, trans_mean: float, trans_std: float,
+                inter_frame: Optional[np.ndarray] = None, init_cam_to_vol: Optional[np.ndarray] = None,
+                inter_wrt_vol: bool = True, img_sim_coeff: Optional[float] = None,
+                penalty_coeff: Optional[float] = None) -> "_lib.XrcSe3Penalty":
+    """Regi2D3DPenaltyFnSE3Mag with FoldNormDist(rot_mean, rot_std) / FoldNormDist(trans_mean, trans_std) for one object
+    (xregRegi2D3DPenaltyFnSE3Mag.cpp, xregFoldNormDist.cpp); coefficients as set_img_sim_penalty_coefs."""
+    p = _lib.XrcSe3Penalty()
+    p.rot_mean, p.rot_std, p.trans_mean, p.trans_std = float(rot_mean), float(rot_std), float(trans_mean), float(trans_std)
+    p.use_coeffs = 0 if img_sim_coeff is None and penalty_coeff is None else 1
+    p.img_sim_coeff = 1.0 if img_sim_coeff is None else float(img_sim_coeff)
+    p.penalty_coeff = 1.0 if penalty_coeff is None else float(penalty_coeff)
+    p.inter_wrt_vol = 1 if inter_wrt_vol else 0
+    eye = np.eye(4, dtype=f32)
+    p.inter_frame[:] = [float(v) for v in to12((eye if inter_frame is None else np.asarray(inter_frame, f32))[None])[0]]
+    p.init_cam_to_vol[:] = [float(v) for v in to12((eye if init_cam_to_vol is None else np.asarray(init_cam_to_vol, f32))[None])[0]]
+    return p
+
+
+def se3_mag_penalty(pen: "_lib.XrcSe3Penalty", poses: np.ndarray) -> np.ndarray:
+    """reg_vals of Regi2D3DPenaltyFnSE3Mag::compute for the poses (n, 4, 4) / (n, 12) handed to the ray caster (host only)."""
+    p12 = to12(poses) if np.asarray(poses).ndim == 3 else np.ascontiguousarray(poses, dtype=f32).reshape(-1, 12)
+    out = np.empty(p12.shape[0], dtype=f32)
+    FP = C.POINTER(C.c_float)
+    _lib.check(_lib.load().xrc_se3_mag_penalty(C.byref(pen), p12.shape[0], p12.ctypes.data_as(FP), out.ctypes.data_as(FP)))
+    return out
 
 
 def multi_device_share(n_dev: int, n_views: int, n_poses: int, dev: int, view: int) -> Tuple[int, int]:
