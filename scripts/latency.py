@@ -36,7 +36,7 @@ def main():
         fixed = synth.add_noise(rc0.proj(0))
         rc0.close()
         fn = regi.Intensity2D3DObjFn(ctx, vol, [cam], [fixed], metric=metric, max_pop=100,
-                                     patch_radius=synth.patch_radius_for(det))
+                                     patch_radius=synth.patch_radius_for(det), layout=os.environ.get("LAT_LAYOUT", "default"))
         if os.environ.get("LAT_VARIANT"):   # kernel variant bits (drr.cu launch_pax_k), measurement only
             fn.rc.set_layout_order(int(os.environ["LAT_VARIANT"]) << 1)
         for pop_n in ((1, 100) if not only else (int(only.split(",")[2]),)):
@@ -49,7 +49,8 @@ def main():
             for k in range(reps):
                 fn(pops[(k % 50):(k % 50) + pop_n] if pop_n == 1 else pops)
             dt = (time.perf_counter() - t0) / reps
-            print(json.dumps({"det": det, "metric": metric, "pop": pop_n, "ms_per_call": dt * 1e3,
+            print(json.dumps({"det": det, "metric": metric, "pop": pop_n, "layout": os.environ.get("LAT_LAYOUT", "default"),
+                              "deep": os.environ.get("XRC_PAX_DEEP", ""), "ms_per_call": dt * 1e3,
                               "poses_per_s": pop_n / dt}), flush=True)
         del fn
 

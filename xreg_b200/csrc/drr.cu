@@ -1023,7 +1023,12 @@ static int launch_pax_k(const DrrArgs& a, cudaStream_t st)
     // loop does not need and measured 1 % slower).  Throughput regime (a CMA-ES population: more CTAs than fit
     // at once): one sample group in flight ahead, 5 CTAs / 40 warps per SM.  Few CTAs (one wave): spend the
     // idle registers on a deeper software pipeline.  All variants add the same values in the same order.
-    if (nblocks <= 148u * 2u)
+    // at most one CTA per SM (a 192 x 192 detector, one pose): every ray is a chain of L2 / HBM-latency load groups
+    // and registers are free: 8 sample groups in flight (population 1 at 192^2: 102 -> 98 us per evaluation)
+    static const int deep = getenv("XRC_PAX_DEEP") ? atoi(getenv("XRC_PAX_DEEP")) : 8;   // 4: the round-1 pipeline (measurement)
+    if (deep == 8 && nblocks <= 160u)
+      drr_pax_kernel<KERNEL_ID, false, 8, 1><<<nblocks, kThreads, 0, st>>>(a);
+    else if (nblocks <= 148u * 2u)
       drr_pax_kernel<KERNEL_ID, false, 4, 2><<<nblocks, kThreads, 0, st>>>(a);
     else if (nblocks <= 148u * 4u)
       drr_pax_kernel<KERNEL_ID, false, 2, 4><<<nblocks, kThreads, 0, st>>>(a);
