@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 
 import xreg_b200
+from xreg_b200 import synth
 from xreg_b200.geometry import CameraModel, Volume, to12
 
 pytestmark = pytest.mark.gpu
@@ -181,3 +182,75 @@ def test_random_metric_case_matches_oracle(ctx, xo, seed):
         assert np.all(np.abs(got - ref) <= 1e-5 * ref + 1e-9 * max(float(ref.max()), 1e-30))
     else:
         assert np.max(np.abs(got - ref)) <= 1.0e-5, (kind, rows, cols, radius, stride, width, mask is not None)
+
+
+def _hdr_volume(rng, dims, kind):
+    """High-dynamic-range volumes: metal next to air, where the difference-form records
+    (drr.cu, pax_lerp: coefficients dA, dB, dAB rounded once; per-sample error ~ ulp of the largest corner) are weakest."""
+    nx, ny, nz = dims
+    if kind == 0:      # soft tissue 0.02 with metal blocks (3.0) and air pockets (0) with sharp faces
+        data = np.full((nz, ny, nx), 0.02, f32)
+        for _ in range(6):
+            c = [int(rng.integers(0, d)) for d in (nz, ny, nx)]
+            r = [int(rng.integers(1, 5)) for _ in range(3)]
+            val = f32(3.0) if rng.random() < 0.5 else f32(0.0)
+            data[max(0, c[0] - r[0]):c[0] + r[0], max(0, c[1] - r[1]):c[1] + r[1], max(0, c[2] - r[2]):c[2] + r[2]] = val
+    elif kind == 1:    # isolated metal voxels and wires in air
+        data = np.zeros((nz, ny, nx), f32)
+        for _ in range(12):
+            data[int(rng.integers(0, nz)), int(rng.integers(0, ny)), int(rng.integers(0, nx))] = f32(rng.choice([3.0, 10.0, 0.5]))
+        data[nz // 2, ny // 2, :] = f32(7.5)      # a wire along x
+        data[:, ny // 3, nx // 3] = f32(2.25)     # and one along z
+    elif kind == 2:    # a CT in Hounsfield units with a metal implant, converted like the reference (HUToLinAtt)
+        hu = rng.uniform(-1000.0, 1500.0, (nz, ny, nx)).astype(f32)
+        hu[nz // 4:nz // 2, ny // 4:ny // 2, nx // 4:nx // 2] = f32(30000.0)      # saturated metal
+        hu[:2] = f32(-1000.0)
+        return hu, True
+    else:              # eight decades: 1e-6 background, 1e2 inserts, checkerboard of the two on one face
+        data = np.full((nz, ny, nx), 1.0e-6, f32)
+        data[::2, ::2, ::2] = f32(1.0e2)
+        data[nz // 2:] = f32(1.0e-6)
+    return data, False
+
+
+@pytest.mark.parametrize("seed", range(16 * _SCALE))
+def test_high_dynamic_range_volume_matches_oracle(ctx, xo, seed):
+    rng = np.random.default_rng(31000 + seed)
+    dims = [int(rng.integers(6, 36)) for _ in range(3)]
+    data, is_hu = _hdr_volume(rng, dims, seed % 4)
+    spacing = tuple(float(s) for s in rng.uniform(0.5, 1.5, 3))
+    vol = Volume(data, spacing=spacing, origin=(-10.0, 5.0, 3.0), direction=np.eye(3))
+    rows, cols = int(rng.integers(24, 64)), int(rng.integers(24, 64))
+    cam = CameraModel().setup(420.0, rows, cols, 1.3, 1.3)
+    base = synth.nominal_pose(vol, src_to_iso=230.0, view_rot_deg=float(rng.choice([0.0, 35.0, 90.0, 140.0])))
+    poses = synth.pose_population(vol, base, 4, seed=int(seed), sigma=(8, 8, 8, 3, 3, 6))
+    xcam = [xo.cam_struct(cam)]
+    step = float(rng.choice([0.3, 1.0, 1.0]))
+    rc = xreg_b200.RayCasterLineIntCUDA(ctx)
+    if is_hu:
+        rc.set_volumes_hu([vol], hu_lower=-1000.0)
+        lin = Volume(xo.hu_to_lin_att(vol.data, -1000.0), spacing=spacing, origin=vol.origin, direction=vol.direction)
+    else:
+        rc.set_volume(vol)
+        lin = vol
+    ref, mask, steps, S = xo.drr(lin.data, lin.idx_to_phys(), xcam, to12(poses), step_size=step, want_info=True)
+    rc.set_camera_model(cam)
+    rc.set_ray_step_size(step)
+    rc.set_num_projs(4)
+    rc.allocate_resources()
+    rc.set_xforms_cam_to_itk_phys(list(poses))
+    rc.compute()
+    got = rc.raw_host_pixel_buf().copy()
+    gmask, gsteps, gS = rc.ray_info()
+    rc.close()
+    np.testing.assert_array_equal(gmask, mask)
+    np.testing.assert_array_equal(gsteps, steps)
+    assert np.all(got[mask == 0] == ref[mask == 0])
+    scale = float(ref.max())
+    assert scale > 0
+    # north_star: per-pixel relative error <= 1e-4.  Every pixel with a line integral above 1e-5 of the brightest one is
+    # judged relatively (a ray that only grazes one metal voxel still qualifies); below that, absolutely
+    sel = (mask == 1) & (ref > 1.0e-5 * scale)
+    rel = np.abs(got[sel] - ref[sel]) / ref[sel]
+    assert rel.max() <= 1.0e-4, (seed, float(rel.max()))
+    assert np.abs(got - ref).max() <= 1.0e-6 * scale

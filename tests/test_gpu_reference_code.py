@@ -78,3 +78,38 @@ def test_config_c1_full_size_against_the_reference_code(ctx, xo):
     # and the oracle is that code, bit for bit, at this size too
     o = xo.drr(vol.data, vol.idx_to_phys(), xcam, to12(pop))
     assert o.tobytes() == ref_drr.tobytes()
+
+
+def test_objective_from_se3_parameters_against_the_reference_exp_map(ctx, xo, small_scene):
+    """xrc_obj_fn_se3 composes pose_p = pre * ExpSE3(x_p) * post inside the library; here the same
+    poses are composed with the REFERENCE's own ExpSE3 / ExpSO3 lines (lib/transforms/xregRigidUtils.cpp:40-85,
+    xregRotUtils.cpp:33-105, oracle/_ref/libxreg_refslice_se3.so), ray cast and scored by the oracle, and the library's
+    one-call objective must agree within the north_star similarity tolerance (the two exp maps agree to f32 rounding,
+    <= 2e-6 per matrix entry: tests/test_oracle_ref_slice.py)."""
+    from xreg_b200 import regi
+    from xreg_b200.geometry import exp_se3
+
+    vol, cam, nominal = small_scene
+    c = np.asarray(vol.origin) + 0.5 * (np.asarray(vol.dims) - 1.0) * np.asarray(vol.spacing)
+    pre, post = np.eye(4, dtype=f32), np.eye(4, dtype=f32)
+    pre[:3, 3] = c
+    post[:3, 3] = -c
+    post = (post @ nominal).astype(f32)
+    rng = np.random.default_rng(11)
+    x = np.concatenate([rng.normal(0, 0.08, (8, 3)), rng.normal(0, 5.0, (8, 3))], axis=1).astype(f32)
+    x[0] = 0
+    ref_poses = []
+    for xi in x:
+        E = np.vstack([ref_slice.exp_se3(xi).reshape(3, 4), [0, 0, 0, 1]]).astype(f32)
+        ref_poses.append((pre.astype(np.float64) @ E.astype(np.float64) @ post.astype(np.float64)).astype(f32))
+    ref_poses = np.stack(ref_poses)
+    xcam = [xo.cam_struct(cam)]
+    drr = xo.drr(vol.data, vol.idx_to_phys(), xcam, to12(ref_poses))
+    fixed = synth.add_noise(drr[0])
+    for metric, ofn in (("grad-ncc", lambda d: xo.grad_ncc(fixed, d)), ("ncc", lambda d: xo.ncc(fixed, d)),
+                        ("patch-grad-ncc", lambda d: xo.patch_grad_ncc(fixed, d, xo.patch_opts(radius=6)))):
+        fn = regi.Intensity2D3DObjFn(ctx, vol, [cam], [fixed], metric=metric, max_pop=8, patch_radius=6)
+        got = fn.eval_se3(x, pre, post)
+        assert np.max(np.abs(got - ofn(drr))) <= 1e-5, metric
+        assert int(np.argmin(got)) == 0
+        fn.close()
