@@ -237,6 +237,8 @@ def main():
     ap.add_argument("--order", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-weak", action="store_true", help="skip the secondary weak-scaling figure at N > 1")
+    ap.add_argument("--shard", default="tiles", choices=["tiles", "poses"],
+                    help="N > 1: shard the detector tiles (projections stored into their owners over NVLink) or the poses")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     w = dict(WORKLOADS[args.workload])
@@ -384,17 +386,56 @@ def main():
                 dist.all_reduce(ms, op=dist.ReduceOp.MAX)
             return float(ms.item())
 
-        # exact sample counts S_k of this rank's chunk per population -- untimed
-        step_resident, keep = make_step(u0, u1, gather=True)
+        tiles = world > 1 and args.shard == "tiles"
+        sharded = regi.ShardedDeviceObjFn(fn, rank, world, mode="tiles" if tiles else "poses") if world > 1 else None
+        flag = torch.zeros(1, dtype=torch.float32, device=dev)
+
+        def make_tile_step():
+            """N > 1, tile sharding: every rank ray casts its tiles of ALL units (stored into their owners' buffers over
+            NVLink), barrier on the streams, metrics of the units it owns, all-gather of the scalars"""
+            res = resident(0, n_units)
+            fn.rc.set_num_projs(n_units)
+            fn._cur_pop = -1
+            sm_all = (C.c_void_p * n_views)(*[sm.handle for sm in fn.sims])
+
+            def drr_only(k):
+                set_resident(res, k, n_units)
+                fn.rc.compute_tiles()
+
+            def step(k):
+                drr_only(k)
+                dist.all_reduce(flag)
+                if n_local:
+                    check(lib.xrc_obj_fn_units_enqueue_metrics(fn.rc.handle, sm_all, n_views, pop_n, u0, n_local))
+                if len(segs) == 1:
+                    send = sims_dev[segs[0][0]][:width]
+                else:
+                    send, off = send_buf[:width], 0
+                    for v, _, cnt in segs:
+                        send[off:off + cnt].copy_(sims_dev[v][:cnt])
+                        off += cnt
+                dist.all_gather_into_tensor(gathered[: width * world], send)
+            return step, drr_only, res
+
+        # exact sample counts S_k of this rank's share per population (SURVEY 8(d)) -- untimed
         S, F = [], []
-        for k in range(n_sets):
-            if n_local == 0:
-                S.append(0)
-                F.append(0)
-                continue
-            set_resident(keep, k, n_local)
-            S.append(fn.rc.ray_info(counts_only=True)[2])
-            F.append(fn.rc.fetched_samples() if args.layout in ("default", "pax") else S[-1])
+        if tiles:
+            step_resident, drr_tiles, keep = make_tile_step()
+            for k in range(n_sets):
+                set_resident(keep, k, n_units)
+                a_k, f_k = fn.rc.tile_samples()
+                S.append(a_k)
+                F.append(f_k)
+        else:
+            step_resident, keep = make_step(u0, u1, gather=True)
+            for k in range(n_sets):
+                if n_local == 0:
+                    S.append(0)
+                    F.append(0)
+                    continue
+                set_resident(keep, k, n_local)
+                S.append(fn.rc.ray_info(counts_only=True)[2])
+                F.append(fn.rc.fetched_samples() if args.layout in ("default", "pax") else S[-1])
 
         for k in range(W):
             step_resident(k)
@@ -408,7 +449,6 @@ def main():
 
             # e2e: the public host API -- host poses in (H2D from pinned staging), host scalars out, every step;
             # N > 1: the sharded objective (chunk per rank, NCCL all-gather of the scalars, D2H, one synchronise)
-            sharded = regi.ShardedDeviceObjFn(fn, rank, world)
             e2e_last = [None]
 
             def step_e2e(k):
@@ -419,13 +459,17 @@ def main():
             ms_e2e = timed(step_e2e, range(W, W + K))
             assert e2e_last[0].shape == (pop_n,) and np.all(np.isfinite(e2e_last[0]))
 
-            # dominant kernel alone: K launches of the DRR kernel on this rank's chunk, CUDA events on its stream
-            setup_chunk(u0, u1)
+            # dominant kernel alone: K launches of the DRR kernel on this rank's share, CUDA events on its stream
+            if tiles:
+                fn.rc.set_num_projs(n_units)
+                step_drr = drr_tiles
+            else:
+                setup_chunk(u0, u1)
 
-            def step_drr(k):
-                if n_local:
-                    set_resident(keep, k, n_local)
-                    fn.rc.compute()
+                def step_drr(k):
+                    if n_local:
+                        set_resident(keep, k, n_local)
+                        fn.rc.compute()
 
             for k in range(W):
                 step_drr(k)
@@ -453,7 +497,7 @@ def main():
         e2e_value = total_poses / (ms_e2e * 1e-3)
         S_timed = float(sum(S[W:W + K]))
         F_timed = float(sum(F[W:W + K]))
-        R_out = float(npix) * n_local * K
+        R_out = (float(npix) * n_units / world if tiles else float(npix) * n_local) * K
         alg_bytes = 32.0 * S_timed + 4.0 * R_out                  # B_drr = 32 S + 4 R_out, this rank's chunk
         fetched_bytes = 32.0 * F_timed + 4.0 * R_out
         achieved = alg_bytes / (ms_drr * 1e-3) / 1e9
@@ -519,15 +563,21 @@ def main():
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": w["desc"], "global_batch": pop_n, "views": n_views,
                            "projections_per_gpu_per_step": shares,
-                           "parallelism": ("(view, pose) list sharded x%d (contiguous balanced chunks), volume and fixed "
-                                           "images replicated, per-view scalars all-gathered (NCCL)" % world) if world > 1
+                           "parallelism": (("detector tiles sharded x%d round robin: every GPU ray casts its tiles of ALL projections "
+                                            "and stores them into their owners' buffers over NVLink (peer stores from the DRR "
+                                            "kernel, CUDA IPC); the (view, pose) list is cut into contiguous balanced chunks for "
+                                            "the metrics; barrier + all-gather of the scalars (NCCL); volume and fixed images "
+                                            "replicated" % world) if tiles else
+                                           ("(view, pose) list sharded x%d (contiguous balanced chunks), volume and fixed "
+                                            "images replicated, per-view scalars all-gathered (NCCL)" % world)) if world > 1
                                           else "one GPU",
+                           "shard": (args.shard if world > 1 else None),
                            "layout": args.layout, "cta_order": args.order,
                            "volume_bytes_resident": fn.rc.volume_bytes(),
                            "cache": "volume payload larger than L2 (126 MB) and a different pose population every step"},
                 "roofline": roofline, "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": "poses/s", "ms_per_step": ms_e2e / K,
-                        "h2d_bytes_per_step": int(n_local * (48 + 4)), "d2h_bytes_per_step": int(width * world * 4) if world > 1 else int(n_units * 4)},
+                        "h2d_bytes_per_step": int((n_units if tiles else n_local) * (48 + 4)), "d2h_bytes_per_step": int(width * world * 4) if world > 1 else int(n_units * 4)},
                 "gpu_launches": int(launches), "clocks": clocks,
             }
             if weak:

@@ -333,6 +333,41 @@ int xrc_obj_fn_units(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t 
  * all-gather straight from that vector) and synchronise once after their collective. */
 int xrc_obj_fn_units_enqueue(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t n_views, uint32_t n_poses,
                              const float* cam_to_phys, uint32_t first_unit, uint32_t n_units);
+/* ---- Tile-sharded objective for one process per GPU.  Sharding the POSES gives every
+ * GPU pop / N projections to ray cast, and a tile's beams are then shared in L2 by pop / N poses only; sharding the
+ * detector TILES instead keeps all pop poses of a tile on one GPU (the single-GPU access pattern) and balances the ray
+ * casting by measured work.  Every rank ray casts its tiles of ALL n_views x n_poses projections and stores each
+ * projection straight into the buffer of the rank that owns it -- the camera-major (view, pose) list cut into contiguous
+ * balanced chunks exactly like xrc_obj_fn_units -- at the projection's global index, through a peer-mapped address
+ * (NVLink stores issued by the ray-casting kernel itself; no staging copy, no all-to-all).  After a barrier across the
+ * ranks, ordered on their streams, every rank scores the projections it owns and the ranks all-gather the scalars.
+ * Results are bitwise those of one GPU (a pixel does not depend on which CTA, GPU or batch computed it).
+ *   xrc_rc_peer_export   cudaIpcGetMemHandle of this ray caster's own projection buffer (after xrc_rc_allocate, which
+ *                        must have room for ALL projections on every rank)
+ *   xrc_rc_peer_attach   the 64-byte handles of all n_ranks <= 8 ranks (this rank's own entry is ignored); opens the
+ *                        peers' buffers (cudaIpcOpenMemHandle, peer access enabled lazily).  Re-allocation detaches.
+ *   xrc_rc_plan_tiles    which tiles each rank ray casts: contiguous ranges of the row-major tile list (neighbouring tiles
+ *                        share their beams in L2), cut where the work measured by one count-only pass of the CURRENT
+ *                        projections balances; exact integer counts, so every rank derives the same plan on its own.
+ *                        Done implicitly by the first xrc_rc_compute_tiles after an attach; call it again when the pose
+ *                        distribution moves (a new registration level).  xrc_rc_tile_plan reads the n_ranks + 1 bounds.
+ *   xrc_rc_compute_tiles RayCaster::compute for this rank's tiles of all current projections, written to their owners
+ *   xrc_rc_tile_samples  instrumentation: trilinear samples of this rank's tiles (algorithmic / fetched), for rooflines */
+#define XRC_IPC_HANDLE_BYTES 64
+int xrc_rc_peer_export(xrc_rc* rc, uint8_t handle[XRC_IPC_HANDLE_BYTES]);
+int xrc_rc_peer_attach(xrc_rc* rc, uint32_t n_ranks, uint32_t rank, const uint8_t* handles);
+int xrc_rc_peer_detach(xrc_rc* rc);
+int xrc_rc_plan_tiles(xrc_rc* rc, uint32_t vol_idx);
+int xrc_rc_tile_plan(const xrc_rc* rc, uint32_t* tile_begin);
+int xrc_rc_compute_tiles(xrc_rc* rc, uint32_t vol_idx);
+int xrc_rc_tile_samples(xrc_rc* rc, uint32_t vol_idx, uint64_t* algorithmic, uint64_t* fetched);
+/* The two halves of the tile-sharded objective, both asynchronous on the context stream: (1) hand over all n_poses
+ * poses (replicated over the views camera-major) and ray cast this rank's tiles; (2) -- after the caller's barrier --
+ * every view's metric over the units [first_unit, first_unit + n_units) this rank owns, read at their global indices.
+ * View v's values land in the first entries of its metric's result vector, as with xrc_obj_fn_units_enqueue. */
+int xrc_obj_fn_tiles_enqueue_drr(xrc_rc* rc, uint32_t vol_idx, uint32_t n_views, uint32_t n_poses, const float* cam_to_phys);
+int xrc_obj_fn_units_enqueue_metrics(xrc_rc* rc, xrc_sm* const* sms, uint32_t n_views, uint32_t n_poses, uint32_t first_unit,
+                                     uint32_t n_units);
 /* The partition xrc_obj_fn_multi uses (host only, needs no device): of view `view`, device `dev` evaluates the poses
  * [*first_pose, *first_pose + *count).  For sizing the per-device objects and for callers that shard by themselves. */
 int xrc_obj_fn_multi_share(uint32_t n_dev, uint32_t n_views, uint32_t n_poses, uint32_t dev, uint32_t view,

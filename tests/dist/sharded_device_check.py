@@ -45,22 +45,34 @@ def main():
         rc0.close()
         single = regi.Intensity2D3DObjFn(ctx, vol, cams, fixed, metric=metric, max_pop=11, patch_radius=6)
         ref = single(pop)
-        fn = regi.Intensity2D3DObjFn(ctx, vol, cams, fixed, metric=metric, max_pop=11, patch_radius=6)
-        sharded = regi.ShardedDeviceObjFn(fn, rank, world)
-        for sel in (slice(0, 11), slice(3, 10), slice(5, 6), slice(0, 2)):
-            got = sharded(pop[sel])
-            same = bool(np.array_equal(got, ref[sel]))
-            # every rank must hold the same full vector
-            t = torch.from_numpy(got.copy()).to(dev)
-            lst = [torch.empty_like(t) for _ in range(world)]
-            dist.all_gather(lst, t)
-            same = same and all(bool(torch.equal(lst[0], x)) for x in lst)
-            ok = ok and same
-            if rank == 0:
-                print(json.dumps({"world": world, "views": len(cams), "metric": metric, "poses": int(len(got)),
-                                  "devices": [int(torch.cuda.current_device())], "bitwise_equal_to_single_gpu": same}), flush=True)
-        del sharded
-        fn.close()
+        for mode in ("poses", "tiles"):
+            fn = regi.Intensity2D3DObjFn(ctx, vol, cams, fixed, metric=metric, max_pop=11, patch_radius=6)
+            sharded = regi.ShardedDeviceObjFn(fn, rank, world, mode=mode)
+            for sel in (slice(0, 11), slice(3, 10), slice(5, 6), slice(0, 2), slice(0, 11)):
+                got = sharded(pop[sel])
+                same = bool(np.array_equal(got, ref[sel]))
+                # every rank must hold the same full vector
+                t = torch.from_numpy(got.copy()).to(dev)
+                lst = [torch.empty_like(t) for _ in range(world)]
+                dist.all_gather(lst, t)
+                same = same and all(bool(torch.equal(lst[0], x)) for x in lst)
+                ok = ok and same
+                if rank == 0:
+                    print(json.dumps({"world": world, "mode": mode, "views": len(cams), "metric": metric, "poses": int(len(got)),
+                                      "bitwise_equal_to_single_gpu": same}), flush=True)
+            if mode == "tiles":
+                # the projections this rank OWNS were assembled from every rank's tiles: they must equal the single-GPU ones
+                n = 11
+                b, e = regi.unit_chunks(len(cams) * n, world)[rank]
+                mine = fn.rc.raw_host_pixel_buf()[b:e]
+                same = bool(np.array_equal(mine, single.rc.raw_host_pixel_buf()[b:e])) if e > b else True
+                ok = ok and same
+                print(json.dumps({"world": world, "mode": mode, "rank": rank, "owned_projections": [b, e],
+                                  "projections_bitwise_equal_to_single_gpu": same}), flush=True)
+                dist.barrier()
+                fn.rc.peer_detach()
+            del sharded
+            fn.close()
         single.close()
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)

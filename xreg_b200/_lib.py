@@ -134,6 +134,15 @@ SIGNATURES = {
     "xrc_obj_fn_se3": [_VP, _U32, C.POINTER(_VP), _U32, _U32, _FP, _FP, _FP, _FP, _FP],
     "xrc_obj_fn_units": [_VP, _U32, C.POINTER(_VP), _U32, _U32, _FP, _U32, _U32, _FP],
     "xrc_obj_fn_units_enqueue": [_VP, _U32, C.POINTER(_VP), _U32, _U32, _FP, _U32, _U32],
+    "xrc_rc_peer_export": [_VP, C.POINTER(C.c_uint8)],
+    "xrc_rc_peer_attach": [_VP, _U32, _U32, C.POINTER(C.c_uint8)],
+    "xrc_rc_peer_detach": [_VP],
+    "xrc_rc_compute_tiles": [_VP, _U32],
+    "xrc_rc_plan_tiles": [_VP, _U32],
+    "xrc_rc_tile_plan": [_VP, _U32P],
+    "xrc_rc_tile_samples": [_VP, _U32, C.POINTER(_U64), C.POINTER(_U64)],
+    "xrc_obj_fn_tiles_enqueue_drr": [_VP, _U32, _U32, _U32, _FP],
+    "xrc_obj_fn_units_enqueue_metrics": [_VP, C.POINTER(_VP), _U32, _U32, _U32, _U32],
     "xrc_obj_fn_multi_share": [_U32, _U32, _U32, _U32, _U32, _U32P, _U32P],
     "xrc_exp_se3": [_FP, _FP],
     "xrc_se3_mag_penalty": [C.POINTER(XrcSe3Penalty), _U32, _FP, _FP],

@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <string>
 #include <limits>
 #include <memory>
 
@@ -113,6 +114,12 @@ struct xrc_rc
   float* d_buf_own = nullptr;   // own projection buffer; a borrower (use_other_proj_buf) has none
   xrc_rc* other = nullptr;      // lender of the projection buffer, resolved at every use (rc_proj_buf)
   uint32_t n_borrowers = 0;     // ray casters whose `other` is this one: it cannot be destroyed before them
+  // multi-GPU tile sharding (xrc_rc_peer_attach): the projection buffers of all ranks, peers' opened over CUDA IPC
+  uint32_t peer_n = 0, peer_rank = 0;
+  float* peer_bufs[kMaxPeers] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // contiguous tile ranges of the ranks, balanced by measured work (xrc_rc_plan_tiles): rank r owns tiles
+  // [tile_begin[r], tile_begin[r + 1]); empty until planned
+  std::vector<uint32_t> tile_begin;
   float* h_poses = nullptr;   // pinned staging: max_projs x 12 floats
   uint32_t* h_cam_idx = nullptr;
   float* d_poses = nullptr;
@@ -317,6 +324,17 @@ int xrc_rc_create(xrc_ctx* ctx, xrc_rc** out)
   return XRC_OK;
 }
 
+static void rc_peer_detach(xrc_rc* rc)
+{
+  for (uint32_t r = 0; r < rc->peer_n; ++r)
+    if (r != rc->peer_rank && rc->peer_bufs[r])
+      cudaIpcCloseMemHandle(rc->peer_bufs[r]);
+  for (uint32_t r = 0; r < kMaxPeers; ++r)
+    rc->peer_bufs[r] = nullptr;
+  rc->peer_n = 0;
+  rc->tile_begin.clear();
+}
+
 static void rc_free_vols(xrc_rc* rc)
 {
   for (auto& v : rc->vols)
@@ -335,6 +353,7 @@ int xrc_rc_destroy(xrc_rc* rc)
     --rc->other->n_borrowers;
   cudaSetDevice(rc->ctx->device);
   cudaStreamSynchronize(rc->ctx->stream);
+  rc_peer_detach(rc);
   rc_free_vols(rc);
   dfree(rc->d_cams);
   dfree(rc->d_buf_own);
@@ -508,6 +527,7 @@ int xrc_rc_allocate(xrc_rc* rc, uint32_t max_projs)
   XRC_CHECK_ARG(max_projs > 0, "xrc_rc_allocate: need at least one projection");
   XRC_TRY(use_device(rc->ctx));
   XRC_CUDA(cudaStreamSynchronize(rc->ctx->stream));
+  rc_peer_detach(rc);   // the peers' mappings of the old buffer are the callers' to drop (xrc_rc_peer_detach on every rank)
   dfree(rc->d_buf_own);
   dfree(rc->d_poses);
   dfree(rc->d_cam_idx);
@@ -902,6 +922,203 @@ int xrc_rc_compute(xrc_rc* rc, uint32_t vol_idx)
   DrrArgs a;
   rc_fill_args(rc, vol_idx, &a);
   return launch_drr(a, rc->vols[vol_idx].layout, rc->kernel_id, rc->ctx->stream);
+}
+
+// ---- multi-GPU tile sharding, one process per GPU
+int xrc_rc_peer_export(xrc_rc* rc, uint8_t handle[XRC_IPC_HANDLE_BYTES])
+{
+  XRC_CHECK_ARG(rc && handle, "null argument");
+  XRC_CHECK_ARG(rc->allocated && rc->d_buf_own, "xrc_rc_peer_export: allocate first (a ray caster that borrows its buffer cannot export it)");
+  static_assert(sizeof(cudaIpcMemHandle_t) == XRC_IPC_HANDLE_BYTES, "IPC handle size");
+  XRC_TRY(use_device(rc->ctx));
+  cudaIpcMemHandle_t h;
+  XRC_CUDA(cudaIpcGetMemHandle(&h, rc->d_buf_own));
+  memcpy(handle, &h, sizeof(h));
+  return XRC_OK;
+}
+
+int xrc_rc_peer_attach(xrc_rc* rc, uint32_t n_ranks, uint32_t rank, const uint8_t* handles)
+{
+  XRC_CHECK_ARG(rc && handles, "null argument");
+  XRC_CHECK_ARG(n_ranks >= 1 && n_ranks <= kMaxPeers && rank < n_ranks, "xrc_rc_peer_attach: 1 <= ranks <= 8, rank < ranks");
+  XRC_CHECK_ARG(rc->allocated && rc->d_buf_own, "xrc_rc_peer_attach: allocate first");
+  XRC_TRY(use_device(rc->ctx));
+  XRC_CUDA(cudaStreamSynchronize(rc->ctx->stream));
+  rc_peer_detach(rc);
+  rc->peer_rank = rank;
+  for (uint32_t r = 0; r < n_ranks; ++r)
+  {
+    if (r == rank)
+    {
+      rc->peer_bufs[r] = rc->d_buf_own;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)r * XRC_IPC_HANDLE_BYTES, sizeof(h));
+    void* p = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess)
+    {
+      rc->peer_n = r;   // close what was opened so far
+      rc_peer_detach(rc);
+      cudaGetLastError();
+      XRC_FAIL(XRC_ERR_CUDA, std::string("xrc_rc_peer_attach: cudaIpcOpenMemHandle failed for rank ") + std::to_string(r) +
+                                 ": " + cudaGetErrorString(e));
+    }
+    rc->peer_bufs[r] = (float*)p;
+  }
+  rc->peer_n = n_ranks;
+  return XRC_OK;
+}
+
+int xrc_rc_peer_detach(xrc_rc* rc)
+{
+  XRC_CHECK_ARG(rc, "null ray caster");
+  XRC_TRY(use_device(rc->ctx));
+  XRC_CUDA(cudaStreamSynchronize(rc->ctx->stream));
+  rc_peer_detach(rc);
+  return XRC_OK;
+}
+
+// Which tiles does each rank ray cast?  Contiguous ranges of the row-major tile list, so that the tiles in flight on a
+// GPU stay neighbours (their beams -- and, with the pose jitter of a population, the beams of the neighbouring tiles'
+// other poses -- overlap in L2: dealing the tiles round robin measured no faster than sharding the poses), cut where the
+// MEASURED work balances: one count-only pass of the current projections gives the samples each tile fetches (exact
+// integers, identical on every rank, so all ranks derive the same plan without talking), plus a constant per ray for
+// its set-up.  Planned once per attach (first xrc_rc_compute_tiles) or on request; an optimiser's later populations
+// stay around the same pose, so the plan stays balanced.
+int xrc_rc_plan_tiles(xrc_rc* rc, uint32_t vol_idx)
+{
+  XRC_CHECK_ARG(rc, "null ray caster");
+  XRC_CHECK_ARG(rc->allocated && rc->peer_n >= 1, "xrc_rc_plan_tiles: allocate and attach first");
+  XRC_CHECK_ARG(vol_idx < rc->vols.size(), "xrc_rc_plan_tiles: volume index out of range");
+  XRC_TRY(use_device(rc->ctx));
+  XRC_TRY(rc_prepare_stacks(rc, vol_idx));
+  XRC_CHECK_ARG(rc->vols[vol_idx].layout == XRC_LAYOUT_PAX, "xrc_rc_plan_tiles: needs the default volume layout");
+  const uint32_t nt = ((rc->cols + 15) / 16) * ((rc->rows + 15) / 16);
+  cudaStream_t st = rc->ctx->stream;
+  unsigned long long* d_cnt = nullptr;
+  XRC_CUDA(cudaMalloc(&d_cnt, (nt + 1) * sizeof(unsigned long long)));
+  cudaMemsetAsync(d_cnt, 0, (nt + 1) * sizeof(unsigned long long), st);
+  DrrArgs a;
+  rc_fill_args(rc, vol_idx, &a);
+  a.sample_counter = d_cnt + nt;
+  a.tile_counter = d_cnt;
+  a.count_only = 1;
+  int status = launch_drr(a, XRC_LAYOUT_PAX, rc->kernel_id, st);
+  std::vector<unsigned long long> cnt(nt + 1, 0ull);
+  if (status == XRC_OK)
+  {
+    cudaMemcpyAsync(cnt.data(), d_cnt, (nt + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess)
+    {
+      set_error("xrc_rc_plan_tiles: device failure");
+      status = XRC_ERR_CUDA;
+    }
+  }
+  cudaFree(d_cnt);
+  XRC_TRY(status);
+  // work of a tile: its fetched samples + 40 sample-equivalents per ray for set-up, trimming and the store
+  std::vector<double> w(nt);
+  double total = 0.0;
+  for (uint32_t t = 0; t < nt; ++t)
+  {
+    w[t] = (double)cnt[t] + 40.0 * 256.0 * (double)rc->num_projs;
+    total += w[t];
+  }
+  rc->tile_begin.assign(rc->peer_n + 1, nt);
+  rc->tile_begin[0] = 0;
+  double acc = 0.0;
+  uint32_t r = 1;
+  for (uint32_t t = 0; t < nt && r < rc->peer_n; ++t)
+  {
+    acc += w[t];
+    while (r < rc->peer_n && acc >= total * (double)r / (double)rc->peer_n)
+      rc->tile_begin[r++] = t + 1;
+  }
+  return XRC_OK;
+}
+
+int xrc_rc_tile_plan(const xrc_rc* rc, uint32_t* tile_begin /* n_ranks + 1 */)
+{
+  XRC_CHECK_ARG(rc && tile_begin, "null argument");
+  XRC_CHECK_ARG(rc->tile_begin.size() == (size_t)rc->peer_n + 1, "xrc_rc_tile_plan: no plan yet (xrc_rc_plan_tiles / first xrc_rc_compute_tiles)");
+  for (size_t i = 0; i < rc->tile_begin.size(); ++i)
+    tile_begin[i] = rc->tile_begin[i];
+  return XRC_OK;
+}
+
+// this rank's tiles of ALL current projections, each stored in its owner's buffer (its global index there)
+static void rc_fill_tile_args(xrc_rc* rc, DrrArgs* a)
+{
+  a->tile_first = rc->tile_begin[rc->peer_rank];
+  a->tile_stride = 1;
+  a->tile_count = rc->tile_begin[rc->peer_rank + 1] - rc->tile_begin[rc->peer_rank];
+  a->peer_n = rc->peer_n;
+  a->peer_base = rc->num_projs / rc->peer_n;
+  a->peer_extra = rc->num_projs % rc->peer_n;
+  for (uint32_t r = 0; r < kMaxPeers; ++r)
+    a->peer_out[r] = rc->peer_bufs[r];
+}
+
+int xrc_rc_compute_tiles(xrc_rc* rc, uint32_t vol_idx)
+{
+  XRC_CHECK_ARG(rc, "null ray caster");
+  XRC_CHECK_ARG(rc->allocated, "xrc_rc_compute_tiles: resources not allocated");
+  XRC_CHECK_ARG(rc->peer_n >= 1, "xrc_rc_compute_tiles: attach the ranks' projection buffers first (xrc_rc_peer_attach)");
+  XRC_CHECK_ARG(vol_idx < rc->vols.size(), "xrc_rc_compute_tiles: volume index out of range");
+  XRC_TRY(use_device(rc->ctx));
+  XRC_TRY(rc_prepare_stacks(rc, vol_idx));
+  XRC_CHECK_ARG(rc->vols[vol_idx].layout == XRC_LAYOUT_PAX, "xrc_rc_compute_tiles: needs the default volume layout");
+  if (rc->tile_begin.size() != (size_t)rc->peer_n + 1)
+    XRC_TRY(xrc_rc_plan_tiles(rc, vol_idx));
+  DrrArgs a;
+  rc_fill_args(rc, vol_idx, &a);
+  rc_fill_tile_args(rc, &a);
+  return launch_drr(a, XRC_LAYOUT_PAX, rc->kernel_id, rc->ctx->stream);
+}
+
+int xrc_rc_tile_samples(xrc_rc* rc, uint32_t vol_idx, uint64_t* algorithmic, uint64_t* fetched)
+{
+  XRC_CHECK_ARG(rc && (algorithmic || fetched), "null argument");
+  XRC_CHECK_ARG(rc->allocated && rc->peer_n >= 1, "xrc_rc_tile_samples: allocate and attach first");
+  XRC_CHECK_ARG(vol_idx < rc->vols.size() && rc->vols[vol_idx].layout == XRC_LAYOUT_PAX, "xrc_rc_tile_samples: bad volume");
+  XRC_TRY(use_device(rc->ctx));
+  XRC_TRY(rc_prepare_stacks(rc, vol_idx));
+  if (rc->tile_begin.size() != (size_t)rc->peer_n + 1)
+    XRC_TRY(xrc_rc_plan_tiles(rc, vol_idx));
+  cudaStream_t st = rc->ctx->stream;
+  unsigned long long* d_cnt = nullptr;
+  XRC_CUDA(cudaMalloc(&d_cnt, 2 * sizeof(unsigned long long)));
+  cudaMemsetAsync(d_cnt, 0, 2 * sizeof(unsigned long long), st);
+  DrrArgs a;
+  rc_fill_args(rc, vol_idx, &a);
+  rc_fill_tile_args(rc, &a);
+  a.peer_n = 0;   // counting only: nothing is stored
+  a.sample_counter = d_cnt;
+  int status = launch_ray_info(a, st);
+  if (status == XRC_OK)
+  {
+    a.sample_counter = d_cnt + 1;
+    a.count_only = 1;
+    status = launch_drr(a, XRC_LAYOUT_PAX, rc->kernel_id, st);
+  }
+  unsigned long long cnt[2] = {0, 0};
+  if (status == XRC_OK)
+  {
+    cudaMemcpyAsync(cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess)
+    {
+      set_error("xrc_rc_tile_samples: device failure");
+      status = XRC_ERR_CUDA;
+    }
+  }
+  cudaFree(d_cnt);
+  if (algorithmic)
+    *algorithmic = cnt[0];
+  if (fetched)
+    *fetched = cnt[1];
+  return status;
 }
 
 int xrc_rc_volume_layout(const xrc_rc* rc, uint32_t vol_idx, int* layout)
@@ -2161,6 +2378,48 @@ static int obj_fn_finish_units(xrc_rc* rc, xrc_sm* const* sms, uint32_t n_views,
     unit_range(u0, u1, v, n_poses, p0, p1);
     if (p1 > p0)
       memcpy(dst + ((size_t)v * n_poses + p0 - dst_first_unit), sms[v]->h_sims, (p1 - p0) * sizeof(float));
+  }
+  return XRC_OK;
+}
+
+// Tile-sharded objective, one process per GPU: every rank ray casts ITS TILES of all n_views x n_poses projections and
+// writes each projection into its owner's buffer (NVLink peer stores, xrc_rc_compute_tiles) ...
+int xrc_obj_fn_tiles_enqueue_drr(xrc_rc* rc, uint32_t vol_idx, uint32_t n_views, uint32_t n_poses, const float* cam_to_phys)
+{
+  XRC_CHECK_ARG(rc && cam_to_phys && n_views > 0, "xrc_obj_fn_tiles_enqueue_drr: bad argument");
+  XRC_CHECK_ARG(rc->allocated, "xrc_obj_fn_tiles_enqueue_drr: ray caster resources not allocated");
+  XRC_CHECK_ARG(n_views == rc->cams.size(), "xrc_obj_fn_tiles_enqueue_drr: need one view per camera model");
+  XRC_CHECK_ARG((uint64_t)n_poses * n_views <= rc->max_projs, "xrc_obj_fn_tiles_enqueue_drr: population exceeds the allocated projections");
+  if (!n_poses)
+    return XRC_OK;
+  if (rc->num_projs != n_poses * n_views)
+    XRC_TRY(xrc_rc_set_num_projs(rc, n_poses * n_views));
+  rc->ext_poses = nullptr;
+  XRC_TRY(obj_fn_set_poses(rc, n_views, n_poses, cam_to_phys));
+  return xrc_rc_compute_tiles(rc, vol_idx);
+}
+
+// ... and, after a barrier across the ranks on their streams, scores the units it owns: view v's metric reads the
+// projections [v * n_poses + p0, v * n_poses + p1) of the unit range at their GLOBAL indices in this rank's buffer.
+int xrc_obj_fn_units_enqueue_metrics(xrc_rc* rc, xrc_sm* const* sms, uint32_t n_views, uint32_t n_poses, uint32_t first_unit,
+                                     uint32_t n_units)
+{
+  XRC_CHECK_ARG(rc && sms && n_views > 0, "xrc_obj_fn_units_enqueue_metrics: bad argument");
+  XRC_CHECK_ARG((uint64_t)first_unit + n_units <= (uint64_t)n_views * n_poses, "xrc_obj_fn_units_enqueue_metrics: unit range outside the list");
+  const uint32_t u0 = first_unit, u1 = first_unit + n_units;
+  for (uint32_t v = 0; v < n_views; ++v)
+  {
+    uint32_t p0, p1;
+    unit_range(u0, u1, v, n_poses, p0, p1);
+    if (p1 == p0)
+      continue;
+    XRC_CHECK_ARG(sms[v] && sms[v]->rc == rc, "xrc_obj_fn_units_enqueue_metrics: every metric must be bound to the ray caster");
+    XRC_CHECK_ARG(p1 - p0 <= sms[v]->max_imgs, "xrc_obj_fn_units_enqueue_metrics: share exceeds a metric's capacity");
+    if (sms[v]->n_imgs != p1 - p0)
+      XRC_TRY(xrc_sm_set_num_imgs(sms[v], p1 - p0));
+    if (sms[v]->proj_offset != v * n_poses + p0)
+      XRC_TRY(xrc_sm_bind_ray_caster(sms[v], rc, v * n_poses + p0));
+    XRC_TRY(xrc_sm_compute(sms[v]));
   }
   return XRC_OK;
 }

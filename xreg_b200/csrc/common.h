@@ -83,6 +83,7 @@ struct DeviceVolume
 };
 
 constexpr uint32_t kInlinePoses = 8;
+constexpr uint32_t kMaxPeers = 8;   // ranks of a tile-sharded job (one box)
 
 // Arguments of the DRR kernels (passed by value).
 struct DrrArgs
@@ -115,6 +116,15 @@ struct DrrArgs
   uint32_t occ_wx, occ_ny;
   float occ_lo[3], occ_hi[3];
   int count_only;             // instrumentation: count the samples the kernel would fetch, do not march / store
+  // tile subset of this launch: tiles tile_first + i * tile_stride, i < tile_count (tile_stride == 0 on entry: all tiles)
+  uint32_t tile_first, tile_stride, tile_count;
+  unsigned long long* tile_counter;   // optional, with sample_counter: fetched samples per detector tile (tile planning)
+  // multi-GPU tile sharding (xrc_rc_compute_tiles): projection `proj` is stored at its global index in the buffer of
+  // the rank that owns it -- peer_out[owner(proj)], a peer-mapped (NVLink) address unless the owner is this rank --
+  // where the n_projs projections are cut into peer_n contiguous balanced chunks (peer_base = n_projs / peer_n, the
+  // first peer_extra chunks take one more).  peer_n == 0: single device, `out`.
+  uint32_t peer_n, peer_base, peer_extra;
+  float* peer_out[kMaxPeers];
   // small populations (latency regime): poses travel in the kernel parameters instead of an H2D copy
   int use_inline;
   float inl_poses[kInlinePoses * 12];

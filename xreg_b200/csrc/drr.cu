@@ -372,17 +372,18 @@ constexpr int kThreads = kTileW * kTileH;
 __device__ __forceinline__ void cta_coords(const DrrArgs& a, uint32_t& proj, uint32_t& tile)
 {
   const uint32_t b = blockIdx.x;
+  uint32_t t;
   if (a.order == 0)
   {
     proj = b % a.n_projs;
-    tile = b / a.n_projs;
+    t = b / a.n_projs;
   }
   else
   {
-    const uint32_t nt = a.tiles_x * a.tiles_y;
-    tile = b % nt;
-    proj = b / nt;
+    t = b % a.tile_count;
+    proj = b / a.tile_count;
   }
+  tile = a.tile_first + t * a.tile_stride;
 }
 
 __device__ __forceinline__ void thread_pixel(const DrrArgs& a, uint32_t tile, uint32_t& row, uint32_t& col)
@@ -927,24 +928,35 @@ __device__ __forceinline__ PaxLane pax_lane_setup(const DrrArgs& a, const PaxCta
 }
 
 // RayCasterCPU::pre_compute + the store of ComputeLineInts (xregRayCastBaseCPU.cpp:128-158, xregRayCastLineIntCPU.cpp:279-285)
+// projection buffer that holds projection `proj`: this device's, or -- tile-sharded over several GPUs -- the owner's
+__device__ __forceinline__ float* proj_out(const DrrArgs& a, uint32_t proj)
+{
+  if (!a.peer_n)
+    return a.out;
+  const uint32_t big = a.peer_extra * (a.peer_base + 1u);   // projections held by the ranks that take one more
+  const uint32_t owner = (proj < big) ? proj / (a.peer_base + 1u) : a.peer_extra + (proj - big) / a.peer_base;
+  return a.peer_out[owner];
+}
+
 template <int KERNEL_ID>
 __device__ __forceinline__ void pax_store(const DrrArgs& a, uint32_t proj, uint32_t ci, uint32_t row, uint32_t col, float sum)
 {
   const size_t npix = (size_t)a.rows * a.cols;
   const size_t o = (size_t)proj * npix + (size_t)row * a.cols + col;
+  float* __restrict__ out = proj_out(a, proj);
   float base_v;
   if (a.init_mode == 0)
     base_v = a.default_bg;
   else if (a.init_mode == 1)
     base_v = __ldg(a.bg + (size_t)ci * npix + (size_t)row * a.cols + col);
   else
-    base_v = a.out[o];
+    base_v = out[o];
   const float aa = fadd(0.0f, fmul(sum, 1.0f));  // :282
-  a.out[o] = (KERNEL_ID == XRC_KERNEL_MAX) ? fmaxf(base_v, aa) : fadd(base_v, aa);  // :285
+  out[o] = (KERNEL_ID == XRC_KERNEL_MAX) ? fmaxf(base_v, aa) : fadd(base_v, aa);  // :285
 }
 
 // instrumentation: add this thread's fetched-sample count to the global counter (all threads of the CTA call it)
-__device__ __forceinline__ void pax_count(const DrrArgs& a, PaxCta& sh, unsigned long long n)
+__device__ __forceinline__ void pax_count(const DrrArgs& a, PaxCta& sh, unsigned long long n, uint32_t tile)
 {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1)
@@ -953,7 +965,11 @@ __device__ __forceinline__ void pax_count(const DrrArgs& a, PaxCta& sh, unsigned
     atomicAdd(&sh.cta_samples, n);
   __syncthreads();
   if (threadIdx.x == 0)
+  {
     atomicAdd(a.sample_counter, sh.cta_samples);
+    if (a.tile_counter)
+      atomicAdd(a.tile_counter + tile, sh.cta_samples);
+  }
 }
 
 // ---- one thread per pixel, CTA = 16 x 16 pixels of one projection ---------------------------------------
@@ -1002,13 +1018,15 @@ __global__ void __launch_bounds__(kThreads, MINB) drr_pax_kernel(const DrrArgs a
   if (in_img && !a.count_only)
     pax_store<KERNEL_ID>(a, proj, ci, row, col, sum);
   if (a.sample_counter)
-    pax_count(a, sh, L.hit ? (unsigned long long)(L.s1 - L.s0) : 0ull);  // samples actually fetched
+    pax_count(a, sh, L.hit ? (unsigned long long)(L.s1 - L.s0) : 0ull, tile);  // samples actually fetched
 }
 
 template <int KERNEL_ID>
 static int launch_pax_k(const DrrArgs& a, cudaStream_t st)
 {
-  const uint32_t nblocks = a.n_projs * a.tiles_x * a.tiles_y;
+  const uint32_t nblocks = a.n_projs * a.tile_count;
+  if (!nblocks)
+    return XRC_OK;
   // variant (measurement only): bit0 packed f32x2 position / floor arithmetic, bit1 force clamped loop, bits 2-3 batch id, bit4 no lane swap,
   // bits 5-7 min CTAs per SM (register budget)
   const bool packed = (a.variant & 1) != 0;
@@ -1102,6 +1120,8 @@ __global__ void __launch_bounds__(kThreads) ray_info_kernel(const DrrArgs a)
 template <int LAYOUT>
 static int launch_layout(const DrrArgs& a, int kernel_id, cudaStream_t st)
 {
+  if (a.peer_n || a.tile_count != a.tiles_x * a.tiles_y)
+    XRC_FAIL(XRC_ERR_UNSUPPORTED, "tile-sharded launches need the default (principal-axis stack) layout");
   const uint32_t nblocks = a.n_projs * a.tiles_x * a.tiles_y;
   if (kernel_id == XRC_KERNEL_SUM)
     drr_kernel<LAYOUT, XRC_KERNEL_SUM><<<nblocks, kThreads, 0, st>>>(a);
@@ -1112,11 +1132,28 @@ static int launch_layout(const DrrArgs& a, int kernel_id, cudaStream_t st)
   return XRC_OK;
 }
 
+// tile_stride == 0 on entry: the whole detector; else the caller's (tile_first, tile_stride, tile_count), clipped
+static void fill_tiles(DrrArgs& a)
+{
+  a.tiles_x = (a.cols + kTileW - 1) / kTileW;
+  a.tiles_y = (a.rows + kTileH - 1) / kTileH;
+  const uint32_t nt = a.tiles_x * a.tiles_y;
+  if (!a.tile_stride)
+  {
+    a.tile_first = 0;
+    a.tile_stride = 1;
+    a.tile_count = nt;
+  }
+  else if (a.tile_first >= nt)
+    a.tile_count = 0;
+  else
+    a.tile_count = std::min(a.tile_count, (nt - a.tile_first + a.tile_stride - 1) / a.tile_stride);
+}
+
 int launch_drr(const DrrArgs& a_in, int layout, int kernel_id, cudaStream_t st)
 {
   DrrArgs a = a_in;
-  a.tiles_x = (a.cols + kTileW - 1) / kTileW;
-  a.tiles_y = (a.rows + kTileH - 1) / kTileH;
+  fill_tiles(a);
   if (!a.n_projs)
     return XRC_OK;
   switch (layout)
@@ -1134,11 +1171,10 @@ int launch_drr(const DrrArgs& a_in, int layout, int kernel_id, cudaStream_t st)
 int launch_ray_info(const DrrArgs& a_in, cudaStream_t st)
 {
   DrrArgs a = a_in;
-  a.tiles_x = (a.cols + kTileW - 1) / kTileW;
-  a.tiles_y = (a.rows + kTileH - 1) / kTileH;
-  if (!a.n_projs)
+  fill_tiles(a);
+  if (!a.n_projs || !a.tile_count)
     return XRC_OK;
-  ray_info_kernel<<<a.n_projs * a.tiles_x * a.tiles_y, kThreads, 0, st>>>(a);
+  ray_info_kernel<<<a.n_projs * a.tile_count, kThreads, 0, st>>>(a);
   count_launch();
   XRC_CUDA(cudaGetLastError());
   return XRC_OK;

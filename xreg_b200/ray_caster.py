@@ -348,6 +348,43 @@ class RayCasterLineIntCUDA:
                 hm.ctypes.data_as(C.POINTER(C.c_float)), hc))
         self._poses_dirty = False
 
+    # ---- multi-GPU tile sharding (one process per GPU; include/xreg_cuda.h "Tile-sharded objective") ----
+    def peer_export(self) -> bytes:
+        """CUDA IPC handle of this ray caster's projection buffer (after allocate_resources)."""
+        h = (C.c_uint8 * 64)()
+        check(self._lib.xrc_rc_peer_export(self.handle, h))
+        return bytes(h)
+
+    def peer_attach(self, n_ranks: int, rank: int, handles: Sequence[bytes]) -> None:
+        """Open the projection buffers of all ranks (their peer_export() handles, in rank order)."""
+        blob = (C.c_uint8 * (64 * n_ranks)).from_buffer_copy(b"".join(bytes(h) for h in handles))
+        check(self._lib.xrc_rc_peer_attach(self.handle, int(n_ranks), int(rank), blob))
+
+    def peer_detach(self) -> None:
+        check(self._lib.xrc_rc_peer_detach(self.handle))
+
+    def compute_tiles(self, vol_idx: int = 0) -> None:
+        """compute() for this rank's detector tiles of ALL current projections, each written into its owner's buffer."""
+        if not self._resources_allocated:
+            raise _lib.XregError("compute_tiles: resources not allocated")
+        self._flush()
+        check(self._lib.xrc_rc_compute_tiles(self.handle, int(vol_idx)))
+
+    def plan_tiles(self, vol_idx: int = 0, n_ranks: int = 0) -> List[int]:
+        """(Re)balance the ranks' tile ranges on the current projections; returns the n_ranks + 1 bounds."""
+        self._flush()
+        check(self._lib.xrc_rc_plan_tiles(self.handle, int(vol_idx)))
+        out = (C.c_uint32 * 9)()
+        check(self._lib.xrc_rc_tile_plan(self.handle, out))
+        return [int(v) for v in out[: (n_ranks + 1) if n_ranks else 9]]
+
+    def tile_samples(self, vol_idx: int = 0):
+        """(algorithmic, fetched) trilinear samples of this rank's tiles for the current poses."""
+        self._flush()
+        a, f = C.c_uint64(), C.c_uint64()
+        check(self._lib.xrc_rc_tile_samples(self.handle, int(vol_idx), C.byref(a), C.byref(f)))
+        return int(a.value), int(f.value)
+
     def compute(self, vol_idx: int = 0) -> None:
         if not self._resources_allocated:
             raise _lib.XregError("compute: resources not allocated (xregRayCastLineIntCPU.cpp:296)")

@@ -143,6 +143,26 @@ class Intensity2D3DObjFn:
         self.rc._poses_dirty = False
         self._cur_pop = -1   # the library re-sized / re-bound the objects
 
+    def enqueue_tiles_drr(self, poses: np.ndarray) -> int:
+        """First half of the tile-sharded objective (xrc_obj_fn_tiles_enqueue_drr): all poses, this rank's tiles."""
+        p12 = to12(poses) if np.asarray(poses).ndim == 3 else np.ascontiguousarray(poses, dtype=f32).reshape(-1, 12)
+        n = p12.shape[0]
+        self.rc._flush_params()
+        _lib.check(self._lib.xrc_obj_fn_tiles_enqueue_drr(self.rc.handle, 0, self.n_views, n, p12.ctypes.data_as(C.POINTER(C.c_float))))
+        self.rc._poses_dirty = False
+        self._cur_pop = -1
+        return n
+
+    def enqueue_units_metrics(self, n: int, first_unit: int, n_units: int) -> None:
+        """Second half (after the ranks' barrier): the metrics of the units this rank owns (xrc_obj_fn_units_enqueue_metrics)."""
+        if n_units == 0:
+            return
+        for sm in self.sims:
+            sm._pre_compute()
+        _lib.check(self._lib.xrc_obj_fn_units_enqueue_metrics(self.rc.handle, self._sm_arr, self.n_views, int(n), int(first_unit),
+                                                              int(n_units)))
+        self._cur_pop = -1
+
     def close(self) -> None:
         """Destroy the metrics and the ray caster (before their Context is closed)."""
         for sm in self.sims:
@@ -417,10 +437,26 @@ class ShardedDeviceObjFn:
     rank returns the full (n,) vector; values are bitwise those of the single-GPU objective (a pose's value does not
     depend on its batch).  The volume and fixed images are replicated; there is no other data-path collective."""
 
-    def __init__(self, fn: Intensity2D3DObjFn, rank: int, world_size: int, group=None):
+    def __init__(self, fn: Intensity2D3DObjFn, rank: int, world_size: int, group=None, mode: str = "poses"):
+        """mode "poses": every rank ray casts and scores its chunk of the (view, pose) list.  mode "tiles": every rank
+        ray casts its detector tiles of ALL projections and stores them into their owners' buffers over NVLink (CUDA IPC
+        peer mappings, include/xreg_cuda.h "Tile-sharded objective"), then scores the chunk it owns; `fn` must be
+        allocated for the whole population on every rank.  Same values either way, bit for bit."""
         import torch
 
         self.fn, self.rank, self.world_size, self.group = fn, int(rank), int(world_size), group
+        self.mode = mode
+        if mode not in ("poses", "tiles"):
+            raise _lib.XregError("ShardedDeviceObjFn: mode must be 'poses' or 'tiles'")
+        if mode == "tiles":
+            import torch.distributed as dist
+
+            handles = [None] * self.world_size
+            if self.world_size > 1:
+                dist.all_gather_object(handles, fn.rc.peer_export(), group=group)
+            else:
+                handles = [fn.rc.peer_export()]
+            fn.rc.peer_attach(self.world_size, self.rank, handles)
         self.n_views = fn.n_views
         self.device = torch.device("cuda", fn.ctx.device)
         self.stream = torch.cuda.ExternalStream(fn.ctx.stream, device=self.device)
@@ -429,6 +465,7 @@ class ShardedDeviceObjFn:
         self._recv = torch.zeros(cap * self.world_size, dtype=torch.float32, device=self.device)
         self._host = torch.zeros(cap * self.world_size, dtype=torch.float32).pin_memory()
         self._sims = [device_vector(sm.device_sims(), fn.max_pop, self.device) for sm in fn.sims]
+        self._flag = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.per_view: Optional[np.ndarray] = None
 
     def enqueue(self, poses: np.ndarray):
@@ -441,7 +478,15 @@ class ShardedDeviceObjFn:
         width = max(hi - lo for lo, hi in bounds)
         b, e = bounds[self.rank]
         with torch.cuda.stream(self.stream):
-            self.fn.enqueue_units(poses, b, e - b)
+            if self.mode == "tiles":
+                self.fn.enqueue_tiles_drr(poses)
+                if self.world_size > 1:
+                    # barrier ordered on the streams: every rank's tiles have landed in their owners' buffers (the
+                    # all-gather below is the barrier that protects those buffers from the NEXT call's stores)
+                    dist.all_reduce(self._flag, group=self.group)
+                self.fn.enqueue_units_metrics(n, b, e - b)
+            else:
+                self.fn.enqueue_units(poses, b, e - b)
             segs = view_segments(b, e, self.n_views, n)
             if len(segs) == 1 and width <= self.fn.max_pop:
                 send = self._sims[segs[0][0]][:width]          # zero copy: the metric's own result vector
