@@ -241,8 +241,10 @@ int xrc_sm_set_patch_params(xrc_sm* sm, uint32_t radius, uint32_t stride,
 enum { XRC_COMBINE_REFERENCE = 0, XRC_COMBINE_REFERENCE_SERIAL = 1, XRC_COMBINE_F64 = 2 };
 int xrc_sm_set_combine_mode(xrc_sm* sm, int mode);
 /* Instrumentation: the kernel behind XRC_COMBINE_REFERENCE on caller data.  host_vals: n_seq sequences of n floats;
- * host_out[s] = (((0 + v[s][0]) + v[s][1]) + ...) with one f32 rounding per addition.  serial != 0 runs the literal
- * loop instead of the parallel emulation.  Synchronises. */
+ * host_out[s] = (((0 + v[s][0]) + v[s][1]) + ...) with one f32 rounding per addition.  serial: 0 the parallel
+ * emulation (binades predicted from a float64 prefix sum, one cheap dependent pass), 1 the literal one-thread loop,
+ * 2 the round-to-round chained emulation (what sequences too long for the first fall back to), 10 + c the first with
+ * a cluster of c = 1, 2, 4 or 8 CTAs per sequence instead of the automatic choice.  Synchronises. */
 int xrc_seqsum_f32(xrc_ctx* ctx, const float* host_vals, uint32_t n_seq, uint64_t n, int serial, float* host_out);
 
 /* ImgSimMetric2DPatchCommon::set_patches_to_use / reset_patches_to_use and the random patches of

@@ -264,7 +264,7 @@ def _seqsum(ctx, seqs, serial=False):
     v = np.ascontiguousarray(seqs, dtype=f32)
     out = np.zeros(v.shape[0], dtype=f32)
     FP = C.POINTER(C.c_float)
-    _lib.check(lib.xrc_seqsum_f32(ctx.handle, v.ctypes.data_as(FP), v.shape[0], v.shape[1], 1 if serial else 0,
+    _lib.check(lib.xrc_seqsum_f32(ctx.handle, v.ctypes.data_as(FP), v.shape[0], v.shape[1], int(serial),
                                   out.ctypes.data_as(FP)))
     return out
 
@@ -282,7 +282,7 @@ def _bits(a):
     return np.ascontiguousarray(a, dtype=f32).view(np.uint32)
 
 
-@pytest.mark.parametrize("n", [0, 1, 5, 127, 128, 129, 1023, 4099, 206116])
+@pytest.mark.parametrize("n", [0, 1, 5, 127, 128, 129, 1023, 4099, 16384, 16385, 206116, 557000, 1600000])
 def test_seqsum_emulation_is_bit_exact(ctx, n):
     """patch_seqsum_kernel == the literal sequential f32 loop, bit for bit, on the sequences the metric produces
     (per-patch values in [0, 2], near-constant weighted values) and on adversarial ones (ties at every step, a sum
@@ -304,7 +304,10 @@ def test_seqsum_emulation_is_bit_exact(ctx, n):
     v = np.stack([np.asarray(s, dtype=f32) for s in seqs])
     want = _seq_literal(v)
     np.testing.assert_array_equal(_bits(_seqsum(ctx, v, serial=True)), _bits(want))
-    np.testing.assert_array_equal(_bits(_seqsum(ctx, v)), _bits(want))
+    np.testing.assert_array_equal(_bits(_seqsum(ctx, v)), _bits(want))             # two-phase emulation (default)
+    np.testing.assert_array_equal(_bits(_seqsum(ctx, v, serial=2)), _bits(want))   # chained emulation (fallback)
+    for cluster in (1, 2, 4, 8):                                                   # two-phase, forced cluster size
+        np.testing.assert_array_equal(_bits(_seqsum(ctx, v, serial=10 + cluster)), _bits(want))
     if n > 200:
         w = v[:1].copy()
         w[0, n // 2] = np.nan

@@ -13,6 +13,9 @@
 //     the reference's O(P * d^2) per image.
 #include "sim.h"
 
+#include <cooperative_groups.h>
+#include <cstring>
+
 namespace xrc
 {
 
@@ -1179,6 +1182,346 @@ __global__ void __launch_bounds__(kSeqWarps * 32) patch_seqsum_kernel(const SeqS
     a.out[blockIdx.x] = S;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Two-phase form of the same evaluation (the default).  patch_seqsum_kernel above carries S from round to round: 51
+// dependent rounds of a barrier-separated scan at C2 (206 116 addends), ~85 us however few sequences there are -- the
+// largest fixed cost of a small population's step (13 poses per GPU on 8 GPUs).  Here the binade of S at the start
+// of every chunk is PREDICTED from a float64 prefix sum, which removes the dependency from everything but a final
+// cheap walk, and a thread-block cluster of up to 8 CTAs shares the independent part of one sequence:
+//   pass 1 (every CTA of the cluster, its rounds of 16 384 addends): float64 round totals, exchanged through
+//     distributed shared memory -> the float64 sum in front of every round;
+//   pass 2 (same rounds): a block scan gives every chunk of 128 addends its predicted start value P; with
+//     key = sign | exponent of (float)P the chunk's addends are rounded to that binade's grid and the chunk records
+//     (sum, min / max prefix, key, bad) exactly as above, into the shared memory of the cluster's CTA 0;
+//   walk (warp 0 of CTA 0): goes through the records 32 at a time with the TRUE f32 sum S: a chunk is accepted if its
+//     key equals S's sign | exponent and its prefixes stay strictly inside the binade -- the same exactness argument
+//     as above; the prediction only decides which grid was prepared, never the result -- otherwise the chunk is
+//     summed by the literal loop (128 dependent adds) and the walk goes on with the new S.  Chunks the prediction
+//     already expects to fail (S = 0 at the start, binade crossings, ties) keep their addends in shared memory.
+// Bitwise equal to the literal loop on the same adversarial sequences (tests/test_gpu_metrics.py), for every
+// cluster size.
+constexpr int kS2Threads = 1024;
+constexpr int kS2Warps = kS2Threads / 32;
+constexpr int kS2RoundChunks = kS2Threads / 8;                 // 128 chunks
+constexpr int kS2Round = kS2RoundChunks * kSeqChunk;           // 16 384 addends per round
+constexpr int kS2Stash = 48;                     // chunks whose addends stay in shared memory for the literal loop
+constexpr int kS2Margin = 2048;                  // ulps: how close to a binade edge the prediction is not trusted
+constexpr int kS2MaxRounds = 96;                 // per sequence (bounds the shared-memory tables; longer -> chained kernel)
+constexpr unsigned kS2BadBit = 0x200u;           // meta: bits 0-8 key (sign | exponent), bit 9 bad, bits 16-23 stash slot + 1
+struct __align__(16) S2Rec
+{
+  int tot, mn, mx;   // pass 2: chunk sum, min / max prefix (grid units); after the window scan: inclusive sum, lo, hi
+  unsigned meta;
+};
+struct S2Fixed   // front of the dynamic shared memory; the records follow
+{
+  float stash[kS2Stash][kSeqChunk];
+  float stage[kSeqChunk];
+  double wt[2][kS2Warps];
+  double rt[kS2MaxRounds];    // float64 totals of this CTA's rounds (local round index)
+  double run[kS2MaxRounds];   // float64 sum in front of this CTA's rounds
+  int nstash;
+  int pad[3];
+};
+constexpr size_t kS2FixedSmem = sizeof(S2Fixed);
+constexpr size_t kS2MaxSmem = 200 * 1024;
+static_assert(kS2FixedSmem % 16 == 0, "records must stay 16-byte aligned");
+
+__global__ void __launch_bounds__(kS2Threads) patch_seqsum2_kernel(const SeqSumArgs a)
+{
+  namespace cg = cooperative_groups;
+  extern __shared__ __align__(16) unsigned char s2_smem[];
+  S2Fixed& sh = *reinterpret_cast<S2Fixed*>(s2_smem);
+  S2Rec* const recs = reinterpret_cast<S2Rec*>(s2_smem + kS2FixedSmem);   // [n_chunks], used in CTA 0 of the cluster
+  cg::cluster_group cluster = cg::this_cluster();
+  const uint32_t C = cluster.num_blocks(), rank = cluster.block_rank();
+  const uint32_t seq = blockIdx.x / C;
+  const float* __restrict__ v = a.vals + (size_t)seq * a.n;
+  const uint64_t n = a.n;
+  const uint32_t n_chunks = (uint32_t)((n + kSeqChunk - 1) / kSeqChunk);
+  const uint32_t n_rounds = (uint32_t)((n + kS2Round - 1) / kS2Round);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, qtr = lane >> 3;
+  if (tid == 0)
+    sh.nstash = 0;
+
+  // ---- pass 1: float64 totals of my rounds ----
+  int par = 0;
+  for (uint32_t R = rank, lr = 0; R < n_rounds; R += C, ++lr, par ^= 1)
+  {
+    float x[kSeqPerLane];
+    seq_load(v, n, (uint64_t)R * kS2Round + (uint64_t)tid * kSeqPerLane, x);
+    float s[kSeqPerLane / 2];
+#pragma unroll
+    for (int j = 0; j < kSeqPerLane / 2; ++j)
+      s[j] = x[2 * j] + x[2 * j + 1];
+    const float ls = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+    const double d = warp_sum((double)ls);
+    if (lane == 0)
+      sh.wt[par][warp] = d;
+    __syncthreads();  // one barrier per round: wt is double buffered by round parity
+    if (warp == 0)
+    {
+      const double w = warp_sum(sh.wt[par][lane]);
+      if (lane == 0)
+        sh.rt[lr] = w;
+    }
+  }
+  cluster.sync();
+  // the float64 sum in front of each of my rounds: prefix over all rounds' totals (read from their owners)
+  if (warp == 0)
+  {
+    double carry = 0.0;
+    for (uint32_t R0 = 0; R0 < n_rounds; R0 += 32)
+    {
+      const uint32_t R = R0 + lane;
+      double val = 0.0;
+      if (R < n_rounds)
+        val = cluster.map_shared_rank(sh.rt, R % C)[R / C];
+      double inc = val;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1)
+      {
+        const double y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o)
+          inc += y;
+      }
+      if (R < n_rounds && (R % C) == rank)
+        sh.run[R / C] = carry + (inc - val);
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+  }
+  __syncthreads();
+
+  // ---- pass 2: chunk records under the predicted binade, into CTA 0 ----
+  S2Rec* const recs0 = cluster.map_shared_rank(recs, 0);
+  float* const stash0 = cluster.map_shared_rank(&sh.stash[0][0], 0);
+  int* const nstash0 = cluster.map_shared_rank(&sh.nstash, 0);
+  for (uint32_t R = rank, lr = 0; R < n_rounds; R += C, ++lr, par ^= 1)
+  {
+    float x[kSeqPerLane];
+    seq_load(v, n, (uint64_t)R * kS2Round + (uint64_t)tid * kSeqPerLane, x);
+    float s[kSeqPerLane / 2];
+#pragma unroll
+    for (int j = 0; j < kSeqPerLane / 2; ++j)
+      s[j] = x[2 * j] + x[2 * j + 1];
+    double inc = (double)(((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7])));
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1)
+    {
+      const double y = __shfl_up_sync(0xffffffffu, inc, o, 8);
+      if ((lane & 7) >= o)
+        inc += y;
+    }
+    const double c0 = __shfl_sync(0xffffffffu, inc, 7), c1 = __shfl_sync(0xffffffffu, inc, 15);
+    const double c2 = __shfl_sync(0xffffffffu, inc, 23), c3 = __shfl_sync(0xffffffffu, inc, 31);
+    const double qpre = (qtr == 0) ? 0.0 : (qtr == 1) ? c0 : (qtr == 2) ? (c0 + c1) : ((c0 + c1) + c2);
+    if (lane == 0)
+      sh.wt[par][warp] = ((c0 + c1) + c2) + c3;
+    __syncthreads();
+    double wi = sh.wt[par][lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+      const double y = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o)
+        wi += y;
+    }
+    const double wprev = __shfl_sync(0xffffffffu, wi, warp > 0 ? warp - 1 : 0);
+    const double P = sh.run[lr] + ((warp > 0) ? wprev : 0.0) + qpre;
+
+    const float S0 = (float)P;
+    const unsigned key = __float_as_uint(S0) >> 23;
+    const int eb = (int)(key & 0xffu);
+    const bool fast = (eb >= 27) && (eb < 227);                             // 2^-100 <= |S0| < 2^100
+    // sign(S0) / u = +-2^(23 - e), exact (RN is symmetric: work with |S|, sgn * x)
+    const float sscale = __int_as_float(((fast ? (277 - eb) : 127) << 23) | (int)((key & 0x100u) << 23));
+    int p = 0, mn = 0x7fffffff, mx = -0x7fffffff - 1;
+    float tsum = 0.0f, tie = 1.0f;
+#pragma unroll
+    for (int j = 0; j < kSeqPerLane; ++j)
+    {
+      const float t = __fmul_rn(x[j], sscale);            // exact (power of two) or flushed towards 0 when tiny
+      const float tm = __fadd_rn(t, 12582912.0f);         // rint by the 1.5 * 2^23 trick (exact for |t| < 2^22)
+      const float r = __fadd_rn(tm, -12582912.0f);
+      tsum = __fadd_rn(tsum, fabsf(t));                                       // NaN / Inf propagate
+      tie = fminf(tie, fabsf(__fadd_rn(fabsf(__fsub_rn(t, r)), -0.5f)));      // 0 iff some t lies exactly half-way
+      p += __float_as_int(tm) - 0x4B400000;
+      mn = min(mn, p);
+      mx = max(mx, p);
+    }
+    // sum |t| <= 2^21 keeps every t inside the trick's exact range and every integer below far inside int32
+    // (|chunk sum| <= 2^24); NaN fails the comparison.  (fminf drops a NaN operand, tsum catches it.)
+    const bool bad = !fast || !(tsum <= 2097152.0f) || (tie == 0.0f);
+    const bool any_bad = ((__ballot_sync(0xffffffffu, bad) >> (8 * qtr)) & 0xffu) != 0u;
+    if (any_bad)
+    {
+      p = 0;
+      mn = 0;
+      mx = 0;
+    }
+    int incl = p;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1)
+    {
+      const int y = __shfl_up_sync(0xffffffffu, incl, o, 8);
+      if ((lane & 7) >= o)
+        incl += y;
+    }
+    const int pre = incl - p;
+    mn += pre;
+    mx += pre;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1)
+    {
+      mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o, 8));
+      mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o, 8));
+    }
+    const int tot = __shfl_sync(0xffffffffu, incl, 7, 8);
+    const uint32_t gc = R * kS2RoundChunks + (uint32_t)(tid >> 3);
+    // does the prediction itself expect this chunk to go to the literal loop?  Then keep its addends on chip.
+    int slot = -1;
+    if ((lane & 7) == 0 && gc < n_chunks)
+    {
+      const long long A0 = (long long)((__float_as_uint(S0) & 0x7fffffu) | 0x800000u);
+      const bool likely = any_bad || (A0 + mn < (1ll << 23) + 1 + kS2Margin) || (A0 + mx > (1ll << 24) - 1 - kS2Margin);
+      if (likely)
+      {
+        const int sl = atomicAdd(nstash0, 1);
+        slot = (sl < kS2Stash) ? sl : -1;
+      }
+      S2Rec rec;
+      rec.tot = tot;
+      rec.mn = mn;
+      rec.mx = mx;
+      rec.meta = key | (any_bad ? kS2BadBit : 0u) | ((unsigned)(slot + 1) << 16);
+      recs0[gc] = rec;
+    }
+    slot = __shfl_sync(0xffffffffu, slot, 0, 8);
+    if (slot >= 0)
+    {
+      float4* dst = reinterpret_cast<float4*>(stash0 + (size_t)slot * kSeqChunk + (lane & 7) * kSeqPerLane);
+#pragma unroll
+      for (int k = 0; k < kSeqPerLane / 4; ++k)
+        dst[k] = make_float4(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]);
+    }
+  }
+  cluster.sync();  // all records and stashed chunks have landed in CTA 0; nobody reads a peer's memory after this
+  if (rank != 0)
+    return;
+
+  // ---- window scan (all warps): per window of 32 chunks the inclusive sum of the chunk sums, and the range of
+  // |S| / u at the window's start (minus what the walk has accepted before) for which the chunk's prefixes stay
+  // strictly inside the binade.  Units differ between chunks of different keys; only the run of chunks whose key
+  // matches S is ever used, and beyond the first rejected chunk nothing is.
+  for (uint32_t w0 = 32u * warp; w0 < n_chunks; w0 += 32u * kS2Warps)
+  {
+    const uint32_t gc = w0 + (uint32_t)lane;
+    const bool exists = gc < n_chunks;
+    S2Rec rec;
+    rec.tot = 0;
+    rec.mn = 0;
+    rec.mx = 0;
+    rec.meta = kS2BadBit;
+    if (exists)
+      rec = recs[gc];
+    int incl = rec.tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+      const int y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o)
+        incl += y;
+    }
+    if (exists)
+    {
+      const int excl = incl - rec.tot;
+      rec.mn = (int)((1u << 23) + 1u - (unsigned)rec.mn - (unsigned)excl);   // lo: wraps only beyond a rejected chunk
+      rec.mx = (int)((1u << 24) - 1u - (unsigned)rec.mx - (unsigned)excl);   // hi
+      rec.tot = incl;
+      recs[gc] = rec;
+    }
+  }
+  __syncthreads();
+  if (warp != 0)
+    return;
+
+  // ---- the walk with the true sum ----
+  float S = 0.0f;
+  for (uint32_t w0 = 0; w0 < n_chunks; w0 += 32)
+  {
+    const uint32_t gc = w0 + (uint32_t)lane;
+    S2Rec rec;
+    rec.tot = 0;
+    rec.mn = 0x7fffffff;   // lo > hi: never valid
+    rec.mx = -0x7fffffff - 1;
+    rec.meta = kS2BadBit;
+    if (gc < n_chunks)
+      rec = recs[gc];
+    const int n_here = (int)min(32u, n_chunks - w0);
+    int first = 0;
+    int base = 0;  // inclusive sum up to chunk first - 1: what lo / hi / tot of the later chunks still contain
+    while (first < n_here)
+    {
+      const unsigned sb = __float_as_uint(S);
+      const unsigned key = sb >> 23;
+      const int A = (int)((sb & 0x7fffffu) | 0x800000u);  // |S| / u when S is normal
+      const int Arel = A - base;
+      // a record's key can only equal S's when the prediction was in the fast range and the chunk is not bad
+      const bool valid = (lane < first) || (((rec.meta & 0x3ffu) == key) && (Arel >= rec.mn) && (Arel <= rec.mx));
+      const unsigned fails = __ballot_sync(0xffffffffu, !valid);
+      const int ok = fails ? (__ffs(fails) - 1) : 32;  // >= first
+      if (ok > first)
+      {
+        const int inc = __shfl_sync(0xffffffffu, rec.tot, ok - 1);
+        const int A_out = Arel + inc;                                    // in [2^23 + 1, 2^24 - 1]
+        const float u = __int_as_float((int)((key & 0xffu) - 23u) << 23);
+        const float mag = __fmul_rn((float)A_out, u);                   // exact
+        S = (key & 0x100u) ? -mag : mag;
+      }
+      if (ok < n_here)
+      {
+        // the literal loop over chunk w0 + ok: every lane runs the same chain on broadcast shared-memory reads
+        const unsigned meta = __shfl_sync(0xffffffffu, rec.meta, ok);
+        base = __shfl_sync(0xffffffffu, rec.tot, ok);
+        const int slot = (int)((meta >> 16) & 0xffu) - 1;
+        const float4* src = reinterpret_cast<const float4*>(sh.stage);
+        if (slot >= 0)
+        {
+          src = reinterpret_cast<const float4*>(sh.stash[slot]);
+        }
+        else
+        {
+          const uint64_t i0 = (uint64_t)(w0 + ok) * kSeqChunk + 4u * lane;
+          float4 q;
+          q.x = (i0 < n) ? __ldg(v + i0) : 0.0f;
+          q.y = (i0 + 1 < n) ? __ldg(v + i0 + 1) : 0.0f;
+          q.z = (i0 + 2 < n) ? __ldg(v + i0 + 2) : 0.0f;
+          q.w = (i0 + 3 < n) ? __ldg(v + i0 + 3) : 0.0f;
+          __syncwarp();
+          reinterpret_cast<float4*>(sh.stage)[lane] = q;
+          __syncwarp();
+        }
+#pragma unroll 8
+        for (int k = 0; k < kSeqChunk / 4; ++k)
+        {
+          const float4 q = src[k];
+          S = __fadd_rn(S, q.x);
+          S = __fadd_rn(S, q.y);
+          S = __fadd_rn(S, q.z);
+          S = __fadd_rn(S, q.w);
+        }
+        first = ok + 1;
+      }
+      else
+      {
+        first = n_here;
+      }
+    }
+  }
+  if (lane == 0)
+    a.out[seq] = S;
+}
+
 __global__ void patch_seqsum_serial_kernel(const SeqSumArgs a)
 {
   const float* __restrict__ v = a.vals + (size_t)blockIdx.x * a.n;
@@ -1192,10 +1535,47 @@ int launch_seqsum(const SeqSumArgs& a, cudaStream_t st)
 {
   if (!a.n_seq)
     return XRC_OK;
-  if (a.serial)
+  const size_t n_chunks = (size_t)((a.n + kSeqChunk - 1) / kSeqChunk);
+  const size_t n_rounds = (size_t)((a.n + kS2Round - 1) / kS2Round);
+  const size_t smem2 = kS2FixedSmem + n_chunks * sizeof(S2Rec);
+  if (a.serial == 1)
+  {
     patch_seqsum_serial_kernel<<<a.n_seq, 1, 0, st>>>(a);
+  }
+  else if (a.serial == 2 || smem2 > kS2MaxSmem || n_rounds > (size_t)kS2MaxRounds)
+  {
+    patch_seqsum_kernel<<<a.n_seq, kSeqWarps * 32, 0, st>>>(a);   // the round-to-round chain (any length)
+  }
   else
-    patch_seqsum_kernel<<<a.n_seq, kSeqWarps * 32, 0, st>>>(a);
+  {
+    static bool attr_set[64] = {};
+    int dev = 0;
+    XRC_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !attr_set[dev])
+    {
+      XRC_CUDA(cudaFuncSetAttribute(patch_seqsum2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kS2MaxSmem));
+      attr_set[dev] = true;
+    }
+    // CTAs per sequence: few sequences (a small population) spread each one over a cluster; serial = 10 + c forces c
+    unsigned c = (a.n_seq <= 18u) ? 8u : (a.n_seq <= 37u) ? 4u : (a.n_seq <= 74u) ? 2u : 1u;
+    if (a.serial >= 11 && a.serial <= 18)
+      c = (unsigned)(a.serial - 10);
+    while (c > 1u && (c > n_rounds || (c & (c - 1u))))
+      --c;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(a.n_seq * c);
+    cfg.blockDim = dim3(kS2Threads);
+    cfg.dynamicSmemBytes = smem2;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = c;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    XRC_CUDA(cudaLaunchKernelEx(&cfg, patch_seqsum2_kernel, a));
+  }
   count_launch();
   XRC_CUDA(cudaGetLastError());
   return XRC_OK;

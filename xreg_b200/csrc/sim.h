@@ -106,7 +106,7 @@ struct SeqSumArgs
   uint64_t n;
   uint32_t n_seq;
   float* out;          // n_seq
-  int serial;
+  int serial;         // 0: two-phase emulation, 1: literal loop, 2: chained emulation
 };
 int launch_seqsum(const SeqSumArgs& a, cudaStream_t st);
 // dst[seq][j] = vals[seq][subset[j]] for n_seq sequences of n_patches values (patch subsets)
