@@ -239,6 +239,8 @@ def main():
     ap.add_argument("--no-weak", action="store_true", help="skip the secondary weak-scaling figure at N > 1")
     ap.add_argument("--shard", default="tiles", choices=["tiles", "poses"],
                     help="N > 1: shard the detector tiles (projections stored into their owners over NVLink) or the poses")
+    ap.add_argument("--balance", type=int, default=3,
+                    help="N > 1, tile sharding: rounds of clock feedback on the tile plan before the timed region (0 = samples only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     w = dict(WORKLOADS[args.workload])
@@ -421,6 +423,10 @@ def main():
         S, F = [], []
         if tiles:
             step_resident, drr_tiles, keep = make_tile_step()
+            # one-time set-up, like the plan itself: let the ranks' measured kernel times correct the tile ranges
+            tile_plan = sharded.balance(pops[0], rounds=args.balance) if args.balance > 0 else fn.rc.plan_tiles(n_ranks=world)
+            fn.rc.set_num_projs(n_units)
+            fn._cur_pop = -1
             for k in range(n_sets):
                 set_resident(keep, k, n_units)
                 a_k, f_k = fn.rc.tile_samples()
@@ -572,6 +578,9 @@ def main():
                                             "images replicated, per-view scalars all-gathered (NCCL)" % world)) if world > 1
                                           else "one GPU",
                            "shard": (args.shard if world > 1 else None),
+                           "tile_plan": ({"bounds": tile_plan, "clock_feedback_rounds": args.balance,
+                                          "drr_ms_per_rank_before_last_cut": getattr(sharded, "last_balance_ms", None)}
+                                         if tiles else None),
                            "layout": args.layout, "cta_order": args.order,
                            "volume_bytes_resident": fn.rc.volume_bytes(),
                            "cache": "volume payload larger than L2 (126 MB) and a different pose population every step"},

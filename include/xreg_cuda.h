@@ -353,6 +353,10 @@ int xrc_obj_fn_units_enqueue(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, u
  *                        projections balances; exact integer counts, so every rank derives the same plan on its own.
  *                        Done implicitly by the first xrc_rc_compute_tiles after an attach; call it again when the pose
  *                        distribution moves (a new registration level).  xrc_rc_tile_plan reads the n_ranks + 1 bounds.
+ *   xrc_rc_plan_tiles_timed  feedback from the clock: rank_ms[r] = what rank r's ray-casting kernel took under the current
+ *                        plan (the same n_ranks numbers on every rank, e.g. all-gathered CUDA-event times); the tiles of a
+ *                        rank that took longer than its planned share get a larger cost multiplier and the ranges are cut
+ *                        again (samples are only a proxy of a tile's cost).  Two or three rounds settle within ~1 %.
  *   xrc_rc_compute_tiles RayCaster::compute for this rank's tiles of all current projections, written to their owners
  *   xrc_rc_tile_samples  instrumentation: trilinear samples of this rank's tiles (algorithmic / fetched), for rooflines */
 #define XRC_IPC_HANDLE_BYTES 64
@@ -360,6 +364,7 @@ int xrc_rc_peer_export(xrc_rc* rc, uint8_t handle[XRC_IPC_HANDLE_BYTES]);
 int xrc_rc_peer_attach(xrc_rc* rc, uint32_t n_ranks, uint32_t rank, const uint8_t* handles);
 int xrc_rc_peer_detach(xrc_rc* rc);
 int xrc_rc_plan_tiles(xrc_rc* rc, uint32_t vol_idx);
+int xrc_rc_plan_tiles_timed(xrc_rc* rc, uint32_t vol_idx, const float* rank_ms);
 int xrc_rc_tile_plan(const xrc_rc* rc, uint32_t* tile_begin);
 int xrc_rc_compute_tiles(xrc_rc* rc, uint32_t vol_idx);
 int xrc_rc_tile_samples(xrc_rc* rc, uint32_t vol_idx, uint64_t* algorithmic, uint64_t* fetched);

@@ -33,6 +33,10 @@ def test_sharded_device_objective_world_1(ctx, xo, small_scene):
             np.testing.assert_array_equal(sh(pop), ref)
             np.testing.assert_array_equal(sh(pop[1:4]), ref[1:4])
             np.testing.assert_array_equal(fn.rc.raw_host_pixel_buf()[:3], single_projs[1:4])
+            if mode == "tiles":
+                plan = sh.balance(pop, rounds=2, reps=2)     # clock feedback: one rank keeps all tiles, values unchanged
+                assert plan[0] == 0 and plan[-1] > 0 and len(plan) == 2
+                np.testing.assert_array_equal(sh(pop), ref)
         np.testing.assert_array_equal(sh(pop), ref)
         np.testing.assert_array_equal(sh(pop[2:7]), ref[2:7])
         np.testing.assert_array_equal(sh(pop[4:5]), ref[4:5])

@@ -139,6 +139,7 @@ SIGNATURES = {
     "xrc_rc_peer_detach": [_VP],
     "xrc_rc_compute_tiles": [_VP, _U32],
     "xrc_rc_plan_tiles": [_VP, _U32],
+    "xrc_rc_plan_tiles_timed": [_VP, _U32, _FP],
     "xrc_rc_tile_plan": [_VP, _U32P],
     "xrc_rc_tile_samples": [_VP, _U32, C.POINTER(_U64), C.POINTER(_U64)],
     "xrc_obj_fn_tiles_enqueue_drr": [_VP, _U32, _U32, _U32, _FP],

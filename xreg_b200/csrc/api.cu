@@ -120,6 +120,9 @@ struct xrc_rc
   // contiguous tile ranges of the ranks, balanced by measured work (xrc_rc_plan_tiles): rank r owns tiles
   // [tile_begin[r], tile_begin[r + 1]); empty until planned
   std::vector<uint32_t> tile_begin;
+  // per-tile cost multipliers learnt from the ranks' measured kernel times (xrc_rc_plan_tiles_timed); empty = all 1
+  std::vector<double> tile_mult;
+  std::vector<double> tile_work;   // the work estimate of the last plan (samples + set-up), before the multipliers
   float* h_poses = nullptr;   // pinned staging: max_projs x 12 floats
   uint32_t* h_cam_idx = nullptr;
   float* d_poses = nullptr;
@@ -333,6 +336,8 @@ static void rc_peer_detach(xrc_rc* rc)
     rc->peer_bufs[r] = nullptr;
   rc->peer_n = 0;
   rc->tile_begin.clear();
+  rc->tile_mult.clear();
+  rc->tile_work.clear();
 }
 
 static void rc_free_vols(xrc_rc* rc)
@@ -987,11 +992,8 @@ int xrc_rc_peer_detach(xrc_rc* rc)
 // integers, identical on every rank, so all ranks derive the same plan without talking), plus a constant per ray for
 // its set-up.  Planned once per attach (first xrc_rc_compute_tiles) or on request; an optimiser's later populations
 // stay around the same pose, so the plan stays balanced.
-int xrc_rc_plan_tiles(xrc_rc* rc, uint32_t vol_idx)
+static int rc_count_tile_work(xrc_rc* rc, uint32_t vol_idx)
 {
-  XRC_CHECK_ARG(rc, "null ray caster");
-  XRC_CHECK_ARG(rc->allocated && rc->peer_n >= 1, "xrc_rc_plan_tiles: allocate and attach first");
-  XRC_CHECK_ARG(vol_idx < rc->vols.size(), "xrc_rc_plan_tiles: volume index out of range");
   XRC_TRY(use_device(rc->ctx));
   XRC_TRY(rc_prepare_stacks(rc, vol_idx));
   XRC_CHECK_ARG(rc->vols[vol_idx].layout == XRC_LAYOUT_PAX, "xrc_rc_plan_tiles: needs the default volume layout");
@@ -1019,23 +1021,76 @@ int xrc_rc_plan_tiles(xrc_rc* rc, uint32_t vol_idx)
   cudaFree(d_cnt);
   XRC_TRY(status);
   // work of a tile: its fetched samples + 40 sample-equivalents per ray for set-up, trimming and the store
-  std::vector<double> w(nt);
+  rc->tile_work.resize(nt);
+  for (uint32_t t = 0; t < nt; ++t)
+    rc->tile_work[t] = (double)cnt[t] + 40.0 * 256.0 * (double)rc->num_projs;
+  if (rc->tile_mult.size() != nt)
+    rc->tile_mult.assign(nt, 1.0);
+  return XRC_OK;
+}
+
+// contiguous ranges of equal (work x multiplier)
+static void rc_cut_tiles(xrc_rc* rc)
+{
+  const uint32_t nt = (uint32_t)rc->tile_work.size();
   double total = 0.0;
   for (uint32_t t = 0; t < nt; ++t)
-  {
-    w[t] = (double)cnt[t] + 40.0 * 256.0 * (double)rc->num_projs;
-    total += w[t];
-  }
+    total += rc->tile_work[t] * rc->tile_mult[t];
   rc->tile_begin.assign(rc->peer_n + 1, nt);
   rc->tile_begin[0] = 0;
   double acc = 0.0;
   uint32_t r = 1;
   for (uint32_t t = 0; t < nt && r < rc->peer_n; ++t)
   {
-    acc += w[t];
+    acc += rc->tile_work[t] * rc->tile_mult[t];
     while (r < rc->peer_n && acc >= total * (double)r / (double)rc->peer_n)
       rc->tile_begin[r++] = t + 1;
   }
+}
+
+int xrc_rc_plan_tiles(xrc_rc* rc, uint32_t vol_idx)
+{
+  XRC_CHECK_ARG(rc, "null ray caster");
+  XRC_CHECK_ARG(rc->allocated && rc->peer_n >= 1, "xrc_rc_plan_tiles: allocate and attach first");
+  XRC_CHECK_ARG(vol_idx < rc->vols.size(), "xrc_rc_plan_tiles: volume index out of range");
+  XRC_TRY(rc_count_tile_work(rc, vol_idx));
+  rc_cut_tiles(rc);
+  return XRC_OK;
+}
+
+// Feedback from the clock: samples are only a proxy of a tile's cost (beams near the detector's edge coalesce worse,
+// long central beams hit L2 more often), so a plan balanced by samples leaves the ranks' kernels a few percent apart.
+// rank_ms[r] = the time rank r's ray-casting kernel took under the CURRENT plan (every rank passes the same n_ranks
+// numbers, e.g. all-gathered CUDA-event times, so that every rank derives the same new plan).  Each rank's tiles get
+// their cost multiplier scaled by (measured time / planned share) ^ 0.7, and the ranges are cut again on the sample
+// counts of the current projections.  Two or three rounds settle within ~1 %.
+int xrc_rc_plan_tiles_timed(xrc_rc* rc, uint32_t vol_idx, const float* rank_ms)
+{
+  XRC_CHECK_ARG(rc && rank_ms, "null argument");
+  XRC_CHECK_ARG(rc->allocated && rc->peer_n >= 1, "xrc_rc_plan_tiles_timed: allocate and attach first");
+  XRC_CHECK_ARG(vol_idx < rc->vols.size(), "xrc_rc_plan_tiles_timed: volume index out of range");
+  XRC_CHECK_ARG(rc->tile_begin.size() == (size_t)rc->peer_n + 1 && !rc->tile_work.empty(),
+                "xrc_rc_plan_tiles_timed: no plan yet (the times must belong to a plan)");
+  double sum_ms = 0.0, sum_w = 0.0;
+  std::vector<double> share(rc->peer_n, 0.0);
+  for (uint32_t r = 0; r < rc->peer_n; ++r)
+  {
+    XRC_CHECK_ARG(rank_ms[r] > 0.0f && rank_ms[r] < 1.0e9f, "xrc_rc_plan_tiles_timed: times must be positive and finite");
+    for (uint32_t t = rc->tile_begin[r]; t < rc->tile_begin[r + 1]; ++t)
+      share[r] += rc->tile_work[t] * rc->tile_mult[t];
+    sum_ms += rank_ms[r];
+    sum_w += share[r];
+  }
+  for (uint32_t r = 0; r < rc->peer_n; ++r)
+  {
+    if (!(share[r] > 0.0))
+      continue;
+    const double f = pow(((double)rank_ms[r] / sum_ms) / (share[r] / sum_w), 0.7);
+    for (uint32_t t = rc->tile_begin[r]; t < rc->tile_begin[r + 1]; ++t)
+      rc->tile_mult[t] *= f;
+  }
+  XRC_TRY(rc_count_tile_work(rc, vol_idx));
+  rc_cut_tiles(rc);
   return XRC_OK;
 }
 

@@ -378,6 +378,16 @@ class RayCasterLineIntCUDA:
         check(self._lib.xrc_rc_tile_plan(self.handle, out))
         return [int(v) for v in out[: (n_ranks + 1) if n_ranks else 9]]
 
+    def plan_tiles_timed(self, rank_ms: Sequence[float], vol_idx: int = 0) -> List[int]:
+        """Re-cut the ranks' tile ranges from the kernel times they measured under the current plan (the same list
+        on every rank); returns the new bounds."""
+        self._flush()
+        ms = (C.c_float * len(rank_ms))(*[float(v) for v in rank_ms])
+        check(self._lib.xrc_rc_plan_tiles_timed(self.handle, int(vol_idx), ms))
+        out = (C.c_uint32 * 9)()
+        check(self._lib.xrc_rc_tile_plan(self.handle, out))
+        return [int(v) for v in out[: len(rank_ms) + 1]]
+
     def tile_samples(self, vol_idx: int = 0):
         """(algorithmic, fetched) trilinear samples of this rank's tiles for the current poses."""
         self._flush()

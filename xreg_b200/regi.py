@@ -468,6 +468,45 @@ class ShardedDeviceObjFn:
         self._flag = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.per_view: Optional[np.ndarray] = None
 
+    def balance(self, poses: np.ndarray, rounds: int = 3, reps: int = 3) -> List[int]:
+        """mode "tiles" (collective: every rank calls it with the same population): let the clock correct the tile
+        plan.  Per round every rank times its ray-casting kernel on `poses` (CUDA events on the library's stream, best
+        of `reps`), the times are all-gathered and xrc_rc_plan_tiles_timed re-cuts the ranges; every rank derives the
+        same plan.  Returns the final tile bounds.  Results never depend on the plan (a pixel is the same whichever GPU
+        computes it); worth calling once per registration level, where the pose distribution moves."""
+        import torch
+        import torch.distributed as dist
+
+        if self.mode != "tiles":
+            return []
+        plan: List[int] = []
+        t = torch.zeros(self.world_size, dtype=torch.float32, device=self.device)
+        mine = torch.zeros(1, dtype=torch.float32, device=self.device)
+        for _ in range(max(int(rounds), 0)):
+            best = float("inf")
+            with torch.cuda.stream(self.stream):
+                self.fn.enqueue_tiles_drr(poses)      # the first launch (re)builds the plan if there is none
+                for _r in range(max(int(reps), 1)):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    if self.world_size > 1:
+                        dist.all_reduce(self._flag, group=self.group)   # start together: peers' stores share NVLink
+                    e0.record(self.stream)
+                    self.fn.rc.compute_tiles()
+                    e1.record(self.stream)
+                    e1.synchronize()
+                    best = min(best, e0.elapsed_time(e1))
+                mine.fill_(best)
+                if self.world_size > 1:
+                    dist.all_gather_into_tensor(t, mine, group=self.group)
+                else:
+                    t.copy_(mine)
+            self.stream.synchronize()
+            plan = self.fn.rc.plan_tiles_timed([float(v) for v in t.cpu().tolist()])
+        if self.world_size > 1:
+            dist.barrier(group=self.group)
+        self.last_balance_ms = [float(v) for v in t.cpu().tolist()]
+        return plan
+
     def enqueue(self, poses: np.ndarray):
         """Everything but the final synchronise: returns (bounds, width) for collect()."""
         import torch
