@@ -237,8 +237,9 @@ def main():
     ap.add_argument("--order", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-weak", action="store_true", help="skip the secondary weak-scaling figure at N > 1")
-    ap.add_argument("--shard", default="tiles", choices=["tiles", "poses"],
-                    help="N > 1: shard the detector tiles (projections stored into their owners over NVLink) or the poses")
+    ap.add_argument("--shard", default="tiles", choices=["tiles", "tiles-nccl", "poses"],
+                    help="N > 1: shard the detector tiles (projections stored into their owners over NVLink; barrier and gather "
+                         "of the scalars by the library's kernel over the peer mappings, or by NCCL) or the poses")
     ap.add_argument("--balance", type=int, default=3,
                     help="N > 1, tile sharding: rounds of clock feedback on the tile plan before the timed region (0 = samples only)")
     args = ap.parse_args()
@@ -388,8 +389,8 @@ def main():
                 dist.all_reduce(ms, op=dist.ReduceOp.MAX)
             return float(ms.item())
 
-        tiles = world > 1 and args.shard == "tiles"
-        sharded = regi.ShardedDeviceObjFn(fn, rank, world, mode="tiles" if tiles else "poses") if world > 1 else None
+        tiles = world > 1 and args.shard in ("tiles", "tiles-nccl")
+        sharded = regi.ShardedDeviceObjFn(fn, rank, world, mode=args.shard) if world > 1 else None
         flag = torch.zeros(1, dtype=torch.float32, device=dev)
 
         def make_tile_step():
@@ -404,6 +405,11 @@ def main():
                 set_resident(res, k, n_units)
                 fn.rc.compute_tiles()
 
+            def step_ipc(k):
+                drr_only(k)
+                check(lib.xrc_rc_peer_barrier(fn.rc.handle))
+                check(lib.xrc_obj_fn_tiles_enqueue_gather(fn.rc.handle, sm_all, n_views, pop_n))
+
             def step(k):
                 drr_only(k)
                 dist.all_reduce(flag)
@@ -417,7 +423,7 @@ def main():
                         send[off:off + cnt].copy_(sims_dev[v][:cnt])
                         off += cnt
                 dist.all_gather_into_tensor(gathered[: width * world], send)
-            return step, drr_only, res
+            return (step if args.shard == "tiles-nccl" else step_ipc), drr_only, res
 
         # exact sample counts S_k of this rank's share per population -- untimed
         S, F = [], []
@@ -572,8 +578,9 @@ def main():
                            "parallelism": (("detector tiles sharded x%d round robin: every GPU ray casts its tiles of ALL projections "
                                             "and stores them into their owners' buffers over NVLink (peer stores from the DRR "
                                             "kernel, CUDA IPC); the (view, pose) list is cut into contiguous balanced chunks for "
-                                            "the metrics; barrier + all-gather of the scalars (NCCL); volume and fixed images "
-                                            "replicated" % world) if tiles else
+                                            "the metrics; barrier + all-gather of the scalars (%s); volume and fixed images "
+                                            "replicated" % (world, "NCCL" if args.shard == "tiles-nccl" else
+                                                            "one kernel per rank over the same peer mappings: system-scope flags + NVLink stores")) if tiles else
                                            ("(view, pose) list sharded x%d (contiguous balanced chunks), volume and fixed "
                                             "images replicated, per-view scalars all-gathered (NCCL)" % world)) if world > 1
                                           else "one GPU",

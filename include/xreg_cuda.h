@@ -375,6 +375,23 @@ int xrc_rc_tile_samples(xrc_rc* rc, uint32_t vol_idx, uint64_t* algorithmic, uin
 int xrc_obj_fn_tiles_enqueue_drr(xrc_rc* rc, uint32_t vol_idx, uint32_t n_views, uint32_t n_poses, const float* cam_to_phys);
 int xrc_obj_fn_units_enqueue_metrics(xrc_rc* rc, xrc_sm* const* sms, uint32_t n_views, uint32_t n_poses, uint32_t first_unit,
                                      uint32_t n_units);
+/* The same step without NCCL: the barrier and the all-gather of the scalars are done by one small kernel per rank over the
+ * peer mappings (an exchange block at the tail of every rank's projection buffer: system-scope flags and NVLink stores).
+ *   xrc_rc_peer_barrier              enqueue: signal every rank, wait for every rank (stream-ordered: what this stream did
+ *                                    before -- the ray casting into the peers' buffers -- is visible to a rank that passes)
+ *   xrc_obj_fn_tiles_enqueue_gather  enqueue: every view's metric over the units this rank owns (rank r owns chunk r of the
+ *                                    camera-major list cut into n_ranks contiguous balanced chunks), their values stored into
+ *                                    EVERY rank's gathered vector, barrier, all n_views x n_poses values to host-mapped memory
+ *   xrc_obj_fn_tiles_finish          synchronise; per_view_out[v * n_poses + p] (optional) and the mean over the views
+ *   xrc_obj_fn_tiles                 the whole evaluation in one call: enqueue_drr, barrier, enqueue_gather, finish.  Every
+ *                                    rank calls it with the same poses and gets the same values, bitwise those of one GPU.
+ * All ranks must make the same sequence of these calls (the barriers count epochs), with buffers allocated for the same
+ * detector and max_projs.  A rank that does not arrive within 30 s makes the others return XRC_ERR_CUDA instead of hanging. */
+int xrc_rc_peer_barrier(xrc_rc* rc);
+int xrc_obj_fn_tiles_enqueue_gather(xrc_rc* rc, xrc_sm* const* sms, uint32_t n_views, uint32_t n_poses);
+int xrc_obj_fn_tiles_finish(xrc_rc* rc, uint32_t n_views, uint32_t n_poses, float* sims_out, float* per_view_out);
+int xrc_obj_fn_tiles(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t n_views, uint32_t n_poses,
+                     const float* cam_to_phys, float* sims_out, float* per_view_out);
 /* The partition xrc_obj_fn_multi uses (host only, needs no device): of view `view`, device `dev` evaluates the poses
  * [*first_pose, *first_pose + *count).  For sizing the per-device objects and for callers that shard by themselves. */
 int xrc_obj_fn_multi_share(uint32_t n_dev, uint32_t n_views, uint32_t n_poses, uint32_t dev, uint32_t view,

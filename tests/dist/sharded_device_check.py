@@ -45,11 +45,11 @@ def main():
         rc0.close()
         single = regi.Intensity2D3DObjFn(ctx, vol, cams, fixed, metric=metric, max_pop=11, patch_radius=6)
         ref = single(pop)
-        for mode in ("poses", "tiles"):
+        for mode in ("poses", "tiles", "tiles-nccl"):
             fn = regi.Intensity2D3DObjFn(ctx, vol, cams, fixed, metric=metric, max_pop=11, patch_radius=6)
             sharded = regi.ShardedDeviceObjFn(fn, rank, world, mode=mode)
             for i_sel, sel in enumerate((slice(0, 11), slice(3, 10), slice(5, 6), slice(0, 2), slice(0, 11))):
-                if mode == "tiles" and i_sel == 3:
+                if mode.startswith("tiles") and i_sel == 3:
                     # clock feedback on the tile plan (collective): the plan may move, the values may not
                     plan = sharded.balance(pop, rounds=2, reps=2)
                     assert len(plan) == world + 1 and plan[0] == 0 and all(a <= b for a, b in zip(plan, plan[1:])), plan
@@ -64,7 +64,7 @@ def main():
                 if rank == 0:
                     print(json.dumps({"world": world, "mode": mode, "views": len(cams), "metric": metric, "poses": int(len(got)),
                                       "bitwise_equal_to_single_gpu": same}), flush=True)
-            if mode == "tiles":
+            if mode.startswith("tiles"):
                 # the projections this rank OWNS were assembled from every rank's tiles: they must equal the single-GPU ones
                 n = 11
                 b, e = regi.unit_chunks(len(cams) * n, world)[rank]

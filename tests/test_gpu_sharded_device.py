@@ -28,12 +28,12 @@ def test_sharded_device_objective_world_1(ctx, xo, small_scene):
         ref = single(pop)
         single_projs = single.rc.raw_host_pixel_buf().copy()
         fn = regi.Intensity2D3DObjFn(ctx, vol, cs, fx, metric="grad-ncc", max_pop=9)
-        for mode in ("poses", "tiles"):     # "tiles" on one rank: this rank's tiles are all tiles, its own buffer the only owner
+        for mode in ("poses", "tiles", "tiles-nccl"):     # "tiles" on one rank: this rank's tiles are all tiles, its own buffer the only owner
             sh = regi.ShardedDeviceObjFn(fn, 0, 1, mode=mode)
             np.testing.assert_array_equal(sh(pop), ref)
             np.testing.assert_array_equal(sh(pop[1:4]), ref[1:4])
             np.testing.assert_array_equal(fn.rc.raw_host_pixel_buf()[:3], single_projs[1:4])
-            if mode == "tiles":
+            if mode.startswith("tiles"):
                 plan = sh.balance(pop, rounds=2, reps=2)     # clock feedback: one rank keeps all tiles, values unchanged
                 assert plan[0] == 0 and plan[-1] > 0 and len(plan) == 2
                 np.testing.assert_array_equal(sh(pop), ref)
@@ -58,7 +58,7 @@ def test_sharded_device_objective_two_gpus_nccl():
                        capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert '"bitwise_equal_to_single_gpu": true' in r.stdout and 'equal_to_single_gpu": false' not in r.stdout
-    assert '"mode": "tiles"' in r.stdout and '"projections_bitwise_equal_to_single_gpu": true' in r.stdout
+    assert '"mode": "tiles"' in r.stdout and '"mode": "tiles-nccl"' in r.stdout and '"projections_bitwise_equal_to_single_gpu": true' in r.stdout
 
 
 def test_pax_stacks_are_built_on_demand(ctx, xo):

@@ -144,6 +144,10 @@ SIGNATURES = {
     "xrc_rc_tile_samples": [_VP, _U32, C.POINTER(_U64), C.POINTER(_U64)],
     "xrc_obj_fn_tiles_enqueue_drr": [_VP, _U32, _U32, _U32, _FP],
     "xrc_obj_fn_units_enqueue_metrics": [_VP, C.POINTER(_VP), _U32, _U32, _U32, _U32],
+    "xrc_rc_peer_barrier": [_VP],
+    "xrc_obj_fn_tiles_enqueue_gather": [_VP, C.POINTER(_VP), _U32, _U32],
+    "xrc_obj_fn_tiles_finish": [_VP, _U32, _U32, _FP, _FP],
+    "xrc_obj_fn_tiles": [_VP, _U32, C.POINTER(_VP), _U32, _U32, _FP, _FP, _FP],
     "xrc_obj_fn_multi_share": [_U32, _U32, _U32, _U32, _U32, _U32P, _U32P],
     "xrc_exp_se3": [_FP, _FP],
     "xrc_se3_mag_penalty": [C.POINTER(XrcSe3Penalty), _U32, _FP, _FP],

@@ -123,6 +123,10 @@ struct xrc_rc
   // per-tile cost multipliers learnt from the ranks' measured kernel times (xrc_rc_plan_tiles_timed); empty = all 1
   std::vector<double> tile_mult;
   std::vector<double> tile_work;   // the work estimate of the last plan (samples + set-up), before the multipliers
+  // exchange block at the tail of the own projection buffer (xchg.cu): flags + the gathered similarity values
+  size_t xchg_off = 0;             // byte offset of the block in d_buf_own (the same on every rank: same sizes)
+  uint32_t xchg_epoch = 0;         // the last epoch this rank signalled; all ranks count the same calls
+  float* h_gather = nullptr;       // host-mapped: max_projs gathered values, then one status word
   float* h_poses = nullptr;   // pinned staging: max_projs x 12 floats
   uint32_t* h_cam_idx = nullptr;
   float* d_poses = nullptr;
@@ -366,6 +370,8 @@ int xrc_rc_destroy(xrc_rc* rc)
   dfree(rc->d_cam_idx);
   dfree(rc->d_zero_idx);
   dfree(rc->d_bg);
+  if (rc->h_gather)
+    cudaFreeHost(rc->h_gather);
   if (rc->h_poses)
     cudaFreeHost(rc->h_poses);
   if (rc->h_cam_idx)
@@ -548,8 +554,16 @@ int xrc_rc_allocate(xrc_rc* rc, uint32_t max_projs)
   const size_t npix = (size_t)rc->rows * rc->cols;
   if (!rc->other)
   {
-    XRC_CUDA(cudaMalloc(&rc->d_buf_own, npix * max_projs * sizeof(float)));
-    XRC_CUDA(cudaMemsetAsync(rc->d_buf_own, 0, npix * max_projs * sizeof(float), rc->ctx->stream));
+    rc->xchg_off = (npix * max_projs * sizeof(float) + 255u) & ~(size_t)255u;
+    const size_t bytes = rc->xchg_off + kXchgBlockBytes + sizeof(float) * max_projs;
+    XRC_CUDA(cudaMalloc(&rc->d_buf_own, bytes));
+    XRC_CUDA(cudaMemsetAsync(rc->d_buf_own, 0, bytes, rc->ctx->stream));
+    rc->xchg_epoch = 0;
+    if (rc->h_gather)
+      cudaFreeHost(rc->h_gather);
+    rc->h_gather = nullptr;
+    XRC_CUDA(cudaHostAlloc(&rc->h_gather, sizeof(float) * ((size_t)max_projs + 1), cudaHostAllocMapped));
+    memset(rc->h_gather, 0, sizeof(float) * ((size_t)max_projs + 1));
   }
   else
   {
@@ -936,6 +950,7 @@ int xrc_rc_peer_export(xrc_rc* rc, uint8_t handle[XRC_IPC_HANDLE_BYTES])
   XRC_CHECK_ARG(rc->allocated && rc->d_buf_own, "xrc_rc_peer_export: allocate first (a ray caster that borrows its buffer cannot export it)");
   static_assert(sizeof(cudaIpcMemHandle_t) == XRC_IPC_HANDLE_BYTES, "IPC handle size");
   XRC_TRY(use_device(rc->ctx));
+  XRC_CUDA(cudaStreamSynchronize(rc->ctx->stream));   // the buffer (and its exchange block) is zeroed before anyone can map it
   cudaIpcMemHandle_t h;
   XRC_CUDA(cudaIpcGetMemHandle(&h, rc->d_buf_own));
   memcpy(handle, &h, sizeof(h));
@@ -2477,6 +2492,96 @@ int xrc_obj_fn_units_enqueue_metrics(xrc_rc* rc, xrc_sm* const* sms, uint32_t n_
     XRC_TRY(xrc_sm_compute(sms[v]));
   }
   return XRC_OK;
+}
+
+// ---- the rest of the tile-sharded step without NCCL: barrier and all-gather by xchg_kernel over the peer mappings ----
+static void rc_fill_xchg(xrc_rc* rc, XchgArgs* x)
+{
+  memset(x, 0, sizeof(*x));
+  x->n_ranks = rc->peer_n;
+  x->rank = rc->peer_rank;
+  x->epoch = ++rc->xchg_epoch;
+  for (uint32_t r = 0; r < rc->peer_n; ++r)
+    x->blk[r] = reinterpret_cast<unsigned char*>(rc->peer_bufs[r]) + rc->xchg_off;
+  x->host_status = reinterpret_cast<uint32_t*>(rc->h_gather + rc->max_projs);
+  x->timeout_ns = 30ull * 1000ull * 1000ull * 1000ull;
+}
+
+// the unit range rank r owns: the camera-major list cut into n contiguous balanced chunks (the first N % n take one more),
+// the same cut as the ray-casting kernel's owner() and regi.unit_chunks
+static void rank_units(uint32_t n_total, uint32_t n_ranks, uint32_t r, uint32_t& u0, uint32_t& u1)
+{
+  const uint32_t base = n_total / n_ranks, extra = n_total % n_ranks;
+  u0 = r * base + std::min(r, extra);
+  u1 = u0 + base + (r < extra ? 1u : 0u);
+}
+
+int xrc_rc_peer_barrier(xrc_rc* rc)
+{
+  XRC_CHECK_ARG(rc, "null ray caster");
+  XRC_CHECK_ARG(rc->allocated && rc->peer_n >= 1 && rc->d_buf_own, "xrc_rc_peer_barrier: allocate and attach first");
+  XRC_TRY(use_device(rc->ctx));
+  XchgArgs x;
+  rc_fill_xchg(rc, &x);
+  return launch_xchg(x, rc->ctx->stream);
+}
+
+int xrc_obj_fn_tiles_enqueue_gather(xrc_rc* rc, xrc_sm* const* sms, uint32_t n_views, uint32_t n_poses)
+{
+  XRC_CHECK_ARG(rc && sms && n_views > 0, "xrc_obj_fn_tiles_enqueue_gather: bad argument");
+  XRC_CHECK_ARG(rc->allocated && rc->peer_n >= 1 && rc->d_buf_own, "xrc_obj_fn_tiles_enqueue_gather: allocate and attach first");
+  XRC_CHECK_ARG((uint64_t)n_views * n_poses <= rc->max_projs, "xrc_obj_fn_tiles_enqueue_gather: population exceeds the allocated projections");
+  XRC_CHECK_ARG(n_views <= kXchgMaxSeg, "xrc_obj_fn_tiles_enqueue_gather: too many views");
+  uint32_t u0, u1;
+  rank_units(n_views * n_poses, rc->peer_n, rc->peer_rank, u0, u1);
+  XRC_TRY(xrc_obj_fn_units_enqueue_metrics(rc, sms, n_views, n_poses, u0, u1 - u0));
+  XRC_TRY(use_device(rc->ctx));
+  XchgArgs x;
+  rc_fill_xchg(rc, &x);
+  for (uint32_t v = 0; v < n_views; ++v)
+  {
+    uint32_t p0, p1;
+    unit_range(u0, u1, v, n_poses, p0, p1);
+    if (p1 == p0)
+      continue;
+    x.seg_src[x.n_seg] = sms[v]->d_sims;
+    x.seg_first[x.n_seg] = v * n_poses + p0;
+    x.seg_count[x.n_seg] = p1 - p0;
+    ++x.n_seg;
+  }
+  x.n_units_total = n_views * n_poses;
+  x.host_out = rc->h_gather;
+  return launch_xchg(x, rc->ctx->stream);
+}
+
+int xrc_obj_fn_tiles_finish(xrc_rc* rc, uint32_t n_views, uint32_t n_poses, float* sims_out, float* per_view_out)
+{
+  XRC_CHECK_ARG(rc && sims_out && n_views > 0, "xrc_obj_fn_tiles_finish: bad argument");
+  XRC_CHECK_ARG(rc->allocated && rc->h_gather && (uint64_t)n_views * n_poses <= rc->max_projs, "xrc_obj_fn_tiles_finish: bad state");
+  XRC_TRY(use_device(rc->ctx));
+  XRC_CUDA(cudaStreamSynchronize(rc->ctx->stream));
+  uint32_t* status = reinterpret_cast<uint32_t*>(rc->h_gather + rc->max_projs);
+  if (*status)
+  {
+    *status = 0;
+    XRC_FAIL(XRC_ERR_CUDA, "tile-sharded objective: a peer rank did not reach the barrier within 30 s");
+  }
+  if (per_view_out)
+    memcpy(per_view_out, rc->h_gather, sizeof(float) * (size_t)n_views * n_poses);
+  combine_mean(rc->h_gather, n_views, n_poses, sims_out);
+  return XRC_OK;
+}
+
+int xrc_obj_fn_tiles(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t n_views, uint32_t n_poses,
+                     const float* cam_to_phys, float* sims_out, float* per_view_out)
+{
+  XRC_CHECK_ARG(sims_out, "xrc_obj_fn_tiles: null output");
+  if (!n_poses)
+    return XRC_OK;
+  XRC_TRY(xrc_obj_fn_tiles_enqueue_drr(rc, vol_idx, n_views, n_poses, cam_to_phys));
+  XRC_TRY(xrc_rc_peer_barrier(rc));   // every rank's tiles have landed in their owners' buffers
+  XRC_TRY(xrc_obj_fn_tiles_enqueue_gather(rc, sms, n_views, n_poses));
+  return xrc_obj_fn_tiles_finish(rc, n_views, n_poses, sims_out, per_view_out);
 }
 
 int xrc_obj_fn_units_enqueue(xrc_rc* rc, uint32_t vol_idx, xrc_sm* const* sms, uint32_t n_views, uint32_t n_poses,

@@ -141,4 +141,23 @@ int launch_ray_info(const DrrArgs& a, cudaStream_t st);
 
 void affine_inverse_f32(const float a[12], float out[12]);
 
+// Cross-GPU exchange block at the tail of every rank's projection buffer (xchg.cu)
+constexpr uint32_t kXchgThreads = 256;
+constexpr uint32_t kXchgMaxSeg = 16;                    // views a rank's unit range can touch
+constexpr uint32_t kXchgSimsOff = 1024;                 // flags (8 x 32 B) first, then the gathered values
+constexpr uint32_t kXchgBlockBytes = kXchgSimsOff;      // + 4 * max_projs
+struct XchgArgs
+{
+  uint32_t n_ranks, rank, epoch;
+  unsigned char* blk[kMaxPeers];         // every rank's exchange block (own included; peers' over CUDA IPC)
+  uint32_t n_seg;                        // this rank's values: seg_count[s] floats at seg_src[s] are units seg_first[s]...
+  const float* seg_src[kXchgMaxSeg];
+  uint32_t seg_first[kXchgMaxSeg], seg_count[kXchgMaxSeg];
+  uint32_t n_units_total;
+  float* host_out;                       // after the barrier: all n_units_total gathered values, host-mapped (or null)
+  uint32_t* host_status;                 // set to 1 when a peer did not arrive within timeout_ns
+  unsigned long long timeout_ns;
+};
+int launch_xchg(const XchgArgs& a, cudaStream_t st);
+
 }  // namespace xrc

@@ -163,6 +163,27 @@ class Intensity2D3DObjFn:
                                                               int(n_units)))
         self._cur_pop = -1
 
+    def eval_tiles(self, poses: np.ndarray) -> np.ndarray:
+        """The whole tile-sharded evaluation in one library call (xrc_obj_fn_tiles; every rank calls it with the same
+        poses after peer_attach): ray cast this rank's tiles into their owners' buffers, barrier, metrics of the units
+        this rank owns, all-gather -- barrier and gather by the library's own kernel over the peer mappings, no NCCL."""
+        p12 = to12(poses) if np.asarray(poses).ndim == 3 else np.ascontiguousarray(poses, dtype=f32).reshape(-1, 12)
+        n = p12.shape[0]
+        if n == 0:
+            return np.zeros(0, dtype=f32)
+        self.rc._flush_params()
+        for sm in self.sims:
+            sm._pre_compute()
+        out = np.empty(n, dtype=f32)
+        per_view = np.empty((self.n_views, n), dtype=f32)
+        FP = C.POINTER(C.c_float)
+        _lib.check(self._lib.xrc_obj_fn_tiles(self.rc.handle, 0, self._sm_arr, self.n_views, n, p12.ctypes.data_as(FP),
+                                              out.ctypes.data_as(FP), per_view.ctypes.data_as(FP)))
+        self.rc._poses_dirty = False
+        self._cur_pop = -1   # the library re-sized / re-bound the objects
+        self.per_view = per_view
+        return out
+
     def close(self) -> None:
         """Destroy the metrics and the ray caster (before their Context is closed)."""
         for sm in self.sims:
@@ -441,14 +462,17 @@ class ShardedDeviceObjFn:
         """mode "poses": every rank ray casts and scores its chunk of the (view, pose) list.  mode "tiles": every rank
         ray casts its detector tiles of ALL projections and stores them into their owners' buffers over NVLink (CUDA IPC
         peer mappings, include/xreg_cuda.h "Tile-sharded objective"), then scores the chunk it owns; `fn` must be
-        allocated for the whole population on every rank.  Same values either way, bit for bit."""
+        allocated for the whole population on every rank; the barrier and the gather of the scalars are the library's
+        own kernel over the same mappings (xrc_obj_fn_tiles).  mode "tiles-nccl": the same with an NCCL all-reduce as
+        the barrier and an NCCL all-gather (comparison).  Same values in every mode, bit for bit."""
         import torch
 
         self.fn, self.rank, self.world_size, self.group = fn, int(rank), int(world_size), group
-        self.mode = mode
-        if mode not in ("poses", "tiles"):
-            raise _lib.XregError("ShardedDeviceObjFn: mode must be 'poses' or 'tiles'")
-        if mode == "tiles":
+        self.mode = "tiles" if mode == "tiles-nccl" else mode
+        self.nccl_exchange = mode != "tiles"      # "tiles": barrier + gather by the library's kernel over the peer mappings
+        if mode not in ("poses", "tiles", "tiles-nccl"):
+            raise _lib.XregError("ShardedDeviceObjFn: mode must be 'poses', 'tiles' or 'tiles-nccl'")
+        if self.mode == "tiles":
             import torch.distributed as dist
 
             handles = [None] * self.world_size
@@ -553,6 +577,10 @@ class ShardedDeviceObjFn:
         n = np.asarray(poses).shape[0]
         if n == 0:
             return np.zeros(0, dtype=f32)
+        if self.mode == "tiles" and not self.nccl_exchange:
+            out = self.fn.eval_tiles(poses)        # one library call, no NCCL on the path
+            self.per_view = self.fn.per_view
+            return out
         bounds, width = self.enqueue(poses)
         return self.collect(bounds, width, n)
 
