@@ -608,8 +608,9 @@ __device__ __forceinline__ void stats_from_sums(double S, double SS, double cnt,
 // d-1 rows above its first window (loads only), so bands give the grid enough CTAs
 // without repeating the horizontal work.  Loads of the next row are issued before the
 // scan of the current one.
-template <int MODE, bool FIXED, int C>
-__global__ void __launch_bounds__(kPatchThreads) patch_kernel(const PatchArgs a)
+// ST1: patch stride 1 (the reference apps' setting) known at compile time -- no integer divisions in the output section
+template <int MODE, bool FIXED, int C, bool ST1>
+__global__ void __launch_bounds__(kPatchThreads, (MODE == 0) ? 4 : 1) patch_kernel(const PatchArgs a)
 {
   constexpr int NQ = PatchQ<MODE, FIXED>::N;
   constexpr int NT = kPatchThreads;
@@ -628,8 +629,8 @@ __global__ void __launch_bounds__(kPatchThreads) patch_kernel(const PatchArgs a)
   const int c0 = strip * W_out;            // first input column == first stride-1 centre column of the strip
   const int ncc_all = cols - 2 * r;        // stride-1 centre columns
   const int nrr_all = rows - 2 * r;        // stride-1 centre rows
-  const int st = (int)a.stride;
-  const int ncc_s = (ncc_all - 1) / st + 1;
+  const int st = ST1 ? 1 : (int)a.stride;
+  const int ncc_s = ST1 ? ncc_all : ((ncc_all - 1) / st + 1);
   const size_t npix = (size_t)rows * cols;
   const int i_begin = band * (int)a.band_rows, i_end = min(i_begin + (int)a.band_rows, nrr_all);
 
@@ -739,9 +740,16 @@ __global__ void __launch_bounds__(kPatchThreads) patch_kernel(const PatchArgs a)
 #pragma unroll
     for (int k = 0; k < NQ; ++k)
     {
+      // totals of the warps to my left, added in warp order (a fixed-length chain under warp-uniform predicates:
+      // the counted loop cost ~60 instructions per quantity)
       double off = 0.0;
-      for (int w = 0; w < warp; ++w)
-        off += wtot[buf][k][w];
+#pragma unroll
+      for (int w = 0; w < NW - 1; ++w)
+      {
+        const double wt = wtot[buf][k][w];
+        if (w < warp)
+          off += wt;
+      }
       ex[k] = off + (incl[k] - L[C - 1][k]);
       Pex[buf][k][0][t] = ex[k];
 #pragma unroll
@@ -886,18 +894,28 @@ __global__ void __launch_bounds__(kPatchThreads) patch_kernel(const PatchArgs a)
   }
 }
 
-template <bool FIXED, int C>
-static int launch_patch_c(const PatchArgs& a, cudaStream_t st)
+template <bool FIXED, int C, bool ST1>
+static int launch_patch_cs(const PatchArgs& a, cudaStream_t st)
 {
   const uint32_t n_imgs = FIXED ? 1 : a.n_imgs;
   const dim3 grid(a.n_parts, n_imgs, a.n_dirs);
   switch (a.mask_mode)
   {
-    case 0: patch_kernel<0, FIXED, C><<<grid, kPatchThreads, 0, st>>>(a); break;
-    case 1: patch_kernel<1, FIXED, C><<<grid, kPatchThreads, 0, st>>>(a); break;
-    case 2: patch_kernel<2, FIXED, C><<<grid, kPatchThreads, 0, st>>>(a); break;
+    case 0: patch_kernel<0, FIXED, C, ST1><<<grid, kPatchThreads, 0, st>>>(a); break;
+    case 1: patch_kernel<1, FIXED, C, ST1><<<grid, kPatchThreads, 0, st>>>(a); break;
+    case 2: patch_kernel<2, FIXED, C, ST1><<<grid, kPatchThreads, 0, st>>>(a); break;
     default: XRC_FAIL(XRC_ERR_INVALID, "bad patch mask mode");
   }
+  return XRC_OK;
+}
+
+template <bool FIXED, int C>
+static int launch_patch_c(const PatchArgs& a, cudaStream_t st)
+{
+  if (a.stride == 1)
+    XRC_TRY((launch_patch_cs<FIXED, C, true>(a, st)));
+  else
+    XRC_TRY((launch_patch_cs<FIXED, C, false>(a, st)));
   count_launch();
   XRC_CUDA(cudaGetLastError());
   return XRC_OK;

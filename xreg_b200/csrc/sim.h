@@ -1,6 +1,8 @@
 // Launchers of the similarity-metric kernels (internal; see sim.cu).
 #pragma once
 
+#include <cstdlib>
+
 #include "common.h"
 
 namespace xrc
@@ -151,6 +153,16 @@ struct PatchPlan
 };
 // n_units = images x directions in flight: small batches get short bands (more CTAs; each band re-reads the
 // d - 1 rows above it, loads only) so that the serial row loop is not the latency of a population-1 evaluation
+// resident CTAs per SM the plan counts on (3: every variant reaches it; XRC_PATCH_SLOTS overrides, measurement only)
+inline uint32_t patch_ctas_per_sm()
+{
+  static const uint32_t k = [] {
+    const char* e = getenv("XRC_PATCH_SLOTS");
+    const int v = e ? atoi(e) : 0;
+    return (uint32_t)((v >= 1 && v <= 8) ? v : 3);
+  }();
+  return k;
+}
 inline PatchPlan patch_plan(uint32_t rows, uint32_t cols, uint32_t radius, uint32_t n_units)
 {
   PatchPlan p;
@@ -161,7 +173,7 @@ inline PatchPlan patch_plan(uint32_t rows, uint32_t cols, uint32_t radius, uint3
   // Every band costs its rows plus the 2 r rows above them (loads only: counted half), and the grid runs in waves
   // of 148 SMs x 3 resident CTAs.  Pick the number of bands that minimises waves x rows per band; bands shorter
   // than kPatchBandRowsMin are not worth their pre-roll.
-  const uint64_t slots = 148u * 3u;
+  const uint64_t slots = 148u * patch_ctas_per_sm();
   uint64_t best_cost = ~0ull;
   uint32_t best_bands = 1;
   const uint32_t max_bands = (nrr + kPatchBandRowsMin - 1) / kPatchBandRowsMin;
