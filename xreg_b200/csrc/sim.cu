@@ -1560,8 +1560,10 @@ int launch_seqsum(const SeqSumArgs& a, cudaStream_t st)
   {
     patch_seqsum_serial_kernel<<<a.n_seq, 1, 0, st>>>(a);
   }
-  else if (a.serial == 2 || smem2 > kS2MaxSmem || n_rounds > (size_t)kS2MaxRounds)
+  else if (a.serial == 2 || smem2 > kS2MaxSmem || n_rounds > (size_t)kS2MaxRounds || (a.serial == 0 && a.n_seq > 74u))
   {
+    // many sequences fill the GPU by themselves: the chain's 256-thread CTAs (several per SM) then beat the two-phase
+    // form's 1024-thread CTAs (measured at C2's length: 100 sequences 85 vs 94 us, 200 sequences 104 vs 178 us)
     patch_seqsum_kernel<<<a.n_seq, kSeqWarps * 32, 0, st>>>(a);   // the round-to-round chain (any length)
   }
   else
