@@ -49,9 +49,29 @@ def main():
             for k in range(reps):
                 fn(pops[(k % 50):(k % 50) + pop_n] if pop_n == 1 else pops)
             dt = (time.perf_counter() - t0) / reps
+            # the same evaluation straight through the C ABI (xrc_obj_fn with prebuilt arguments): what a C++ caller
+            # pays, without the Python mirror's array conversions and bookkeeping
+            import ctypes as C
+
+            from xreg_b200 import _lib
+            from xreg_b200.geometry import to12
+
+            lib = _lib.load()
+            FP = C.POINTER(C.c_float)
+            p12 = [np.ascontiguousarray(to12(pops[(k % 50):(k % 50) + pop_n] if pop_n == 1 else pops)) for k in range(50 if pop_n == 1 else 1)]
+            out = np.empty(pop_n, dtype=np.float32)
+            outp = out.ctypes.data_as(FP)
+            args = [x.ctypes.data_as(FP) for x in p12]
+            fn(pops[:pop_n])   # sizes / binds the objects for this population
+            for k in range(5):
+                _lib.check(lib.xrc_obj_fn(fn.rc.handle, 0, fn._sm_arr, 1, pop_n, args[k % len(args)], outp, None))
+            t0 = time.perf_counter()
+            for k in range(reps):
+                lib.xrc_obj_fn(fn.rc.handle, 0, fn._sm_arr, 1, pop_n, args[k % len(args)], outp, None)
+            dt_abi = (time.perf_counter() - t0) / reps
             print(json.dumps({"det": det, "metric": metric, "pop": pop_n, "layout": os.environ.get("LAT_LAYOUT", "default"),
                               "deep": os.environ.get("XRC_PAX_DEEP", ""), "ms_per_call": dt * 1e3,
-                              "poses_per_s": pop_n / dt}), flush=True)
+                              "ms_per_call_c_abi": dt_abi * 1e3, "poses_per_s": pop_n / dt}), flush=True)
         del fn
 
 
