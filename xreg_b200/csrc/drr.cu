@@ -604,20 +604,7 @@ __device__ __forceinline__ void pax_advance(float& pa, float& pb, float& pc, flo
 // (97 % busy in ncu, profiles/); the extra loads in flight per thread keep that pipe
 // fed through L1 misses.  Positions and the sum advance in sample order, exactly like
 // the sequential reference loop (xregRayCastLineIntCPU.cpp:270-277).
-// L2 prefetch hint for the few-pose regime (PF > 0): the record a ray will read PF samples from now.  With one pose no
-// other CTA has pulled a beam's records into L2, every L1 miss goes to HBM, and the misses an SM can keep in flight
-// bound the kernel; a prefetch does not hold an L1 miss slot.  The position is a hint (one multiply-add, clamped into
-// the stack), not the reference's chain of additions: it changes no value.
-__device__ __forceinline__ void pax_prefetch(const PaxStack& st, float pa, float pb, float pc, float sa, float sb, float sc,
-                                             float dist)
-{
-  uint32_t rec;
-  float w0, w1, w2;
-  pax_cell<false, true>(st, fmaf(dist, sa, pa), fmaf(dist, sb, pb), fmaf(dist, sc, pc), rec, w0, w1, w2);
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(st.base + rec + st.Sc));
-}
-
-template <int KERNEL_ID, bool PACK, bool CLAMP, int BATCH, int PF = 0>
+template <int KERNEL_ID, bool PACK, bool CLAMP, int BATCH>
 __device__ __forceinline__ float pax_march(const PaxStack& st, float pa, float pb, float pc, float sa, float sb,
                                            float sc, uint32_t n)
 {
@@ -648,8 +635,6 @@ __device__ __forceinline__ float pax_march(const PaxStack& st, float pa, float p
         pax_cell<PACK, CLAMP>(st, pa, pb, pc, rec, nwa[j], nwb[j], nwc[j]);
         n0[j] = pax_load(st.base, rec);
         n1[j] = pax_load(st.base, rec + st.Sc);
-        if (PF > 0)
-          pax_prefetch(st, pa, pb, pc, sa, sb, sc, (float)PF);
         pax_advance<PACK>(pa, pb, pc, sa, sb, sc);
       }
 #pragma unroll
@@ -988,7 +973,7 @@ __device__ __forceinline__ void pax_count(const DrrArgs& a, PaxCta& sh, unsigned
 }
 
 // ---- one thread per pixel, CTA = 16 x 16 pixels of one projection ---------------------------------------
-template <int KERNEL_ID, bool PACK, int BATCH, int MINB, int PF = 0>
+template <int KERNEL_ID, bool PACK, int BATCH, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) drr_pax_kernel(const DrrArgs a)
 {
   __shared__ PaxCta sh;
@@ -1023,7 +1008,7 @@ __global__ void __launch_bounds__(kThreads, MINB) drr_pax_kernel(const DrrArgs a
     for (uint32_t i = 0; i < L.s0; ++i)
       pax_advance<PACK>(L.a0, L.b0, L.c0, L.sa, L.sb, L.sc);
     if (L.safe)
-      sum = pax_march<KERNEL_ID, PACK, false, BATCH, PF>(L.st, L.a0, L.b0, L.c0, L.sa, L.sb, L.sc, L.s1 - L.s0);
+      sum = pax_march<KERNEL_ID, PACK, false, BATCH>(L.st, L.a0, L.b0, L.c0, L.sa, L.sb, L.sc, L.s1 - L.s0);
     else
       sum = pax_march<KERNEL_ID, PACK, true, 1>(L.st, L.a0, L.b0, L.c0, L.sa, L.sb, L.sc, L.s1 - L.s0);
   }
@@ -1034,19 +1019,6 @@ __global__ void __launch_bounds__(kThreads, MINB) drr_pax_kernel(const DrrArgs a
     pax_store<KERNEL_ID>(a, proj, ci, row, col, sum);
   if (a.sample_counter)
     pax_count(a, sh, L.hit ? (unsigned long long)(L.s1 - L.s0) : 0ull, tile);  // samples actually fetched
-}
-
-// few-pose prefetch distance in samples (0 = off) and the largest projection count it is used for; XRC_PAX_PF /
-// XRC_PAX_PF_PROJS override (measurement)
-static int pf_dist()
-{
-  static const int v = getenv("XRC_PAX_PF") ? atoi(getenv("XRC_PAX_PF")) : 0;
-  return v;
-}
-static uint32_t pf_max_projs()
-{
-  static const uint32_t v = getenv("XRC_PAX_PF_PROJS") ? (uint32_t)atoi(getenv("XRC_PAX_PF_PROJS")) : 4u;
-  return v;
 }
 
 template <int KERNEL_ID>
@@ -1078,16 +1050,6 @@ static int launch_pax_k(const DrrArgs& a, cudaStream_t st)
       drr_pax_kernel<KERNEL_ID, false, 4, 2><<<nblocks, kThreads, 0, st>>>(a);
     else if (nblocks <= 148u * 4u)
       drr_pax_kernel<KERNEL_ID, false, 2, 4><<<nblocks, kThreads, 0, st>>>(a);
-    else if (pf_dist() > 0 && a.n_projs <= pf_max_projs())
-    {
-      // a few poses on a large detector: nothing shares the beams in L2, prefetch ahead (see pax_prefetch)
-      if (pf_dist() <= 16)
-        drr_pax_kernel<KERNEL_ID, false, 1, 5, 16><<<nblocks, kThreads, 0, st>>>(a);
-      else if (pf_dist() <= 32)
-        drr_pax_kernel<KERNEL_ID, false, 1, 5, 32><<<nblocks, kThreads, 0, st>>>(a);
-      else
-        drr_pax_kernel<KERNEL_ID, false, 1, 5, 64><<<nblocks, kThreads, 0, st>>>(a);
-    }
     else
       drr_pax_kernel<KERNEL_ID, false, 1, 5><<<nblocks, kThreads, 0, st>>>(a);
   }
