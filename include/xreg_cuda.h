@@ -61,9 +61,11 @@ typedef struct xrc_cam
   int32_t frame_type;     /* CameraCoordFrame: 0 DET_POS_Z, 1 DET_NEG_Z, 2 ORIGIN_ON_DETECTOR */
 } xrc_cam;
 
-/* RayCaster::InterpMethod (xregRayCastInterface.h:61-67).  Only LINEAR is
- * implemented; the others return XRC_ERR_UNSUPPORTED like the OpenCL backend
- * (xregRayCastBaseOCL.cpp:338-341). */
+/* RayCaster::InterpMethod (xregRayCastInterface.h:61-67).  LINEAR (the default and the optimised path) and NN
+ * (nearest neighbour: the voxel at floor(x + 0.5) per axis, ITK's ConvertContinuousIndexToNearestIndex; sums
+ * bit-identical to the CPU class, xregRayCastLineIntCPU.cpp:128-130; plain xrc_rc_compute only, not tile-sharded) are
+ * implemented; SINC and BSPLINE return XRC_ERR_UNSUPPORTED (the reference's OpenCL backend supports linear only,
+ * xregRayCastBaseOCL.cpp:338-341). */
 enum { XRC_INTERP_LINEAR = 0, XRC_INTERP_NN = 1, XRC_INTERP_SINC = 2, XRC_INTERP_BSPLINE = 3 };
 /* RayCaster::ProjPixelStoreMethod (xregRayCastInterface.h:71-75) */
 enum { XRC_STORE_REPLACE = 0, XRC_STORE_ACCUM = 1 };

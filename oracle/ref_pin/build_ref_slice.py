@@ -194,10 +194,24 @@ extern "C" void xref_pre_compute(float* buf, uint32_t n_projs, uint32_t rows, ui
 // RayCasterLineIntCPU::compute's call of ComputeLineInts (xregRayCastLineIntCPU.cpp, after pre_compute): the caller
 // passes the already inverted physical-point -> index transform (Eigen's .inverse() is third-party arithmetic) and an
 // initialised projection buffer (REPLACE: zeros / background, ACCUM: the previous content).
+extern "C" int xref_compute_line_ints_interp(const float* vol, const uint64_t dims[3], const float phys_to_idx[12],
+                                             const xref_cam* cams, uint32_t n_cams, const float* poses,
+                                             const uint32_t* cam_idx, uint32_t n_projs, float step_size, int kernel_id,
+                                             int interp, float* proj_buf);
 extern "C" int xref_compute_line_ints(const float* vol, const uint64_t dims[3], const float phys_to_idx[12],
                                       const xref_cam* cams, uint32_t n_cams, const float* poses,
                                       const uint32_t* cam_idx, uint32_t n_projs, float step_size, int kernel_id,
                                       float* proj_buf)
+{
+  return xref_compute_line_ints_interp(vol, dims, phys_to_idx, cams, n_cams, poses, cam_idx, n_projs, step_size, kernel_id,
+                                       (int)xreg::RayCaster::kRAY_CAST_INTERP_LINEAR, proj_buf);
+}
+
+// interp: RayCaster::InterpMethod (0 linear, 1 nearest neighbour; the stand-ins for sinc / B-spline throw)
+extern "C" int xref_compute_line_ints_interp(const float* vol, const uint64_t dims[3], const float phys_to_idx[12],
+                                             const xref_cam* cams, uint32_t n_cams, const float* poses,
+                                             const uint32_t* cam_idx, uint32_t n_projs, float step_size, int kernel_id,
+                                             int interp, float* proj_buf)
 {
   if (!n_cams || !n_projs)
     return 0;
@@ -222,7 +236,7 @@ extern "C" int xref_compute_line_ints(const float* vol, const uint64_t dims[3], 
     bb_max(i) = static_cast<float>(dims[i] - 1);
   }
   const LineIntParams params = {0, &img, bb_min, bb_max, affine_from12(phys_to_idx), n_projs, cam_list, xforms, assoc,
-                                step_size, xreg::RayCaster::kRAY_CAST_INTERP_LINEAR};
+                                step_size, static_cast<xreg::RayCaster::InterpMethod>(interp)};
   const xreg::RangeType full_range(0, (std::size_t)n_projs * cam_list[0].num_det_rows * cam_list[0].num_det_cols);
   if (kernel_id == 0)
     ComputeLineInts<AccumLineIntKernel>(params, proj_buf, full_range);

@@ -320,10 +320,36 @@ struct UnsupportedInterp : Base
   static Pointer New() { throw std::runtime_error("interpolation method outside the pinned path"); }
   double EvaluateAtContinuousIndex(const typename Base::ContinuousIndexType&) const override { return 0.0; }
 };
+/* itk::NearestNeighborInterpolateImageFunction<Image<float,3>,float>::EvaluateAtContinuousIndex, ITK 5.1.1: the pixel at
+ * ConvertContinuousIndexToNearestIndex(x) = Math::RoundHalfIntegerUp per axis, stated as floor(x + 0.5) evaluated
+ * exactly; the index is clamped (ITK would read out of bounds, the ray caster's nudge keeps it inside) */
 template <class TImage, class TCoord>
-struct NearestNeighborInterpolateImageFunction
-  : UnsupportedInterp<NearestNeighborInterpolateImageFunction<TImage, TCoord>, InterpolateImageFunction<TImage, TCoord>>
+struct NearestNeighborInterpolateImageFunction : InterpolateImageFunction<TImage, TCoord>
 {
+  using Base = InterpolateImageFunction<TImage, TCoord>;
+  using Pointer = FnPtr<NearestNeighborInterpolateImageFunction>;
+  static Pointer New()
+  {
+    Pointer p;
+    p.p = std::make_shared<NearestNeighborInterpolateImageFunction>();
+    return p;
+  }
+  double EvaluateAtContinuousIndex(const typename Base::ContinuousIndexType& x) const override
+  {
+    const TImage& im = *this->img;
+    long b[3];
+    for (int k = 0; k < 3; ++k)
+    {
+      const long end = (long)im.size[k] - 1;
+      long bk = (long)std::floor(static_cast<double>(x[k]) + 0.5);
+      if (bk < 0)
+        bk = 0;
+      if (bk > end)
+        bk = end;
+      b[k] = bk;
+    }
+    return im.GetPixelAt(b[0], b[1], b[2]);
+  }
 };
 template <class TImage, class TCoord = double>
 struct BSplineInterpolateImageFunction

@@ -26,6 +26,7 @@ def lib():
         _lib = C.CDLL(build_ref_slice.LIB)
         _lib.xref_ray_rect_intersect.restype = C.c_int
         _lib.xref_compute_line_ints.restype = C.c_int
+        _lib.xref_compute_line_ints_interp.restype = C.c_int
     return _lib
 
 
@@ -43,7 +44,7 @@ def ind_pt_to_phys_det_pt(cam: XoCam, col: float, row: float) -> np.ndarray:
     return out
 
 
-def compute_line_ints(vol, phys_to_idx, cams, poses, cam_idx=None, step_size=1.0, kernel_id=0, buf=None):
+def compute_line_ints(vol, phys_to_idx, cams, poses, cam_idx=None, step_size=1.0, kernel_id=0, buf=None, interp=0):
     """ComputeLineInts<Accum|Max kernel> over the whole projection range (serial).  vol (nz, ny, nx) f32; phys_to_idx the
     already inverted 3x4 (row-major); cams list of XoCam; poses (n, 12).  buf: initialised projection buffer or None
     (zeros: the REPLACE store without background)."""
@@ -58,9 +59,9 @@ def compute_line_ints(vol, phys_to_idx, cams, poses, cam_idx=None, step_size=1.0
     if buf is None:
         buf = np.zeros((n, rows, cols), np.float32)
     a = _f32(phys_to_idx).reshape(12)
-    rc = lib().xref_compute_line_ints(_fp(vol), dims, _fp(a), cam_arr, C.c_uint32(len(cams)), _fp(poses),
-                                      ci.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_uint32(n), C.c_float(step_size),
-                                      C.c_int(kernel_id), _fp(buf))
+    rc = lib().xref_compute_line_ints_interp(_fp(vol), dims, _fp(a), cam_arr, C.c_uint32(len(cams)), _fp(poses),
+                                             ci.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_uint32(n), C.c_float(step_size),
+                                             C.c_int(kernel_id), C.c_int(interp), _fp(buf))
     if rc != 0:
         raise ValueError("xref_compute_line_ints failed")
     return buf

@@ -288,6 +288,27 @@ double xo_interp_linear(const float* vol, const uint64_t dims[3], const float x[
   return vxx0 + (vxx1 - vxx0) * d2;
 }
 
+/* ITK 5.1.1 NearestNeighborInterpolateImageFunction<Image<float,3>,float>::EvaluateAtContinuousIndex: the pixel at
+ * ConvertContinuousIndexToNearestIndex(x), i.e. Index::CopyWithRound -> Math::RoundHalfIntegerUp per axis (the other
+ * interpolator RayCasterLineIntCPU can select, xregRayCastLineIntCPU.cpp:128-130).  ITK is un-vendored: restated as
+ * floor(x + 0.5) evaluated exactly (in double; ITK's SSE form 2x + 0.5 -> cvt -> >> 1 agrees except within one f32 ulp
+ * of a half-integer at coordinates >= 2^22).  ITK would read out of bounds for an index outside the image; the ray
+ * caster's 1e-3 nudge keeps x inside [0, n - 1] up to f32 drift, and the index is clamped here. */
+double xo_interp_nn(const float* vol, const uint64_t dims[3], const float x[3])
+{
+  int64_t b[3];
+  for (int k = 0; k < 3; ++k)
+  {
+    int64_t bk = (int64_t)floor((double)x[k] + 0.5);
+    if (bk < 0)
+      bk = 0;
+    if (bk > (int64_t)dims[k] - 1)
+      bk = (int64_t)dims[k] - 1;
+    b[k] = bk;
+  }
+  return (double)vol[(size_t)b[0] + (size_t)b[1] * dims[0] + (size_t)b[2] * dims[0] * dims[1]];
+}
+
 /* lib/spatial/xregSpatialPrimitives.cpp:175-222, limit_to_segment = true */
 static int ray_rect_intersect(const float mn[3], const float mx[3], const float p[3],
                               const float d[3], float* t_start, float* t_stop)
@@ -341,8 +362,21 @@ int xo_drr(const float* vol, const uint64_t dims[3], const float idx_to_phys[12]
            float* buf, uint8_t* hit_mask, uint32_t* num_steps_out,
            uint64_t* total_samples, int n_threads)
 {
+  return xo_drr_interp(vol, dims, idx_to_phys, cams, n_cams, poses, cam_idx, n_projs, step_size, kernel_id, XO_INTERP_LINEAR,
+                       buf, hit_mask, num_steps_out, total_samples, n_threads);
+}
+
+int xo_drr_interp(const float* vol, const uint64_t dims[3], const float idx_to_phys[12],
+                  const xo_cam* cams, uint32_t n_cams,
+                  const float* poses, const uint32_t* cam_idx, uint32_t n_projs,
+                  float step_size, int kernel_id, int interp,
+                  float* buf, uint8_t* hit_mask, uint32_t* num_steps_out,
+                  uint64_t* total_samples, int n_threads)
+{
   if (!n_cams || !n_projs)
     return 0;
+  if (interp != XO_INTERP_LINEAR && interp != XO_INTERP_NN)
+    return -3; /* sinc / B-spline: not restated */
   const uint32_t rows = cams[0].rows, cols = cams[0].cols;
   for (uint32_t c = 1; c < n_cams; ++c)
   {
@@ -434,7 +468,7 @@ int xo_drr(const float* vol, const uint64_t dims[3], const float idx_to_phys[12]
 
       for (uint64_t s = 0; s <= num_steps; ++s) /* :270-277 */
       {
-        const float v = (float)xo_interp_linear(vol, dims, x);
+        const float v = (interp == XO_INTERP_NN) ? (float)xo_interp_nn(vol, dims, x) : (float)xo_interp_linear(vol, dims, x);
         if (kernel_id == XO_KERNEL_MAX)
           sum = (sum < v) ? v : sum;
         else

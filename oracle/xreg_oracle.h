@@ -119,8 +119,21 @@ int xo_drr(const float* vol, const uint64_t dims[3], const float idx_to_phys[12]
            float* buf, uint8_t* hit_mask, uint32_t* num_steps_out,
            uint64_t* total_samples, int n_threads);
 
+/* the same with the interpolator selectable (RayCaster::InterpMethod, xregRayCastInterface.h: kRAY_CAST_INTERP_LINEAR = 0,
+ * kRAY_CAST_INTERP_NN = 1; sinc / B-spline are not restated: -3) */
+#define XO_INTERP_LINEAR 0
+#define XO_INTERP_NN 1
+int xo_drr_interp(const float* vol, const uint64_t dims[3], const float idx_to_phys[12],
+                  const xo_cam* cams, uint32_t n_cams,
+                  const float* poses, const uint32_t* cam_idx, uint32_t n_projs,
+                  float step_size, int kernel_id, int interp,
+                  float* buf, uint8_t* hit_mask, uint32_t* num_steps_out,
+                  uint64_t* total_samples, int n_threads);
+
 /* ITK LinearInterpolateImageFunction::EvaluateOptimized(Dispatch<3>) restated. */
 double xo_interp_linear(const float* vol, const uint64_t dims[3], const float x[3]);
+/* ITK NearestNeighborInterpolateImageFunction::EvaluateAtContinuousIndex restated. */
+double xo_interp_nn(const float* vol, const uint64_t dims[3], const float x[3]);
 
 /* ---- similarity metrics ---- */
 

@@ -63,6 +63,8 @@ def lib():
         _lib.xo_interp_linear.restype = C.c_double
         _lib.xo_num_patches.restype = C.c_uint64
         _lib.xo_drr.restype = C.c_int
+        _lib.xo_drr_interp.restype = C.c_int
+        _lib.xo_interp_nn.restype = C.c_double
         _lib.xo_num_threads.restype = C.c_int
     return _lib
 
@@ -157,7 +159,7 @@ def pre_compute(buf, cam_idx, bg_projs=None, store_method=0, default_bg=0.0):
 
 
 def drr(vol, idx_to_phys, cams, poses, cam_idx=None, step_size=1.0, kernel_id=0, buf=None,
-        want_info=False, n_threads=0):
+        want_info=False, n_threads=0, interp=0):
     """vol: (nz, ny, nx) float32.  cams: list of XoCam.  poses: (n, 12).
 
     Returns buf (n, rows, cols) [and (hit_mask, num_samples, S) if want_info].
@@ -180,9 +182,9 @@ def drr(vol, idx_to_phys, cams, poses, cam_idx=None, step_size=1.0, kernel_id=0,
     mask = np.zeros((n, rows, cols), np.uint8) if want_info else None
     steps = np.zeros((n, rows, cols), np.uint32) if want_info else None
     S = C.c_uint64(0)
-    rc = lib().xo_drr(_fp(vol), dims, _fp(a), cam_arr, C.c_uint32(len(cams)), _fp(poses),
+    rc = lib().xo_drr_interp(_fp(vol), dims, _fp(a), cam_arr, C.c_uint32(len(cams)), _fp(poses),
                       cam_idx.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_uint32(n), C.c_float(step_size),
-                      C.c_int(kernel_id), _fp(buf),
+                      C.c_int(kernel_id), C.c_int(interp), _fp(buf),
                       _u8p(mask) if want_info else None,
                       steps.ctypes.data_as(C.POINTER(C.c_uint32)) if want_info else None,
                       C.byref(S), C.c_int(n_threads))
@@ -199,6 +201,14 @@ def interp_linear(vol, x):
     dims = (C.c_uint64 * 3)(nx, ny, nz)
     xx = _f32(x).reshape(3)
     return float(lib().xo_interp_linear(_fp(vol), dims, _fp(xx)))
+
+
+def interp_nn(vol, x):
+    vol = _f32(vol)
+    nz, ny, nx = vol.shape
+    dims = (C.c_uint64 * 3)(nx, ny, nz)
+    xx = _f32(x).reshape(3)
+    return float(lib().xo_interp_nn(_fp(vol), dims, _fp(xx)))
 
 
 def ncc(fixed, mov, mask=None, n_threads=0, inplace=False):

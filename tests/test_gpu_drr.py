@@ -51,6 +51,43 @@ def test_drr_parity_all_layouts(ctx, xo, small_scene, layout):
     np.testing.assert_array_equal(rc.proj(3), got[3])
 
 
+@pytest.mark.parametrize("layout", ["pax", "linear", "quad", "oct"])
+@pytest.mark.parametrize("kernel_id", [0, 1])
+def test_nearest_neighbour_interpolation_is_bit_exact(ctx, xo, small_scene, layout, kernel_id):
+    """kRAY_CAST_INTERP_NN (xregRayCastLineIntCPU.cpp:128-130): no arithmetic on the voxel values, so the sums (and the
+    max kernel's maxima) equal the oracle's bit for bit -- for every payload the voxel can be read from, several views
+    (the on-demand stack differs), REPLACE and ACCUM; switching back to linear gives the linear result again."""
+    vol, cam, nominal = small_scene
+    xc = [xo.cam_struct(cam)]
+    rc = _make_rc(ctx, vol, [cam], 4, layout)
+    rc.set_kernel_id(kernel_id)
+    for view in (0.0, 90.0, 40.0):
+        poses = synth.pose_population(vol, synth.nominal_pose(vol, src_to_iso=250.0, view_rot_deg=view), 4,
+                                      sigma=(10, 10, 10, 6, 6, 6))
+        ref, mask, steps, S = xo.drr(vol.data, vol.idx_to_phys(), xc, to12(poses), want_info=True, interp=1, kernel_id=kernel_id)
+        lin = xo.drr(vol.data, vol.idx_to_phys(), xc, to12(poses), kernel_id=kernel_id)
+        rc.set_xforms_cam_to_itk_phys(list(poses))
+        rc.use_nn_interp()
+        rc.compute()
+        got = rc.raw_host_pixel_buf().copy()
+        assert got.tobytes() == ref.tobytes() and got.tobytes() != lin.tobytes()
+        gmask, gsteps, gS = rc.ray_info()
+        np.testing.assert_array_equal(gmask, mask)
+        assert gS == S
+        rc.use_proj_store_accum_method()
+        rc.compute()
+        ref2 = xo.drr(vol.data, vol.idx_to_phys(), xc, to12(poses), interp=1, kernel_id=kernel_id, buf=ref.copy())
+        assert rc.raw_host_pixel_buf().tobytes() == ref2.tobytes()
+        rc.use_proj_store_replace_method()
+        rc.use_linear_interp()
+        rc.compute()
+        _check_drr(rc.raw_host_pixel_buf(), lin, mask)
+    rc.use_sinc_interp()
+    with pytest.raises(xreg_b200.UnsupportedOperationException):
+        rc.compute()
+    rc.close()
+
+
 def test_layouts_agree_bitwise(ctx, small_scene):
     vol, cam, nominal = small_scene
     poses = synth.pose_population(vol, nominal, 3)

@@ -60,14 +60,27 @@ def test_detector_points_are_the_reference_code(xo, frame):
     # a one-voxel-thick slab orthogonal to nothing in particular: the DRR comparison below is the bitwise statement
 
 
-def _both(xo, vol, cam, poses, step, kernel_id, cam_idx=None, buf=None):
+def _both(xo, vol, cam, poses, step, kernel_id, cam_idx=None, buf=None, interp=0):
     xcams = cam if isinstance(cam, list) else [xo.cam_struct(cam)]
     p12 = to12(poses)
     a = xo.drr(vol.data, vol.idx_to_phys(), xcams, p12, cam_idx=cam_idx, step_size=step, kernel_id=kernel_id,
-               buf=None if buf is None else buf.copy(), n_threads=1)
+               buf=None if buf is None else buf.copy(), n_threads=1, interp=interp)
     b = ref_slice.compute_line_ints(vol.data, xo.affine_inverse(vol.idx_to_phys()), xcams, p12, cam_idx=cam_idx,
-                                    step_size=step, kernel_id=kernel_id, buf=None if buf is None else buf.copy())
+                                    step_size=step, kernel_id=kernel_id, buf=None if buf is None else buf.copy(), interp=interp)
     return a, b
+
+
+@pytest.mark.parametrize("seed", range(0, 48, 3))
+def test_oracle_nearest_neighbour_drr_equals_the_reference_code(xo, seed):
+    """kRAY_CAST_INTERP_NN (xregRayCastLineIntCPU.cpp:128-130): the reference's ComputeLineInts with the
+    nearest-neighbour interpolator (ITK's rounding stated as floor(x + 0.5)) against xo_drr_interp, bit for bit; and
+    the two interpolators really differ."""
+    vol, cam, poses, step, kernel_id, kind = _scene(seed)
+    a, b = _both(xo, vol, cam, poses, step, kernel_id, interp=1)
+    assert a.tobytes() == b.tobytes()
+    lin, _ = _both(xo, vol, cam, poses, step, kernel_id, interp=0)
+    if vol.data.size > 8 and np.ptp(vol.data) > 0 and a.max() > 0:
+        assert a.tobytes() != lin.tobytes()
 
 
 @pytest.mark.parametrize("seed", range(48))

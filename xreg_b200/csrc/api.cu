@@ -734,8 +734,9 @@ int xrc_rc_set_params(xrc_rc* rc, float step_size, int interp, int kernel_id, in
   XRC_CHECK_ARG(rc, "null ray caster");
   XRC_CHECK_ARG(step_size > 0.0f, "xrc_rc_set_params: step size must be positive");
   XRC_CHECK_ARG(interp >= XRC_INTERP_LINEAR && interp <= XRC_INTERP_BSPLINE, "xrc_rc_set_params: bad interpolation id");
-  if (interp != XRC_INTERP_LINEAR)
-    XRC_FAIL(XRC_ERR_UNSUPPORTED, "only linear interpolation is supported on the GPU (as in xregRayCastBaseOCL.cpp:338-341)");
+  if (interp != XRC_INTERP_LINEAR && interp != XRC_INTERP_NN)
+    XRC_FAIL(XRC_ERR_UNSUPPORTED, "sinc / B-spline interpolation is not supported on the GPU (the reference's OpenCL ray caster "
+                                  "supports linear only, xregRayCastBaseOCL.cpp:338-341; here: linear and nearest neighbour)");
   XRC_CHECK_ARG(kernel_id == XRC_KERNEL_SUM || kernel_id == XRC_KERNEL_MAX, "xrc_rc_set_params: unsupported line integral kernel");
   XRC_CHECK_ARG(store_method == XRC_STORE_REPLACE || store_method == XRC_STORE_ACCUM, "xrc_rc_set_params: bad store method");
   rc->step_size = step_size;
@@ -929,6 +930,44 @@ static void rc_fill_args(xrc_rc* rc, uint32_t vol_idx, DrrArgs* a)
   }
 }
 
+// where voxel (ix, iy, iz) lives as a plain float in whatever payload the volume has (nearest-neighbour interpolation)
+static int rc_fill_nn(const DeviceVolume& v, DrrArgs* a)
+{
+  const uint32_t nx = (uint32_t)v.dims[0], ny = (uint32_t)v.dims[1];
+  a->nn_off = 0;
+  switch (v.layout)
+  {
+    case XRC_LAYOUT_LINEAR:   // padded (nx + 1) x (ny + 1) x (nz + 1)
+      a->nn_base = (const float*)v.data;
+      a->nn_s[0] = 1; a->nn_s[1] = nx + 1; a->nn_s[2] = (nx + 1) * (ny + 1);
+      return XRC_OK;
+    case XRC_LAYOUT_QUAD:     // float4 {v(x, y), ...} per voxel
+      a->nn_base = (const float*)v.data;
+      a->nn_s[0] = 4; a->nn_s[1] = 4 * nx; a->nn_s[2] = 4 * nx * ny;
+      return XRC_OK;
+    case XRC_LAYOUT_OCT:      // two float4 per voxel, v(x, y, z) first
+      a->nn_base = (const float*)v.data;
+      a->nn_s[0] = 8; a->nn_s[1] = 8 * nx; a->nn_s[2] = 8 * nx * ny;
+      return XRC_OK;
+    case XRC_LAYOUT_PAX:
+      for (int k = 0; k < 3; ++k)
+        if (v.pax[k])
+        {
+          // stack k: rec = (ic + 1) Sc + (ib + 1) Sb + (ia + 1), c = axis k, a = (k + 1) % 3, b = (k + 2) % 3; the record's
+          // first component is v(ia, ib, ic) itself (the difference form keeps it)
+          const int ka = (k + 1) % 3, kb = (k + 2) % 3;
+          XRC_CHECK_ARG((uint64_t)4 * v.pax_sc[k] * (v.dims[k] + 2) < (1ull << 32), "nearest-neighbour interpolation: volume too large");
+          a->nn_base = (const float*)v.pax[k];
+          a->nn_s[ka] = 4; a->nn_s[kb] = 4 * v.pax_sb[k]; a->nn_s[k] = 4 * v.pax_sc[k];
+          a->nn_off = 4 * (v.pax_sc[k] + v.pax_sb[k] + 1);
+          return XRC_OK;
+        }
+      XRC_FAIL(XRC_ERR_INVALID, "nearest-neighbour interpolation: no volume stack built");
+    default:
+      XRC_FAIL(XRC_ERR_UNSUPPORTED, "nearest-neighbour interpolation is not available for the texture layouts");
+  }
+}
+
 int xrc_rc_compute(xrc_rc* rc, uint32_t vol_idx)
 {
   XRC_CHECK_ARG(rc, "null ray caster");
@@ -940,6 +979,11 @@ int xrc_rc_compute(xrc_rc* rc, uint32_t vol_idx)
   XRC_TRY(rc_prepare_stacks(rc, vol_idx));
   DrrArgs a;
   rc_fill_args(rc, vol_idx, &a);
+  if (rc->interp == XRC_INTERP_NN)
+  {
+    XRC_TRY(rc_fill_nn(rc->vols[vol_idx], &a));
+    return launch_drr(a, kLayoutNN, rc->kernel_id, rc->ctx->stream);
+  }
   return launch_drr(a, rc->vols[vol_idx].layout, rc->kernel_id, rc->ctx->stream);
 }
 
@@ -1137,6 +1181,8 @@ int xrc_rc_compute_tiles(xrc_rc* rc, uint32_t vol_idx)
   XRC_CHECK_ARG(rc->allocated, "xrc_rc_compute_tiles: resources not allocated");
   XRC_CHECK_ARG(rc->peer_n >= 1, "xrc_rc_compute_tiles: attach the ranks' projection buffers first (xrc_rc_peer_attach)");
   XRC_CHECK_ARG(vol_idx < rc->vols.size(), "xrc_rc_compute_tiles: volume index out of range");
+  if (rc->interp != XRC_INTERP_LINEAR)
+    XRC_FAIL(XRC_ERR_UNSUPPORTED, "xrc_rc_compute_tiles: the tile-sharded path is linear interpolation only");
   XRC_TRY(use_device(rc->ctx));
   XRC_TRY(rc_prepare_stacks(rc, vol_idx));
   XRC_CHECK_ARG(rc->vols[vol_idx].layout == XRC_LAYOUT_PAX, "xrc_rc_compute_tiles: needs the default volume layout");

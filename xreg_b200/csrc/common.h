@@ -82,6 +82,7 @@ struct DeviceVolume
   float occ_lo[3] = {0, 0, 0}, occ_hi[3] = {0, 0, 0};  // box of sample positions that can touch a non-zero voxel
 };
 
+constexpr int kLayoutNN = 100;      // launch_drr: nearest-neighbour sampling of any payload (not an XRC_LAYOUT_* of the ABI)
 constexpr uint32_t kInlinePoses = 8;
 constexpr uint32_t kMaxPeers = 8;   // ranks of a tile-sharded job (one box)
 
@@ -125,6 +126,10 @@ struct DrrArgs
   // first peer_extra chunks take one more).  peer_n == 0: single device, `out`.
   uint32_t peer_n, peer_base, peer_extra;
   float* peer_out[kMaxPeers];
+  // nearest-neighbour interpolation (kLayoutNN): voxel (ix, iy, iz) is the float at nn_base[nn_off + ix * nn_s[0] +
+  // iy * nn_s[1] + iz * nn_s[2]] -- the padded f32 copy, or the first component of a record of whatever stack exists
+  const float* nn_base;
+  uint32_t nn_s[3], nn_off;
   // small populations (latency regime): poses travel in the kernel parameters instead of an H2D copy
   int use_inline;
   float inl_poses[kInlinePoses * 12];

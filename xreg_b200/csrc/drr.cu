@@ -362,6 +362,29 @@ struct Sampler<XRC_LAYOUT_TEX_QUAD>
   }
 };
 
+// Nearest-neighbour interpolation (RayCaster::kRAY_CAST_INTERP_NN, xregRayCastLineIntCPU.cpp:128-130): the voxel at
+// ITK's ConvertContinuousIndexToNearestIndex = floor(x + 0.5) per axis (evaluated exactly, in double), clamped to the
+// volume.  No arithmetic on the values: sums are bit-identical to the oracle's.  Reads the padded f32 copy or the first
+// component of a record (every record layout keeps v(ix, iy, iz) there unchanged), whichever payload the volume has.
+template <>
+struct Sampler<kLayoutNN>
+{
+  const float* __restrict__ v;
+  size_t s0, s1, s2, off;
+  int hx, hy, hz;
+  __device__ Sampler(const DrrArgs& a)
+      : v(a.nn_base), s0(a.nn_s[0]), s1(a.nn_s[1]), s2(a.nn_s[2]), off(a.nn_off), hx(a.nx - 1), hy(a.ny - 1), hz(a.nz - 1)
+  {
+  }
+  __device__ __forceinline__ float operator()(float x, float y, float z) const
+  {
+    const int ix = min(max((int)floor((double)x + 0.5), 0), hx);
+    const int iy = min(max((int)floor((double)y + 0.5), 0), hy);
+    const int iz = min(max((int)floor((double)z + 0.5), 0), hz);
+    return __ldg(v + (off + (size_t)ix * s0 + (size_t)iy * s1 + (size_t)iz * s2));
+  }
+};
+
 // ----------------------------------------------------------------------------
 // main kernel
 // ----------------------------------------------------------------------------
@@ -1164,6 +1187,7 @@ int launch_drr(const DrrArgs& a_in, int layout, int kernel_id, cudaStream_t st)
     case XRC_LAYOUT_TEX: return launch_layout<XRC_LAYOUT_TEX>(a, kernel_id, st);
     case XRC_LAYOUT_TEX_QUAD: return launch_layout<XRC_LAYOUT_TEX_QUAD>(a, kernel_id, st);
     case XRC_LAYOUT_PAX: return launch_pax(a, kernel_id, st);
+    case kLayoutNN: return launch_layout<kLayoutNN>(a, kernel_id, st);
     default: XRC_FAIL(XRC_ERR_INVALID, "unknown volume layout");
   }
 }
