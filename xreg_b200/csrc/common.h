@@ -80,6 +80,7 @@ struct DeviceVolume
   uint32_t* occ = nullptr;
   uint32_t occ_wx = 0, occ_ny = 0, occ_nz = 0;   // words per block row, block rows, block slices
   float occ_lo[3] = {0, 0, 0}, occ_hi[3] = {0, 0, 0};  // box of sample positions that can touch a non-zero voxel
+  float occ_fill = 1.0f;            // fraction of the map's bits that are set inside that box (sparse volumes: interior gaps)
 };
 
 constexpr int kLayoutNN = 100;      // launch_drr: nearest-neighbour sampling of any payload (not an XRC_LAYOUT_* of the ABI)
@@ -117,6 +118,7 @@ struct DrrArgs
   uint32_t occ_wx, occ_ny;
   float occ_lo[3], occ_hi[3];
   int count_only;             // instrumentation: count the samples the kernel would fetch, do not march / store
+  int gaps;                   // sparse volume: also skip runs of empty samples INSIDE a ray's trimmed range (drr.cu, GAPS)
   // tile subset of this launch: tiles tile_first + i * tile_stride, i < tile_count (tile_stride == 0 on entry: all tiles)
   uint32_t tile_first, tile_stride, tile_count;
   unsigned long long* tile_counter;   // optional, with sample_counter: fetched samples per detector tile (tile planning)

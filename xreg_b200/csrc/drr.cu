@@ -628,10 +628,12 @@ __device__ __forceinline__ void pax_advance(float& pa, float& pb, float& pc, flo
 // fed through L1 misses.  Positions and the sum advance in sample order, exactly like
 // the sequential reference loop (xregRayCastLineIntCPU.cpp:270-277).
 template <int KERNEL_ID, bool PACK, bool CLAMP, int BATCH>
-__device__ __forceinline__ float pax_march(const PaxStack& st, float pa, float pb, float pc, float sa, float sb,
-                                           float sc, uint32_t n)
+__device__ __forceinline__ float pax_march(const PaxStack& st, float& pa, float& pb, float& pc, float sa, float sb,
+                                           float sc, uint32_t n, float sum0)
 {
-  float sum = (KERNEL_ID == XRC_KERNEL_MAX) ? -3.402823466e+38f : 0.0f;
+  // sum0: the running value (0 / -FLT_MAX at the start of a ray; the sum so far when a ray is marched in segments);
+  // pa, pb, pc are left at the position after the n samples
+  float sum = sum0;
   const uint32_t ng = n / BATCH;
   if (ng > 0)
   {
@@ -888,6 +890,7 @@ struct PaxLane
   bool hit, safe;
   uint32_t n;       // num_steps + 1
   uint32_t s0, s1;  // samples to fetch: [s0, s1) (empty-space trimming; the whole warp shares s0)
+  float rx, ry, rz, rsx, rsy, rsz;   // first sample and step in volume axes (interior-gap tests)
 };
 
 template <int KERNEL_ID>
@@ -902,6 +905,7 @@ __device__ __forceinline__ PaxLane pax_lane_setup(const DrrArgs& a, const PaxCta
     ray = setup_ray(sh.cam, sh.pc, a.step_size, a.nx, a.ny, a.nz, row, col);
   L.hit = ray.hit;
   L.n = ray.nsamples;
+  L.rx = ray.x, L.ry = ray.y, L.rz = ray.z, L.rsx = ray.sx, L.rsy = ray.sy, L.rsz = ray.sz;
   L.safe = false;
   L.st.base = nullptr;
   L.st.Sb = L.st.Sc = L.st.K = 0u;
@@ -996,7 +1000,16 @@ __device__ __forceinline__ void pax_count(const DrrArgs& a, PaxCta& sh, unsigned
 }
 
 // ---- one thread per pixel, CTA = 16 x 16 pixels of one projection ---------------------------------------
-template <int KERNEL_ID, bool PACK, int BATCH, int MINB>
+// Interior gaps (GAPS, sum kernel, sparse volumes -- a bone-masked CT, what the reference's registration apps ray cast):
+// the range [s0, s1) left by the trimming still crosses the air between two bones.  The warp therefore marches in
+// segments of kGapSeg samples and asks the empty-space map before each one: when every lane's bit is clear, the warp
+// skips what the bits vouch for (minimum over the lanes) -- the skipped samples keep their three position FADDs, lose
+// their fetch, and a sample whose 8 corners are zero adds +0 to the sequential sum, so no bit of the result changes
+// (tests/test_gpu_skip_empty.py).  Control flow is warp-uniform: the lanes stay on the same stack planes.
+constexpr uint32_t kGapSeg = 16;   // samples marched between two looks at the map
+constexpr uint32_t kGapMin = 4;    // shortest run worth skipping
+
+template <int KERNEL_ID, bool PACK, int BATCH, int MINB, bool GAPS = false>
 __global__ void __launch_bounds__(kThreads, MINB) drr_pax_kernel(const DrrArgs a)
 {
   __shared__ PaxCta sh;
@@ -1026,14 +1039,75 @@ __global__ void __launch_bounds__(kThreads, MINB) drr_pax_kernel(const DrrArgs a
   PaxLane L = pax_lane_setup<KERNEL_ID>(a, sh, row, col, in_img);
 
   float sum = (KERNEL_ID == XRC_KERNEL_MAX) ? -3.402823466e+38f : 0.0f;
-  if (L.hit && L.s1 > L.s0 && !a.count_only)
+  unsigned long long fetched = 0ull;
+  if (GAPS && KERNEL_ID == XRC_KERNEL_SUM)
   {
-    for (uint32_t i = 0; i < L.s0; ++i)
-      pax_advance<PACK>(L.a0, L.b0, L.c0, L.sa, L.sb, L.sc);
-    if (L.safe)
-      sum = pax_march<KERNEL_ID, PACK, false, BATCH>(L.st, L.a0, L.b0, L.c0, L.sa, L.sb, L.sc, L.s1 - L.s0);
-    else
-      sum = pax_march<KERNEL_ID, PACK, true, 1>(L.st, L.a0, L.b0, L.c0, L.sa, L.sb, L.sc, L.s1 - L.s0);
+    const bool work = L.hit && L.s1 > L.s0;
+    const uint32_t lo = __reduce_min_sync(0xffffffffu, work ? L.s0 : 0xffffffffu);
+    const uint32_t hi = __reduce_max_sync(0xffffffffu, work ? L.s1 : 0u);
+    if (work && !a.count_only)
+      for (uint32_t i = 0; i < L.s0; ++i)
+        pax_advance<PACK>(L.a0, L.b0, L.c0, L.sa, L.sb, L.sc);
+    const float ivx = __frcp_rn(fmaxf(fabsf(L.rsx), 1.0e-6f)), ivy = __frcp_rn(fmaxf(fabsf(L.rsy), 1.0e-6f)),
+                ivz = __frcp_rn(fmaxf(fabsf(L.rsz), 1.0e-6f));
+    const bool can_skip = a.occ && (fmaxf(fabsf(L.rsx), fmaxf(fabsf(L.rsy), fabsf(L.rsz))) <= kOccReach);
+    uint32_t sidx = lo;   // warp-uniform
+    while (sidx < hi)
+    {
+      const bool mine = work && sidx < L.s1;    // (work lanes share s0 == lo)
+      uint32_t skip = 0xffffu;
+      if (mine)
+      {
+        skip = 0u;
+        if (L.safe && can_skip)
+        {
+          const float f = (float)sidx;
+          uint32_t m;
+          if (occ_clear(a, fmaf(f, L.rsx, L.rx), fmaf(f, L.rsy, L.ry), fmaf(f, L.rsz, L.rz), L.rsx, L.rsy, L.rsz, ivx, ivy, ivz, m))
+            skip = m;
+        }
+      }
+      const uint32_t wskip = __reduce_min_sync(0xffffffffu, skip);
+      if (wskip >= kGapMin)
+      {
+        const uint32_t k = min(wskip, hi - sidx);
+        if (mine && !a.count_only)
+        {
+          const uint32_t kk = min(k, L.s1 - sidx);
+          for (uint32_t i = 0; i < kk; ++i)
+            pax_advance<PACK>(L.a0, L.b0, L.c0, L.sa, L.sb, L.sc);
+        }
+        sidx += k;
+        continue;
+      }
+      const uint32_t g = min(kGapSeg, hi - sidx);
+      if (mine)
+      {
+        const uint32_t n = min(g, L.s1 - sidx);
+        fetched += n;
+        if (!a.count_only)
+        {
+          if (L.safe)
+            sum = pax_march<KERNEL_ID, PACK, false, BATCH>(L.st, L.a0, L.b0, L.c0, L.sa, L.sb, L.sc, n, sum);
+          else
+            sum = pax_march<KERNEL_ID, PACK, true, 1>(L.st, L.a0, L.b0, L.c0, L.sa, L.sb, L.sc, n, sum);
+        }
+      }
+      sidx += g;
+    }
+  }
+  else
+  {
+    if (L.hit && L.s1 > L.s0 && !a.count_only)
+    {
+      for (uint32_t i = 0; i < L.s0; ++i)
+        pax_advance<PACK>(L.a0, L.b0, L.c0, L.sa, L.sb, L.sc);
+      if (L.safe)
+        sum = pax_march<KERNEL_ID, PACK, false, BATCH>(L.st, L.a0, L.b0, L.c0, L.sa, L.sb, L.sc, L.s1 - L.s0, sum);
+      else
+        sum = pax_march<KERNEL_ID, PACK, true, 1>(L.st, L.a0, L.b0, L.c0, L.sa, L.sb, L.sc, L.s1 - L.s0, sum);
+    }
+    fetched = L.hit ? (unsigned long long)(L.s1 - L.s0) : 0ull;
   }
   if (L.hit)
     sum = fmul(sum, a.step_size);  // xregRayCastLineIntCPU.cpp:279
@@ -1041,7 +1115,7 @@ __global__ void __launch_bounds__(kThreads, MINB) drr_pax_kernel(const DrrArgs a
   if (in_img && !a.count_only)
     pax_store<KERNEL_ID>(a, proj, ci, row, col, sum);
   if (a.sample_counter)
-    pax_count(a, sh, L.hit ? (unsigned long long)(L.s1 - L.s0) : 0ull, tile);  // samples actually fetched
+    pax_count(a, sh, fetched, tile);  // samples actually fetched
 }
 
 template <int KERNEL_ID>
@@ -1067,14 +1141,24 @@ static int launch_pax_k(const DrrArgs& a, cudaStream_t st)
     // at most one CTA per SM (a 192 x 192 detector, one pose): every ray is a chain of L2 / HBM-latency load groups
     // and registers are free: 8 sample groups in flight (population 1 at 192^2: 102 -> 98 us per evaluation)
     static const int deep = getenv("XRC_PAX_DEEP") ? atoi(getenv("XRC_PAX_DEEP")) : 8;   // 4: the round-1 pipeline (measurement)
+    const bool gaps = a.occ && a.gaps;   // sparse volume: interior gaps too (see GAPS above)
+#define XRC_PAX_GO(B, M)                                                             \
+  do                                                                                 \
+  {                                                                                  \
+    if (gaps)                                                                        \
+      drr_pax_kernel<KERNEL_ID, false, B, M, true><<<nblocks, kThreads, 0, st>>>(a); \
+    else                                                                             \
+      drr_pax_kernel<KERNEL_ID, false, B, M><<<nblocks, kThreads, 0, st>>>(a);       \
+  } while (0)
     if (deep == 8 && nblocks <= 160u)
-      drr_pax_kernel<KERNEL_ID, false, 8, 1><<<nblocks, kThreads, 0, st>>>(a);
+      XRC_PAX_GO(8, 1);
     else if (nblocks <= 148u * 2u)
-      drr_pax_kernel<KERNEL_ID, false, 4, 2><<<nblocks, kThreads, 0, st>>>(a);
+      XRC_PAX_GO(4, 2);
     else if (nblocks <= 148u * 4u)
-      drr_pax_kernel<KERNEL_ID, false, 2, 4><<<nblocks, kThreads, 0, st>>>(a);
+      XRC_PAX_GO(2, 4);
     else
-      drr_pax_kernel<KERNEL_ID, false, 1, 5><<<nblocks, kThreads, 0, st>>>(a);
+      XRC_PAX_GO(1, 5);
+#undef XRC_PAX_GO
   }
   else if (!packed)
     drr_pax_kernel<KERNEL_ID, false, 1, 5><<<nblocks, kThreads, 0, st>>>(a);
@@ -1426,6 +1510,8 @@ int build_occupancy(const float* d_linear, DeviceVolume* v, cudaStream_t st)
   occ_bbox_kernel<<<148 * 2, 256, 0, st>>>(raw, d_bb, gx, gy, gz);
   count_launch(3);
   cudaMemcpyAsync(h_bb, d_bb, sizeof(h_bb), cudaMemcpyDeviceToHost, st);
+  std::vector<uint8_t> h_raw((size_t)gx * gy * gz);
+  cudaMemcpyAsync(h_raw.data(), raw, h_raw.size(), cudaMemcpyDeviceToHost, st);
   const cudaError_t e = cudaStreamSynchronize(st);
   cudaFree(raw);
   cudaFree(d_bb);
@@ -1449,6 +1535,18 @@ int build_occupancy(const float* d_linear, DeviceVolume* v, cudaStream_t st)
   v->occ_wx = (uint32_t)wx;
   v->occ_ny = (uint32_t)gy;
   v->occ_nz = (uint32_t)gz;
+  // how full is the box of the non-zero voxels (blocks with a non-zero voxel / blocks of the box)?  A body in air: 0.55
+  // and more; a bone-masked CT: a small fraction -- then the rays' trimmed ranges still cross air between the bones and
+  // the kernel looks for interior gaps too
+  v->occ_fill = 1.0f;
+  if (h_bb[3] >= 0)
+  {
+    unsigned long long set = 0;
+    for (uint8_t b : h_raw)
+      set += b ? 1u : 0u;
+    const double box = (double)(h_bb[3] - h_bb[0] + 1) * (double)(h_bb[4] - h_bb[1] + 1) * (double)(h_bb[5] - h_bb[2] + 1);
+    v->occ_fill = (float)std::min(1.0, (double)set / std::max(box, 1.0));
+  }
   return XRC_OK;
 }
 

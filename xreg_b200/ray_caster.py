@@ -449,9 +449,10 @@ class RayCasterLineIntCUDA:
         check(self._lib.xrc_rc_volume_bytes(self.handle, C.byref(n)))
         return int(n.value)
 
-    def set_skip_empty(self, enable: bool) -> None:
-        """Empty-space trimming of the sum kernel (exact, default on); off only for measurement."""
-        check(self._lib.xrc_rc_set_skip_empty(self.handle, 1 if enable else 0))
+    def set_skip_empty(self, enable) -> None:
+        """Empty-space trimming of the sum kernel (exact, default on); off only for measurement.  2 / 3: on, with the
+        interior-gap skipping of sparse volumes forced off / on (default: automatic)."""
+        check(self._lib.xrc_rc_set_skip_empty(self.handle, int(enable) if not isinstance(enable, bool) else (1 if enable else 0)))
 
     def fetched_samples(self, vol_idx: int = 0) -> int:
         """Trilinear samples compute() actually fetches for the current poses (<= S of ray_info)."""
