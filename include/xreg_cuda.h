@@ -117,10 +117,11 @@ int xrc_rc_volume_layout(const xrc_rc* rc, uint32_t vol_idx, int* layout);
 /* Empty-space trimming, default on.  Samples whose 8 corner voxels are all zero add +0 to the
  * sequential f32 sum of xregRayCastLineIntCPU.cpp:270-279, so the sum kernel does not fetch the leading
  * and trailing samples of a ray that a per-volume block map proves to be zero (air around the body,
- * everything outside the bone mask).  For a sparse volume (a bone-masked CT: the block map is less than half full
- * inside the bounding box of the non-zero voxels) the kernel also skips runs of empty samples INSIDE a ray's range --
- * the air between two bones -- warp by warp.  Results are bit-identical with trimming on or off; 0 turns it off
- * (measurement), 1 = on (interior gaps automatic), 2 = on without, 3 = on with interior gaps.  The max kernel never trims. */
+ * everything outside the bone mask).  Results are bit-identical with trimming on or off; 0 turns it off
+ * (measurement), 1 (or 2) = on.  3 = on, and the kernel also skips runs of empty samples INSIDE a ray's range -- the air
+ * between two separated structures along the view direction -- warp by warp, marching in segments of 16 samples between
+ * looks at the map (same bits again; pays when such gaps are long: marching in segments costs ~5 % where there are none,
+ * so it is a request, not the default).  The max kernel never trims. */
 int xrc_rc_set_skip_empty(xrc_rc* rc, int enable);
 
 /* RayCaster::set_volumes (xregRayCastInterface.h:90) + vols_changed (:425).

@@ -81,7 +81,7 @@ def main():
         fn = regi.Intensity2D3DObjFn(ctx, vol, [cam], [fixed], metric="patch-grad-ncc", max_pop=100,
                                      patch_radius=synth.patch_radius_for(480))
         pops = [synth.pose_population(vol, nominal, 100, seed=30 + k) for k in range(3)]
-        for skip, label in ((1, "on (automatic: ends + interior gaps)"), (2, "on, ends only"), (3, "on, ends + interior gaps"), (0, "off")):
+        for skip, label in ((1, "on"), (3, "on + interior gaps (on request)"), (0, "off")):
             fn.rc.set_skip_empty(skip)
             dt = timed(fn, pops, 10)
             report("C2 geometry, bone-masked volume (non-bone voxels zero), patch gradient-NCC, trimming %s" % label, fn, pops, dt)

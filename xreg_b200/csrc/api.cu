@@ -146,7 +146,7 @@ struct xrc_rc
   float* d_bg = nullptr;
   int order = 0;
   bool skip_empty = true;  // empty-space trimming (exact; xrc_rc_set_skip_empty)
-  int gap_mode = -1;       // interior gaps: -1 automatic (sparse maps), 0 never, 1 always (xrc_rc_set_skip_empty: 2 / 3)
+  int gap_mode = 0;        // interior gaps: 0 no, 1 yes (xrc_rc_set_skip_empty(rc, 3))
   // latency regime (xrc_obj_fn with <= kInlinePoses projections): the poses in h_poses / h_cam_idx travel in the
   // kernel parameters; d_poses is refreshed lazily if another entry point needs it
   bool inline_poses = false;
@@ -922,8 +922,10 @@ static void rc_fill_args(xrc_rc* rc, uint32_t vol_idx, DrrArgs* a)
     memcpy(a->inl_cam, rc->h_cam_idx, sizeof(uint32_t) * rc->num_projs);
   }
   a->occ = rc->skip_empty ? v.occ : nullptr;
-  // interior gaps: worth their map look-ups when the non-zero blocks are sparse inside their own bounding box
-  a->gaps = (rc->skip_empty && v.occ && ((rc->gap_mode == 1) || (rc->gap_mode < 0 && v.occ_fill < 0.4f))) ? 1 : 0;
+  // interior gaps: on request only (xrc_rc_set_skip_empty(rc, 3)).  v.occ_fill tells how sparse the volume is, but sparse is
+  // not enough: the C2 phantom reduced to its 12 bones (fill 0.04) has few gaps ALONG its rays -- 7 % fewer samples
+  // fetched, 5 % slower for the segment-wise marching -- while two organs far apart along the view direction gain
+  a->gaps = (rc->skip_empty && v.occ && rc->gap_mode == 1) ? 1 : 0;
   a->occ_wx = v.occ_wx;
   a->occ_ny = v.occ_ny;
   for (int k = 0; k < 3; ++k)
@@ -1346,9 +1348,9 @@ int xrc_rc_ray_info(xrc_rc* rc, uint32_t vol_idx, uint8_t* host_mask, uint32_t* 
 int xrc_rc_set_skip_empty(xrc_rc* rc, int enable)
 {
   XRC_CHECK_ARG(rc, "null ray caster");
-  XRC_CHECK_ARG(enable >= 0 && enable <= 3, "xrc_rc_set_skip_empty: 0 off, 1 on (interior gaps automatic), 2 on without / 3 on with interior gaps");
+  XRC_CHECK_ARG(enable >= 0 && enable <= 3, "xrc_rc_set_skip_empty: 0 off, 1 (or 2) on, 3 on with interior gaps");
   rc->skip_empty = enable != 0;
-  rc->gap_mode = (enable == 2) ? 0 : ((enable == 3) ? 1 : -1);
+  rc->gap_mode = (enable == 3) ? 1 : 0;
   return XRC_OK;
 }
 

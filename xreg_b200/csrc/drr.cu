@@ -1000,7 +1000,8 @@ __device__ __forceinline__ void pax_count(const DrrArgs& a, PaxCta& sh, unsigned
 }
 
 // ---- one thread per pixel, CTA = 16 x 16 pixels of one projection ---------------------------------------
-// Interior gaps (GAPS, sum kernel, sparse volumes -- a bone-masked CT, what the reference's registration apps ray cast):
+// Interior gaps (GAPS, sum kernel, on request: xrc_rc_set_skip_empty(rc, 3); for volumes whose non-zero structures lie far
+// apart along the view direction):
 // the range [s0, s1) left by the trimming still crosses the air between two bones.  The warp therefore marches in
 // segments of kGapSeg samples and asks the empty-space map before each one: when every lane's bit is clear, the warp
 // skips what the bits vouch for (minimum over the lanes) -- the skipped samples keep their three position FADDs, lose
@@ -1141,7 +1142,7 @@ static int launch_pax_k(const DrrArgs& a, cudaStream_t st)
     // at most one CTA per SM (a 192 x 192 detector, one pose): every ray is a chain of L2 / HBM-latency load groups
     // and registers are free: 8 sample groups in flight (population 1 at 192^2: 102 -> 98 us per evaluation)
     static const int deep = getenv("XRC_PAX_DEEP") ? atoi(getenv("XRC_PAX_DEEP")) : 8;   // 4: the round-1 pipeline (measurement)
-    const bool gaps = a.occ && a.gaps;   // sparse volume: interior gaps too (see GAPS above)
+    const bool gaps = a.occ && a.gaps;   // on request: interior gaps too (see GAPS above)
 #define XRC_PAX_GO(B, M)                                                             \
   do                                                                                 \
   {                                                                                  \

@@ -450,8 +450,8 @@ class RayCasterLineIntCUDA:
         return int(n.value)
 
     def set_skip_empty(self, enable) -> None:
-        """Empty-space trimming of the sum kernel (exact, default on); off only for measurement.  2 / 3: on, with the
-        interior-gap skipping of sparse volumes forced off / on (default: automatic)."""
+        """Empty-space trimming of the sum kernel (exact, default on); off only for measurement.  3: on, plus skipping of
+        empty runs INSIDE a ray's range (structures far apart along the view direction; same bits)."""
         check(self._lib.xrc_rc_set_skip_empty(self.handle, int(enable) if not isinstance(enable, bool) else (1 if enable else 0)))
 
     def fetched_samples(self, vol_idx: int = 0) -> int:
