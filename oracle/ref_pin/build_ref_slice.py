@@ -64,6 +64,14 @@ def slices():
     body = ln[s:e + 1]
     assert any("void ComputeLineInts(" in x for x in body) and any("struct LineIntParams" in x for x in body)
     out.append(("lib/ray_cast/xregRayCastLineIntCPU.cpp", s, e, body))
+    # the un-named namespace of the CPU depth ray caster: RayCastDepthFn
+    ln = _lines("lib/ray_cast/xregRayCastDepthCPU.cpp")
+    k = next(i for i, x in enumerate(ln) if x.startswith("struct RayCastDepthFn"))
+    s = max(i for i in range(k) if ln[i].strip().startswith("namespace"))
+    e = next(i for i in range(k, len(ln)) if re.match(r"^\}\s*//\s*un-named", ln[i]))
+    body = ln[s:e + 1]
+    assert any("collision_thresh" in x for x in body) and any("num_backtracking_steps" in x for x in body)
+    out.append(("lib/ray_cast/xregRayCastDepthCPU.cpp", s, e, body))
     # RayCaster::distribute_xforms_among_cam_models and RayCasterCPU::pre_compute
     ln = _lines("lib/ray_cast/xregRayCastInterface.cpp")
     s, e = _cut_function(ln, r"^void xreg::RayCaster::distribute_xforms_among_cam_models\(")
@@ -205,6 +213,42 @@ extern "C" int xref_compute_line_ints(const float* vol, const uint64_t dims[3], 
 {
   return xref_compute_line_ints_interp(vol, dims, phys_to_idx, cams, n_cams, poses, cam_idx, n_projs, step_size, kernel_id,
                                        (int)xreg::RayCaster::kRAY_CAST_INTERP_LINEAR, proj_buf);
+}
+
+// RayCasterDepthCPU::compute's call of RayCastDepthFn over the whole projection range (xregRayCastDepthCPU.cpp:254-268);
+// proj_buf initialised by the caller (pre_compute: kRAY_CAST_MAX_DEPTH or the previous content)
+extern "C" int xref_compute_depth(const float* vol, const uint64_t dims[3], const float phys_to_idx[12],
+                                  const xref_cam* cams, uint32_t n_cams, const float* poses, const uint32_t* cam_idx,
+                                  uint32_t n_projs, float step_size, int interp, float collision_thresh,
+                                  uint32_t num_backtracking_steps, float* proj_buf)
+{
+  if (!n_cams || !n_projs)
+    return 0;
+  xreg::RayCaster::Vol img;
+  img.data = vol;
+  for (int i = 0; i < 3; ++i)
+    img.size[i] = (std::size_t)dims[i];
+  xreg::RayCaster::CameraModelList cam_list;
+  for (uint32_t c = 0; c < n_cams; ++c)
+    cam_list.push_back(cam_from(cams[c]));
+  xreg::FrameTransformList xforms;
+  xreg::RayCaster::CamModelAssocList assoc;
+  for (uint32_t p = 0; p < n_projs; ++p)
+  {
+    xforms.push_back(affine_from12(poses + 12 * (std::size_t)p));
+    assoc.push_back(cam_idx ? cam_idx[p] : 0);
+  }
+  xreg::Pt3 bb_min, bb_max;
+  for (int i = 0; i < 3; ++i)
+  {
+    bb_min(i) = 0;
+    bb_max(i) = static_cast<float>(dims[i] - 1);
+  }
+  RayCastDepthFn fn = {&img, bb_min, bb_max, affine_from12(phys_to_idx), n_projs, cam_list, xforms, assoc, step_size,
+                       static_cast<xreg::RayCaster::InterpMethod>(interp), proj_buf, collision_thresh,
+                       (xreg::size_type)num_backtracking_steps};
+  fn(xreg::RangeType(0, (std::size_t)n_projs * cam_list[0].num_det_rows * cam_list[0].num_det_cols));
+  return 0;
 }
 
 // interp: RayCaster::InterpMethod (0 linear, 1 nearest neighbour; the stand-ins for sinc / B-spline throw)

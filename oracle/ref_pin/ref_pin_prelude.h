@@ -49,6 +49,12 @@ struct Vec
     for (int i = 0; i < N; ++i)
       v[i] = 0.0f;
   }
+  Vec(float a, float b)   /* Pt2{col, row} (xregRayCastDepthCPU.cpp:126) */
+  {
+    static_assert(N == 2, "two-component initialiser");
+    v[0] = a;
+    v[1] = b;
+  }
   static Vec Zero() { return Vec(); }
   float& operator()(int i) { return v[i]; }
   const float& operator()(int i) const { return v[i]; }
@@ -158,6 +164,26 @@ struct Affine3
   }
   static Affine3 Identity() { return Affine3(); }
   Mat4View matrix() const { return Mat4View{m}; }
+  /* Transform<float,3,Affine>::inverse(): linear^-1 by cofactors (Eigen 3.3 compute_inverse_size3 shape: inv(i,j) =
+   * cof<j,i> / det, det = (cof<0,0> m00 + cof<1,0> m10) + cof<2,0> m20) and -(linear^-1) t -- third-party arithmetic,
+   * the convention the oracle states too (xo_affine_inverse); used by the depth ray caster's slice only */
+  Affine3 inverse() const
+  {
+    auto cof = [this](int i, int j) {
+      const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      return (m[i1][j1] * m[i2][j2]) - (m[i1][j2] * m[i2][j1]);
+    };
+    const float c0 = cof(0, 0), c1 = cof(1, 0), c2 = cof(2, 0);
+    const float det = ((c0 * m[0][0]) + (c1 * m[1][0])) + (c2 * m[2][0]);
+    const float invdet = 1.0f / det;
+    Affine3 r;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j)
+        r.m[i][j] = cof(j, i) * invdet;
+    for (int i = 0; i < 3; ++i)
+      r.m[i][3] = -(((r.m[i][0] * m[0][3]) + (r.m[i][1] * m[1][3])) + (r.m[i][2] * m[2][3]));
+    return r;
+  }
 };
 /* Transform * Transform, Affine mode: res.affine() = lhs.affine() * rhs.matrix() (sum over all four inner indices, in
  * order), last row copied */
@@ -199,6 +225,19 @@ struct Vector
   T v[N];
   T& operator[](unsigned i) { return v[i]; }
   const T& operator[](unsigned i) const { return v[i]; }
+  Vector& operator*=(const T& s)   /* itk::Vector::operator*=(const ValueType&): the scalar is converted to T first */
+  {
+    for (unsigned i = 0; i < N; ++i)
+      v[i] = static_cast<T>(v[i] * s);
+    return *this;
+  }
+  Vector operator-() const
+  {
+    Vector r;
+    for (unsigned i = 0; i < N; ++i)
+      r.v[i] = -v[i];
+    return r;
+  }
 };
 
 template <class T, unsigned N>
@@ -211,6 +250,12 @@ struct ContinuousIndex
   {
     for (unsigned i = 0; i < N; ++i)
       v[i] = v[i] + d.v[i];
+    return *this;
+  }
+  ContinuousIndex& operator-=(const Vector<T, N>& d)
+  {
+    for (unsigned i = 0; i < N; ++i)
+      v[i] = v[i] - d.v[i];
     return *this;
   }
 };
@@ -459,6 +504,9 @@ struct RayCasterCPU : RayCaster
 };
 
 struct RayCasterLineIntCPU : RayCasterCPU
+{
+};
+struct RayCasterDepthCPU : RayCasterCPU   /* the constant RayCastDepthFn names */
 {
 };
 

@@ -27,6 +27,7 @@ def lib():
         _lib.xref_ray_rect_intersect.restype = C.c_int
         _lib.xref_compute_line_ints.restype = C.c_int
         _lib.xref_compute_line_ints_interp.restype = C.c_int
+        _lib.xref_compute_depth.restype = C.c_int
     return _lib
 
 
@@ -64,6 +65,27 @@ def compute_line_ints(vol, phys_to_idx, cams, poses, cam_idx=None, step_size=1.0
                                              C.c_int(kernel_id), C.c_int(interp), _fp(buf))
     if rc != 0:
         raise ValueError("xref_compute_line_ints failed")
+    return buf
+
+
+def compute_depth(vol, phys_to_idx, cams, poses, cam_idx=None, step_size=1.0, interp=0, thresh=150.0, n_backtrack=0, buf=None):
+    """RayCastDepthFn over the whole projection range (serial); buf initialised by the caller or with kRAY_CAST_MAX_DEPTH."""
+    vol = _f32(vol)
+    nz, ny, nx = vol.shape
+    dims = (C.c_uint64 * 3)(nx, ny, nz)
+    poses = _f32(poses).reshape(-1, 12)
+    n = poses.shape[0]
+    cam_arr = (XoCam * len(cams))(*cams)
+    rows, cols = cams[0].rows, cams[0].cols
+    ci = np.ascontiguousarray(np.zeros(n, np.uint32) if cam_idx is None else cam_idx, dtype=np.uint32)
+    if buf is None:
+        buf = np.full((n, rows, cols), np.float32(1.0e37), np.float32)
+    a = _f32(phys_to_idx).reshape(12)
+    rc = lib().xref_compute_depth(_fp(vol), dims, _fp(a), cam_arr, C.c_uint32(len(cams)), _fp(poses),
+                                  ci.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_uint32(n), C.c_float(step_size),
+                                  C.c_int(interp), C.c_float(thresh), C.c_uint32(n_backtrack), _fp(buf))
+    if rc != 0:
+        raise ValueError("xref_compute_depth failed")
     return buf
 
 

@@ -310,10 +310,17 @@ double xo_interp_nn(const float* vol, const uint64_t dims[3], const float x[3])
 }
 
 /* lib/spatial/xregSpatialPrimitives.cpp:175-222, limit_to_segment = true */
+static int ray_rect_intersect_ex(const float mn[3], const float mx[3], const float p[3],
+                                 const float d[3], int limit_to_segment, float* t_start, float* t_stop);
 static int ray_rect_intersect(const float mn[3], const float mx[3], const float p[3],
                               const float d[3], float* t_start, float* t_stop)
 {
-  float t0 = 0.0f, t1 = 1.0f;
+  return ray_rect_intersect_ex(mn, mx, p, d, 1, t_start, t_stop);
+}
+static int ray_rect_intersect_ex(const float mn[3], const float mx[3], const float p[3],
+                                 const float d[3], int limit_to_segment, float* t_start, float* t_stop)
+{
+  float t0 = 0.0f, t1 = limit_to_segment ? 1.0f : INFINITY;
   int hit = 1;
   for (int k = 0; k < 3; ++k)
   {
@@ -493,6 +500,134 @@ int xo_drr_interp(const float* vol, const uint64_t dims[3], const float idx_to_p
   }
   if (total_samples)
     *total_samples = S;
+  return 0;
+}
+
+/* RayCasterDepthCPU::compute / RayCastDepthFn::operator() (lib/ray_cast/xregRayCastDepthCPU.cpp:42-272): per ray, walk
+ * the volume from the source side in steps of step_size; at the first sample whose interpolated value is >=
+ * collision_thresh refine the crossing by num_backtracking_steps halvings of the step (:206-216), take the distance of
+ * that point from the pinhole in the camera frame (through the INVERSE of the camera -> index transform, :97, :228) and
+ * store buf = min(buf, depth) (:226).  Rays that never reach the threshold leave buf alone (the class initialises it
+ * with kRAY_CAST_MAX_DEPTH = 1e37 through pre_compute; call xo_pre_compute with that default first).  The ray is NOT
+ * limited to the source-detector segment (RayRectIntersect(..., false), :118-121).  Eigen's Transform::inverse() is
+ * the stated convention of xo_affine_inverse. */
+int xo_depth(const float* vol, const uint64_t dims[3], const float idx_to_phys[12],
+             const xo_cam* cams, uint32_t n_cams,
+             const float* poses, const uint32_t* cam_idx, uint32_t n_projs,
+             float step_size, int interp, float collision_thresh, uint32_t num_backtracking_steps,
+             float* buf, int n_threads)
+{
+  if (!n_cams || !n_projs)
+    return 0;
+  if (interp != XO_INTERP_LINEAR && interp != XO_INTERP_NN)
+    return -3;
+  const uint32_t rows = cams[0].rows, cols = cams[0].cols;
+  for (uint32_t c = 1; c < n_cams; ++c)
+    if (cams[c].rows != rows || cams[c].cols != cols)
+      return -1;
+  for (uint32_t p = 0; p < n_projs; ++p)
+    if (cam_idx[p] >= n_cams)
+      return -2;
+  const float aabb_min[3] = {0.0f, 0.0f, 0.0f};
+  const float aabb_max[3] = {(float)(dims[0] - 1), (float)(dims[1] - 1), (float)(dims[2] - 1)};
+  float phys_to_idx[12];
+  xo_affine_inverse(idx_to_phys, phys_to_idx); /* :245-249 */
+  const size_t npix = (size_t)rows * cols;
+  const int64_t n_rays = (int64_t)npix * n_projs;
+  const int nt = resolve_threads(n_threads);
+  (void)nt;
+
+#pragma omp parallel for schedule(dynamic, 1024) num_threads(nt)
+  for (int64_t i = 0; i < n_rays; ++i)
+  {
+    const size_t proj = (size_t)i / npix;
+    const size_t off = (size_t)i - npix * proj;
+    const size_t row = off / cols;
+    const size_t col = off - (size_t)cols * row;
+    const xo_cam* cam = &cams[cam_idx[proj]];
+
+    /* CameraModel::ind_pt_to_phys_det_pt (xregPerspectiveXform.cpp:391-414), :88-89 */
+    const float det_z = ((cam->frame_type == 1) ? -1.0f : 1.0f) * cam->focal_len;
+    const float ind[3] = {det_z * (float)col, det_z * (float)row, det_z * 1.0f};
+    float tmp3[3], det[3];
+    mat3_apply(cam->intrins_inv, ind, tmp3);
+    if (cam->frame_type == 2)
+    {
+      tmp3[0] = tmp3[0] + 0.0f;
+      tmp3[1] = tmp3[1] + 0.0f;
+      tmp3[2] = tmp3[2] + (-cam->focal_len);
+    }
+    affine_apply(cam->extrins_inv, tmp3, det);
+
+    float X[12], Xinv[12];
+    xo_affine_compose(phys_to_idx, poses + 12 * proj, X); /* :93 */
+    xo_affine_inverse(X, Xinv);                           /* :95 */
+
+    float p[3], xd[3], d[3];
+    affine_apply(X, cam->pinhole, p); /* :98 */
+    affine_apply(X, det, xd);         /* :101 */
+    d[0] = xd[0] - p[0];
+    d[1] = xd[1] - p[1];
+    d[2] = xd[2] - p[2];
+
+    float t0 = 0.0f, t1 = 0.0f;
+    const int hit = ray_rect_intersect_ex(aabb_min, aabb_max, p, d, 0, &t0, &t1); /* :118-121 */
+    if (!(hit && ((t1 - t0) > (2.0f * XO_VOL_BB_STEP_INC_TOL))))                  /* :125 */
+      continue;
+    t0 += XO_VOL_BB_STEP_INC_TOL;
+    t1 -= XO_VOL_BB_STEP_INC_TOL;
+    float x[3] = {p[0] + (t0 * d[0]), p[1] + (t0 * d[1]), p[2] + (t0 * d[2])}; /* :131 */
+    const float L = norm3(d);                                                  /* :133 */
+    const float len = (t1 - t0) * L;                                           /* :134 */
+    float dir[3] = {det[0] - cam->pinhole[0], det[1] - cam->pinhole[1], det[2] - cam->pinhole[2]};
+    const float dn = norm3(dir);
+    dir[0] = (dir[0] / dn) * step_size;
+    dir[1] = (dir[1] / dn) * step_size;
+    dir[2] = (dir[2] / dn) * step_size;
+    float sv0[3];
+    for (int r = 0; r < 3; ++r)
+      sv0[r] = dot3(X[4 * r], X[4 * r + 1], X[4 * r + 2], dir[0], dir[1], dir[2]);
+    const float step_len = norm3(sv0);                     /* :137 */
+    const uint64_t num_steps = (uint64_t)(len / step_len); /* :139 */
+    const float scale = step_len / L;                      /* :147 */
+    float sv[3] = {d[0] * scale, d[1] * scale, d[2] * scale};
+
+    for (uint64_t s = 0; s <= num_steps; ++s) /* :155 */
+    {
+      float v = (interp == XO_INTERP_NN) ? (float)xo_interp_nn(vol, dims, x) : (float)xo_interp_linear(vol, dims, x);
+      if (v >= collision_thresh)
+      {
+        for (uint32_t b = 0; b < num_backtracking_steps; ++b) /* :162-171 */
+        {
+          sv[0] *= 0.5f;
+          sv[1] *= 0.5f;
+          sv[2] *= 0.5f;
+          if (v >= collision_thresh)
+          {
+            x[0] = x[0] - sv[0];
+            x[1] = x[1] - sv[1];
+            x[2] = x[2] - sv[2];
+          }
+          else
+          {
+            x[0] = x[0] - (-sv[0]);
+            x[1] = x[1] - (-sv[1]);
+            x[2] = x[2] - (-sv[2]);
+          }
+          v = (interp == XO_INTERP_NN) ? (float)xo_interp_nn(vol, dims, x) : (float)xo_interp_linear(vol, dims, x);
+        }
+        float c[3];
+        affine_apply(Xinv, x, c); /* :180-181 */
+        const float e[3] = {c[0] - cam->pinhole[0], c[1] - cam->pinhole[1], c[2] - cam->pinhole[2]};
+        const float depth = norm3(e);
+        buf[i] = (depth < buf[i]) ? depth : buf[i]; /* std::min(buf, depth) */
+        break;
+      }
+      x[0] += sv[0];
+      x[1] += sv[1];
+      x[2] += sv[2];
+    }
+  }
   return 0;
 }
 

@@ -130,6 +130,16 @@ int xo_drr_interp(const float* vol, const uint64_t dims[3], const float idx_to_p
                   float* buf, uint8_t* hit_mask, uint32_t* num_steps_out,
                   uint64_t* total_samples, int n_threads);
 
+/* RayCasterDepthCPU::compute (lib/ray_cast/xregRayCastDepthCPU.cpp:42-272): depth of the first sample >= collision_thresh
+ * along every ray, refined by num_backtracking_steps step halvings; buf = min(buf, depth) (initialise buf with
+ * kRAY_CAST_MAX_DEPTH = 1e37 via xo_pre_compute, as the class does). */
+#define XO_RAY_CAST_MAX_DEPTH 1.0e37f
+int xo_depth(const float* vol, const uint64_t dims[3], const float idx_to_phys[12],
+             const xo_cam* cams, uint32_t n_cams,
+             const float* poses, const uint32_t* cam_idx, uint32_t n_projs,
+             float step_size, int interp, float collision_thresh, uint32_t num_backtracking_steps,
+             float* buf, int n_threads);
+
 /* ITK LinearInterpolateImageFunction::EvaluateOptimized(Dispatch<3>) restated. */
 double xo_interp_linear(const float* vol, const uint64_t dims[3], const float x[3]);
 /* ITK NearestNeighborInterpolateImageFunction::EvaluateAtContinuousIndex restated. */

@@ -64,6 +64,7 @@ def lib():
         _lib.xo_num_patches.restype = C.c_uint64
         _lib.xo_drr.restype = C.c_int
         _lib.xo_drr_interp.restype = C.c_int
+        _lib.xo_depth.restype = C.c_int
         _lib.xo_interp_nn.restype = C.c_double
         _lib.xo_num_threads.restype = C.c_int
     return _lib
@@ -192,6 +193,36 @@ def drr(vol, idx_to_phys, cams, poses, cam_idx=None, step_size=1.0, kernel_id=0,
         raise ValueError("xo_drr failed with code %d" % rc)
     if want_info:
         return buf, mask, steps, int(S.value)
+    return buf
+
+
+RAY_CAST_MAX_DEPTH = np.float32(1.0e37)   # xregRayCastInterface.h:601
+
+
+def depth(vol, idx_to_phys, cams, poses, cam_idx=None, step_size=1.0, interp=0, thresh=150.0, n_backtrack=0, buf=None,
+          n_threads=0):
+    """RayCasterDepthCPU::compute (xo_depth).  buf (n, rows, cols): min-combined in place; None = a buffer initialised with
+    kRAY_CAST_MAX_DEPTH (the class's default background).  thresh / n_backtrack default like RayCasterDepthCPU
+    (xregRayCastInterface.cpp:427-428)."""
+    vol = _f32(vol)
+    nz, ny, nx = vol.shape
+    dims = (C.c_uint64 * 3)(nx, ny, nz)
+    a = _f32(idx_to_phys).reshape(12)
+    poses = _f32(poses).reshape(-1, 12)
+    n = poses.shape[0]
+    cam_arr = (XoCam * len(cams))(*cams)
+    rows, cols = cams[0].rows, cams[0].cols
+    if cam_idx is None:
+        cam_idx = np.zeros(n, np.uint32)
+    cam_idx = np.ascontiguousarray(cam_idx, dtype=np.uint32)
+    if buf is None:
+        buf = np.full((n, rows, cols), RAY_CAST_MAX_DEPTH, np.float32)
+    assert buf.dtype == np.float32 and buf.flags.c_contiguous and buf.shape == (n, rows, cols)
+    rc = lib().xo_depth(_fp(vol), dims, _fp(a), cam_arr, C.c_uint32(len(cams)), _fp(poses),
+                        cam_idx.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_uint32(n), C.c_float(step_size), C.c_int(interp),
+                        C.c_float(thresh), C.c_uint32(n_backtrack), _fp(buf), C.c_int(n_threads))
+    if rc != 0:
+        raise ValueError("xo_depth failed with code %d" % rc)
     return buf
 
 

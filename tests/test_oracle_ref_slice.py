@@ -95,6 +95,38 @@ def test_oracle_drr_equals_the_reference_code_on_random_scenes(xo, seed):
     assert a2.tobytes() == b2.tobytes()
 
 
+@pytest.mark.parametrize("seed", range(0, 48, 2))
+def test_oracle_depth_equals_the_reference_code(xo, seed):
+    """RayCasterDepthCPU (xregRayCastDepthCPU.cpp:42-229): the reference's RayCastDepthFn -- first sample >= threshold
+    along the unlimited ray, step-halving refinement, distance from the pinhole through the inverse camera -> index
+    transform, min store -- against xo_depth, bit for bit, linear and nearest-neighbour interpolation, several
+    thresholds and refinement counts, on top of kRAY_CAST_MAX_DEPTH and on top of a previous depth image."""
+    vol, cam, poses, step, kernel_id, kind = _scene(seed)
+    xcams = [xo.cam_struct(cam)]
+    p12 = to12(poses)
+    vmax = float(vol.data.max())
+    hits = 0
+    for interp in (0, 1):
+        for frac, nb in ((0.3, 0), (0.6, 4), (0.05, 20), (2.0, 3)):
+            thr = frac * vmax if vmax > 0 else 0.5
+            a = xo.depth(vol.data, vol.idx_to_phys(), xcams, p12, step_size=step, interp=interp, thresh=thr, n_backtrack=nb,
+                         n_threads=1)
+            b = ref_slice.compute_depth(vol.data, xo.affine_inverse(vol.idx_to_phys()), xcams, p12, step_size=step,
+                                        interp=interp, thresh=thr, n_backtrack=nb)
+            assert a.tobytes() == b.tobytes()
+            hits += int(np.count_nonzero(a < 1.0e36))
+            if frac >= 2.0:
+                assert np.all(a == xo.RAY_CAST_MAX_DEPTH)      # nothing reaches a threshold above the maximum
+            prev = np.where(a < 1.0e36, a * f32(0.5), f32(40.0)).astype(f32)
+            a2 = xo.depth(vol.data, vol.idx_to_phys(), xcams, p12, step_size=step, interp=interp, thresh=thr, n_backtrack=nb,
+                          buf=prev.copy(), n_threads=1)
+            b2 = ref_slice.compute_depth(vol.data, xo.affine_inverse(vol.idx_to_phys()), xcams, p12, step_size=step,
+                                         interp=interp, thresh=thr, n_backtrack=nb, buf=prev.copy())
+            assert a2.tobytes() == b2.tobytes() and np.all(a2 <= prev)
+    if vmax > 0 and seed in (0, 2, 4, 6):
+        assert hits > 0        # the comparison is not vacuous: surfaces are found
+
+
 def test_oracle_drr_equals_the_reference_code_on_the_test_scene(xo, small_scene):
     """The 64x64x48 anisotropic phantom of the GPU parity tests, two cameras, camera-major association."""
     vol, cam, nominal = small_scene
