@@ -114,6 +114,16 @@ int xrc_rc_volume_bytes(const xrc_rc* rc, uint64_t* bytes);
 /* The layout volume vol_idx really uses (XRC_LAYOUT_*): with XRC_LAYOUT_DEFAULT the library chooses the principal-axis
  * stacks and falls back to one XY-quad stack when the record index does not fit 32 bits or device memory runs out. */
 int xrc_rc_volume_layout(const xrc_rc* rc, uint32_t vol_idx, int* layout);
+/* RayCasterDepthCPU::compute (lib/ray_cast/xregRayCastDepthCPU.cpp:42-272) on this ray caster's
+ * volumes, cameras and poses: per pixel the depth -- distance from the pinhole, in the camera frame -- of the first sample
+ * along the (unlimited) ray whose interpolated value is >= collision_thresh, refined by num_backtracking_steps halvings
+ * of the step; out = min(initial value, depth) with the initial value as for xrc_rc_compute (the class's default
+ * background is kRAY_CAST_MAX_DEPTH: xrc_rc_set_params(..., default_bg = XRC_RAY_CAST_MAX_DEPTH)); rays that never reach
+ * the threshold keep the initial value.  Linear (ITK's arithmetic itself: f64 lerps of the f32 voxels, so that every
+ * threshold decision is the CPU class's) or nearest-neighbour interpolation.  Bit-identical to the CPU class.
+ * The class defaults are collision_thresh 150, num_backtracking_steps 0 (xregRayCastInterface.cpp:427-428). */
+#define XRC_RAY_CAST_MAX_DEPTH 1.0e37f
+int xrc_rc_compute_depth(xrc_rc* rc, uint32_t vol_idx, float collision_thresh, uint32_t num_backtracking_steps);
 /* Empty-space trimming, default on.  Samples whose 8 corner voxels are all zero add +0 to the
  * sequential f32 sum of xregRayCastLineIntCPU.cpp:270-279, so the sum kernel does not fetch the leading
  * and trailing samples of a ray that a per-volume block map proves to be zero (air around the body,

@@ -791,7 +791,7 @@ protected:
     }
   }
 
-private:
+protected:
   friend class Intensity2D3DObjFn;
 
   /// xrc_obj_fn sized the library's ray caster for num_projs projections and distributed its own poses
@@ -852,6 +852,36 @@ private:
   bool host_valid_ = false;
   std::vector<float> tmp_poses_;
   std::vector<uint32_t> tmp_cam_idx_;
+};
+
+/// xreg::RayCasterDepthCPU (lib/ray_cast/xregRayCastDepthCPU.{h,cpp}) with RayCasterCollisionParamInterface
+/// (xregRayCastInterface.h:436-475): per pixel the depth of the first sample >= render_thresh() along the ray, refined
+/// by num_backtracking_steps() halvings of the step, min-combined on top of the background (kRAY_CAST_MAX_DEPTH by
+/// default, as the class's constructor sets it).  Everything else is the line-integral ray caster's state.
+constexpr float kRAY_CAST_MAX_DEPTH = XRC_RAY_CAST_MAX_DEPTH;  // xregRayCastInterface.h:601
+
+class RayCasterDepthCUDA : public RayCasterLineIntCUDA
+{
+public:
+  explicit RayCasterDepthCUDA(Context& ctx) : RayCasterLineIntCUDA(ctx) { set_default_bg_pixel_val(kRAY_CAST_MAX_DEPTH); }
+
+  void set_render_thresh(const PixelScalar3D t) { render_thresh_ = t; }
+  PixelScalar3D render_thresh() const { return render_thresh_; }
+  void set_num_backtracking_steps(const size_type n) { num_backtracking_steps_ = n; }
+  size_type num_backtracking_steps() const { return num_backtracking_steps_; }
+
+  void compute(const size_type vol_idx = 0) override
+  {
+    detail::Assert(resources_allocated_, "resources_allocated_ (xregRayCastDepthCPU.cpp:238)");
+    flush();
+    detail::Check(xrc_rc_compute_depth(rc_, static_cast<uint32_t>(vol_idx), render_thresh_,
+                                       static_cast<uint32_t>(num_backtracking_steps_)));
+    host_valid_ = false;
+  }
+
+private:
+  PixelScalar3D render_thresh_ = 150;          // xregRayCastInterface.cpp:427-428
+  size_type num_backtracking_steps_ = 0;
 };
 
 /// xreg::ImgSimMetric2D (xregImgSimMetric2D.h:42-156) over the xrc_sm_* entry points.

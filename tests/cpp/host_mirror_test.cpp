@@ -469,9 +469,28 @@ static void TestRayCaster(Context& ctx, const Scene& s)
     rc.use_external_host_pixel_buf(nullptr);
   }
 
-  // only linear interpolation, like the OpenCL backend (xregRayCastBaseOCL.cpp:338-341)
-  rc.use_nn_interp();
+  // linear and nearest-neighbour interpolation; sinc / B-spline are unsupported (the OpenCL backend is linear only,
+  // xregRayCastBaseOCL.cpp:338-341)
+  rc.use_sinc_interp();
   CHECK(Throws<UnsupportedOperationException>([&] { rc.compute(); }));
+  rc.use_bspline_interp();
+  CHECK(Throws<UnsupportedOperationException>([&] { rc.compute(); }));
+  rc.use_nn_interp();
+  rc.compute();
+  {
+    // nearest neighbour: no arithmetic on the voxel values -> bit-identical to the CPU class (xo_drr_interp)
+    std::vector<float> o(6 * npix, 0.0f);
+    std::vector<float> p12(12 * poses.size());
+    std::vector<uint32_t> ci(poses.size(), 0u);
+    for (size_type i = 0; i < poses.size(); ++i)
+      poses[i].to3x4(&p12[12 * i]);
+    float i2p[12];
+    s.vol.idx_to_phys(i2p);
+    const xo_cam oc = ToOracleCam(s.cam);
+    CHECK(xo_drr_interp(s.vol.data, s.vol.size, i2p, &oc, 1, p12.data(), ci.data(), static_cast<uint32_t>(poses.size()), 1.0f,
+                        XO_KERNEL_SUM, XO_INTERP_NN, o.data(), nullptr, nullptr, nullptr, 0) == 0);
+    CHECK(std::memcmp(o.data(), rc.raw_host_pixel_buf(), sizeof(float) * o.size()) == 0);
+  }
   rc.use_linear_interp();
   rc.compute();
   CheckDrr(rc.raw_host_pixel_buf(), ref);

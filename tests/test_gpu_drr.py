@@ -88,6 +88,56 @@ def test_nearest_neighbour_interpolation_is_bit_exact(ctx, xo, small_scene, layo
     rc.close()
 
 
+@pytest.mark.parametrize("layout", ["pax", "linear", "quad"])
+def test_depth_ray_caster_is_bit_exact(ctx, xo, small_scene, layout):
+    """RayCasterDepthCUDA == RayCasterDepthCPU (oracle xo_depth, itself pinned to the reference's RayCastDepthFn), bit for
+    bit: thresholds, step-halving refinement, linear and nearest-neighbour interpolation, min on top of the default
+    background (kRAY_CAST_MAX_DEPTH), of a previous depth image (ACCUM) and of a background projection; two cameras."""
+    vol, cam, nominal = small_scene
+    cam2 = CameraModel().setup(380.0, cam.num_det_rows, cam.num_det_cols, 1.7, 1.4)
+    xc = [xo.cam_struct(cam), xo.cam_struct(cam2)]
+    vmax = float(vol.data.max())
+    rc = xreg_b200.RayCasterDepthCUDA(ctx, layout=layout)
+    rc.set_volume(vol)
+    rc.set_camera_models([cam, cam2])
+    rc.set_num_projs(6)
+    rc.allocate_resources()
+    cam_idx = np.array([0, 0, 0, 1, 1, 1], np.uint32)
+    found = 0
+    for view in (0.0, 90.0, 40.0):
+        pop = synth.pose_population(vol, synth.nominal_pose(vol, src_to_iso=250.0, view_rot_deg=view), 3, sigma=(10, 10, 10, 6, 6, 6))
+        rc.distribute_xforms_among_cam_models(list(pop))
+        p12 = to12(np.concatenate([pop, pop]))
+        for interp in (0, 1):
+            rc.set_interp_method(interp)
+            for frac, nb, step in ((0.5, 0, 1.0), (0.7, 6, 1.0), (0.2, 20, 0.6), (3.0, 2, 1.0)):
+                rc.set_render_thresh(frac * vmax)
+                rc.set_num_backtracking_steps(nb)
+                rc.set_ray_step_size(step)
+                rc.use_proj_store_replace_method()
+                rc.compute()
+                got = rc.raw_host_pixel_buf().copy()
+                ref = xo.depth(vol.data, vol.idx_to_phys(), xc, p12, cam_idx=cam_idx, step_size=step, interp=interp,
+                               thresh=frac * vmax, n_backtrack=nb)
+                assert got.tobytes() == ref.tobytes(), (layout, view, interp, frac, nb)
+                found += int(np.count_nonzero(ref < 1.0e36))
+                if frac > 1.0:
+                    assert np.all(got == np.float32(1.0e37))
+                # ACCUM: min with what is there (a second surface at a lower threshold can only come closer)
+                rc.use_proj_store_accum_method()
+                rc.set_render_thresh(0.5 * frac * vmax)
+                rc.compute()
+                ref2 = xo.depth(vol.data, vol.idx_to_phys(), xc, p12, cam_idx=cam_idx, step_size=step, interp=interp,
+                                thresh=0.5 * frac * vmax, n_backtrack=nb, buf=ref.copy())
+                got2 = rc.raw_host_pixel_buf()
+                assert got2.tobytes() == ref2.tobytes() and np.all(got2 <= got)
+    assert found > 1000
+    rc.use_sinc_interp()
+    with pytest.raises(xreg_b200.UnsupportedOperationException):
+        rc.compute()
+    rc.close()
+
+
 def test_layouts_agree_bitwise(ctx, small_scene):
     vol, cam, nominal = small_scene
     poses = synth.pose_population(vol, nominal, 3)

@@ -992,6 +992,27 @@ int xrc_rc_compute(xrc_rc* rc, uint32_t vol_idx)
   return launch_drr(a, rc->vols[vol_idx].layout, rc->kernel_id, rc->ctx->stream);
 }
 
+// RayCasterDepthCPU::compute (lib/ray_cast/xregRayCastDepthCPU.cpp:236-272) on this ray caster's volumes / cameras / poses
+int xrc_rc_compute_depth(xrc_rc* rc, uint32_t vol_idx, float collision_thresh, uint32_t num_backtracking_steps)
+{
+  XRC_CHECK_ARG(rc, "null ray caster");
+  XRC_CHECK_ARG(rc->allocated, "xrc_rc_compute_depth: resources not allocated (xregRayCastDepthCPU.cpp:238)");
+  XRC_CHECK_ARG(vol_idx < rc->vols.size(), "xrc_rc_compute_depth: volume index out of range");
+  XRC_CHECK_ARG(rc_proj_buf(rc) && rc->num_projs <= rc_proj_capacity(rc),
+                "xrc_rc_compute_depth: the shared projection buffer (xrc_rc_use_other_proj_buf) is gone or too small");
+  XRC_CHECK_ARG(num_backtracking_steps <= 64, "xrc_rc_compute_depth: more than 64 refinement steps halve the step to nothing");
+  if (rc->interp != XRC_INTERP_LINEAR && rc->interp != XRC_INTERP_NN)
+    XRC_FAIL(XRC_ERR_UNSUPPORTED, "xrc_rc_compute_depth: linear and nearest-neighbour interpolation only");
+  XRC_TRY(use_device(rc->ctx));
+  XRC_TRY(rc_prepare_stacks(rc, vol_idx));
+  DrrArgs a;
+  rc_fill_args(rc, vol_idx, &a);
+  XRC_TRY(rc_fill_nn(rc->vols[vol_idx], &a));
+  a.depth_thresh = collision_thresh;
+  a.depth_backtrack = num_backtracking_steps;
+  return launch_depth(a, rc->interp == XRC_INTERP_NN ? 1 : 0, rc->ctx->stream);
+}
+
 // ---- multi-GPU tile sharding, one process per GPU
 int xrc_rc_peer_export(xrc_rc* rc, uint8_t handle[XRC_IPC_HANDLE_BYTES])
 {

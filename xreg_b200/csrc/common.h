@@ -132,6 +132,9 @@ struct DrrArgs
   // iy * nn_s[1] + iz * nn_s[2]] -- the padded f32 copy, or the first component of a record of whatever stack exists
   const float* nn_base;
   uint32_t nn_s[3], nn_off;
+  // depth ray caster (launch_depth): collision threshold and number of step-halving refinements
+  float depth_thresh;
+  uint32_t depth_backtrack;
   // small populations (latency regime): poses travel in the kernel parameters instead of an H2D copy
   int use_inline;
   float inl_poses[kInlinePoses * 12];
@@ -145,6 +148,7 @@ void launch_hu_to_lin_att(float* d_vol, size_t n, float hu_lower, cudaStream_t s
 void free_volume(DeviceVolume* v);
 int launch_drr(const DrrArgs& a, int layout, int kernel_id, cudaStream_t st);
 int launch_ray_info(const DrrArgs& a, cudaStream_t st);
+int launch_depth(const DrrArgs& a, int nearest, cudaStream_t st);   // needs the nn_* payload description
 
 void affine_inverse_f32(const float a[12], float out[12]);
 

@@ -97,7 +97,7 @@ __device__ __forceinline__ void compute_proj_const(const DrrArgs& a, const xrc_c
 
 // xregRayCastLineIntCPU.cpp:176-268 for one pixel
 __device__ __forceinline__ Ray setup_ray(const xrc_cam& cam, const ProjConst& pc, float step_size,
-                                         int nx, int ny, int nz, uint32_t row, uint32_t col)
+                                         int nx, int ny, int nz, uint32_t row, uint32_t col, bool limit_to_segment = true)
 {
   Ray ray;
   ray.hit = false;
@@ -128,8 +128,9 @@ __device__ __forceinline__ Ray setup_ray(const xrc_cam& cam, const ProjConst& pc
   const float dy = fsub(fadd(dot3(X[4], X[5], X[6], d0, d1, d2), X[7]), py);
   const float dz = fsub(fadd(dot3(X[8], X[9], X[10], d0, d1, d2), X[11]), pz);
 
-  // RayRectIntersect, limit_to_segment = true (xregSpatialPrimitives.cpp:175-222)
-  float t0 = 0.f, t1 = 1.f;
+  // RayRectIntersect (xregSpatialPrimitives.cpp:175-222); the line integral limits the ray to the source-detector segment,
+  // the depth ray caster does not (xregRayCastDepthCPU.cpp:118-121)
+  float t0 = 0.f, t1 = limit_to_segment ? 1.f : __int_as_float(0x7f800000);
   bool hit = true;
   const float pp[3] = {px, py, pz};
   const float dd[3] = {dx, dy, dz};
@@ -502,6 +503,185 @@ __global__ void __launch_bounds__(kThreads) drr_kernel(const DrrArgs a)
   }
 }
 
+
+// ----------------------------------------------------------------------------
+// Depth ray caster (RayCasterDepthCPU, lib/ray_cast/xregRayCastDepthCPU.cpp:42-272): per ray the
+// first sample whose interpolated value reaches the collision threshold, refined by step halvings, as the distance of
+// that point from the pinhole in the camera frame; stored with min.  Every decision (value >= threshold) must be the
+// CPU class's, so the interpolation here is ITK's arithmetic itself -- f64 lerps of the f32 corners with f32 weights,
+// uncontracted -- read from whatever payload the volume has (like the nearest-neighbour sampler).  Not a throughput
+// kernel: a depth image is rendered once in a while, not per optimiser iteration.
+// ----------------------------------------------------------------------------
+struct VoxelReader
+{
+  const float* __restrict__ v;
+  size_t s0, s1, s2, off;
+  int hx, hy, hz;
+  __device__ VoxelReader(const DrrArgs& a)
+      : v(a.nn_base), s0(a.nn_s[0]), s1(a.nn_s[1]), s2(a.nn_s[2]), off(a.nn_off), hx(a.nx - 1), hy(a.ny - 1), hz(a.nz - 1)
+  {
+  }
+  __device__ __forceinline__ double at(int ix, int iy, int iz) const
+  {
+    return (double)__ldg(v + (off + (size_t)ix * s0 + (size_t)iy * s1 + (size_t)iz * s2));
+  }
+  __device__ __forceinline__ float nearest(float x, float y, float z) const
+  {
+    const int ix = min(max((int)floor((double)x + 0.5), 0), hx);
+    const int iy = min(max((int)floor((double)y + 0.5), 0), hy);
+    const int iz = min(max((int)floor((double)z + 0.5), 0), hz);
+    return (float)at(ix, iy, iz);
+  }
+  // itk::LinearInterpolateImageFunction::EvaluateOptimized(Dispatch<3>) as the oracle restates it (xo_interp_linear)
+  __device__ __forceinline__ float linear(float x, float y, float z) const
+  {
+    const float xs[3] = {x, y, z};
+    const int h[3] = {hx, hy, hz};
+    int b[3], n[3];
+    double d[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+    {
+      int bk = (int)floorf(xs[k]);
+      bk = min(max(bk, 0), h[k]);
+      float dist = __fsub_rn(xs[k], (float)bk);
+      int nk = bk + 1;
+      if (dist <= 0.0f)
+      {
+        dist = 0.0f;
+        nk = bk;
+      }
+      if (nk > h[k])
+      {
+        nk = bk;
+        dist = 0.0f;
+      }
+      b[k] = bk;
+      n[k] = nk;
+      d[k] = (double)dist;
+    }
+    const double v000 = at(b[0], b[1], b[2]), v100 = at(n[0], b[1], b[2]);
+    const double v010 = at(b[0], n[1], b[2]), v110 = at(n[0], n[1], b[2]);
+    const double v001 = at(b[0], b[1], n[2]), v101 = at(n[0], b[1], n[2]);
+    const double v011 = at(b[0], n[1], n[2]), v111 = at(n[0], n[1], n[2]);
+    auto lerp64 = [](double a, double bb, double w) { return __dadd_rn(a, __dmul_rn(__dsub_rn(bb, a), w)); };
+    const double vx00 = lerp64(v000, v100, d[0]);
+    const double vx10 = lerp64(v010, v110, d[0]);
+    const double vxx0 = lerp64(vx00, vx10, d[1]);
+    const double vx01 = lerp64(v001, v101, d[0]);
+    const double vx11 = lerp64(v011, v111, d[0]);
+    const double vxx1 = lerp64(vx01, vx11, d[1]);
+    return (float)lerp64(vxx0, vxx1, d[2]);
+  }
+};
+
+template <bool NN>
+__global__ void __launch_bounds__(256) depth_kernel(const DrrArgs a)
+{
+  __shared__ ProjConst pc;
+  __shared__ xrc_cam cam_s;
+  __shared__ float Xinv[12];
+
+  const uint32_t tiles_x = (a.cols + 15u) / 16u, tiles_y = (a.rows + 15u) / 16u;
+  const uint32_t proj = blockIdx.x % a.n_projs, tile = blockIdx.x / a.n_projs;
+  const uint32_t ci = proj_cam_index(a, proj);
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.cams + ci);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&cam_s);
+    if (threadIdx.x < sizeof(xrc_cam) / 4)
+      dst[threadIdx.x] = src[threadIdx.x];
+  }
+  __syncthreads();
+  compute_proj_const(a, cam_s, proj, &pc);
+  if (threadIdx.x == 0)
+  {
+    // Transform<float,3,Affine>::inverse() in the oracle's convention (xo_affine_inverse): cofactor inverse of the linear
+    // part, det = (cof00 m00 + cof10 m10) + cof20 m20, translation -(inv . t)
+    const float* X = pc.X;
+    auto m = [X](int i, int j) { return X[4 * i + j]; };
+    auto cof = [&m](int i, int j) {
+      const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      return fsub(fmul(m(i1, j1), m(i2, j2)), fmul(m(i1, j2), m(i2, j1)));
+    };
+    const float c0 = cof(0, 0), c1 = cof(1, 0), c2 = cof(2, 0);
+    const float det = fadd(fadd(fmul(c0, m(0, 0)), fmul(c1, m(1, 0))), fmul(c2, m(2, 0)));
+    const float invdet = fdiv(1.0f, det);
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j)
+        Xinv[4 * i + j] = fmul(cof(j, i), invdet);
+    for (int i = 0; i < 3; ++i)
+      Xinv[4 * i + 3] = -dot3(Xinv[4 * i], Xinv[4 * i + 1], Xinv[4 * i + 2], X[3], X[7], X[11]);
+  }
+  __syncthreads();
+  (void)tiles_y;
+
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
+  const uint32_t col = tx * 16u + (warp & 1) * 8u + (lane & 7), row = ty * 16u + (warp >> 1) * 4u + (lane >> 3);
+  if (row >= a.rows || col >= a.cols)
+    return;
+
+  const size_t npix = (size_t)a.rows * a.cols;
+  const size_t o = (size_t)proj * npix + (size_t)row * a.cols + col;
+  float base;   // RayCasterCPU::pre_compute
+  if (a.init_mode == 0)
+    base = a.default_bg;
+  else if (a.init_mode == 1)
+    base = __ldg(a.bg + (size_t)ci * npix + (size_t)row * a.cols + col);
+  else
+    base = a.out[o];
+
+  const Ray ray = setup_ray(cam_s, pc, a.step_size, a.nx, a.ny, a.nz, row, col, false);
+  float out = base;
+  if (ray.hit)
+  {
+    const VoxelReader vr(a);
+    float x = ray.x, y = ray.y, z = ray.z;
+    float sx = ray.sx, sy = ray.sy, sz = ray.sz;
+    for (uint32_t s = 0; s < ray.nsamples; ++s)
+    {
+      float v = NN ? vr.nearest(x, y, z) : vr.linear(x, y, z);
+      if (v >= a.depth_thresh)
+      {
+        for (uint32_t bt = 0; bt < a.depth_backtrack; ++bt)   // xregRayCastDepthCPU.cpp:206-216
+        {
+          sx = fmul(sx, 0.5f);
+          sy = fmul(sy, 0.5f);
+          sz = fmul(sz, 0.5f);
+          const bool back = v >= a.depth_thresh;
+          x = back ? fsub(x, sx) : fsub(x, -sx);
+          y = back ? fsub(y, sy) : fsub(y, -sy);
+          z = back ? fsub(z, sz) : fsub(z, -sz);
+          v = NN ? vr.nearest(x, y, z) : vr.linear(x, y, z);
+        }
+        const float cx = fadd(dot3(Xinv[0], Xinv[1], Xinv[2], x, y, z), Xinv[3]);
+        const float cy = fadd(dot3(Xinv[4], Xinv[5], Xinv[6], x, y, z), Xinv[7]);
+        const float cz = fadd(dot3(Xinv[8], Xinv[9], Xinv[10], x, y, z), Xinv[11]);
+        const float depth = norm3(fsub(cx, cam_s.pinhole[0]), fsub(cy, cam_s.pinhole[1]), fsub(cz, cam_s.pinhole[2]));
+        out = (depth < base) ? depth : base;   // std::min(buf, depth), :226
+        break;
+      }
+      x = fadd(x, sx);
+      y = fadd(y, sy);
+      z = fadd(z, sz);
+    }
+  }
+  a.out[o] = out;
+}
+
+int launch_depth(const DrrArgs& a, int nearest, cudaStream_t st)
+{
+  if (!a.n_projs)
+    return XRC_OK;
+  const uint32_t tiles = ((a.cols + 15u) / 16u) * ((a.rows + 15u) / 16u);
+  if (nearest)
+    depth_kernel<true><<<a.n_projs * tiles, 256, 0, st>>>(a);
+  else
+    depth_kernel<false><<<a.n_projs * tiles, 256, 0, st>>>(a);
+  count_launch();
+  XRC_CUDA(cudaGetLastError());
+  return XRC_OK;
+}
 
 // ----------------------------------------------------------------------------
 // XRC_LAYOUT_PAX: principal-axis stacks (the default layout)

@@ -471,3 +471,39 @@ class RayCasterLineIntCUDA:
             self.close()
         except Exception:
             pass
+
+
+kRAY_CAST_MAX_DEPTH = 1.0e37   # xregRayCastInterface.h:601
+
+
+class RayCasterDepthCUDA(RayCasterLineIntCUDA):
+    """RayCasterDepthCPU (lib/ray_cast/xregRayCastDepthCPU.{h,cpp}) + RayCasterCollisionParamInterface
+    (xregRayCastInterface.h:436-475, .cpp:352-371): every pixel gets the depth -- distance from the pinhole in the camera
+    frame -- of the first sample along its ray whose interpolated value reaches render_thresh(), refined by
+    num_backtracking_steps() halvings of the step; combined with min on top of the background, which defaults to
+    kRAY_CAST_MAX_DEPTH (the class's constructor, xregRayCastDepthCPU.cpp:231-234).  Linear or nearest-neighbour
+    interpolation.  Same volumes / cameras / poses / store methods as the line-integral ray caster."""
+
+    def __init__(self, ctx: Context, layout: str = "default"):
+        super().__init__(ctx, layout)
+        self.set_default_bg_pixel_val(kRAY_CAST_MAX_DEPTH)
+        self._render_thresh = 150.0          # xregRayCastInterface.cpp:427-428
+        self._num_backtracking_steps = 0
+
+    def set_render_thresh(self, t: float) -> None:
+        self._render_thresh = float(t)
+
+    def render_thresh(self) -> float:
+        return self._render_thresh
+
+    def set_num_backtracking_steps(self, n: int) -> None:
+        self._num_backtracking_steps = int(n)
+
+    def num_backtracking_steps(self) -> int:
+        return self._num_backtracking_steps
+
+    def compute(self, vol_idx: int = 0) -> None:
+        if not self._resources_allocated:
+            raise _lib.XregError("compute: resources not allocated (xregRayCastDepthCPU.cpp:238)")
+        self._flush()
+        check(self._lib.xrc_rc_compute_depth(self.handle, int(vol_idx), self._render_thresh, self._num_backtracking_steps))
