@@ -215,6 +215,20 @@ void xreg::RayCasterLineIntCUDA::compute(const size_type vol_idx)
   sync_to_host_.set_modified();
 }
 
+xreg::RayCasterDepthCUDA::RayCasterDepthCUDA(xrc_ctx* ctx) : RayCasterLineIntCUDA(ctx)
+{
+  this->default_bg_pixel_val_ = kRAY_CAST_MAX_DEPTH;  // as RayCasterDepthCPU::RayCasterDepthCPU (xregRayCastDepthCPU.cpp:231-234)
+}
+
+void xreg::RayCasterDepthCUDA::compute(const size_type vol_idx)
+{
+  xregASSERT(this->resources_allocated_);
+  push_params_and_poses();
+  CheckXRC(xrc_rc_compute_depth(handle(), static_cast<uint32_t>(vol_idx), this->render_thresh(),
+                                static_cast<uint32_t>(this->num_backtracking_steps())));
+  sync_to_host_buf().set_modified();
+}
+
 xreg::RayCaster::ProjPtr xreg::RayCasterLineIntCUDA::proj(const size_type proj_idx)
 {
   sync_to_host_.sync();

@@ -84,9 +84,13 @@ protected:
 
   void camera_models_changed() override;
 
-private:
+protected:
+  /// flattens the RayCaster state into the library (parameters, poses, background flag): what compute() does first
   void push_params_and_poses();
 
+  RayCastSyncHostBufFromCUDA& sync_to_host_buf() { return sync_to_host_; }
+
+private:
   xrc_ctx* ctx_ = nullptr;
   xrc_rc* rc_ = nullptr;
 
@@ -94,6 +98,18 @@ private:
 
   std::vector<float> tmp_poses_;      // num_projs x 12, row-major
   std::vector<uint32_t> tmp_cam_idx_;
+};
+
+/// RayCasterDepthCUDA -- the CUDA counterpart of RayCasterDepthCPU (lib/ray_cast/xregRayCastDepthCPU.{h,cpp}): the depth
+/// of the first sample along every ray whose interpolated value reaches render_thresh(), refined by
+/// num_backtracking_steps() halvings of the step, min-combined with the background (kRAY_CAST_MAX_DEPTH by default).
+/// Volumes, cameras, poses, store methods and the host hand-off are the line-integral adapter's.
+class RayCasterDepthCUDA : public RayCasterLineIntCUDA, public RayCasterCollisionParamInterface
+{
+public:
+  explicit RayCasterDepthCUDA(xrc_ctx* ctx);
+
+  void compute(const size_type vol_idx = 0) override;
 };
 
 }  // namespace xreg

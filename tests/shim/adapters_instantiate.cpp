@@ -18,6 +18,20 @@ std::shared_ptr<xreg::RayCaster> MakeLineIntRayCaster(xrc_ctx* ctx)
   return rc;
 }
 
+// the depth ray caster behind the reference's base class and its collision-parameter mix-in
+// (RayCasterDepthCPU : RayCasterCPU, RayCasterCollisionParamInterface)
+std::shared_ptr<xreg::RayCaster> MakeDepthRayCaster(xrc_ctx* ctx)
+{
+  auto rc = std::make_shared<xreg::RayCasterDepthCUDA>(ctx);
+  rc->set_render_thresh(200);
+  rc->set_num_backtracking_steps(8);
+  if (auto* coll = dynamic_cast<xreg::RayCasterCollisionParamInterface*>(rc.get()))
+  {
+    coll->set_render_thresh(coll->render_thresh() + 1);
+  }
+  return rc;
+}
+
 std::shared_ptr<xreg::ImgSimMetric2D> MakeSimMetric(xrc_ctx* ctx, const int which)
 {
   switch (which)
@@ -35,6 +49,15 @@ float UseThroughTheReferenceInterfaces(xrc_ctx* ctx, xreg::RayCaster::VolPtr vol
                                        xreg::ImgSimMetric2D::ImagePtr fixed, xreg::ImgSimMetric2D::ImageMaskPtr mask,
                                        const xreg::FrameTransformList& poses)
 {
+  {
+    auto depth = MakeDepthRayCaster(ctx);
+    depth->set_volume(vol);
+    depth->set_camera_model(cam);
+    depth->set_num_projs(poses.size());
+    depth->allocate_resources();
+    depth->set_xforms_cam_to_itk_phys(poses);
+    depth->compute();
+  }
   auto rc = MakeLineIntRayCaster(ctx);
   rc->set_volume(vol);
   rc->set_camera_model(cam);
