@@ -575,7 +575,7 @@ def main():
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": w["desc"], "global_batch": pop_n, "views": n_views,
                            "projections_per_gpu_per_step": shares,
-                           "parallelism": (("detector tiles sharded x%d round robin: every GPU ray casts its tiles of ALL projections "
+                           "parallelism": (("detector tiles sharded x%d (contiguous ranges of the row-major tile list, cut by measured work and corrected by the clock): every GPU ray casts its tiles of ALL projections "
                                             "and stores them into their owners' buffers over NVLink (peer stores from the DRR "
                                             "kernel, CUDA IPC); the (view, pose) list is cut into contiguous balanced chunks for "
                                             "the metrics; barrier + all-gather of the scalars (%s); volume and fixed images "
