@@ -390,7 +390,26 @@ def main():
             return float(ms.item())
 
         tiles = world > 1 and args.shard in ("tiles", "tiles-nccl")
-        sharded = regi.ShardedDeviceObjFn(fn, rank, world, mode=args.shard) if world > 1 else None
+        sharded, shard_note = None, None
+        if world > 1:
+            # tile sharding maps every rank's projection buffer into every other rank (CUDA IPC): if a box does not allow
+            # that (all ranks must agree), fall back to sharding the poses -- same values, the NCCL path
+            ok = torch.ones(1, dtype=torch.float32, device=dev)
+            try:
+                sharded = regi.ShardedDeviceObjFn(fn, rank, world, mode=args.shard)
+                if os.environ.get("XRC_BENCH_FORCE_IPC_FAIL") and tiles and rank == world - 1:
+                    raise RuntimeError("forced (XRC_BENCH_FORCE_IPC_FAIL)")     # exercises the fall-back on one rank
+            except Exception as exc:   # noqa: BLE001
+                ok.zero_()
+                shard_note = "tile sharding unavailable on this box (%s): fell back to sharding the poses" % str(exc)[:200]
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if float(ok.item()) < 1.0:
+                if sharded is not None and tiles:
+                    fn.rc.peer_detach()
+                if shard_note is None:
+                    shard_note = "tile sharding unavailable on another rank: fell back to sharding the poses"
+                args.shard, tiles = "poses", False
+                sharded = regi.ShardedDeviceObjFn(fn, rank, world, mode="poses")
         flag = torch.zeros(1, dtype=torch.float32, device=dev)
 
         def make_tile_step():
@@ -584,7 +603,7 @@ def main():
                                            ("(view, pose) list sharded x%d (contiguous balanced chunks), volume and fixed "
                                             "images replicated, per-view scalars all-gathered (NCCL)" % world)) if world > 1
                                           else "one GPU",
-                           "shard": (args.shard if world > 1 else None),
+                           "shard": (args.shard if world > 1 else None), "shard_note": shard_note,
                            "tile_plan": ({"bounds": tile_plan, "clock_feedback_rounds": args.balance,
                                           "drr_ms_per_rank_before_last_cut": getattr(sharded, "last_balance_ms", None)}
                                          if tiles else None),
