@@ -114,6 +114,16 @@ int xrc_rc_volume_bytes(const xrc_rc* rc, uint64_t* bytes);
 /* The layout volume vol_idx really uses (XRC_LAYOUT_*): with XRC_LAYOUT_DEFAULT the library chooses the principal-axis
  * stacks and falls back to one XY-quad stack when the record index does not fit 32 bits or device memory runs out. */
 int xrc_rc_volume_layout(const xrc_rc* rc, uint32_t vol_idx, int* layout);
+/* Log remap of a projection (pre-processing): ImageIntensLogTransFilter
+ * (lib/image/xregImageIntensLogTrans.{h,cpp}; what ProjPreProc applies to every fluoroscopic image,
+ * lib/image/xregProjPreProc.cpp:63-84) on the device: out = -log(x / I0) for x > 1e-6, and the value of the smallest such
+ * pixel for the others.  normalize_zero_one: the image is scaled by 1 / max first (SetNormalizeZeroOne);
+ * use_max_intensity_as_I0 (the filter's default): I0 = the maximum of the image smoothed by a discrete Gaussian of
+ * variance 2 (itk::DiscreteGaussianImageFilter -- ITK is an un-vendored dependency of the reference, its published
+ * algorithm is restated), or 1 after normalisation; else the given I0 (SetI0).  host_img / host_out:
+ * rows x cols floats (may alias); I0_used (optional) returns the I0 of the map.  Synchronises. */
+int xrc_log_remap(xrc_ctx* ctx, const float* host_img, uint32_t rows, uint32_t cols, int normalize_zero_one,
+                  int use_max_intensity_as_I0, float I0, float* host_out, float* I0_used);
 /* RayCasterDepthCPU::compute (lib/ray_cast/xregRayCastDepthCPU.cpp:42-272) on this ray caster's
  * volumes, cameras and poses: per pixel the depth -- distance from the pinhole, in the camera frame -- of the first sample
  * along the (unlimited) ray whose interpolated value is >= collision_thresh, refined by num_backtracking_steps halvings

@@ -814,6 +814,38 @@ def itk_slices():
     return out
 
 
+LOG_WRAPPER = r"""
+// set_* + Update() of the filter on a caller's image; the DiscreteGaussianImageFilter inside is the installed call-out
+extern "C" void xref_log_remap_set_gaussian(xref_gaussian_fn fn) { g_xref_gaussian = fn; }
+
+extern "C" void xref_log_remap(const float* img, uint32_t rows, uint32_t cols, int normalize_zero_one,
+                               int use_max_intensity_as_I0, float I0, float* out)
+{
+  itk::Image<float, 2> in;
+  in.region.rows = rows;
+  in.region.cols = cols;
+  in.ext = img;
+  xreg::ImageIntensLogTransFilter f;
+  f.in = &in;
+  f.normalize_zero_one_ = normalize_zero_one != 0;
+  f.use_max_intensity_as_I0_ = use_max_intensity_as_I0 != 0;
+  f.I0_ = I0;
+  f.GenerateData();
+  const float* o = static_cast<const itk::Image<float, 2>&>(f.out).GetBufferPointer();
+  std::copy(o, o + (std::size_t)rows * cols, out);
+}
+"""
+
+
+def log_slices():
+    rel = "lib/image/xregImageIntensLogTrans.cpp"
+    ln = _lines(rel)
+    s, e = _cut_function(ln, r"^void xreg::ImageIntensLogTransFilter::GenerateData\(\)")
+    body = ln[s:e + 1]
+    assert any("min_pos" in x for x in body) and any("DiscreteGaussianImageFilter" in x for x in body)
+    return [(rel, s, e, ["#include <cstdint>"] + body)]
+
+
 UNITS = (
     # (library, prelude header, slice list function, C ABI wrapper)
     ("libxreg_refslice.so", "ref_pin_prelude.h", slices, WRAPPER),
@@ -824,7 +856,9 @@ UNITS = (
     ("libxreg_refslice_se3.so", "ref_pin_se3_prelude.h", se3_slices, SE3_WRAPPER),
     ("libxreg_refslice_cam.so", "ref_pin_cam_prelude.h", cam_slices, CAM_WRAPPER),
     ("libxreg_refslice_itk.so", "ref_pin_itk_prelude.h", itk_slices, ITK_WRAPPER),
+    ("libxreg_refslice_log.so", "ref_pin_log_prelude.h", log_slices, LOG_WRAPPER),
 )
+LOG_LIB = os.path.join(OUT_DIR, "libxreg_refslice_log.so")
 ITK_LIB = os.path.join(OUT_DIR, "libxreg_refslice_itk.so")
 CAM_LIB = os.path.join(OUT_DIR, "libxreg_refslice_cam.so")
 SE3_LIB = os.path.join(OUT_DIR, "libxreg_refslice_se3.so")

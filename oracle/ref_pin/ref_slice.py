@@ -342,3 +342,37 @@ def itk_volume_geometry(dims, origin, spacing, direction):
     DP = C.POINTER(C.c_double)
     il.xref_itk_volume_geometry(d, o.ctypes.data_as(DP), sp.ctypes.data_as(DP), dr.ctypes.data_as(DP), _fp(mn), _fp(mx), _fp(a))
     return mn, mx, a
+
+
+# ---- the reference's log remap (oracle/_ref/libxreg_refslice_log.so) ------------------------------------------------------
+_llib = None
+_gauss_keep = []
+
+
+def log_lib():
+    global _llib
+    if _llib is None:
+        lib()   # (re)builds every unit where the reference exists
+        _llib = C.CDLL(build_ref_slice.LOG_LIB)
+    return _llib
+
+
+def log_remap(img, normalize_zero_one=False, use_max_intensity_as_I0=True, I0=1.0, gaussian=None):
+    """ImageIntensLogTransFilter::GenerateData, the reference's lines; `gaussian(img2d, variance) -> img2d` is installed as
+    the itk::DiscreteGaussianImageFilter call-out (ITK itself is absent)."""
+    img = _f32(img)
+    rows, cols = img.shape
+    GFN = C.CFUNCTYPE(None, C.POINTER(C.c_float), C.c_uint, C.c_uint, C.c_double, C.POINTER(C.c_float))
+
+    def cb(pin, r, c, var, pout):
+        a = np.ctypeslib.as_array(pin, shape=(r, c)).copy()
+        o = np.ascontiguousarray(gaussian(a, var), dtype=np.float32)
+        np.ctypeslib.as_array(pout, shape=(r, c))[:] = o
+
+    fn = GFN(cb)
+    _gauss_keep.append(fn)
+    log_lib().xref_log_remap_set_gaussian(fn)
+    out = np.empty_like(img)
+    log_lib().xref_log_remap(_fp(img), C.c_uint32(rows), C.c_uint32(cols), C.c_int(1 if normalize_zero_one else 0),
+                             C.c_int(1 if use_max_intensity_as_I0 else 0), C.c_float(I0), _fp(out))
+    return out

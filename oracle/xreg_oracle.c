@@ -631,6 +631,202 @@ int xo_depth(const float* vol, const uint64_t dims[3], const float idx_to_phys[1
   return 0;
 }
 
+/* ---- log remap of a projection (pre-processing) -------------------------------------------------
+ * ImageIntensLogTransFilter::GenerateData (lib/image/xregImageIntensLogTrans.cpp:55-144) is restated line by line
+ * (xo_log_remap) and pinned to the reference's own lines (tests/test_oracle_ref_slice.py).  Its default path takes I0 from
+ * the maximum of the image smoothed by itk::DiscreteGaussianImageFilter (variance 2, :97-105): that filter is ITK 5.1.1, an
+ * un-vendored dependency -- its published algorithm is restated below and is PARITY UNPINNED (nothing of ITK can be run
+ * here): itk::GaussianOperator::GenerateCoefficients (discrete Gaussian e^-t I_n(t) from the modified Bessel functions, the
+ * Abramowitz & Stegun 9.8.1-9.8.4 polynomials and the downward recurrence with accuracy 40, summed until 1 - max error,
+ * at most 32 wide, normalised), applied per dimension (y first, then x: the filter assigns the operators in reverse
+ * order) with a zero-flux Neumann boundary, double accumulation in kernel order, a float image between the passes. */
+static double itk_bessel_i0(double y)
+{
+  const double d = fabs(y);
+  if (d < 3.75)
+  {
+    double m = y / 3.75;
+    m *= m;
+    return 1.0 + m * (3.5156229 + m * (3.0899424 + m * (1.2067492 + m * (0.2659732 + m * (0.360768e-1 + m * 0.45813e-2)))));
+  }
+  const double m = 3.75 / d;
+  return (exp(d) / sqrt(d)) *
+         (0.39894228 + m * (0.1328592e-1 + m * (0.225319e-2 + m * (-0.157565e-2 + m * (0.916281e-2 + m * (-0.2057706e-1 +
+          m * (0.2635537e-1 + m * (-0.1647633e-1 + m * 0.392377e-2))))))));
+}
+
+static double itk_bessel_i1(double y)
+{
+  const double d = fabs(y);
+  double acc;
+  if (d < 3.75)
+  {
+    double m = y / 3.75;
+    m *= m;
+    acc = d * (0.5 + m * (0.87890594 + m * (0.51498869 + m * (0.15084934 + m * (0.2658733e-1 + m * (0.301532e-2 + m * 0.32411e-3))))));
+  }
+  else
+  {
+    const double m = 3.75 / d;
+    acc = 0.2282967e-1 + m * (-0.2895312e-1 + m * (0.1787654e-1 - m * 0.420059e-2));
+    acc = 0.39894228 + m * (-0.3988024e-1 + m * (-0.362018e-2 + m * (0.163801e-2 + m * (-0.1031555e-1 + m * acc))));
+    acc *= (exp(d) / sqrt(d));
+  }
+  return (y < 0.0) ? -acc : acc;
+}
+
+static double itk_bessel_i(int n, double y)
+{
+  const double ACCURACY = 40.0;
+  if (y == 0.0)
+    return 0.0;
+  const double toy = 2.0 / fabs(y);
+  double qip = 0.0, acc = 0.0, qi = 1.0;
+  for (int j = 2 * (n + (int)sqrt(ACCURACY * n)); j > 0; j--)
+  {
+    const double qim = qip + j * toy * qi;
+    qip = qi;
+    qi = qim;
+    if (fabs(qi) > 1.0e10)
+    {
+      acc *= 1.0e-10;
+      qi *= 1.0e-10;
+      qip *= 1.0e-10;
+    }
+    if (j == n)
+      acc = qip;
+  }
+  acc *= itk_bessel_i0(y) / qi;
+  return (y < 0.0 && (n & 1)) ? -acc : acc;
+}
+
+/* coeffs[0 .. 2 radius]: the symmetric kernel; returns the radius (<= max_width) */
+int xo_itk_gaussian_coeffs(double variance, double max_error, int max_width, double* coeffs)
+{
+  double half[80];
+  const double et = exp(-variance), cap = 1.0 - max_error;
+  int n = 0;
+  half[n++] = et * itk_bessel_i0(variance);
+  double sum = half[0];
+  half[n++] = et * itk_bessel_i1(variance);
+  sum += half[1] * 2.0;
+  for (int i = 2; sum < cap; i++)
+  {
+    half[n++] = et * itk_bessel_i(i, variance);
+    sum += half[i] * 2.0;
+    if (half[i] <= 0.0)
+      break;
+    if (n > max_width || n >= 79)
+      break;
+  }
+  for (int i = 0; i < n; ++i)
+    half[i] /= sum;
+  const int r = n - 1;
+  for (int i = 0; i <= r; ++i)
+  {
+    coeffs[r + i] = half[i];
+    coeffs[r - i] = half[i];
+  }
+  return r;
+}
+
+void xo_itk_discrete_gaussian_2d(const float* img, uint32_t rows, uint32_t cols, double variance, float* out)
+{
+  double k[160];
+  const int r = xo_itk_gaussian_coeffs(variance, 0.01, 32, k);
+  float* tmp = (float*)malloc(sizeof(float) * (size_t)rows * cols);
+  for (int64_t y = 0; y < (int64_t)rows; ++y)   /* first filter: along y */
+    for (int64_t x = 0; x < (int64_t)cols; ++x)
+    {
+      double s = 0.0;
+      for (int i = 0; i <= 2 * r; ++i)
+      {
+        int64_t yy = y + i - r;
+        yy = yy < 0 ? 0 : (yy > (int64_t)rows - 1 ? (int64_t)rows - 1 : yy);
+        s += k[i] * (double)img[(size_t)yy * cols + x];
+      }
+      tmp[(size_t)y * cols + x] = (float)s;
+    }
+  for (int64_t y = 0; y < (int64_t)rows; ++y)   /* last filter: along x */
+    for (int64_t x = 0; x < (int64_t)cols; ++x)
+    {
+      double s = 0.0;
+      for (int i = 0; i <= 2 * r; ++i)
+      {
+        int64_t xx = x + i - r;
+        xx = xx < 0 ? 0 : (xx > (int64_t)cols - 1 ? (int64_t)cols - 1 : xx);
+        s += k[i] * (double)tmp[(size_t)y * cols + xx];
+      }
+      out[(size_t)y * cols + x] = (float)s;
+    }
+  free(tmp);
+}
+
+/* ImageIntensLogTransFilter::GenerateData (lib/image/xregImageIntensLogTrans.cpp:55-144).  smoothed: the output of the
+ * DiscreteGaussianImageFilter call (:97-103) when use_max_intensity_as_I0 and not normalize_zero_one, else unused (NULL:
+ * computed with the restatement above).  I0_used (optional) returns the I0 of the log map. */
+void xo_log_remap(const float* img, uint32_t rows, uint32_t cols, int normalize_zero_one, int use_max_intensity_as_I0,
+                  float I0, const float* smoothed, float* out, float* I0_used)
+{
+  const float eps = 1.0e-6f;
+  const size_t n = (size_t)rows * cols;
+  float I0_to_use = I0;
+  const float* src = img;
+  if (normalize_zero_one)
+  {
+    float mx = img[0];
+    for (size_t i = 1; i < n; ++i)
+      mx = (mx < img[i]) ? img[i] : mx; /* std::max_element */
+    const float scale = 1.0f / mx;
+    for (size_t i = 0; i < n; ++i)
+      out[i] = img[i] * scale;
+    src = out;
+    if (use_max_intensity_as_I0)
+      I0_to_use = 1.0f;
+  }
+  else if (use_max_intensity_as_I0)
+  {
+    float* own = NULL;
+    if (!smoothed)
+    {
+      own = (float*)malloc(sizeof(float) * n);
+      xo_itk_discrete_gaussian_2d(img, rows, cols, 2.0, own);
+      smoothed = own;
+    }
+    float mx = smoothed[0];
+    for (size_t i = 1; i < n; ++i)
+      mx = (mx < smoothed[i]) ? smoothed[i] : mx;
+    I0_to_use = mx;
+    free(own);
+  }
+  float min_pos = 0.0f;
+  int found = 0;
+  for (size_t i = 0; i < n; ++i)
+  {
+    if (src[i] > eps)
+    {
+      if (found)
+      {
+        if (min_pos > src[i])
+          min_pos = src[i];
+      }
+      else
+      {
+        min_pos = src[i];
+        found = 1;
+      }
+    }
+  }
+  const float out_max_val = -logf(min_pos / I0_to_use);
+  for (size_t i = 0; i < n; ++i)
+  {
+    const float x = src[i];
+    out[i] = (x > eps) ? -logf(x / I0_to_use) : out_max_val;
+  }
+  if (I0_used)
+    *I0_used = I0_to_use;
+}
+
 /* HUToLinAttFilter::GenerateData (lib/image/xregHUToLinAtt.cpp:45-69; constants xregHUToLinAtt.h:73-76) */
 void xo_hu_to_lin_att(const float* hu, float* att, uint64_t n, float hu_lower)
 {

@@ -140,6 +140,13 @@ int xo_depth(const float* vol, const uint64_t dims[3], const float idx_to_phys[1
              float step_size, int interp, float collision_thresh, uint32_t num_backtracking_steps,
              float* buf, int n_threads);
 
+/* Log remap of a projection: ImageIntensLogTransFilter::GenerateData (lib/image/xregImageIntensLogTrans.cpp:55-144), and
+ * the ITK smoothing behind its default I0 (itk::DiscreteGaussianImageFilter, restated; PARITY UNPINNED for that piece). */
+int xo_itk_gaussian_coeffs(double variance, double max_error, int max_width, double* coeffs);
+void xo_itk_discrete_gaussian_2d(const float* img, uint32_t rows, uint32_t cols, double variance, float* out);
+void xo_log_remap(const float* img, uint32_t rows, uint32_t cols, int normalize_zero_one, int use_max_intensity_as_I0,
+                  float I0, const float* smoothed, float* out, float* I0_used);
+
 /* ITK LinearInterpolateImageFunction::EvaluateOptimized(Dispatch<3>) restated. */
 double xo_interp_linear(const float* vol, const uint64_t dims[3], const float x[3]);
 /* ITK NearestNeighborInterpolateImageFunction::EvaluateAtContinuousIndex restated. */

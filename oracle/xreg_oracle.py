@@ -226,6 +226,27 @@ def depth(vol, idx_to_phys, cams, poses, cam_idx=None, step_size=1.0, interp=0, 
     return buf
 
 
+def itk_discrete_gaussian_2d(img, variance):
+    """itk::DiscreteGaussianImageFilter (UseImageSpacing off, max error 0.01, max kernel width 32) restated; PARITY
+    UNPINNED (ITK is absent)."""
+    img = _f32(img)
+    out = np.empty_like(img)
+    lib().xo_itk_discrete_gaussian_2d(_fp(img), C.c_uint32(img.shape[0]), C.c_uint32(img.shape[1]), C.c_double(variance), _fp(out))
+    return out
+
+
+def log_remap(img, normalize_zero_one=False, use_max_intensity_as_I0=True, I0=1.0, smoothed=None):
+    """ImageIntensLogTransFilter (lib/image/xregImageIntensLogTrans.cpp:55-144).  Returns (out, I0 used)."""
+    img = _f32(img)
+    out = np.empty_like(img)
+    i0 = C.c_float(0)
+    sm = None if smoothed is None else _f32(smoothed)
+    lib().xo_log_remap(_fp(img), C.c_uint32(img.shape[0]), C.c_uint32(img.shape[1]), C.c_int(1 if normalize_zero_one else 0),
+                       C.c_int(1 if use_max_intensity_as_I0 else 0), C.c_float(I0), None if sm is None else _fp(sm), _fp(out),
+                       C.byref(i0))
+    return out, np.float32(i0.value)
+
+
 def interp_linear(vol, x):
     vol = _f32(vol)
     nz, ny, nx = vol.shape

@@ -1,0 +1,43 @@
+"""GPU parity of the projection pre-processing: xrc_log_remap against the oracle's xo_log_remap, which
+is pinned bit for bit to the reference's ImageIntensLogTransFilter::GenerateData lines (tests/test_oracle_ref_slice.py)."""
+import numpy as np
+import pytest
+
+import xreg_b200
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+
+
+def _ulps(a, b):
+    ia, ib = a.view(np.int32).astype(np.int64), b.view(np.int32).astype(np.int64)
+    return np.abs(ia - ib)
+
+
+@pytest.mark.parametrize("shape", [(3, 5), (64, 80), (257, 301), (480, 480)])
+def test_log_remap_matches_the_oracle(ctx, xo, shape):
+    """I0 (the maximum of the smoothed image: the device runs the same restated ITK smoothing, double accumulation in tap
+    order) and the value given to the non-positive pixels are bit-equal; the map itself is -log(x / I0) rounded once from a
+    double logarithm, which equals glibc's logf except for rare last-bit cases (tolerance: 1 ulp)."""
+    rng = np.random.default_rng(shape[0] * 1000 + shape[1])
+    img = (rng.uniform(0.0, 4000.0, shape) * (rng.random(shape) < 0.93)).astype(f32)
+    img[rng.integers(0, shape[0]), rng.integers(0, shape[1])] = f32(5.0e-7)   # below eps
+    for norm, use_max, i0 in ((False, True, 1.0), (True, True, 1.0), (False, False, 4096.0), (True, False, 2.5)):
+        want, want_i0 = xo.log_remap(img, norm, use_max, i0)
+        got, got_i0 = xreg_b200.log_remap(ctx, img, norm, use_max, i0)
+        assert got_i0.tobytes() == want_i0.tobytes(), (norm, use_max)
+        assert np.all(np.isfinite(got))
+        d = _ulps(got, want)
+        assert d.max() <= 1, d.max()
+        assert np.count_nonzero(d) <= max(2, got.size // 1000)
+        low = img * (f32(1.0) / img.max() if norm else f32(1.0)) <= f32(1.0e-6)
+        assert got[low].tobytes() == want[low].tobytes()      # the value of the smallest positive pixel
+
+
+def test_log_remap_all_dark_and_errors(ctx, xo):
+    img = np.zeros((8, 9), f32)
+    want, _ = xo.log_remap(img, False, False, 1.0)
+    got, _ = xreg_b200.log_remap(ctx, img, False, False, 1.0)
+    assert np.array_equal(got, want) and np.all(np.isinf(got))     # min_pos stays 0 (:112): -log(0)
+    with pytest.raises(xreg_b200.XregError):
+        xreg_b200.log_remap(ctx, np.zeros((0, 4), f32))

@@ -474,3 +474,30 @@ def test_volume_geometry_is_the_reference_code():
         vol = Volume(np.zeros((1, 1, 1), f32), spacing=tuple(spacing), origin=tuple(origin), direction=D)
         assert np.asarray(vol.idx_to_phys(), f32).tobytes() == a.tobytes()
         assert np.array_equal(mn, np.zeros(3, f32)) and np.array_equal(mx, (np.array(dims) - 1).astype(f32))
+
+
+# ---- log remap of a projection -------------------------------------------------------------------------
+@pytest.mark.parametrize("seed", range(10))
+def test_oracle_log_remap_equals_the_reference_filter_code(xo, seed):
+    """ImageIntensLogTransFilter::GenerateData (lib/image/xregImageIntensLogTrans.cpp:55-144), the reference's own lines,
+    against xo_log_remap, bit for bit, in its three modes: normalise to [0, 1]; I0 = max of the smoothed image (the
+    DiscreteGaussianImageFilter is a call-out: ITK is absent, the oracle's restatement of it is installed -- that piece
+    is unpinned); a given I0.  Zeros and sub-eps pixels take the value of the smallest positive pixel."""
+    rng = np.random.default_rng(500 + seed)
+    rows, cols = int(rng.integers(3, 60)), int(rng.integers(3, 70))
+    img = (rng.uniform(0.0, 4000.0, (rows, cols)) * (rng.random((rows, cols)) < 0.9)).astype(f32)
+    img[rng.integers(0, rows), rng.integers(0, cols)] = f32(5.0e-7)     # below eps
+    if seed % 3 == 0:
+        img *= f32(1.0e-3)
+    calls = []
+
+    def gauss(a, var):
+        calls.append(var)
+        return xo.itk_discrete_gaussian_2d(a, var)
+
+    for norm, use_max, i0 in ((False, True, 1.0), (True, True, 1.0), (False, False, 4096.0), (True, False, 2.5)):
+        want = ref_slice.log_remap(img, norm, use_max, i0, gaussian=gauss)
+        got, _ = xo.log_remap(img, norm, use_max, i0)
+        assert got.tobytes() == want.tobytes(), (norm, use_max, i0)
+        assert np.all(np.isfinite(got)) and got.max() == got[img <= 1.0e-6].max()
+    assert calls == [2.0]      # only the default mode smooths, with variance 2 (:100)

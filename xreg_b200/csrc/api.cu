@@ -1420,6 +1420,184 @@ int xrc_rc_set_cta_order(xrc_rc* rc, int order)
   return XRC_OK;
 }
 
+// ---------------------------------------------------------------- projection pre-processing
+// itk::GaussianOperator<double>::GenerateCoefficients (ITK 5.1.1, restated: discrete Gaussian e^-t I_n(t) from the modified
+// Bessel functions -- Abramowitz & Stegun 9.8.1-9.8.4 polynomials, downward recurrence with accuracy 40 --, summed until
+// 1 - max error, at most max_width wide, normalised).  Returns the radius; k[0 .. 2 radius].
+static double itk_bessel_i0(double y)
+{
+  const double d = fabs(y);
+  if (d < 3.75)
+  {
+    double m = y / 3.75;
+    m *= m;
+    return 1.0 + m * (3.5156229 + m * (3.0899424 + m * (1.2067492 + m * (0.2659732 + m * (0.360768e-1 + m * 0.45813e-2)))));
+  }
+  const double m = 3.75 / d;
+  return (exp(d) / sqrt(d)) *
+         (0.39894228 + m * (0.1328592e-1 + m * (0.225319e-2 + m * (-0.157565e-2 + m * (0.916281e-2 + m * (-0.2057706e-1 +
+          m * (0.2635537e-1 + m * (-0.1647633e-1 + m * 0.392377e-2))))))));
+}
+static double itk_bessel_i1(double y)
+{
+  const double d = fabs(y);
+  double acc;
+  if (d < 3.75)
+  {
+    double m = y / 3.75;
+    m *= m;
+    acc = d * (0.5 + m * (0.87890594 + m * (0.51498869 + m * (0.15084934 + m * (0.2658733e-1 + m * (0.301532e-2 + m * 0.32411e-3))))));
+  }
+  else
+  {
+    const double m = 3.75 / d;
+    acc = 0.2282967e-1 + m * (-0.2895312e-1 + m * (0.1787654e-1 - m * 0.420059e-2));
+    acc = 0.39894228 + m * (-0.3988024e-1 + m * (-0.362018e-2 + m * (0.163801e-2 + m * (-0.1031555e-1 + m * acc))));
+    acc *= (exp(d) / sqrt(d));
+  }
+  return (y < 0.0) ? -acc : acc;
+}
+static double itk_bessel_i(int n, double y)
+{
+  if (y == 0.0)
+    return 0.0;
+  const double toy = 2.0 / fabs(y);
+  double qip = 0.0, acc = 0.0, qi = 1.0;
+  for (int j = 2 * (n + (int)sqrt(40.0 * n)); j > 0; j--)
+  {
+    const double qim = qip + j * toy * qi;
+    qip = qi;
+    qi = qim;
+    if (fabs(qi) > 1.0e10)
+    {
+      acc *= 1.0e-10;
+      qi *= 1.0e-10;
+      qip *= 1.0e-10;
+    }
+    if (j == n)
+      acc = qip;
+  }
+  acc *= itk_bessel_i0(y) / qi;
+  return (y < 0.0 && (n & 1)) ? -acc : acc;
+}
+static int itk_gaussian_coeffs(double variance, double max_error, int max_width, double* k)
+{
+  double half[40];
+  const double et = exp(-variance), cap = 1.0 - max_error;
+  int n = 0;
+  half[n++] = et * itk_bessel_i0(variance);
+  double sum = half[0];
+  half[n++] = et * itk_bessel_i1(variance);
+  sum += half[1] * 2.0;
+  for (int i = 2; sum < cap; i++)
+  {
+    half[n++] = et * itk_bessel_i(i, variance);
+    sum += half[i] * 2.0;
+    if (half[i] <= 0.0 || n > max_width || n >= 33)
+      break;
+  }
+  for (int i = 0; i < n; ++i)
+    half[i] /= sum;
+  const int r = n - 1;
+  for (int i = 0; i <= r; ++i)
+    k[r + i] = k[r - i] = half[i];
+  return r;
+}
+
+// ImageIntensLogTransFilter::GenerateData (lib/image/xregImageIntensLogTrans.cpp:55-144) on the device
+int xrc_log_remap(xrc_ctx* ctx, const float* host_img, uint32_t rows, uint32_t cols, int normalize_zero_one,
+                  int use_max_intensity_as_I0, float I0, float* host_out, float* I0_used)
+{
+  XRC_CHECK_ARG(ctx && host_img && host_out && rows > 0 && cols > 0, "xrc_log_remap: bad argument");
+  XRC_TRY(use_device(ctx));
+  const size_t n = (size_t)rows * cols;
+  cudaStream_t st = ctx->stream;
+  float *d_img = nullptr, *d_a = nullptr, *d_b = nullptr, *d_mm = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(d_img);
+    cudaFree(d_a);
+    cudaFree(d_b);
+    cudaFree(d_mm);
+  };
+  if (cudaMalloc(&d_img, n * sizeof(float)) != cudaSuccess || cudaMalloc(&d_a, n * sizeof(float)) != cudaSuccess ||
+      cudaMalloc(&d_b, n * sizeof(float)) != cudaSuccess || cudaMalloc(&d_mm, 2 * sizeof(float)) != cudaSuccess)
+  {
+    cleanup();
+    cudaGetLastError();
+    XRC_FAIL(XRC_ERR_NOMEM, "xrc_log_remap: out of device memory");
+  }
+  const float eps = 1.0e-6f;
+  float mm[2] = {0.f, 0.f};
+  float scale = 1.0f, I0_to_use = I0;
+  int status = XRC_OK;
+  auto sync_mm = [&]() -> int {
+    if (cudaMemcpyAsync(mm, d_mm, sizeof(mm), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+    {
+      set_error("xrc_log_remap: device failure");
+      return XRC_ERR_CUDA;
+    }
+    return XRC_OK;
+  };
+  if (cudaMemcpyAsync(d_img, host_img, n * sizeof(float), cudaMemcpyHostToDevice, st) != cudaSuccess)
+    status = XRC_ERR_CUDA;
+  if (status == XRC_OK && normalize_zero_one)
+  {
+    // scale to [0, 1] by 1 / max (:74-85); I0 = 1 when the maximum is to be I0 (:89-92)
+    status = launch_minmax(d_img, n, 1.0f, eps, d_mm, st);
+    if (status == XRC_OK)
+      status = sync_mm();
+    scale = 1.0f / mm[0];
+    if (use_max_intensity_as_I0)
+      I0_to_use = 1.0f;
+  }
+  else if (status == XRC_OK && use_max_intensity_as_I0)
+  {
+    // I0 = max of the image smoothed with a discrete Gaussian of variance 2 (:95-105)
+    ItkGaussArgs g;
+    memset(&g, 0, sizeof(g));
+    g.rows = rows;
+    g.cols = cols;
+    g.radius = itk_gaussian_coeffs(2.0, 0.01, 32, g.k);
+    g.src = d_img;
+    g.dst = d_a;
+    g.along_x = 0;
+    status = launch_itk_gauss(g, st);
+    g.src = d_a;
+    g.dst = d_b;
+    g.along_x = 1;
+    if (status == XRC_OK)
+      status = launch_itk_gauss(g, st);
+    if (status == XRC_OK)
+      status = launch_minmax(d_b, n, 1.0f, eps, d_mm, st);
+    if (status == XRC_OK)
+      status = sync_mm();
+    I0_to_use = mm[0];
+  }
+  if (status == XRC_OK)
+  {
+    // smallest pixel above eps of the (scaled) image -> what zero pixels map to (:108-133)
+    status = launch_minmax(d_img, n, scale, eps, d_mm, st);
+    if (status == XRC_OK)
+      status = sync_mm();
+  }
+  if (status == XRC_OK)
+  {
+    const volatile float q = mm[1] / I0_to_use;
+    const float out_max = -logf(q);
+    status = launch_log_map(d_img, d_a, n, scale, 1, eps, I0_to_use, out_max, st);
+  }
+  if (status == XRC_OK && (cudaMemcpyAsync(host_out, d_a, n * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                           cudaStreamSynchronize(st) != cudaSuccess))
+  {
+    set_error("xrc_log_remap: device failure");
+    status = XRC_ERR_CUDA;
+  }
+  cleanup();
+  if (status == XRC_OK && I0_used)
+    *I0_used = I0_to_use;
+  return status;
+}
+
 // ---------------------------------------------------------------- metrics
 static bool sm_is_patch_kind(int kind) { return kind == XRC_SM_PATCH_NCC || kind == XRC_SM_PATCH_GRAD_NCC; }
 

@@ -1624,6 +1624,113 @@ int launch_patch_gather(const float* vals, const uint32_t* subset, float* dst, u
   return XRC_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Log remap of a projection (pre-processing, once per fixed image): itk::DiscreteGaussianImageFilter's passes for the
+// default I0 (restated from ITK 5.1.1's published algorithm, DESIGN.md section 4.7: double accumulation over the taps in
+// kernel order, zero-flux Neumann border, float image between the passes), the two reductions, and the map itself.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) itk_gauss_kernel(const ItkGaussArgs a)
+{
+  const size_t n = (size_t)a.rows * a.cols;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+  {
+    const int64_t y = (int64_t)(i / a.cols), x = (int64_t)(i % a.cols);
+    double s = 0.0;
+    for (int t = 0; t <= 2 * a.radius; ++t)
+    {
+      int64_t yy = y, xx = x;
+      if (a.along_x)
+        xx = min(max(x + t - a.radius, (int64_t)0), (int64_t)a.cols - 1);
+      else
+        yy = min(max(y + t - a.radius, (int64_t)0), (int64_t)a.rows - 1);
+      s = __dadd_rn(s, __dmul_rn(a.k[t], (double)__ldg(a.src + (size_t)yy * a.cols + xx)));
+    }
+    a.dst[i] = (float)s;
+  }
+}
+
+int launch_itk_gauss(const ItkGaussArgs& a, cudaStream_t st)
+{
+  const size_t n = (size_t)a.rows * a.cols;
+  if (!n)
+    return XRC_OK;
+  itk_gauss_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(a);
+  count_launch();
+  XRC_CUDA(cudaGetLastError());
+  return XRC_OK;
+}
+
+__global__ void __launch_bounds__(1024) minmax_kernel(const float* __restrict__ src, uint64_t n, float scale, float eps, float* out2)
+{
+  __shared__ float s_mx[32], s_mn[32];
+  float mx = -3.402823466e+38f, mn = 3.402823466e+38f;   // mn: smallest value > eps
+  for (uint64_t i = threadIdx.x; i < n; i += 1024)
+  {
+    const float v = __fmul_rn(__ldg(src + i), scale);
+    mx = fmaxf(mx, v);
+    if (v > eps)
+      mn = fminf(mn, v);
+  }
+  for (int o = 16; o > 0; o >>= 1)
+  {
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  }
+  if ((threadIdx.x & 31) == 0)
+  {
+    s_mx[threadIdx.x >> 5] = mx;
+    s_mn[threadIdx.x >> 5] = mn;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32)
+  {
+    mx = s_mx[threadIdx.x];
+    mn = s_mn[threadIdx.x];
+    for (int o = 16; o > 0; o >>= 1)
+    {
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    }
+    if (threadIdx.x == 0)
+    {
+      out2[0] = mx;
+      out2[1] = (mn == 3.402823466e+38f) ? 0.0f : mn;   // no positive pixel: min_pos stays 0 (:112)
+    }
+  }
+}
+
+int launch_minmax(const float* src, uint64_t n, float scale, float eps, float* out2, cudaStream_t st)
+{
+  minmax_kernel<<<1, 1024, 0, st>>>(src, n, scale, eps, out2);
+  count_launch();
+  XRC_CUDA(cudaGetLastError());
+  return XRC_OK;
+}
+
+__global__ void __launch_bounds__(256) log_map_kernel(const float* __restrict__ src, float* __restrict__ dst, uint64_t n,
+                                                      float scale, int log_mode, float eps, float I0, float out_max)
+{
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+  {
+    const float v = __fmul_rn(__ldg(src + i), scale);
+    // -std::log(x / I0) in float (:140): the quotient is an IEEE division, the logarithm is evaluated in double and
+    // rounded once (glibc's logf is correctly rounded in all but rare cases; CUDA's logf is only within 1 ulp)
+    dst[i] = log_mode ? ((v > eps) ? -(float)log((double)__fdiv_rn(v, I0)) : out_max) : v;
+  }
+}
+
+int launch_log_map(const float* src, float* dst, uint64_t n, float scale, int log_mode, float eps, float I0, float out_max,
+                   cudaStream_t st)
+{
+  if (!n)
+    return XRC_OK;
+  log_map_kernel<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(src, dst, n, scale, log_mode, eps, I0,
+                                                                                         out_max);
+  count_launch();
+  XRC_CUDA(cudaGetLastError());
+  return XRC_OK;
+}
+
 int launch_patch_finalize(const PatchFinalizeArgs& a, cudaStream_t st)
 {
   if (!a.n_imgs)

@@ -122,6 +122,22 @@ int launch_patch(const PatchArgs& a, cudaStream_t st);
 int launch_patch_fixed_stats(const PatchArgs& a, cudaStream_t st);
 int launch_patch_finalize(const PatchFinalizeArgs& a, cudaStream_t st);
 
+// ---- log remap of a projection (ImageIntensLogTransFilter, lib/image/xregImageIntensLogTrans.cpp:55-144)
+struct ItkGaussArgs
+{
+  const float* src;
+  float* dst;
+  uint32_t rows, cols;
+  int radius, along_x;
+  double k[65];   // symmetric kernel, 2 radius + 1 taps (itk::GaussianOperator, max width 32)
+};
+int launch_itk_gauss(const ItkGaussArgs& a, cudaStream_t st);
+// out[0] = max over all pixels, out[1] = smallest pixel > eps (0 if none), of src * scale (scale == 1: src itself)
+int launch_minmax(const float* src, uint64_t n, float scale, float eps, float* out2, cudaStream_t st);
+// dst = src * scale (log_mode 0) or (v > eps ? -log(v / I0) : out_max) with v = src * scale (log_mode 1)
+int launch_log_map(const float* src, float* dst, uint64_t n, float scale, int log_mode, float eps, float I0, float out_max,
+                   cudaStream_t st);
+
 // Gaussian widths served by the warp-streaming gradient kernel (the reference's apps use 5; 0 = no smoothing)
 inline bool grad_fast_path(int gauss_width) { return gauss_width <= 1 || gauss_width == 3 || gauss_width == 5 || gauss_width == 7; }
 // rows per warp of the fast kernel: long bands amortise the halo rows, short bands give a small batch
