@@ -124,6 +124,18 @@ int xrc_rc_volume_layout(const xrc_rc* rc, uint32_t vol_idx, int* layout);
  * rows x cols floats (may alias); I0_used (optional) returns the I0 of the map.  Synchronises. */
 int xrc_log_remap(xrc_ctx* ctx, const float* host_img, uint32_t rows, uint32_t cols, int normalize_zero_one,
                   int use_max_intensity_as_I0, float I0, float* host_out, float* I0_used);
+/* Down-sampling of a projection image (pre-processing): DownsampleImage
+ * (lib/itk/xregITKResampleUtils.h:49-112 with the cubic B-spline default of :181-188), the image half of DownsampleProjData
+ * (lib/image/xregProjData.cpp:40-99; the camera half is DownsampleCameraModel, plain host arithmetic) that
+ * MultiLevelMultiObjRegi applies to every fixed image at every level: Gaussian smoothing with sigma (< 0: 0.5 / factor;
+ * |sigma| <= 1e-6 or factor >= 1: none), then resampling at the continuous input indices i / factor with a cubic B-spline,
+ * 0 outside the buffer; out_rows x out_cols = xrc_downsample_size (size * factor + 0.5, truncated).  All of the
+ * arithmetic is ITK 5.1.1's (DiscreteGaussianImageFilter, BSplineDecompositionImageFilter,
+ * BSplineInterpolateImageFunction, ResampleImageFilter) -- un-vendored: restated from the published algorithms,
+ * DESIGN.md section 4.8.  Synchronises. */
+int xrc_downsample_size(uint32_t rows, uint32_t cols, double factor, uint32_t* out_rows, uint32_t* out_cols);
+int xrc_downsample_image(xrc_ctx* ctx, const float* host_img, uint32_t rows, uint32_t cols, double factor, double sigma,
+                         float* host_out);
 /* RayCasterDepthCPU::compute (lib/ray_cast/xregRayCastDepthCPU.cpp:42-272) on this ray caster's
  * volumes, cameras and poses: per pixel the depth -- distance from the pinhole, in the camera frame -- of the first sample
  * along the (unlimited) ray whose interpolated value is >= collision_thresh, refined by num_backtracking_steps halvings

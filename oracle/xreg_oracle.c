@@ -827,6 +827,147 @@ void xo_log_remap(const float* img, uint32_t rows, uint32_t cols, int normalize_
     *I0_used = I0_to_use;
 }
 
+/* ---- down-sampling of a projection image (pre-processing) ------------------------------------------
+ * DownsampleImage (lib/itk/xregITKResampleUtils.h:49-112, the B-spline default of :181-188), what DownsampleProjData
+ * (lib/image/xregProjData.cpp:40-99) applies to the fixed image of every registration level: smooth with
+ * itk::DiscreteGaussianImageFilter (variance (0.5 / factor)^2, image spacing ignored) when factor < 1, then
+ * itk::ResampleImageFilter with the identity transform, the same origin / direction, spacing / factor, size
+ * (unsigned long)(size * factor + 0.5), and a cubic itk::BSplineInterpolateImageFunction.  The control flow is the
+ * reference's; ALL of the arithmetic is ITK 5.1.1's (un-vendored): restated from its published algorithms and PARITY
+ * UNPINNED -- the discrete Gaussian above; BSplineDecompositionImageFilter (Unser's recursive prefilter, pole sqrt(3) - 2,
+ * gain (1 - z)(1 - 1/z), causal initialisation truncated at tolerance 1e-10 or the full mirror sum, anti-causal
+ * initialisation z / (z^2 - 1) (z c[N-2] + c[N-1]), dimension 0 first, double coefficients); evaluation at the continuous
+ * input index i / factor (identity transform, same origin and direction) with the cubic weights
+ * w3 = w^3 / 6, w0 = 1/6 + w (w - 1) / 2 - w3, w2 = w + w0 - 2 w3, w1 = 1 - w0 - w2 - w3, support floor(x) - 1 .. + 2,
+ * mirror (whole-sample) boundary, sum over the 16 taps with dimension 0 fastest in double; pixels whose index is outside
+ * [-0.5, size - 0.5) take the default value 0; the result is cast to float.  An independent implementation of the same
+ * published algorithm (SciPy's spline_filter / map_coordinates, mode 'mirror') agrees to rounding
+ * (tests/test_oracle_metrics.py). */
+static void bspline3_prefilter_line(double* c, int64_t n)
+{
+  if (n == 1)
+    return;
+  const double z = sqrt(3.0) - 2.0;
+  const double c0 = (1.0 - z) * (1.0 - 1.0 / z);
+  for (int64_t i = 0; i < n; ++i)
+    c[i] *= c0;
+  /* causal initialisation (mirror boundaries) */
+  {
+    double zn = z, sum;
+    const int64_t horizon = (int64_t)ceil(log(1.0e-10) / log(fabs(z)));
+    if (horizon < n)
+    {
+      sum = c[0];
+      for (int64_t i = 1; i < horizon; ++i)
+      {
+        sum += zn * c[i];
+        zn *= z;
+      }
+      c[0] = sum;
+    }
+    else
+    {
+      const double iz = 1.0 / z;
+      double z2n = pow(z, (double)(n - 1));
+      sum = c[0] + z2n * c[n - 1];
+      z2n *= z2n * iz;
+      for (int64_t i = 1; i <= n - 2; ++i)
+      {
+        sum += (zn + z2n) * c[i];
+        zn *= z;
+        z2n *= iz;
+      }
+      c[0] = sum / (1.0 - zn * zn);
+    }
+  }
+  for (int64_t i = 1; i < n; ++i)
+    c[i] += z * c[i - 1];
+  c[n - 1] = (z / (z * z - 1.0)) * (z * c[n - 2] + c[n - 1]);
+  for (int64_t i = n - 2; i >= 0; --i)
+    c[i] = z * (c[i + 1] - c[i]);
+}
+
+static int64_t mirror_index(int64_t i, int64_t n)
+{
+  if (n == 1)
+    return 0;
+  if (i < 0)
+    i = -i;
+  if (i >= n)
+    i = (n - 1) - (i - (n - 1));
+  return i;
+}
+
+void xo_downsample_size(uint32_t rows, uint32_t cols, double factor, uint32_t* out_rows, uint32_t* out_cols)
+{
+  *out_cols = (uint32_t)(unsigned long)((double)cols * factor + 0.5);
+  *out_rows = (uint32_t)(unsigned long)((double)rows * factor + 0.5);
+}
+
+void xo_downsample_image(const float* img, uint32_t rows, uint32_t cols, double factor, double sigma, float* out)
+{
+  uint32_t orows, ocols;
+  xo_downsample_size(rows, cols, factor, &orows, &ocols);
+  const size_t n = (size_t)rows * cols;
+  float* sm = NULL;
+  const float* src = img;
+  if ((factor < 1.0) && (fabs(sigma) > 1.0e-6))   /* xregITKResampleUtils.h:68-86 */
+  {
+    const double s = (sigma < 0.0) ? (0.5 / factor) : sigma;
+    sm = (float*)malloc(sizeof(float) * n);
+    xo_itk_discrete_gaussian_2d(img, rows, cols, s * s, sm);
+    src = sm;
+  }
+  double* c = (double*)malloc(sizeof(double) * n);
+  for (size_t i = 0; i < n; ++i)
+    c[i] = (double)src[i];
+  for (int64_t y = 0; y < (int64_t)rows; ++y)   /* dimension 0 (x) first */
+    bspline3_prefilter_line(c + (size_t)y * cols, (int64_t)cols);
+  double* line = (double*)malloc(sizeof(double) * rows);
+  for (int64_t x = 0; x < (int64_t)cols; ++x)
+  {
+    for (int64_t y = 0; y < (int64_t)rows; ++y)
+      line[y] = c[(size_t)y * cols + x];
+    bspline3_prefilter_line(line, (int64_t)rows);
+    for (int64_t y = 0; y < (int64_t)rows; ++y)
+      c[(size_t)y * cols + x] = line[y];
+  }
+  free(line);
+  for (int64_t oy = 0; oy < (int64_t)orows; ++oy)
+    for (int64_t ox = 0; ox < (int64_t)ocols; ++ox)
+    {
+      const double xs[2] = {(double)ox / factor, (double)oy / factor};
+      const int64_t len[2] = {(int64_t)cols, (int64_t)rows};
+      float v = 0.0f;
+      if (xs[0] >= -0.5 && xs[0] < (double)cols - 0.5 && xs[1] >= -0.5 && xs[1] < (double)rows - 0.5)
+      {
+        double w[2][4];
+        int64_t idx[2][4];
+        for (int d = 0; d < 2; ++d)
+        {
+          const int64_t i0 = (int64_t)floor((float)xs[d]) - 1;
+          const double t = xs[d] - (double)(i0 + 1);
+          w[d][3] = (1.0 / 6.0) * t * t * t;
+          w[d][0] = (1.0 / 6.0) + 0.5 * t * (t - 1.0) - w[d][3];
+          w[d][2] = t + w[d][0] - 2.0 * w[d][3];
+          w[d][1] = 1.0 - w[d][0] - w[d][2] - w[d][3];
+          for (int k = 0; k < 4; ++k)
+            idx[d][k] = mirror_index(i0 + k, len[d]);
+        }
+        double acc = 0.0;
+        for (int p = 0; p < 16; ++p)   /* dimension 0 fastest */
+        {
+          const int kx = p & 3, ky = p >> 2;
+          acc += (w[0][kx] * w[1][ky]) * c[(size_t)idx[1][ky] * cols + (size_t)idx[0][kx]];
+        }
+        v = (float)acc;
+      }
+      out[(size_t)oy * ocols + ox] = v;
+    }
+  free(c);
+  free(sm);
+}
+
 /* HUToLinAttFilter::GenerateData (lib/image/xregHUToLinAtt.cpp:45-69; constants xregHUToLinAtt.h:73-76) */
 void xo_hu_to_lin_att(const float* hu, float* att, uint64_t n, float hu_lower)
 {

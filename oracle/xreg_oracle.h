@@ -147,6 +147,12 @@ void xo_itk_discrete_gaussian_2d(const float* img, uint32_t rows, uint32_t cols,
 void xo_log_remap(const float* img, uint32_t rows, uint32_t cols, int normalize_zero_one, int use_max_intensity_as_I0,
                   float I0, const float* smoothed, float* out, float* I0_used);
 
+/* DownsampleImage (lib/itk/xregITKResampleUtils.h:49-112, cubic B-spline default :181-188), what DownsampleProjData
+ * (lib/image/xregProjData.cpp:40-99) applies to a projection: ITK's Gaussian smoothing + B-spline resampling restated
+ * (PARITY UNPINNED: all of the arithmetic is ITK's).  sigma < 0: the default 0.5 / factor.  out: xo_downsample_size. */
+void xo_downsample_size(uint32_t rows, uint32_t cols, double factor, uint32_t* out_rows, uint32_t* out_cols);
+void xo_downsample_image(const float* img, uint32_t rows, uint32_t cols, double factor, double sigma, float* out);
+
 /* ITK LinearInterpolateImageFunction::EvaluateOptimized(Dispatch<3>) restated. */
 double xo_interp_linear(const float* vol, const uint64_t dims[3], const float x[3]);
 /* ITK NearestNeighborInterpolateImageFunction::EvaluateAtContinuousIndex restated. */

@@ -235,6 +235,17 @@ def itk_discrete_gaussian_2d(img, variance):
     return out
 
 
+def downsample_image(img, factor, sigma=-1.0):
+    """DownsampleImage (lib/itk/xregITKResampleUtils.h:49-112, B-spline default): ITK's Gaussian + cubic B-spline resampling
+    restated; PARITY UNPINNED."""
+    img = _f32(img)
+    orows, ocols = C.c_uint32(0), C.c_uint32(0)
+    lib().xo_downsample_size(C.c_uint32(img.shape[0]), C.c_uint32(img.shape[1]), C.c_double(factor), C.byref(orows), C.byref(ocols))
+    out = np.empty((orows.value, ocols.value), np.float32)
+    lib().xo_downsample_image(_fp(img), C.c_uint32(img.shape[0]), C.c_uint32(img.shape[1]), C.c_double(factor), C.c_double(sigma), _fp(out))
+    return out
+
+
 def log_remap(img, normalize_zero_one=False, use_max_intensity_as_I0=True, I0=1.0, smoothed=None):
     """ImageIntensLogTransFilter (lib/image/xregImageIntensLogTrans.cpp:55-144).  Returns (out, I0 used)."""
     img = _f32(img)

@@ -42,3 +42,32 @@ def test_log_remap_all_dark_and_errors(ctx, xo):
     assert np.array_equal(got, want) and np.all(np.isinf(got))     # min_pos stays 0 (:112): -log(0)
     with pytest.raises(xreg_b200.XregError):
         xreg_b200.log_remap(ctx, np.zeros((0, 4), f32))
+
+
+@pytest.mark.parametrize("shape,factor", [((37, 53), 0.5), ((64, 64), 0.25), ((192, 160), 0.125), ((33, 29), 0.7),
+                                          ((1, 40), 0.5), ((12, 9), 0.5), ((480, 480), 0.5)])
+def test_downsample_image_is_the_oracle_bit_for_bit(ctx, xo, shape, factor):
+    """xrc_downsample_image == xo_downsample_image (ITK's DownsampleImage chain restated: discrete Gaussian, cubic B-spline
+    prefilter and evaluation): the same double arithmetic in the same order, uncontracted -> identical bytes; with the
+    default smoothing, without, and with a given sigma; short lines take the prefilter's full-sum initialisation."""
+    rng = np.random.default_rng(shape[0] * 131 + shape[1])
+    img = rng.uniform(0.0, 3000.0, shape).astype(f32)
+    for sigma in (-1.0, 0.0, 1.3):
+        want = xo.downsample_image(img, factor, sigma)
+        got = xreg_b200.downsample_image(ctx, img, factor, sigma)
+        assert got.shape == want.shape and got.tobytes() == want.tobytes(), (sigma, float(np.abs(got - want).max()))
+
+
+def test_downsample_proj_data(ctx, xo):
+    """DownsampleProjData (lib/image/xregProjData.cpp:40-99): camera through DownsampleCameraModel, image through
+    DownsampleImage, even dimensions forced by cropping from index (0, 0)."""
+    from xreg_b200.geometry import CameraModel
+
+    cam = CameraModel().setup(1020.0, 150, 190, 0.5, 0.5)
+    img = np.random.default_rng(2).uniform(0, 100, (150, 190)).astype(f32)
+    dimg, dcam = xreg_b200.downsample_proj_data(ctx, img, cam, 0.25, force_even_dims=True)
+    assert dimg.shape == (dcam.num_det_rows, dcam.num_det_cols) == (38, 48)
+    full = xo.downsample_image(img, 0.25)
+    assert full.shape == (38, 48) and dimg.tobytes() == full[:38, :48].tobytes()
+    dimg2, dcam2 = xreg_b200.downsample_proj_data(ctx, img[:, :150], CameraModel().setup(1020.0, 150, 150, 0.5, 0.5), 0.5 * 0.7)
+    assert dimg2.shape == (dcam2.num_det_rows, dcam2.num_det_cols)

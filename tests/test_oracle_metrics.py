@@ -186,3 +186,40 @@ def test_patch_grad_ncc_composition_and_combine(xo):
     np.testing.assert_array_equal(s, (0.5 * (sx.astype(np.float64) + sy)).astype(f32))
     assert s[1] < s[0]
     np.testing.assert_allclose(xo.combine_mean(np.stack([sx, sy])), 0.5 * (sx + sy), rtol=1e-6)
+
+
+# ---- pre-processing restated from ITK (parity unpinned: pinned here by independent implementations of the same algorithms) ----
+def test_itk_discrete_gaussian_coefficients_are_the_discrete_gaussian(xo):
+    """itk::GaussianOperator: e^-t I_n(t), normalised, summed until 1 - 0.01 -- against SciPy's exact Bessel functions."""
+    import ctypes as C
+
+    from scipy.special import ive
+
+    lib = xo.lib()
+    lib.xo_itk_gaussian_coeffs.restype = C.c_int
+    for var, radius in ((2.0, 4), (1.0, 3), (4.0, 5), (16.0, 10), (0.25, 2)):
+        k = (C.c_double * 160)()
+        r = lib.xo_itk_gaussian_coeffs(C.c_double(var), C.c_double(0.01), 32, k)
+        kk = np.array(k[: 2 * r + 1])
+        ref = ive(np.arange(-r, r + 1), var)
+        assert r == radius and abs(kk.sum() - 1.0) < 1e-14 and np.abs(kk - ref / ref.sum()).max() < 5e-9
+        assert 2.0 * ive(np.arange(1, r), var).sum() + ive(0, var) < 0.99 <= 2.0 * ive(np.arange(1, r + 1), var).sum() + ive(0, var)
+
+
+def test_downsample_image_matches_an_independent_bspline_implementation(xo):
+    """DownsampleImage's resampling (cubic B-spline prefilter with mirror boundaries + 16-tap evaluation at i / factor)
+    against SciPy's spline_filter / map_coordinates (mode 'mirror': the same published algorithm, another code base)."""
+    from scipy import ndimage
+
+    rng = np.random.default_rng(3)
+    for shape, f in (((37, 53), 0.5), ((64, 64), 0.25), ((96, 80), 0.125), ((33, 29), 0.7), ((7, 5), 0.6)):
+        img = rng.uniform(0, 100, shape).astype(f32)
+        for sigma in (0.0, -1.0):
+            got = xo.downsample_image(img, f, sigma)
+            src = img if sigma == 0.0 else xo.itk_discrete_gaussian_2d(img, (0.5 / f) ** 2)
+            c = ndimage.spline_filter(src.astype(np.float64), order=3, mode="mirror")
+            yy, xx = np.meshgrid(np.arange(got.shape[0]) / f, np.arange(got.shape[1]) / f, indexing="ij")
+            ref = ndimage.map_coordinates(c, [yy, xx], order=3, mode="mirror", prefilter=False)
+            inside = (yy < shape[0] - 0.5) & (xx < shape[1] - 0.5)
+            assert got.shape == (int(shape[0] * f + 0.5), int(shape[1] * f + 0.5))
+            assert np.abs(got - ref)[inside].max() <= 1e-5 and np.all(got[~inside] == 0)

@@ -5,7 +5,7 @@ from . import _lib
 from ._lib import UnsupportedOperationException, XregCudaError, XregError, launch_count
 from .geometry import (CameraModel, Volume, downsample_camera_model, exp_se3, se3_inv, to12,
                        kORIGIN_AT_FOCAL_PT_DET_NEG_Z, kORIGIN_AT_FOCAL_PT_DET_POS_Z, kORIGIN_ON_DETECTOR)
-from .preproc import log_remap
+from .preproc import downsample_image, downsample_proj_data, log_remap
 from .ray_caster import Context, RayCasterDepthCUDA, RayCasterLineIntCUDA, kRAY_CAST_MAX_DEPTH
 from .sim_metrics import (ImgSimMetric2D, ImgSimMetric2DCombineMean, ImgSimMetric2DGradNCCCUDA,
                           ImgSimMetric2DNCCCUDA, ImgSimMetric2DPatchGradNCCCUDA, ImgSimMetric2DPatchNCCCUDA,

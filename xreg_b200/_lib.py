@@ -136,6 +136,8 @@ SIGNATURES = {
     "xrc_obj_fn_units_enqueue": [_VP, _U32, C.POINTER(_VP), _U32, _U32, _FP, _U32, _U32],
     "xrc_rc_compute_depth": [_VP, _U32, C.c_float, _U32],
     "xrc_log_remap": [_VP, _FP, _U32, _U32, C.c_int, C.c_int, C.c_float, _FP, _FP],
+    "xrc_downsample_size": [_U32, _U32, C.c_double, _U32P, _U32P],
+    "xrc_downsample_image": [_VP, _FP, _U32, _U32, C.c_double, C.c_double, _FP],
     "xrc_rc_peer_export": [_VP, C.POINTER(C.c_uint8)],
     "xrc_rc_peer_attach": [_VP, _U32, _U32, C.POINTER(C.c_uint8)],
     "xrc_rc_peer_detach": [_VP],

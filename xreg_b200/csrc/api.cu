@@ -1598,6 +1598,86 @@ int xrc_log_remap(xrc_ctx* ctx, const float* host_img, uint32_t rows, uint32_t c
   return status;
 }
 
+// DownsampleImage (lib/itk/xregITKResampleUtils.h:49-112, the cubic B-spline default of :181-188) on the device
+int xrc_downsample_size(uint32_t rows, uint32_t cols, double factor, uint32_t* out_rows, uint32_t* out_cols)
+{
+  XRC_CHECK_ARG(out_rows && out_cols && factor > 0.0, "xrc_downsample_size: bad argument");
+  *out_cols = (uint32_t)(unsigned long)((double)cols * factor + 0.5);   // :101-105
+  *out_rows = (uint32_t)(unsigned long)((double)rows * factor + 0.5);
+  return XRC_OK;
+}
+
+int xrc_downsample_image(xrc_ctx* ctx, const float* host_img, uint32_t rows, uint32_t cols, double factor, double sigma,
+                         float* host_out)
+{
+  XRC_CHECK_ARG(ctx && host_img && host_out && rows > 0 && cols > 0 && factor > 0.0, "xrc_downsample_image: bad argument");
+  uint32_t orows = 0, ocols = 0;
+  XRC_TRY(xrc_downsample_size(rows, cols, factor, &orows, &ocols));
+  XRC_CHECK_ARG(orows > 0 && ocols > 0, "xrc_downsample_image: the factor leaves no pixel");
+  XRC_TRY(use_device(ctx));
+  const size_t n = (size_t)rows * cols, n_out = (size_t)orows * ocols;
+  cudaStream_t st = ctx->stream;
+  float *d_img = nullptr, *d_a = nullptr, *d_b = nullptr, *d_out = nullptr;
+  double* d_c = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(d_img);
+    cudaFree(d_a);
+    cudaFree(d_b);
+    cudaFree(d_out);
+    cudaFree(d_c);
+  };
+  if (cudaMalloc(&d_img, n * sizeof(float)) != cudaSuccess || cudaMalloc(&d_a, n * sizeof(float)) != cudaSuccess ||
+      cudaMalloc(&d_b, n * sizeof(float)) != cudaSuccess || cudaMalloc(&d_out, n_out * sizeof(float)) != cudaSuccess ||
+      cudaMalloc(&d_c, n * sizeof(double)) != cudaSuccess)
+  {
+    cleanup();
+    cudaGetLastError();
+    XRC_FAIL(XRC_ERR_NOMEM, "xrc_downsample_image: out of device memory");
+  }
+  int status = XRC_OK;
+  if (cudaMemcpyAsync(d_img, host_img, n * sizeof(float), cudaMemcpyHostToDevice, st) != cudaSuccess)
+    status = XRC_ERR_CUDA;
+  const float* d_src = d_img;
+  if (status == XRC_OK && (factor < 1.0) && (fabs(sigma) > 1.0e-6))   // smooth before down-sampling (:68-86)
+  {
+    const double sg = (sigma < 0.0) ? (0.5 / factor) : sigma;
+    ItkGaussArgs g;
+    memset(&g, 0, sizeof(g));
+    g.rows = rows;
+    g.cols = cols;
+    g.radius = itk_gaussian_coeffs(sg * sg, 0.01, 32, g.k);
+    g.src = d_img;
+    g.dst = d_a;
+    g.along_x = 0;
+    status = launch_itk_gauss(g, st);
+    g.src = d_a;
+    g.dst = d_b;
+    g.along_x = 1;
+    if (status == XRC_OK)
+      status = launch_itk_gauss(g, st);
+    d_src = d_b;
+  }
+  // itk::BSplineDecompositionImageFilter (order 3), dimension 0 first, then the 16-tap evaluation per output pixel
+  const double z = sqrt(3.0) - 2.0;
+  const int64_t horizon = (int64_t)ceil(log(1.0e-10) / log(fabs(z)));
+  if (status == XRC_OK)
+    status = launch_f32_to_f64(d_src, d_c, n, st);
+  if (status == XRC_OK)
+    status = launch_bspline_prefilter(d_c, rows, cols, 1, pow(z, (double)((int64_t)cols - 1)), horizon, st);
+  if (status == XRC_OK)
+    status = launch_bspline_prefilter(d_c, rows, cols, 0, pow(z, (double)((int64_t)rows - 1)), horizon, st);
+  if (status == XRC_OK)
+    status = launch_bspline_resample(d_c, rows, cols, d_out, orows, ocols, factor, st);
+  if (status == XRC_OK && (cudaMemcpyAsync(host_out, d_out, n_out * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                           cudaStreamSynchronize(st) != cudaSuccess))
+  {
+    set_error("xrc_downsample_image: device failure");
+    status = XRC_ERR_CUDA;
+  }
+  cleanup();
+  return status;
+}
+
 // ---------------------------------------------------------------- metrics
 static bool sm_is_patch_kind(int kind) { return kind == XRC_SM_PATCH_NCC || kind == XRC_SM_PATCH_GRAD_NCC; }
 

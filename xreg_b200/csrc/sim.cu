@@ -1731,6 +1731,153 @@ int launch_log_map(const float* src, float* dst, uint64_t n, float scale, int lo
   return XRC_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Down-sampling of a projection: itk::BSplineDecompositionImageFilter + cubic BSplineInterpolateImageFunction restated
+// (DESIGN.md section 4.8).  One thread per image line for the recursive prefilter (sequential by nature, a few hundred
+// lines of a few hundred pixels, once per registration level), one thread per output pixel for the 16-tap evaluation;
+// double arithmetic, uncontracted, in the oracle's operation order.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void f32_to_f64_kernel(const float* __restrict__ src, double* __restrict__ dst, uint64_t n)
+{
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    dst[i] = (double)src[i];
+}
+
+int launch_f32_to_f64(const float* src, double* dst, uint64_t n, cudaStream_t st)
+{
+  if (!n)
+    return XRC_OK;
+  f32_to_f64_kernel<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(src, dst, n);
+  count_launch();
+  XRC_CUDA(cudaGetLastError());
+  return XRC_OK;
+}
+
+__global__ void __launch_bounds__(64) bspline_prefilter_kernel(double* __restrict__ c, uint32_t rows, uint32_t cols, int along_x,
+                                                               double zpow, long long horizon)
+{
+  const uint32_t line = blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n = along_x ? cols : rows;
+  const uint32_t n_lines = along_x ? rows : cols;
+  if (line >= n_lines || n == 1)
+    return;
+  const size_t stride = along_x ? 1 : cols;
+  double* p = c + (along_x ? (size_t)line * cols : (size_t)line);
+#define C_(i) p[(size_t)(i) * stride]
+  const double z = __dsub_rn(sqrt(3.0), 2.0);
+  const double c0 = __dmul_rn(__dsub_rn(1.0, z), __dsub_rn(1.0, __ddiv_rn(1.0, z)));
+  for (long long i = 0; i < n; ++i)
+    C_(i) = __dmul_rn(C_(i), c0);
+  {
+    double zn = z, sum;
+    if (horizon < n)
+    {
+      sum = C_(0);
+      for (long long i = 1; i < horizon; ++i)
+      {
+        sum = __dadd_rn(sum, __dmul_rn(zn, C_(i)));
+        zn = __dmul_rn(zn, z);
+      }
+      C_(0) = sum;
+    }
+    else
+    {
+      const double iz = __ddiv_rn(1.0, z);
+      double z2n = zpow;
+      sum = __dadd_rn(C_(0), __dmul_rn(z2n, C_(n - 1)));
+      z2n = __dmul_rn(z2n, __dmul_rn(z2n, iz));
+      for (long long i = 1; i <= n - 2; ++i)
+      {
+        sum = __dadd_rn(sum, __dmul_rn(__dadd_rn(zn, z2n), C_(i)));
+        zn = __dmul_rn(zn, z);
+        z2n = __dmul_rn(z2n, iz);
+      }
+      C_(0) = __ddiv_rn(sum, __dsub_rn(1.0, __dmul_rn(zn, zn)));
+    }
+  }
+  for (long long i = 1; i < n; ++i)
+    C_(i) = __dadd_rn(C_(i), __dmul_rn(z, C_(i - 1)));
+  C_(n - 1) = __dmul_rn(__ddiv_rn(z, __dsub_rn(__dmul_rn(z, z), 1.0)), __dadd_rn(__dmul_rn(z, C_(n - 2)), C_(n - 1)));
+  for (long long i = n - 2; i >= 0; --i)
+    C_(i) = __dmul_rn(z, __dsub_rn(C_(i + 1), C_(i)));
+#undef C_
+}
+
+int launch_bspline_prefilter(double* c, uint32_t rows, uint32_t cols, int along_x, double zpow, int64_t horizon, cudaStream_t st)
+{
+  const uint32_t n_lines = along_x ? rows : cols;
+  if (!n_lines)
+    return XRC_OK;
+  bspline_prefilter_kernel<<<(n_lines + 63) / 64, 64, 0, st>>>(c, rows, cols, along_x, zpow, (long long)horizon);
+  count_launch();
+  XRC_CUDA(cudaGetLastError());
+  return XRC_OK;
+}
+
+__device__ __forceinline__ long long mirror_index(long long i, long long n)
+{
+  if (n == 1)
+    return 0;
+  if (i < 0)
+    i = -i;
+  if (i >= n)
+    i = (n - 1) - (i - (n - 1));
+  return i;
+}
+
+__global__ void __launch_bounds__(256) bspline_resample_kernel(const double* __restrict__ c, uint32_t rows, uint32_t cols,
+                                                               float* __restrict__ out, uint32_t orows, uint32_t ocols, double factor)
+{
+  const size_t n_out = (size_t)orows * ocols;
+  for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < n_out; o += (size_t)gridDim.x * blockDim.x)
+  {
+    const long long oy = (long long)(o / ocols), ox = (long long)(o % ocols);
+    const double xs[2] = {__ddiv_rn((double)ox, factor), __ddiv_rn((double)oy, factor)};
+    const long long len[2] = {(long long)cols, (long long)rows};
+    float v = 0.0f;
+    if (xs[0] >= -0.5 && xs[0] < (double)cols - 0.5 && xs[1] >= -0.5 && xs[1] < (double)rows - 0.5)
+    {
+      double w[2][4];
+      long long idx[2][4];
+#pragma unroll
+      for (int d = 0; d < 2; ++d)
+      {
+        const long long i0 = (long long)floorf((float)xs[d]) - 1;
+        const double t = __dsub_rn(xs[d], (double)(i0 + 1));
+        w[d][3] = __dmul_rn(__dmul_rn(__dmul_rn(1.0 / 6.0, t), t), t);
+        w[d][0] = __dsub_rn(__dadd_rn(1.0 / 6.0, __dmul_rn(__dmul_rn(0.5, t), __dsub_rn(t, 1.0))), w[d][3]);
+        w[d][2] = __dsub_rn(__dadd_rn(t, w[d][0]), __dmul_rn(2.0, w[d][3]));
+        w[d][1] = __dsub_rn(__dsub_rn(__dsub_rn(1.0, w[d][0]), w[d][2]), w[d][3]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          idx[d][k] = mirror_index(i0 + k, len[d]);
+      }
+      double acc = 0.0;
+#pragma unroll
+      for (int pp = 0; pp < 16; ++pp)
+      {
+        const int kx = pp & 3, ky = pp >> 2;
+        acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(w[0][kx], w[1][ky]), c[(size_t)idx[1][ky] * cols + (size_t)idx[0][kx]]));
+      }
+      v = (float)acc;
+    }
+    out[o] = v;
+  }
+}
+
+int launch_bspline_resample(const double* c, uint32_t rows, uint32_t cols, float* out, uint32_t orows, uint32_t ocols,
+                            double factor, cudaStream_t st)
+{
+  const size_t n_out = (size_t)orows * ocols;
+  if (!n_out)
+    return XRC_OK;
+  bspline_resample_kernel<<<(unsigned)std::min<size_t>((n_out + 255) / 256, 148 * 8), 256, 0, st>>>(c, rows, cols, out, orows,
+                                                                                                      ocols, factor);
+  count_launch();
+  XRC_CUDA(cudaGetLastError());
+  return XRC_OK;
+}
+
 int launch_patch_finalize(const PatchFinalizeArgs& a, cudaStream_t st)
 {
   if (!a.n_imgs)

@@ -138,6 +138,15 @@ int launch_minmax(const float* src, uint64_t n, float scale, float eps, float* o
 int launch_log_map(const float* src, float* dst, uint64_t n, float scale, int log_mode, float eps, float I0, float out_max,
                    cudaStream_t st);
 
+// ---- down-sampling of a projection (DownsampleImage, lib/itk/xregITKResampleUtils.h:49-112)
+// cubic B-spline prefilter (itk::BSplineDecompositionImageFilter) of a rows x cols double image, in place, along x or y;
+// zpow = z^(n - 1) for the line length n (only short lines use it; computed on the host like the oracle's pow)
+int launch_bspline_prefilter(double* c, uint32_t rows, uint32_t cols, int along_x, double zpow, int64_t horizon, cudaStream_t st);
+int launch_f32_to_f64(const float* src, double* dst, uint64_t n, cudaStream_t st);
+// out[oy][ox] = cubic B-spline value at the continuous input index (ox / factor, oy / factor), 0 outside the buffer
+int launch_bspline_resample(const double* c, uint32_t rows, uint32_t cols, float* out, uint32_t orows, uint32_t ocols,
+                            double factor, cudaStream_t st);
+
 // Gaussian widths served by the warp-streaming gradient kernel (the reference's apps use 5; 0 = no smoothing)
 inline bool grad_fast_path(int gauss_width) { return gauss_width <= 1 || gauss_width == 3 || gauss_width == 5 || gauss_width == 7; }
 // rows per warp of the fast kernel: long bands amortise the halo rows, short bands give a small batch
