@@ -1414,6 +1414,34 @@ private:
   std::vector<float> tmp_, out_, per_view_;
 };
 
+// ---- projection pre-processing ------------------------------------------------------------------
+/// xreg::ImageIntensLogTransFilter (lib/image/xregImageIntensLogTrans.{h,cpp}) as one call: SetNormalizeZeroOne /
+/// SetUseMaxIntensityAsI0 / SetI0 are the arguments, Update() is the call.  In place when dst == src.  Returns the I0 used.
+inline float LogRemap(Context& ctx, const Image2D<const float>& src, float* dst, const bool normalize_zero_one = false,
+                      const bool use_max_intensity_as_I0 = true, const float I0 = 1.0f)
+{
+  detail::Assert(bool(src) && dst, "LogRemap: null image");
+  float used = 0.0f;
+  detail::Check(xrc_log_remap(ctx.handle(), src.data, static_cast<uint32_t>(src.rows), static_cast<uint32_t>(src.cols),
+                              normalize_zero_one ? 1 : 0, use_max_intensity_as_I0 ? 1 : 0, I0, dst, &used));
+  return used;
+}
+
+/// xreg::DownsampleImage (lib/itk/xregITKResampleUtils.h:49-112, cubic B-spline default): the image comes back in `dst`
+/// (resized), its size in rows / cols.  sigma < 0: the default smoothing 0.5 / factor.
+inline void DownsampleImage(Context& ctx, const Image2D<const float>& src, const double factor, std::vector<float>* dst,
+                            size_type* rows, size_type* cols, const double sigma = -1.0)
+{
+  detail::Assert(bool(src) && dst && rows && cols, "DownsampleImage: null argument");
+  uint32_t r = 0, c = 0;
+  detail::Check(xrc_downsample_size(static_cast<uint32_t>(src.rows), static_cast<uint32_t>(src.cols), factor, &r, &c));
+  dst->assign(static_cast<size_t>(r) * c, 0.0f);
+  detail::Check(xrc_downsample_image(ctx.handle(), src.data, static_cast<uint32_t>(src.rows), static_cast<uint32_t>(src.cols),
+                                     factor, sigma, dst->data()));
+  *rows = r;
+  *cols = c;
+}
+
 }  // namespace xreg_b200
 
 #endif

@@ -789,6 +789,99 @@ static void TestMultiViewObjective(Context& ctx, const Scene& s)
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// the depth ray caster behind the same base class, and the projection pre-processing
+static void TestDepthAndPreProc(Context& ctx, const Scene& s)
+{
+  const size_type rows = s.cam.num_det_rows, cols = s.cam.num_det_cols, npix = rows * cols, n = 3;
+  const FrameTransformList poses = MakePoses(s, n, 11, 10.0, 6.0);
+  float vmax = 0.0f;
+  const size_t nvox = static_cast<size_t>(s.vol.size[0]) * s.vol.size[1] * s.vol.size[2];
+  for (size_t i = 0; i < nvox; ++i)
+  {
+    vmax = std::max(vmax, s.vol.data[i]);
+  }
+  std::vector<float> p12(12 * n);
+  std::vector<uint32_t> ci(n, 0u);
+  for (size_type i = 0; i < n; ++i)
+  {
+    poses[i].to3x4(&p12[12 * i]);
+  }
+  float i2p[12];
+  s.vol.idx_to_phys(i2p);
+  const xo_cam oc = ToOracleCam(s.cam);
+
+  RayCasterDepthCUDA depth(ctx);
+  RayCaster& rc = depth;   // through the base class, as the factories hand it out
+  rc.set_volume(s.vol);
+  rc.set_camera_model(s.cam);
+  rc.set_num_projs(n);
+  rc.allocate_resources();
+  rc.set_xforms_cam_to_itk_phys(poses);
+  CHECK(rc.default_bg_pixel_val() == kRAY_CAST_MAX_DEPTH);
+  size_t surfaces = 0;
+  for (int pass = 0; pass < 2; ++pass)
+  {
+    const float thr = (pass ? 0.7f : 0.4f) * vmax;
+    const size_type nb = pass ? 6 : 0;
+    depth.set_render_thresh(thr);
+    depth.set_num_backtracking_steps(nb);
+    rc.compute();
+    std::vector<float> want(n * npix, XO_RAY_CAST_MAX_DEPTH);
+    CHECK(xo_depth(s.vol.data, s.vol.size, i2p, &oc, 1, p12.data(), ci.data(), static_cast<uint32_t>(n), 1.0f, XO_INTERP_LINEAR,
+                   thr, static_cast<uint32_t>(nb), want.data(), 0) == 0);
+    CHECK(std::memcmp(want.data(), rc.raw_host_pixel_buf(), sizeof(float) * want.size()) == 0);
+    for (const float d : want)
+    {
+      surfaces += (d < 1.0e36f) ? 1 : 0;
+    }
+  }
+  CHECK(surfaces > 1000);
+  std::printf("  depth ray caster: bit-identical, %zu surface pixels\n", surfaces);
+
+  // log remap and down-sampling of a projection (a line-integral DRR turned into an intensity image)
+  RayCasterLineIntCUDA lin(ctx);
+  lin.set_volume(s.vol);
+  lin.set_camera_model(s.cam);
+  lin.set_num_projs(1);
+  lin.allocate_resources();
+  lin.set_xforms_cam_to_itk_phys(FrameTransformList(1, poses[0]));
+  lin.compute();
+  std::vector<float> img(lin.raw_host_pixel_buf(), lin.raw_host_pixel_buf() + npix);
+  for (float& v : img)
+  {
+    v = 4000.0f * std::exp(-v);
+  }
+  img[5] = 0.0f;
+  {
+    std::vector<float> got(npix), want(npix);
+    const float i0 = LogRemap(ctx, Image2D<const float>(img.data(), rows, cols), got.data());
+    float want_i0 = 0.0f;
+    xo_log_remap(img.data(), static_cast<uint32_t>(rows), static_cast<uint32_t>(cols), 0, 1, 1.0f, nullptr, want.data(), &want_i0);
+    CHECK(i0 == want_i0);
+    double worst = 0.0;
+    for (size_type i = 0; i < npix; ++i)
+    {
+      worst = std::max(worst, static_cast<double>(std::fabs(got[i] - want[i])) / std::max(1.0e-30, static_cast<double>(std::fabs(want[i]))));
+    }
+    CHECK(worst <= 2.5e-7);   // 1 ulp: correctly rounded logarithm vs glibc's logf
+    std::printf("  log remap: I0 %.6g bit-equal, max rel diff %.2e\n", static_cast<double>(i0), worst);
+  }
+  for (const double f : {0.5, 0.25})
+  {
+    std::vector<float> got;
+    size_type r = 0, c = 0;
+    DownsampleImage(ctx, Image2D<const float>(img.data(), rows, cols), f, &got, &r, &c);
+    uint32_t wr = 0, wc = 0;
+    xo_downsample_size(static_cast<uint32_t>(rows), static_cast<uint32_t>(cols), f, &wr, &wc);
+    std::vector<float> want(static_cast<size_t>(wr) * wc);
+    xo_downsample_image(img.data(), static_cast<uint32_t>(rows), static_cast<uint32_t>(cols), f, -1.0, want.data());
+    CHECK(r == wr && c == wc && got.size() == want.size());
+    CHECK(std::memcmp(got.data(), want.data(), sizeof(float) * want.size()) == 0);
+  }
+  std::printf("  down-sampling: bit-identical to the oracle\n");
+}
+
 int main(int argc, char** argv)
 {
   const bool no_gpu = (argc > 1 && std::strcmp(argv[1], "--no-gpu") == 0);
@@ -817,6 +910,7 @@ int main(int argc, char** argv)
     TestRayCaster(ctx, s);
     TestMetrics(ctx, s);
     TestMultiViewObjective(ctx, s);
+    TestDepthAndPreProc(ctx, s);
   }
   catch (const std::exception& e)
   {
