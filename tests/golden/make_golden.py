@@ -46,5 +46,30 @@ def main():
     print("wrote", path, os.path.getsize(path), "bytes; S =", S)
 
 
+def main_round2():
+    """tests/golden/round2.npz: the round-2 additions on the same scene (nearest-neighbour DRR, depth images, log remap and
+    down-sampling of the fixed image), by the oracle."""
+    vol, cam, poses = scene()
+    cams = [xo.cam_struct(cam)]
+    drr = xo.drr(vol.data, vol.idx_to_phys(), cams, to12(poses))
+    fixed = synth.add_noise(drr[0], seed=77)
+    intens = (4000.0 * np.exp(-fixed)).astype(np.float32)     # an intensity image, as a detector would deliver it
+    intens[3, 7] = 0.0
+    vmax = float(vol.data.max())
+    log_img, log_i0 = xo.log_remap(intens)
+    out = dict(
+        drr_nn=xo.drr(vol.data, vol.idx_to_phys(), cams, to12(poses), interp=1),
+        depth=xo.depth(vol.data, vol.idx_to_phys(), cams, to12(poses), thresh=0.5 * vmax, n_backtrack=4),
+        depth_nn=xo.depth(vol.data, vol.idx_to_phys(), cams, to12(poses), interp=1, thresh=0.3 * vmax, n_backtrack=0),
+        depth_thresh=np.float32(0.5 * vmax), depth_nn_thresh=np.float32(0.3 * vmax),
+        intens=intens, log_remap=log_img, log_i0=log_i0,
+        down_half=xo.downsample_image(intens, 0.5), down_quarter_nosmooth=xo.downsample_image(intens, 0.25, 0.0),
+    )
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "round2.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
     main()
+    main_round2()
